@@ -1,0 +1,642 @@
+// ============================================================================
+// oracle/oracle.cpp  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Dependency-free CPU restatement of the reference's wavefront hot path
+// (naturerobots/mesh_navigation @ b9f2851).  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs may load this file's
+// shared object.  The product library (mesh_navigation_b200/csrc) never links,
+// loads or calls it.
+//
+// Every function cites the reference file:line it follows.  The reference's TUs
+// include <lvr2/...> and <rclcpp/...> (neither is on this machine)
+// so the reference cannot be compiled here; this file restates the arithmetic
+// with flat arrays standing in for the lvr2 attribute maps and an indexed binary
+// min-heap standing in for lvr2::Meap (un-vendored dependency lvr2 @ "main",
+// source_dependencies.yaml:4-7).
+//
+// PARITY PINNING
+//   pinned by the reference's own tests (mesh_layers/test/inflation_layer_test.cpp):
+//     * InflationLayer::waveFrontUpdate on the single triangle -> true, d[v2]==0.5f
+//     * InflationLayer::fading table (0.2->0.9, 0.5->0.9, 0<f(0.6)<0.9, 2.0->0)
+//   everything else (Dijkstra, CVP, waveCostInflation as a whole, edge weights,
+//   the geometric layers, lvr2::Meap tie order, lvr2 circulator order):
+//   PARITY UNPINNED -- the reference holds no test or golden vector for them;
+//   parity is defined against this restatement (DESIGN.md says the same).
+//
+// Canonical orders replacing lvr2 circulators (results depend on them only for
+// exact float ties and the inflation vector-field accumulation):
+//   faces of a vertex  : ascending face id
+//   edges of a vertex  : ascending edge id
+// Build: g++ -O3 -ffp-contract=off  (the reference builds for generic x86-64, no
+// FMA contraction; keep expression evaluation identical).
+// ============================================================================
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+namespace {
+
+constexpr float FINF = std::numeric_limits<float>::infinity();
+
+// ---------------------------------------------------------------------------
+// lvr2::Meap<VertexHandle,float> restated (lvr2/util/Meap.hpp, un-vendored).
+// Array binary min-heap + key->slot index.  insert() on a present key updates
+// the value and re-sifts (relied on at cvp_mesh_planner.cpp:814,
+// dijkstra_mesh_planner.cpp:335, inflation_layer.cpp:452).  Strict '<' sifts.
+// ---------------------------------------------------------------------------
+struct Meap {
+  struct Item { uint32_t key; float value; };
+  std::vector<Item> heap;
+  std::vector<int32_t> slot;  // -1 = absent
+  explicit Meap(uint32_t n) : slot(n, -1) {}
+  bool isEmpty() const { return heap.empty(); }
+  void swapSlots(size_t a, size_t b) {
+    std::swap(heap[a], heap[b]);
+    slot[heap[a].key] = (int32_t)a;
+    slot[heap[b].key] = (int32_t)b;
+  }
+  void bubbleUp(size_t idx) {
+    while (idx != 0) {
+      size_t father = (idx - 1) / 2;
+      if (heap[idx].value < heap[father].value) { swapSlots(idx, father); idx = father; }
+      else break;
+    }
+  }
+  void bubbleDown(size_t idx) {
+    const size_t n = heap.size();
+    for (;;) {
+      size_t l = 2 * idx + 1, r = 2 * idx + 2, s = idx;
+      if (l < n && heap[l].value < heap[s].value) s = l;
+      if (r < n && heap[r].value < heap[s].value) s = r;
+      if (s == idx) break;
+      swapSlots(idx, s);
+      idx = s;
+    }
+  }
+  void insert(uint32_t key, float value) {
+    int32_t s = slot[key];
+    if (s >= 0) {
+      float old = heap[s].value;
+      heap[s].value = value;
+      if (value > old) bubbleDown((size_t)s); else bubbleUp((size_t)s);
+      return;
+    }
+    heap.push_back({key, value});
+    slot[key] = (int32_t)(heap.size() - 1);
+    bubbleUp(heap.size() - 1);
+  }
+  Item popMin() {
+    Item top = heap[0];
+    swapSlots(0, heap.size() - 1);
+    heap.pop_back();
+    slot[top.key] = -1;
+    if (!heap.empty()) bubbleDown(0);
+    return top;
+  }
+};
+
+struct OrcMesh {
+  uint32_t V = 0, F = 0, E = 0;
+  std::vector<float> pos;           // 3V
+  std::vector<uint32_t> faces;      // 3F, cyclic order as given
+  std::vector<uint32_t> edges;      // 2E, (lo, hi)
+  std::vector<uint32_t> face_edges; // 3F: edge(v0,v1), edge(v1,v2), edge(v2,v0)
+  std::vector<uint32_t> ve_ptr, ve_edge, ve_nbr;  // vertex -> incident edges
+  std::vector<uint32_t> vf_ptr, vf_face;          // vertex -> incident faces
+  std::vector<int32_t> edge_faces;                // 2E, -1 = none
+};
+
+inline uint64_t ekey(uint32_t a, uint32_t b) {
+  uint32_t lo = a < b ? a : b, hi = a < b ? b : a;
+  return ((uint64_t)lo << 32) | hi;
+}
+
+void buildTopology(OrcMesh& m, const uint32_t* edges_in, uint32_t E_in) {
+  const uint32_t V = m.V, F = m.F;
+  // edges
+  std::vector<uint64_t> keys;
+  if (edges_in) {
+    keys.resize(E_in);
+    for (uint32_t e = 0; e < E_in; ++e) keys[e] = ekey(edges_in[2 * e], edges_in[2 * e + 1]);
+    m.E = E_in;
+    m.edges.assign(edges_in, edges_in + 2 * (size_t)E_in);
+  } else {
+    keys.reserve(3 * (size_t)F);
+    for (uint32_t f = 0; f < F; ++f) {
+      const uint32_t* v = &m.faces[3 * (size_t)f];
+      keys.push_back(ekey(v[0], v[1]));
+      keys.push_back(ekey(v[1], v[2]));
+      keys.push_back(ekey(v[2], v[0]));
+    }
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    m.E = (uint32_t)keys.size();
+    m.edges.resize(2 * (size_t)m.E);
+    for (uint32_t e = 0; e < m.E; ++e) {
+      m.edges[2 * (size_t)e] = (uint32_t)(keys[e] >> 32);
+      m.edges[2 * (size_t)e + 1] = (uint32_t)(keys[e] & 0xffffffffu);
+    }
+  }
+  // key -> edge id lookup (sorted copy with ids when caller supplied the order)
+  std::vector<std::pair<uint64_t, uint32_t>> lut(m.E);
+  for (uint32_t e = 0; e < m.E; ++e) lut[e] = {ekey(m.edges[2 * (size_t)e], m.edges[2 * (size_t)e + 1]), e};
+  std::sort(lut.begin(), lut.end());
+  auto find_edge = [&](uint32_t a, uint32_t b) -> uint32_t {
+    uint64_t k = ekey(a, b);
+    auto it = std::lower_bound(lut.begin(), lut.end(), std::make_pair(k, (uint32_t)0));
+    return it->second;
+  };
+  m.face_edges.resize(3 * (size_t)F);
+  m.edge_faces.assign(2 * (size_t)m.E, -1);
+  for (uint32_t f = 0; f < F; ++f) {
+    const uint32_t* v = &m.faces[3 * (size_t)f];
+    for (int k = 0; k < 3; ++k) {
+      uint32_t e = find_edge(v[k], v[(k + 1) % 3]);
+      m.face_edges[3 * (size_t)f + k] = e;
+      if (m.edge_faces[2 * (size_t)e] < 0) m.edge_faces[2 * (size_t)e] = (int32_t)f;
+      else m.edge_faces[2 * (size_t)e + 1] = (int32_t)f;
+    }
+  }
+  // vertex -> edges (ascending edge id)
+  m.ve_ptr.assign((size_t)V + 1, 0);
+  for (uint32_t e = 0; e < m.E; ++e) { m.ve_ptr[m.edges[2 * (size_t)e] + 1]++; m.ve_ptr[m.edges[2 * (size_t)e + 1] + 1]++; }
+  for (uint32_t v = 0; v < V; ++v) m.ve_ptr[v + 1] += m.ve_ptr[v];
+  m.ve_edge.resize(m.ve_ptr[V]); m.ve_nbr.resize(m.ve_ptr[V]);
+  {
+    std::vector<uint32_t> cur(m.ve_ptr.begin(), m.ve_ptr.end() - 1);
+    for (uint32_t e = 0; e < m.E; ++e) {
+      uint32_t a = m.edges[2 * (size_t)e], b = m.edges[2 * (size_t)e + 1];
+      m.ve_edge[cur[a]] = e; m.ve_nbr[cur[a]++] = b;
+      m.ve_edge[cur[b]] = e; m.ve_nbr[cur[b]++] = a;
+    }
+  }
+  // vertex -> faces (ascending face id)
+  m.vf_ptr.assign((size_t)V + 1, 0);
+  for (size_t i = 0; i < 3 * (size_t)F; ++i) m.vf_ptr[m.faces[i] + 1]++;
+  for (uint32_t v = 0; v < V; ++v) m.vf_ptr[v + 1] += m.vf_ptr[v];
+  m.vf_face.resize(m.vf_ptr[V]);
+  {
+    std::vector<uint32_t> cur(m.vf_ptr.begin(), m.vf_ptr.end() - 1);
+    for (uint32_t f = 0; f < F; ++f)
+      for (int k = 0; k < 3; ++k) m.vf_face[cur[m.faces[3 * (size_t)f + k]]++] = f;
+  }
+}
+
+// edge id between two vertices of face f (lvr2 getEdgeBetween, cvp:380-388, inflation:255-257)
+inline uint32_t edgeBetweenInFace(const OrcMesh& m, uint32_t f, uint32_t a, uint32_t b) {
+  const uint32_t* v = &m.faces[3 * (size_t)f];
+  for (int k = 0; k < 3; ++k) {
+    uint32_t p = v[k], q = v[(k + 1) % 3];
+    if ((p == a && q == b) || (p == b && q == a)) return m.face_edges[3 * (size_t)f + k];
+  }
+  return 0xffffffffu;
+}
+
+// ---------------------------------------------------------------------------
+// CVPMeshPlanner::waveFrontUpdate (default variant)  cvp_mesh_planner.cpp:369-556
+// ---------------------------------------------------------------------------
+struct CvpState {
+  float* distances; uint32_t* predecessors; float* direction; int32_t* cutting_faces;
+};
+
+inline bool cvpWaveFrontUpdate(const OrcMesh& m, CvpState& s, const float* edge_weights,
+                               uint32_t face, uint32_t v1, uint32_t v2, uint32_t v3) {
+  const double u1 = s.distances[v1];                                   // :376
+  const double u2 = s.distances[v2];
+  const double u3 = s.distances[v3];
+  const double c = edge_weights[edgeBetweenInFace(m, face, v1, v2)];   // :380-382
+  const double c_sq = c * c;
+  const double b = edge_weights[edgeBetweenInFace(m, face, v1, v3)];   // :384-386
+  const double b_sq = b * b;
+  const double a = edge_weights[edgeBetweenInFace(m, face, v2, v3)];   // :388-390
+  const double a_sq = a * a;
+  const double u1_sq = u1 * u1;
+  const double u2_sq = u2 * u2;
+  const double sx = (c_sq + u1_sq - u2_sq) / (2 * c);                  // :395
+  const double sy = -sqrt(std::max(u1_sq - sx * sx, 0.0));             // :396
+  const double p = (b_sq + c_sq - a_sq) / (2 * c);                     // :398
+  const double hc = sqrt(std::max(b_sq - p * p, 0.0));                 // :399
+  const double dy = hc - sy;
+  const double dx = p - sx;
+  const double u3tmp_sq = dx * dx + dy * dy;
+  double u3tmp = sqrt(u3tmp_sq);                                       // :405
+  if (u3tmp < u3) {                                                    // :411
+    const double t0a = (a_sq + b_sq - c_sq) / (2 * a * b);             // :413
+    const double t1a = (u3tmp_sq + b_sq - u1_sq) / (2 * u3tmp * b);
+    const double t2a = (a_sq + u3tmp_sq - u2_sq) / (2 * a * u3tmp);
+    if (std::fabs(t1a) > 1) {                                          // :418
+      u3tmp = u1 + b;
+      if (u3tmp < u3) {
+        s.cutting_faces[v3] = (int32_t)face; s.predecessors[v3] = v1;
+        s.distances[v3] = static_cast<float>(u3tmp); s.direction[v3] = 0;
+        return true;
+      }
+      return false;
+    } else if (std::fabs(t2a) > 1) {                                   // :437
+      u3tmp = u2 + a;
+      if (u3tmp < u3) {
+        s.cutting_faces[v3] = (int32_t)face; s.predecessors[v3] = v2;
+        s.distances[v3] = static_cast<float>(u3tmp); s.direction[v3] = 0;
+        return true;
+      }
+      return false;
+    }
+    const double theta0 = acos(t0a);                                   // :456-458
+    const double theta1 = acos(t1a);
+    const double theta2 = acos(t2a);
+    if (theta1 < theta0 && theta2 < theta0) {                          // :493
+      s.cutting_faces[v3] = (int32_t)face;
+      s.distances[v3] = static_cast<float>(u3tmp);
+      if (theta1 < theta2) { s.predecessors[v3] = v1; s.direction[v3] = (float)theta1; }
+      else { s.predecessors[v3] = v2; s.direction[v3] = (float)(-theta2); }
+      return true;
+    } else if (theta1 < theta2) {                                      // :518
+      u3tmp = u1 + b;
+      if (u3tmp < u3) {
+        s.cutting_faces[v3] = (int32_t)face; s.predecessors[v3] = v1;
+        s.distances[v3] = static_cast<float>(u3tmp); s.direction[v3] = 0;
+        return true;
+      }
+      return false;
+    } else {                                                           // :536
+      u3tmp = u2 + a;
+      if (u3tmp < u3) {
+        s.cutting_faces[v3] = (int32_t)face; s.predecessors[v3] = v2;
+        s.distances[v3] = static_cast<float>(u3tmp); s.direction[v3] = 0;
+        return true;
+      }
+      return false;
+    }
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------
+// InflationLayer::computeUpdateSethianMethod  inflation_layer.cpp:181-234
+// (float throughout; literal conditions, including `sin` not `sin^2` at :195)
+// ---------------------------------------------------------------------------
+constexpr float INFLATION_EPSILON = 1e-9;  // `const float EPSILON = 1e-9;` mesh_layers/include/mesh_layers/inflation_layer.h:46
+
+inline float sethianUpdate(const float d1, const float d2, const float a, const float b,
+                           const float dot, const float F) {
+  float t = FINF;
+  float r_cos_angle = dot;
+  float r_sin_angle = std::sqrt(1 - dot * dot);
+  float u = d2 - d1;
+  float f2 = a * a + b * b - 2 * a * b * r_cos_angle;
+  float f1 = b * u * (a * r_cos_angle - b);
+  float f0 = b * b * (u * u - F * F * a * a * r_sin_angle);
+  float delta = f1 * f1 - f0 * f2;
+  if (delta >= 0) {
+    if (std::fabs(f2) > INFLATION_EPSILON) {
+      t = (-f1 - std::sqrt(delta)) / f2;
+      if (t < u || b * (t - u) / t < a * r_cos_angle || a / r_cos_angle < b * (t - u) / 2) {
+        t = (-f1 + std::sqrt(delta)) / f2;
+      } else {
+        if (f1 != 0) t = -f0 / f1; else t = -FINF;
+      }
+    }
+  } else {
+    t = -FINF;
+  }
+  if (u < t && a * r_cos_angle < b * (t - u) / t && b * (t - u) / t < a / r_cos_angle) return t + d1;
+  return std::min(b * F + d1, a * F + d2);
+}
+
+inline void vnormalize(float* v) {
+  float l = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  if (l > 0) { v[0] /= l; v[1] /= l; v[2] /= l; }
+}
+
+// InflationLayer::waveFrontUpdate  inflation_layer.cpp:236-313
+inline bool inflationWaveFrontUpdate(const OrcMesh& m, float* distances, float* vector_map /*3V or null*/,
+                                     const float max_distance, const float* edge_weights,
+                                     uint32_t face, uint32_t v1h, uint32_t v2h, uint32_t v3h) {
+  const float u1 = distances[v1h];
+  const float u2 = distances[v2h];
+  const float u3 = distances[v3h];
+  if (u3 == 0) return false;                                                        // :252
+  const float c = edge_weights[edgeBetweenInFace(m, face, v1h, v2h)];
+  const float c_sq = c * c;
+  const float b = edge_weights[edgeBetweenInFace(m, face, v1h, v3h)];
+  const float b_sq = b * b;
+  const float a = edge_weights[edgeBetweenInFace(m, face, v2h, v3h)];
+  const float a_sq = a * a;
+  float dot = (a_sq + b_sq - c_sq) / (2 * a * b);                                   // :268
+  float u3tmp = sethianUpdate(u1, u2, a, b, dot, 1.0f);
+  if (!std::isfinite(u3tmp)) return false;                                          // :271
+  const float d31 = u3tmp - u1;
+  const float d32 = u3tmp - u2;
+  if (vector_map && u1 == 0 && u2 == 0) {                                           // :277-295
+    const float* p1 = &m.pos[3 * (size_t)v1h]; const float* p2 = &m.pos[3 * (size_t)v2h];
+    const float* p3 = &m.pos[3 * (size_t)v3h];
+    float dir[3];
+    for (int k = 0; k < 3; ++k) dir[k] = (p3[k] - p2[k]) + (p3[k] - p1[k]);
+    vnormalize(dir);
+    for (uint32_t vh : {v1h, v2h, v3h}) {
+      float* vm = &vector_map[3 * (size_t)vh];
+      for (int k = 0; k < 3; ++k) vm[k] = vm[k] + dir[k];
+      vnormalize(vm);
+    }
+  }
+  if (u3tmp < u3) {                                                                 // :297
+    distances[v3h] = u3tmp;
+    if (vector_map && (u1 != 0 || u2 != 0)) {
+      const float* va = &vector_map[3 * (size_t)v1h]; const float* vb = &vector_map[3 * (size_t)v2h];
+      float out[3];
+      for (int k = 0; k < 3; ++k) out[k] = va[k] * d31 + vb[k] * d32;
+      vnormalize(out);
+      for (int k = 0; k < 3; ++k) vector_map[3 * (size_t)v3h + k] = out[k];
+    }
+    return u1 <= max_distance && u2 <= max_distance;                                // :310
+  }
+  return false;
+}
+
+struct InflationConfig {   // mesh_layers/include/mesh_layers/inflation_layer.h:240-248 (doubles)
+  double inscribed_radius, inflation_radius, lethal_value, inscribed_value, cost_scaling_factor;
+};
+
+// InflationLayer::fading  inflation_layer.cpp:315-339 (config members are double)
+inline float fading(const InflationConfig& cfg, const float distance) {
+  if (distance > cfg.inflation_radius) return 0;
+  if (distance > cfg.inscribed_radius) {
+    const float factor = exp(-1.0f * cfg.cost_scaling_factor * (distance - cfg.inscribed_radius));
+    const float cost = cfg.inscribed_value * factor;
+    return cost;
+  }
+  if (distance > 0) return cfg.inscribed_value;
+  return cfg.lethal_value;
+}
+
+inline double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+extern "C" {
+
+void* orc_mesh_create(uint32_t V, uint32_t F, const float* pos, const uint32_t* faces,
+                      const uint32_t* edges /*nullable*/, uint32_t E) {
+  OrcMesh* m = new OrcMesh();
+  m->V = V; m->F = F;
+  m->pos.assign(pos, pos + 3 * (size_t)V);
+  m->faces.assign(faces, faces + 3 * (size_t)F);
+  buildTopology(*m, edges, E);
+  return m;
+}
+void orc_mesh_destroy(void* h) { delete (OrcMesh*)h; }
+uint32_t orc_mesh_num_edges(void* h) { return ((OrcMesh*)h)->E; }
+void orc_mesh_get_edges(void* h, uint32_t* out) {
+  OrcMesh* m = (OrcMesh*)h; std::memcpy(out, m->edges.data(), sizeof(uint32_t) * 2 * (size_t)m->E);
+}
+
+// lvr2::calcVertexDistances as used for MeshMap::edge_distances (mesh_map.cpp:404-425):
+// Euclidean length of every edge, float arithmetic (BaseVector<float>::distanceFrom).
+void orc_edge_distances(void* h, float* out) {
+  OrcMesh* m = (OrcMesh*)h;
+  for (uint32_t e = 0; e < m->E; ++e) {
+    const float* p = &m->pos[3 * (size_t)m->edges[2 * (size_t)e]];
+    const float* q = &m->pos[3 * (size_t)m->edges[2 * (size_t)e + 1]];
+    float dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
+    out[e] = std::sqrt(dx * dx + dy * dy + dz * dz);
+  }
+}
+
+// MeshMap::computeEdgeWeights  mesh_map.cpp:517-561 (formula :539-553; edge_cost_factor is double, mesh_map.h:516)
+void orc_edge_weights(void* h, const float* vertex_costs, const float* edge_distances,
+                      double edge_cost_factor, float* edge_weights) {
+  OrcMesh* m = (OrcMesh*)h;
+  for (uint32_t e = 0; e < m->E; ++e) {
+    const float v1cost = vertex_costs[m->edges[2 * (size_t)e]];
+    const float v2cost = vertex_costs[m->edges[2 * (size_t)e + 1]];
+    if (std::isinf(v1cost) || std::isinf(v2cost)) {
+      edge_weights[e] = FINF;
+    } else {
+      const float vertex_dist = edge_distances[e];
+      const float edge_cost = vertex_dist * (v1cost + v2cost) / 2.0;
+      edge_weights[e] = vertex_dist + edge_cost_factor * edge_cost;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// DijkstraMeshPlanner::dijkstra  dijkstra_mesh_planner.cpp:217-398 (loop :287-348)
+//   seed_vertex  = reference "start_vertex" (nearest vertex to the navigation goal, :235)
+//   robot_vertex = reference "goal_vertex"  (nearest vertex to the robot, :236); -1 = none
+// returns the MBF outcome code (0 SUCCESS, 54 NO_PATH_FOUND); stats[0]=fixed_set_cnt,
+// stats[1]=expanded vertices (reached the edge loop), stats[2]=propagation seconds.
+// ---------------------------------------------------------------------------
+uint32_t orc_dijkstra(void* h, const float* edge_weights, const float* vertex_costs,
+                      const uint8_t* invalid, uint32_t seed_vertex, int64_t robot_vertex,
+                      double cost_limit, double goal_dist_offset,
+                      float* distances, uint32_t* predecessors, double* stats) {
+  OrcMesh& m = *(OrcMesh*)h;
+  const uint32_t V = m.V;
+  if (robot_vertex >= 0 && (uint32_t)robot_vertex == seed_vertex) return 0;          // :252-255
+  std::vector<uint8_t> fixed(V, 0);                                                  // :257
+  for (uint32_t v = 0; v < V; ++v) { distances[v] = FINF; predecessors[v] = v; }     // :266-270
+  Meap pq(V);
+  distances[seed_vertex] = 0;                                                        // :276
+  pq.insert(seed_vertex, 0);
+  float goal_dist = FINF;                                                            // :279
+  size_t fixed_set_cnt = 0, expanded = 0;
+  const double t0 = now_s();
+  while (!pq.isEmpty()) {                                                            // :287
+    uint32_t cur = pq.popMin().key;
+    fixed[cur] = 1;
+    fixed_set_cnt++;
+    if (robot_vertex >= 0 && cur == (uint32_t)robot_vertex)                          // :293-297
+      goal_dist = distances[cur] + goal_dist_offset;
+    if (distances[cur] > goal_dist) continue;                                        // :299
+    if (vertex_costs[cur] > cost_limit) continue;                                    // :302
+    expanded++;
+    for (uint32_t k = m.ve_ptr[cur]; k < m.ve_ptr[cur + 1]; ++k) {                   // :320
+      uint32_t vH = m.ve_nbr[k];
+      if (fixed[vH]) continue;                                                       // :326
+      if (invalid && invalid[vH]) continue;                                          // :328
+      float tmp_cost = distances[cur] + edge_weights[m.ve_edge[k]];                  // :331
+      if (tmp_cost < distances[vH]) {                                                // :332
+        distances[vH] = tmp_cost;
+        pq.insert(vH, tmp_cost);
+        predecessors[vH] = cur;
+      }
+    }
+  }
+  const double t1 = now_s();
+  if (stats) { stats[0] = (double)fixed_set_cnt; stats[1] = (double)expanded; stats[2] = t1 - t0; }
+  if (robot_vertex >= 0 && predecessors[robot_vertex] == (uint32_t)robot_vertex) return 54;  // :358-362
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// CVPMeshPlanner::waveFrontPropagation  cvp_mesh_planner.cpp:651-970
+// (seeding :719-728, heap loop :747-886).  seed_face/seed_pos = reference
+// "start_face"/"start" (the navigation goal, :673), robot_face = reference
+// "goal_face" (-1 = none, full field).
+// stats: [0]=fixed_set_cnt [1]=expanded pops [2]=seconds [3]=#waveFrontUpdate calls
+//        [4]=#accepted updates [5]=#pops whose key < running max popped key (non-monotone)
+//        [6]=max back-step magnitude
+// ---------------------------------------------------------------------------
+uint32_t orc_cvp(void* h, const float* edge_weights, const float* vertex_costs, const uint8_t* invalid,
+                 uint32_t seed_face, const float* seed_pos, int64_t robot_face,
+                 double cost_limit, double goal_dist_offset,
+                 float* distances, uint32_t* predecessors, float* direction, int32_t* cutting_faces,
+                 double* stats) {
+  OrcMesh& m = *(OrcMesh*)h;
+  const uint32_t V = m.V;
+  std::vector<uint8_t> fixed(V, 0);                                                  // :702
+  for (uint32_t v = 0; v < V; ++v) {                                                 // :710-714
+    distances[v] = FINF; predecessors[v] = v; direction[v] = 0; cutting_faces[v] = -1;
+  }
+  CvpState st{distances, predecessors, direction, cutting_faces};
+  Meap pq(V);
+  for (int k = 0; k < 3; ++k) {                                                      // :719-728
+    uint32_t vH = m.faces[3 * (size_t)seed_face + k];
+    const float dx = seed_pos[0] - m.pos[3 * (size_t)vH], dy = seed_pos[1] - m.pos[3 * (size_t)vH + 1],
+                dz = seed_pos[2] - m.pos[3 * (size_t)vH + 2];
+    const float dist = std::sqrt(dx * dx + dy * dy + dz * dz);
+    distances[vH] = dist;
+    cutting_faces[vH] = (int32_t)seed_face;
+    fixed[vH] = 1;
+    pq.insert(vH, dist);
+  }
+  uint32_t goal_vertices[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
+  if (robot_face >= 0) for (int k = 0; k < 3; ++k) goal_vertices[k] = m.faces[3 * (size_t)robot_face + k];
+  float goal_dist = FINF;                                                            // :738
+  size_t fixed_set_cnt = 0, expanded = 0, n_updates = 0, n_accept = 0, n_back = 0;
+  double max_back = 0; float hi_water = 0;
+  const double t0 = now_s();
+  while (!pq.isEmpty()) {                                                            // :747
+    uint32_t cur = pq.popMin().key;
+    fixed[cur] = 1;                                                                  // :751
+    fixed_set_cnt++;
+    if (distances[cur] < hi_water) { n_back++; max_back = std::max(max_back, (double)(hi_water - distances[cur])); }
+    else hi_water = distances[cur];
+    if (distances[cur] > goal_dist) continue;                                        // :754
+    if (vertex_costs[cur] >= cost_limit) continue;                                   // :757
+    if (invalid && invalid[cur]) continue;                                           // :760
+    if (cur == goal_vertices[0] || cur == goal_vertices[1] || cur == goal_vertices[2]) {  // :763-771
+      if (goal_dist == FINF && fixed[goal_vertices[0]] && fixed[goal_vertices[1]] && fixed[goal_vertices[2]])
+        goal_dist = distances[cur] + goal_dist_offset;
+    }
+    expanded++;
+    for (uint32_t k = m.vf_ptr[cur]; k < m.vf_ptr[cur + 1]; ++k) {                   // :778
+      const uint32_t fh = m.vf_face[k];
+      const uint32_t a = m.faces[3 * (size_t)fh], b = m.faces[3 * (size_t)fh + 1], c = m.faces[3 * (size_t)fh + 2];
+      if (invalid && (invalid[a] || invalid[b] || invalid[c])) continue;             // :785
+      if (fixed[a] && fixed[b] && fixed[c]) continue;                                // :790
+      else if (fixed[a] && fixed[b] && !fixed[c]) {                                  // :798
+        if (vertex_costs[c] >= cost_limit) continue;
+        n_updates++;
+        if (cvpWaveFrontUpdate(m, st, edge_weights, fh, a, b, c)) { pq.insert(c, distances[c]); n_accept++; }
+      } else if (fixed[a] && !fixed[b] && fixed[c]) {                                // :821
+        if (vertex_costs[b] >= cost_limit) continue;
+        n_updates++;
+        if (cvpWaveFrontUpdate(m, st, edge_weights, fh, c, a, b)) { pq.insert(b, distances[b]); n_accept++; }
+      } else if (!fixed[a] && fixed[b] && fixed[c]) {                                // :844
+        if (vertex_costs[a] >= cost_limit) continue;
+        n_updates++;
+        if (cvpWaveFrontUpdate(m, st, edge_weights, fh, b, c, a)) { pq.insert(a, distances[a]); n_accept++; }
+      } else continue;                                                               // :867
+    }
+  }
+  const double t1 = now_s();
+  if (stats) {
+    stats[0] = (double)fixed_set_cnt; stats[1] = (double)expanded; stats[2] = t1 - t0;
+    stats[3] = (double)n_updates; stats[4] = (double)n_accept; stats[5] = (double)n_back; stats[6] = max_back;
+  }
+  if (robot_face >= 0) {                                                             // :902-918
+    bool any = false;
+    for (int k = 0; k < 3; ++k) if (goal_vertices[k] != predecessors[goal_vertices[k]]) { any = true; break; }
+    if (!any && (uint32_t)robot_face != seed_face) return 54;
+  }
+  return 0;
+}
+
+// single call of CVPMeshPlanner::waveFrontUpdate on face `face` (for derived golden vectors)
+int orc_cvp_wavefront_update(void* h, const float* edge_weights, uint32_t face, uint32_t v1, uint32_t v2, uint32_t v3,
+                             float* distances, uint32_t* predecessors, float* direction, int32_t* cutting_faces) {
+  CvpState st{distances, predecessors, direction, cutting_faces};
+  return cvpWaveFrontUpdate(*(OrcMesh*)h, st, edge_weights, face, v1, v2, v3) ? 1 : 0;
+}
+
+// single call of InflationLayer::waveFrontUpdate (pinned by inflation_layer_test.cpp:62-76)
+int orc_inflation_wavefront_update(void* h, float* distances, float* vector_map, float max_distance,
+                                   const float* edge_weights, uint32_t face, uint32_t v1, uint32_t v2, uint32_t v3) {
+  return inflationWaveFrontUpdate(*(OrcMesh*)h, distances, vector_map, max_distance, edge_weights, face, v1, v2, v3) ? 1 : 0;
+}
+
+float orc_fading(double inscribed_radius, double inflation_radius, double lethal_value, double inscribed_value,
+                 double cost_scaling_factor, float distance) {
+  InflationConfig cfg{inscribed_radius, inflation_radius, lethal_value, inscribed_value, cost_scaling_factor};
+  return fading(cfg, distance);
+}
+
+float orc_sethian_update(float d1, float d2, float a, float b, float dot, float F) {
+  return sethianUpdate(d1, d2, a, b, dot, F);
+}
+
+// ---------------------------------------------------------------------------
+// InflationLayer::waveCostInflation  inflation_layer.cpp:341-491 (loop :407-478)
+// lethals must be ascending (std::set iteration order, :397).  distances: +inf
+// = "not in the sparse map".  cost_out: NaN = "not in the sparse map" (:484-490).
+// stats: [0]=pops [1]=seconds [2]=update calls
+// ---------------------------------------------------------------------------
+void orc_inflation(void* h, const float* edge_distances, const uint8_t* invalid,
+                   const uint32_t* lethals, uint32_t n_lethals,
+                   double inscribed_radius, double inflation_radius, double lethal_value,
+                   double inscribed_value, double cost_scaling_factor,
+                   float* distances, float* cost_out, float* vector_out /*nullable 3V*/, double* stats) {
+  OrcMesh& m = *(OrcMesh*)h;
+  const uint32_t V = m.V;
+  InflationConfig cfg{inscribed_radius, inflation_radius, lethal_value, inscribed_value, cost_scaling_factor};
+  const float max_distance = (float)inflation_radius;   // double -> `const float&` parameter (:450, :240)
+  std::vector<uint8_t> fixed(V, 0);
+  for (uint32_t v = 0; v < V; ++v) distances[v] = FINF;
+  if (vector_out) std::memset(vector_out, 0, sizeof(float) * 3 * (size_t)V);
+  Meap pq(V);
+  for (uint32_t i = 0; i < n_lethals; ++i) {                                         // :397-402
+    uint32_t vH = lethals[i];
+    distances[vH] = 0.0f; fixed[vH] = 1; pq.insert(vH, 0);
+  }
+  size_t pops = 0, calls = 0;
+  const double t0 = now_s();
+  while (!pq.isEmpty()) {                                                            // :407
+    uint32_t cur = pq.popMin().key;
+    pops++;
+    if (cur >= V) continue;                                                          // :412
+    if (invalid && invalid[cur]) continue;                                           // :417
+    fixed[cur] = 1;                                                                  // :422
+    for (uint32_t k = m.ve_ptr[cur]; k < m.ve_ptr[cur + 1]; ++k) {                   // :423 neighbours
+      const uint32_t e = m.ve_edge[k];
+      for (int side = 0; side < 2; ++side) {                                         // :427 both faces of the halfedge
+        const int32_t fh = m.edge_faces[2 * (size_t)e + side];
+        if (fh < 0) continue;
+        const uint32_t a = m.faces[3 * (size_t)fh], b = m.faces[3 * (size_t)fh + 1], c = m.faces[3 * (size_t)fh + 2];
+        if (fixed[a] && fixed[b] && fixed[c]) continue;                              // :443
+        else if (fixed[a] && fixed[b] && !fixed[c]) {
+          calls++;
+          if (inflationWaveFrontUpdate(m, distances, vector_out, max_distance, edge_distances, fh, a, b, c)) pq.insert(c, distances[c]);
+        } else if (fixed[a] && !fixed[b] && fixed[c]) {
+          calls++;
+          if (inflationWaveFrontUpdate(m, distances, vector_out, max_distance, edge_distances, fh, c, a, b)) pq.insert(b, distances[b]);
+        } else if (!fixed[a] && fixed[b] && fixed[c]) {
+          calls++;
+          if (inflationWaveFrontUpdate(m, distances, vector_out, max_distance, edge_distances, fh, b, c, a)) pq.insert(a, distances[a]);
+        } else continue;
+      }
+    }
+  }
+  const double t1 = now_s();
+  for (uint32_t v = 0; v < V; ++v)                                                   // :482-490
+    cost_out[v] = std::isinf(distances[v]) ? std::numeric_limits<float>::quiet_NaN() : fading(cfg, distances[v]);
+  if (stats) { stats[0] = (double)pops; stats[1] = t1 - t0; stats[2] = (double)calls; }
+}
+
+}  // extern "C"

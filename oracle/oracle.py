@@ -1,0 +1,156 @@
+"""ctypes loader for the CPU oracle (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module.  The product package
+(mesh_navigation_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "oracle.cpp")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        vp, u32, i64, dbl, f32 = C.c_void_p, C.c_uint32, C.c_int64, C.c_double, C.c_float
+        L.orc_mesh_create.restype = vp
+        L.orc_mesh_create.argtypes = [u32, u32, vp, vp, vp, u32]
+        L.orc_mesh_destroy.argtypes = [vp]
+        L.orc_mesh_num_edges.restype = u32
+        L.orc_mesh_num_edges.argtypes = [vp]
+        L.orc_mesh_get_edges.argtypes = [vp, vp]
+        L.orc_edge_distances.argtypes = [vp, vp]
+        L.orc_edge_weights.argtypes = [vp, vp, vp, dbl, vp]
+        L.orc_dijkstra.restype = u32
+        L.orc_dijkstra.argtypes = [vp, vp, vp, vp, u32, i64, dbl, dbl, vp, vp, vp]
+        L.orc_cvp.restype = u32
+        L.orc_cvp.argtypes = [vp, vp, vp, vp, u32, vp, i64, dbl, dbl, vp, vp, vp, vp, vp]
+        L.orc_cvp_wavefront_update.restype = C.c_int
+        L.orc_cvp_wavefront_update.argtypes = [vp, vp, u32, u32, u32, u32, vp, vp, vp, vp]
+        L.orc_inflation_wavefront_update.restype = C.c_int
+        L.orc_inflation_wavefront_update.argtypes = [vp, vp, vp, f32, vp, u32, u32, u32, u32]
+        L.orc_fading.restype = f32
+        L.orc_fading.argtypes = [dbl, dbl, dbl, dbl, dbl, f32]
+        L.orc_sethian_update.restype = f32
+        L.orc_sethian_update.argtypes = [f32] * 6
+        L.orc_inflation.argtypes = [vp, vp, vp, vp, u32, dbl, dbl, dbl, dbl, dbl, vp, vp, vp, vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class OracleMesh:
+    def __init__(self, pos: np.ndarray, faces: np.ndarray, edges: np.ndarray | None = None):
+        self.pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        self.faces = np.ascontiguousarray(faces, dtype=np.uint32).reshape(-1, 3)
+        self.V = self.pos.shape[0]
+        self.F = self.faces.shape[0]
+        e = None if edges is None else np.ascontiguousarray(edges, dtype=np.uint32).reshape(-1, 2)
+        self._h = lib().orc_mesh_create(self.V, self.F, _p(self.pos), _p(self.faces), _p(e),
+                                        0 if e is None else e.shape[0])
+        self.E = lib().orc_mesh_num_edges(self._h)
+        self.edges = np.empty((self.E, 2), dtype=np.uint32)
+        lib().orc_mesh_get_edges(self._h, _p(self.edges))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_mesh_destroy(self._h)
+            self._h = None
+
+    def edge_distances(self) -> np.ndarray:
+        out = np.empty(self.E, dtype=np.float32)
+        lib().orc_edge_distances(self._h, _p(out))
+        return out
+
+    def edge_weights(self, vertex_costs, edge_distances, edge_cost_factor: float) -> np.ndarray:
+        vc = np.ascontiguousarray(vertex_costs, dtype=np.float32)
+        ed = np.ascontiguousarray(edge_distances, dtype=np.float32)
+        out = np.empty(self.E, dtype=np.float32)
+        lib().orc_edge_weights(self._h, _p(vc), _p(ed), float(edge_cost_factor), _p(out))
+        return out
+
+    def dijkstra(self, edge_weights, vertex_costs, seed_vertex: int, robot_vertex: int = -1,
+                 invalid=None, cost_limit: float = 1.0, goal_dist_offset: float = 0.3):
+        ew = np.ascontiguousarray(edge_weights, dtype=np.float32)
+        vc = np.ascontiguousarray(vertex_costs, dtype=np.float32)
+        inv = None if invalid is None else np.ascontiguousarray(invalid, dtype=np.uint8)
+        dist = np.empty(self.V, dtype=np.float32)
+        pred = np.empty(self.V, dtype=np.uint32)
+        stats = np.zeros(8, dtype=np.float64)
+        rc = lib().orc_dijkstra(self._h, _p(ew), _p(vc), _p(inv), int(seed_vertex), int(robot_vertex),
+                                float(cost_limit), float(goal_dist_offset), _p(dist), _p(pred), _p(stats))
+        return dict(outcome=rc, dist=dist, pred=pred, fixed=int(stats[0]), expanded=int(stats[1]),
+                    seconds=float(stats[2]))
+
+    def cvp(self, edge_weights, vertex_costs, seed_face: int, seed_pos, robot_face: int = -1,
+            invalid=None, cost_limit: float = 1.0, goal_dist_offset: float = 0.3):
+        ew = np.ascontiguousarray(edge_weights, dtype=np.float32)
+        vc = np.ascontiguousarray(vertex_costs, dtype=np.float32)
+        inv = None if invalid is None else np.ascontiguousarray(invalid, dtype=np.uint8)
+        sp = np.ascontiguousarray(seed_pos, dtype=np.float32)
+        dist = np.empty(self.V, dtype=np.float32)
+        pred = np.empty(self.V, dtype=np.uint32)
+        direction = np.empty(self.V, dtype=np.float32)
+        cut = np.empty(self.V, dtype=np.int32)
+        stats = np.zeros(8, dtype=np.float64)
+        rc = lib().orc_cvp(self._h, _p(ew), _p(vc), _p(inv), int(seed_face), _p(sp), int(robot_face),
+                           float(cost_limit), float(goal_dist_offset), _p(dist), _p(pred), _p(direction),
+                           _p(cut), _p(stats))
+        return dict(outcome=rc, dist=dist, pred=pred, direction=direction, cutting_face=cut,
+                    fixed=int(stats[0]), expanded=int(stats[1]), seconds=float(stats[2]),
+                    updates=int(stats[3]), accepted=int(stats[4]), backsteps=int(stats[5]),
+                    max_backstep=float(stats[6]))
+
+    def cvp_wavefront_update(self, edge_weights, face, v1, v2, v3, dist, pred, direction, cut) -> bool:
+        ew = np.ascontiguousarray(edge_weights, dtype=np.float32)
+        return bool(lib().orc_cvp_wavefront_update(self._h, _p(ew), face, v1, v2, v3, _p(dist), _p(pred),
+                                                   _p(direction), _p(cut)))
+
+    def inflation_wavefront_update(self, dist, vectors, max_distance, edge_weights, face, v1, v2, v3) -> bool:
+        ew = np.ascontiguousarray(edge_weights, dtype=np.float32)
+        return bool(lib().orc_inflation_wavefront_update(self._h, _p(dist), _p(vectors), float(max_distance),
+                                                         _p(ew), face, v1, v2, v3))
+
+    def inflation(self, edge_distances, lethals, invalid=None, inscribed_radius=0.25, inflation_radius=0.4,
+                  lethal_value=1.0, inscribed_value=0.99, cost_scaling_factor=1.0, with_vectors=False):
+        ed = np.ascontiguousarray(edge_distances, dtype=np.float32)
+        le = np.unique(np.ascontiguousarray(lethals, dtype=np.uint32))  # std::set order
+        inv = None if invalid is None else np.ascontiguousarray(invalid, dtype=np.uint8)
+        dist = np.empty(self.V, dtype=np.float32)
+        cost = np.empty(self.V, dtype=np.float32)
+        vec = np.zeros((self.V, 3), dtype=np.float32) if with_vectors else None
+        stats = np.zeros(8, dtype=np.float64)
+        lib().orc_inflation(self._h, _p(ed), _p(inv), _p(le), le.size, float(inscribed_radius),
+                            float(inflation_radius), float(lethal_value), float(inscribed_value),
+                            float(cost_scaling_factor), _p(dist), _p(cost), _p(vec), _p(stats))
+        return dict(dist=dist, cost=cost, vectors=vec, pops=int(stats[0]), seconds=float(stats[1]),
+                    updates=int(stats[2]))
+
+
+def fading(distance, inscribed_radius=0.25, inflation_radius=0.4, lethal_value=1.0, inscribed_value=0.99,
+           cost_scaling_factor=1.0) -> float:
+    return float(lib().orc_fading(inscribed_radius, inflation_radius, lethal_value, inscribed_value,
+                                  cost_scaling_factor, float(distance)))
