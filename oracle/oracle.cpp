@@ -52,7 +52,15 @@ struct Meap {
   struct Item { uint32_t key; float value; };
   std::vector<Item> heap;
   std::vector<int32_t> slot;  // -1 = absent
-  explicit Meap(uint32_t n) : slot(n, -1) {}
+  // canonical_ties = false: plain value comparison (lvr2::Meap as restated; pop order among
+  //   bit-identical float keys then depends on heap history -- unpinned).
+  // canonical_ties = true : ties between bit-identical keys pop in ascending vertex index.  This
+  //   makes the result independent of heap internals; the GPU path implements the same rule.
+  bool canonical_ties;
+  explicit Meap(uint32_t n, bool canonical = false) : slot(n, -1), canonical_ties(canonical) {}
+  bool less(const Item& a, const Item& b) const {
+    return a.value < b.value || (canonical_ties && a.value == b.value && a.key < b.key);
+  }
   bool isEmpty() const { return heap.empty(); }
   void swapSlots(size_t a, size_t b) {
     std::swap(heap[a], heap[b]);
@@ -62,7 +70,7 @@ struct Meap {
   void bubbleUp(size_t idx) {
     while (idx != 0) {
       size_t father = (idx - 1) / 2;
-      if (heap[idx].value < heap[father].value) { swapSlots(idx, father); idx = father; }
+      if (less(heap[idx], heap[father])) { swapSlots(idx, father); idx = father; }
       else break;
     }
   }
@@ -70,8 +78,8 @@ struct Meap {
     const size_t n = heap.size();
     for (;;) {
       size_t l = 2 * idx + 1, r = 2 * idx + 2, s = idx;
-      if (l < n && heap[l].value < heap[s].value) s = l;
-      if (r < n && heap[r].value < heap[s].value) s = r;
+      if (l < n && less(heap[l], heap[s])) s = l;
+      if (r < n && less(heap[r], heap[s])) s = r;
       if (s == idx) break;
       swapSlots(idx, s);
       idx = s;
@@ -434,14 +442,14 @@ void orc_edge_weights(void* h, const float* vertex_costs, const float* edge_dist
 // ---------------------------------------------------------------------------
 uint32_t orc_dijkstra(void* h, const float* edge_weights, const float* vertex_costs,
                       const uint8_t* invalid, uint32_t seed_vertex, int64_t robot_vertex,
-                      double cost_limit, double goal_dist_offset,
+                      double cost_limit, double goal_dist_offset, int canonical_ties,
                       float* distances, uint32_t* predecessors, double* stats) {
   OrcMesh& m = *(OrcMesh*)h;
   const uint32_t V = m.V;
   if (robot_vertex >= 0 && (uint32_t)robot_vertex == seed_vertex) return 0;          // :252-255
   std::vector<uint8_t> fixed(V, 0);                                                  // :257
   for (uint32_t v = 0; v < V; ++v) { distances[v] = FINF; predecessors[v] = v; }     // :266-270
-  Meap pq(V);
+  Meap pq(V, canonical_ties != 0);
   distances[seed_vertex] = 0;                                                        // :276
   pq.insert(seed_vertex, 0);
   float goal_dist = FINF;                                                            // :279
@@ -485,7 +493,7 @@ uint32_t orc_dijkstra(void* h, const float* edge_weights, const float* vertex_co
 // ---------------------------------------------------------------------------
 uint32_t orc_cvp(void* h, const float* edge_weights, const float* vertex_costs, const uint8_t* invalid,
                  uint32_t seed_face, const float* seed_pos, int64_t robot_face,
-                 double cost_limit, double goal_dist_offset,
+                 double cost_limit, double goal_dist_offset, int canonical_ties,
                  float* distances, uint32_t* predecessors, float* direction, int32_t* cutting_faces,
                  double* stats) {
   OrcMesh& m = *(OrcMesh*)h;
@@ -495,7 +503,7 @@ uint32_t orc_cvp(void* h, const float* edge_weights, const float* vertex_costs, 
     distances[v] = FINF; predecessors[v] = v; direction[v] = 0; cutting_faces[v] = -1;
   }
   CvpState st{distances, predecessors, direction, cutting_faces};
-  Meap pq(V);
+  Meap pq(V, canonical_ties != 0);
   for (int k = 0; k < 3; ++k) {                                                      // :719-728
     uint32_t vH = m.faces[3 * (size_t)seed_face + k];
     const float dx = seed_pos[0] - m.pos[3 * (size_t)vH], dy = seed_pos[1] - m.pos[3 * (size_t)vH + 1],
@@ -591,7 +599,7 @@ float orc_sethian_update(float d1, float d2, float a, float b, float dot, float 
 void orc_inflation(void* h, const float* edge_distances, const uint8_t* invalid,
                    const uint32_t* lethals, uint32_t n_lethals,
                    double inscribed_radius, double inflation_radius, double lethal_value,
-                   double inscribed_value, double cost_scaling_factor,
+                   double inscribed_value, double cost_scaling_factor, int canonical_ties,
                    float* distances, float* cost_out, float* vector_out /*nullable 3V*/, double* stats) {
   OrcMesh& m = *(OrcMesh*)h;
   const uint32_t V = m.V;
@@ -600,7 +608,7 @@ void orc_inflation(void* h, const float* edge_distances, const uint8_t* invalid,
   std::vector<uint8_t> fixed(V, 0);
   for (uint32_t v = 0; v < V; ++v) distances[v] = FINF;
   if (vector_out) std::memset(vector_out, 0, sizeof(float) * 3 * (size_t)V);
-  Meap pq(V);
+  Meap pq(V, canonical_ties != 0);
   for (uint32_t i = 0; i < n_lethals; ++i) {                                         // :397-402
     uint32_t vH = lethals[i];
     distances[vH] = 0.0f; fixed[vH] = 1; pq.insert(vH, 0);

@@ -42,9 +42,9 @@ def lib():
         L.orc_edge_distances.argtypes = [vp, vp]
         L.orc_edge_weights.argtypes = [vp, vp, vp, dbl, vp]
         L.orc_dijkstra.restype = u32
-        L.orc_dijkstra.argtypes = [vp, vp, vp, vp, u32, i64, dbl, dbl, vp, vp, vp]
+        L.orc_dijkstra.argtypes = [vp, vp, vp, vp, u32, i64, dbl, dbl, C.c_int, vp, vp, vp]
         L.orc_cvp.restype = u32
-        L.orc_cvp.argtypes = [vp, vp, vp, vp, u32, vp, i64, dbl, dbl, vp, vp, vp, vp, vp]
+        L.orc_cvp.argtypes = [vp, vp, vp, vp, u32, vp, i64, dbl, dbl, C.c_int, vp, vp, vp, vp, vp]
         L.orc_cvp_wavefront_update.restype = C.c_int
         L.orc_cvp_wavefront_update.argtypes = [vp, vp, u32, u32, u32, u32, vp, vp, vp, vp]
         L.orc_inflation_wavefront_update.restype = C.c_int
@@ -53,7 +53,7 @@ def lib():
         L.orc_fading.argtypes = [dbl, dbl, dbl, dbl, dbl, f32]
         L.orc_sethian_update.restype = f32
         L.orc_sethian_update.argtypes = [f32] * 6
-        L.orc_inflation.argtypes = [vp, vp, vp, vp, u32, dbl, dbl, dbl, dbl, dbl, vp, vp, vp, vp]
+        L.orc_inflation.argtypes = [vp, vp, vp, vp, u32, dbl, dbl, dbl, dbl, dbl, C.c_int, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -93,7 +93,7 @@ class OracleMesh:
         return out
 
     def dijkstra(self, edge_weights, vertex_costs, seed_vertex: int, robot_vertex: int = -1,
-                 invalid=None, cost_limit: float = 1.0, goal_dist_offset: float = 0.3):
+                 invalid=None, cost_limit: float = 1.0, goal_dist_offset: float = 0.3, canonical_ties: bool = True):
         ew = np.ascontiguousarray(edge_weights, dtype=np.float32)
         vc = np.ascontiguousarray(vertex_costs, dtype=np.float32)
         inv = None if invalid is None else np.ascontiguousarray(invalid, dtype=np.uint8)
@@ -101,12 +101,12 @@ class OracleMesh:
         pred = np.empty(self.V, dtype=np.uint32)
         stats = np.zeros(8, dtype=np.float64)
         rc = lib().orc_dijkstra(self._h, _p(ew), _p(vc), _p(inv), int(seed_vertex), int(robot_vertex),
-                                float(cost_limit), float(goal_dist_offset), _p(dist), _p(pred), _p(stats))
+                                float(cost_limit), float(goal_dist_offset), int(canonical_ties), _p(dist), _p(pred), _p(stats))
         return dict(outcome=rc, dist=dist, pred=pred, fixed=int(stats[0]), expanded=int(stats[1]),
                     seconds=float(stats[2]))
 
     def cvp(self, edge_weights, vertex_costs, seed_face: int, seed_pos, robot_face: int = -1,
-            invalid=None, cost_limit: float = 1.0, goal_dist_offset: float = 0.3):
+            invalid=None, cost_limit: float = 1.0, goal_dist_offset: float = 0.3, canonical_ties: bool = True):
         ew = np.ascontiguousarray(edge_weights, dtype=np.float32)
         vc = np.ascontiguousarray(vertex_costs, dtype=np.float32)
         inv = None if invalid is None else np.ascontiguousarray(invalid, dtype=np.uint8)
@@ -117,7 +117,7 @@ class OracleMesh:
         cut = np.empty(self.V, dtype=np.int32)
         stats = np.zeros(8, dtype=np.float64)
         rc = lib().orc_cvp(self._h, _p(ew), _p(vc), _p(inv), int(seed_face), _p(sp), int(robot_face),
-                           float(cost_limit), float(goal_dist_offset), _p(dist), _p(pred), _p(direction),
+                           float(cost_limit), float(goal_dist_offset), int(canonical_ties), _p(dist), _p(pred), _p(direction),
                            _p(cut), _p(stats))
         return dict(outcome=rc, dist=dist, pred=pred, direction=direction, cutting_face=cut,
                     fixed=int(stats[0]), expanded=int(stats[1]), seconds=float(stats[2]),
@@ -135,7 +135,8 @@ class OracleMesh:
                                                          _p(ew), face, v1, v2, v3))
 
     def inflation(self, edge_distances, lethals, invalid=None, inscribed_radius=0.25, inflation_radius=0.4,
-                  lethal_value=1.0, inscribed_value=0.99, cost_scaling_factor=1.0, with_vectors=False):
+                  lethal_value=1.0, inscribed_value=0.99, cost_scaling_factor=1.0, with_vectors=False,
+                  canonical_ties: bool = True):
         ed = np.ascontiguousarray(edge_distances, dtype=np.float32)
         le = np.unique(np.ascontiguousarray(lethals, dtype=np.uint32))  # std::set order
         inv = None if invalid is None else np.ascontiguousarray(invalid, dtype=np.uint8)
@@ -145,7 +146,7 @@ class OracleMesh:
         stats = np.zeros(8, dtype=np.float64)
         lib().orc_inflation(self._h, _p(ed), _p(inv), _p(le), le.size, float(inscribed_radius),
                             float(inflation_radius), float(lethal_value), float(inscribed_value),
-                            float(cost_scaling_factor), _p(dist), _p(cost), _p(vec), _p(stats))
+                            float(cost_scaling_factor), int(canonical_ties), _p(dist), _p(cost), _p(vec), _p(stats))
         return dict(dist=dist, cost=cost, vectors=vec, pops=int(stats[0]), seconds=float(stats[1]),
                     updates=int(stats[2]))
 

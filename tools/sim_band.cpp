@@ -22,14 +22,14 @@ constexpr float FINF = std::numeric_limits<float>::infinity();
 struct Sim {
   HostTopology T;
   const float* w; const float* cost; const uint8_t* invalid;
-  double cost_limit; int gate;
+  double cost_limit; int gate; int flags_;
   std::vector<float> d, tau;
   std::vector<uint8_t> fixed;
   float band_end;
 
   // recompute vertex c from scratch, emulating the reference's per-vertex event order
   float recompute(uint32_t c, float* tau_out) {
-    struct Cand { float T; float u1, u2, a, b, cw; };
+    struct Cand { float T; uint32_t Tid; float u1, u2, a, b, cw; };
     Cand cs[64]; int n = 0;
     for (uint32_t k = T.vcor_ptr[c]; k < T.vcor_ptr[c + 1] && n < 64; ++k) {
       const uint32_t v1 = T.cor_v1[k], v2 = T.cor_v2[k];
@@ -37,22 +37,26 @@ struct Sim {
       const float d1 = d[v1], d2 = d[v2];
       const bool av1 = fixed[v1] || d1 < band_end, av2 = fixed[v2] || d2 < band_end;
       if (!av1 || !av2) continue;
-      // the later of (v1,v2) is the one whose pop visits the face: it must expand (cvp:757)
-      const uint32_t later = (tau[v1] > tau[v2]) ? v1 : v2;
+      // event time of a vertex = (tau, id) lexicographic; the later of (v1,v2) is the one whose
+      // pop visits the face: it must expand (cvp:757)
+      const bool v1_later = tau[v1] > tau[v2] || (tau[v1] == tau[v2] && v1 > v2);
+      const uint32_t later = v1_later ? v1 : v2;
       if (!(cost[later] < cost_limit)) continue;
-      cs[n++] = {std::fmax(tau[v1], tau[v2]), d1, d2, w[T.cor_ea[k]], w[T.cor_eb[k]], w[T.cor_ec[k]]};
+      cs[n++] = {tau[later], later, d1, d2, w[T.cor_ea[k]], w[T.cor_eb[k]], w[T.cor_ec[k]]};
     }
-    // process in order of T (selection sort, n small)
     float cur = FINF, tcur = FINF;
     for (int i = 0; i < n; ++i) {
       int best = i;
-      for (int j = i + 1; j < n; ++j) if (cs[j].T < cs[best].T) best = j;
+      for (int j = i + 1; j < n; ++j)
+        if (cs[j].T < cs[best].T || (cs[j].T == cs[best].T && cs[j].Tid < cs[best].Tid)) best = j;
       std::swap(cs[i], cs[best]);
-      if (gate && !(cs[i].T < tcur)) break;   // c would already have been popped
+      const bool before = cs[i].T < tcur || (cs[i].T == tcur && cs[i].Tid < c);
+      if (gate && !before) break;   // c would already have been popped
       CvpResult r;
       if (cvp_update(cs[i].u1, cs[i].u2, cur, cs[i].a, cs[i].b, cs[i].cw, r)) {
         cur = r.value;
         tcur = std::fmax(cur, cs[i].T);
+        if ((flags_ & 4) && tcur == cs[i].T && !(cs[i].Tid < c)) tcur = std::nextafter(tcur, FINF);
       }
     }
     *tau_out = tcur;
@@ -68,7 +72,7 @@ extern "C" int sim_cvp_band(uint32_t V, uint32_t F, const uint32_t* faces, const
   Sim S;
   S.T.build(V, F, faces, edges, E);
   S.w = edge_weights; S.cost = vertex_costs; S.invalid = invalid; S.cost_limit = cost_limit;
-  S.gate = flags & 1;
+  S.gate = flags & 1; S.flags_ = flags;
   const bool use_tau = flags & 2;
   S.d.assign(V, FINF); S.tau.assign(V, FINF); S.fixed.assign(V, 0);
   std::vector<uint8_t> in_cand(V, 0);
@@ -95,8 +99,10 @@ extern "C" int sim_cvp_band(uint32_t V, uint32_t F, const uint32_t* faces, const
   size_t rounds = 0, recomputes = 0;
   std::vector<float> nd, nt;
   std::vector<uint8_t> was_avail;
+  const size_t max_rounds = 200000;
   while (!cand.empty()) {
     rounds++;
+    if (rounds > max_rounds) { if (stats) { stats[0] = -1; } break; }
     float lo = FINF;
     for (uint32_t c : cand) lo = std::fmin(lo, S.d[c]);
     S.band_end = (lo == FINF) ? FINF : (float)(lo + delta);
