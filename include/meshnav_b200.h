@@ -1,0 +1,145 @@
+/*
+ * meshnav_b200.h -- C ABI of libmeshnav_b200.so
+ *
+ * B200-native (sm_100a CUDA) replacement for the wavefront hot path of
+ * naturerobots/mesh_navigation.  Plain pointers and sizes only; no C++ / torch
+ * types cross this boundary.  Every entry point names the reference interface
+ * it stands in for (paths relative to the reference repo).
+ *
+ * Conventions
+ *   - all calls return MNB_OK (0) or a negative MNB_E_* code, except the
+ *     planner calls which return the MBF GetPath::Result code the reference's
+ *     makePlan would return (dijkstra_mesh_planner.h:72-85): 0 SUCCESS,
+ *     51 CANCELED, 52 INVALID_START, 53 INVALID_GOAL, 54 NO_PATH_FOUND,
+ *     or a negative MNB_E_* code on CUDA / argument errors.
+ *   - array arguments are HOST pointers by default.  After
+ *     mnb_set_pointer_mode(ctx, MNB_PTR_DEVICE) array arguments of the
+ *     per-call functions (costs, weights, outputs) are DEVICE pointers on the
+ *     context's device and no host<->device copy happens inside the call.
+ *   - the library never frees or keeps caller memory; outputs are written into
+ *     caller-provided buffers of the stated length.
+ *   - an mnb_ctx is single-caller (one stream); mnb_cancel() is the only entry
+ *     point that may be called concurrently from another thread
+ *     (reference: CVPMeshPlanner::cancel, cvp_mesh_planner.cpp:142-146).
+ *   - there is NO CPU fallback: every compute entry point fails with
+ *     MNB_E_CUDA if no sm_100 device is usable.
+ */
+#ifndef MESHNAV_B200_H
+#define MESHNAV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MNB_OK 0
+#define MNB_E_ARG (-1)
+#define MNB_E_CUDA (-2)
+#define MNB_E_STATE (-3)
+#define MNB_E_NCCL (-4)
+#define MNB_E_NOMEM (-5)
+
+/* MBF outcome codes (mbf_msgs/action/GetPath; dijkstra_mesh_planner.h:72-85) */
+#define MNB_SUCCESS 0
+#define MNB_CANCELED 51
+#define MNB_INVALID_START 52
+#define MNB_INVALID_GOAL 53
+#define MNB_NO_PATH_FOUND 54
+
+#define MNB_PTR_HOST 0
+#define MNB_PTR_DEVICE 1
+
+typedef struct mnb_ctx mnb_ctx;
+
+/* ---- lifetime ----------------------------------------------------------- */
+int32_t mnb_create(int32_t device, mnb_ctx** out_ctx);
+void mnb_destroy(mnb_ctx* ctx);
+const char* mnb_last_error(mnb_ctx* ctx);
+int32_t mnb_set_pointer_mode(mnb_ctx* ctx, int32_t mode);
+/* cudaStream_t (as void*) the context launches on; lets a caller time with CUDA events. */
+void* mnb_stream(mnb_ctx* ctx);
+
+/* ---- map upload: replaces the lvr2 half-edge mesh the plugins read ------
+ * mesh_map::MeshMap::mesh() / edgeDistances() (mesh_map.h:97-452, mesh_map.cpp:404-425).
+ * pos[3V] float xyz, faces[3F] vertex ids in the mesh's cyclic (CCW) order.
+ * edges[2E] may be NULL: the library then numbers edges by ascending (lo,hi)
+ * vertex pair; pass the caller's own edge order (e.g. lvr2 EdgeHandle order)
+ * so that edge_weights / edge_distances arrays use the caller's indices.
+ * Always HOST pointers (one-time setup). */
+int32_t mnb_set_mesh(mnb_ctx* ctx, uint32_t V, uint32_t F, const float* pos, const uint32_t* faces,
+                     const uint32_t* edges, uint32_t E);
+uint32_t mnb_num_vertices(mnb_ctx* ctx);
+uint32_t mnb_num_faces(mnb_ctx* ctx);
+uint32_t mnb_num_edges(mnb_ctx* ctx);
+int32_t mnb_get_edges(mnb_ctx* ctx, uint32_t* out_edges /* 2E, host */);
+/* lvr2::calcVertexDistances as used for MeshMap::edge_distances (mesh_map.cpp:414) */
+int32_t mnb_get_edge_distances(mnb_ctx* ctx, float* out_edge_distances /* E */);
+
+/* ---- MeshMap::computeEdgeWeights (mesh_map.cpp:517-561) -----------------
+ * edge_weights[e] = +inf if an endpoint cost is inf, else
+ * dist[e] + edge_cost_factor * (dist[e] * (c1 + c2) / 2).  Writes out_edge_weights (E) if
+ * non-NULL and installs vertex_costs + the weights as the planners' inputs. */
+int32_t mnb_compute_edge_weights(mnb_ctx* ctx, const float* vertex_costs /* V */, double edge_cost_factor,
+                                 float* out_edge_weights /* E or NULL */);
+
+/* ---- per-plan inputs the planners read from the map ---------------------
+ * MeshMap::vertexCosts() / edgeWeights() / invalid
+ * (cvp_mesh_planner.cpp:245,663-664; dijkstra_mesh_planner.cpp:214,227-229).
+ * invalid may be NULL (no invalid vertices). */
+int32_t mnb_set_costs(mnb_ctx* ctx, const float* vertex_costs /* V */, const float* edge_weights /* E */,
+                      const uint8_t* invalid /* V or NULL */);
+
+/* ---- DijkstraMeshPlanner::dijkstra (dijkstra_mesh_planner.cpp:217-398) ---
+ * seed_vertex  = the reference's start_vertex (nearest vertex to the navigation goal, :235)
+ * robot_vertex = the reference's goal_vertex (nearest vertex to the robot, :236) or -1 for a
+ *                full field.  out_dist[V] (+inf = unreached), out_pred[V] (self = none). */
+int32_t mnb_dijkstra(mnb_ctx* ctx, uint32_t seed_vertex, int64_t robot_vertex, double cost_limit,
+                     double goal_dist_offset, float* out_dist, uint32_t* out_pred);
+
+/* ---- CVPMeshPlanner::waveFrontPropagation (cvp_mesh_planner.cpp:651-886) -
+ * seed_face / seed_pos = the reference's start_face / start (navigation goal, :673,:719-728)
+ * robot_face           = the reference's goal_face (:674) or -1 for a full field.
+ * Outputs (any may be NULL): potential_ , predecessors_, direction_, cutting_faces_ (-1 = none). */
+int32_t mnb_cvp(mnb_ctx* ctx, uint32_t seed_face, const float seed_pos[3], int64_t robot_face,
+                double cost_limit, double goal_dist_offset, float* out_dist, uint32_t* out_pred,
+                float* out_direction, int32_t* out_cutting_face);
+
+/* Batched full-field CVP potentials: n independent goals on the installed map, one wavefront
+ * per thread-block cluster, all SMs busy.  out_dist is [n][V] row-major. */
+int32_t mnb_cvp_batch(mnb_ctx* ctx, uint32_t n, const uint32_t* seed_faces /* n, host */,
+                      const float* seed_pos /* 3n, host */, double cost_limit, float* out_dist);
+
+/* ---- InflationLayer::waveCostInflation (inflation_layer.cpp:341-491) -----
+ * lethals[n] (any order, duplicates allowed).  Uses edge_distances (:383), not edge_weights.
+ * out_dist[V]: distances_ (+inf = not in the sparse map); out_cost[V]: riskiness_ =
+ * fading(dist) (NaN = not in the sparse map).  Either may be NULL. */
+typedef struct mnb_inflation_params {
+  double inscribed_radius;    /* 0.25  (inflation_layer.h:240-248) */
+  double inflation_radius;    /* 0.4  */
+  double lethal_value;        /* 1.0  */
+  double inscribed_value;     /* 0.99 */
+  double cost_scaling_factor; /* 1.0  */
+} mnb_inflation_params;
+int32_t mnb_inflate(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, const uint8_t* invalid /* V or NULL */,
+                    const mnb_inflation_params* params, float* out_dist, float* out_cost);
+
+/* ---- cancel (CVPMeshPlanner::cancel / DijkstraMeshPlanner::cancel) ------- */
+int32_t mnb_cancel(mnb_ctx* ctx);
+
+/* ---- introspection for tests / bench ------------------------------------ */
+typedef struct mnb_stats {
+  uint64_t rounds;          /* band rounds of the last wavefront call */
+  uint64_t recomputes;      /* vertex recomputations (>= settled vertices) */
+  uint64_t settled;         /* vertices with a finite final label */
+  uint64_t kernel_launches; /* kernels launched by the last call */
+  float kernel_ms;          /* CUDA-event time of the wavefront kernel(s) of the last call */
+} mnb_stats;
+int32_t mnb_get_stats(mnb_ctx* ctx, mnb_stats* out);
+/* tuning knobs: band width delta (metres) and CTAs per wavefront cluster (1,2,4,8,16) */
+int32_t mnb_set_tuning(mnb_ctx* ctx, float band_delta, int32_t cluster_size, int32_t threads_per_cta);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MESHNAV_B200_H */

@@ -1,0 +1,195 @@
+"""Thin Python driver over the C ABI (test / bench orchestration only).
+
+Mirrors the names of the reference's hot-path entry points:
+  MeshMap.computeEdgeWeights      mesh_map/src/mesh_map.cpp:517-561
+  DijkstraMeshPlanner.dijkstra    dijkstra_mesh_planner/src/dijkstra_mesh_planner.cpp:217-398
+  CVPMeshPlanner.waveFrontPropagation  cvp_mesh_planner/src/cvp_mesh_planner.cpp:651-886
+  InflationLayer.waveCostInflation     mesh_layers/src/inflation_layer.cpp:341-491
+All compute happens in libmeshnav_b200.so on the GPU; nothing here falls back to
+numpy or to the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class MeshNavError(RuntimeError):
+    pass
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class MeshMap:
+    """Device-resident flattened mesh + the per-plan inputs the planners read
+    (vertex_costs, edge_weights, invalid) -- the slice of mesh_map::MeshMap the hot path touches."""
+
+    def __init__(self, pos: np.ndarray, faces: np.ndarray, edges: np.ndarray | None = None, device: int = 0):
+        self.L = _lib.load()
+        self._ctx = C.c_void_p()
+        rc = self.L.mnb_create(device, C.byref(self._ctx))
+        if rc != 0:
+            raise MeshNavError(f"mnb_create failed ({rc}): no usable sm_100 CUDA device; there is no CPU fallback")
+        self.pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        self.faces = np.ascontiguousarray(faces, dtype=np.uint32).reshape(-1, 3)
+        e = None if edges is None else np.ascontiguousarray(edges, dtype=np.uint32).reshape(-1, 2)
+        self._check(self.L.mnb_set_mesh(self._ctx, self.pos.shape[0], self.faces.shape[0], _p(self.pos), _p(self.faces),
+                                        _p(e), 0 if e is None else e.shape[0]))
+        self.V = self.L.mnb_num_vertices(self._ctx)
+        self.F = self.L.mnb_num_faces(self._ctx)
+        self.E = self.L.mnb_num_edges(self._ctx)
+        self.device_pointers = False
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self.L.mnb_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise MeshNavError(f"meshnav_b200 error {rc}: {self.L.mnb_last_error(self._ctx).decode()}")
+        return rc
+
+    # -- setup ------------------------------------------------------------
+    def set_tuning(self, band_delta: float = 0.0, cluster_size: int = 0, threads: int = 0):
+        self._check(self.L.mnb_set_tuning(self._ctx, band_delta, cluster_size, threads))
+
+    def use_device_pointers(self, on: bool):
+        self._check(self.L.mnb_set_pointer_mode(self._ctx, 1 if on else 0))
+        self.device_pointers = on
+
+    def stream(self) -> int:
+        return int(self.L.mnb_stream(self._ctx) or 0)
+
+    def edges(self) -> np.ndarray:
+        out = np.empty((self.E, 2), dtype=np.uint32)
+        self._check(self.L.mnb_get_edges(self._ctx, _p(out)))
+        return out
+
+    def edgeDistances(self) -> np.ndarray:
+        assert not self.device_pointers
+        out = np.empty(self.E, dtype=np.float32)
+        self._check(self.L.mnb_get_edge_distances(self._ctx, _p(out)))
+        return out
+
+    def computeEdgeWeights(self, vertex_costs, edge_cost_factor: float = 0.0, want_output: bool = True):
+        vc = np.ascontiguousarray(vertex_costs, dtype=np.float32)
+        out = np.empty(self.E, dtype=np.float32) if want_output else None
+        self._check(self.L.mnb_compute_edge_weights(self._ctx, _p(vc), float(edge_cost_factor), _p(out)))
+        return out
+
+    def setCosts(self, vertex_costs, edge_weights, invalid=None):
+        if self.device_pointers:
+            self._check(self.L.mnb_set_costs(self._ctx, _p(vertex_costs), _p(edge_weights), _p(invalid)))
+            return
+        vc = np.ascontiguousarray(vertex_costs, dtype=np.float32)
+        ew = np.ascontiguousarray(edge_weights, dtype=np.float32)
+        inv = None if invalid is None else np.ascontiguousarray(invalid, dtype=np.uint8)
+        assert vc.size == self.V and ew.size == self.E
+        self._check(self.L.mnb_set_costs(self._ctx, _p(vc), _p(ew), _p(inv)))
+
+    def stats(self) -> dict:
+        s = _lib.Stats()
+        self._check(self.L.mnb_get_stats(self._ctx, C.byref(s)))
+        return dict(rounds=s.rounds, recomputes=s.recomputes, settled=s.settled, kernel_launches=s.kernel_launches,
+                    kernel_ms=s.kernel_ms)
+
+    def cancel(self):
+        self._check(self.L.mnb_cancel(self._ctx))
+
+    # -- raw device-pointer entry points (bench "value" leg) ---------------
+    def dijkstra_dev(self, seed_vertex, robot_vertex, cost_limit, goal_dist_offset, d_dist: int, d_pred: int) -> int:
+        return self._check(self.L.mnb_dijkstra(self._ctx, int(seed_vertex), int(robot_vertex), float(cost_limit),
+                                               float(goal_dist_offset), _p(d_dist), _p(d_pred)))
+
+    def cvp_dev(self, seed_face, seed_pos, robot_face, cost_limit, goal_dist_offset, d_dist: int, d_pred: int = 0,
+                d_dir: int = 0, d_cut: int = 0) -> int:
+        sp = np.ascontiguousarray(seed_pos, dtype=np.float32)
+        return self._check(self.L.mnb_cvp(self._ctx, int(seed_face), _p(sp), int(robot_face), float(cost_limit),
+                                          float(goal_dist_offset), _p(d_dist) if d_dist else None,
+                                          _p(d_pred) if d_pred else None, _p(d_dir) if d_dir else None,
+                                          _p(d_cut) if d_cut else None))
+
+    def cvp_batch_dev(self, seed_faces, seed_pos, cost_limit, d_out: int) -> int:
+        sf = np.ascontiguousarray(seed_faces, dtype=np.uint32)
+        sp = np.ascontiguousarray(seed_pos, dtype=np.float32).reshape(-1, 3)
+        return self._check(self.L.mnb_cvp_batch(self._ctx, sf.size, _p(sf), _p(sp), float(cost_limit), _p(d_out)))
+
+
+class DijkstraMeshPlanner:
+    """dijkstra_mesh_planner::DijkstraMeshPlanner -- wavefront part (dijkstra():217-398)."""
+
+    def __init__(self, mesh_map: MeshMap, cost_limit: float = 1.0, goal_dist_offset: float = 0.3):
+        self.map = mesh_map
+        self.cost_limit = cost_limit                # dijkstra_mesh_planner.h:178-187
+        self.goal_dist_offset = goal_dist_offset
+
+    def dijkstra(self, seed_vertex: int, robot_vertex: int = -1):
+        m = self.map
+        dist = np.empty(m.V, dtype=np.float32)
+        pred = np.empty(m.V, dtype=np.uint32)
+        rc = m._check(m.L.mnb_dijkstra(m._ctx, int(seed_vertex), int(robot_vertex), float(self.cost_limit),
+                                       float(self.goal_dist_offset), _p(dist), _p(pred)))
+        return dict(outcome=rc, dist=dist, pred=pred, **m.stats())
+
+
+class CVPMeshPlanner:
+    """cvp_mesh_planner::CVPMeshPlanner -- wavefront part (waveFrontPropagation():651-886)."""
+
+    def __init__(self, mesh_map: MeshMap, cost_limit: float = 1.0, goal_dist_offset: float = 0.3):
+        self.map = mesh_map
+        self.cost_limit = cost_limit                # cvp_mesh_planner.h:201-212
+        self.goal_dist_offset = goal_dist_offset
+
+    def waveFrontPropagation(self, seed_face: int, seed_pos, robot_face: int = -1):
+        m = self.map
+        sp = np.ascontiguousarray(seed_pos, dtype=np.float32)
+        dist = np.empty(m.V, dtype=np.float32)
+        pred = np.empty(m.V, dtype=np.uint32)
+        direction = np.empty(m.V, dtype=np.float32)
+        cut = np.empty(m.V, dtype=np.int32)
+        rc = m._check(m.L.mnb_cvp(m._ctx, int(seed_face), _p(sp), int(robot_face), float(self.cost_limit),
+                                  float(self.goal_dist_offset), _p(dist), _p(pred), _p(direction), _p(cut)))
+        return dict(outcome=rc, dist=dist, pred=pred, direction=direction, cutting_face=cut, **m.stats())
+
+    def waveFrontPropagationBatch(self, seed_faces, seed_pos):
+        m = self.map
+        sf = np.ascontiguousarray(seed_faces, dtype=np.uint32)
+        sp = np.ascontiguousarray(seed_pos, dtype=np.float32).reshape(-1, 3)
+        out = np.empty((sf.size, m.V), dtype=np.float32)
+        rc = m._check(m.L.mnb_cvp_batch(m._ctx, sf.size, _p(sf), _p(sp), float(self.cost_limit), _p(out)))
+        return dict(outcome=rc, dist=out, **m.stats())
+
+
+class InflationLayer:
+    """mesh_layers::InflationLayer -- waveCostInflation (inflation_layer.cpp:341-491)."""
+
+    def __init__(self, mesh_map: MeshMap, inscribed_radius=0.25, inflation_radius=0.4, lethal_value=1.0,
+                 inscribed_value=0.99, cost_scaling_factor=1.0):
+        self.map = mesh_map
+        self.config = _lib.InflationParams(inscribed_radius, inflation_radius, lethal_value, inscribed_value,
+                                           cost_scaling_factor)   # inflation_layer.h:240-248
+
+    def waveCostInflation(self, lethals, invalid=None):
+        m = self.map
+        le = np.ascontiguousarray(lethals, dtype=np.uint32)
+        inv = None if invalid is None else np.ascontiguousarray(invalid, dtype=np.uint8)
+        dist = np.empty(m.V, dtype=np.float32)
+        cost = np.empty(m.V, dtype=np.float32)
+        m._check(m.L.mnb_inflate(m._ctx, _p(le), le.size, _p(inv), C.byref(self.config), _p(dist), _p(cost)))
+        return dict(dist=dist, cost=cost, **m.stats())

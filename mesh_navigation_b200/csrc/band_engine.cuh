@@ -1,0 +1,209 @@
+// Sliding-band pull wavefront engine (sm_100a).
+//
+// What it replaces: the heap loops of the reference
+//   CVPMeshPlanner::waveFrontPropagation   cvp_mesh_planner.cpp:747-886
+//   DijkstraMeshPlanner::dijkstra          dijkstra_mesh_planner.cpp:287-348
+//   InflationLayer::waveCostInflation      inflation_layer.cpp:407-478
+// which pop one vertex at a time from lvr2::Meap and push updates to the free
+// vertex of every incident face (edge) that has all its other vertices fixed.
+//
+// B200 formulation (not a translation of the heap):
+//   * every vertex carries one 64-bit word  {d : potential, tau : pop time}.
+//     tau = max(d, pop time of the face that produced d) is the moment the
+//     sequential algorithm would have popped the vertex; event order is the
+//     lexicographic pair (tau, vertex id)  ==  the oracle's canonical heap.
+//   * a *candidate* vertex is recomputed FROM SCRATCH ("pull") from its corner
+//     records: the faces are visited in the order their later source vertex
+//     pops, and a face only fires while the candidate itself has not popped yet.
+//     That vertex-local replay reproduces the sequential result including the
+//     non-causal "back-steps" of the CVP unfolding update; the
+//     CPU simulator of exactly this rule is bit-identical to the oracle on the
+//     10k / 1M meshes (tools/sim_band.cpp).
+//   * candidates within a sliding band [lo, lo+delta) of potentials are
+//     recomputed every round; everything whose tau lies strictly below the
+//     smallest tau that changed in the round is a converged prefix and leaves
+//     the list ("settled").  One barrier per round.
+//   * one wavefront is owned by ONE thread-block cluster (CS CTAs, CS in
+//     {1,2,4,8,16}); the barrier is the hardware cluster barrier (or
+//     __syncthreads for CS==1), not a grid-wide sync, so a round costs ~1 us
+//     instead of a kernel launch.  Batches run one wavefront per cluster on all
+//     148 SMs; CS==0 selects a cooperative whole-grid group (used by the
+//     multi-source inflation wave which has few, very wide rounds).
+//   * the next round's candidate list is staged in shared memory per CTA and
+//     flushed with one global atomic per CTA per round.
+#pragma once
+#include <cooperative_groups.h>
+#include <cstdint>
+
+#include "wavefront_math.cuh"
+
+namespace mnb {
+namespace cg = cooperative_groups;
+
+constexpr uint32_t INF_BITS = 0x7f800000u;
+constexpr unsigned long long STATE_INF = ((unsigned long long)INF_BITS << 32) | INF_BITS;
+
+__device__ __forceinline__ unsigned long long pack_state(float d, float tau) {
+  return ((unsigned long long)__float_as_uint(tau) << 32) | __float_as_uint(d);
+}
+__device__ __forceinline__ float state_d(unsigned long long s) { return __uint_as_float((uint32_t)s); }
+__device__ __forceinline__ float state_tau(unsigned long long s) { return __uint_as_float((uint32_t)(s >> 32)); }
+
+// mark[] values
+constexpr uint32_t MARK_NONE = 0, MARK_CAND = 1, MARK_FIXED = 2, MARK_CAND_ACT = 3;
+
+struct GroupCtl {               // one per wavefront group, global memory
+  unsigned int count[3];        // candidate list sizes (ring over rounds)
+  unsigned int m_tau[3];        // float bits: min tau touched by a change in the round
+  unsigned int lo[3];           // float bits: min potential over surviving candidates
+  unsigned int goal_bits;       // float bits of goal_dist (cvp:738,769 / dijkstra:279,296)
+  int robot_left;               // robot-face vertices not yet settled
+  unsigned int stop;            // cancel request observed
+  unsigned int query;           // batch: query index owned by the group
+  unsigned long long rounds, recomputes, settled;
+};
+
+template <int CS>
+__device__ __forceinline__ void group_sync() {
+  if constexpr (CS == 1) {
+    __syncthreads();
+  } else if constexpr (CS == 0) {
+    cg::this_grid().sync();
+  } else {
+    cg::this_cluster().sync();
+  }
+}
+
+// per-CTA staging of appends to the next candidate list
+struct Stage {
+  static constexpr int CAP = 3072;
+  uint32_t buf[CAP];
+  unsigned int n;
+  unsigned int base;
+  unsigned int m_tau;
+  unsigned int lo;
+};
+
+__device__ __forceinline__ void stage_push(Stage& st, uint32_t v, uint32_t* list_next, unsigned int* count_next) {
+  const unsigned int p = atomicAdd(&st.n, 1u);
+  if (p < Stage::CAP) st.buf[p] = v;
+  else list_next[atomicAdd(count_next, 1u)] = v;  // overflow: straight to global
+}
+
+// flush the CTA stage to the global list (all threads of the CTA call this)
+__device__ __forceinline__ void stage_flush(Stage& st, uint32_t* list_next, unsigned int* count_next,
+                                            unsigned int* g_m_tau, unsigned int* g_lo) {
+  __syncthreads();
+  const unsigned int n = st.n < Stage::CAP ? st.n : Stage::CAP;
+  if (threadIdx.x == 0) {
+    st.base = n ? atomicAdd(count_next, n) : 0u;
+    if (st.m_tau != INF_BITS) atomicMin(g_m_tau, st.m_tau);
+    if (st.lo != INF_BITS) atomicMin(g_lo, st.lo);
+  }
+  __syncthreads();
+  const unsigned int base = st.base;
+  for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) list_next[base + i] = st.buf[i];
+  __syncthreads();
+  if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; }
+  __syncthreads();
+}
+
+// -----------------------------------------------------------------------------
+// The round loop.  Preconditions (established by the caller inside the kernel,
+// followed by a group_sync): states of seeds written, mark[seed] = MARK_FIXED,
+// list0 holds the first candidates (mark = MARK_CAND), ctl->count[0] = |list0|,
+// ctl->count[1] = ctl->count[2] = 0, ctl->m_tau[0] = ctl->lo[0] = INF,
+// ctl->m_tau[1] = ctl->lo[1] = INF, ctl->m_tau[2] = 0, ctl->lo[2] = bits(seed_min).
+//
+// Problem P provides
+//   bool  recompute(c, band_end, goal, d_old, tau_old, &d_new, &tau_new)  -> true if changed
+//         (writes state/aux itself)
+//   void  activate(c, push)   calls push(x) for every vertex x that shares a face/edge with c
+//   bool  eligible(x)         may x ever receive a label
+// -----------------------------------------------------------------------------
+template <int CS, class P>
+__device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_t* list1, uint32_t* mark,
+                                Stage& st, const float delta, const uint32_t gthreads, const uint32_t gtid,
+                                const int has_robot, const uint32_t r0, const uint32_t r1, const uint32_t r2,
+                                const double goal_dist_offset, const volatile int* cancel_flag,
+                                const float band_end_init) {
+  float band_end_prev = band_end_init;  // > every seed potential: seeds are available from round 0
+  unsigned long long my_recomputes = 0, my_settled = 0;
+  uint32_t r = 0;
+  for (;; ++r) {
+    const uint32_t slot = r % 3, prev = (r + 2) % 3, next = (r + 1) % 3;
+    const unsigned int n = __ldcg(&ctl->count[slot]);
+    const float m_prev = __uint_as_float(__ldcg(&ctl->m_tau[prev]));
+    const float lo_prev = __uint_as_float(__ldcg(&ctl->lo[prev]));
+    const float goal = __uint_as_float(__ldcg(&ctl->goal_bits));
+    const unsigned int stop = __ldcg(&ctl->stop);
+    if (n == 0 || stop) break;
+    if (r > 0 && __float_as_uint(m_prev) == INF_BITS &&
+        (__float_as_uint(lo_prev) == INF_BITS || lo_prev > goal)) break;
+    float band_end = lo_prev + delta;
+    if (!(band_end > band_end_prev)) band_end = band_end_prev;
+    uint32_t* list_r = (r & 1) ? list1 : list0;
+    uint32_t* list_n = (r & 1) ? list0 : list1;
+    if (gtid == 0) {
+      ctl->count[(r + 2) % 3] = 0;         // list r+2's counter (free during this round)
+      ctl->m_tau[next] = INF_BITS;
+      ctl->lo[next] = INF_BITS;
+      if (cancel_flag && (r & 31) == 0 && *cancel_flag) ctl->stop = 1;
+    }
+    float my_mtau = __uint_as_float(INF_BITS), my_lo = __uint_as_float(INF_BITS);
+    for (unsigned int i = gtid; i < n; i += gthreads) {
+      const uint32_t c = __ldcg(&list_r[i]);
+      const unsigned long long s = prob.load_state(c);
+      const float d = state_d(s), tau = state_tau(s);
+      if (tau < m_prev && tau < band_end_prev) {
+        // converged prefix: the sequential algorithm has popped c with exactly this label
+        mark[c] = MARK_FIXED;
+        my_settled++;
+        if (has_robot && (c == r0 || c == r1 || c == r2)) {
+          if (atomicSub(&ctl->robot_left, 1) == 1) {
+            // c is not necessarily the last of the three in event order: take the latest (tau,id)
+            float bd = d, bt = tau; uint32_t bi = c;
+            const uint32_t rv[3] = {r0, r1, r2};
+            for (int k = 0; k < 3; ++k) {
+              const unsigned long long so = prob.load_state(rv[k]);
+              const float to = state_tau(so);
+              if (to > bt || (to == bt && rv[k] > bi)) { bt = to; bi = rv[k]; bd = state_d(so); }
+            }
+            ctl->goal_bits = __float_as_uint((float)((double)bd + goal_dist_offset));
+          }
+        }
+        continue;
+      }
+      float nd, ntau;
+      my_recomputes++;
+      if (prob.recompute(c, band_end, goal, d, tau, nd, ntau)) my_mtau = fminf(my_mtau, fminf(tau, ntau));
+      my_lo = fminf(my_lo, nd);
+      stage_push(st, c, list_n, &ctl->count[next]);
+      // a vertex that holds a finite label pulls its neighbours into the candidate set (once)
+      if (__float_as_uint(nd) != INF_BITS && mark[c] == MARK_CAND) {
+        mark[c] = MARK_CAND_ACT;
+        prob.activate(c, [&](uint32_t x) {
+          if (__ldcg(&mark[x]) == MARK_NONE && prob.eligible(x) && atomicCAS(&mark[x], MARK_NONE, MARK_CAND) == MARK_NONE)
+            stage_push(st, x, list_n, &ctl->count[next]);
+        });
+      }
+    }
+    {
+      const unsigned int wm = __reduce_min_sync(0xffffffffu, __float_as_uint(my_mtau));
+      const unsigned int wl = __reduce_min_sync(0xffffffffu, __float_as_uint(my_lo));
+      if ((threadIdx.x & 31) == 0) {
+        if (wm != INF_BITS) atomicMin(&st.m_tau, wm);
+        if (wl != INF_BITS) atomicMin(&st.lo, wl);
+      }
+    }
+    stage_flush(st, list_n, &ctl->count[next], &ctl->m_tau[slot], &ctl->lo[slot]);
+    band_end_prev = band_end;
+    group_sync<CS>();
+  }
+  // statistics
+  atomicAdd(&ctl->recomputes, my_recomputes);
+  atomicAdd(&ctl->settled, my_settled);
+  if (gtid == 0) ctl->rounds += r;
+}
+
+}  // namespace mnb

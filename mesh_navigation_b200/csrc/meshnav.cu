@@ -1,0 +1,699 @@
+// libmeshnav_b200.so -- C ABI (include/meshnav_b200.h) over the sm_100a kernels.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -std=c++17
+//             -Xcompiler -fPIC -shared -o libmeshnav_b200.so meshnav.cu
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/meshnav_b200.h"
+#include "band_engine.cuh"
+#include "problems.cuh"
+#include "topology.hpp"
+
+using namespace mnb;
+
+// ============================================================================
+// small map kernels
+// ============================================================================
+// lvr2::calcVertexDistances equivalent (mesh_map.cpp:404-425): Euclidean edge length, float.
+__global__ void k_edge_dist(const float* __restrict__ pos, const uint32_t* __restrict__ edges, uint32_t E,
+                            float* __restrict__ out) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const uint32_t a = edges[2 * (size_t)e], b = edges[2 * (size_t)e + 1];
+  const float dx = pos[3 * (size_t)a] - pos[3 * (size_t)b];
+  const float dy = pos[3 * (size_t)a + 1] - pos[3 * (size_t)b + 1];
+  const float dz = pos[3 * (size_t)a + 2] - pos[3 * (size_t)b + 2];
+  out[e] = sqrtf(dx * dx + dy * dy + dz * dz);
+}
+
+// MeshMap::computeEdgeWeights (mesh_map.cpp:517-561)
+__global__ void k_edge_weights(const float* __restrict__ cost, const uint32_t* __restrict__ edges,
+                               const float* __restrict__ dist, double factor, uint32_t E, float* __restrict__ out) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const float c1 = cost[edges[2 * (size_t)e]], c2 = cost[edges[2 * (size_t)e + 1]];
+  if (isinf(c1) || isinf(c2)) {
+    out[e] = __uint_as_float(INF_BITS);
+  } else {
+    const float vertex_dist = dist[e];
+    const float edge_cost = (float)((double)(vertex_dist * (c1 + c2)) / 2.0);   // :550 (float product, /2.0 in double)
+    out[e] = (float)((double)vertex_dist + factor * (double)edge_cost);         // :552
+  }
+}
+
+// per-corner weight records {w(v1,v2), w(v1,c), w(v2,c), 0}
+__global__ void k_gather_corner_w(const uint4* __restrict__ cor_eid, const float* __restrict__ w, size_t NC,
+                                  float4* __restrict__ out) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= NC) return;
+  const uint4 e = cor_eid[k];
+  out[k] = make_float4(w[e.x], w[e.y], w[e.z], 0.0f);
+}
+
+// per-directed-edge records {neighbour, weight bits}
+__global__ void k_gather_adj_w(const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ eid,
+                               const float* __restrict__ w, size_t NA, uint2* __restrict__ out) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= NA) return;
+  out[k] = make_uint2(nbr[k], __float_as_uint(w[eid[k]]));
+}
+
+// ============================================================================
+// wavefront kernels
+// ============================================================================
+struct WaveWorkspace {     // per group (index g): state + g*V etc.
+  unsigned long long* state;
+  uint32_t* mark;
+  uint32_t* list0;
+  uint32_t* list1;
+  GroupCtl* ctl;
+};
+
+struct CvpKernelArgs {
+  uint32_t V;
+  const float* pos;
+  const uint32_t* faces;
+  const uint32_t* cor_ptr; const int4* cor_idx; const float4* cor_w;
+  const float* cost; const uint8_t* invalid;
+  WaveWorkspace ws;
+  uint32_t n_queries;
+  const uint32_t* seed_faces;   // [n_queries] device
+  const float* seed_pos;        // [3 n_queries] device
+  long long robot_face;         // single query only, -1 = none
+  double cost_limit, goal_dist_offset;
+  float delta;
+  float* out_dist;              // [n_queries][V]
+  uint32_t* out_pred;           // single query or null
+  float* out_dir;
+  int32_t* out_cut;
+  unsigned int* next_query;
+  const int* cancel_flag;
+};
+
+template <int CS>
+__device__ __forceinline__ void group_coords(uint32_t& g, uint32_t& gthreads, uint32_t& gtid) {
+  if constexpr (CS == 0) {
+    g = 0; gthreads = gridDim.x * blockDim.x; gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  } else {
+    g = blockIdx.x / CS; gthreads = CS * blockDim.x; gtid = (blockIdx.x % CS) * blockDim.x + threadIdx.x;
+  }
+}
+
+__device__ __forceinline__ void ctl_reset(GroupCtl* ctl, unsigned int n0, float seed_min) {
+  ctl->count[0] = n0; ctl->count[1] = 0; ctl->count[2] = 0;
+  ctl->m_tau[0] = INF_BITS; ctl->m_tau[1] = INF_BITS; ctl->m_tau[2] = 0u;
+  ctl->lo[0] = INF_BITS; ctl->lo[1] = INF_BITS; ctl->lo[2] = __float_as_uint(seed_min);
+  ctl->goal_bits = INF_BITS; ctl->robot_left = 0; ctl->stop = 0;
+}
+
+template <int CS>
+__global__ void __launch_bounds__(512, 1) k_cvp(const CvpKernelArgs a) {
+  __shared__ Stage st;
+  uint32_t g, gthreads, gtid;
+  group_coords<CS>(g, gthreads, gtid);
+  const uint32_t V = a.V;
+  unsigned long long* state = a.ws.state + (size_t)g * V;
+  uint32_t* mark = a.ws.mark + (size_t)g * V;
+  uint32_t* list0 = a.ws.list0 + (size_t)g * V;
+  uint32_t* list1 = a.ws.list1 + (size_t)g * V;
+  GroupCtl* ctl = a.ws.ctl + g;
+  if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; }
+  __syncthreads();
+
+  for (;;) {
+    if (gtid == 0) ctl->query = atomicAdd(a.next_query, 1u);
+    group_sync<CS>();
+    const uint32_t q = __ldcg(&ctl->query);
+    if (q >= a.n_queries) break;
+    const bool single = (a.n_queries == 1);
+    uint32_t* pred = single ? a.out_pred : nullptr;
+    float* dir = single ? a.out_dir : nullptr;
+    int32_t* cut = single ? a.out_cut : nullptr;
+
+    for (uint32_t v = gtid; v < V; v += gthreads) {
+      state[v] = STATE_INF; mark[v] = MARK_NONE;
+      if (pred) { pred[v] = v; dir[v] = 0.0f; cut[v] = -1; }
+    }
+    group_sync<CS>();
+
+    const uint32_t sf = a.seed_faces[q];
+    const uint32_t s0 = a.faces[3 * (size_t)sf], s1 = a.faces[3 * (size_t)sf + 1], s2 = a.faces[3 * (size_t)sf + 2];
+    CvpProblem prob;
+    prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_w = a.cor_w; prob.cost = a.cost; prob.invalid = a.invalid;
+    prob.state = state; prob.pred = pred; prob.dir = dir; prob.cut = cut; prob.cost_limit = a.cost_limit;
+    prob.s0 = s0; prob.s1 = s1; prob.s2 = s2; prob.seed_noexpand = 0;
+    float sd[3];
+    {
+      const uint32_t sv[3] = {s0, s1, s2};
+      for (int k = 0; k < 3; ++k) {   // cvp:719-728
+        const float dx = a.seed_pos[3 * (size_t)q] - a.pos[3 * (size_t)sv[k]];
+        const float dy = a.seed_pos[3 * (size_t)q + 1] - a.pos[3 * (size_t)sv[k] + 1];
+        const float dz = a.seed_pos[3 * (size_t)q + 2] - a.pos[3 * (size_t)sv[k] + 2];
+        sd[k] = sqrtf(dx * dx + dy * dy + dz * dz);
+        const bool noexp = ((double)a.cost[sv[k]] >= a.cost_limit) || (a.invalid && a.invalid[sv[k]]);  // cvp:757,760
+        if (noexp) prob.seed_noexpand |= (1u << k);
+      }
+    }
+    const float seed_min = fminf(sd[0], fminf(sd[1], sd[2]));
+    const float seed_max = fmaxf(sd[0], fmaxf(sd[1], sd[2]));
+    uint32_t r0 = 0xffffffffu, r1 = 0xffffffffu, r2 = 0xffffffffu;
+    const int has_robot = single && a.robot_face >= 0;
+    if (has_robot) {
+      r0 = a.faces[3 * (size_t)a.robot_face]; r1 = a.faces[3 * (size_t)a.robot_face + 1]; r2 = a.faces[3 * (size_t)a.robot_face + 2];
+    }
+    if (gtid == 0) {
+      const uint32_t sv[3] = {s0, s1, s2};
+      for (int k = 0; k < 3; ++k) {
+        state[sv[k]] = pack_state(sd[k], sd[k]);
+        mark[sv[k]] = MARK_FIXED;
+        if (cut) cut[sv[k]] = (int32_t)sf;               // cvp:725
+      }
+      unsigned int n0 = 0;
+      for (int k = 0; k < 3; ++k)
+        prob.activate(sv[k], [&](uint32_t x) {
+          if (mark[x] == MARK_NONE && prob.eligible(x)) { mark[x] = MARK_CAND; list0[n0++] = x; }
+        });
+      ctl_reset(ctl, n0, seed_min);
+      if (has_robot) {
+        int left = 0; const uint32_t rv[3] = {r0, r1, r2};
+        for (int k = 0; k < 3; ++k) if (mark[rv[k]] != MARK_FIXED) left++;
+        ctl->robot_left = left;
+        if (left == 0) {  // robot face == seed face: cutoff armed when the last seed pops (cvp:763-771)
+          ctl->goal_bits = __float_as_uint((float)((double)seed_max + a.goal_dist_offset));
+        }
+      }
+    }
+    group_sync<CS>();
+    float delta = a.delta;
+    if (has_robot && a.goal_dist_offset < (double)delta) delta = (float)fmax(a.goal_dist_offset, 1e-4);
+    run_band_rounds<CS>(prob, ctl, list0, list1, mark, st, delta, gthreads, gtid, has_robot, r0, r1, r2,
+                        a.goal_dist_offset, a.cancel_flag, nextafterf(seed_max, __uint_as_float(INF_BITS)));
+    group_sync<CS>();
+    if (a.out_dist) {
+      float* od = a.out_dist + (size_t)q * V;
+      for (uint32_t v = gtid; v < V; v += gthreads) od[v] = state_d(state[v]);
+    }
+    group_sync<CS>();
+  }
+}
+
+struct DijkstraKernelArgs {
+  uint32_t V;
+  const uint32_t* adj_ptr; const uint2* adj_nw;
+  const float* cost; const uint8_t* invalid;
+  WaveWorkspace ws;
+  uint32_t seed_vertex; long long robot_vertex;
+  double cost_limit, goal_dist_offset;
+  float delta;
+  float* out_dist; uint32_t* out_pred;
+  const int* cancel_flag;
+};
+
+template <int CS>
+__global__ void __launch_bounds__(512, 1) k_dijkstra(const DijkstraKernelArgs a) {
+  __shared__ Stage st;
+  uint32_t g, gthreads, gtid;
+  group_coords<CS>(g, gthreads, gtid);
+  const uint32_t V = a.V;
+  unsigned long long* state = a.ws.state;
+  uint32_t* mark = a.ws.mark; uint32_t* list0 = a.ws.list0; uint32_t* list1 = a.ws.list1;
+  GroupCtl* ctl = a.ws.ctl;
+  if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; }
+  __syncthreads();
+  for (uint32_t v = gtid; v < V; v += gthreads) { state[v] = STATE_INF; mark[v] = MARK_NONE; a.out_pred[v] = v; }
+  group_sync<CS>();
+  DijkstraProblem prob;
+  prob.adj_ptr = a.adj_ptr; prob.adj_nw = a.adj_nw; prob.cost = a.cost; prob.invalid = a.invalid;
+  prob.state = state; prob.pred = a.out_pred; prob.cost_limit = a.cost_limit;
+  const int has_robot = a.robot_vertex >= 0;
+  const uint32_t rv = has_robot ? (uint32_t)a.robot_vertex : 0xffffffffu;
+  if (gtid == 0) {
+    state[a.seed_vertex] = pack_state(0.0f, 0.0f);     // dijkstra:276
+    mark[a.seed_vertex] = MARK_FIXED;
+    unsigned int n0 = 0;
+    prob.activate(a.seed_vertex, [&](uint32_t x) {
+      if (mark[x] == MARK_NONE && prob.eligible(x)) { mark[x] = MARK_CAND; list0[n0++] = x; }
+    });
+    ctl_reset(ctl, n0, 0.0f);
+    if (has_robot) ctl->robot_left = 1;
+  }
+  group_sync<CS>();
+  float delta = a.delta;
+  if (has_robot && a.goal_dist_offset < (double)delta) delta = (float)fmax(a.goal_dist_offset, 1e-4);
+  run_band_rounds<CS>(prob, ctl, list0, list1, mark, st, delta, gthreads, gtid, has_robot, rv, rv, rv,
+                      a.goal_dist_offset, a.cancel_flag, 1e-30f);
+  group_sync<CS>();
+  for (uint32_t v = gtid; v < V; v += gthreads) a.out_dist[v] = state_d(state[v]);
+}
+
+// ============================================================================
+// host side
+// ============================================================================
+struct mnb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int ptr_mode = MNB_PTR_HOST;
+  int sm_count = 0;
+  // mesh
+  uint32_t V = 0, F = 0, E = 0;
+  size_t NC = 0, NA = 0;
+  HostTopology topo;
+  float* d_pos = nullptr; uint32_t* d_faces = nullptr; uint32_t* d_edges = nullptr;
+  uint32_t* d_cor_ptr = nullptr; int4* d_cor_idx = nullptr; uint4* d_cor_eid = nullptr;
+  float4* d_cor_w = nullptr; float4* d_cor_wd = nullptr;
+  uint32_t* d_adj_ptr = nullptr; uint32_t* d_adj_nbr = nullptr; uint32_t* d_adj_eid = nullptr; uint2* d_adj_nw = nullptr;
+  float* d_edge_dist = nullptr; float* d_edge_w = nullptr; float* d_cost = nullptr; uint8_t* d_invalid = nullptr;
+  bool has_invalid = false, costs_set = false;
+  // workspace
+  uint32_t ws_groups = 0;
+  WaveWorkspace ws{};
+  unsigned int* d_next_query = nullptr;
+  int* h_cancel = nullptr; int* d_cancel = nullptr;
+  // scratch outputs for host-pointer mode
+  float* d_out_dist = nullptr; size_t out_dist_cap = 0;
+  uint32_t* d_out_pred = nullptr; float* d_out_dir = nullptr; int32_t* d_out_cut = nullptr;
+  uint32_t* d_seed_faces = nullptr; float* d_seed_pos = nullptr; uint32_t seed_cap = 0;
+  // tuning
+  float delta = 0.3f; int cluster = 8; int threads = 512;
+  mnb_stats stats{};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+#define CK(call)                                                                   \
+  do {                                                                             \
+    cudaError_t e_ = (call);                                                       \
+    if (e_ != cudaSuccess) {                                                       \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);               \
+      return MNB_E_CUDA;                                                           \
+    }                                                                              \
+  } while (0)
+
+template <class T>
+static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T) > 0 ? n * sizeof(T) : 1); }
+template <class T>
+static void dfree(T*& p) { if (p) cudaFree(p); p = nullptr; }
+
+static void free_mesh(mnb_ctx* c) {
+  dfree(c->d_pos); dfree(c->d_faces); dfree(c->d_edges); dfree(c->d_cor_ptr); dfree(c->d_cor_idx); dfree(c->d_cor_eid);
+  dfree(c->d_cor_w); dfree(c->d_cor_wd); dfree(c->d_adj_ptr); dfree(c->d_adj_nbr); dfree(c->d_adj_eid); dfree(c->d_adj_nw);
+  dfree(c->d_edge_dist); dfree(c->d_edge_w); dfree(c->d_cost); dfree(c->d_invalid);
+  dfree(c->ws.state); dfree(c->ws.mark); dfree(c->ws.list0); dfree(c->ws.list1); dfree(c->ws.ctl);
+  c->ws_groups = 0;
+  dfree(c->d_out_dist); c->out_dist_cap = 0; dfree(c->d_out_pred); dfree(c->d_out_dir); dfree(c->d_out_cut);
+  c->costs_set = false;
+}
+
+static int32_t ensure_workspace(mnb_ctx* ctx, uint32_t groups) {
+  if (groups <= ctx->ws_groups) return MNB_OK;
+  dfree(ctx->ws.state); dfree(ctx->ws.mark); dfree(ctx->ws.list0); dfree(ctx->ws.list1); dfree(ctx->ws.ctl);
+  ctx->ws_groups = 0;
+  const size_t n = (size_t)groups * ctx->V;
+  CK(dalloc(&ctx->ws.state, n)); CK(dalloc(&ctx->ws.mark, n)); CK(dalloc(&ctx->ws.list0, n)); CK(dalloc(&ctx->ws.list1, n));
+  CK(dalloc(&ctx->ws.ctl, groups));
+  ctx->ws_groups = groups;
+  return MNB_OK;
+}
+
+extern "C" {
+
+int32_t mnb_create(int32_t device, mnb_ctx** out_ctx) {
+  if (!out_ctx) return MNB_E_ARG;
+  *out_ctx = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return MNB_E_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MNB_E_CUDA;
+  if (prop.major < 10) return MNB_E_CUDA;   // sm_100a only; no fallback path exists
+  if (cudaSetDevice(device) != cudaSuccess) return MNB_E_CUDA;
+  mnb_ctx* c = new mnb_ctx();
+  c->device = device; c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MNB_E_CUDA; }
+  cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+  cudaMalloc((void**)&c->d_next_query, sizeof(unsigned int));
+  if (cudaHostAlloc((void**)&c->h_cancel, sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+    *c->h_cancel = 0;
+    cudaHostGetDevicePointer((void**)&c->d_cancel, c->h_cancel, 0);
+  }
+  *out_ctx = c;
+  return MNB_OK;
+}
+
+void mnb_destroy(mnb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_mesh(ctx);
+  dfree(ctx->d_next_query); dfree(ctx->d_seed_faces); dfree(ctx->d_seed_pos);
+  if (ctx->h_cancel) cudaFreeHost(ctx->h_cancel);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* mnb_last_error(mnb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int32_t mnb_set_pointer_mode(mnb_ctx* ctx, int32_t mode) {
+  if (!ctx || (mode != MNB_PTR_HOST && mode != MNB_PTR_DEVICE)) return MNB_E_ARG;
+  ctx->ptr_mode = mode; return MNB_OK;
+}
+void* mnb_stream(mnb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint32_t mnb_num_vertices(mnb_ctx* ctx) { return ctx ? ctx->V : 0; }
+uint32_t mnb_num_faces(mnb_ctx* ctx) { return ctx ? ctx->F : 0; }
+uint32_t mnb_num_edges(mnb_ctx* ctx) { return ctx ? ctx->E : 0; }
+
+int32_t mnb_set_tuning(mnb_ctx* ctx, float band_delta, int32_t cluster_size, int32_t threads_per_cta) {
+  if (!ctx) return MNB_E_ARG;
+  if (band_delta > 0) ctx->delta = band_delta;
+  if (cluster_size == 1 || cluster_size == 2 || cluster_size == 4 || cluster_size == 8 || cluster_size == 16)
+    ctx->cluster = cluster_size;
+  else if (cluster_size != 0) return MNB_E_ARG;
+  if (threads_per_cta == 128 || threads_per_cta == 256 || threads_per_cta == 512) ctx->threads = threads_per_cta;
+  else if (threads_per_cta != 0) return MNB_E_ARG;
+  return MNB_OK;
+}
+
+int32_t mnb_get_stats(mnb_ctx* ctx, mnb_stats* out) {
+  if (!ctx || !out) return MNB_E_ARG;
+  *out = ctx->stats; return MNB_OK;
+}
+
+int32_t mnb_set_mesh(mnb_ctx* ctx, uint32_t V, uint32_t F, const float* pos, const uint32_t* faces,
+                     const uint32_t* edges, uint32_t E) {
+  if (!ctx || !pos || !faces || V == 0 || F == 0) return MNB_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  free_mesh(ctx);
+  try {
+    ctx->topo.build(V, F, faces, edges, E);
+  } catch (const std::exception& ex) {
+    ctx->err = ex.what();
+    return MNB_E_ARG;
+  }
+  HostTopology& T = ctx->topo;
+  ctx->V = V; ctx->F = F; ctx->E = T.E; ctx->NC = T.cor_v1.size(); ctx->NA = T.vadj_nbr.size();
+  const size_t NC = ctx->NC, NA = ctx->NA;
+  CK(dalloc(&ctx->d_pos, 3 * (size_t)V)); CK(dalloc(&ctx->d_faces, 3 * (size_t)F)); CK(dalloc(&ctx->d_edges, 2 * (size_t)T.E));
+  CK(dalloc(&ctx->d_cor_ptr, (size_t)V + 1)); CK(dalloc(&ctx->d_cor_idx, NC)); CK(dalloc(&ctx->d_cor_eid, NC));
+  CK(dalloc(&ctx->d_cor_w, NC)); CK(dalloc(&ctx->d_cor_wd, NC));
+  CK(dalloc(&ctx->d_adj_ptr, (size_t)V + 1)); CK(dalloc(&ctx->d_adj_nbr, NA)); CK(dalloc(&ctx->d_adj_eid, NA)); CK(dalloc(&ctx->d_adj_nw, NA));
+  CK(dalloc(&ctx->d_edge_dist, (size_t)T.E)); CK(dalloc(&ctx->d_edge_w, (size_t)T.E)); CK(dalloc(&ctx->d_cost, (size_t)V));
+  CK(dalloc(&ctx->d_invalid, (size_t)V));
+  CK(cudaMemcpyAsync(ctx->d_pos, pos, sizeof(float) * 3 * (size_t)V, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_faces, faces, sizeof(uint32_t) * 3 * (size_t)F, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_edges, T.edges.data(), sizeof(uint32_t) * 2 * (size_t)T.E, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_cor_ptr, T.vcor_ptr.data(), sizeof(uint32_t) * ((size_t)V + 1), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_adj_ptr, T.vadj_ptr.data(), sizeof(uint32_t) * ((size_t)V + 1), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_adj_nbr, T.vadj_nbr.data(), sizeof(uint32_t) * NA, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_adj_eid, T.vadj_eid.data(), sizeof(uint32_t) * NA, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    std::vector<int4> idx(NC); std::vector<uint4> eid(NC);
+    for (size_t k = 0; k < NC; ++k) {
+      idx[k] = make_int4((int)T.cor_v1[k], (int)T.cor_v2[k], (int)T.cor_face[k], 0);
+      eid[k] = make_uint4(T.cor_ec[k], T.cor_eb[k], T.cor_ea[k], 0);
+    }
+    CK(cudaMemcpyAsync(ctx->d_cor_idx, idx.data(), sizeof(int4) * NC, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_cor_eid, eid.data(), sizeof(uint4) * NC, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  // the host copies of the big per-corner arrays are no longer needed
+  std::vector<uint32_t>().swap(T.cor_v1); std::vector<uint32_t>().swap(T.cor_v2); std::vector<uint32_t>().swap(T.cor_face);
+  std::vector<uint32_t>().swap(T.cor_ec); std::vector<uint32_t>().swap(T.cor_eb); std::vector<uint32_t>().swap(T.cor_ea);
+  std::vector<uint32_t>().swap(T.vadj_nbr); std::vector<uint32_t>().swap(T.vadj_eid); std::vector<uint32_t>().swap(T.face_edges);
+  k_edge_dist<<<(T.E + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_pos, ctx->d_edges, T.E, ctx->d_edge_dist);
+  k_gather_corner_w<<<(unsigned)((NC + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_cor_eid, ctx->d_edge_dist, NC, ctx->d_cor_wd);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MNB_OK;
+}
+
+int32_t mnb_get_edges(mnb_ctx* ctx, uint32_t* out_edges) {
+  if (!ctx || !out_edges || !ctx->V) return MNB_E_ARG;
+  std::memcpy(out_edges, ctx->topo.edges.data(), sizeof(uint32_t) * 2 * (size_t)ctx->E);
+  return MNB_OK;
+}
+
+static cudaMemcpyKind in_kind(mnb_ctx* c) { return c->ptr_mode == MNB_PTR_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice; }
+static cudaMemcpyKind out_kind(mnb_ctx* c) { return c->ptr_mode == MNB_PTR_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice; }
+
+int32_t mnb_get_edge_distances(mnb_ctx* ctx, float* out) {
+  if (!ctx || !out || !ctx->V) return MNB_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(out, ctx->d_edge_dist, sizeof(float) * (size_t)ctx->E, out_kind(ctx), ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MNB_OK;
+}
+
+static int32_t install_weights(mnb_ctx* ctx) {
+  k_gather_corner_w<<<(unsigned)((ctx->NC + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_cor_eid, ctx->d_edge_w, ctx->NC, ctx->d_cor_w);
+  k_gather_adj_w<<<(unsigned)((ctx->NA + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_adj_nbr, ctx->d_adj_eid, ctx->d_edge_w, ctx->NA, ctx->d_adj_nw);
+  CK(cudaGetLastError());
+  ctx->costs_set = true;
+  return MNB_OK;
+}
+
+int32_t mnb_compute_edge_weights(mnb_ctx* ctx, const float* vertex_costs, double edge_cost_factor, float* out_w) {
+  if (!ctx || !vertex_costs || !ctx->V) return MNB_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->d_cost, vertex_costs, sizeof(float) * (size_t)ctx->V, in_kind(ctx), ctx->stream));
+  k_edge_weights<<<(ctx->E + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_cost, ctx->d_edges, ctx->d_edge_dist, edge_cost_factor, ctx->E, ctx->d_edge_w);
+  CK(cudaGetLastError());
+  int32_t rc = install_weights(ctx);
+  if (rc != MNB_OK) return rc;
+  if (out_w) CK(cudaMemcpyAsync(out_w, ctx->d_edge_w, sizeof(float) * (size_t)ctx->E, out_kind(ctx), ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MNB_OK;
+}
+
+int32_t mnb_set_costs(mnb_ctx* ctx, const float* vertex_costs, const float* edge_weights, const uint8_t* invalid) {
+  if (!ctx || !vertex_costs || !edge_weights || !ctx->V) return MNB_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->d_cost, vertex_costs, sizeof(float) * (size_t)ctx->V, in_kind(ctx), ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_edge_w, edge_weights, sizeof(float) * (size_t)ctx->E, in_kind(ctx), ctx->stream));
+  if (invalid) CK(cudaMemcpyAsync(ctx->d_invalid, invalid, (size_t)ctx->V, in_kind(ctx), ctx->stream));
+  ctx->has_invalid = invalid != nullptr;
+  int32_t rc = install_weights(ctx);
+  if (rc != MNB_OK) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MNB_OK;
+}
+
+int32_t mnb_cancel(mnb_ctx* ctx) {
+  if (!ctx || !ctx->h_cancel) return MNB_E_ARG;
+  *(volatile int*)ctx->h_cancel = 1;
+  return MNB_OK;
+}
+
+}  // extern "C"
+
+template <class KArgs>
+static cudaError_t launch_cluster(void (*kern)(const KArgs), const KArgs& args, int cs, unsigned blocks, int threads,
+                                  cudaStream_t stream) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = cs > 1 ? 1 : 0;
+  if (cs > 8) {
+    cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, args);
+}
+
+static int32_t launch_cvp(mnb_ctx* ctx, const CvpKernelArgs& a, int cs, unsigned groups) {
+  cudaError_t e;
+  const unsigned blocks = groups * cs;
+  switch (cs) {
+    case 1: e = launch_cluster(k_cvp<1>, a, 1, blocks, ctx->threads, ctx->stream); break;
+    case 2: e = launch_cluster(k_cvp<2>, a, 2, blocks, ctx->threads, ctx->stream); break;
+    case 4: e = launch_cluster(k_cvp<4>, a, 4, blocks, ctx->threads, ctx->stream); break;
+    case 8: e = launch_cluster(k_cvp<8>, a, 8, blocks, ctx->threads, ctx->stream); break;
+    default: e = launch_cluster(k_cvp<16>, a, 16, blocks, ctx->threads, ctx->stream); break;
+  }
+  if (e != cudaSuccess) { ctx->err = std::string("cvp launch: ") + cudaGetErrorString(e); return MNB_E_CUDA; }
+  return MNB_OK;
+}
+
+static int32_t finish_stats(mnb_ctx* ctx, unsigned groups, unsigned launches) {
+  std::vector<GroupCtl> h(groups);
+  CK(cudaMemcpyAsync(h.data(), ctx->ws.ctl, sizeof(GroupCtl) * groups, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.rounds = 0; ctx->stats.recomputes = 0; ctx->stats.settled = 0;
+  for (auto& c : h) { ctx->stats.rounds += c.rounds; ctx->stats.recomputes += c.recomputes; ctx->stats.settled += c.settled; }
+  ctx->stats.kernel_launches = launches;
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->stats.kernel_ms = ms;
+  return MNB_OK;
+}
+
+static int32_t ensure_out(mnb_ctx* ctx, size_t n_dist, bool aux) {
+  if (n_dist > ctx->out_dist_cap) { dfree(ctx->d_out_dist); CK(dalloc(&ctx->d_out_dist, n_dist)); ctx->out_dist_cap = n_dist; }
+  if (aux && !ctx->d_out_pred) {
+    CK(dalloc(&ctx->d_out_pred, (size_t)ctx->V)); CK(dalloc(&ctx->d_out_dir, (size_t)ctx->V)); CK(dalloc(&ctx->d_out_cut, (size_t)ctx->V));
+  }
+  return MNB_OK;
+}
+
+static int32_t ensure_seeds(mnb_ctx* ctx, uint32_t n) {
+  if (n > ctx->seed_cap) {
+    dfree(ctx->d_seed_faces); dfree(ctx->d_seed_pos);
+    CK(dalloc(&ctx->d_seed_faces, (size_t)n)); CK(dalloc(&ctx->d_seed_pos, 3 * (size_t)n));
+    ctx->seed_cap = n;
+  }
+  return MNB_OK;
+}
+
+static void fill_cvp_args(mnb_ctx* ctx, CvpKernelArgs& a) {
+  a.V = ctx->V; a.pos = ctx->d_pos; a.faces = ctx->d_faces; a.cor_ptr = ctx->d_cor_ptr; a.cor_idx = ctx->d_cor_idx;
+  a.cor_w = ctx->d_cor_w; a.cost = ctx->d_cost; a.invalid = ctx->has_invalid ? ctx->d_invalid : nullptr; a.ws = ctx->ws;
+  a.seed_faces = ctx->d_seed_faces; a.seed_pos = ctx->d_seed_pos; a.delta = ctx->delta; a.next_query = ctx->d_next_query;
+  a.cancel_flag = ctx->d_cancel;
+}
+
+extern "C" {
+
+int32_t mnb_cvp(mnb_ctx* ctx, uint32_t seed_face, const float seed_pos[3], int64_t robot_face, double cost_limit,
+                double goal_dist_offset, float* out_dist, uint32_t* out_pred, float* out_direction, int32_t* out_cut) {
+  if (!ctx || !seed_pos || !ctx->V) return MNB_E_ARG;
+  if (!ctx->costs_set) { ctx->err = "mnb_set_costs / mnb_compute_edge_weights not called"; return MNB_E_STATE; }
+  if (seed_face >= ctx->F) return MNB_INVALID_START;
+  if (robot_face >= (int64_t)ctx->F) return MNB_INVALID_GOAL;
+  CK(cudaSetDevice(ctx->device));
+  int32_t rc;
+  if ((rc = ensure_workspace(ctx, 1)) != MNB_OK) return rc;
+  if ((rc = ensure_seeds(ctx, 1)) != MNB_OK) return rc;
+  const bool dev = ctx->ptr_mode == MNB_PTR_DEVICE;
+  if ((rc = ensure_out(ctx, dev ? 0 : (size_t)ctx->V, true)) != MNB_OK) return rc;
+  if (ctx->h_cancel) *ctx->h_cancel = 0;     // cvp:679 "reset cancel planning"
+  CK(cudaMemcpyAsync(ctx->d_seed_faces, &seed_face, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_seed_pos, seed_pos, 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_next_query, 0, sizeof(unsigned int), ctx->stream));
+  CK(cudaMemsetAsync(ctx->ws.ctl, 0, sizeof(GroupCtl), ctx->stream));
+  CvpKernelArgs a{};
+  fill_cvp_args(ctx, a);
+  a.n_queries = 1; a.robot_face = robot_face; a.cost_limit = cost_limit; a.goal_dist_offset = goal_dist_offset;
+  a.out_dist = dev ? out_dist : ctx->d_out_dist;
+  // aux outputs are always produced for a single plan (the outcome code needs predecessors_)
+  a.out_pred = (dev && out_pred) ? out_pred : ctx->d_out_pred;
+  a.out_dir = (dev && out_direction) ? out_direction : ctx->d_out_dir;
+  a.out_cut = (dev && out_cut) ? out_cut : ctx->d_out_cut;
+  if (dev && !out_dist) { if ((rc = ensure_out(ctx, (size_t)ctx->V, true)) != MNB_OK) return rc; a.out_dist = ctx->d_out_dist; }
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  if ((rc = launch_cvp(ctx, a, ctx->cluster, 1)) != MNB_OK) return rc;
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (!dev) {
+    if (out_dist) CK(cudaMemcpyAsync(out_dist, a.out_dist, sizeof(float) * (size_t)ctx->V, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_pred) CK(cudaMemcpyAsync(out_pred, a.out_pred, sizeof(uint32_t) * (size_t)ctx->V, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_direction) CK(cudaMemcpyAsync(out_direction, a.out_dir, sizeof(float) * (size_t)ctx->V, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_cut) CK(cudaMemcpyAsync(out_cut, a.out_cut, sizeof(int32_t) * (size_t)ctx->V, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  // outcome (cvp:888-918)
+  uint32_t rf[3] = {0, 0, 0}, rp[3] = {0, 0, 0};
+  if (robot_face >= 0) {
+    CK(cudaMemcpyAsync(rf, ctx->d_faces + 3 * (size_t)robot_face, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 3; ++k)
+      CK(cudaMemcpyAsync(&rp[k], a.out_pred + rf[k], sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if ((rc = finish_stats(ctx, 1, 1)) != MNB_OK) return rc;
+  if (ctx->h_cancel && *ctx->h_cancel) return MNB_CANCELED;
+  if (robot_face >= 0) {
+    bool any = false;
+    for (int k = 0; k < 3; ++k) if (rp[k] != rf[k]) any = true;
+    if (!any && (uint32_t)robot_face != seed_face) return MNB_NO_PATH_FOUND;
+  }
+  return MNB_SUCCESS;
+}
+
+int32_t mnb_cvp_batch(mnb_ctx* ctx, uint32_t n, const uint32_t* seed_faces, const float* seed_pos, double cost_limit,
+                      float* out_dist) {
+  if (!ctx || !seed_faces || !seed_pos || !out_dist || !ctx->V || n == 0) return MNB_E_ARG;
+  if (!ctx->costs_set) { ctx->err = "costs not set"; return MNB_E_STATE; }
+  for (uint32_t i = 0; i < n; ++i) if (seed_faces[i] >= ctx->F) return MNB_INVALID_START;
+  CK(cudaSetDevice(ctx->device));
+  const int cs = ctx->cluster > 8 ? 8 : ctx->cluster;
+  unsigned groups = (unsigned)(ctx->sm_count / cs);
+  if (groups > n) groups = n;
+  if (groups == 0) groups = 1;
+  int32_t rc;
+  if ((rc = ensure_workspace(ctx, groups)) != MNB_OK) return rc;
+  if ((rc = ensure_seeds(ctx, n)) != MNB_OK) return rc;
+  const bool dev = ctx->ptr_mode == MNB_PTR_DEVICE;
+  if ((rc = ensure_out(ctx, dev ? 0 : (size_t)n * ctx->V, false)) != MNB_OK) return rc;
+  if (ctx->h_cancel) *ctx->h_cancel = 0;
+  CK(cudaMemcpyAsync(ctx->d_seed_faces, seed_faces, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_seed_pos, seed_pos, 3 * sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_next_query, 0, sizeof(unsigned int), ctx->stream));
+  CK(cudaMemsetAsync(ctx->ws.ctl, 0, sizeof(GroupCtl) * groups, ctx->stream));
+  CvpKernelArgs a{};
+  fill_cvp_args(ctx, a);
+  a.n_queries = n; a.robot_face = -1; a.cost_limit = cost_limit; a.goal_dist_offset = 0.0;
+  a.out_dist = dev ? out_dist : ctx->d_out_dist;
+  a.out_pred = nullptr; a.out_dir = nullptr; a.out_cut = nullptr;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  if ((rc = launch_cvp(ctx, a, cs, groups)) != MNB_OK) return rc;
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (!dev) CK(cudaMemcpyAsync(out_dist, a.out_dist, sizeof(float) * (size_t)n * ctx->V, cudaMemcpyDeviceToHost, ctx->stream));
+  if ((rc = finish_stats(ctx, groups, 1)) != MNB_OK) return rc;
+  if (ctx->h_cancel && *ctx->h_cancel) return MNB_CANCELED;
+  return MNB_SUCCESS;
+}
+
+int32_t mnb_dijkstra(mnb_ctx* ctx, uint32_t seed_vertex, int64_t robot_vertex, double cost_limit, double goal_dist_offset,
+                     float* out_dist, uint32_t* out_pred) {
+  if (!ctx || !ctx->V) return MNB_E_ARG;
+  if (!ctx->costs_set) { ctx->err = "costs not set"; return MNB_E_STATE; }
+  if (seed_vertex >= ctx->V) return MNB_INVALID_START;
+  if (robot_vertex >= (int64_t)ctx->V) return MNB_INVALID_GOAL;
+  CK(cudaSetDevice(ctx->device));
+  int32_t rc;
+  if ((rc = ensure_workspace(ctx, 1)) != MNB_OK) return rc;
+  const bool dev = ctx->ptr_mode == MNB_PTR_DEVICE;
+  if ((rc = ensure_out(ctx, (size_t)ctx->V, true)) != MNB_OK) return rc;
+  if (ctx->h_cancel) *ctx->h_cancel = 0;     // dijkstra:238
+  CK(cudaMemsetAsync(ctx->ws.ctl, 0, sizeof(GroupCtl), ctx->stream));
+  DijkstraKernelArgs a{};
+  a.V = ctx->V; a.adj_ptr = ctx->d_adj_ptr; a.adj_nw = ctx->d_adj_nw; a.cost = ctx->d_cost;
+  a.invalid = ctx->has_invalid ? ctx->d_invalid : nullptr; a.ws = ctx->ws; a.seed_vertex = seed_vertex;
+  a.robot_vertex = robot_vertex; a.cost_limit = cost_limit; a.goal_dist_offset = goal_dist_offset; a.delta = ctx->delta;
+  a.out_dist = (dev && out_dist) ? out_dist : ctx->d_out_dist;
+  a.out_pred = (dev && out_pred) ? out_pred : ctx->d_out_pred;
+  a.cancel_flag = ctx->d_cancel;
+  if (robot_vertex >= 0 && (uint32_t)robot_vertex == seed_vertex) return MNB_SUCCESS;   // dijkstra:252-255
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  cudaError_t e;
+  const int cs = ctx->cluster;
+  switch (cs) {
+    case 1: e = launch_cluster(k_dijkstra<1>, a, 1, 1, ctx->threads, ctx->stream); break;
+    case 2: e = launch_cluster(k_dijkstra<2>, a, 2, 2, ctx->threads, ctx->stream); break;
+    case 4: e = launch_cluster(k_dijkstra<4>, a, 4, 4, ctx->threads, ctx->stream); break;
+    case 8: e = launch_cluster(k_dijkstra<8>, a, 8, 8, ctx->threads, ctx->stream); break;
+    default: e = launch_cluster(k_dijkstra<16>, a, 16, 16, ctx->threads, ctx->stream); break;
+  }
+  if (e != cudaSuccess) { ctx->err = std::string("dijkstra launch: ") + cudaGetErrorString(e); return MNB_E_CUDA; }
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (!dev) {
+    if (out_dist) CK(cudaMemcpyAsync(out_dist, a.out_dist, sizeof(float) * (size_t)ctx->V, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_pred) CK(cudaMemcpyAsync(out_pred, a.out_pred, sizeof(uint32_t) * (size_t)ctx->V, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  uint32_t rp = 0;
+  if (robot_vertex >= 0) CK(cudaMemcpyAsync(&rp, a.out_pred + robot_vertex, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if ((rc = finish_stats(ctx, 1, 1)) != MNB_OK) return rc;
+  if (ctx->h_cancel && *ctx->h_cancel) return MNB_CANCELED;
+  if (robot_vertex >= 0 && rp == (uint32_t)robot_vertex) return MNB_NO_PATH_FOUND;          // dijkstra:358-362
+  return MNB_SUCCESS;
+}
+
+int32_t mnb_inflate(mnb_ctx* ctx, const uint32_t*, uint32_t, const uint8_t*, const mnb_inflation_params*, float*, float*) {
+  if (!ctx) return MNB_E_ARG;
+  ctx->err = "mnb_inflate: not built yet";
+  return MNB_E_STATE;
+}
+
+}  // extern "C"
