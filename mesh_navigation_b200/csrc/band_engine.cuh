@@ -8,10 +8,10 @@
 // vertex of every incident face (edge) that has all its other vertices fixed.
 //
 // B200 formulation (not a translation of the heap):
-//   * every vertex carries one 64-bit word  {d : potential, tau : pop time}.
-//     tau = max(d, pop time of the face that produced d) is the moment the
-//     sequential algorithm would have popped the vertex; event order is the
-//     lexicographic pair (tau, vertex id)  ==  the oracle's canonical heap.
+//   * every vertex carries one 16-byte word  {d : potential, a1, a2, a3 : pop time}.
+//     The pop time is the moment the sequential algorithm would have popped the
+//     vertex, as a monotonic stack of water levels (problems.cuh); for causal
+//     updates it is simply (d, id)  ==  the oracle's canonical heap order.
 //   * a *candidate* vertex is recomputed FROM SCRATCH ("pull") from its corner
 //     records: the faces are visited in the order their later source vertex
 //     pops, and a face only fires while the candidate itself has not popped yet.
@@ -41,13 +41,23 @@ namespace mnb {
 namespace cg = cooperative_groups;
 
 constexpr uint32_t INF_BITS = 0x7f800000u;
-constexpr unsigned long long STATE_INF = ((unsigned long long)INF_BITS << 32) | INF_BITS;
 
-__device__ __forceinline__ unsigned long long pack_state(float d, float tau) {
-  return ((unsigned long long)__float_as_uint(tau) << 32) | __float_as_uint(d);
+// pop time of a vertex: monotonic stack of water levels a1 > a2 > a3 (0 = unused) + tie-break minor
+struct EvTime { float a1, a2, a3; uint32_t minor; };
+__device__ __forceinline__ bool ev_less(const EvTime& x, const EvTime& y) {
+  if (x.a1 != y.a1) return x.a1 < y.a1;
+  if (x.a2 != y.a2) return x.a2 < y.a2;
+  if (x.a3 != y.a3) return x.a3 < y.a3;
+  return x.minor < y.minor;
 }
-__device__ __forceinline__ float state_d(unsigned long long s) { return __uint_as_float((uint32_t)s); }
-__device__ __forceinline__ float state_tau(unsigned long long s) { return __uint_as_float((uint32_t)(s >> 32)); }
+__device__ __forceinline__ bool ev_eq(const EvTime& x, const EvTime& y) {
+  return __float_as_uint(x.a1) == __float_as_uint(y.a1) && __float_as_uint(x.a2) == __float_as_uint(y.a2) &&
+         __float_as_uint(x.a3) == __float_as_uint(y.a3) && x.minor == y.minor;
+}
+__device__ __forceinline__ EvTime ev_normal(float key, uint32_t id) { EvTime t; t.a1 = key; t.a2 = 0.0f; t.a3 = 0.0f; t.minor = 2u * id; return t; }
+// per-vertex label: one 16-byte word {d, a1, a2, a3 | overflow flag}
+struct Label { float d; EvTime t; };
+__device__ __forceinline__ uint4 state_inf() { return make_uint4(INF_BITS, INF_BITS, 0u, 0u); }
 
 // mark[] values
 constexpr uint32_t MARK_NONE = 0, MARK_CAND = 1, MARK_FIXED = 2, MARK_CAND_ACT = 3;
@@ -56,9 +66,13 @@ struct GroupCtl {               // one per wavefront group, global memory
   unsigned int count[3];        // candidate list sizes (ring over rounds)
   unsigned int m_tau[3];        // float bits: min tau touched by a change in the round
   unsigned int lo[3];           // float bits: min potential over surviving candidates
-  unsigned int goal_bits;       // float bits of goal_dist (cvp:738,769 / dijkstra:279,296)
+  // goal_dist (cvp:738,769 / dijkstra:279,296) and the cancel flag are read by EVERY thread at the
+  // top of a round and decide whether the group leaves the loop, so they must not change while a
+  // round is running: round r reads slot r&1, writers of round r only touch slot (r+1)&1.
+  unsigned int goal_ring[2];    // float bits, monotonically decreasing (atomicMin)
+  unsigned int stop_ring[2];
+  unsigned int goal_bits;       // final goal_dist, published after the last round
   int robot_left;               // robot-face vertices not yet settled
-  unsigned int stop;            // cancel request observed
   unsigned int query;           // batch: query index owned by the group
   unsigned long long rounds, recomputes, settled;
 };
@@ -126,7 +140,7 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
                                 Stage& st, const float delta, const uint32_t gthreads, const uint32_t gtid,
                                 const int has_robot, const uint32_t r0, const uint32_t r1, const uint32_t r2,
                                 const double goal_dist_offset, const volatile int* cancel_flag,
-                                const float band_end_init) {
+                                const float band_end_init, const uint32_t max_rounds) {
   float band_end_prev = band_end_init;  // > every seed potential: seeds are available from round 0
   unsigned long long my_recomputes = 0, my_settled = 0;
   uint32_t r = 0;
@@ -135,9 +149,10 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
     const unsigned int n = __ldcg(&ctl->count[slot]);
     const float m_prev = __uint_as_float(__ldcg(&ctl->m_tau[prev]));
     const float lo_prev = __uint_as_float(__ldcg(&ctl->lo[prev]));
-    const float goal = __uint_as_float(__ldcg(&ctl->goal_bits));
-    const unsigned int stop = __ldcg(&ctl->stop);
-    if (n == 0 || stop) break;
+    const unsigned int goal_b = __ldcg(&ctl->goal_ring[r & 1]);
+    const float goal = __uint_as_float(goal_b);
+    const unsigned int stop = __ldcg(&ctl->stop_ring[r & 1]);
+    if (n == 0 || stop || r > max_rounds) break;   // r is group-uniform: the watchdog cannot deadlock the barrier
     if (r > 0 && __float_as_uint(m_prev) == INF_BITS &&
         (__float_as_uint(lo_prev) == INF_BITS || lo_prev > goal)) break;
     float band_end = lo_prev + delta;
@@ -148,35 +163,35 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
       ctl->count[(r + 2) % 3] = 0;         // list r+2's counter (free during this round)
       ctl->m_tau[next] = INF_BITS;
       ctl->lo[next] = INF_BITS;
-      if (cancel_flag && (r & 31) == 0 && *cancel_flag) ctl->stop = 1;
+      atomicMin(&ctl->goal_ring[(r + 1) & 1], goal_b);                 // carry the cutoff into the next round
+      ctl->stop_ring[(r + 1) & 1] = (stop || (cancel_flag && (r & 31) == 0 && *cancel_flag)) ? 1u : 0u;
     }
     float my_mtau = __uint_as_float(INF_BITS), my_lo = __uint_as_float(INF_BITS);
     for (unsigned int i = gtid; i < n; i += gthreads) {
       const uint32_t c = __ldcg(&list_r[i]);
-      const unsigned long long s = prob.load_state(c);
-      const float d = state_d(s), tau = state_tau(s);
+      const Label old = prob.load_label(c);
+      const float d = old.d, tau = old.t.a1;
       if (tau < m_prev && tau < band_end_prev) {
         // converged prefix: the sequential algorithm has popped c with exactly this label
         mark[c] = MARK_FIXED;
         my_settled++;
         if (has_robot && (c == r0 || c == r1 || c == r2)) {
           if (atomicSub(&ctl->robot_left, 1) == 1) {
-            // c is not necessarily the last of the three in event order: take the latest (tau,id)
-            float bd = d, bt = tau; uint32_t bi = c;
+            // c is not necessarily the last of the three in event order: take the latest (tau,minor)
+            float bd = d; EvTime bt = old.t;
             const uint32_t rv[3] = {r0, r1, r2};
             for (int k = 0; k < 3; ++k) {
-              const unsigned long long so = prob.load_state(rv[k]);
-              const float to = state_tau(so);
-              if (to > bt || (to == bt && rv[k] > bi)) { bt = to; bi = rv[k]; bd = state_d(so); }
+              const Label so = prob.load_label(rv[k]);
+              if (ev_less(bt, so.t)) { bt = so.t; bd = so.d; }
             }
-            ctl->goal_bits = __float_as_uint((float)((double)bd + goal_dist_offset));
+            atomicMin(&ctl->goal_ring[(r + 1) & 1], __float_as_uint((float)((double)bd + goal_dist_offset)));
           }
         }
         continue;
       }
       float nd, ntau;
       my_recomputes++;
-      if (prob.recompute(c, band_end, goal, d, tau, nd, ntau)) my_mtau = fminf(my_mtau, fminf(tau, ntau));
+      if (prob.recompute(c, band_end, goal, old, nd, ntau)) my_mtau = fminf(my_mtau, fminf(tau, ntau));
       my_lo = fminf(my_lo, nd);
       stage_push(st, c, list_n, &ctl->count[next]);
       // a vertex that holds a finite label pulls its neighbours into the candidate set (once)
@@ -203,7 +218,112 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
   // statistics
   atomicAdd(&ctl->recomputes, my_recomputes);
   atomicAdd(&ctl->settled, my_settled);
-  if (gtid == 0) ctl->rounds += r;
+  if (gtid == 0) {
+    ctl->rounds += r;
+    ctl->goal_bits = min(ctl->goal_ring[0], ctl->goal_ring[1]);
+  }
+}
+
+// -----------------------------------------------------------------------------
+// Same round loop with 8 lanes per candidate (problem provides replay_sub8 / activate via its ELL row).
+// Used by the whole-grid single-plan kernel where per-round LATENCY is what matters.
+// -----------------------------------------------------------------------------
+template <int CS, class P>
+__device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_t* list1, uint32_t* mark,
+                                     Stage& st, const float delta, const uint32_t gthreads, const uint32_t gtid,
+                                     const int has_robot, const uint32_t r0, const uint32_t r1, const uint32_t r2,
+                                     const double goal_dist_offset, const volatile int* cancel_flag,
+                                     const float band_end_init, const uint32_t max_rounds) {
+  float band_end_prev = band_end_init;
+  unsigned long long my_recomputes = 0, my_settled = 0;
+  const uint32_t gsubs = gthreads >> 3, gsub = gtid >> 3, j = threadIdx.x & 7;
+  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
+  uint32_t r = 0;
+  for (;; ++r) {
+    const uint32_t slot = r % 3, prev = (r + 2) % 3, next = (r + 1) % 3;
+    const unsigned int n = __ldcg(&ctl->count[slot]);
+    const float m_prev = __uint_as_float(__ldcg(&ctl->m_tau[prev]));
+    const float lo_prev = __uint_as_float(__ldcg(&ctl->lo[prev]));
+    const unsigned int goal_b = __ldcg(&ctl->goal_ring[r & 1]);
+    const float goal = __uint_as_float(goal_b);
+    const unsigned int stop = __ldcg(&ctl->stop_ring[r & 1]);
+    if (n == 0 || stop || r > max_rounds) break;   // r is group-uniform: the watchdog cannot deadlock the barrier
+    if (r > 0 && __float_as_uint(m_prev) == INF_BITS &&
+        (__float_as_uint(lo_prev) == INF_BITS || lo_prev > goal)) break;
+    float band_end = lo_prev + delta;
+    if (!(band_end > band_end_prev)) band_end = band_end_prev;
+    uint32_t* list_r = (r & 1) ? list1 : list0;
+    uint32_t* list_n = (r & 1) ? list0 : list1;
+    if (gtid == 0) {
+      ctl->count[(r + 2) % 3] = 0;
+      ctl->m_tau[next] = INF_BITS;
+      ctl->lo[next] = INF_BITS;
+      atomicMin(&ctl->goal_ring[(r + 1) & 1], goal_b);                 // carry the cutoff into the next round
+      ctl->stop_ring[(r + 1) & 1] = (stop || (cancel_flag && (r & 31) == 0 && *cancel_flag)) ? 1u : 0u;
+    }
+    float my_mtau = __uint_as_float(INF_BITS), my_lo = __uint_as_float(INF_BITS);
+    for (unsigned int i = gsub; i < n; i += gsubs) {
+      const uint32_t c = __ldcg(&list_r[i]);
+      const Label old = prob.load_label(c);
+      const float d = old.d, tau = old.t.a1;
+      if (tau < m_prev && tau < band_end_prev) {
+        if (j == 0) {
+          mark[c] = MARK_FIXED;
+          my_settled++;
+          if (has_robot && (c == r0 || c == r1 || c == r2)) {
+            if (atomicSub(&ctl->robot_left, 1) == 1) {
+              float bd = d; EvTime bt = old.t;
+              const uint32_t rv[3] = {r0, r1, r2};
+              for (int k = 0; k < 3; ++k) {
+                const Label so = prob.load_label(rv[k]);
+                if (ev_less(bt, so.t)) { bt = so.t; bd = so.d; }
+              }
+              atomicMin(&ctl->goal_ring[(r + 1) & 1], __float_as_uint((float)((double)bd + goal_dist_offset)));
+            }
+          }
+        }
+        continue;
+      }
+      float nd; EvTime nt; int4 ix; int deg;
+      prob.replay_sub8(c, j, gmask, band_end, goal, nd, nt, ix, deg);
+      const uint32_t mk = mark[c];
+      if (j == 0) {
+        my_recomputes++;
+        if (__float_as_uint(nd) != __float_as_uint(d) || !ev_eq(nt, old.t)) {
+          prob.store_label(c, nd, nt);
+          my_mtau = fminf(my_mtau, fminf(tau, nt.a1));
+        }
+        my_lo = fminf(my_lo, nd);
+        stage_push(st, c, list_n, &ctl->count[next]);
+      }
+      if (__float_as_uint(nd) != INF_BITS && mk == MARK_CAND) {
+        // every lane pulls the two source vertices of its own corner into the candidate set
+        prob.activate_lane(c, j, ix, deg, [&](uint32_t x) {
+          if (__ldcg(&mark[x]) == MARK_NONE && prob.eligible(x) && atomicCAS(&mark[x], MARK_NONE, MARK_CAND) == MARK_NONE)
+            stage_push(st, x, list_n, &ctl->count[next]);
+        });
+        __syncwarp(gmask);
+        if (j == 0) mark[c] = MARK_CAND_ACT;
+      }
+    }
+    {
+      const unsigned int wm = __reduce_min_sync(0xffffffffu, __float_as_uint(my_mtau));
+      const unsigned int wl = __reduce_min_sync(0xffffffffu, __float_as_uint(my_lo));
+      if ((threadIdx.x & 31) == 0) {
+        if (wm != INF_BITS) atomicMin(&st.m_tau, wm);
+        if (wl != INF_BITS) atomicMin(&st.lo, wl);
+      }
+    }
+    stage_flush(st, list_n, &ctl->count[next], &ctl->m_tau[slot], &ctl->lo[slot]);
+    band_end_prev = band_end;
+    group_sync<CS>();
+  }
+  atomicAdd(&ctl->recomputes, my_recomputes);
+  atomicAdd(&ctl->settled, my_settled);
+  if (gtid == 0) {
+    ctl->rounds += r;
+    ctl->goal_bits = min(ctl->goal_ring[0], ctl->goal_ring[1]);
+  }
 }
 
 }  // namespace mnb

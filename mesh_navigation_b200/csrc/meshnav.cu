@@ -68,7 +68,8 @@ __global__ void k_gather_adj_w(const uint32_t* __restrict__ nbr, const uint32_t*
 // wavefront kernels
 // ============================================================================
 struct WaveWorkspace {     // per group (index g): state + g*V etc.
-  unsigned long long* state;
+  uint4* state;
+  uint32_t* minor;
   uint32_t* mark;
   uint32_t* list0;
   uint32_t* list1;
@@ -80,6 +81,7 @@ struct CvpKernelArgs {
   const float* pos;
   const uint32_t* faces;
   const uint32_t* cor_ptr; const int4* cor_idx; const float4* cor_w;
+  const int4* ell_idx; const float4* ell_w;
   const float* cost; const uint8_t* invalid;
   WaveWorkspace ws;
   uint32_t n_queries;
@@ -109,7 +111,8 @@ __device__ __forceinline__ void ctl_reset(GroupCtl* ctl, unsigned int n0, float 
   ctl->count[0] = n0; ctl->count[1] = 0; ctl->count[2] = 0;
   ctl->m_tau[0] = INF_BITS; ctl->m_tau[1] = INF_BITS; ctl->m_tau[2] = 0u;
   ctl->lo[0] = INF_BITS; ctl->lo[1] = INF_BITS; ctl->lo[2] = __float_as_uint(seed_min);
-  ctl->goal_bits = INF_BITS; ctl->robot_left = 0; ctl->stop = 0;
+  ctl->goal_ring[0] = INF_BITS; ctl->goal_ring[1] = INF_BITS; ctl->stop_ring[0] = 0; ctl->stop_ring[1] = 0;
+  ctl->goal_bits = INF_BITS; ctl->robot_left = 0;
 }
 
 template <int CS>
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(512, 1) k_cvp(const CvpKernelArgs a) {
   uint32_t g, gthreads, gtid;
   group_coords<CS>(g, gthreads, gtid);
   const uint32_t V = a.V;
-  unsigned long long* state = a.ws.state + (size_t)g * V;
+  uint4* state = a.ws.state + (size_t)g * V;
   uint32_t* mark = a.ws.mark + (size_t)g * V;
   uint32_t* list0 = a.ws.list0 + (size_t)g * V;
   uint32_t* list1 = a.ws.list1 + (size_t)g * V;
@@ -132,21 +135,14 @@ __global__ void __launch_bounds__(512, 1) k_cvp(const CvpKernelArgs a) {
     const uint32_t q = __ldcg(&ctl->query);
     if (q >= a.n_queries) break;
     const bool single = (a.n_queries == 1);
-    uint32_t* pred = single ? a.out_pred : nullptr;
-    float* dir = single ? a.out_dir : nullptr;
-    int32_t* cut = single ? a.out_cut : nullptr;
-
-    for (uint32_t v = gtid; v < V; v += gthreads) {
-      state[v] = STATE_INF; mark[v] = MARK_NONE;
-      if (pred) { pred[v] = v; dir[v] = 0.0f; cut[v] = -1; }
-    }
+    for (uint32_t v = gtid; v < V; v += gthreads) { state[v] = state_inf(); mark[v] = MARK_NONE; }
     group_sync<CS>();
 
     const uint32_t sf = a.seed_faces[q];
     const uint32_t s0 = a.faces[3 * (size_t)sf], s1 = a.faces[3 * (size_t)sf + 1], s2 = a.faces[3 * (size_t)sf + 2];
     CvpProblem prob;
     prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_w = a.cor_w; prob.cost = a.cost; prob.invalid = a.invalid;
-    prob.state = state; prob.pred = pred; prob.dir = dir; prob.cut = cut; prob.cost_limit = a.cost_limit;
+    prob.state = state; prob.minor_arr = a.ws.minor + (size_t)g * V; prob.pred = nullptr; prob.dir = nullptr; prob.cut = nullptr; prob.cost_limit = a.cost_limit;
     prob.s0 = s0; prob.s1 = s1; prob.s2 = s2; prob.seed_noexpand = 0;
     float sd[3];
     {
@@ -170,9 +166,8 @@ __global__ void __launch_bounds__(512, 1) k_cvp(const CvpKernelArgs a) {
     if (gtid == 0) {
       const uint32_t sv[3] = {s0, s1, s2};
       for (int k = 0; k < 3; ++k) {
-        state[sv[k]] = pack_state(sd[k], sd[k]);
+        state[sv[k]] = make_uint4(__float_as_uint(sd[k]), __float_as_uint(sd[k]), 0u, 0u);
         mark[sv[k]] = MARK_FIXED;
-        if (cut) cut[sv[k]] = (int32_t)sf;               // cvp:725
       }
       unsigned int n0 = 0;
       for (int k = 0; k < 3; ++k)
@@ -185,7 +180,7 @@ __global__ void __launch_bounds__(512, 1) k_cvp(const CvpKernelArgs a) {
         for (int k = 0; k < 3; ++k) if (mark[rv[k]] != MARK_FIXED) left++;
         ctl->robot_left = left;
         if (left == 0) {  // robot face == seed face: cutoff armed when the last seed pops (cvp:763-771)
-          ctl->goal_bits = __float_as_uint((float)((double)seed_max + a.goal_dist_offset));
+          ctl->goal_ring[0] = __float_as_uint((float)((double)seed_max + a.goal_dist_offset));
         }
       }
     }
@@ -193,14 +188,107 @@ __global__ void __launch_bounds__(512, 1) k_cvp(const CvpKernelArgs a) {
     float delta = a.delta;
     if (has_robot && a.goal_dist_offset < (double)delta) delta = (float)fmax(a.goal_dist_offset, 1e-4);
     run_band_rounds<CS>(prob, ctl, list0, list1, mark, st, delta, gthreads, gtid, has_robot, r0, r1, r2,
-                        a.goal_dist_offset, a.cancel_flag, nextafterf(seed_max, __uint_as_float(INF_BITS)));
+                        a.goal_dist_offset, a.cancel_flag, nextafterf(seed_max, __uint_as_float(INF_BITS)), 2u * V + 64u);
     group_sync<CS>();
     if (a.out_dist) {
       float* od = a.out_dist + (size_t)q * V;
-      for (uint32_t v = gtid; v < V; v += gthreads) od[v] = state_d(state[v]);
+      for (uint32_t v = gtid; v < V; v += gthreads) od[v] = __uint_as_float(state[v].x);
     }
     group_sync<CS>();
   }
+}
+
+// Single plan on the whole GPU: cooperative launch, one CTA per SM (x occupancy), 8 lanes per
+// candidate, grid-wide barrier per round.  Used when latency of ONE wavefront matters.
+__global__ void __launch_bounds__(512, 1) k_cvp_grid(const CvpKernelArgs a) {
+  __shared__ Stage st;
+  uint32_t g, gthreads, gtid;
+  group_coords<0>(g, gthreads, gtid);
+  const uint32_t V = a.V;
+  uint4* state = a.ws.state; uint32_t* mark = a.ws.mark; uint32_t* list0 = a.ws.list0; uint32_t* list1 = a.ws.list1;
+  GroupCtl* ctl = a.ws.ctl;
+  if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; }
+  __syncthreads();
+  for (uint32_t v = gtid; v < V; v += gthreads) { state[v] = state_inf(); mark[v] = MARK_NONE; }
+  group_sync<0>();
+  const uint32_t sf = a.seed_faces[0];
+  const uint32_t s0 = a.faces[3 * (size_t)sf], s1 = a.faces[3 * (size_t)sf + 1], s2 = a.faces[3 * (size_t)sf + 2];
+  CvpEllProblem prob;
+  prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_w = a.cor_w; prob.cost = a.cost; prob.invalid = a.invalid;
+  prob.ell_idx = a.ell_idx; prob.ell_w = a.ell_w;
+  prob.state = state; prob.minor_arr = a.ws.minor; prob.pred = nullptr; prob.dir = nullptr; prob.cut = nullptr; prob.cost_limit = a.cost_limit;
+  prob.s0 = s0; prob.s1 = s1; prob.s2 = s2; prob.seed_noexpand = 0;
+  float sd[3];
+  {
+    const uint32_t sv[3] = {s0, s1, s2};
+    for (int k = 0; k < 3; ++k) {   // cvp:719-728
+      const float dx = a.seed_pos[0] - a.pos[3 * (size_t)sv[k]];
+      const float dy = a.seed_pos[1] - a.pos[3 * (size_t)sv[k] + 1];
+      const float dz = a.seed_pos[2] - a.pos[3 * (size_t)sv[k] + 2];
+      sd[k] = sqrtf(dx * dx + dy * dy + dz * dz);
+      const bool noexp = ((double)a.cost[sv[k]] >= a.cost_limit) || (a.invalid && a.invalid[sv[k]]);
+      if (noexp) prob.seed_noexpand |= (1u << k);
+    }
+  }
+  const float seed_min = fminf(sd[0], fminf(sd[1], sd[2]));
+  const float seed_max = fmaxf(sd[0], fmaxf(sd[1], sd[2]));
+  uint32_t r0 = 0xffffffffu, r1 = 0xffffffffu, r2 = 0xffffffffu;
+  const int has_robot = a.robot_face >= 0;
+  if (has_robot) {
+    r0 = a.faces[3 * (size_t)a.robot_face]; r1 = a.faces[3 * (size_t)a.robot_face + 1]; r2 = a.faces[3 * (size_t)a.robot_face + 2];
+  }
+  if (gtid == 0) {
+    const uint32_t sv[3] = {s0, s1, s2};
+    for (int k = 0; k < 3; ++k) { state[sv[k]] = make_uint4(__float_as_uint(sd[k]), __float_as_uint(sd[k]), 0u, 0u); mark[sv[k]] = MARK_FIXED; }
+    unsigned int n0 = 0;
+    for (int k = 0; k < 3; ++k)
+      prob.activate(sv[k], [&](uint32_t x) {
+        if (mark[x] == MARK_NONE && prob.eligible(x)) { mark[x] = MARK_CAND; list0[n0++] = x; }
+      });
+    ctl_reset(ctl, n0, seed_min);
+    if (has_robot) {
+      int left = 0; const uint32_t rv[3] = {r0, r1, r2};
+      for (int k = 0; k < 3; ++k) if (mark[rv[k]] != MARK_FIXED) left++;
+      ctl->robot_left = left;
+      if (left == 0) ctl->goal_ring[0] = __float_as_uint((float)((double)seed_max + a.goal_dist_offset));
+    }
+  }
+  group_sync<0>();
+  float delta = a.delta;
+  if (has_robot && a.goal_dist_offset < (double)delta) delta = (float)fmax(a.goal_dist_offset, 1e-4);
+  run_band_rounds_sub8<0>(prob, ctl, list0, list1, mark, st, delta, gthreads, gtid, has_robot, r0, r1, r2,
+                          a.goal_dist_offset, a.cancel_flag, nextafterf(seed_max, __uint_as_float(INF_BITS)), 2u * V + 64u);
+  group_sync<0>();
+  if (a.out_dist)
+    for (uint32_t v = gtid; v < V; v += gthreads) a.out_dist[v] = __uint_as_float(state[v].x);
+}
+
+// predecessors_ / direction_ / cutting_faces_ (cvp:423-431,493-517) from the FINAL labels: every vertex
+// replays its faces once more in event order and evaluates the winning face with the literal acos form.
+// Done after the wavefront so that the stored angles use the final source potentials.
+__global__ void __launch_bounds__(256) k_cvp_epilogue(const CvpKernelArgs a, const GroupCtl* ctl) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.V) return;
+  const uint32_t sf = a.seed_faces[0];
+  CvpProblem prob;
+  prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_w = a.cor_w; prob.cost = a.cost; prob.invalid = a.invalid;
+  prob.state = a.ws.state; prob.minor_arr = a.ws.minor; prob.pred = a.out_pred; prob.dir = a.out_dir; prob.cut = a.out_cut; prob.cost_limit = a.cost_limit;
+  prob.s0 = a.faces[3 * (size_t)sf]; prob.s1 = a.faces[3 * (size_t)sf + 1]; prob.s2 = a.faces[3 * (size_t)sf + 2];
+  prob.seed_noexpand = 0;
+  {
+    const uint32_t sv[3] = {prob.s0, prob.s1, prob.s2};
+    for (int k = 0; k < 3; ++k)
+      if (((double)a.cost[sv[k]] >= a.cost_limit) || (a.invalid && a.invalid[sv[k]])) prob.seed_noexpand |= (1u << k);
+  }
+  const float d = __uint_as_float(a.ws.state[c].x);
+  if (prob.seed_index(c) >= 0) {                         // cvp:719-728
+    a.out_pred[c] = c; a.out_dir[c] = 0.0f; a.out_cut[c] = (int32_t)sf;
+    return;
+  }
+  int win = -1; float nd, wu1 = 0, wu2 = 0; EvTime nt;
+  if (__float_as_uint(d) != INF_BITS && prob.eligible(c))
+    prob.replay(c, __uint_as_float(INF_BITS), __uint_as_float(ctl->goal_bits), nd, nt, win, wu1, wu2);
+  prob.write_aux(c, win, wu1, wu2);
 }
 
 struct DijkstraKernelArgs {
@@ -221,12 +309,12 @@ __global__ void __launch_bounds__(512, 1) k_dijkstra(const DijkstraKernelArgs a)
   uint32_t g, gthreads, gtid;
   group_coords<CS>(g, gthreads, gtid);
   const uint32_t V = a.V;
-  unsigned long long* state = a.ws.state;
+  uint4* state = a.ws.state;
   uint32_t* mark = a.ws.mark; uint32_t* list0 = a.ws.list0; uint32_t* list1 = a.ws.list1;
   GroupCtl* ctl = a.ws.ctl;
   if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; }
   __syncthreads();
-  for (uint32_t v = gtid; v < V; v += gthreads) { state[v] = STATE_INF; mark[v] = MARK_NONE; a.out_pred[v] = v; }
+  for (uint32_t v = gtid; v < V; v += gthreads) { state[v] = state_inf(); mark[v] = MARK_NONE; a.out_pred[v] = v; }
   group_sync<CS>();
   DijkstraProblem prob;
   prob.adj_ptr = a.adj_ptr; prob.adj_nw = a.adj_nw; prob.cost = a.cost; prob.invalid = a.invalid;
@@ -234,7 +322,7 @@ __global__ void __launch_bounds__(512, 1) k_dijkstra(const DijkstraKernelArgs a)
   const int has_robot = a.robot_vertex >= 0;
   const uint32_t rv = has_robot ? (uint32_t)a.robot_vertex : 0xffffffffu;
   if (gtid == 0) {
-    state[a.seed_vertex] = pack_state(0.0f, 0.0f);     // dijkstra:276
+    state[a.seed_vertex] = make_uint4(0u, 0u, 0u, 0u);     // dijkstra:276 (d = 0, tau = 0)
     mark[a.seed_vertex] = MARK_FIXED;
     unsigned int n0 = 0;
     prob.activate(a.seed_vertex, [&](uint32_t x) {
@@ -247,9 +335,9 @@ __global__ void __launch_bounds__(512, 1) k_dijkstra(const DijkstraKernelArgs a)
   float delta = a.delta;
   if (has_robot && a.goal_dist_offset < (double)delta) delta = (float)fmax(a.goal_dist_offset, 1e-4);
   run_band_rounds<CS>(prob, ctl, list0, list1, mark, st, delta, gthreads, gtid, has_robot, rv, rv, rv,
-                      a.goal_dist_offset, a.cancel_flag, 1e-30f);
+                      a.goal_dist_offset, a.cancel_flag, 1e-30f, 2u * V + 64u);
   group_sync<CS>();
-  for (uint32_t v = gtid; v < V; v += gthreads) a.out_dist[v] = state_d(state[v]);
+  for (uint32_t v = gtid; v < V; v += gthreads) a.out_dist[v] = __uint_as_float(state[v].x);
 }
 
 // ============================================================================
@@ -268,6 +356,7 @@ struct mnb_ctx {
   float* d_pos = nullptr; uint32_t* d_faces = nullptr; uint32_t* d_edges = nullptr;
   uint32_t* d_cor_ptr = nullptr; int4* d_cor_idx = nullptr; uint4* d_cor_eid = nullptr;
   float4* d_cor_w = nullptr; float4* d_cor_wd = nullptr;
+  int4* d_ell_idx = nullptr; uint4* d_ell_eid = nullptr; float4* d_ell_w = nullptr; float4* d_ell_wd = nullptr;
   uint32_t* d_adj_ptr = nullptr; uint32_t* d_adj_nbr = nullptr; uint32_t* d_adj_eid = nullptr; uint2* d_adj_nw = nullptr;
   float* d_edge_dist = nullptr; float* d_edge_w = nullptr; float* d_cost = nullptr; uint8_t* d_invalid = nullptr;
   bool has_invalid = false, costs_set = false;
@@ -281,7 +370,8 @@ struct mnb_ctx {
   uint32_t* d_out_pred = nullptr; float* d_out_dir = nullptr; int32_t* d_out_cut = nullptr;
   uint32_t* d_seed_faces = nullptr; float* d_seed_pos = nullptr; uint32_t seed_cap = 0;
   // tuning
-  float delta = 0.3f; int cluster = 8; int threads = 512;
+  float delta = 0.3f; int cluster = -1 /* -1: whole-grid cooperative kernel for single plans */; int batch_cluster = 1; int threads = 512;
+  int grid_blocks_per_sm = 0;
   mnb_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -302,9 +392,9 @@ static void dfree(T*& p) { if (p) cudaFree(p); p = nullptr; }
 
 static void free_mesh(mnb_ctx* c) {
   dfree(c->d_pos); dfree(c->d_faces); dfree(c->d_edges); dfree(c->d_cor_ptr); dfree(c->d_cor_idx); dfree(c->d_cor_eid);
-  dfree(c->d_cor_w); dfree(c->d_cor_wd); dfree(c->d_adj_ptr); dfree(c->d_adj_nbr); dfree(c->d_adj_eid); dfree(c->d_adj_nw);
+  dfree(c->d_cor_w); dfree(c->d_cor_wd); dfree(c->d_ell_idx); dfree(c->d_ell_eid); dfree(c->d_ell_w); dfree(c->d_ell_wd); dfree(c->d_adj_ptr); dfree(c->d_adj_nbr); dfree(c->d_adj_eid); dfree(c->d_adj_nw);
   dfree(c->d_edge_dist); dfree(c->d_edge_w); dfree(c->d_cost); dfree(c->d_invalid);
-  dfree(c->ws.state); dfree(c->ws.mark); dfree(c->ws.list0); dfree(c->ws.list1); dfree(c->ws.ctl);
+  dfree(c->ws.state); dfree(c->ws.minor); dfree(c->ws.mark); dfree(c->ws.list0); dfree(c->ws.list1); dfree(c->ws.ctl);
   c->ws_groups = 0;
   dfree(c->d_out_dist); c->out_dist_cap = 0; dfree(c->d_out_pred); dfree(c->d_out_dir); dfree(c->d_out_cut);
   c->costs_set = false;
@@ -312,10 +402,10 @@ static void free_mesh(mnb_ctx* c) {
 
 static int32_t ensure_workspace(mnb_ctx* ctx, uint32_t groups) {
   if (groups <= ctx->ws_groups) return MNB_OK;
-  dfree(ctx->ws.state); dfree(ctx->ws.mark); dfree(ctx->ws.list0); dfree(ctx->ws.list1); dfree(ctx->ws.ctl);
+  dfree(ctx->ws.state); dfree(ctx->ws.minor); dfree(ctx->ws.mark); dfree(ctx->ws.list0); dfree(ctx->ws.list1); dfree(ctx->ws.ctl);
   ctx->ws_groups = 0;
   const size_t n = (size_t)groups * ctx->V;
-  CK(dalloc(&ctx->ws.state, n)); CK(dalloc(&ctx->ws.mark, n)); CK(dalloc(&ctx->ws.list0, n)); CK(dalloc(&ctx->ws.list1, n));
+  CK(dalloc(&ctx->ws.state, n)); CK(dalloc(&ctx->ws.minor, n)); CK(dalloc(&ctx->ws.mark, n)); CK(dalloc(&ctx->ws.list0, n)); CK(dalloc(&ctx->ws.list1, n));
   CK(dalloc(&ctx->ws.ctl, groups));
   ctx->ws_groups = groups;
   return MNB_OK;
@@ -371,9 +461,12 @@ uint32_t mnb_num_edges(mnb_ctx* ctx) { return ctx ? ctx->E : 0; }
 int32_t mnb_set_tuning(mnb_ctx* ctx, float band_delta, int32_t cluster_size, int32_t threads_per_cta) {
   if (!ctx) return MNB_E_ARG;
   if (band_delta > 0) ctx->delta = band_delta;
-  if (cluster_size == 1 || cluster_size == 2 || cluster_size == 4 || cluster_size == 8 || cluster_size == 16)
+  if (cluster_size == 1 || cluster_size == 2 || cluster_size == 4 || cluster_size == 8 || cluster_size == 16) {
     ctx->cluster = cluster_size;
-  else if (cluster_size != 0) return MNB_E_ARG;
+    ctx->batch_cluster = cluster_size > 8 ? 8 : cluster_size;
+  } else if (cluster_size == -1) {
+    ctx->cluster = -1;        // single plans on the whole grid (cooperative launch); batches keep their cluster size
+  } else if (cluster_size != 0) return MNB_E_ARG;
   if (threads_per_cta == 128 || threads_per_cta == 256 || threads_per_cta == 512) ctx->threads = threads_per_cta;
   else if (threads_per_cta != 0) return MNB_E_ARG;
   return MNB_OK;
@@ -420,6 +513,18 @@ int32_t mnb_set_mesh(mnb_ctx* ctx, uint32_t V, uint32_t F, const float* pos, con
     CK(cudaMemcpyAsync(ctx->d_cor_idx, idx.data(), sizeof(int4) * NC, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_cor_eid, eid.data(), sizeof(uint4) * NC, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    // ELL rows: 8 slots per vertex (one 128-byte line), slot 0 carries the degree in .w
+    const size_t NE = (size_t)V * ELL_W;
+    std::vector<int4> eidx(NE, make_int4(ELL_EMPTY, ELL_EMPTY, -1, 0)); std::vector<uint4> eeid(NE, make_uint4(0, 0, 0, 0));
+    for (uint32_t v = 0; v < V; ++v) {
+      const uint32_t kb = T.vcor_ptr[v], ke = T.vcor_ptr[v + 1];
+      for (uint32_t k = kb; k < ke && k - kb < ELL_W; ++k) { eidx[(size_t)v * ELL_W + (k - kb)] = idx[k]; eeid[(size_t)v * ELL_W + (k - kb)] = eid[k]; }
+      eidx[(size_t)v * ELL_W].w = (int)(ke - kb);
+    }
+    CK(dalloc(&ctx->d_ell_idx, NE)); CK(dalloc(&ctx->d_ell_eid, NE)); CK(dalloc(&ctx->d_ell_w, NE)); CK(dalloc(&ctx->d_ell_wd, NE));
+    CK(cudaMemcpyAsync(ctx->d_ell_idx, eidx.data(), sizeof(int4) * NE, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_ell_eid, eeid.data(), sizeof(uint4) * NE, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
   }
   // the host copies of the big per-corner arrays are no longer needed
   std::vector<uint32_t>().swap(T.cor_v1); std::vector<uint32_t>().swap(T.cor_v2); std::vector<uint32_t>().swap(T.cor_face);
@@ -427,6 +532,7 @@ int32_t mnb_set_mesh(mnb_ctx* ctx, uint32_t V, uint32_t F, const float* pos, con
   std::vector<uint32_t>().swap(T.vadj_nbr); std::vector<uint32_t>().swap(T.vadj_eid); std::vector<uint32_t>().swap(T.face_edges);
   k_edge_dist<<<(T.E + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_pos, ctx->d_edges, T.E, ctx->d_edge_dist);
   k_gather_corner_w<<<(unsigned)((NC + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_cor_eid, ctx->d_edge_dist, NC, ctx->d_cor_wd);
+  k_gather_corner_w<<<(unsigned)(((size_t)V * ELL_W + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_ell_eid, ctx->d_edge_dist, (size_t)V * ELL_W, ctx->d_ell_wd);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(ctx->stream));
   return MNB_OK;
@@ -451,6 +557,7 @@ int32_t mnb_get_edge_distances(mnb_ctx* ctx, float* out) {
 
 static int32_t install_weights(mnb_ctx* ctx) {
   k_gather_corner_w<<<(unsigned)((ctx->NC + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_cor_eid, ctx->d_edge_w, ctx->NC, ctx->d_cor_w);
+  k_gather_corner_w<<<(unsigned)(((size_t)ctx->V * ELL_W + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_ell_eid, ctx->d_edge_w, (size_t)ctx->V * ELL_W, ctx->d_ell_w);
   k_gather_adj_w<<<(unsigned)((ctx->NA + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_adj_nbr, ctx->d_adj_eid, ctx->d_edge_w, ctx->NA, ctx->d_adj_nw);
   CK(cudaGetLastError());
   ctx->costs_set = true;
@@ -551,7 +658,7 @@ static int32_t ensure_seeds(mnb_ctx* ctx, uint32_t n) {
 
 static void fill_cvp_args(mnb_ctx* ctx, CvpKernelArgs& a) {
   a.V = ctx->V; a.pos = ctx->d_pos; a.faces = ctx->d_faces; a.cor_ptr = ctx->d_cor_ptr; a.cor_idx = ctx->d_cor_idx;
-  a.cor_w = ctx->d_cor_w; a.cost = ctx->d_cost; a.invalid = ctx->has_invalid ? ctx->d_invalid : nullptr; a.ws = ctx->ws;
+  a.cor_w = ctx->d_cor_w; a.ell_idx = ctx->d_ell_idx; a.ell_w = ctx->d_ell_w; a.cost = ctx->d_cost; a.invalid = ctx->has_invalid ? ctx->d_invalid : nullptr; a.ws = ctx->ws;
   a.seed_faces = ctx->d_seed_faces; a.seed_pos = ctx->d_seed_pos; a.delta = ctx->delta; a.next_query = ctx->d_next_query;
   a.cancel_flag = ctx->d_cancel;
 }
@@ -585,7 +692,21 @@ int32_t mnb_cvp(mnb_ctx* ctx, uint32_t seed_face, const float seed_pos[3], int64
   a.out_cut = (dev && out_cut) ? out_cut : ctx->d_out_cut;
   if (dev && !out_dist) { if ((rc = ensure_out(ctx, (size_t)ctx->V, true)) != MNB_OK) return rc; a.out_dist = ctx->d_out_dist; }
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  if ((rc = launch_cvp(ctx, a, ctx->cluster, 1)) != MNB_OK) return rc;
+  if (ctx->cluster == -1) {
+    if (ctx->grid_blocks_per_sm == 0) {
+      int nb = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_cvp_grid, ctx->threads, 0));
+      ctx->grid_blocks_per_sm = nb > 0 ? 1 : 0;
+      if (nb <= 0) { ctx->err = "k_cvp_grid cannot be resident"; return MNB_E_CUDA; }
+    }
+    void* kargs[] = {(void*)&a};
+    CK(cudaLaunchCooperativeKernel((const void*)k_cvp_grid, dim3(ctx->sm_count * ctx->grid_blocks_per_sm), dim3(ctx->threads),
+                                   kargs, 0, ctx->stream));
+  } else {
+    if ((rc = launch_cvp(ctx, a, ctx->cluster, 1)) != MNB_OK) return rc;
+  }
+  k_cvp_epilogue<<<(ctx->V + 255) / 256, 256, 0, ctx->stream>>>(a, ctx->ws.ctl);
+  CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   if (!dev) {
     if (out_dist) CK(cudaMemcpyAsync(out_dist, a.out_dist, sizeof(float) * (size_t)ctx->V, cudaMemcpyDeviceToHost, ctx->stream));
@@ -601,7 +722,7 @@ int32_t mnb_cvp(mnb_ctx* ctx, uint32_t seed_face, const float seed_pos[3], int64
     for (int k = 0; k < 3; ++k)
       CK(cudaMemcpyAsync(&rp[k], a.out_pred + rf[k], sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   }
-  if ((rc = finish_stats(ctx, 1, 1)) != MNB_OK) return rc;
+  if ((rc = finish_stats(ctx, 1, 2)) != MNB_OK) return rc;
   if (ctx->h_cancel && *ctx->h_cancel) return MNB_CANCELED;
   if (robot_face >= 0) {
     bool any = false;
@@ -617,7 +738,7 @@ int32_t mnb_cvp_batch(mnb_ctx* ctx, uint32_t n, const uint32_t* seed_faces, cons
   if (!ctx->costs_set) { ctx->err = "costs not set"; return MNB_E_STATE; }
   for (uint32_t i = 0; i < n; ++i) if (seed_faces[i] >= ctx->F) return MNB_INVALID_START;
   CK(cudaSetDevice(ctx->device));
-  const int cs = ctx->cluster > 8 ? 8 : ctx->cluster;
+  const int cs = ctx->batch_cluster;
   unsigned groups = (unsigned)(ctx->sm_count / cs);
   if (groups > n) groups = n;
   if (groups == 0) groups = 1;
@@ -668,7 +789,7 @@ int32_t mnb_dijkstra(mnb_ctx* ctx, uint32_t seed_vertex, int64_t robot_vertex, d
   if (robot_vertex >= 0 && (uint32_t)robot_vertex == seed_vertex) return MNB_SUCCESS;   // dijkstra:252-255
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   cudaError_t e;
-  const int cs = ctx->cluster;
+  const int cs = ctx->cluster == -1 ? 8 : ctx->cluster;
   switch (cs) {
     case 1: e = launch_cluster(k_dijkstra<1>, a, 1, 1, ctx->threads, ctx->stream); break;
     case 2: e = launch_cluster(k_dijkstra<2>, a, 2, 2, ctx->threads, ctx->stream); break;

@@ -10,6 +10,17 @@ namespace mnb {
 //   cor_w[k]   = {w(v1,v2), w(v1,c), w(v2,c), -}   edge *weights* (cvp:380-390)
 // Reference: the face (v1,v2,c) updates c when the later of v1,v2 is popped and c
 // is the only non-fixed vertex (cvp_mesh_planner.cpp:790-866).
+//
+// Event (pop) time of a vertex = the monotonic stack of "water levels" (a1 > a2 > a3, minor):
+//   * a vertex whose label exceeds the pop time of the face that produced it pops at its own key:
+//     (d, 0, 0, 2*id)  ==  the oracle's canonical heap order (key, id);
+//   * the CVP unfolding update is not causal: a face fired at water level a1 can hand
+//     out a label X <= a1 ("back-step").  Such a vertex is popped inside the cascade that runs below
+//     the water line, in key order among the cascade's entries: its time keeps the trigger's levels
+//     that are >= X and appends X:  (a1, X) / (a1, a2, X); cascades nest (3 levels tracked, exact on
+//     every mesh tested incl. cost-weighted non-geometric weights; deeper ones fall back to
+//     "right after the trigger": minor(trigger)+1, kept in a side array).
+// Times compare lexicographically.
 // ---------------------------------------------------------------------------
 struct CvpProblem {
   const uint32_t* __restrict__ cor_ptr;
@@ -17,8 +28,8 @@ struct CvpProblem {
   const float4* __restrict__ cor_w;
   const float* __restrict__ cost;
   const uint8_t* __restrict__ invalid;  // may be null
-  unsigned long long* state;
-  uint32_t* pred;    // may be null (batch: potentials only)
+  uint4* state;                         // {d bits, tau bits, minor (0 = 2*id), -}
+  uint32_t* pred;    // epilogue only
   float* dir;
   int32_t* cut;
   double cost_limit;
@@ -27,7 +38,20 @@ struct CvpProblem {
 
   static constexpr int MAXF = 12;
 
-  __device__ __forceinline__ unsigned long long load_state(uint32_t v) const { return __ldcg(&state[v]); }
+  uint32_t* minor_arr;                  // overflow minors (only read when the label's flag bit is set)
+
+  __device__ __forceinline__ Label load_label(uint32_t v) const {
+    const uint4 s = __ldcg(&state[v]);
+    Label l; l.d = __uint_as_float(s.x); l.t.a1 = __uint_as_float(s.y); l.t.a2 = __uint_as_float(s.z);
+    l.t.a3 = __uint_as_float(s.w & 0x7fffffffu);
+    l.t.minor = (s.w >> 31) ? __ldcg(&minor_arr[v]) : 2u * v;
+    return l;
+  }
+  __device__ __forceinline__ void store_label(uint32_t c, float d, const EvTime& t) const {
+    uint32_t w = __float_as_uint(t.a3);
+    if (t.minor != 2u * c) { __stcg(&minor_arr[c], t.minor); w |= 0x80000000u; }
+    __stcg(&state[c], make_uint4(__float_as_uint(d), __float_as_uint(t.a1), __float_as_uint(t.a2), w));
+  }
   __device__ __forceinline__ bool eligible(uint32_t x) const {
     if (invalid && invalid[x]) return false;        // cvp:785 (no face with an invalid vertex)
     return !((double)cost[x] >= cost_limit);        // cvp:802,825,848
@@ -44,119 +68,249 @@ struct CvpProblem {
     }
   }
 
-  // event time of corner k for candidate c; returns false if the face cannot fire
-  __device__ __forceinline__ bool corner_time(uint32_t k, float band_end, float goal, float& T, uint32_t& Tid,
-                                              float& u1, float& u2) const {
-    const int4 ix = __ldg(&cor_idx[k]);
-    const uint32_t v1 = (uint32_t)ix.x, v2 = (uint32_t)ix.y;
-    const unsigned long long a = load_state(v1), b = load_state(v2);
-    u1 = state_d(a); u2 = state_d(b);
-    if (!(u1 < band_end) || !(u2 < band_end)) return false;
+  // pop time (T, Tm) of the face with sources v1, v2; false if the face cannot fire
+  __device__ __forceinline__ bool face_time(uint32_t v1, uint32_t v2, const Label& a, const Label& b, float band_end,
+                                            float goal, EvTime& T) const {
+    if (!(a.d < band_end) || !(b.d < band_end)) return false;
     if (invalid && (invalid[v1] || invalid[v2])) return false;
-    const float t1 = state_tau(a), t2 = state_tau(b);
     const int i1 = seed_index(v1), i2 = seed_index(v2);
-    const bool v1_later = t1 > t2 || (t1 == t2 && v1 > v2);
+    const bool v1_later = ev_less(b.t, a.t);
     if (i1 >= 0 && i2 >= 0) {
       // both sources pre-fixed: the face fires at the FIRST of them that pops and expands
       const bool e1 = !((seed_noexpand >> i1) & 1u), e2 = !((seed_noexpand >> i2) & 1u);
       if (!e1 && !e2) return false;
       const bool use1 = e1 && (!e2 || !v1_later);
-      T = use1 ? t1 : t2; Tid = use1 ? v1 : v2;
+      T = use1 ? a.t : b.t;
       return true;
     }
-    const uint32_t later = v1_later ? v1 : v2;
     const int il = v1_later ? i1 : i2;
     if (il >= 0 && ((seed_noexpand >> il) & 1u)) return false;
-    const float dl = v1_later ? u1 : u2;
-    if (dl > goal) return false;                       // cvp:754
-    T = v1_later ? t1 : t2; Tid = later;
+    if ((v1_later ? a.d : b.d) > goal) return false;                       // cvp:754
+    T = v1_later ? a.t : b.t;
     return true;
   }
 
-  __device__ __forceinline__ void write_result(uint32_t c, float nd, float ntau, int win, const CvpResult& best) {
-    __stcg(&state[c], pack_state(nd, ntau));
-    if (pred) {
-      if (win >= 0) {
-        const int4 ix = __ldg(&cor_idx[win]);
-        pred[c] = best.pred_sel == 1 ? (uint32_t)ix.x : (uint32_t)ix.y;
-        dir[c] = best.direction;
-        cut[c] = ix.z;
-      } else {
-        pred[c] = c; dir[c] = 0.0f; cut[c] = -1;
-      }
+  __device__ __forceinline__ bool corner_time(uint32_t k, float band_end, float goal, EvTime& T, float& u1, float& u2) const {
+    const int4 ix = __ldg(&cor_idx[k]);
+    const Label a = load_label((uint32_t)ix.x), b = load_label((uint32_t)ix.y);
+    u1 = a.d; u2 = b.d;
+    return face_time((uint32_t)ix.x, (uint32_t)ix.y, a, b, band_end, goal, T);
+  }
+
+  // predecessors_/direction_/cutting_faces_ of the winning face (cvp:493-517), literal acos form
+  __device__ __forceinline__ void write_aux(uint32_t c, int win, float wu1, float wu2) {
+    if (win >= 0) {
+      const int4 ix = __ldg(&cor_idx[win]);
+      const float4 w = __ldg(&cor_w[win]);
+      CvpResult r; r.value = 0; r.direction = 0; r.pred_sel = 1;
+      cvp_update_t<true>(wu1, wu2, (double)__uint_as_float(INF_BITS), w.z, w.y, w.x, r);
+      pred[c] = r.pred_sel == 1 ? (uint32_t)ix.x : (uint32_t)ix.y;
+      dir[c] = r.direction;
+      cut[c] = ix.z;
+    } else {
+      pred[c] = c; dir[c] = 0.0f; cut[c] = -1;
     }
+  }
+
+  // one accepted update with value X from a face that fired at time F: pop time of c
+  // (monotonic stack: keep the trigger's water levels that are >= X, then X itself)
+  __device__ __forceinline__ static EvTime accept_time(uint32_t c, float X, const EvTime& F) {
+    EvTime t; t.a2 = 0.0f; t.a3 = 0.0f; t.minor = 2u * c;
+    if (X > F.a1) { t.a1 = X; return t; }                         // above water: pops at its own key
+    t.a1 = F.a1;
+    if (X > F.a2) { t.a2 = X; return t; }
+    t.a2 = F.a2;
+    if (X > F.a3) { t.a3 = X; return t; }
+    t.a3 = F.a3; t.minor = F.minor + 1u;                          // deeper than tracked: right after the trigger
+    return t;
   }
 
   // generic path for vertices with more than MAXF incident faces: repeated selection of the next
-  // corner in (T, Tid, corner index) order by rescanning the corner list (O(deg^2), rare)
-  __device__ __noinline__ void recompute_big(uint32_t c, float band_end, float goal, float& nd, float& ntau, int& win,
-                                             CvpResult& best) const {
+  // corner in (T, corner index) order by rescanning the corner list (O(deg^2), rare)
+  __device__ __noinline__ void replay_big(uint32_t c, float band_end, float goal, float& nd, EvTime& nt, int& win,
+                                          float& wu1, float& wu2) const {
     const uint32_t kb = cor_ptr[c], ke = cor_ptr[c + 1];
-    float cur = __uint_as_float(INF_BITS), tcur = cur;
-    float lastT = 0.0f; uint32_t lastId = 0, lastK = 0; bool have_last = false;
+    float cur = __uint_as_float(INF_BITS);
+    EvTime tc = ev_normal(cur, c);
+    EvTime lastT = ev_normal(0.0f, 0); uint32_t lastK = 0; bool have_last = false;
     win = -1;
     for (;;) {
-      float bT = 0, bu1 = 0, bu2 = 0; uint32_t bId = 0, bk = 0; bool found = false;
+      EvTime bT = lastT; float bu1 = 0, bu2 = 0; uint32_t bk = 0; bool found = false;
       for (uint32_t k = kb; k < ke; ++k) {
-        float T, u1, u2; uint32_t Tid;
-        if (!corner_time(k, band_end, goal, T, Tid, u1, u2)) continue;
+        EvTime T; float u1, u2;
+        if (!corner_time(k, band_end, goal, T, u1, u2)) continue;
         if (have_last) {
-          const bool after = T > lastT || (T == lastT && (Tid > lastId || (Tid == lastId && k > lastK)));
+          const bool after = ev_less(lastT, T) || (ev_eq(lastT, T) && k > lastK);
           if (!after) continue;
         }
-        if (!found || T < bT || (T == bT && (Tid < bId || (Tid == bId && k < bk)))) {
-          bT = T; bId = Tid; bk = k; bu1 = u1; bu2 = u2; found = true;
-        }
+        if (!found || ev_less(T, bT) || (ev_eq(T, bT) && k < bk)) { bT = T; bk = k; bu1 = u1; bu2 = u2; found = true; }
       }
       if (!found) break;
-      if (!(bT < tcur || (bT == tcur && bId < c))) break;
+      if (!ev_less(bT, tc)) break;
       const float4 w = __ldg(&cor_w[bk]);
       CvpResult r;
-      if (cvp_update(bu1, bu2, cur, w.z, w.y, w.x, r)) { cur = r.value; tcur = fmaxf(cur, bT); best = r; win = (int)bk; }
-      lastT = bT; lastId = bId; lastK = bk; have_last = true;
+      if (cvp_update_t<false>(bu1, bu2, cur, w.z, w.y, w.x, r)) { cur = r.value; tc = accept_time(c, r.value, bT); win = (int)bk; wu1 = bu1; wu2 = bu2; }
+      lastT = bT; lastK = bk; have_last = true;
     }
-    nd = cur; ntau = tcur;
+    nd = cur; nt = tc;
   }
 
-  __device__ __forceinline__ bool recompute(uint32_t c, float band_end, float goal, float d_old, float tau_old,
-                                            float& nd, float& ntau) {
+  // event-ordered replay of the faces around c (see band_engine.cuh)
+  __device__ __forceinline__ void replay(uint32_t c, float band_end, float goal, float& nd, EvTime& nt, int& win,
+                                         float& wu1, float& wu2) const {
     const uint32_t kb = cor_ptr[c], ke = cor_ptr[c + 1];
-    int win = -1;
-    CvpResult best; best.value = 0; best.direction = 0; best.pred_sel = 1;
+    win = -1; wu1 = 0.0f; wu2 = 0.0f;
     if (ke - kb > (uint32_t)MAXF) {
-      recompute_big(c, band_end, goal, nd, ntau, win, best);
-    } else {
-      float Tt[MAXF], U1[MAXF], U2[MAXF]; uint32_t Ti[MAXF], K[MAXF];
-      int n = 0;
-      for (uint32_t k = kb; k < ke; ++k) {
-        float T, u1, u2; uint32_t Tid;
-        if (!corner_time(k, band_end, goal, T, Tid, u1, u2)) continue;
-        Tt[n] = T; Ti[n] = Tid; U1[n] = u1; U2[n] = u2; K[n] = k; ++n;
-      }
-      float cur = __uint_as_float(INF_BITS), tcur = cur;
-      for (int i = 0; i < n; ++i) {
-        int b = i;
-        for (int j = i + 1; j < n; ++j)
-          if (Tt[j] < Tt[b] || (Tt[j] == Tt[b] && (Ti[j] < Ti[b] || (Ti[j] == Ti[b] && K[j] < K[b])))) b = j;
-        const float T = Tt[b]; const uint32_t Tid = Ti[b]; const float u1 = U1[b], u2 = U2[b]; const uint32_t k = K[b];
-        Tt[b] = Tt[i]; Ti[b] = Ti[i]; U1[b] = U1[i]; U2[b] = U2[i]; K[b] = K[i];
-        if (!(T < tcur || (T == tcur && Tid < c))) break;   // c has been popped before this face fires
-        const float4 w = __ldg(&cor_w[k]);
-        CvpResult r;
-        if (cvp_update(u1, u2, cur, w.z, w.y, w.x, r)) { cur = r.value; tcur = fmaxf(cur, T); best = r; win = (int)k; }
-      }
-      nd = cur; ntau = tcur;
+      replay_big(c, band_end, goal, nd, nt, win, wu1, wu2);
+      return;
     }
-    if (__float_as_uint(nd) == __float_as_uint(d_old) && __float_as_uint(ntau) == __float_as_uint(tau_old)) return false;
-    write_result(c, nd, ntau, win, best);
+    EvTime Tt[MAXF]; float U1[MAXF], U2[MAXF]; uint32_t K[MAXF];
+    int n = 0;
+    for (uint32_t k = kb; k < ke; ++k) {
+      EvTime T; float u1, u2;
+      if (!corner_time(k, band_end, goal, T, u1, u2)) continue;
+      Tt[n] = T; U1[n] = u1; U2[n] = u2; K[n] = k; ++n;
+    }
+    float cur = __uint_as_float(INF_BITS);
+    EvTime tc = ev_normal(cur, c);
+    for (int i = 0; i < n; ++i) {
+      int b = i;
+      for (int j = i + 1; j < n; ++j)
+        if (ev_less(Tt[j], Tt[b]) || (ev_eq(Tt[j], Tt[b]) && K[j] < K[b])) b = j;
+      const EvTime T = Tt[b]; const float u1 = U1[b], u2 = U2[b]; const uint32_t k = K[b];
+      Tt[b] = Tt[i]; U1[b] = U1[i]; U2[b] = U2[i]; K[b] = K[i];
+      if (!ev_less(T, tc)) break;   // c has been popped before this face fires
+      const float4 w = __ldg(&cor_w[k]);
+      CvpResult r;
+      if (cvp_update_t<false>(u1, u2, cur, w.z, w.y, w.x, r)) { cur = r.value; tc = accept_time(c, r.value, T); win = (int)k; wu1 = u1; wu2 = u2; }
+    }
+    nd = cur; nt = tc;
+  }
+
+  // engine hook: returns true if the label changed (and stores it)
+  __device__ __forceinline__ bool recompute(uint32_t c, float band_end, float goal, const Label& old, float& nd, float& ntau) {
+    int win; float wu1, wu2; EvTime nt;
+    replay(c, band_end, goal, nd, nt, win, wu1, wu2);
+    ntau = nt.a1;
+    if (__float_as_uint(nd) == __float_as_uint(old.d) && ev_eq(nt, old.t)) return false;
+    store_label(c, nd, nt);
     return true;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// CVP, 8 lanes per candidate ("sub-warp pull").  Corner records live in an ELL
+// table: row c = 8 slots x {v1, v2, face, deg} (one 128-byte line) and a matching
+// row of weights, so the 8 lanes of a group fetch a vertex's whole 1-ring with two
+// coalesced 128-byte loads.  Each lane evaluates its own face (the double-precision
+// unfolding) concurrently; the reference's event order is then replayed across the
+// lanes with shuffles.  Vertices with more than 8 faces take the CSR path on lane 0.
+// ---------------------------------------------------------------------------
+constexpr uint32_t ELL_W = 8;
+constexpr int ELL_EMPTY = -1;
+
+struct CvpEllProblem : CvpProblem {
+  const int4* __restrict__ ell_idx;
+  const float4* __restrict__ ell_w;
+
+  // face evaluation without a current label: U = unfolded distance, X = value the reference would
+  // store (U when the angle test passes, else the edge fallback).  accept(cur) <=> U < cur && X < cur.
+  __device__ __forceinline__ static void eval_face(double u1, double u2, double a, double b, double c, double& U, double& X) {
+    const double c_sq = c * c, b_sq = b * b, a_sq = a * a;
+    const double u1_sq = u1 * u1, u2_sq = u2 * u2;
+    const double sx = (c_sq + u1_sq - u2_sq) / (2 * c);
+    const double sy = -sqrt(fmax(u1_sq - sx * sx, 0.0));
+    const double p = (b_sq + c_sq - a_sq) / (2 * c);
+    const double hc = sqrt(fmax(b_sq - p * p, 0.0));
+    const double dy = hc - sy;
+    const double dx = p - sx;
+    const double u3tmp_sq = dx * dx + dy * dy;
+    const double u3tmp = sqrt(u3tmp_sq);
+    U = u3tmp;
+    const double t0a = (a_sq + b_sq - c_sq) / (2 * a * b);
+    const double t1a = (u3tmp_sq + b_sq - u1_sq) / (2 * u3tmp * b);
+    const double t2a = (a_sq + u3tmp_sq - u2_sq) / (2 * a * u3tmp);
+    int fb;
+    if (fabs(t1a) > 1) fb = 1;
+    else if (fabs(t2a) > 1) fb = 2;
+    else if (fabs(t0a) <= 1 && t1a > t0a && t2a > t0a) { X = u3tmp; return; }   // |t0a| > 1: acos(t0a) is NaN in the reference
+    else fb = (t1a > t2a) ? 1 : 2;
+    X = (fb == 1) ? (u1 + b) : (u2 + a);
+  }
+
+  template <class F>
+  __device__ __forceinline__ void activate_lane(uint32_t c, uint32_t j, const int4& ix, int deg, F push) const {
+    if (ix.x != ELL_EMPTY) { push((uint32_t)ix.x); push((uint32_t)ix.y); }
+    if (j == 0 && deg > (int)ELL_W) activate(c, push);   // faces beyond the 8 ELL slots
+  }
+
+  // all 8 lanes of the group call this with the same c; every lane returns the same label
+  __device__ __forceinline__ void replay_sub8(uint32_t c, uint32_t j, unsigned gmask, float band_end, float goal,
+                                              float& nd, EvTime& nt, int4& ix_out, int& deg_out) const {
+    const int lane0 = (threadIdx.x & 31) & ~7;
+    const int4 ix = __ldg(&ell_idx[(size_t)c * ELL_W + j]);
+    ix_out = ix;
+    const int deg = __shfl_sync(gmask, ix.w, lane0);
+    deg_out = deg;
+    if (deg > (int)ELL_W) {   // rare: CSR path on the group's first lane, result broadcast
+      float d0 = 0; EvTime t0 = ev_normal(0.0f, c);
+      if (j == 0) { int win; float a1, a2; replay(c, band_end, goal, d0, t0, win, a1, a2); }
+      nd = __shfl_sync(gmask, d0, lane0);
+      nt.a1 = __shfl_sync(gmask, t0.a1, lane0); nt.a2 = __shfl_sync(gmask, t0.a2, lane0);
+      nt.a3 = __shfl_sync(gmask, t0.a3, lane0); nt.minor = __shfl_sync(gmask, t0.minor, lane0);
+      return;
+    }
+    const float INF = __uint_as_float(INF_BITS);
+    bool valid = ix.x != ELL_EMPTY;
+    EvTime T = ev_normal(INF, 0xffffffffu >> 1);
+    double U = 0.0, X = 0.0;
+    if (valid) {
+      const float4 w = __ldg(&ell_w[(size_t)c * ELL_W + j]);
+      const uint32_t v1 = (uint32_t)ix.x, v2 = (uint32_t)ix.y;
+      const Label a = load_label(v1), b = load_label(v2);
+      valid = face_time(v1, v2, a, b, band_end, goal, T);
+      if (valid) eval_face((double)a.d, (double)b.d, (double)w.z, (double)w.y, (double)w.x, U, X);
+    }
+    // rank of every valid lane in (T, slot) order: all-pairs comparison inside the 8-lane group
+    const unsigned long long hi = ((unsigned long long)__float_as_uint(T.a1) << 32) | __float_as_uint(T.a2);
+    const unsigned long long lo = ((unsigned long long)__float_as_uint(T.a3) << 32) | T.minor;
+    int rank = 0;
+#pragma unroll
+    for (int d = 1; d < 8; ++d) {
+      const int src = lane0 + (int)((j + d) & 7);
+      const unsigned long long ohi = __shfl_sync(gmask, hi, src);
+      const unsigned long long olo = __shfl_sync(gmask, lo, src);
+      const int ovalid = __shfl_sync(gmask, (int)valid, src);
+      const uint32_t oj = (j + d) & 7;
+      if (ovalid && (ohi < hi || (ohi == hi && (olo < lo || (olo == lo && oj < j))))) ++rank;
+    }
+    if (!valid) rank = 99;
+    const unsigned vmask = __ballot_sync(gmask, valid) & gmask;
+    const int nvalid = __popc(vmask);
+    float cur = INF;
+    EvTime tc = ev_normal(INF, c);
+    for (int r = 0; r < nvalid; ++r) {
+      const unsigned who = __ballot_sync(gmask, rank == r) & gmask;
+      const int src = __ffs(who) - 1;
+      EvTime Tw;
+      const unsigned long long whi = __shfl_sync(gmask, hi, src), wlo = __shfl_sync(gmask, lo, src);
+      Tw.a1 = __uint_as_float((uint32_t)(whi >> 32)); Tw.a2 = __uint_as_float((uint32_t)whi);
+      Tw.a3 = __uint_as_float((uint32_t)(wlo >> 32)); Tw.minor = (uint32_t)wlo;
+      if (!ev_less(Tw, tc)) break;
+      const double Uw = __shfl_sync(gmask, U, src);
+      const double Xw = __shfl_sync(gmask, X, src);
+      const double cd = (double)cur;
+      if (Uw < cd && Xw < cd) { cur = (float)Xw; tc = accept_time(c, cur, Tw); }
+    }
+    nd = cur; nt = tc;
   }
 };
 
 // ---------------------------------------------------------------------------
 // Dijkstra: d[c] = min over expandable neighbours u of fl(d[u] + w(u,c));
 // among equal sums the neighbour that pops first wins (strict '<' at
-// dijkstra_mesh_planner.cpp:332): order (d[u], u).
+// dijkstra_mesh_planner.cpp:332): order (d[u], u).  Edge weights are >= 0 so a
+// vertex always pops at its own key: tau = d, minor = 2*id.
 //   adj_nw[k] = {neighbour id, float bits of the edge weight}
 // ---------------------------------------------------------------------------
 struct DijkstraProblem {
@@ -164,11 +318,15 @@ struct DijkstraProblem {
   const uint2* __restrict__ adj_nw;
   const float* __restrict__ cost;
   const uint8_t* __restrict__ invalid;  // may be null
-  unsigned long long* state;
+  uint4* state;
   uint32_t* pred;
   double cost_limit;
 
-  __device__ __forceinline__ unsigned long long load_state(uint32_t v) const { return __ldcg(&state[v]); }
+  __device__ __forceinline__ Label load_label(uint32_t v) const {
+    const uint4 s = __ldcg(&state[v]);
+    Label l; l.d = __uint_as_float(s.x); l.t = ev_normal(__uint_as_float(s.y), v);
+    return l;
+  }
   __device__ __forceinline__ bool eligible(uint32_t x) const { return !(invalid && invalid[x]); }  // :328
 
   template <class F>
@@ -177,14 +335,13 @@ struct DijkstraProblem {
     for (uint32_t k = kb; k < ke; ++k) push(__ldg(&adj_nw[k]).x);
   }
 
-  __device__ __forceinline__ bool recompute(uint32_t c, float band_end, float goal, float d_old, float tau_old,
-                                            float& nd, float& ntau) {
+  __device__ __forceinline__ bool recompute(uint32_t c, float band_end, float goal, const Label& old, float& nd, float& ntau) {
     const uint32_t kb = adj_ptr[c], ke = adj_ptr[c + 1];
     float best = __uint_as_float(INF_BITS), best_du = best; uint32_t best_u = c;
     for (uint32_t k = kb; k < ke; ++k) {
       const uint2 nw = __ldg(&adj_nw[k]);
       const uint32_t u = nw.x;
-      const float du = state_d(load_state(u));
+      const float du = __uint_as_float(__ldcg(&state[u]).x);
       if (!(du < band_end)) continue;
       if (du > goal) continue;                               // :299
       if ((double)__ldg(&cost[u]) > cost_limit) continue;    // :302
@@ -195,13 +352,12 @@ struct DijkstraProblem {
       }
     }
     nd = best; ntau = best;
-    if (__float_as_uint(nd) == __float_as_uint(d_old)) {
+    if (__float_as_uint(nd) == __float_as_uint(old.d)) {
       // same potential; the predecessor can still change among exact ties
-      if (__float_as_uint(nd) == INF_BITS || pred[c] == best_u) return false;
-      pred[c] = best_u;
+      if (__float_as_uint(nd) != INF_BITS && pred[c] != best_u) pred[c] = best_u;
       return false;
     }
-    __stcg(&state[c], pack_state(nd, ntau));
+    __stcg(&state[c], make_uint4(__float_as_uint(nd), __float_as_uint(ntau), 0u, 0u));
     pred[c] = best_u;
     return true;
   }

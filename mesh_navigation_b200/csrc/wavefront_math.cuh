@@ -31,7 +31,15 @@ struct CvpResult {
 // u1,u2 = potentials of v1,v2 ; u3 = current potential of v3 (may be +inf)
 // c = |v1v2|, b = |v1v3|, a = |v2v3| as edge *weights* (cvp:380-390).
 // Returns true iff the reference would have written distances[v3].
-MNB_HD bool cvp_update(double u1, double u2, double u3, double a, double b, double c, CvpResult& r) {
+//
+// ANGLES = true : literal restatement, three acos calls (cvp:456-458), fills r.direction.
+// ANGLES = false: the wavefront hot loop.  theta_i = acos(t_i) is strictly decreasing, so the
+//   reference's comparisons  theta1 < theta0, theta2 < theta0, theta1 < theta2  are evaluated as
+//   t1a > t0a, t2a > t0a, t1a > t2a  without calling acos (the decisions can differ only when two
+//   cosines are closer than one rounding of acos, ~1e-16 relative).  r.direction is NOT filled; the
+//   caller re-evaluates the winning face once with ANGLES = true when it stores the result.
+template <bool ANGLES>
+MNB_HD bool cvp_update_t(double u1, double u2, double u3, double a, double b, double c, CvpResult& r) {
   const double c_sq = c * c, b_sq = b * b, a_sq = a * a;
   const double u1_sq = u1 * u1, u2_sq = u2 * u2;
   const double sx = (c_sq + u1_sq - u2_sq) / (2 * c);
@@ -51,7 +59,7 @@ MNB_HD bool cvp_update(double u1, double u2, double u3, double a, double b, doub
     edge_fallback = 1;
   } else if (fabs(t2a) > 1) {
     edge_fallback = 2;
-  } else {
+  } else if (ANGLES) {
     const double theta0 = acos(t0a);
     const double theta1 = acos(t1a);
     const double theta2 = acos(t2a);
@@ -62,6 +70,18 @@ MNB_HD bool cvp_update(double u1, double u2, double u3, double a, double b, doub
       return true;
     }
     edge_fallback = (theta1 < theta2) ? 1 : 2;
+  } else {
+    // NaN cosines (degenerate triangles) make every acos comparison false in the reference:
+    // '>' on NaN is false as well, so the same branch (u2 + a) is taken.  The reference guards
+    // |t1a|, |t2a| <= 1 but NOT t0a: with cost-weighted (non-geometric) edge weights |t0a| can exceed
+    // 1, acos(t0a) is NaN and both comparisons against theta0 are false.
+    if (fabs(t0a) <= 1 && t1a > t0a && t2a > t0a) {
+      r.value = (float)u3tmp;
+      r.pred_sel = (t1a > t2a) ? 1 : 2;
+      r.direction = 0.0f;
+      return true;
+    }
+    edge_fallback = (t1a > t2a) ? 1 : 2;
   }
   u3tmp = (edge_fallback == 1) ? (u1 + b) : (u2 + a);
   if (!(u3tmp < u3)) return false;
@@ -69,6 +89,10 @@ MNB_HD bool cvp_update(double u1, double u2, double u3, double a, double b, doub
   r.pred_sel = edge_fallback;
   r.direction = 0.0f;
   return true;
+}
+
+MNB_HD bool cvp_update(double u1, double u2, double u3, double a, double b, double c, CvpResult& r) {
+  return cvp_update_t<true>(u1, u2, u3, a, b, c, r);
 }
 
 // d1,d2 = distances of v1,v2 ; a = |v2v3| ; b = |v1v3| ; dot = cos of the angle at v3.

@@ -387,7 +387,12 @@ inline double now_s() {
 
 }  // namespace
 
+// debugging aid for the tests/tools: when set, orc_cvp records the pop sequence number of every vertex
+static uint32_t* g_pop_index = nullptr;
+
 extern "C" {
+
+void orc_debug_set_pop_buffer(uint32_t* buf) { g_pop_index = buf; }
 
 void* orc_mesh_create(uint32_t V, uint32_t F, const float* pos, const uint32_t* faces,
                       const uint32_t* edges /*nullable*/, uint32_t E) {
@@ -523,6 +528,7 @@ uint32_t orc_cvp(void* h, const float* edge_weights, const float* vertex_costs, 
   while (!pq.isEmpty()) {                                                            // :747
     uint32_t cur = pq.popMin().key;
     fixed[cur] = 1;                                                                  // :751
+    if (g_pop_index) g_pop_index[cur] = (uint32_t)fixed_set_cnt;
     fixed_set_cnt++;
     if (distances[cur] < hi_water) { n_back++; max_back = std::max(max_back, (double)(hi_water - distances[cur])); }
     else hi_water = distances[cur];

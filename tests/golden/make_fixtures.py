@@ -1,0 +1,45 @@
+"""Regenerates tests/golden/*.npz from the oracle (python -m tests.golden.make_fixtures).
+
+The reference cannot be built or imported in this container (lvr2 / ROS 2 absent), so these are
+ORACLE outputs on tiny seeded meshes -- regression fixtures for the restatement, not reference output.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+from tests.util import centre_seed, disc_lethals, mesh_case  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def run_case(name):
+    terrain = "terrain" in name
+    pos, faces = mesh_case(30, terrain)
+    m = O.OracleMesh(pos, faces)
+    ed = m.edge_distances()
+    rng = np.random.default_rng(3)
+    vc = (rng.random(m.V) * 0.6).astype(np.float32)
+    w = m.edge_weights(vc, ed, 1.0)
+    v, f, sp = centre_seed(pos, faces, (0.4, 0.55))
+    if name.startswith("cvp"):
+        r = m.cvp(w, vc, f, sp)
+        return dict(dist=r["dist"], pred=r["pred"], direction=r["direction"], cut=r["cutting_face"].astype(np.int32))
+    if name.startswith("dijkstra"):
+        r = m.dijkstra(w, vc, v)
+        return dict(dist=r["dist"], pred=r["pred"])
+    if name.startswith("inflation"):
+        le = disc_lethals(pos, 3, 0.25, seed=5)
+        r = m.inflation(ed, le)
+        return dict(dist=r["dist"], cost=r["cost"])
+    raise KeyError(name)
+
+
+if __name__ == "__main__":
+    for n in ["cvp_planar30", "cvp_terrain30", "dijkstra_terrain30", "inflation_terrain30"]:
+        np.savez_compressed(os.path.join(HERE, n + ".npz"), **run_case(n))
+        print("wrote", n)

@@ -1,0 +1,133 @@
+"""CPU tests: pin the oracle against every known answer the reference's own tests hold for the
+hot path (mesh_layers/test/inflation_layer_test.cpp) plus derived golden vectors and fixtures."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import centre_seed, mesh_case
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def triangle(O):
+    # inflation_layer_test.cpp:7-23 genTriangle()
+    pos = np.array([[0, 0, 0], [0.5, 0, 0], [0, 0.5, 0]], np.float32)
+    faces = np.array([[0, 1, 2]], np.uint32)
+    return O.OracleMesh(pos, faces)
+
+
+def test_reference_wave_front_update(oracle_mod):
+    """inflation_layer_test.cpp:38-80 test_wave_front_update"""
+    O = oracle_mod
+    m = triangle(O)
+    ew = m.edge_distances()                       # calcEdgeWeights(): Euclidean (:26-36)
+    e01 = [i for i, e in enumerate(m.edges.tolist()) if e == [0, 1]][0]
+    dist = np.array([0.0, ew[e01], np.inf], np.float32)   # sparse map: v2 has no distance yet
+    vec = np.zeros((3, 3), np.float32)
+    assert m.inflation_wavefront_update(dist, vec, 5.0, ew, 0, 0, 1, 2) is True      # EXPECT_TRUE :62
+    assert dist[2] == np.float32(0.5)                                                # EXPECT_FLOAT_EQ :76
+    assert O.fading(dist[2], 0.5, 1.5, 1.0, 0.9, 1.0) == np.float32(0.9)             # :79
+
+
+def test_reference_fading(oracle_mod):
+    """inflation_layer_test.cpp:83-100 test_fading"""
+    O = oracle_mod
+    f = lambda d: O.fading(d, 0.5, 1.5, 1.0, 0.9, 1.0)
+    assert f(0.2) == np.float32(0.9)
+    assert 0.0 < f(0.6) < 0.9
+    assert abs(f(0.6) - 0.9 * np.exp(-0.1)) < 1e-6
+    assert f(2.0) == 0.0
+    assert f(0.0) == 1.0          # lethality branch (inflation_layer.cpp:337-338)
+
+
+def test_derived_cvp_triangle(oracle_mod):
+    """SURVEY 8c derived vector: same triangle through CVP waveFrontUpdate -> d[v2]=0.5, pred v0, theta 0"""
+    m = triangle(oracle_mod)
+    ew = m.edge_distances()
+    dist = np.array([0.0, 0.5, np.inf], np.float32)
+    pred = np.arange(3, dtype=np.uint32); dr = np.zeros(3, np.float32); cut = -np.ones(3, np.int32)
+    assert m.cvp_wavefront_update(ew, 0, 0, 1, 2, dist, pred, dr, cut)
+    assert dist[2] == np.float32(0.5) and pred[2] == 0 and dr[2] == 0.0 and cut[2] == 0
+
+
+def test_edge_weights_formula(oracle_mod):
+    """mesh_map.cpp:539-553"""
+    pos, faces = mesh_case(12, True)
+    m = oracle_mod.OracleMesh(pos, faces)
+    ed = m.edge_distances()
+    rng = np.random.default_rng(0)
+    vc = rng.random(m.V).astype(np.float32)
+    vc[5] = np.inf
+    w = m.edge_weights(vc, ed, 1.5)
+    a, b = m.edges[:, 0], m.edges[:, 1]
+    infm = np.isinf(vc[a]) | np.isinf(vc[b])
+    assert np.isinf(w[infm]).all() and infm.sum() > 0
+    edge_cost = ((ed * (vc[a] + vc[b])).astype(np.float32).astype(np.float64) / 2.0).astype(np.float32)   # :550
+    expect = (ed.astype(np.float64) + np.float64(1.5) * edge_cost.astype(np.float64)).astype(np.float32)  # :552
+    assert (w[~infm] == expect[~infm]).all()
+    assert (m.edge_weights(vc, ed, 0.0)[~infm] == ed[~infm]).all()
+
+
+def test_planar_sanity(oracle_mod):
+    """Dijkstra >= Euclid, CVP ~ Euclid on the planar jittered grid (SURVEY 8c sanity vectors)."""
+    pos, faces = mesh_case(100, False)
+    m = oracle_mod.OracleMesh(pos, faces)
+    ed = m.edge_distances(); vc = np.zeros(m.V, np.float32)
+    v, f, sp = centre_seed(pos, faces)
+    rd = m.dijkstra(ed, vc, v)
+    eu = np.linalg.norm(pos - pos[v], axis=1)
+    assert (rd["dist"] >= eu - 1e-4).all() and rd["fixed"] == m.V
+    rc = m.cvp(ed, vc, f, sp)
+    eu = np.linalg.norm(pos - sp, axis=1)
+    far = eu > 1.0
+    assert np.max(np.abs(rc["dist"][far] - eu[far]) / eu[far]) < 0.03      # discretisation error of the method
+    assert (rc["dist"] >= eu - 1e-5).all()                                  # never shorter than the straight line
+    # predecessor trees are consistent
+    p = rd["pred"]; nz = p != np.arange(m.V)
+    assert (rd["dist"][p[nz]] < rd["dist"][nz]).all()
+
+
+def test_tie_modes_agree_on_jittered_mesh(oracle_mod):
+    """canonical tie-break == plain lvr2-style heap unless two heap keys are bit-identical"""
+    pos, faces = mesh_case(60, True)
+    m = oracle_mod.OracleMesh(pos, faces)
+    ed = m.edge_distances(); vc = np.zeros(m.V, np.float32)
+    v, f, sp = centre_seed(pos, faces)
+    a = m.cvp(ed, vc, f, sp, canonical_ties=True); b = m.cvp(ed, vc, f, sp, canonical_ties=False)
+    assert (a["dist"] == b["dist"]).all()
+    a = m.dijkstra(ed, vc, v, canonical_ties=True); b = m.dijkstra(ed, vc, v, canonical_ties=False)
+    assert (a["dist"] == b["dist"]).all() and (a["pred"] == b["pred"]).all()
+
+
+def test_goal_cutoff_and_no_path(oracle_mod):
+    pos, faces = mesh_case(50, False)
+    m = oracle_mod.OracleMesh(pos, faces)
+    ed = m.edge_distances(); vc = np.zeros(m.V, np.float32)
+    v, f, sp = centre_seed(pos, faces, (0.25, 0.25))
+    rv, rf, _ = centre_seed(pos, faces, (0.6, 0.6))
+    full = m.dijkstra(ed, vc, v)
+    cut = m.dijkstra(ed, vc, v, robot_vertex=rv)
+    assert cut["outcome"] == 0 and cut["expanded"] < full["expanded"]
+    lim = np.float32(full["dist"][rv] + 0.3)
+    inside = full["dist"] <= lim
+    assert (cut["dist"][inside] == full["dist"][inside]).all()
+    # wall of lethal cost between seed and robot -> NO_PATH_FOUND (54)
+    vc2 = vc.copy(); vc2[(pos[:, 0] > 2.2) & (pos[:, 0] < 2.5)] = 2.0
+    assert m.dijkstra(ed, vc2, v, robot_vertex=rv)["outcome"] == 54
+    assert m.cvp(ed, vc2, f, sp, robot_face=rf)["outcome"] == 54
+    assert m.cvp(ed, vc, f, sp, robot_face=rf)["outcome"] == 0
+
+
+@pytest.mark.parametrize("name", ["cvp_planar30", "cvp_terrain30", "dijkstra_terrain30", "inflation_terrain30"])
+def test_committed_fixtures(oracle_mod, name):
+    """Fixtures under tests/golden were generated by tests/golden/make_fixtures.py from this oracle
+    (the reference cannot run here); they guard the oracle against silent changes."""
+    from tests.golden.make_fixtures import run_case
+    path = os.path.join(GOLD, name + ".npz")
+    assert os.path.exists(path), "run python -m tests.golden.make_fixtures"
+    gold = np.load(path)
+    now = run_case(name)
+    for k in gold.files:
+        a, b = gold[k], now[k]
+        assert a.shape == b.shape and (a.view(np.uint32) == b.view(np.uint32)).all(), f"{name}:{k} drifted"

@@ -1,0 +1,42 @@
+"""Shared helpers for the tests (mesh cases, seeds)."""
+import numpy as np
+
+from mesh_navigation_b200 import synth
+
+
+def mesh_case(n, terrain, seed=42):
+    pos, faces = synth.grid_mesh(n, n, terrain=terrain, seed=seed)
+    return pos, faces
+
+
+def face_of_vertex(faces, v):
+    return int(np.where((faces == v).any(1))[0][0])
+
+
+def centre_seed(pos, faces, frac=(0.5, 0.5)):
+    n_extent = pos[:, :2].max(0)
+    v = synth.nearest_vertex(pos, [n_extent[0] * frac[0], n_extent[1] * frac[1], float(pos[:, 2].mean())])
+    f = face_of_vertex(faces, v)
+    return v, f, pos[faces[f]].mean(0).astype(np.float32)
+
+
+def rel_err(got, ref):
+    fin = np.isfinite(ref)
+    assert (np.isfinite(got) == fin).all(), "reached sets differ"
+    r = np.zeros_like(ref, dtype=np.float64)
+    r[fin] = np.abs(got[fin].astype(np.float64) - ref[fin]) / np.maximum(ref[fin], 1e-30)
+    return r
+
+
+def disc_lethals(pos, n_discs, radius, seed=7):
+    """Synthetic obstacle lethals: vertices inside n discs at PCG32(seed) positions."""
+    V = pos.shape[0]
+    centres = synth.pcg32_stream(seed, n_discs, V)
+    mask = np.zeros(V, dtype=bool)
+    xy = pos[:, :2]
+    for c in centres:
+        d = xy - xy[c]
+        lo = np.abs(d).max(1) <= radius
+        idx = np.where(lo)[0]
+        mask[idx[(d[idx] ** 2).sum(1) <= radius * radius]] = True
+    return np.where(mask)[0].astype(np.uint32)

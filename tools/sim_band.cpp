@@ -1,8 +1,9 @@
 // DEVELOPMENT TOOL (not product, not oracle): sequential CPU emulation of the
-// round structure of the GPU "sliding band" wavefront, used in the build
-// container (no GPU) to check the parallel semantics against the oracle before
-// the CUDA kernel runs on a B200.  Shares wavefront_math.cuh / topology.hpp
-// with the kernels so the per-face arithmetic is the same source.
+// round structure of the GPU "sliding band" wavefront (Jacobi rounds), used in the
+// build container (no GPU) to check the parallel semantics against the oracle
+// before the CUDA kernel runs on a B200.  Mirrors CvpProblem::replay / face_time and
+// run_band_rounds (band_engine.cuh, problems.cuh); shares wavefront_math.cuh /
+// topology.hpp with the kernels so the per-face arithmetic is the same source.
 //
 // g++ -O2 -ffp-contract=off -shared -fPIC -o tools/libsimband.so tools/sim_band.cpp
 #include <cmath>
@@ -19,125 +20,160 @@ using namespace mnb;
 namespace {
 constexpr float FINF = std::numeric_limits<float>::infinity();
 
+constexpr int MAXL = 12;
+static int g_levels = 3;   // the CUDA labels track 3 water levels
+struct Tm3 { float a[MAXL]; uint32_t minor; };
+struct Lab { float d; Tm3 t; };
+static inline bool tless(const Tm3& x, const Tm3& y) {
+  for (int i = 0; i < g_levels; ++i) { if (x.a[i] < y.a[i]) return true; if (x.a[i] > y.a[i]) return false; }
+  return x.minor < y.minor;
+}
+static inline bool teq(const Tm3& x, const Tm3& y) {
+  for (int i = 0; i < g_levels; ++i) if (x.a[i] != y.a[i]) return false;
+  return x.minor == y.minor;
+}
+static inline Tm3 tnormal(float key, uint32_t c) { Tm3 t{}; t.a[0] = key; t.minor = 2u * c; return t; }
+
 struct Sim {
   HostTopology T;
   const float* w; const float* cost; const uint8_t* invalid;
-  double cost_limit; int gate; int flags_;
-  std::vector<float> d, tau;
-  std::vector<uint8_t> fixed;
-  float band_end;
+  double cost_limit;
+  std::vector<Lab> L;
+  uint32_t s[3]; uint32_t seed_noexpand = 0;
+  float band_end, goal;
 
-  // recompute vertex c from scratch, emulating the reference's per-vertex event order
-  float recompute(uint32_t c, float* tau_out) {
-    struct Cand { float T; uint32_t Tid; float u1, u2, a, b, cw; };
+  int seed_index(uint32_t v) const { return v == s[0] ? 0 : (v == s[1] ? 1 : (v == s[2] ? 2 : -1)); }
+
+  bool face_time(uint32_t v1, uint32_t v2, Tm3& T) const {
+    const Lab &a = L[v1], &b = L[v2];
+    if (!(a.d < band_end) || !(b.d < band_end)) return false;
+    if (invalid && (invalid[v1] || invalid[v2])) return false;
+    const int i1 = seed_index(v1), i2 = seed_index(v2);
+    const Tm3 &ta = a.t, &tb = b.t;
+    const bool v1_later = tless(tb, ta);
+    if (i1 >= 0 && i2 >= 0) {
+      const bool e1 = !((seed_noexpand >> i1) & 1u), e2 = !((seed_noexpand >> i2) & 1u);
+      if (!e1 && !e2) return false;
+      const bool use1 = e1 && (!e2 || !v1_later);
+      T = use1 ? ta : tb;
+      return true;
+    }
+    const int il = v1_later ? i1 : i2;
+    if (il >= 0 && ((seed_noexpand >> il) & 1u)) return false;
+    if ((v1_later ? a.d : b.d) > goal) return false;
+    T = v1_later ? ta : tb;
+    return true;
+  }
+
+  Lab replay(uint32_t c) const {
+    struct Cand { Tm3 T; uint32_t k; float u1, u2; };
     Cand cs[64]; int n = 0;
     for (uint32_t k = T.vcor_ptr[c]; k < T.vcor_ptr[c + 1] && n < 64; ++k) {
-      const uint32_t v1 = T.cor_v1[k], v2 = T.cor_v2[k];
-      if (invalid && (invalid[v1] || invalid[v2])) continue;
-      const float d1 = d[v1], d2 = d[v2];
-      const bool av1 = fixed[v1] || d1 < band_end, av2 = fixed[v2] || d2 < band_end;
-      if (!av1 || !av2) continue;
-      // event time of a vertex = (tau, id) lexicographic; the later of (v1,v2) is the one whose
-      // pop visits the face: it must expand (cvp:757)
-      const bool v1_later = tau[v1] > tau[v2] || (tau[v1] == tau[v2] && v1 > v2);
-      const uint32_t later = v1_later ? v1 : v2;
-      if (!(cost[later] < cost_limit)) continue;
-      cs[n++] = {tau[later], later, d1, d2, w[T.cor_ea[k]], w[T.cor_eb[k]], w[T.cor_ec[k]]};
+      Tm3 Tt;
+      if (!face_time(T.cor_v1[k], T.cor_v2[k], Tt)) continue;
+      cs[n++] = {Tt, k, L[T.cor_v1[k]].d, L[T.cor_v2[k]].d};
     }
-    float cur = FINF, tcur = FINF;
+    float cur = FINF; Tm3 tc = tnormal(FINF, c);
     for (int i = 0; i < n; ++i) {
-      int best = i;
+      int b = i;
       for (int j = i + 1; j < n; ++j)
-        if (cs[j].T < cs[best].T || (cs[j].T == cs[best].T && cs[j].Tid < cs[best].Tid)) best = j;
-      std::swap(cs[i], cs[best]);
-      const bool before = cs[i].T < tcur || (cs[i].T == tcur && cs[i].Tid < c);
-      if (gate && !before) break;   // c would already have been popped
+        if (tless(cs[j].T, cs[b].T) || (!tless(cs[b].T, cs[j].T) && cs[j].k < cs[b].k)) b = j;
+      std::swap(cs[i], cs[b]);
+      if (!tless(cs[i].T, tc)) break;
       CvpResult r;
-      if (cvp_update(cs[i].u1, cs[i].u2, cur, cs[i].a, cs[i].b, cs[i].cw, r)) {
+      const uint32_t k = cs[i].k;
+      if (cvp_update_t<false>(cs[i].u1, cs[i].u2, cur, w[T.cor_ea[k]], w[T.cor_eb[k]], w[T.cor_ec[k]], r)) {
         cur = r.value;
-        tcur = std::fmax(cur, cs[i].T);
-        if ((flags_ & 4) && tcur == cs[i].T && !(cs[i].Tid < c)) tcur = std::nextafter(tcur, FINF);
+        const Tm3& F = cs[i].T;
+        // monotonic stack of water levels: keep the levels above the new key, then the key itself
+        Tm3 nt{}; int lvl = 0;
+        while (lvl < g_levels && !(r.value > F.a[lvl])) { nt.a[lvl] = F.a[lvl]; ++lvl; }
+        if (lvl < g_levels) { nt.a[lvl] = r.value; nt.minor = 2u * c; }
+        else nt.minor = F.minor + 1u;          // deeper than we track: right after the trigger
+        tc = nt;
       }
     }
-    *tau_out = tcur;
-    return cur;
+    return {cur, tc};
   }
 };
 }  // namespace
+
+static std::vector<Lab> g_last;
+extern "C" void sim_get_label(uint32_t v, double* out) { out[0]=g_last[v].d; out[1]=g_last[v].t.a[0]; out[2]=g_last[v].t.a[1]; out[3]=g_last[v].t.minor; }
 
 extern "C" int sim_cvp_band(uint32_t V, uint32_t F, const uint32_t* faces, const uint32_t* edges, uint32_t E,
                             const float* pos, const float* edge_weights, const float* vertex_costs,
                             const uint8_t* invalid, uint32_t seed_face, const float* seed_pos,
                             double cost_limit, double delta, int flags, float* out_dist, double* stats) {
   Sim S;
+  g_levels = flags > 0 ? flags : 3;
   S.T.build(V, F, faces, edges, E);
   S.w = edge_weights; S.cost = vertex_costs; S.invalid = invalid; S.cost_limit = cost_limit;
-  S.gate = flags & 1; S.flags_ = flags;
-  const bool use_tau = flags & 2;
-  S.d.assign(V, FINF); S.tau.assign(V, FINF); S.fixed.assign(V, 0);
-  std::vector<uint8_t> in_cand(V, 0);
-  std::vector<uint32_t> cand;
-  auto add_neighbours = [&](uint32_t v) {
+  S.goal = FINF;
+  S.L.resize(V);
+  for (uint32_t v = 0; v < V; ++v) { S.L[v].d = FINF; S.L[v].t = tnormal(FINF, v); }
+  std::vector<uint8_t> mark(V, 0);   // 0 none, 1 cand, 2 fixed, 3 cand+activated
+  std::vector<uint32_t> cand, next;
+  auto eligible = [&](uint32_t x) { return !(invalid && invalid[x]) && !((double)vertex_costs[x] >= cost_limit); };
+  auto activate = [&](uint32_t v, std::vector<uint32_t>& out) {
     for (uint32_t k = S.T.vcor_ptr[v]; k < S.T.vcor_ptr[v + 1]; ++k)
       for (uint32_t x : {S.T.cor_v1[k], S.T.cor_v2[k]})
-        if (!S.fixed[x] && !in_cand[x] && !(invalid && invalid[x]) && vertex_costs[x] < cost_limit) {
-          in_cand[x] = 1; cand.push_back(x);
-        }
+        if (mark[x] == 0 && eligible(x)) { mark[x] = 1; out.push_back(x); }
   };
-  float seed_min = FINF;
+  float seed_min = FINF, seed_max = 0;
   for (int k = 0; k < 3; ++k) {
     const uint32_t v = faces[3 * (size_t)seed_face + k];
+    S.s[k] = v;
     const float dx = seed_pos[0] - pos[3 * (size_t)v], dy = seed_pos[1] - pos[3 * (size_t)v + 1],
                 dz = seed_pos[2] - pos[3 * (size_t)v + 2];
-    S.d[v] = std::sqrt(dx * dx + dy * dy + dz * dz);
-    S.fixed[v] = 1;
-    seed_min = std::fmin(seed_min, S.d[v]);
+    const float d = std::sqrt(dx * dx + dy * dy + dz * dz);
+    S.L[v].d = d; S.L[v].t = tnormal(d, v);
+    mark[v] = 2;
+    seed_min = std::fmin(seed_min, d); seed_max = std::fmax(seed_max, d);
+    if (((double)vertex_costs[v] >= cost_limit) || (invalid && invalid[v])) S.seed_noexpand |= 1u << k;
   }
-  for (int k = 0; k < 3; ++k) { const uint32_t v = faces[3 * (size_t)seed_face + k]; S.tau[v] = seed_min; }
-  for (int k = 0; k < 3; ++k) add_neighbours(faces[3 * (size_t)seed_face + k]);
+  for (int k = 0; k < 3; ++k) activate(S.s[k], cand);
 
   size_t rounds = 0, recomputes = 0;
-  std::vector<float> nd, nt;
-  std::vector<uint8_t> was_avail;
-  const size_t max_rounds = 200000;
+  float m_prev = 0.0f, lo_prev = seed_min, band_end_prev = std::nextafter(seed_max, FINF);
+  const size_t max_rounds = 2 * (size_t)V + 64;
+  std::vector<Lab> nl;
+  if (stats) stats[2] = 0;
   while (!cand.empty()) {
-    rounds++;
-    if (rounds > max_rounds) { if (stats) { stats[0] = -1; } break; }
-    float lo = FINF;
-    for (uint32_t c : cand) lo = std::fmin(lo, S.d[c]);
-    S.band_end = (lo == FINF) ? FINF : (float)(lo + delta);
-    nd.resize(cand.size()); nt.resize(cand.size());
-    for (size_t i = 0; i < cand.size(); ++i) { nd[i] = S.recompute(cand[i], &nt[i]); recomputes++; }
-    float m = FINF; bool any = false;
-    const size_t ncand = cand.size();
-    for (size_t i = 0; i < ncand; ++i) {
-      const uint32_t c = cand[i];
-      const float old = S.d[c];
-      if (nd[i] != old) { any = true; m = std::fmin(m, std::fmin(old, nd[i])); }
-    }
-    for (size_t i = 0; i < ncand; ++i) {
-      const uint32_t c = cand[i];
-      const bool newly_avail = !(S.d[c] < S.band_end) && (nd[i] < S.band_end);
-      S.d[c] = nd[i]; S.tau[c] = use_tau ? nt[i] : nd[i];
-      if (newly_avail || (nd[i] < S.band_end)) add_neighbours(c);
-    }
-    // everything strictly below the smallest changed value is a converged prefix
-    const float fix_below = any ? m : S.band_end;
-    size_t wr = 0;
+    if (rounds > 0 && m_prev == FINF && lo_prev == FINF) break;
+    if (rounds > max_rounds) { if (stats) stats[2] = 1; break; }
+    float band_end = (float)(lo_prev + (float)delta);
+    if (!(band_end > band_end_prev)) band_end = band_end_prev;
+    S.band_end = band_end;
+    next.clear();
+    float m = FINF, lo = FINF;
+    // Jacobi: decide "fixed" on the labels of the previous round, recompute the rest from old labels
+    nl.resize(cand.size());
+    std::vector<uint8_t> fixed_now(cand.size(), 0);
     for (size_t i = 0; i < cand.size(); ++i) {
       const uint32_t c = cand[i];
-      if (S.d[c] < fix_below && S.d[c] < S.band_end) { S.fixed[c] = 1; in_cand[c] = 0; }
-      else cand[wr++] = c;
+      const Lab old = S.L[c];
+      if (old.t.a[0] < m_prev && old.t.a[0] < band_end_prev) { fixed_now[i] = 1; continue; }
+      nl[i] = S.replay(c); recomputes++;
     }
-    cand.resize(wr);
-    if (!any && fix_below == FINF) {
-      // nothing labelled and nothing changed: remaining candidates are unreachable
-      bool labelled = false;
-      for (uint32_t c : cand) if (S.d[c] < FINF) { labelled = true; break; }
-      if (!labelled) break;
+    for (size_t i = 0; i < cand.size(); ++i) {
+      const uint32_t c = cand[i];
+      if (fixed_now[i]) { mark[c] = 2; continue; }
+      const Lab old = S.L[c];
+      if (nl[i].d != old.d || !teq(nl[i].t, old.t)) {
+        m = std::fmin(m, std::fmin(old.t.a[0], nl[i].t.a[0]));
+        S.L[c] = nl[i];
+      }
+      lo = std::fmin(lo, nl[i].d);
+      next.push_back(c);
+      if (nl[i].d < FINF && mark[c] == 1) { mark[c] = 3; activate(c, next); }
     }
+    cand.swap(next);
+    m_prev = m; lo_prev = lo; band_end_prev = band_end;
+    rounds++;
   }
-  for (uint32_t v = 0; v < V; ++v) out_dist[v] = S.d[v];
+  for (uint32_t v = 0; v < V; ++v) out_dist[v] = S.L[v].d;
+  g_last = S.L;
   if (stats) { stats[0] = (double)rounds; stats[1] = (double)recomputes; }
   return 0;
 }
