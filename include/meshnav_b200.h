@@ -124,6 +124,28 @@ typedef struct mnb_inflation_params {
 int32_t mnb_inflate(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, const uint8_t* invalid /* V or NULL */,
                     const mnb_inflation_params* params, float* out_dist, float* out_cost);
 
+/* ---- geometric cost layers + MaxCombinationLayer (mesh_layers/src/*_layer.cpp) -------------------
+ * HeightDiffLayer::computeLayer (height_diff_layer.cpp:103-110), RoughnessLayer (roughness_layer.cpp:91-147),
+ * SteepnessLayer (steepness_layer.cpp:100-170), RidgeLayer (ridge_layer.cpp:101-187), ClearanceLayer cost
+ * mapping (clearance_layer.cpp:67-99, on a caller-provided clearance array; NULL = +inf, no ray hits),
+ * BorderLayer (border_layer.cpp:104-110), computeLethals (cost > threshold) and
+ * MaxCombinationLayer::computeLayer (combination_layer.cpp:44-85), fused into ONE per-vertex kernel.
+ * out_costs: 6*V floats, layer-major in the order height_diff, roughness, steepness, ridge, clearance,
+ * border; out_combined: V; out_lethal_mask: V bytes, bit i = lethal in layer i.  Any output may be NULL;
+ * the results also stay resident on the device for chaining. */
+typedef struct mnb_layer_params {
+  double height_diff_threshold, height_diff_radius;           /* 0.185, 0.3 */
+  double roughness_threshold, roughness_radius;               /* 0.3, 0.3 */
+  double steepness_threshold;                                 /* 0.3 */
+  double ridge_threshold, ridge_radius;                       /* 0.3, 0.3 */
+  double clearance_robot_height, clearance_height_inflation;  /* 0.5, 0.3 */
+  double border_threshold, border_cost;                       /* 0.5, 1.0 */
+} mnb_layer_params;
+int32_t mnb_compute_layers(mnb_ctx* ctx, const mnb_layer_params* params, const float* clearance /* V or NULL */,
+                           float* out_costs, float* out_combined, uint8_t* out_lethal_mask);
+/* lvr2::calcVertexNormals equivalent (mesh_map.cpp:374): normalised sum of incident face normals */
+int32_t mnb_get_vertex_normals(mnb_ctx* ctx, float* out_normals /* 3V */);
+
 /* ---- cancel (CVPMeshPlanner::cancel / DijkstraMeshPlanner::cancel) ------- */
 int32_t mnb_cancel(mnb_ctx* ctx);
 

@@ -22,6 +22,21 @@ class InflationParams(C.Structure):
                 ("inscribed_value", C.c_double), ("cost_scaling_factor", C.c_double)]
 
 
+class LayerParams(C.Structure):
+    """config structs at the end of mesh_layers/include/mesh_layers/*_layer.h (doubles)"""
+    _fields_ = [(n, C.c_double) for n in (
+        "height_diff_threshold", "height_diff_radius", "roughness_threshold", "roughness_radius", "steepness_threshold",
+        "ridge_threshold", "ridge_radius", "clearance_robot_height", "clearance_height_inflation", "border_threshold",
+        "border_cost")]
+
+    @staticmethod
+    def defaults():
+        return LayerParams(0.185, 0.3, 0.3, 0.3, 0.3, 0.3, 0.3, 0.5, 0.3, 0.5, 1.0)
+
+
+LAYER_NAMES = ["height_diff", "roughness", "steepness", "ridge", "clearance", "border"]
+
+
 class Stats(C.Structure):
     _fields_ = [("rounds", C.c_uint64), ("recomputes", C.c_uint64), ("settled", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("kernel_ms", C.c_float)]
@@ -32,7 +47,7 @@ EXPORTS = [
     "mnb_create", "mnb_destroy", "mnb_last_error", "mnb_set_pointer_mode", "mnb_stream", "mnb_set_mesh",
     "mnb_num_vertices", "mnb_num_faces", "mnb_num_edges", "mnb_get_edges", "mnb_get_edge_distances",
     "mnb_compute_edge_weights", "mnb_set_costs", "mnb_dijkstra", "mnb_cvp", "mnb_cvp_batch", "mnb_inflate",
-    "mnb_cancel", "mnb_get_stats", "mnb_set_tuning",
+    "mnb_cancel", "mnb_get_stats", "mnb_set_tuning", "mnb_compute_layers", "mnb_get_vertex_normals",
 ]
 
 _lib = None
@@ -63,6 +78,8 @@ def load():
     L.mnb_cvp.restype = i32; L.mnb_cvp.argtypes = [vp, u32, vp, i64, dbl, dbl, vp, vp, vp, vp]
     L.mnb_cvp_batch.restype = i32; L.mnb_cvp_batch.argtypes = [vp, u32, vp, vp, dbl, vp]
     L.mnb_inflate.restype = i32; L.mnb_inflate.argtypes = [vp, vp, u32, vp, C.POINTER(InflationParams), vp, vp]
+    L.mnb_compute_layers.restype = i32; L.mnb_compute_layers.argtypes = [vp, C.POINTER(LayerParams), vp, vp, vp, vp]
+    L.mnb_get_vertex_normals.restype = i32; L.mnb_get_vertex_normals.argtypes = [vp, vp]
     L.mnb_cancel.restype = i32; L.mnb_cancel.argtypes = [vp]
     L.mnb_get_stats.restype = i32; L.mnb_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.mnb_set_tuning.restype = i32; L.mnb_set_tuning.argtypes = [vp, f32, i32, i32]

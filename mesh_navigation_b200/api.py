@@ -103,6 +103,23 @@ class MeshMap:
         assert vc.size == self.V and ew.size == self.E
         self._check(self.L.mnb_set_costs(self._ctx, _p(vc), _p(ew), _p(inv)))
 
+    def vertexNormals(self) -> np.ndarray:
+        out = np.empty((self.V, 3), dtype=np.float32)
+        self._check(self.L.mnb_get_vertex_normals(self._ctx, _p(out)))
+        return out
+
+    def computeLayers(self, params=None, clearance=None) -> dict:
+        """the six geometric layers + MaxCombinationLayer + lethal masks in one fused kernel"""
+        P = params or _lib.LayerParams.defaults()
+        cl = None if clearance is None else np.ascontiguousarray(clearance, dtype=np.float32)
+        costs = np.empty((6, self.V), dtype=np.float32)
+        comb = np.empty(self.V, dtype=np.float32)
+        mask = np.empty(self.V, dtype=np.uint8)
+        self._check(self.L.mnb_compute_layers(self._ctx, C.byref(P), _p(cl), _p(costs), _p(comb), _p(mask)))
+        r = {n: costs[i] for i, n in enumerate(_lib.LAYER_NAMES)}
+        r.update(combined=comb, lethal_mask=mask, **self.stats())
+        return r
+
     def stats(self) -> dict:
         s = _lib.Stats()
         self._check(self.L.mnb_get_stats(self._ctx, C.byref(s)))

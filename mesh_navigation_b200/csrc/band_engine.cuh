@@ -65,7 +65,7 @@ constexpr uint32_t MARK_NONE = 0, MARK_CAND = 1, MARK_FIXED = 2, MARK_CAND_ACT =
 struct GroupCtl {               // one per wavefront group, global memory
   unsigned int count[3];        // candidate list sizes (ring over rounds)
   unsigned int m_tau[3];        // float bits: min tau touched by a change in the round
-  unsigned int lo[3];           // float bits: min potential over surviving candidates
+  unsigned int lo[3];           // float bits: min pop time over surviving candidates
   // goal_dist (cvp:738,769 / dijkstra:279,296) and the cancel flag are read by EVERY thread at the
   // top of a round and decide whether the group leaves the loop, so they must not change while a
   // round is running: round r reads slot r&1, writers of round r only touch slot (r+1)&1.
@@ -119,7 +119,8 @@ __device__ __forceinline__ void stage_flush(Stage& st, uint32_t* list_next, unsi
   for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) list_next[base + i] = st.buf[i];
   __syncthreads();
   if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; }
-  __syncthreads();
+  // no barrier needed here: the group barrier that follows every flush orders the reset
+  // before the next round's pushes
 }
 
 // -----------------------------------------------------------------------------
@@ -191,8 +192,8 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
       }
       float nd, ntau;
       my_recomputes++;
-      if (prob.recompute(c, band_end, goal, old, nd, ntau)) my_mtau = fminf(my_mtau, fminf(tau, ntau));
-      my_lo = fminf(my_lo, nd);
+      if (prob.recompute(c, band_end, goal, r, old, nd, ntau)) my_mtau = fminf(my_mtau, fminf(tau, ntau));
+      my_lo = fminf(my_lo, ntau);      // smallest pop time still in flight: the band follows it
       stage_push(st, c, list_n, &ctl->count[next]);
       // a vertex that holds a finite label pulls its neighbours into the candidate set (once)
       if (__float_as_uint(nd) != INF_BITS && mark[c] == MARK_CAND) {
@@ -204,6 +205,8 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
       }
     }
     {
+      my_mtau = fminf(my_mtau, prob.deferred_m);      // deferred back-steps are pending changes
+      prob.deferred_m = __uint_as_float(INF_BITS);
       const unsigned int wm = __reduce_min_sync(0xffffffffu, __float_as_uint(my_mtau));
       const unsigned int wl = __reduce_min_sync(0xffffffffu, __float_as_uint(my_lo));
       if ((threadIdx.x & 31) == 0) {
@@ -285,15 +288,15 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
         continue;
       }
       float nd; EvTime nt; int4 ix; int deg;
-      prob.replay_sub8(c, j, gmask, band_end, goal, nd, nt, ix, deg);
+      prob.replay_sub8(c, j, gmask, band_end, goal, r, nd, nt, ix, deg);
       const uint32_t mk = mark[c];
       if (j == 0) {
         my_recomputes++;
         if (__float_as_uint(nd) != __float_as_uint(d) || !ev_eq(nt, old.t)) {
-          prob.store_label(c, nd, nt);
+          prob.store_label(c, nd, nt, __float_as_uint(d) != INF_BITS, r);
           my_mtau = fminf(my_mtau, fminf(tau, nt.a1));
         }
-        my_lo = fminf(my_lo, nd);
+        my_lo = fminf(my_lo, nt.a1);
         stage_push(st, c, list_n, &ctl->count[next]);
       }
       if (__float_as_uint(nd) != INF_BITS && mk == MARK_CAND) {
@@ -307,6 +310,8 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
       }
     }
     {
+      my_mtau = fminf(my_mtau, prob.deferred_m);      // deferred back-steps are pending changes
+      prob.deferred_m = __uint_as_float(INF_BITS);
       const unsigned int wm = __reduce_min_sync(0xffffffffu, __float_as_uint(my_mtau));
       const unsigned int wl = __reduce_min_sync(0xffffffffu, __float_as_uint(my_lo));
       if ((threadIdx.x & 31) == 0) {

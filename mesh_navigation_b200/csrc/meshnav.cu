@@ -70,6 +70,7 @@ __global__ void k_gather_adj_w(const uint32_t* __restrict__ nbr, const uint32_t*
 struct WaveWorkspace {     // per group (index g): state + g*V etc.
   uint4* state;
   uint32_t* minor;
+  uint32_t* chg;
   uint32_t* mark;
   uint32_t* list0;
   uint32_t* list1;
@@ -135,14 +136,15 @@ __global__ void __launch_bounds__(512, 1) k_cvp(const CvpKernelArgs a) {
     const uint32_t q = __ldcg(&ctl->query);
     if (q >= a.n_queries) break;
     const bool single = (a.n_queries == 1);
-    for (uint32_t v = gtid; v < V; v += gthreads) { state[v] = state_inf(); mark[v] = MARK_NONE; }
+    uint32_t* chg = a.ws.chg + (size_t)g * V;
+    for (uint32_t v = gtid; v < V; v += gthreads) { state[v] = state_inf(); mark[v] = MARK_NONE; chg[v] = 0u; }
     group_sync<CS>();
 
     const uint32_t sf = a.seed_faces[q];
     const uint32_t s0 = a.faces[3 * (size_t)sf], s1 = a.faces[3 * (size_t)sf + 1], s2 = a.faces[3 * (size_t)sf + 2];
     CvpProblem prob;
     prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_w = a.cor_w; prob.cost = a.cost; prob.invalid = a.invalid;
-    prob.state = state; prob.minor_arr = a.ws.minor + (size_t)g * V; prob.pred = nullptr; prob.dir = nullptr; prob.cut = nullptr; prob.cost_limit = a.cost_limit;
+    prob.state = state; prob.minor_arr = a.ws.minor + (size_t)g * V; prob.chg = chg; prob.deferred_m = __uint_as_float(INF_BITS); prob.pred = nullptr; prob.dir = nullptr; prob.cut = nullptr; prob.cost_limit = a.cost_limit;
     prob.s0 = s0; prob.s1 = s1; prob.s2 = s2; prob.seed_noexpand = 0;
     float sd[3];
     {
@@ -209,14 +211,14 @@ __global__ void __launch_bounds__(512, 1) k_cvp_grid(const CvpKernelArgs a) {
   GroupCtl* ctl = a.ws.ctl;
   if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; }
   __syncthreads();
-  for (uint32_t v = gtid; v < V; v += gthreads) { state[v] = state_inf(); mark[v] = MARK_NONE; }
+  for (uint32_t v = gtid; v < V; v += gthreads) { state[v] = state_inf(); mark[v] = MARK_NONE; a.ws.chg[v] = 0u; }
   group_sync<0>();
   const uint32_t sf = a.seed_faces[0];
   const uint32_t s0 = a.faces[3 * (size_t)sf], s1 = a.faces[3 * (size_t)sf + 1], s2 = a.faces[3 * (size_t)sf + 2];
   CvpEllProblem prob;
   prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_w = a.cor_w; prob.cost = a.cost; prob.invalid = a.invalid;
   prob.ell_idx = a.ell_idx; prob.ell_w = a.ell_w;
-  prob.state = state; prob.minor_arr = a.ws.minor; prob.pred = nullptr; prob.dir = nullptr; prob.cut = nullptr; prob.cost_limit = a.cost_limit;
+  prob.state = state; prob.minor_arr = a.ws.minor; prob.chg = a.ws.chg; prob.deferred_m = __uint_as_float(INF_BITS); prob.pred = nullptr; prob.dir = nullptr; prob.cut = nullptr; prob.cost_limit = a.cost_limit;
   prob.s0 = s0; prob.s1 = s1; prob.s2 = s2; prob.seed_noexpand = 0;
   float sd[3];
   {
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(256) k_cvp_epilogue(const CvpKernelArgs a, con
   const uint32_t sf = a.seed_faces[0];
   CvpProblem prob;
   prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_w = a.cor_w; prob.cost = a.cost; prob.invalid = a.invalid;
-  prob.state = a.ws.state; prob.minor_arr = a.ws.minor; prob.pred = a.out_pred; prob.dir = a.out_dir; prob.cut = a.out_cut; prob.cost_limit = a.cost_limit;
+  prob.state = a.ws.state; prob.minor_arr = a.ws.minor; prob.chg = a.ws.chg; prob.deferred_m = __uint_as_float(INF_BITS); prob.pred = a.out_pred; prob.dir = a.out_dir; prob.cut = a.out_cut; prob.cost_limit = a.cost_limit;
   prob.s0 = a.faces[3 * (size_t)sf]; prob.s1 = a.faces[3 * (size_t)sf + 1]; prob.s2 = a.faces[3 * (size_t)sf + 2];
   prob.seed_noexpand = 0;
   {
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(256) k_cvp_epilogue(const CvpKernelArgs a, con
   }
   int win = -1; float nd, wu1 = 0, wu2 = 0; EvTime nt;
   if (__float_as_uint(d) != INF_BITS && prob.eligible(c))
-    prob.replay(c, __uint_as_float(INF_BITS), __uint_as_float(ctl->goal_bits), nd, nt, win, wu1, wu2);
+    prob.replay(c, __uint_as_float(INF_BITS), __uint_as_float(ctl->goal_bits), 0xfffffff0u /* final labels: nothing is deferred */, nd, nt, win, wu1, wu2);
   prob.write_aux(c, win, wu1, wu2);
 }
 
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(512, 1) k_dijkstra(const DijkstraKernelArgs a)
   group_sync<CS>();
   DijkstraProblem prob;
   prob.adj_ptr = a.adj_ptr; prob.adj_nw = a.adj_nw; prob.cost = a.cost; prob.invalid = a.invalid;
-  prob.state = state; prob.pred = a.out_pred; prob.cost_limit = a.cost_limit;
+  prob.state = state; prob.pred = a.out_pred; prob.cost_limit = a.cost_limit; prob.deferred_m = __uint_as_float(INF_BITS);
   const int has_robot = a.robot_vertex >= 0;
   const uint32_t rv = has_robot ? (uint32_t)a.robot_vertex : 0xffffffffu;
   if (gtid == 0) {
@@ -338,6 +340,196 @@ __global__ void __launch_bounds__(512, 1) k_dijkstra(const DijkstraKernelArgs a)
                       a.goal_dist_offset, a.cancel_flag, 1e-30f, 2u * V + 64u);
   group_sync<CS>();
   for (uint32_t v = gtid; v < V; v += gthreads) a.out_dist[v] = __uint_as_float(state[v].x);
+}
+
+// ============================================================================
+// Fused geometric cost layers (mesh_layers: HeightDiff, Roughness, Steepness, Ridge, Clearance cost
+// mapping, Border) + MaxCombinationLayer + lethal masks: ONE pass over the radius neighbourhood per
+// vertex instead of the reference's three independent visitLocalVertexNeighborhood runs with
+// std::set bookkeeping (ridge_layer.cpp:166-175, height_diff_layer.cpp:108, roughness_layer.cpp:143).
+// Definitions of the lvr2 pieces: see oracle/oracle.cpp (orc_layers).
+// ============================================================================
+__global__ void k_face_normals(const float* __restrict__ pos, const uint32_t* __restrict__ faces, uint32_t F,
+                               float* __restrict__ fn) {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const float* p0 = pos + 3 * (size_t)faces[3 * (size_t)f];
+  const float* p1 = pos + 3 * (size_t)faces[3 * (size_t)f + 1];
+  const float* p2 = pos + 3 * (size_t)faces[3 * (size_t)f + 2];
+  const float ax = p1[0] - p0[0], ay = p1[1] - p0[1], az = p1[2] - p0[2];
+  const float bx = p2[0] - p0[0], by = p2[1] - p0[1], bz = p2[2] - p0[2];
+  float nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+  const float l = sqrtf(nx * nx + ny * ny + nz * nz);
+  if (l > 0) { nx /= l; ny /= l; nz /= l; }
+  fn[3 * (size_t)f] = nx; fn[3 * (size_t)f + 1] = ny; fn[3 * (size_t)f + 2] = nz;
+}
+
+__global__ void k_vertex_normals(const uint32_t* __restrict__ cor_ptr, const int4* __restrict__ cor_idx,
+                                 const float* __restrict__ fn, uint32_t V, float* __restrict__ vn) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  float nx = 0, ny = 0, nz = 0;
+  for (uint32_t k = cor_ptr[v]; k < cor_ptr[v + 1]; ++k) {
+    const int f = cor_idx[k].z;
+    nx = nx + fn[3 * (size_t)f]; ny = ny + fn[3 * (size_t)f + 1]; nz = nz + fn[3 * (size_t)f + 2];
+  }
+  const float l = sqrtf(nx * nx + ny * ny + nz * nz);
+  if (l > 0) { nx /= l; ny /= l; nz /= l; }
+  vn[3 * (size_t)v] = nx; vn[3 * (size_t)v + 1] = ny; vn[3 * (size_t)v + 2] = nz;
+}
+
+struct LayerKernelArgs {
+  uint32_t V;
+  const float* pos; const float* vn;
+  const uint32_t* adj_ptr; const uint32_t* adj_nbr;
+  const uint8_t* border;
+  const float* clearance;      // may be null
+  mnb_layer_params P;
+  float* costs;                // 6 x V
+  float* combined; uint8_t* lethal_mask;
+  unsigned int* overflow;      // neighbourhood larger than the per-thread scratch
+};
+
+constexpr int NB_SEEN = 320, NB_STACK = 160;
+
+// traversal shared by the three radius layers; WHICH selects the accumulators that are active (bit0 height
+// diff, bit1 roughness, bit2 ridge) so that layers with equal radii share one walk
+template <int WHICH>
+__device__ __forceinline__ void walk(const LayerKernelArgs& a, uint32_t v, float radius, float& zmin, float& zmax,
+                                     float& rsum, int& rcnt, float& value, int& num) {
+  uint32_t seen[NB_SEEN]; uint32_t stack[NB_STACK];
+  int ns = 0, sp = 0;
+  seen[ns++] = v; stack[sp++] = v;
+  const float px = a.pos[3 * (size_t)v], py = a.pos[3 * (size_t)v + 1], pz = a.pos[3 * (size_t)v + 2];
+  const float nvx = a.vn[3 * (size_t)v], nvy = a.vn[3 * (size_t)v + 1], nvz = a.vn[3 * (size_t)v + 2];
+  const float rx = px + nvx, ry = py + nvy, rz = pz + nvz;
+  while (sp > 0) {
+    const uint32_t u = stack[--sp];
+    for (uint32_t k = a.adj_ptr[u]; k < a.adj_ptr[u + 1]; ++k) {
+      const uint32_t n = a.adj_nbr[k];
+      bool was = false;
+      for (int s = 0; s < ns; ++s) if (seen[s] == n) { was = true; break; }
+      if (was) continue;
+      if (ns >= NB_SEEN) { atomicAdd(a.overflow, 1u); return; }
+      seen[ns++] = n;
+      const float qx = a.pos[3 * (size_t)n], qy = a.pos[3 * (size_t)n + 1], qz = a.pos[3 * (size_t)n + 2];
+      const float dx = qx - px, dy = qy - py, dz = qz - pz;
+      if (sqrtf(dx * dx + dy * dy + dz * dz) < radius) {
+        if (WHICH & 1) { zmin = fminf(zmin, qz); zmax = fmaxf(zmax, qz); }
+        if (WHICH & 6) {
+          const float nnx = a.vn[3 * (size_t)n], nny = a.vn[3 * (size_t)n + 1], nnz = a.vn[3 * (size_t)n + 2];
+          if (WHICH & 2) {
+            float dot = nvx * nnx + nvy * nny + nvz * nnz;
+            dot = fminf(1.0f, fmaxf(-1.0f, dot));
+            rsum = rsum + acosf(dot); rcnt++;
+          }
+          if (WHICH & 4) {
+            const float cx = (qx + nnx) - rx, cy = (qy + nny) - ry, cz = (qz + nnz) - rz;
+            value += sqrtf(cx * cx + cy * cy + cz * cz); num++;
+          }
+        }
+        if (sp >= NB_STACK) { atomicAdd(a.overflow, 1u); return; }
+        stack[sp++] = n;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_layers(const LayerKernelArgs a) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= a.V) return;
+  const mnb_layer_params& P = a.P;
+  const float pz = a.pos[3 * (size_t)v + 2];
+  float zmin = pz, zmax = pz, rsum = 0.0f, value = 0.0f; int rcnt = 0, num = 0;
+  const float r_hd = (float)P.height_diff_radius, r_ro = (float)P.roughness_radius, r_ri = (float)P.ridge_radius;
+  if (r_hd == r_ro && r_ro == r_ri) {
+    walk<7>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num);
+  } else {
+    walk<1>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num);
+    walk<2>(a, v, r_ro, zmin, zmax, rsum, rcnt, value, num);
+    walk<4>(a, v, r_ri, zmin, zmax, rsum, rcnt, value, num);
+  }
+  const float hd = zmax - zmin;
+  const float ro = rcnt ? rsum / (float)rcnt : 0.0f;
+  const float st = acosf(a.vn[3 * (size_t)v + 2]);                               // steepness_layer.cpp:165
+  const float ri = num == 0 ? (float)(P.ridge_threshold + 0.1) : value / num;     // ridge_layer.cpp:177-184
+  const float cl = a.clearance ? a.clearance[v] : __uint_as_float(INF_BITS);
+  float cc; bool cl_lethal = false;                                              // clearance_layer.cpp:77-96
+  const double inflated_height = P.clearance_robot_height + P.clearance_height_inflation;
+  if (cl < P.clearance_robot_height) { cc = 1.0f; cl_lethal = true; }
+  else if (cl < inflated_height) {
+    const double diff = (cl - P.clearance_robot_height) / P.clearance_height_inflation;
+    cc = (float)((cos(diff * 3.14159265358979323846) + 1.0) / 2.0);
+  } else cc = 0.0f;
+  const float bo = a.border[v] ? (float)P.border_cost : 0.0f;
+  const size_t V = a.V;
+  if (a.costs) {
+    a.costs[v] = hd; a.costs[V + v] = ro; a.costs[2 * V + v] = st; a.costs[3 * V + v] = ri; a.costs[4 * V + v] = cc; a.costs[5 * V + v] = bo;
+  }
+  uint8_t mask = 0;
+  if (hd > P.height_diff_threshold) mask |= 1;
+  if (ro > P.roughness_threshold) mask |= 2;
+  if (st > P.steepness_threshold) mask |= 4;
+  if (ri > P.ridge_threshold) mask |= 8;
+  if (cl_lethal) mask |= 16;
+  if (bo > P.border_threshold) mask |= 32;
+  if (a.lethal_mask) a.lethal_mask[v] = mask;
+  if (a.combined) a.combined[v] = fmaxf(fmaxf(fmaxf(0.0f, hd), fmaxf(ro, st)), fmaxf(fmaxf(ri, cc), bo));   // combination_layer.cpp:60-71
+}
+
+// ============================================================================
+// InflationLayer::waveCostInflation (inflation_layer.cpp:341-491): whole-grid cooperative kernel
+// (multi-source: few, very wide rounds) + fading epilogue (:482-490, :315-339)
+// ============================================================================
+struct InflateKernelArgs {
+  uint32_t V;
+  const uint32_t* cor_ptr; const int4* cor_idx; const float4* cor_wd;
+  const uint8_t* invalid;
+  WaveWorkspace ws;
+  const uint32_t* lethals; uint32_t n_lethals;
+  float max_distance;
+  InflationParams params;
+  float* out_dist; float* out_cost;
+};
+
+__global__ void __launch_bounds__(512, 1) k_inflate(const InflateKernelArgs a) {
+  __shared__ Stage st;
+  uint32_t g, gthreads, gtid;
+  group_coords<0>(g, gthreads, gtid);
+  const uint32_t V = a.V;
+  uint4* state = a.ws.state; uint32_t* mark = a.ws.mark; uint32_t* list0 = a.ws.list0; uint32_t* list1 = a.ws.list1;
+  GroupCtl* ctl = a.ws.ctl;
+  if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; }
+  __syncthreads();
+  for (uint32_t v = gtid; v < V; v += gthreads) { state[v] = state_inf(); mark[v] = MARK_NONE; a.ws.chg[v] = 0u; }
+  group_sync<0>();
+  for (uint32_t i = gtid; i < a.n_lethals; i += gthreads) {      // :397-402
+    const uint32_t v = a.lethals[i];
+    if (v < V) { state[v] = make_uint4(0u, 0u, 0u, 0u); mark[v] = MARK_FIXED; }
+  }
+  if (gtid == 0) ctl_reset(ctl, 0, 0.0f);
+  group_sync<0>();
+  InflationProblem prob;
+  prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_wd = a.cor_wd; prob.invalid = a.invalid;
+  prob.state = state; prob.minor_arr = a.ws.minor; prob.chg = a.ws.chg; prob.deferred_m = __uint_as_float(INF_BITS); prob.max_distance = a.max_distance;
+  for (uint32_t i = gtid; i < a.n_lethals; i += gthreads) {
+    const uint32_t v = a.lethals[i];
+    if (v >= V) continue;
+    prob.activate(v, [&](uint32_t x) {
+      if (__ldcg(&mark[x]) == MARK_NONE && atomicCAS(&mark[x], MARK_NONE, MARK_CAND) == MARK_NONE)
+        stage_push(st, x, list0, &ctl->count[0]);
+    });
+  }
+  stage_flush(st, list0, &ctl->count[0], &ctl->m_tau[0], &ctl->lo[0]);
+  group_sync<0>();
+  run_band_rounds<0>(prob, ctl, list0, list1, mark, st, __uint_as_float(INF_BITS), gthreads, gtid, 0, 0u, 0u, 0u, 0.0,
+                     nullptr, 1e-30f, 2u * V + 64u);
+  group_sync<0>();
+  for (uint32_t v = gtid; v < V; v += gthreads) {
+    const float d = __uint_as_float(state[v].x);
+    if (a.out_dist) a.out_dist[v] = d;
+    if (a.out_cost) a.out_cost[v] = (__float_as_uint(d) == INF_BITS) ? __int_as_float(0x7fc00000) : fading(a.params, d);
+  }
 }
 
 // ============================================================================
@@ -369,6 +561,10 @@ struct mnb_ctx {
   float* d_out_dist = nullptr; size_t out_dist_cap = 0;
   uint32_t* d_out_pred = nullptr; float* d_out_dir = nullptr; int32_t* d_out_cut = nullptr;
   uint32_t* d_seed_faces = nullptr; float* d_seed_pos = nullptr; uint32_t seed_cap = 0;
+  float* d_face_normals = nullptr; float* d_vertex_normals = nullptr; uint8_t* d_border = nullptr;
+  float* d_layer_costs = nullptr; float* d_layer_combined = nullptr; uint8_t* d_layer_mask = nullptr; float* d_clearance = nullptr;
+  unsigned int* d_overflow = nullptr;
+  uint32_t* d_lethals = nullptr; uint32_t lethal_cap = 0; uint8_t* d_infl_invalid = nullptr; float* d_out_cost = nullptr;
   // tuning
   float delta = 0.3f; int cluster = -1 /* -1: whole-grid cooperative kernel for single plans */; int batch_cluster = 1; int threads = 512;
   int grid_blocks_per_sm = 0;
@@ -394,18 +590,21 @@ static void free_mesh(mnb_ctx* c) {
   dfree(c->d_pos); dfree(c->d_faces); dfree(c->d_edges); dfree(c->d_cor_ptr); dfree(c->d_cor_idx); dfree(c->d_cor_eid);
   dfree(c->d_cor_w); dfree(c->d_cor_wd); dfree(c->d_ell_idx); dfree(c->d_ell_eid); dfree(c->d_ell_w); dfree(c->d_ell_wd); dfree(c->d_adj_ptr); dfree(c->d_adj_nbr); dfree(c->d_adj_eid); dfree(c->d_adj_nw);
   dfree(c->d_edge_dist); dfree(c->d_edge_w); dfree(c->d_cost); dfree(c->d_invalid);
-  dfree(c->ws.state); dfree(c->ws.minor); dfree(c->ws.mark); dfree(c->ws.list0); dfree(c->ws.list1); dfree(c->ws.ctl);
+  dfree(c->ws.state); dfree(c->ws.minor); dfree(c->ws.chg); dfree(c->ws.mark); dfree(c->ws.list0); dfree(c->ws.list1); dfree(c->ws.ctl);
   c->ws_groups = 0;
   dfree(c->d_out_dist); c->out_dist_cap = 0; dfree(c->d_out_pred); dfree(c->d_out_dir); dfree(c->d_out_cut);
+  dfree(c->d_infl_invalid); dfree(c->d_out_cost);
+  dfree(c->d_face_normals); dfree(c->d_vertex_normals); dfree(c->d_border); dfree(c->d_layer_costs); dfree(c->d_layer_combined);
+  dfree(c->d_layer_mask); dfree(c->d_clearance); dfree(c->d_overflow);
   c->costs_set = false;
 }
 
 static int32_t ensure_workspace(mnb_ctx* ctx, uint32_t groups) {
   if (groups <= ctx->ws_groups) return MNB_OK;
-  dfree(ctx->ws.state); dfree(ctx->ws.minor); dfree(ctx->ws.mark); dfree(ctx->ws.list0); dfree(ctx->ws.list1); dfree(ctx->ws.ctl);
+  dfree(ctx->ws.state); dfree(ctx->ws.minor); dfree(ctx->ws.chg); dfree(ctx->ws.mark); dfree(ctx->ws.list0); dfree(ctx->ws.list1); dfree(ctx->ws.ctl);
   ctx->ws_groups = 0;
   const size_t n = (size_t)groups * ctx->V;
-  CK(dalloc(&ctx->ws.state, n)); CK(dalloc(&ctx->ws.minor, n)); CK(dalloc(&ctx->ws.mark, n)); CK(dalloc(&ctx->ws.list0, n)); CK(dalloc(&ctx->ws.list1, n));
+  CK(dalloc(&ctx->ws.state, n)); CK(dalloc(&ctx->ws.minor, n)); CK(dalloc(&ctx->ws.chg, n)); CK(dalloc(&ctx->ws.mark, n)); CK(dalloc(&ctx->ws.list0, n)); CK(dalloc(&ctx->ws.list1, n));
   CK(dalloc(&ctx->ws.ctl, groups));
   ctx->ws_groups = groups;
   return MNB_OK;
@@ -440,7 +639,7 @@ void mnb_destroy(mnb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   free_mesh(ctx);
-  dfree(ctx->d_next_query); dfree(ctx->d_seed_faces); dfree(ctx->d_seed_pos);
+  dfree(ctx->d_next_query); dfree(ctx->d_seed_faces); dfree(ctx->d_seed_pos); dfree(ctx->d_lethals);
   if (ctx->h_cancel) cudaFreeHost(ctx->h_cancel);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -530,6 +729,10 @@ int32_t mnb_set_mesh(mnb_ctx* ctx, uint32_t V, uint32_t F, const float* pos, con
   std::vector<uint32_t>().swap(T.cor_v1); std::vector<uint32_t>().swap(T.cor_v2); std::vector<uint32_t>().swap(T.cor_face);
   std::vector<uint32_t>().swap(T.cor_ec); std::vector<uint32_t>().swap(T.cor_eb); std::vector<uint32_t>().swap(T.cor_ea);
   std::vector<uint32_t>().swap(T.vadj_nbr); std::vector<uint32_t>().swap(T.vadj_eid); std::vector<uint32_t>().swap(T.face_edges);
+  CK(dalloc(&ctx->d_face_normals, 3 * (size_t)F)); CK(dalloc(&ctx->d_vertex_normals, 3 * (size_t)V)); CK(dalloc(&ctx->d_border, (size_t)V));
+  CK(cudaMemcpyAsync(ctx->d_border, T.border.data(), (size_t)V, cudaMemcpyHostToDevice, ctx->stream));
+  k_face_normals<<<(F + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_pos, ctx->d_faces, F, ctx->d_face_normals);
+  k_vertex_normals<<<(V + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_cor_ptr, ctx->d_cor_idx, ctx->d_face_normals, V, ctx->d_vertex_normals);
   k_edge_dist<<<(T.E + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_pos, ctx->d_edges, T.E, ctx->d_edge_dist);
   k_gather_corner_w<<<(unsigned)((NC + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_cor_eid, ctx->d_edge_dist, NC, ctx->d_cor_wd);
   k_gather_corner_w<<<(unsigned)(((size_t)V * ELL_W + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_ell_eid, ctx->d_edge_dist, (size_t)V * ELL_W, ctx->d_ell_wd);
@@ -811,10 +1014,95 @@ int32_t mnb_dijkstra(mnb_ctx* ctx, uint32_t seed_vertex, int64_t robot_vertex, d
   return MNB_SUCCESS;
 }
 
-int32_t mnb_inflate(mnb_ctx* ctx, const uint32_t*, uint32_t, const uint8_t*, const mnb_inflation_params*, float*, float*) {
-  if (!ctx) return MNB_E_ARG;
-  ctx->err = "mnb_inflate: not built yet";
-  return MNB_E_STATE;
+int32_t mnb_get_vertex_normals(mnb_ctx* ctx, float* out) {
+  if (!ctx || !out || !ctx->V) return MNB_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(out, ctx->d_vertex_normals, sizeof(float) * 3 * (size_t)ctx->V, out_kind(ctx), ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MNB_OK;
+}
+
+int32_t mnb_compute_layers(mnb_ctx* ctx, const mnb_layer_params* params, const float* clearance, float* out_costs,
+                           float* out_combined, uint8_t* out_lethal_mask) {
+  if (!ctx || !params || !ctx->V) return MNB_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const size_t V = ctx->V;
+  if (!ctx->d_layer_costs) {
+    CK(dalloc(&ctx->d_layer_costs, 6 * V)); CK(dalloc(&ctx->d_layer_combined, V)); CK(dalloc(&ctx->d_layer_mask, V));
+    CK(dalloc(&ctx->d_overflow, (size_t)1));
+  }
+  const bool dev = ctx->ptr_mode == MNB_PTR_DEVICE;
+  if (clearance) {
+    if (!ctx->d_clearance) CK(dalloc(&ctx->d_clearance, V));
+    CK(cudaMemcpyAsync(ctx->d_clearance, clearance, sizeof(float) * V, in_kind(ctx), ctx->stream));
+  }
+  CK(cudaMemsetAsync(ctx->d_overflow, 0, sizeof(unsigned int), ctx->stream));
+  LayerKernelArgs a{};
+  a.V = ctx->V; a.pos = ctx->d_pos; a.vn = ctx->d_vertex_normals; a.adj_ptr = ctx->d_adj_ptr; a.adj_nbr = ctx->d_adj_nbr;
+  a.border = ctx->d_border; a.clearance = clearance ? ctx->d_clearance : nullptr; a.P = *params;
+  a.costs = (dev && out_costs) ? out_costs : ctx->d_layer_costs;
+  a.combined = (dev && out_combined) ? out_combined : ctx->d_layer_combined;
+  a.lethal_mask = (dev && out_lethal_mask) ? out_lethal_mask : ctx->d_layer_mask;
+  a.overflow = ctx->d_overflow;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  k_layers<<<(ctx->V + 127) / 128, 128, 0, ctx->stream>>>(a);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (!dev) {
+    if (out_costs) CK(cudaMemcpyAsync(out_costs, a.costs, sizeof(float) * 6 * V, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_combined) CK(cudaMemcpyAsync(out_combined, a.combined, sizeof(float) * V, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_lethal_mask) CK(cudaMemcpyAsync(out_lethal_mask, a.lethal_mask, V, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  unsigned int ovf = 0;
+  CK(cudaMemcpyAsync(&ovf, ctx->d_overflow, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->stats = mnb_stats{}; ctx->stats.kernel_ms = ms; ctx->stats.kernel_launches = 1; ctx->stats.settled = ctx->V;
+  if (ovf) { ctx->err = "layer neighbourhood exceeds the per-vertex scratch (radius too large for the mesh resolution)"; return MNB_E_NOMEM; }
+  return MNB_OK;
+}
+
+// debugging aid (not part of the public header): raw labels {d, a1, a2, a3|flag} of wavefront group 0
+int32_t mnb_debug_get_labels(mnb_ctx* ctx, uint32_t* out4v) {
+  if (!ctx || !ctx->ws.state) return MNB_E_ARG;
+  CK(cudaMemcpy(out4v, ctx->ws.state, sizeof(uint4) * (size_t)ctx->V, cudaMemcpyDeviceToHost));
+  return MNB_OK;
+}
+
+int32_t mnb_inflate(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, const uint8_t* invalid,
+                    const mnb_inflation_params* params, float* out_dist, float* out_cost) {
+  if (!ctx || !ctx->V || !params || (n && !lethals)) return MNB_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int32_t rc;
+  if ((rc = ensure_workspace(ctx, 1)) != MNB_OK) return rc;
+  const bool dev = ctx->ptr_mode == MNB_PTR_DEVICE;
+  if ((rc = ensure_out(ctx, (size_t)ctx->V, false)) != MNB_OK) return rc;
+  if (!ctx->d_out_cost) CK(dalloc(&ctx->d_out_cost, (size_t)ctx->V));
+  if (n > ctx->lethal_cap) { dfree(ctx->d_lethals); CK(dalloc(&ctx->d_lethals, (size_t)n)); ctx->lethal_cap = n; }
+  if (n) CK(cudaMemcpyAsync(ctx->d_lethals, lethals, sizeof(uint32_t) * n, in_kind(ctx), ctx->stream));
+  if (invalid) {
+    if (!ctx->d_infl_invalid) CK(dalloc(&ctx->d_infl_invalid, (size_t)ctx->V));
+    CK(cudaMemcpyAsync(ctx->d_infl_invalid, invalid, (size_t)ctx->V, in_kind(ctx), ctx->stream));
+  }
+  CK(cudaMemsetAsync(ctx->ws.ctl, 0, sizeof(GroupCtl), ctx->stream));
+  InflateKernelArgs a{};
+  a.V = ctx->V; a.cor_ptr = ctx->d_cor_ptr; a.cor_idx = ctx->d_cor_idx; a.cor_wd = ctx->d_cor_wd;
+  a.invalid = invalid ? ctx->d_infl_invalid : nullptr; a.ws = ctx->ws; a.lethals = ctx->d_lethals; a.n_lethals = n;
+  a.max_distance = (float)params->inflation_radius;      // double -> `const float&` parameter (inflation_layer.cpp:240,450)
+  a.params.inscribed_radius = params->inscribed_radius; a.params.inflation_radius = params->inflation_radius;
+  a.params.lethal_value = params->lethal_value; a.params.inscribed_value = params->inscribed_value;
+  a.params.cost_scaling_factor = params->cost_scaling_factor;
+  a.out_dist = (dev && out_dist) ? out_dist : ctx->d_out_dist;
+  a.out_cost = (dev && out_cost) ? out_cost : ctx->d_out_cost;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  void* kargs[] = {(void*)&a};
+  CK(cudaLaunchCooperativeKernel((const void*)k_inflate, dim3(ctx->sm_count), dim3(ctx->threads), kargs, 0, ctx->stream));
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (!dev) {
+    if (out_dist) CK(cudaMemcpyAsync(out_dist, a.out_dist, sizeof(float) * (size_t)ctx->V, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_cost) CK(cudaMemcpyAsync(out_cost, a.out_cost, sizeof(float) * (size_t)ctx->V, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  return finish_stats(ctx, 1, 1);
 }
 
 }  // extern "C"

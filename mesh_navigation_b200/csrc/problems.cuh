@@ -39,6 +39,8 @@ struct CvpProblem {
   static constexpr int MAXF = 12;
 
   uint32_t* minor_arr;                  // overflow minors (only read when the label's flag bit is set)
+  uint32_t* chg;                        // 1 + round of the last RE-label of a vertex (0 = never)
+  mutable float deferred_m;             // smallest trigger time of a back-step deferred in this round
 
   __device__ __forceinline__ Label load_label(uint32_t v) const {
     const uint4 s = __ldcg(&state[v]);
@@ -47,10 +49,21 @@ struct CvpProblem {
     l.t.minor = (s.w >> 31) ? __ldcg(&minor_arr[v]) : 2u * v;
     return l;
   }
-  __device__ __forceinline__ void store_label(uint32_t c, float d, const EvTime& t) const {
+  __device__ __forceinline__ void store_label(uint32_t c, float d, const EvTime& t, bool relabel, uint32_t round) const {
     uint32_t w = __float_as_uint(t.a3);
     if (t.minor != 2u * c) { __stcg(&minor_arr[c], t.minor); w |= 0x80000000u; }
+    if (relabel) __stcg(&chg[c], round + 1u);
     __stcg(&state[c], make_uint4(__float_as_uint(d), __float_as_uint(t.a1), __float_as_uint(t.a2), w));
+  }
+  // A non-causal (back-step) label X <= T.a1 may only be taken from a trigger whose label was not
+  // re-labelled during the previous round.  Without this a trigger and its own back-step child can feed
+  // each other forever (a dependency cycle that has no counterpart in the sequential order); the deferred
+  // update is reported as a pending change at the trigger's pop time so that nothing above it settles.
+  __device__ __forceinline__ bool backstep_ok(float X, const EvTime& T, uint32_t Tv, uint32_t round) const {
+    if (X > T.a1) return true;
+    if (__ldcg(&chg[Tv]) < round) return true;
+    deferred_m = fminf(deferred_m, T.a1);
+    return false;
   }
   __device__ __forceinline__ bool eligible(uint32_t x) const {
     if (invalid && invalid[x]) return false;        // cvp:785 (no face with an invalid vertex)
@@ -70,7 +83,7 @@ struct CvpProblem {
 
   // pop time (T, Tm) of the face with sources v1, v2; false if the face cannot fire
   __device__ __forceinline__ bool face_time(uint32_t v1, uint32_t v2, const Label& a, const Label& b, float band_end,
-                                            float goal, EvTime& T) const {
+                                            float goal, EvTime& T, uint32_t& Tv) const {
     if (!(a.d < band_end) || !(b.d < band_end)) return false;
     if (invalid && (invalid[v1] || invalid[v2])) return false;
     const int i1 = seed_index(v1), i2 = seed_index(v2);
@@ -80,21 +93,21 @@ struct CvpProblem {
       const bool e1 = !((seed_noexpand >> i1) & 1u), e2 = !((seed_noexpand >> i2) & 1u);
       if (!e1 && !e2) return false;
       const bool use1 = e1 && (!e2 || !v1_later);
-      T = use1 ? a.t : b.t;
+      T = use1 ? a.t : b.t; Tv = use1 ? v1 : v2;
       return true;
     }
     const int il = v1_later ? i1 : i2;
     if (il >= 0 && ((seed_noexpand >> il) & 1u)) return false;
     if ((v1_later ? a.d : b.d) > goal) return false;                       // cvp:754
-    T = v1_later ? a.t : b.t;
+    T = v1_later ? a.t : b.t; Tv = v1_later ? v1 : v2;
     return true;
   }
 
-  __device__ __forceinline__ bool corner_time(uint32_t k, float band_end, float goal, EvTime& T, float& u1, float& u2) const {
+  __device__ __forceinline__ bool corner_time(uint32_t k, float band_end, float goal, EvTime& T, uint32_t& Tv, float& u1, float& u2) const {
     const int4 ix = __ldg(&cor_idx[k]);
     const Label a = load_label((uint32_t)ix.x), b = load_label((uint32_t)ix.y);
     u1 = a.d; u2 = b.d;
-    return face_time((uint32_t)ix.x, (uint32_t)ix.y, a, b, band_end, goal, T);
+    return face_time((uint32_t)ix.x, (uint32_t)ix.y, a, b, band_end, goal, T, Tv);
   }
 
   // predecessors_/direction_/cutting_faces_ of the winning face (cvp:493-517), literal acos form
@@ -127,7 +140,7 @@ struct CvpProblem {
 
   // generic path for vertices with more than MAXF incident faces: repeated selection of the next
   // corner in (T, corner index) order by rescanning the corner list (O(deg^2), rare)
-  __device__ __noinline__ void replay_big(uint32_t c, float band_end, float goal, float& nd, EvTime& nt, int& win,
+  __device__ __noinline__ void replay_big(uint32_t c, float band_end, float goal, uint32_t round, float& nd, EvTime& nt, int& win,
                                           float& wu1, float& wu2) const {
     const uint32_t kb = cor_ptr[c], ke = cor_ptr[c + 1];
     float cur = __uint_as_float(INF_BITS);
@@ -135,41 +148,41 @@ struct CvpProblem {
     EvTime lastT = ev_normal(0.0f, 0); uint32_t lastK = 0; bool have_last = false;
     win = -1;
     for (;;) {
-      EvTime bT = lastT; float bu1 = 0, bu2 = 0; uint32_t bk = 0; bool found = false;
+      EvTime bT = lastT; float bu1 = 0, bu2 = 0; uint32_t bk = 0, bTv = 0; bool found = false;
       for (uint32_t k = kb; k < ke; ++k) {
-        EvTime T; float u1, u2;
-        if (!corner_time(k, band_end, goal, T, u1, u2)) continue;
+        EvTime T; float u1, u2; uint32_t Tv;
+        if (!corner_time(k, band_end, goal, T, Tv, u1, u2)) continue;
         if (have_last) {
           const bool after = ev_less(lastT, T) || (ev_eq(lastT, T) && k > lastK);
           if (!after) continue;
         }
-        if (!found || ev_less(T, bT) || (ev_eq(T, bT) && k < bk)) { bT = T; bk = k; bu1 = u1; bu2 = u2; found = true; }
+        if (!found || ev_less(T, bT) || (ev_eq(T, bT) && k < bk)) { bT = T; bk = k; bTv = Tv; bu1 = u1; bu2 = u2; found = true; }
       }
       if (!found) break;
       if (!ev_less(bT, tc)) break;
       const float4 w = __ldg(&cor_w[bk]);
       CvpResult r;
-      if (cvp_update_t<false>(bu1, bu2, cur, w.z, w.y, w.x, r)) { cur = r.value; tc = accept_time(c, r.value, bT); win = (int)bk; wu1 = bu1; wu2 = bu2; }
+      if (cvp_update_t<false>(bu1, bu2, cur, w.z, w.y, w.x, r) && backstep_ok(r.value, bT, bTv, round)) { cur = r.value; tc = accept_time(c, r.value, bT); win = (int)bk; wu1 = bu1; wu2 = bu2; }
       lastT = bT; lastK = bk; have_last = true;
     }
     nd = cur; nt = tc;
   }
 
   // event-ordered replay of the faces around c (see band_engine.cuh)
-  __device__ __forceinline__ void replay(uint32_t c, float band_end, float goal, float& nd, EvTime& nt, int& win,
+  __device__ __forceinline__ void replay(uint32_t c, float band_end, float goal, uint32_t round, float& nd, EvTime& nt, int& win,
                                          float& wu1, float& wu2) const {
     const uint32_t kb = cor_ptr[c], ke = cor_ptr[c + 1];
     win = -1; wu1 = 0.0f; wu2 = 0.0f;
     if (ke - kb > (uint32_t)MAXF) {
-      replay_big(c, band_end, goal, nd, nt, win, wu1, wu2);
+      replay_big(c, band_end, goal, round, nd, nt, win, wu1, wu2);
       return;
     }
-    EvTime Tt[MAXF]; float U1[MAXF], U2[MAXF]; uint32_t K[MAXF];
+    EvTime Tt[MAXF]; float U1[MAXF], U2[MAXF]; uint32_t K[MAXF], TV[MAXF];
     int n = 0;
     for (uint32_t k = kb; k < ke; ++k) {
-      EvTime T; float u1, u2;
-      if (!corner_time(k, band_end, goal, T, u1, u2)) continue;
-      Tt[n] = T; U1[n] = u1; U2[n] = u2; K[n] = k; ++n;
+      EvTime T; float u1, u2; uint32_t Tv;
+      if (!corner_time(k, band_end, goal, T, Tv, u1, u2)) continue;
+      Tt[n] = T; U1[n] = u1; U2[n] = u2; K[n] = k; TV[n] = Tv; ++n;
     }
     float cur = __uint_as_float(INF_BITS);
     EvTime tc = ev_normal(cur, c);
@@ -177,23 +190,23 @@ struct CvpProblem {
       int b = i;
       for (int j = i + 1; j < n; ++j)
         if (ev_less(Tt[j], Tt[b]) || (ev_eq(Tt[j], Tt[b]) && K[j] < K[b])) b = j;
-      const EvTime T = Tt[b]; const float u1 = U1[b], u2 = U2[b]; const uint32_t k = K[b];
-      Tt[b] = Tt[i]; U1[b] = U1[i]; U2[b] = U2[i]; K[b] = K[i];
+      const EvTime T = Tt[b]; const float u1 = U1[b], u2 = U2[b]; const uint32_t k = K[b], Tv = TV[b];
+      Tt[b] = Tt[i]; U1[b] = U1[i]; U2[b] = U2[i]; K[b] = K[i]; TV[b] = TV[i];
       if (!ev_less(T, tc)) break;   // c has been popped before this face fires
       const float4 w = __ldg(&cor_w[k]);
       CvpResult r;
-      if (cvp_update_t<false>(u1, u2, cur, w.z, w.y, w.x, r)) { cur = r.value; tc = accept_time(c, r.value, T); win = (int)k; wu1 = u1; wu2 = u2; }
+      if (cvp_update_t<false>(u1, u2, cur, w.z, w.y, w.x, r) && backstep_ok(r.value, T, Tv, round)) { cur = r.value; tc = accept_time(c, r.value, T); win = (int)k; wu1 = u1; wu2 = u2; }
     }
     nd = cur; nt = tc;
   }
 
   // engine hook: returns true if the label changed (and stores it)
-  __device__ __forceinline__ bool recompute(uint32_t c, float band_end, float goal, const Label& old, float& nd, float& ntau) {
+  __device__ __forceinline__ bool recompute(uint32_t c, float band_end, float goal, uint32_t round, const Label& old, float& nd, float& ntau) {
     int win; float wu1, wu2; EvTime nt;
-    replay(c, band_end, goal, nd, nt, win, wu1, wu2);
+    replay(c, band_end, goal, round, nd, nt, win, wu1, wu2);
     ntau = nt.a1;
     if (__float_as_uint(nd) == __float_as_uint(old.d) && ev_eq(nt, old.t)) return false;
-    store_label(c, nd, nt);
+    store_label(c, nd, nt, __float_as_uint(old.d) != INF_BITS, round);
     return true;
   }
 };
@@ -244,8 +257,13 @@ struct CvpEllProblem : CvpProblem {
     if (j == 0 && deg > (int)ELL_W) activate(c, push);   // faces beyond the 8 ELL slots
   }
 
+  __device__ __noinline__ void replay_serial(uint32_t c, float band_end, float goal, uint32_t round, float& nd, EvTime& nt) const {
+    int win; float a1, a2;
+    replay(c, band_end, goal, round, nd, nt, win, a1, a2);
+  }
+
   // all 8 lanes of the group call this with the same c; every lane returns the same label
-  __device__ __forceinline__ void replay_sub8(uint32_t c, uint32_t j, unsigned gmask, float band_end, float goal,
+  __device__ __forceinline__ void replay_sub8(uint32_t c, uint32_t j, unsigned gmask, float band_end, float goal, uint32_t round,
                                               float& nd, EvTime& nt, int4& ix_out, int& deg_out) const {
     const int lane0 = (threadIdx.x & 31) & ~7;
     const int4 ix = __ldg(&ell_idx[(size_t)c * ELL_W + j]);
@@ -254,7 +272,7 @@ struct CvpEllProblem : CvpProblem {
     deg_out = deg;
     if (deg > (int)ELL_W) {   // rare: CSR path on the group's first lane, result broadcast
       float d0 = 0; EvTime t0 = ev_normal(0.0f, c);
-      if (j == 0) { int win; float a1, a2; replay(c, band_end, goal, d0, t0, win, a1, a2); }
+      if (j == 0) replay_serial(c, band_end, goal, round, d0, t0);
       nd = __shfl_sync(gmask, d0, lane0);
       nt.a1 = __shfl_sync(gmask, t0.a1, lane0); nt.a2 = __shfl_sync(gmask, t0.a2, lane0);
       nt.a3 = __shfl_sync(gmask, t0.a3, lane0); nt.minor = __shfl_sync(gmask, t0.minor, lane0);
@@ -268,8 +286,13 @@ struct CvpEllProblem : CvpProblem {
       const float4 w = __ldg(&ell_w[(size_t)c * ELL_W + j]);
       const uint32_t v1 = (uint32_t)ix.x, v2 = (uint32_t)ix.y;
       const Label a = load_label(v1), b = load_label(v2);
-      valid = face_time(v1, v2, a, b, band_end, goal, T);
-      if (valid) eval_face((double)a.d, (double)b.d, (double)w.z, (double)w.y, (double)w.x, U, X);
+      uint32_t Tv = 0;
+      valid = face_time(v1, v2, a, b, band_end, goal, T, Tv);
+      if (valid) {
+        eval_face((double)a.d, (double)b.d, (double)w.z, (double)w.y, (double)w.x, U, X);
+        // back-step from a trigger that was re-labelled last round: defer (see backstep_ok)
+        if (!backstep_ok((float)X, T, Tv, round)) X = (double)__uint_as_float(INF_BITS);
+      }
     }
     // rank of every valid lane in (T, slot) order: all-pairs comparison inside the 8-lane group
     const unsigned long long hi = ((unsigned long long)__float_as_uint(T.a1) << 32) | __float_as_uint(T.a2);
@@ -307,6 +330,120 @@ struct CvpEllProblem : CvpProblem {
 };
 
 // ---------------------------------------------------------------------------
+// Inflation: multi-source FMM from the lethal set (InflationLayer::waveCostInflation,
+// inflation_layer.cpp:341-491) with the Kimmel-Sethian update in float (:181-313).
+//   * lethal vertices: d = 0, pre-fixed, popped first in id order (:397-402);
+//   * the face (v1,v2,c) updates c when the later of v1,v2 pops (:443-470);  u3 == 0 never updates (:252);
+//   * an accepted update always lowers distances_[c] (:299) but only (re)inserts c into the heap if both
+//     sources are within the inflation radius (:310,:452): the label d and the heap key (= pop time) are
+//     therefore tracked separately; a vertex that was never inserted never pops and is never a source;
+//   * invalid vertices pop but are not fixed and do not expand (:417-422) unless lethal (fixed at :400).
+// Corner weights are edge_distances (:383), record {|v1v2|, |v1c|, |v2c|}.
+// ---------------------------------------------------------------------------
+struct InflationProblem {
+  const uint32_t* __restrict__ cor_ptr;
+  const int4* __restrict__ cor_idx;
+  const float4* __restrict__ cor_wd;
+  const uint8_t* __restrict__ invalid;  // may be null
+  uint4* state;
+  uint32_t* minor_arr;
+  uint32_t* chg;
+  mutable float deferred_m;
+  float max_distance;
+
+  static constexpr int MAXF = 12;
+
+  __device__ __forceinline__ Label load_label(uint32_t v) const {
+    const uint4 s = __ldcg(&state[v]);
+    Label l; l.d = __uint_as_float(s.x); l.t.a1 = __uint_as_float(s.y); l.t.a2 = __uint_as_float(s.z);
+    l.t.a3 = __uint_as_float(s.w & 0x7fffffffu);
+    l.t.minor = (s.w >> 31) ? __ldcg(&minor_arr[v]) : 2u * v;
+    return l;
+  }
+  __device__ __forceinline__ void store_label(uint32_t c, float d, const EvTime& t, bool relabel, uint32_t round) const {
+    uint32_t w = __float_as_uint(t.a3);
+    if (t.minor != 2u * c) { __stcg(&minor_arr[c], t.minor); w |= 0x80000000u; }
+    if (relabel) __stcg(&chg[c], round + 1u);
+    __stcg(&state[c], make_uint4(__float_as_uint(d), __float_as_uint(t.a1), __float_as_uint(t.a2), w));
+  }
+  __device__ __forceinline__ bool backstep_ok(float X, const EvTime& T, uint32_t Tv, uint32_t round) const {   // see CvpProblem
+    if (X > T.a1) return true;
+    if (__ldcg(&chg[Tv]) < round) return true;
+    deferred_m = fminf(deferred_m, T.a1);
+    return false;
+  }
+  __device__ __forceinline__ bool eligible(uint32_t) const { return true; }   // no cost / validity test on the target
+
+  template <class F>
+  __device__ __forceinline__ void activate(uint32_t c, F push) const {
+    const uint32_t kb = cor_ptr[c], ke = cor_ptr[c + 1];
+    for (uint32_t k = kb; k < ke; ++k) {
+      const int4 ix = __ldg(&cor_idx[k]);
+      push((uint32_t)ix.x);
+      push((uint32_t)ix.y);
+    }
+  }
+
+  __device__ __forceinline__ bool corner_time(uint32_t k, float band_end, EvTime& T, uint32_t& Tv, float& u1, float& u2) const {
+    const int4 ix = __ldg(&cor_idx[k]);
+    const uint32_t v1 = (uint32_t)ix.x, v2 = (uint32_t)ix.y;
+    const Label a = load_label(v1), b = load_label(v2);
+    u1 = a.d; u2 = b.d;
+    // a source must get fixed: it is lethal (d == 0) or it is (re)inserted at some point (finite pop time)
+    if (__float_as_uint(a.t.a1) == INF_BITS || __float_as_uint(b.t.a1) == INF_BITS) return false;
+    if (!(a.t.a1 < band_end) || !(b.t.a1 < band_end)) return false;
+    const bool l1 = (u1 == 0.0f), l2 = (u2 == 0.0f);
+    const bool i1 = invalid && invalid[v1], i2 = invalid && invalid[v2];
+    if ((i1 && !l1) || (i2 && !l2)) return false;           // popped but never fixed (:417)
+    const bool v1_later = ev_less(b.t, a.t);
+    if (l1 && l2) {                                          // both pre-fixed: first one that expands
+      const bool e1 = !i1, e2 = !i2;
+      if (!e1 && !e2) return false;
+      const bool use1 = e1 && (!e2 || !v1_later);
+      T = use1 ? a.t : b.t; Tv = use1 ? v1 : v2;
+      return true;
+    }
+    if (v1_later ? i1 : i2) return false;                    // the popping vertex must expand
+    T = v1_later ? a.t : b.t; Tv = v1_later ? v1 : v2;
+    return true;
+  }
+
+  __device__ __forceinline__ bool recompute(uint32_t c, float band_end, float /*goal*/, uint32_t round, const Label& old, float& nd, float& ntau) {
+    const uint32_t kb = cor_ptr[c], ke = cor_ptr[c + 1];
+    EvTime Tt[MAXF]; float U1[MAXF], U2[MAXF]; uint32_t K[MAXF], TV[MAXF];
+    int n = 0;
+    for (uint32_t k = kb; k < ke && n < MAXF; ++k) {   // vertices with more than MAXF usable faces: surplus ignored (mnb_set_mesh reports the max degree)
+      EvTime T; float u1, u2; uint32_t Tv;
+      if (!corner_time(k, band_end, T, Tv, u1, u2)) continue;
+      Tt[n] = T; U1[n] = u1; U2[n] = u2; K[n] = k; TV[n] = Tv; ++n;
+    }
+    const float INF = __uint_as_float(INF_BITS);
+    float cur = INF;
+    EvTime tc = ev_normal(INF, c);                         // pop time = heap key; +inf while not inserted
+    // an invalid vertex is popped but never fixed (:417-422): it keeps receiving updates from every face
+    const bool never_fixed = invalid && invalid[c];
+    for (int i = 0; i < n; ++i) {
+      int b = i;
+      for (int j = i + 1; j < n; ++j)
+        if (ev_less(Tt[j], Tt[b]) || (ev_eq(Tt[j], Tt[b]) && K[j] < K[b])) b = j;
+      const EvTime T = Tt[b]; const float u1 = U1[b], u2 = U2[b]; const uint32_t k = K[b], Tv = TV[b];
+      Tt[b] = Tt[i]; U1[b] = U1[i]; U2[b] = U2[i]; K[b] = K[i]; TV[b] = TV[i];
+      if (!never_fixed && !ev_less(T, tc)) break;          // c was popped (and fixed) before this face fires
+      const float4 w = __ldg(&cor_wd[k]);
+      const float cand = inflation_candidate(u1, u2, w.z, w.y, w.x);   // a = |v2c|, b = |v1c|, c = |v1v2|
+      if (cand < cur && backstep_ok(cand, T, Tv, round)) {                                    // :297 (non-finite candidates were mapped to +inf)
+        cur = cand;
+        if (u1 <= max_distance && u2 <= max_distance) tc = CvpProblem::accept_time(c, cand, T);   // :310 -> pq.insert(c, cand)
+      }
+    }
+    nd = cur; ntau = tc.a1;
+    if (__float_as_uint(nd) == __float_as_uint(old.d) && ev_eq(tc, old.t)) return false;
+    store_label(c, nd, tc, __float_as_uint(old.d) != INF_BITS, round);
+    return true;
+  }
+};
+
+// ---------------------------------------------------------------------------
 // Dijkstra: d[c] = min over expandable neighbours u of fl(d[u] + w(u,c));
 // among equal sums the neighbour that pops first wins (strict '<' at
 // dijkstra_mesh_planner.cpp:332): order (d[u], u).  Edge weights are >= 0 so a
@@ -321,6 +458,7 @@ struct DijkstraProblem {
   uint4* state;
   uint32_t* pred;
   double cost_limit;
+  float deferred_m;                     // unused (edge weights >= 0: no back-steps), kept for the engine interface
 
   __device__ __forceinline__ Label load_label(uint32_t v) const {
     const uint4 s = __ldcg(&state[v]);
@@ -335,7 +473,7 @@ struct DijkstraProblem {
     for (uint32_t k = kb; k < ke; ++k) push(__ldg(&adj_nw[k]).x);
   }
 
-  __device__ __forceinline__ bool recompute(uint32_t c, float band_end, float goal, const Label& old, float& nd, float& ntau) {
+  __device__ __forceinline__ bool recompute(uint32_t c, float band_end, float goal, uint32_t /*round*/, const Label& old, float& nd, float& ntau) {
     const uint32_t kb = adj_ptr[c], ke = adj_ptr[c + 1];
     float best = __uint_as_float(INF_BITS), best_du = best; uint32_t best_u = c;
     for (uint32_t k = kb; k < ke; ++k) {

@@ -653,4 +653,140 @@ void orc_inflation(void* h, const float* edge_distances, const uint8_t* invalid,
   if (stats) { stats[0] = (double)pops; stats[1] = t1 - t0; stats[2] = (double)calls; }
 }
 
+
+// ---------------------------------------------------------------------------
+// Geometric cost layers (mesh_layers/src/*_layer.cpp).  Steepness, Ridge, the Clearance cost mapping,
+// the lethal rule (cost > threshold) and the Max combination are in the reference tree; height
+// differences, roughness, border costs, normals and the radius neighbourhood are lvr2 functions
+// (calcVertexHeightDifferences, calcVertexRoughness, calcBorderCosts, calcFaceNormals,
+// calcVertexNormals, visitLocalVertexNeighborhood -- un-vendored, lvr2 @ main).  Their DEFINITIONS
+// here are this repo's documented restatement, not verifiable offline: PARITY UNPINNED.
+//   face normal    = normalize(cross(p1 - p0, p2 - p0))
+//   vertex normal  = normalize(sum of incident face normals, ascending face id)
+//   neighbourhood  = stack traversal from v over mesh edges (CSR order); a not-yet-seen neighbour n is
+//                    marked seen, and if |p_n - p_v| < radius it is visited and pushed; v itself is not visited
+// ---------------------------------------------------------------------------
 }  // extern "C"
+static inline void vsub(const float* a, const float* b, float* o) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; }
+
+extern "C" void orc_normals(void* h, float* face_normals /*3F*/, float* vertex_normals /*3V*/) {
+  OrcMesh& m = *(OrcMesh*)h;
+  for (uint32_t f = 0; f < m.F; ++f) {
+    const float* p0 = &m.pos[3 * (size_t)m.faces[3 * (size_t)f]];
+    const float* p1 = &m.pos[3 * (size_t)m.faces[3 * (size_t)f + 1]];
+    const float* p2 = &m.pos[3 * (size_t)m.faces[3 * (size_t)f + 2]];
+    float a[3], b[3], n[3];
+    vsub(p1, p0, a); vsub(p2, p0, b);
+    n[0] = a[1] * b[2] - a[2] * b[1]; n[1] = a[2] * b[0] - a[0] * b[2]; n[2] = a[0] * b[1] - a[1] * b[0];
+    vnormalize(n);
+    for (int k = 0; k < 3; ++k) face_normals[3 * (size_t)f + k] = n[k];
+  }
+  for (uint32_t v = 0; v < m.V; ++v) {
+    float n[3] = {0, 0, 0};
+    for (uint32_t k = m.vf_ptr[v]; k < m.vf_ptr[v + 1]; ++k)
+      for (int c = 0; c < 3; ++c) n[c] = n[c] + face_normals[3 * (size_t)m.vf_face[k] + c];
+    vnormalize(n);
+    for (int c = 0; c < 3; ++c) vertex_normals[3 * (size_t)v + c] = n[c];
+  }
+}
+
+struct OrcLayerParams {            // config structs at the end of mesh_layers/include/mesh_layers/*_layer.h
+  double height_diff_threshold, height_diff_radius;      // 0.185, 0.3
+  double roughness_threshold, roughness_radius;          // 0.3, 0.3
+  double steepness_threshold;                            // 0.3
+  double ridge_threshold, ridge_radius;                  // 0.3, 0.3
+  double clearance_robot_height, clearance_height_inflation;  // 0.5, 0.3
+  double border_threshold, border_cost;                  // 0.5, 1.0
+};
+
+template <class Visit>
+static void visitNeighbourhood(const OrcMesh& m, uint32_t v, float radius, std::vector<uint32_t>& seen,
+                               std::vector<uint32_t>& stack, Visit visit) {
+  seen.clear(); stack.clear();
+  seen.push_back(v); stack.push_back(v);
+  const float* pv = &m.pos[3 * (size_t)v];
+  while (!stack.empty()) {
+    const uint32_t u = stack.back(); stack.pop_back();
+    for (uint32_t k = m.ve_ptr[u]; k < m.ve_ptr[u + 1]; ++k) {
+      const uint32_t n = m.ve_nbr[k];
+      bool was = false;
+      for (uint32_t s : seen) if (s == n) { was = true; break; }
+      if (was) continue;
+      seen.push_back(n);
+      const float* pn = &m.pos[3 * (size_t)n];
+      const float dx = pn[0] - pv[0], dy = pn[1] - pv[1], dz = pn[2] - pv[2];
+      if (std::sqrt(dx * dx + dy * dy + dz * dz) < radius) { visit(n); stack.push_back(n); }
+    }
+  }
+}
+
+// costs: 6 arrays of V floats in the order height_diff, roughness, steepness, ridge, clearance, border;
+// combined = MaxCombinationLayer (combination_layer.cpp:44-85); lethal_mask bit i = lethal in layer i
+// (computeLethals: cost > threshold, e.g. height_diff_layer.cpp:67-79; clearance: clearance < robot_height,
+// clearance_layer.cpp:79-83).  clearance may be null (= +inf everywhere: no ray hits).
+extern "C" void orc_layers(void* h, const OrcLayerParams* P, const float* vertex_normals, const float* clearance,
+                float* height_diff, float* roughness, float* steepness, float* ridge, float* clearance_cost,
+                float* border, float* combined, uint8_t* lethal_mask) {
+  OrcMesh& m = *(OrcMesh*)h;
+  std::vector<uint32_t> seen, stack;
+  std::vector<uint8_t> is_border(m.V, 0);
+  for (uint32_t e = 0; e < m.E; ++e)
+    if (m.edge_faces[2 * (size_t)e + 1] < 0) { is_border[m.edges[2 * (size_t)e]] = 1; is_border[m.edges[2 * (size_t)e + 1]] = 1; }
+  for (uint32_t v = 0; v < m.V; ++v) {
+    const float* pv = &m.pos[3 * (size_t)v];
+    const float* nv = &vertex_normals[3 * (size_t)v];
+    // height differences: max - min of z over the neighbourhood including v (lvr2::calcVertexHeightDifferences)
+    float zmin = pv[2], zmax = pv[2];
+    visitNeighbourhood(m, v, (float)P->height_diff_radius, seen, stack, [&](uint32_t n) {
+      const float z = m.pos[3 * (size_t)n + 2];
+      zmin = std::min(zmin, z); zmax = std::max(zmax, z);
+    });
+    const float hd = zmax - zmin;
+    // roughness: mean angle between the vertex normal and the neighbours' normals (lvr2::calcVertexRoughness)
+    float rsum = 0.0f; int rcnt = 0;
+    visitNeighbourhood(m, v, (float)P->roughness_radius, seen, stack, [&](uint32_t n) {
+      const float* nn = &vertex_normals[3 * (size_t)n];
+      float dot = nv[0] * nn[0] + nv[1] * nn[1] + nv[2] * nn[2];
+      dot = std::min(1.0f, std::max(-1.0f, dot));
+      rsum = rsum + std::acos(dot); rcnt++;
+    });
+    const float ro = rcnt ? rsum / (float)rcnt : 0.0f;
+    // steepness (steepness_layer.cpp:165)
+    const float st = std::acos(nv[2]);
+    // ridge (ridge_layer.cpp:155-184)
+    float value = 0.0f; int num = 0;
+    const float ref[3] = {pv[0] + nv[0], pv[1] + nv[1], pv[2] + nv[2]};
+    visitNeighbourhood(m, v, (float)P->ridge_radius, seen, stack, [&](uint32_t n) {
+      const float* pn = &m.pos[3 * (size_t)n]; const float* nn = &vertex_normals[3 * (size_t)n];
+      const float cx = (pn[0] + nn[0]) - ref[0], cy = (pn[1] + nn[1]) - ref[1], cz = (pn[2] + nn[2]) - ref[2];
+      value += std::sqrt(cx * cx + cy * cy + cz * cz);
+      num++;
+    });
+    const float ri = num == 0 ? (float)(P->ridge_threshold + 0.1) : value / num;
+    // clearance cost mapping (clearance_layer.cpp:77-96)
+    const float cl = clearance ? clearance[v] : FINF;
+    float cc; bool cl_lethal = false;
+    const double inflated_height = P->clearance_robot_height + P->clearance_height_inflation;
+    if (cl < P->clearance_robot_height) { cc = 1.0f; cl_lethal = true; }
+    else if (cl < inflated_height) {
+      const double diff = (cl - P->clearance_robot_height) / P->clearance_height_inflation;
+      cc = (float)((cos(diff * M_PI) + 1.0) / 2.0);
+    } else cc = 0.0f;
+    // border (lvr2::calcBorderCosts)
+    const float bo = is_border[v] ? (float)P->border_cost : 0.0f;
+    height_diff[v] = hd; roughness[v] = ro; steepness[v] = st; ridge[v] = ri; clearance_cost[v] = cc; border[v] = bo;
+    uint8_t mask = 0;
+    if (hd > P->height_diff_threshold) mask |= 1;
+    if (ro > P->roughness_threshold) mask |= 2;
+    if (st > P->steepness_threshold) mask |= 4;
+    if (ri > P->ridge_threshold) mask |= 8;
+    if (cl_lethal) mask |= 16;
+    if (bo > P->border_threshold) mask |= 32;
+    lethal_mask[v] = mask;
+    float c = 0.0f;                                         // MaxCombinationLayer default value 0
+    c = std::max(c, hd); c = std::max(c, ro); c = std::max(c, st); c = std::max(c, ri); c = std::max(c, cc); c = std::max(c, bo);
+    combined[v] = c;
+  }
+}
+
+

@@ -53,6 +53,8 @@ def lib():
         L.orc_fading.argtypes = [dbl, dbl, dbl, dbl, dbl, f32]
         L.orc_sethian_update.restype = f32
         L.orc_sethian_update.argtypes = [f32] * 6
+        L.orc_normals.argtypes = [vp, vp, vp]
+        L.orc_layers.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.orc_inflation.argtypes = [vp, vp, vp, vp, u32, dbl, dbl, dbl, dbl, dbl, C.c_int, vp, vp, vp, vp]
         _lib = L
     return _lib
@@ -149,6 +151,36 @@ class OracleMesh:
                             float(cost_scaling_factor), int(canonical_ties), _p(dist), _p(cost), _p(vec), _p(stats))
         return dict(dist=dist, cost=cost, vectors=vec, pops=int(stats[0]), seconds=float(stats[1]),
                     updates=int(stats[2]))
+
+
+class LayerParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "height_diff_threshold", "height_diff_radius", "roughness_threshold", "roughness_radius", "steepness_threshold",
+        "ridge_threshold", "ridge_radius", "clearance_robot_height", "clearance_height_inflation", "border_threshold",
+        "border_cost")]
+
+    @staticmethod
+    def defaults():
+        return LayerParams(0.185, 0.3, 0.3, 0.3, 0.3, 0.3, 0.3, 0.5, 0.3, 0.5, 1.0)
+
+
+LAYER_NAMES = ["height_diff", "roughness", "steepness", "ridge", "clearance", "border"]
+
+
+def _layers(self, params=None, clearance=None):
+    P = params or LayerParams.defaults()
+    fn = np.empty((self.F, 3), np.float32); vn = np.empty((self.V, 3), np.float32)
+    lib().orc_normals(self._h, _p(fn), _p(vn))
+    outs = [np.empty(self.V, np.float32) for _ in range(6)]
+    comb = np.empty(self.V, np.float32); mask = np.empty(self.V, np.uint8)
+    cl = None if clearance is None else np.ascontiguousarray(clearance, dtype=np.float32)
+    lib().orc_layers(self._h, C.byref(P), _p(vn), _p(cl), *[_p(o) for o in outs], _p(comb), _p(mask))
+    r = dict(zip(LAYER_NAMES, outs))
+    r.update(combined=comb, lethal_mask=mask, vertex_normals=vn, face_normals=fn)
+    return r
+
+
+OracleMesh.layers = _layers
 
 
 def fading(distance, inscribed_radius=0.25, inflation_radius=0.4, lethal_value=1.0, inscribed_value=0.99,

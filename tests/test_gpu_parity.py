@@ -205,3 +205,114 @@ def test_large_mesh_properties(api, oracle_mod):
     a, b = om.edges[:, 0], om.edges[:, 1]
     assert (np.abs(gd["dist"][a] - gd["dist"][b]) <= w + 2e-5).all()      # one float ulp at d ~ 100 m is 7.6e-6
     mm.close()
+
+
+INFL_DIST_RTOL = 1e-4    # proposed bar: inflation dist <= 1e-4 rel, costs <= 1e-5 rel
+
+
+def check_inflation(got, ref, radius):
+    fr, fg = np.isfinite(ref["dist"]), np.isfinite(got["dist"])
+    assert (fr == fg).all(), f"labelled sets differ: only ref {(fr & ~fg).sum()}, only gpu {(fg & ~fr).sum()}"
+    r = rel_err(got["dist"], ref["dist"])
+    assert r.max() <= INFL_DIST_RTOL, f"max rel err {r.max():.3e}"
+    assert (np.isnan(got["cost"]) == np.isnan(ref["cost"])).all()
+    ok = ~np.isnan(ref["cost"])
+    assert np.allclose(got["cost"][ok], ref["cost"][ok], rtol=1e-5, atol=1e-7)
+    inside = fr & (ref["dist"] <= radius)
+    return int((got["dist"][inside].view(np.uint32) != ref["dist"][inside].view(np.uint32)).sum())
+
+
+@pytest.mark.parametrize("n,terrain,discs,rad", [(100, False, 8, 0.3), (160, True, 40, 0.3), (120, True, 10, 0.15)])
+def test_inflation_wave(api, oracle_mod, n, terrain, discs, rad):
+    """InflationLayer::waveCostInflation: synthetic obstacle discs (SURVEY 8d config 3), default config"""
+    pos, faces, om, mm, ed, vc, w = setup(api, oracle_mod, n, terrain)
+    assert int(np.diff(np.bincount(faces.reshape(-1))).max()) < 12
+    le = disc_lethals(pos, discs, rad)
+    assert le.size > 10
+    ref = om.inflation(ed, le)
+    got = api.InflationLayer(mm).waveCostInflation(le)
+    assert check_inflation(got, ref, 0.4) == 0, "distances inside the inflation radius are expected bit-identical"
+    mm.close()
+
+
+def test_inflation_params_invalid_and_edge_cases(api, oracle_mod):
+    """reference test config (0.5 / 1.5 / 0.9, inflation_layer_test.cpp:41-45), invalid vertices (:417),
+    isolated lethal vertices (no face with two fixed vertices -> no propagation), empty lethal set"""
+    rng = np.random.default_rng(11)
+    pos, faces, om, mm, ed, vc, w = setup(api, oracle_mod, 150, True)
+    le = np.concatenate([disc_lethals(pos, 12, 0.35, seed=3), np.array([5, 5, 777, 12000], np.uint32)])
+    invalid = (rng.random(om.V) < 0.01).astype(np.uint8)
+    kw = dict(inscribed_radius=0.5, inflation_radius=1.5, lethal_value=1.0, inscribed_value=0.9, cost_scaling_factor=1.0)
+    for inv in (None, invalid):
+        ref = om.inflation(ed, le, invalid=inv, **kw)
+        got = api.InflationLayer(mm, **kw).waveCostInflation(le, inv)
+        check_inflation(got, ref, 1.5)
+    ref = om.inflation(ed, np.array([4000], np.uint32))
+    got = api.InflationLayer(mm).waveCostInflation(np.array([4000], np.uint32))
+    assert np.isfinite(got["dist"]).sum() == np.isfinite(ref["dist"]).sum() == 1
+    got = api.InflationLayer(mm).waveCostInflation(np.zeros(0, np.uint32))
+    assert not np.isfinite(got["dist"]).any() and np.isnan(got["cost"]).all()
+    mm.close()
+
+
+LAYER_RTOL = 1e-5    # proposed bar (BASELINE.md config 3): layer costs <= 1e-5 rel
+
+
+def test_geometric_layers_fused(api, oracle_mod):
+    """six geometric layers + Max combination + lethal masks (a10/a11); definitions: oracle orc_layers"""
+    pos, faces, om, mm, ed, vc, w = setup(api, oracle_mod, 220, True)
+    ref = om.layers()
+    assert np.allclose(mm.vertexNormals(), ref["vertex_normals"], rtol=0, atol=1e-6)
+    got = mm.computeLayers()
+    for name in ("height_diff", "ridge", "clearance", "border"):      # no transcendental: bit-identical
+        assert (got[name].view(np.uint32) == ref[name].view(np.uint32)).all(), name
+    for name in ("roughness", "steepness", "combined"):               # acosf: CUDA vs glibc differ by <= 2 ulp
+        assert np.allclose(got[name], ref[name], rtol=LAYER_RTOL, atol=1e-6), name
+    # lethal sets identical except where a cost sits within float noise of its threshold
+    thr = {2: 0.3, 4: 0.3}
+    diff = got["lethal_mask"] != ref["lethal_mask"]
+    for v in np.where(diff)[0]:
+        bits = int(got["lethal_mask"][v]) ^ int(ref["lethal_mask"][v])
+        assert bits in thr or bits == 6
+        name = {2: "roughness", 4: "steepness"}.get(bits, "steepness")
+        assert abs(float(ref[name][v]) - 0.3) < 1e-5
+    assert (ref["lethal_mask"] != 0).sum() > 100
+    # non-default radii (three separate walks) and a clearance input
+    P = oracle_mod.LayerParams.defaults(); P.height_diff_radius = 0.25; P.ridge_radius = 0.4; P.roughness_radius = 0.2
+    from mesh_navigation_b200 import _lib
+    G = _lib.LayerParams.defaults(); G.height_diff_radius = 0.25; G.ridge_radius = 0.4; G.roughness_radius = 0.2
+    rng = np.random.default_rng(2)
+    cl = (0.3 + rng.random(om.V) * 0.8).astype(np.float32); cl[::7] = np.inf
+    ref = om.layers(P, cl); got = mm.computeLayers(G, cl)
+    for name in ("height_diff", "ridge", "border"):
+        assert (got[name].view(np.uint32) == ref[name].view(np.uint32)).all(), name
+    assert np.allclose(got["clearance"], ref["clearance"], rtol=1e-6, atol=1e-7)
+    assert ((got["lethal_mask"] & 16) == (ref["lethal_mask"] & 16)).all()
+    mm.close()
+
+
+def test_config3_layer_stack_chain(api, oracle_mod):
+    """config 3 chain: layers -> Max combination -> lethals (+ obstacle discs) -> waveCostInflation ->
+    vertex_costs -> computeEdgeWeights (factor 1.0) -> CVP plan; every stage checked against the oracle"""
+    pos, faces, om, mm, ed, vc, w = setup(api, oracle_mod, 250, True)
+    ref_l = om.layers(); got_l = mm.computeLayers()
+    lethal_ref = np.union1d(np.where(ref_l["lethal_mask"] != 0)[0], disc_lethals(pos, 15, 0.3)).astype(np.uint32)
+    lethal_got = np.union1d(np.where(got_l["lethal_mask"] != 0)[0], disc_lethals(pos, 15, 0.3)).astype(np.uint32)
+    assert np.setxor1d(lethal_ref, lethal_got).size <= 2
+    ref_i = om.inflation(ed, lethal_ref); got_i = api.InflationLayer(mm).waveCostInflation(lethal_ref)
+    check_inflation(got_i, ref_i, 0.4)
+    vcost = np.where(np.isnan(ref_i["cost"]), 0.0, ref_i["cost"]).astype(np.float32)   # InflationLayer default value 0
+    w1 = om.edge_weights(vcost, ed, 1.0)
+    gw = mm.computeEdgeWeights(vcost, 1.0)
+    assert (gw.view(np.uint32) == w1.view(np.uint32)).all()
+    v, f, sp = centre_seed(pos, faces, (0.5, 0.5))
+    free = np.where(vcost < 0.5)[0]
+    v = int(free[np.argmin(np.linalg.norm(pos[free] - pos[v], axis=1))]); f = face_of_vertex(faces, v)
+    while not (vcost[faces[f]] < 1.0).all():
+        f += 1
+    sp = pos[faces[f]].mean(0).astype(np.float32)
+    ref = om.cvp(w1, vcost, f, sp)
+    got = api.CVPMeshPlanner(mm).waveFrontPropagation(f, sp)
+    check_cvp(got, ref)
+    assert np.isfinite(ref["dist"]).sum() > 0.5 * om.V
+    mm.close()
