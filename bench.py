@@ -154,6 +154,9 @@ def main():
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--delta", type=float, default=0.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch-goals", type=int, default=1024, help="goals of the batched leg (config 4); 0 disables it")
+    ap.add_argument("--batch-size", type=int, default=1000, help="grid side of the batched leg's mesh")
+    ap.add_argument("--batch-steps", type=int, default=2)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -247,6 +250,51 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = total_settled * e2e_steps / float(te[0])
 
+    # ---- batched leg (config 4): G goals on the 1M terrain, goal k -> rank k mod N, potentials all-gathered ----
+    batched = None
+    if args.batch_goals > 0:
+        from mesh_navigation_b200 import parallel as PL
+        from mesh_navigation_b200 import synth
+        nb = args.batch_size
+        bpos, bfaces = build_workload(nb)
+        bm = MeshMap(bpos, bfaces, device=local)
+        bm.setCosts(np.zeros(bm.V, np.float32), bm.edgeDistances())
+        goals = synth.batch_goal_vertices(bm.V, args.batch_goals, seed=1234)
+        gi, gj = np.minimum(goals % nb, nb - 2), np.minimum(goals // nb, nb - 2)
+        sfs = (2 * (gj * (nb - 1) + gi)).astype(np.uint32)
+        sps = bpos[bfaces[sfs]].mean(1).astype(np.float32)
+        bm.use_device_pointers(True)
+        b_kernel_ms = []
+
+        def compute_chunk(idx, out):
+            bm.cvp_batch_dev(sfs[idx], sps[idx], 1.0, out.data_ptr())
+            b_kernel_ms.append(bm.stats()["kernel_ms"])
+
+        def batch_step():
+            return PL.sharded_potentials(compute_chunk, args.batch_goals, bm.V, rank=rank, world=world, device=dev,
+                                         chunk=512, dist=dist if world > 1 else None, torch=torch)
+
+        batch_step(); sync_all()
+        b_kernel_ms.clear()
+        t0 = time.perf_counter()
+        for _ in range(args.batch_steps):
+            res = batch_step()
+        sync_all()
+        dtb = time.perf_counter() - t0
+        tb = torch.tensor([dtb], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        dtb = float(tb[0])
+        bm.use_device_pointers(False)
+        plans_s = args.batch_goals * args.batch_steps / dtb
+        b_achieved = CVP_BYTES_PER_VERTEX * bm.V * len(PL.shard_indices(args.batch_goals, rank, world)) * args.batch_steps / (sum(b_kernel_ms) * 1e-3) / 1e9
+        batched = {"plans_per_s": plans_s, "goals": args.batch_goals, "mesh_vertices": int(bm.V), "n_gpus": world,
+                   "vertex_relaxations_per_s": plans_s * bm.V, "ms_per_batch": 1e3 * dtb / args.batch_steps,
+                   "scaling": "strong (fixed goal count)", "gather": "NCCL all_gather of float[goals][V], overlapped per chunk" if world > 1 else "none (single GPU)",
+                   "roofline_hbm_frac_rank0": b_achieved / peaks()[0], "achieved_gbs_rank0": b_achieved}
+        del res
+        bm.close()
+
     if rank == 0:
         hbm, which = peaks()
         k_ms = float(np.mean(kernel_ms))
@@ -267,6 +315,8 @@ def main():
                          "note": "single wavefront is dependency-latency bound (SURVEY.md H3)"},
             "clocks": clocks,
         }
+        if batched:
+            line["batched"] = batched
         if not args.no_cpu_baseline:
             from oracle import oracle as O
             nb = args.ref_size

@@ -41,6 +41,7 @@ namespace mnb {
 namespace cg = cooperative_groups;
 
 constexpr uint32_t INF_BITS = 0x7f800000u;
+constexpr int STAGNATION_ROUNDS = 24;
 
 // pop time of a vertex: monotonic stack of water levels a1 > a2 > a3 (0 = unused) + tie-break minor
 struct EvTime { float a1, a2, a3; uint32_t minor; };
@@ -75,6 +76,7 @@ struct GroupCtl {               // one per wavefront group, global memory
   int robot_left;               // robot-face vertices not yet settled
   unsigned int query;           // batch: query index owned by the group
   unsigned long long rounds, recomputes, settled;
+  unsigned int strict_armed;    // wavefronts that had to arm the strict back-step rule
 };
 
 template <int CS>
@@ -144,6 +146,8 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
                                 const float band_end_init, const uint32_t max_rounds) {
   float band_end_prev = band_end_init;  // > every seed potential: seeds are available from round 0
   unsigned long long my_recomputes = 0, my_settled = 0;
+  float lo_best = -1.0f; int stagnant = 0;       // best (largest) earliest-unsettled pop time seen so far
+  prob.strict = 0;
   uint32_t r = 0;
   for (;; ++r) {
     const uint32_t slot = r % 3, prev = (r + 2) % 3, next = (r + 1) % 3;
@@ -156,6 +160,10 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
     if (n == 0 || stop || r > max_rounds) break;   // r is group-uniform: the watchdog cannot deadlock the barrier
     if (r > 0 && __float_as_uint(m_prev) == INF_BITS &&
         (__float_as_uint(lo_prev) == INF_BITS || lo_prev > goal)) break;
+    // stagnation watch (all values are group-uniform): labels keep changing but the earliest unsettled pop
+    // time does not move -> a dependency cycle between a trigger and its back-step child; arm the strict rule
+    if (r > 0 && __float_as_uint(m_prev) != INF_BITS && !(lo_prev > lo_best)) { if (++stagnant >= STAGNATION_ROUNDS) prob.strict = 1; }
+    else { stagnant = 0; if (lo_prev > lo_best) lo_best = lo_prev; }
     float band_end = lo_prev + delta;
     if (!(band_end > band_end_prev)) band_end = band_end_prev;
     uint32_t* list_r = (r & 1) ? list1 : list0;
@@ -223,6 +231,7 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
   atomicAdd(&ctl->settled, my_settled);
   if (gtid == 0) {
     ctl->rounds += r;
+    if (prob.strict) ctl->strict_armed += 1;
     ctl->goal_bits = min(ctl->goal_ring[0], ctl->goal_ring[1]);
   }
 }
@@ -239,6 +248,8 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
                                      const float band_end_init, const uint32_t max_rounds) {
   float band_end_prev = band_end_init;
   unsigned long long my_recomputes = 0, my_settled = 0;
+  float lo_best = -1.0f; int stagnant = 0;       // best (largest) earliest-unsettled pop time seen so far
+  prob.strict = 0;
   const uint32_t gsubs = gthreads >> 3, gsub = gtid >> 3, j = threadIdx.x & 7;
   const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
   uint32_t r = 0;
@@ -253,6 +264,10 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
     if (n == 0 || stop || r > max_rounds) break;   // r is group-uniform: the watchdog cannot deadlock the barrier
     if (r > 0 && __float_as_uint(m_prev) == INF_BITS &&
         (__float_as_uint(lo_prev) == INF_BITS || lo_prev > goal)) break;
+    // stagnation watch (all values are group-uniform): labels keep changing but the earliest unsettled pop
+    // time does not move -> a dependency cycle between a trigger and its back-step child; arm the strict rule
+    if (r > 0 && __float_as_uint(m_prev) != INF_BITS && !(lo_prev > lo_best)) { if (++stagnant >= STAGNATION_ROUNDS) prob.strict = 1; }
+    else { stagnant = 0; if (lo_prev > lo_best) lo_best = lo_prev; }
     float band_end = lo_prev + delta;
     if (!(band_end > band_end_prev)) band_end = band_end_prev;
     uint32_t* list_r = (r & 1) ? list1 : list0;
@@ -327,6 +342,7 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
   atomicAdd(&ctl->settled, my_settled);
   if (gtid == 0) {
     ctl->rounds += r;
+    if (prob.strict) ctl->strict_armed += 1;
     ctl->goal_bits = min(ctl->goal_ring[0], ctl->goal_ring[1]);
   }
 }

@@ -116,8 +116,11 @@ __device__ __forceinline__ void ctl_reset(GroupCtl* ctl, unsigned int n0, float 
   ctl->goal_bits = INF_BITS; ctl->robot_left = 0;
 }
 
+#ifndef MNB_CVP_MINBLOCKS
+#define MNB_CVP_MINBLOCKS 1
+#endif
 template <int CS>
-__global__ void __launch_bounds__(512, 1) k_cvp(const CvpKernelArgs a) {
+__global__ void __launch_bounds__(512, MNB_CVP_MINBLOCKS) k_cvp(const CvpKernelArgs a) {
   __shared__ Stage st;
   uint32_t g, gthreads, gtid;
   group_coords<CS>(g, gthreads, gtid);
@@ -142,8 +145,9 @@ __global__ void __launch_bounds__(512, 1) k_cvp(const CvpKernelArgs a) {
 
     const uint32_t sf = a.seed_faces[q];
     const uint32_t s0 = a.faces[3 * (size_t)sf], s1 = a.faces[3 * (size_t)sf + 1], s2 = a.faces[3 * (size_t)sf + 2];
-    CvpProblem prob;
+    CvpEllProblem prob;
     prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_w = a.cor_w; prob.cost = a.cost; prob.invalid = a.invalid;
+    prob.ell_idx = a.ell_idx; prob.ell_w = a.ell_w;
     prob.state = state; prob.minor_arr = a.ws.minor + (size_t)g * V; prob.chg = chg; prob.deferred_m = __uint_as_float(INF_BITS); prob.pred = nullptr; prob.dir = nullptr; prob.cut = nullptr; prob.cost_limit = a.cost_limit;
     prob.s0 = s0; prob.s1 = s1; prob.s2 = s2; prob.seed_noexpand = 0;
     float sd[3];
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(512, 1) k_cvp(const CvpKernelArgs a) {
     group_sync<CS>();
     float delta = a.delta;
     if (has_robot && a.goal_dist_offset < (double)delta) delta = (float)fmax(a.goal_dist_offset, 1e-4);
-    run_band_rounds<CS>(prob, ctl, list0, list1, mark, st, delta, gthreads, gtid, has_robot, r0, r1, r2,
+    run_band_rounds_sub8<CS>(prob, ctl, list0, list1, mark, st, delta, gthreads, gtid, has_robot, r0, r1, r2,
                         a.goal_dist_offset, a.cancel_flag, nextafterf(seed_max, __uint_as_float(INF_BITS)), 2u * V + 64u);
     group_sync<CS>();
     if (a.out_dist) {
@@ -942,7 +946,9 @@ int32_t mnb_cvp_batch(mnb_ctx* ctx, uint32_t n, const uint32_t* seed_faces, cons
   for (uint32_t i = 0; i < n; ++i) if (seed_faces[i] >= ctx->F) return MNB_INVALID_START;
   CK(cudaSetDevice(ctx->device));
   const int cs = ctx->batch_cluster;
-  unsigned groups = (unsigned)(ctx->sm_count / cs);
+  int per_sm = 1;
+  if (cs == 1) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cvp<1>, ctx->threads, 0)); if (per_sm < 1) per_sm = 1; if (per_sm > 2) per_sm = 2; }
+  unsigned groups = (unsigned)(ctx->sm_count * per_sm / cs);
   if (groups > n) groups = n;
   if (groups == 0) groups = 1;
   int32_t rc;

@@ -41,6 +41,7 @@ struct CvpProblem {
   uint32_t* minor_arr;                  // overflow minors (only read when the label's flag bit is set)
   uint32_t* chg;                        // 1 + round of the last RE-label of a vertex (0 = never)
   mutable float deferred_m;             // smallest trigger time of a back-step deferred in this round
+  int strict;                           // set by the engine once it has detected stagnation (see backstep_ok)
 
   __device__ __forceinline__ Label load_label(uint32_t v) const {
     const uint4 s = __ldcg(&state[v]);
@@ -59,8 +60,10 @@ struct CvpProblem {
   // re-labelled during the previous round.  Without this a trigger and its own back-step child can feed
   // each other forever (a dependency cycle that has no counterpart in the sequential order); the deferred
   // update is reported as a pending change at the trigger's pop time so that nothing above it settles.
+  // The rule costs ~25% more rounds, so the engine only arms it (strict) after the band has made no
+  // progress for a number of rounds -- the signature of such a cycle; on causal-enough inputs it never arms.
   __device__ __forceinline__ bool backstep_ok(float X, const EvTime& T, uint32_t Tv, uint32_t round) const {
-    if (X > T.a1) return true;
+    if (!strict || X > T.a1) return true;
     if (__ldcg(&chg[Tv]) < round) return true;
     deferred_m = fminf(deferred_m, T.a1);
     return false;
@@ -349,6 +352,7 @@ struct InflationProblem {
   uint32_t* minor_arr;
   uint32_t* chg;
   mutable float deferred_m;
+  int strict;
   float max_distance;
 
   static constexpr int MAXF = 12;
@@ -367,7 +371,7 @@ struct InflationProblem {
     __stcg(&state[c], make_uint4(__float_as_uint(d), __float_as_uint(t.a1), __float_as_uint(t.a2), w));
   }
   __device__ __forceinline__ bool backstep_ok(float X, const EvTime& T, uint32_t Tv, uint32_t round) const {   // see CvpProblem
-    if (X > T.a1) return true;
+    if (!strict || X > T.a1) return true;
     if (__ldcg(&chg[Tv]) < round) return true;
     deferred_m = fminf(deferred_m, T.a1);
     return false;
@@ -459,6 +463,7 @@ struct DijkstraProblem {
   uint32_t* pred;
   double cost_limit;
   float deferred_m;                     // unused (edge weights >= 0: no back-steps), kept for the engine interface
+  int strict;
 
   __device__ __forceinline__ Label load_label(uint32_t v) const {
     const uint4 s = __ldcg(&state[v]);
