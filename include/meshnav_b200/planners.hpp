@@ -1,0 +1,261 @@
+// ROS-free C++ host mirror of the reference's plugin interface for the hot path, over the C ABI
+// (include/meshnav_b200.h).  Same names, argument meaning and outcome codes as
+//   mbf_mesh_core::MeshPlanner            mbf_mesh_core/include/mbf_mesh_core/mesh_planner.h:50-92
+//   dijkstra_mesh_planner::DijkstraMeshPlanner   dijkstra_mesh_planner/src/dijkstra_mesh_planner.cpp
+//   cvp_mesh_planner::CVPMeshPlanner             cvp_mesh_planner/src/cvp_mesh_planner.cpp
+//   mesh_layers::InflationLayer                  mesh_layers/src/inflation_layer.cpp
+// with plain structs standing in for geometry_msgs / lvr2 types (ROS 2 and lvr2 are not available in
+// this image; the pluginlib shims that wrap these classes are sketched in INTEGRATION.md).
+// All compute happens in libmeshnav_b200.so on the GPU.  Header-only; link with -lmeshnav_b200.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <list>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../meshnav_b200.h"
+
+namespace meshnav_b200 {
+
+struct Vector { float x = 0, y = 0, z = 0; };                       // mesh_map::Vector = lvr2::BaseVector<float>
+inline Vector operator-(const Vector& a, const Vector& b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline float length(const Vector& v) { return std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z); }
+inline Vector normalized(const Vector& v) { const float l = length(v); return l > 0 ? Vector{v.x / l, v.y / l, v.z / l} : v; }
+
+struct PoseStamped {                                                // geometry_msgs::msg::PoseStamped (position + heading)
+  Vector position;
+  Vector direction;                                                 // unit vector along the path (orientation's x axis)
+};
+
+// outcome codes: mbf_msgs::action::GetPath::Result (dijkstra_mesh_planner.h:72-85)
+enum : uint32_t { SUCCESS = 0, CANCELED = 51, INVALID_START = 52, INVALID_GOAL = 53, NO_PATH_FOUND = 54, INTERNAL_ERROR = 59 };
+
+// The slice of mesh_map::MeshMap the hot path touches (mesh_map/include/mesh_map/mesh_map.h:97-452).
+class MeshMap {
+ public:
+  MeshMap(const std::vector<float>& pos, const std::vector<uint32_t>& faces, int device = 0) : pos_(pos), faces_(faces) {
+    if (mnb_create(device, &ctx_) != MNB_OK) throw std::runtime_error("meshnav_b200: no usable sm_100 device (no CPU fallback)");
+    if (mnb_set_mesh(ctx_, (uint32_t)(pos.size() / 3), (uint32_t)(faces.size() / 3), pos.data(), faces.data(), nullptr, 0) != MNB_OK)
+      throw std::runtime_error(mnb_last_error(ctx_));
+    vertex_costs_.assign(numVertices(), 0.0f);
+    edge_distances_.resize(numEdges());
+    mnb_get_edge_distances(ctx_, edge_distances_.data());
+    edge_weights_ = edge_distances_;
+    invalid_.assign(numVertices(), 0);
+  }
+  ~MeshMap() { mnb_destroy(ctx_); }
+  MeshMap(const MeshMap&) = delete;
+  MeshMap& operator=(const MeshMap&) = delete;
+
+  uint32_t numVertices() const { return mnb_num_vertices(ctx_); }
+  uint32_t numFaces() const { return mnb_num_faces(ctx_); }
+  uint32_t numEdges() const { return mnb_num_edges(ctx_); }
+  mnb_ctx* ctx() const { return ctx_; }
+  Vector vertexPosition(uint32_t v) const { return {pos_[3 * v], pos_[3 * v + 1], pos_[3 * v + 2]}; }
+  const std::vector<uint32_t>& faces() const { return faces_; }
+  std::vector<float>& vertexCosts() { return vertex_costs_; }          // MeshMap::vertexCosts()
+  std::vector<float>& edgeWeights() { return edge_weights_; }          // MeshMap::edgeWeights()
+  const std::vector<float>& edgeDistances() const { return edge_distances_; }
+  std::vector<uint8_t>& invalid() { return invalid_; }                 // MeshMap::invalid (mesh_map.h:447)
+  double edge_cost_factor = 0.0;                                       // mesh_map.cpp:105
+
+  // MeshMap::computeEdgeWeights (mesh_map.cpp:517-561)
+  bool computeEdgeWeights() {
+    return mnb_compute_edge_weights(ctx_, vertex_costs_.data(), edge_cost_factor, edge_weights_.data()) == MNB_OK;
+  }
+  // pushes vertex_costs / edge_weights / invalid the way the planners read them (cvp:245,663-664)
+  bool syncCosts() { return mnb_set_costs(ctx_, vertex_costs_.data(), edge_weights_.data(), invalid_.data()) == MNB_OK; }
+
+  // MeshMap::getNearestVertexHandle (mesh_map.cpp:1161-1174): exhaustive 1-NN on the host (SURVEY f2 "next" row)
+  int64_t getNearestVertexHandle(const Vector& p) const {
+    int64_t best = -1; float bd = std::numeric_limits<float>::infinity();
+    for (uint32_t v = 0; v < numVertices(); ++v) { const float d = length(vertexPosition(v) - p); if (d < bd) { bd = d; best = v; } }
+    return best;
+  }
+  // MeshMap::getContainingFace (mesh_map.cpp:1110-1159), simplified: a face of the nearest vertex whose
+  // centroid is closest to the point; max_dist as in the reference call (cvp:673, 0.4 m)
+  int64_t getContainingFace(const Vector& p, float max_dist) const {
+    const int64_t v = getNearestVertexHandle(p);
+    if (v < 0 || length(vertexPosition((uint32_t)v) - p) > max_dist) return -1;
+    int64_t best = -1; float bd = std::numeric_limits<float>::infinity();
+    for (uint32_t f = 0; f < numFaces(); ++f) {
+      const uint32_t* t = &faces_[3 * (size_t)f];
+      if (t[0] != (uint32_t)v && t[1] != (uint32_t)v && t[2] != (uint32_t)v) continue;
+      const Vector a = vertexPosition(t[0]), b = vertexPosition(t[1]), c = vertexPosition(t[2]);
+      const Vector cen{(a.x + b.x + c.x) / 3, (a.y + b.y + c.y) / 3, (a.z + b.z + c.z) / 3};
+      const float d = length(cen - p);
+      if (d < bd) { bd = d; best = f; }
+    }
+    return best;
+  }
+
+ private:
+  mnb_ctx* ctx_ = nullptr;
+  std::vector<float> pos_; std::vector<uint32_t> faces_;
+  std::vector<float> vertex_costs_, edge_weights_, edge_distances_;
+  std::vector<uint8_t> invalid_;
+};
+
+// mbf_mesh_core::MeshPlanner (mesh_planner.h:50-92)
+class MeshPlanner {
+ public:
+  virtual ~MeshPlanner() = default;
+  virtual uint32_t makePlan(const PoseStamped& start, const PoseStamped& goal, double tolerance,
+                            std::vector<PoseStamped>& plan, double& cost, std::string& message) = 0;     // :71-73
+  virtual bool cancel() = 0;                                                                                // :80
+  virtual bool initialize(const std::string& name, const std::shared_ptr<MeshMap>& mesh_map_ptr) = 0;       // :88
+};
+
+class DijkstraMeshPlanner : public MeshPlanner {
+ public:
+  struct { double goal_dist_offset = 0.3; double cost_limit = 1.0; } config_;     // dijkstra_mesh_planner.h:178-187
+
+  bool initialize(const std::string& name, const std::shared_ptr<MeshMap>& mesh_map_ptr) override {
+    name_ = name; mesh_map_ = mesh_map_ptr; return true;
+  }
+  bool cancel() override { return mnb_cancel(mesh_map_->ctx()) == MNB_OK; }                   // dijkstra_mesh_planner.cpp:136-140
+
+  // dijkstra_mesh_planner.cpp:55-134: the wave is seeded at the GOAL, the robot (start) is the target
+  uint32_t makePlan(const PoseStamped& start, const PoseStamped& goal, double /*tolerance*/, std::vector<PoseStamped>& plan,
+                    double& cost, std::string& message) override {
+    std::list<uint32_t> path;
+    const uint32_t outcome = dijkstra(goal.position, start.position, path);     // :81
+    path.reverse();                                                              // :83
+    cost = 0;
+    if (!path.empty()) {                                                         // :90-116
+      Vector vec = start.position;
+      while (!path.empty()) {
+        const Vector next = mesh_map_->vertexPosition(path.front());
+        PoseStamped pose; pose.position = vec; pose.direction = normalized(next - vec);
+        cost += length(next - vec);
+        vec = next;
+        plan.push_back(pose);
+        path.pop_front();
+      }
+      PoseStamped pose; pose.position = vec; pose.direction = normalized(goal.position - vec);
+      cost += length(goal.position - vec);
+      plan.push_back(pose);
+    }
+    if (outcome == NO_PATH_FOUND) message = "Predecessor of the goal is not set! No path found!";
+    return outcome;
+  }
+
+  // dijkstra_mesh_planner.cpp:211-398 (original_start = wave seed, original_goal = robot)
+  uint32_t dijkstra(const Vector& original_start, const Vector& original_goal, std::list<uint32_t>& path) {
+    const int64_t start_vertex = mesh_map_->getNearestVertexHandle(original_start);   // :235
+    const int64_t goal_vertex = mesh_map_->getNearestVertexHandle(original_goal);     // :236
+    if (start_vertex < 0) return INVALID_START;
+    if (goal_vertex < 0) return INVALID_GOAL;
+    path.clear();
+    if (goal_vertex == start_vertex) return SUCCESS;                                   // :252-255
+    const uint32_t V = mesh_map_->numVertices();
+    potential_.assign(V, 0.0f); predecessors_.assign(V, 0);
+    if (!mesh_map_->syncCosts()) return INTERNAL_ERROR;
+    const int32_t rc = mnb_dijkstra(mesh_map_->ctx(), (uint32_t)start_vertex, goal_vertex, config_.cost_limit,
+                                    config_.goal_dist_offset, potential_.data(), predecessors_.data());
+    if (rc < 0) return INTERNAL_ERROR;
+    if (rc != SUCCESS) return (uint32_t)rc;
+    uint32_t vH = (uint32_t)goal_vertex;                                               // :367-373
+    while (vH != (uint32_t)start_vertex) { vH = predecessors_[vH]; path.push_front(vH); }
+    computeVectorMap();                                                                // :380
+    return SUCCESS;
+  }
+
+  // dijkstra_mesh_planner.cpp:189-209
+  void computeVectorMap() {
+    const uint32_t V = mesh_map_->numVertices();
+    vector_map_.assign(V, Vector{});
+    for (uint32_t v3 = 0; v3 < V; ++v3) {
+      const uint32_t v1 = predecessors_[v3];
+      if (v1 == v3) continue;
+      vector_map_[v3] = normalized(mesh_map_->vertexPosition(v1) - mesh_map_->vertexPosition(v3));
+    }
+  }
+  const std::vector<float>& potential() const { return potential_; }
+  const std::vector<uint32_t>& predecessors() const { return predecessors_; }
+  const std::vector<Vector>& getVectorMap() const { return vector_map_; }              // :171-174
+
+ private:
+  std::string name_; std::shared_ptr<MeshMap> mesh_map_;
+  std::vector<float> potential_; std::vector<uint32_t> predecessors_; std::vector<Vector> vector_map_;
+};
+
+class CVPMeshPlanner : public MeshPlanner {
+ public:
+  struct { double goal_dist_offset = 0.3; double cost_limit = 1.0; double step_width = 0.4; } config_;   // cvp_mesh_planner.h:201-212
+
+  bool initialize(const std::string& name, const std::shared_ptr<MeshMap>& mesh_map_ptr) override {
+    name_ = name; mesh_map_ = mesh_map_ptr; return true;
+  }
+  bool cancel() override { return mnb_cancel(mesh_map_->ctx()) == MNB_OK; }                               // cvp:142-146
+
+  // cvp_mesh_planner.cpp:62-140.  Round 1 builds the wavefront (potential / predecessors / direction / cutting
+  // faces); the vector-field back-tracking of :920-951 (MeshMap::meshAhead) is a SURVEY 8f "next" row, so the
+  // returned plan holds the two end poses only and `cost` is the potential at the robot's face.
+  uint32_t makePlan(const PoseStamped& start, const PoseStamped& goal, double /*tolerance*/, std::vector<PoseStamped>& plan,
+                    double& cost, std::string& message) override {
+    const uint32_t outcome = waveFrontPropagation(goal.position, start.position, message);               // :89
+    cost = 0;
+    if (outcome == SUCCESS) {
+      const int64_t rf = mesh_map_->getContainingFace(start.position, 0.4f);
+      float c = 0; for (int k = 0; k < 3; ++k) c += potential_[mesh_map_->faces()[3 * (size_t)rf + k]] / 3.0f;
+      cost = c;
+      plan.push_back(start); plan.push_back(goal);
+    }
+    return outcome;
+  }
+
+  // cvp_mesh_planner.cpp:241-247, 651-970 (propagation part)
+  uint32_t waveFrontPropagation(const Vector& start, const Vector& goal, std::string& message) {
+    const int64_t start_face = mesh_map_->getContainingFace(start, 0.4f);                                // :673
+    const int64_t goal_face = mesh_map_->getContainingFace(goal, 0.4f);                                  // :674
+    if (start_face < 0) { message = "Could not find a face close enough to the given start pose"; return INVALID_START; }   // :681-685
+    if (goal_face < 0) { message = "Could not find a face close enough to the given goal pose"; return INVALID_GOAL; }     // :686-690
+    const uint32_t V = mesh_map_->numVertices();
+    potential_.assign(V, 0.0f); predecessors_.assign(V, 0); direction_.assign(V, 0.0f); cutting_faces_.assign(V, -1);
+    if (!mesh_map_->syncCosts()) return INTERNAL_ERROR;
+    const float sp[3] = {start.x, start.y, start.z};
+    const int32_t rc = mnb_cvp(mesh_map_->ctx(), (uint32_t)start_face, sp, goal_face, config_.cost_limit, config_.goal_dist_offset,
+                               potential_.data(), predecessors_.data(), direction_.data(), cutting_faces_.data());
+    if (rc < 0) { message = mnb_last_error(mesh_map_->ctx()); return INTERNAL_ERROR; }
+    if (rc == NO_PATH_FOUND) message = "Predecessor of the goal is not set! No path found!";             // :915
+    return (uint32_t)rc;
+  }
+  const std::vector<float>& potential() const { return potential_; }
+  const std::vector<uint32_t>& predecessors() const { return predecessors_; }
+  const std::vector<float>& direction() const { return direction_; }
+  const std::vector<int32_t>& cuttingFaces() const { return cutting_faces_; }
+
+ private:
+  std::string name_; std::shared_ptr<MeshMap> mesh_map_;
+  std::vector<float> potential_, direction_; std::vector<uint32_t> predecessors_; std::vector<int32_t> cutting_faces_;
+};
+
+// mesh_layers::InflationLayer -- waveCostInflation + fading (inflation_layer.cpp:315-491)
+class InflationLayer {
+ public:
+  struct {                                                           // inflation_layer.h:240-248
+    double inscribed_radius = 0.25, inflation_radius = 0.4, lethal_value = 1.0, inscribed_value = 0.99,
+           cost_scaling_factor = 1.0;
+  } config_;
+  explicit InflationLayer(const std::shared_ptr<MeshMap>& map) : map_(map) {}
+
+  // returns false on error; riskiness (NaN = not in the sparse map) and distances (+inf = not in the map)
+  bool waveCostInflation(const std::vector<uint32_t>& lethals, std::vector<float>& cost_out, std::vector<float>& distances) {
+    const uint32_t V = map_->numVertices();
+    cost_out.assign(V, 0.0f); distances.assign(V, 0.0f);
+    const mnb_inflation_params p{config_.inscribed_radius, config_.inflation_radius, config_.lethal_value,
+                                 config_.inscribed_value, config_.cost_scaling_factor};
+    return mnb_inflate(map_->ctx(), lethals.data(), (uint32_t)lethals.size(), map_->invalid().data(), &p, distances.data(),
+                       cost_out.data()) == MNB_OK;
+  }
+
+ private:
+  std::shared_ptr<MeshMap> map_;
+};
+
+}  // namespace meshnav_b200

@@ -77,6 +77,7 @@ struct GroupCtl {               // one per wavefront group, global memory
   unsigned int query;           // batch: query index owned by the group
   unsigned long long rounds, recomputes, settled;
   unsigned int strict_armed;    // wavefronts that had to arm the strict back-step rule
+  unsigned int watchdog;        // a wavefront hit the round watchdog (reported as non-convergence)
 };
 
 template <int CS>
@@ -232,6 +233,7 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
   if (gtid == 0) {
     ctl->rounds += r;
     if (prob.strict) ctl->strict_armed += 1;
+    if (r > max_rounds) ctl->watchdog = 1;
     ctl->goal_bits = min(ctl->goal_ring[0], ctl->goal_ring[1]);
   }
 }
@@ -343,6 +345,7 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
   if (gtid == 0) {
     ctl->rounds += r;
     if (prob.strict) ctl->strict_armed += 1;
+    if (r > max_rounds) ctl->watchdog = 1;
     ctl->goal_bits = min(ctl->goal_ring[0], ctl->goal_ring[1]);
   }
 }

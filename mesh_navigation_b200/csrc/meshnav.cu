@@ -67,6 +67,10 @@ __global__ void k_gather_adj_w(const uint32_t* __restrict__ nbr, const uint32_t*
 // ============================================================================
 // wavefront kernels
 // ============================================================================
+// round watchdog (group-uniform): far above the dependency depth of any sane mesh (a grid needs ~ D/h rounds),
+// small enough that a livelock is reported in seconds instead of hanging the device
+static inline uint32_t watchdog_rounds(uint32_t V) { return 200000u + 256u * (uint32_t)sqrt((double)V); }
+
 struct WaveWorkspace {     // per group (index g): state + g*V etc.
   uint4* state;
   uint32_t* minor;
@@ -97,6 +101,7 @@ struct CvpKernelArgs {
   int32_t* out_cut;
   unsigned int* next_query;
   const int* cancel_flag;
+  uint32_t max_rounds;
 };
 
 template <int CS>
@@ -194,7 +199,7 @@ __global__ void __launch_bounds__(512, MNB_CVP_MINBLOCKS) k_cvp(const CvpKernelA
     float delta = a.delta;
     if (has_robot && a.goal_dist_offset < (double)delta) delta = (float)fmax(a.goal_dist_offset, 1e-4);
     run_band_rounds_sub8<CS>(prob, ctl, list0, list1, mark, st, delta, gthreads, gtid, has_robot, r0, r1, r2,
-                        a.goal_dist_offset, a.cancel_flag, nextafterf(seed_max, __uint_as_float(INF_BITS)), 2u * V + 64u);
+                        a.goal_dist_offset, a.cancel_flag, nextafterf(seed_max, __uint_as_float(INF_BITS)), a.max_rounds);
     group_sync<CS>();
     if (a.out_dist) {
       float* od = a.out_dist + (size_t)q * V;
@@ -263,7 +268,7 @@ __global__ void __launch_bounds__(512, 1) k_cvp_grid(const CvpKernelArgs a) {
   float delta = a.delta;
   if (has_robot && a.goal_dist_offset < (double)delta) delta = (float)fmax(a.goal_dist_offset, 1e-4);
   run_band_rounds_sub8<0>(prob, ctl, list0, list1, mark, st, delta, gthreads, gtid, has_robot, r0, r1, r2,
-                          a.goal_dist_offset, a.cancel_flag, nextafterf(seed_max, __uint_as_float(INF_BITS)), 2u * V + 64u);
+                          a.goal_dist_offset, a.cancel_flag, nextafterf(seed_max, __uint_as_float(INF_BITS)), a.max_rounds);
   group_sync<0>();
   if (a.out_dist)
     for (uint32_t v = gtid; v < V; v += gthreads) a.out_dist[v] = __uint_as_float(state[v].x);
@@ -307,6 +312,7 @@ struct DijkstraKernelArgs {
   float delta;
   float* out_dist; uint32_t* out_pred;
   const int* cancel_flag;
+  uint32_t max_rounds;
 };
 
 template <int CS>
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(512, 1) k_dijkstra(const DijkstraKernelArgs a)
   float delta = a.delta;
   if (has_robot && a.goal_dist_offset < (double)delta) delta = (float)fmax(a.goal_dist_offset, 1e-4);
   run_band_rounds<CS>(prob, ctl, list0, list1, mark, st, delta, gthreads, gtid, has_robot, rv, rv, rv,
-                      a.goal_dist_offset, a.cancel_flag, 1e-30f, 2u * V + 64u);
+                      a.goal_dist_offset, a.cancel_flag, 1e-30f, a.max_rounds);
   group_sync<CS>();
   for (uint32_t v = gtid; v < V; v += gthreads) a.out_dist[v] = __uint_as_float(state[v].x);
 }
@@ -494,6 +500,7 @@ struct InflateKernelArgs {
   float max_distance;
   InflationParams params;
   float* out_dist; float* out_cost;
+  uint32_t max_rounds;
 };
 
 __global__ void __launch_bounds__(512, 1) k_inflate(const InflateKernelArgs a) {
@@ -527,7 +534,7 @@ __global__ void __launch_bounds__(512, 1) k_inflate(const InflateKernelArgs a) {
   stage_flush(st, list0, &ctl->count[0], &ctl->m_tau[0], &ctl->lo[0]);
   group_sync<0>();
   run_band_rounds<0>(prob, ctl, list0, list1, mark, st, __uint_as_float(INF_BITS), gthreads, gtid, 0, 0u, 0u, 0u, 0.0,
-                     nullptr, 1e-30f, 2u * V + 64u);
+                     nullptr, 1e-30f, a.max_rounds);
   group_sync<0>();
   for (uint32_t v = gtid; v < V; v += gthreads) {
     const float d = __uint_as_float(state[v].x);
@@ -843,6 +850,8 @@ static int32_t finish_stats(mnb_ctx* ctx, unsigned groups, unsigned launches) {
   for (auto& c : h) { ctx->stats.rounds += c.rounds; ctx->stats.recomputes += c.recomputes; ctx->stats.settled += c.settled; }
   ctx->stats.kernel_launches = launches;
   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->stats.kernel_ms = ms;
+  for (auto& c : h)
+    if (c.watchdog) { ctx->err = "wavefront did not converge within the round watchdog"; return MNB_E_STATE; }
   return MNB_OK;
 }
 
@@ -867,7 +876,7 @@ static void fill_cvp_args(mnb_ctx* ctx, CvpKernelArgs& a) {
   a.V = ctx->V; a.pos = ctx->d_pos; a.faces = ctx->d_faces; a.cor_ptr = ctx->d_cor_ptr; a.cor_idx = ctx->d_cor_idx;
   a.cor_w = ctx->d_cor_w; a.ell_idx = ctx->d_ell_idx; a.ell_w = ctx->d_ell_w; a.cost = ctx->d_cost; a.invalid = ctx->has_invalid ? ctx->d_invalid : nullptr; a.ws = ctx->ws;
   a.seed_faces = ctx->d_seed_faces; a.seed_pos = ctx->d_seed_pos; a.delta = ctx->delta; a.next_query = ctx->d_next_query;
-  a.cancel_flag = ctx->d_cancel;
+  a.cancel_flag = ctx->d_cancel; a.max_rounds = watchdog_rounds(ctx->V);
 }
 
 extern "C" {
@@ -994,7 +1003,7 @@ int32_t mnb_dijkstra(mnb_ctx* ctx, uint32_t seed_vertex, int64_t robot_vertex, d
   a.robot_vertex = robot_vertex; a.cost_limit = cost_limit; a.goal_dist_offset = goal_dist_offset; a.delta = ctx->delta;
   a.out_dist = (dev && out_dist) ? out_dist : ctx->d_out_dist;
   a.out_pred = (dev && out_pred) ? out_pred : ctx->d_out_pred;
-  a.cancel_flag = ctx->d_cancel;
+  a.cancel_flag = ctx->d_cancel; a.max_rounds = watchdog_rounds(ctx->V);
   if (robot_vertex >= 0 && (uint32_t)robot_vertex == seed_vertex) return MNB_SUCCESS;   // dijkstra:252-255
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   cudaError_t e;
@@ -1100,6 +1109,7 @@ int32_t mnb_inflate(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, const uin
   a.params.cost_scaling_factor = params->cost_scaling_factor;
   a.out_dist = (dev && out_dist) ? out_dist : ctx->d_out_dist;
   a.out_cost = (dev && out_cost) ? out_cost : ctx->d_out_cost;
+  a.max_rounds = watchdog_rounds(ctx->V);
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   void* kargs[] = {(void*)&a};
   CK(cudaLaunchCooperativeKernel((const void*)k_inflate, dim3(ctx->sm_count), dim3(ctx->threads), kargs, 0, ctx->stream));

@@ -1,0 +1,102 @@
+// GPU test of the C++ host mirror (include/meshnav_b200/planners.hpp) against the oracle.
+// Mirrors how the reference's gtest (mesh_layers/test/inflation_layer_test.cpp) drives the classes directly,
+// without a ROS graph.  Built and run by tests/test_gpu_cpp_host.py (g++, links libmeshnav_b200.so + liboracle.so).
+#include <cassert>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+
+#include "../../include/meshnav_b200/planners.hpp"
+
+extern "C" {   // oracle (test infrastructure)
+void* orc_mesh_create(uint32_t V, uint32_t F, const float* pos, const uint32_t* faces, const uint32_t* edges, uint32_t E);
+void orc_mesh_destroy(void* h);
+void orc_edge_distances(void* h, float* out);
+uint32_t orc_dijkstra(void* h, const float* edge_weights, const float* vertex_costs, const uint8_t* invalid, uint32_t seed_vertex,
+                      int64_t robot_vertex, double cost_limit, double goal_dist_offset, int canonical_ties, float* distances,
+                      uint32_t* predecessors, double* stats);
+uint32_t orc_cvp(void* h, const float* edge_weights, const float* vertex_costs, const uint8_t* invalid, uint32_t seed_face,
+                 const float* seed_pos, int64_t robot_face, double cost_limit, double goal_dist_offset, int canonical_ties,
+                 float* distances, uint32_t* predecessors, float* direction, int32_t* cutting_faces, double* stats);
+}
+
+using namespace meshnav_b200;
+#define CHECK(c) do { if (!(c)) { std::fprintf(stderr, "CHECK failed %s:%d: %s\n", __FILE__, __LINE__, #c); std::exit(1); } } while (0)
+
+static uint64_t splitmix(uint64_t x) { x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; return x ^ (x >> 31); }
+
+int main() {
+  const int n = 80; const float h = 0.1f;
+  std::vector<float> pos(3 * n * n); std::vector<uint32_t> faces;
+  for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+    const uint64_t r = splitmix((uint64_t)(j * n + i) ^ 42ull);
+    pos[3 * (j * n + i)] = i * h + ((float)((r >> 11) & 0xffff) / 65535.0f - 0.5f) * 0.04f;
+    pos[3 * (j * n + i) + 1] = j * h + ((float)((r >> 31) & 0xffff) / 65535.0f - 0.5f) * 0.04f;
+    pos[3 * (j * n + i) + 2] = 0.3f * std::sin(0.7f * i * h) * std::cos(0.5f * j * h);
+  }
+  for (int j = 0; j + 1 < n; ++j) for (int i = 0; i + 1 < n; ++i) {
+    const uint32_t v00 = j * n + i, v10 = v00 + 1, v01 = v00 + n, v11 = v01 + 1;
+    faces.insert(faces.end(), {v00, v10, v11, v00, v11, v01});
+  }
+  auto map = std::make_shared<MeshMap>(pos, faces);
+  void* om = orc_mesh_create(n * n, (uint32_t)faces.size() / 3, pos.data(), faces.data(), nullptr, 0);
+  const uint32_t V = map->numVertices(), E = map->numEdges();
+  std::vector<float> ed(E); orc_edge_distances(om, ed.data());
+  CHECK(std::memcmp(ed.data(), map->edgeDistances().data(), sizeof(float) * E) == 0);
+
+  PoseStamped robot, goal;
+  robot.position = map->vertexPosition(15 * n + 12); goal.position = map->vertexPosition(60 * n + 65);
+
+  // ---- DijkstraMeshPlanner::makePlan ----
+  DijkstraMeshPlanner dj; CHECK(dj.initialize("dijkstra", map));
+  std::vector<PoseStamped> plan; double cost = 0; std::string msg;
+  CHECK(dj.makePlan(robot, goal, 0.1, plan, cost, msg) == SUCCESS);
+  CHECK(plan.size() > 10 && cost > 6.0 && cost < 12.0);
+  std::vector<float> od(V); std::vector<uint32_t> op(V);
+  const uint32_t seed_v = (uint32_t)map->getNearestVertexHandle(goal.position), robot_v = (uint32_t)map->getNearestVertexHandle(robot.position);
+  CHECK(orc_dijkstra(om, ed.data(), map->vertexCosts().data(), nullptr, seed_v, robot_v, 1.0, 0.3, 1, od.data(), op.data(), nullptr) == 0);
+  CHECK(std::memcmp(od.data(), dj.potential().data(), sizeof(float) * V) == 0);          // bit-identical distances
+  CHECK(std::memcmp(op.data(), dj.predecessors().data(), sizeof(uint32_t) * V) == 0);    // bit-exact predecessors
+  CHECK(std::fabs(cost - (double)od[robot_v]) < 0.05 * cost + 0.3);                      // path length ~ potential at the robot
+  // robot == goal vertex -> SUCCESS with an empty vertex path (dijkstra_mesh_planner.cpp:252-255)
+  plan.clear(); CHECK(dj.makePlan(goal, goal, 0.1, plan, cost, msg) == SUCCESS);
+  // lethal wall -> NO_PATH_FOUND (:358-362)
+  for (uint32_t v = 0; v < V; ++v) if (pos[3 * v] > 3.0f && pos[3 * v] < 3.3f) map->vertexCosts()[v] = 2.0f;
+  plan.clear(); CHECK(dj.makePlan(robot, goal, 0.1, plan, cost, msg) == NO_PATH_FOUND && !msg.empty());
+
+  // ---- CVPMeshPlanner::makePlan / waveFrontPropagation ----
+  CVPMeshPlanner cvp; CHECK(cvp.initialize("cvp", map));
+  plan.clear(); msg.clear();
+  CHECK(cvp.makePlan(robot, goal, 0.1, plan, cost, msg) == NO_PATH_FOUND);
+  std::fill(map->vertexCosts().begin(), map->vertexCosts().end(), 0.0f);
+  plan.clear();
+  CHECK(cvp.makePlan(robot, goal, 0.1, plan, cost, msg) == SUCCESS && cost > 6.0);
+  std::vector<float> cd(V), cdir(V); std::vector<uint32_t> cp(V); std::vector<int32_t> cc(V);
+  const int64_t sf = map->getContainingFace(goal.position, 0.4f), rf = map->getContainingFace(robot.position, 0.4f);
+  const float sp[3] = {goal.position.x, goal.position.y, goal.position.z};
+  CHECK(orc_cvp(om, ed.data(), map->vertexCosts().data(), nullptr, (uint32_t)sf, sp, rf, 1.0, 0.3, 1, cd.data(), cp.data(), cdir.data(), cc.data(), nullptr) == 0);
+  double maxrel = 0;
+  for (uint32_t v = 0; v < V; ++v) {
+    CHECK(std::isfinite(cd[v]) == std::isfinite(cvp.potential()[v]));
+    if (std::isfinite(cd[v])) maxrel = std::fmax(maxrel, std::fabs((double)cd[v] - cvp.potential()[v]) / std::fmax((double)cd[v], 1e-30));
+  }
+  CHECK(maxrel <= 1e-4);                                                                  // north-star tolerance
+  // INVALID_GOAL: robot far off the mesh (cvp_mesh_planner.cpp:686-690)
+  PoseStamped off; off.position = {100.f, 100.f, 0.f};
+  plan.clear(); CHECK(cvp.makePlan(off, goal, 0.1, plan, cost, msg) == INVALID_GOAL);
+  plan.clear(); CHECK(cvp.makePlan(robot, off, 0.1, plan, cost, msg) == INVALID_START);
+
+  // ---- InflationLayer ----
+  InflationLayer infl(map);
+  std::vector<uint32_t> lethals; for (uint32_t v = 0; v < V; ++v) if (std::hypot(pos[3 * v] - 4.0f, pos[3 * v + 1] - 4.0f) < 0.35f) lethals.push_back(v);
+  std::vector<float> risk, dist;
+  CHECK(infl.waveCostInflation(lethals, risk, dist));
+  size_t inflated = 0; for (uint32_t v = 0; v < V; ++v) if (std::isfinite(dist[v]) && dist[v] > 0 && dist[v] <= 0.4f) { inflated++; CHECK(risk[v] > 0 && risk[v] <= 0.99f); }
+  CHECK(inflated > 20);
+  for (uint32_t v : lethals) CHECK(dist[v] == 0.0f && risk[v] == 1.0f);
+  orc_mesh_destroy(om);
+  std::printf("cpp host mirror ok: dijkstra bit-exact, cvp max rel %.2e, %zu inflated vertices\n", maxrel, inflated);
+  return 0;
+}
