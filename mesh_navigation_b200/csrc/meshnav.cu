@@ -211,7 +211,10 @@ __global__ void __launch_bounds__(512, MNB_CVP_MINBLOCKS) k_cvp(const CvpKernelA
 
 // Single plan on the whole GPU: cooperative launch, one CTA per SM (x occupancy), 8 lanes per
 // candidate, grid-wide barrier per round.  Used when latency of ONE wavefront matters.
-__global__ void __launch_bounds__(512, 1) k_cvp_grid(const CvpKernelArgs a) {
+#ifndef MNB_GRID_MINBLOCKS
+#define MNB_GRID_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(512, MNB_GRID_MINBLOCKS) k_cvp_grid(const CvpKernelArgs a) {
   __shared__ Stage st;
   uint32_t g, gthreads, gtid;
   group_coords<0>(g, gthreads, gtid);
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(512, 1) k_cvp_grid(const CvpKernelArgs a) {
   if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; }
   __syncthreads();
   for (uint32_t v = gtid; v < V; v += gthreads) { state[v] = state_inf(); mark[v] = MARK_NONE; a.ws.chg[v] = 0u; }
-  group_sync<0>();
+  group_sync<0>(ctl->barrier);
   const uint32_t sf = a.seed_faces[0];
   const uint32_t s0 = a.faces[3 * (size_t)sf], s1 = a.faces[3 * (size_t)sf + 1], s2 = a.faces[3 * (size_t)sf + 2];
   CvpEllProblem prob;
@@ -264,12 +267,12 @@ __global__ void __launch_bounds__(512, 1) k_cvp_grid(const CvpKernelArgs a) {
       if (left == 0) ctl->goal_ring[0] = __float_as_uint((float)((double)seed_max + a.goal_dist_offset));
     }
   }
-  group_sync<0>();
+  group_sync<0>(ctl->barrier);
   float delta = a.delta;
   if (has_robot && a.goal_dist_offset < (double)delta) delta = (float)fmax(a.goal_dist_offset, 1e-4);
   run_band_rounds_sub8<0>(prob, ctl, list0, list1, mark, st, delta, gthreads, gtid, has_robot, r0, r1, r2,
                           a.goal_dist_offset, a.cancel_flag, nextafterf(seed_max, __uint_as_float(INF_BITS)), a.max_rounds);
-  group_sync<0>();
+  group_sync<0>(ctl->barrier);
   if (a.out_dist)
     for (uint32_t v = gtid; v < V; v += gthreads) a.out_dist[v] = __uint_as_float(state[v].x);
 }
@@ -513,13 +516,13 @@ __global__ void __launch_bounds__(512, 1) k_inflate(const InflateKernelArgs a) {
   if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; }
   __syncthreads();
   for (uint32_t v = gtid; v < V; v += gthreads) { state[v] = state_inf(); mark[v] = MARK_NONE; a.ws.chg[v] = 0u; }
-  group_sync<0>();
+  group_sync<0>(ctl->barrier);
   for (uint32_t i = gtid; i < a.n_lethals; i += gthreads) {      // :397-402
     const uint32_t v = a.lethals[i];
     if (v < V) { state[v] = make_uint4(0u, 0u, 0u, 0u); mark[v] = MARK_FIXED; }
   }
   if (gtid == 0) ctl_reset(ctl, 0, 0.0f);
-  group_sync<0>();
+  group_sync<0>(ctl->barrier);
   InflationProblem prob;
   prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_wd = a.cor_wd; prob.invalid = a.invalid;
   prob.state = state; prob.minor_arr = a.ws.minor; prob.chg = a.ws.chg; prob.deferred_m = __uint_as_float(INF_BITS); prob.max_distance = a.max_distance;
@@ -532,10 +535,10 @@ __global__ void __launch_bounds__(512, 1) k_inflate(const InflateKernelArgs a) {
     });
   }
   stage_flush(st, list0, &ctl->count[0], &ctl->m_tau[0], &ctl->lo[0]);
-  group_sync<0>();
+  group_sync<0>(ctl->barrier);
   run_band_rounds<0>(prob, ctl, list0, list1, mark, st, __uint_as_float(INF_BITS), gthreads, gtid, 0, 0u, 0u, 0u, 0.0,
                      nullptr, 1e-30f, a.max_rounds);
-  group_sync<0>();
+  group_sync<0>(ctl->barrier);
   for (uint32_t v = gtid; v < V; v += gthreads) {
     const float d = __uint_as_float(state[v].x);
     if (a.out_dist) a.out_dist[v] = d;
@@ -850,6 +853,7 @@ static int32_t finish_stats(mnb_ctx* ctx, unsigned groups, unsigned launches) {
   for (auto& c : h) { ctx->stats.rounds += c.rounds; ctx->stats.recomputes += c.recomputes; ctx->stats.settled += c.settled; }
   ctx->stats.kernel_launches = launches;
   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->stats.kernel_ms = ms;
+  if (getenv("MNB_PHASE_TIMING")) for (auto& c : h) fprintf(stderr, "[mnb] rounds %llu: CTA0 cycles work %llu flush %llu sync %llu (per round %.0f / %.0f / %.0f) iter phases: load %llu replay %llu post %llu n %llu | src-labels %llu upto-eval %llu rank %llu merge %llu\n", c.rounds, c.t_work, c.t_flush, c.t_sync, (double)c.t_work / (double)(c.rounds ? c.rounds : 1), (double)c.t_flush / (double)(c.rounds ? c.rounds : 1), (double)c.t_sync / (double)(c.rounds ? c.rounds : 1), c.t_ph[0], c.t_ph[1], c.t_ph[2], c.t_ph[3], c.t_ph[4], c.t_ph[5], c.t_ph[6], c.t_ph[7]);
   for (auto& c : h)
     if (c.watchdog) { ctx->err = "wavefront did not converge within the round watchdog"; return MNB_E_STATE; }
   return MNB_OK;
@@ -912,7 +916,7 @@ int32_t mnb_cvp(mnb_ctx* ctx, uint32_t seed_face, const float seed_pos[3], int64
     if (ctx->grid_blocks_per_sm == 0) {
       int nb = 0;
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_cvp_grid, ctx->threads, 0));
-      ctx->grid_blocks_per_sm = nb > 0 ? 1 : 0;
+      ctx->grid_blocks_per_sm = nb > MNB_GRID_MINBLOCKS ? MNB_GRID_MINBLOCKS : nb;
       if (nb <= 0) { ctx->err = "k_cvp_grid cannot be resident"; return MNB_E_CUDA; }
     }
     void* kargs[] = {(void*)&a};

@@ -265,68 +265,136 @@ struct CvpEllProblem : CvpProblem {
     replay(c, band_end, goal, round, nd, nt, win, a1, a2);
   }
 
-  // all 8 lanes of the group call this with the same c; every lane returns the same label
-  __device__ __forceinline__ void replay_sub8(uint32_t c, uint32_t j, unsigned gmask, float band_end, float goal, uint32_t round,
-                                              float& nd, EvTime& nt, int4& ix_out, int& deg_out) const {
-    const int lane0 = (threadIdx.x & 31) & ~7;
-    const int4 ix = __ldg(&ell_idx[(size_t)c * ELL_W + j]);
-    ix_out = ix;
-    const int deg = __shfl_sync(gmask, ix.w, lane0);
-    deg_out = deg;
-    if (deg > (int)ELL_W) {   // rare: CSR path on the group's first lane, result broadcast
-      float d0 = 0; EvTime t0 = ev_normal(0.0f, c);
-      if (j == 0) replay_serial(c, band_end, goal, round, d0, t0);
-      nd = __shfl_sync(gmask, d0, lane0);
-      nt.a1 = __shfl_sync(gmask, t0.a1, lane0); nt.a2 = __shfl_sync(gmask, t0.a2, lane0);
-      nt.a3 = __shfl_sync(gmask, t0.a3, lane0); nt.minor = __shfl_sync(gmask, t0.minor, lane0);
-      return;
-    }
+  __device__ __forceinline__ int4 load_row_idx(uint32_t c, uint32_t j) const { return __ldg(&ell_idx[(size_t)c * ELL_W + j]); }
+  __device__ __forceinline__ float4 load_row_w(uint32_t c, uint32_t j) const { return __ldg(&ell_w[(size_t)c * ELL_W + j]); }
+
+  // static part of the unfolding (depends on the face's weights only): apex of the triangle and the cosine at v3.
+  // Evaluated while the source labels are still in flight.
+  struct FaceGeo { double p, hc, t0a; };
+  __device__ __forceinline__ static FaceGeo face_geo(double a, double b, double c) {
+    const double c_sq = c * c, b_sq = b * b, a_sq = a * a;
+    FaceGeo g;
+    g.p = (b_sq + c_sq - a_sq) / (2 * c);
+    g.hc = sqrt(fmax(b_sq - g.p * g.p, 0.0));
+    g.t0a = (a_sq + b_sq - c_sq) / (2 * a * b);
+    return g;
+  }
+  // dynamic part: same arithmetic, same order of operations as eval_face / the reference
+  __device__ __forceinline__ static void eval_face_geo(double u1, double u2, double a, double b, double c, const FaceGeo& g,
+                                                       double& U, double& X) {
+    const double c_sq = c * c, b_sq = b * b, a_sq = a * a;
+    const double u1_sq = u1 * u1, u2_sq = u2 * u2;
+    const double sx = (c_sq + u1_sq - u2_sq) / (2 * c);
+    const double sy = -sqrt(fmax(u1_sq - sx * sx, 0.0));
+    const double dy = g.hc - sy;
+    const double dx = g.p - sx;
+    const double u3tmp_sq = dx * dx + dy * dy;
+    const double u3tmp = sqrt(u3tmp_sq);
+    U = u3tmp;
+    const double t1a = (u3tmp_sq + b_sq - u1_sq) / (2 * u3tmp * b);
+    const double t2a = (a_sq + u3tmp_sq - u2_sq) / (2 * a * u3tmp);
+    int fb;
+    if (fabs(t1a) > 1) fb = 1;
+    else if (fabs(t2a) > 1) fb = 2;
+    else if (fabs(g.t0a) <= 1 && t1a > g.t0a && t2a > g.t0a) { X = u3tmp; return; }   // |t0a| > 1: acos(t0a) is NaN in the reference
+    else fb = (t1a > t2a) ? 1 : 2;
+    X = (fb == 1) ? (u1 + b) : (u2 + a);
+  }
+
+  // Every lane of the WARP calls this (groups without work pass has = false): all shuffles use the
+  // compile-time full mask with width 8.  Lanes of a group return the same label.  mk1/mk2 return the
+  // activation marks of the lane's two source vertices (fetched together with their labels).
+  __device__ __forceinline__ void replay_sub8(uint32_t c, uint32_t j, bool has, const int4& ix, const float4& w, float band_end,
+                                              float goal, uint32_t round, const uint32_t* mark, float& nd, EvTime& nt, int& deg_out,
+                                              uint32_t& mk1, uint32_t& mk2) const {
+    constexpr unsigned FULL = 0xffffffffu;
     const float INF = __uint_as_float(INF_BITS);
-    bool valid = ix.x != ELL_EMPTY;
-    EvTime T = ev_normal(INF, 0xffffffffu >> 1);
+    const int deg = __shfl_sync(FULL, ix.w, 0, 8);
+    deg_out = deg;
+    const bool big = has && deg > (int)ELL_W;
+    bool valid = has && !big && ix.x != ELL_EMPTY;
+    EvTime T = ev_normal(INF, 0x7fffffffu);
+    uint32_t Tv = 0x7fffffffu;
     double U = 0.0, X = 0.0;
+    const unsigned sh = (threadIdx.x & 31) & ~7;
     if (valid) {
-      const float4 w = __ldg(&ell_w[(size_t)c * ELL_W + j]);
       const uint32_t v1 = (uint32_t)ix.x, v2 = (uint32_t)ix.y;
-      const Label a = load_label(v1), b = load_label(v2);
-      uint32_t Tv = 0;
+      // issue the four loads, then do the label-independent half of the unfolding while they are in flight
+      const uint4 sa = __ldcg(&state[v1]), sb = __ldcg(&state[v2]);
+      mk1 = __ldcg(&mark[v1]); mk2 = __ldcg(&mark[v2]);
+      const FaceGeo g = face_geo((double)w.z, (double)w.y, (double)w.x);
+      Label a, b;
+      a.d = __uint_as_float(sa.x); a.t.a1 = __uint_as_float(sa.y); a.t.a2 = __uint_as_float(sa.z); a.t.a3 = __uint_as_float(sa.w & 0x7fffffffu);
+      a.t.minor = (sa.w >> 31) ? __ldcg(&minor_arr[v1]) : 2u * v1;
+      b.d = __uint_as_float(sb.x); b.t.a1 = __uint_as_float(sb.y); b.t.a2 = __uint_as_float(sb.z); b.t.a3 = __uint_as_float(sb.w & 0x7fffffffu);
+      b.t.minor = (sb.w >> 31) ? __ldcg(&minor_arr[v2]) : 2u * v2;
       valid = face_time(v1, v2, a, b, band_end, goal, T, Tv);
       if (valid) {
-        eval_face((double)a.d, (double)b.d, (double)w.z, (double)w.y, (double)w.x, U, X);
+        eval_face_geo((double)a.d, (double)b.d, (double)w.z, (double)w.y, (double)w.x, g, U, X);
         // back-step from a trigger that was re-labelled last round: defer (see backstep_ok)
-        if (!backstep_ok((float)X, T, Tv, round)) X = (double)__uint_as_float(INF_BITS);
+        if (!backstep_ok((float)X, T, Tv, round)) X = (double)INF;
       }
     }
-    // rank of every valid lane in (T, slot) order: all-pairs comparison inside the 8-lane group
-    const unsigned long long hi = ((unsigned long long)__float_as_uint(T.a1) << 32) | __float_as_uint(T.a2);
+    // Common case: every firing face of the warp has a plain pop time (a2 == a3 == 0, default minor = 2*Tv):
+    // the event order is the 64-bit key (a1, Tv).  Cascade members (rare) take the general 128-bit path.
+    const bool plain = !valid || (T.a2 == 0.0f && T.a3 == 0.0f && T.minor == 2u * Tv);
+    const bool all_plain = __all_sync(FULL, plain);
+    const unsigned long long hi = all_plain ? (((unsigned long long)__float_as_uint(T.a1) << 32) | Tv)
+                                            : (((unsigned long long)__float_as_uint(T.a1) << 32) | __float_as_uint(T.a2));
     const unsigned long long lo = ((unsigned long long)__float_as_uint(T.a3) << 32) | T.minor;
     int rank = 0;
+    if (all_plain) {
 #pragma unroll
-    for (int d = 1; d < 8; ++d) {
-      const int src = lane0 + (int)((j + d) & 7);
-      const unsigned long long ohi = __shfl_sync(gmask, hi, src);
-      const unsigned long long olo = __shfl_sync(gmask, lo, src);
-      const int ovalid = __shfl_sync(gmask, (int)valid, src);
-      const uint32_t oj = (j + d) & 7;
-      if (ovalid && (ohi < hi || (ohi == hi && (olo < lo || (olo == lo && oj < j))))) ++rank;
+      for (int d = 1; d < 8; ++d) {
+        const int src = (int)((j + d) & 7);
+        const unsigned long long ohi = __shfl_sync(FULL, hi, src, 8);
+        const int ovalid = __shfl_sync(FULL, (int)valid, src, 8);
+        if (ovalid && (ohi < hi || (ohi == hi && (uint32_t)src < j))) ++rank;
+      }
+    } else {
+#pragma unroll
+      for (int d = 1; d < 8; ++d) {
+        const int src = (int)((j + d) & 7);
+        const unsigned long long ohi = __shfl_sync(FULL, hi, src, 8);
+        const unsigned long long olo = __shfl_sync(FULL, lo, src, 8);
+        const int ovalid = __shfl_sync(FULL, (int)valid, src, 8);
+        if (ovalid && (ohi < hi || (ohi == hi && (olo < lo || (olo == lo && (uint32_t)src < j))))) ++rank;
+      }
     }
     if (!valid) rank = 99;
-    const unsigned vmask = __ballot_sync(gmask, valid) & gmask;
-    const int nvalid = __popc(vmask);
+    const unsigned vmask = (__ballot_sync(FULL, valid) >> sh) & 0xFFu;
+    // the replay loop runs to the largest face count among the 4 groups of the warp (idle iterations are masked)
+    int nmax = __popc(vmask);
+    nmax = max(nmax, __shfl_xor_sync(FULL, nmax, 8));
+    nmax = max(nmax, __shfl_xor_sync(FULL, nmax, 16));
     float cur = INF;
     EvTime tc = ev_normal(INF, c);
-    for (int r = 0; r < nvalid; ++r) {
-      const unsigned who = __ballot_sync(gmask, rank == r) & gmask;
-      const int src = __ffs(who) - 1;
+    bool open = true;                                   // c has not been popped yet
+    for (int r = 0; r < nmax; ++r) {
+      const unsigned who = (__ballot_sync(FULL, rank == r) >> sh) & 0xFFu;
+      const int src = who ? (__ffs(who) - 1) : 0;
+      const unsigned long long whi = __shfl_sync(FULL, hi, src, 8);
+      unsigned long long wlo = 0;
+      if (!all_plain) wlo = __shfl_sync(FULL, lo, src, 8);
+      const double Uw = __shfl_sync(FULL, U, src, 8);
+      const double Xw = __shfl_sync(FULL, X, src, 8);
+      if (!who || !open) continue;
       EvTime Tw;
-      const unsigned long long whi = __shfl_sync(gmask, hi, src), wlo = __shfl_sync(gmask, lo, src);
-      Tw.a1 = __uint_as_float((uint32_t)(whi >> 32)); Tw.a2 = __uint_as_float((uint32_t)whi);
-      Tw.a3 = __uint_as_float((uint32_t)(wlo >> 32)); Tw.minor = (uint32_t)wlo;
-      if (!ev_less(Tw, tc)) break;
-      const double Uw = __shfl_sync(gmask, U, src);
-      const double Xw = __shfl_sync(gmask, X, src);
+      Tw.a1 = __uint_as_float((uint32_t)(whi >> 32));
+      if (all_plain) { Tw.a2 = 0.0f; Tw.a3 = 0.0f; Tw.minor = 2u * (uint32_t)whi; }
+      else { Tw.a2 = __uint_as_float((uint32_t)whi); Tw.a3 = __uint_as_float((uint32_t)(wlo >> 32)); Tw.minor = (uint32_t)wlo; }
+      if (!ev_less(Tw, tc)) { open = false; continue; }
       const double cd = (double)cur;
       if (Uw < cd && Xw < cd) { cur = (float)Xw; tc = accept_time(c, cur, Tw); }
+    }
+    if (big) {   // rare: more than 8 faces -> CSR path on the group's first lane, result broadcast below
+      if (j == 0) replay_serial(c, band_end, goal, round, cur, tc);
+    }
+    const unsigned anybig = __ballot_sync(FULL, big);
+    if (anybig) {
+      cur = __shfl_sync(FULL, cur, 0, 8);
+      tc.a1 = __shfl_sync(FULL, tc.a1, 0, 8); tc.a2 = __shfl_sync(FULL, tc.a2, 0, 8);
+      tc.a3 = __shfl_sync(FULL, tc.a3, 0, 8); tc.minor = __shfl_sync(FULL, tc.minor, 0, 8);
     }
     nd = cur; nt = tc;
   }
