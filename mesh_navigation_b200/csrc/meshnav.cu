@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(512, 1) k_dijkstra(const DijkstraKernelArgs a)
   if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; }
   __syncthreads();
   for (uint32_t v = gtid; v < V; v += gthreads) { state[v] = state_inf(); mark[v] = MARK_NONE; a.out_pred[v] = v; }
-  group_sync<CS>();
+  group_sync<CS>(ctl->barrier);
   DijkstraProblem prob;
   prob.adj_ptr = a.adj_ptr; prob.adj_nw = a.adj_nw; prob.cost = a.cost; prob.invalid = a.invalid;
   prob.state = state; prob.pred = a.out_pred; prob.cost_limit = a.cost_limit; prob.deferred_m = __uint_as_float(INF_BITS);
@@ -1011,7 +1011,11 @@ int32_t mnb_dijkstra(mnb_ctx* ctx, uint32_t seed_vertex, int64_t robot_vertex, d
   if (robot_vertex >= 0 && (uint32_t)robot_vertex == seed_vertex) return MNB_SUCCESS;   // dijkstra:252-255
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   cudaError_t e;
-  const int cs = ctx->cluster == -1 ? 8 : ctx->cluster;
+  const int cs = ctx->cluster;
+  if (cs == -1) {   // single plan on the whole GPU (cooperative launch, one CTA per SM)
+    void* kargs[] = {(void*)&a};
+    e = cudaLaunchCooperativeKernel((const void*)k_dijkstra<0>, dim3(ctx->sm_count), dim3(ctx->threads), kargs, 0, ctx->stream);
+  } else
   switch (cs) {
     case 1: e = launch_cluster(k_dijkstra<1>, a, 1, 1, ctx->threads, ctx->stream); break;
     case 2: e = launch_cluster(k_dijkstra<2>, a, 2, 2, ctx->threads, ctx->stream); break;
