@@ -316,3 +316,88 @@ def test_config3_layer_stack_chain(api, oracle_mod):
     check_cvp(got, ref)
     assert np.isfinite(ref["dist"]).sum() > 0.5 * om.V
     mm.close()
+
+
+def test_irregular_mesh_all_paths(api, oracle_mod):
+    """Delaunay mesh with vertex degrees 3..24: exercises the ELL overflow (> 8 faces) and the rescanning replay
+    (> 12 faces) paths, a mesh boundary everywhere and strongly varying triangle shapes."""
+    from tests.util import delaunay_mesh
+    pos, faces = delaunay_mesh(6000)
+    om = oracle_mod.OracleMesh(pos, faces)
+    deg = np.bincount(faces.reshape(-1))
+    assert deg.max() >= 24 and (deg > 8).sum() > 20
+    mm = api.MeshMap(pos, faces)
+    assert (mm.edges() == om.edges).all()
+    ed = om.edge_distances()
+    assert (mm.edgeDistances().view(np.uint32) == ed.view(np.uint32)).all()
+    rng = np.random.default_rng(9)
+    vc = (rng.random(om.V) * 0.6).astype(np.float32)
+    for factor in (0.0, 1.0):
+        w = om.edge_weights(vc, ed, factor)
+        assert (mm.computeEdgeWeights(vc, factor).view(np.uint32) == w.view(np.uint32)).all()
+        hub = om.V - 1
+        seeds = [hub, int(np.argmin(np.linalg.norm(pos[:, :2] - [1.0, 1.0], axis=1)))]
+        for sv in seeds:
+            ref = om.dijkstra(w, vc, sv); got = api.DijkstraMeshPlanner(mm).dijkstra(sv)
+            assert (got["dist"].view(np.uint32) == ref["dist"].view(np.uint32)).all() and (got["pred"] == ref["pred"]).all()
+            f = face_of_vertex(faces, sv); sp = pos[faces[f]].mean(0).astype(np.float32)
+            ref = om.cvp(w, vc, f, sp)
+            for cluster in (-1, 2):
+                mm.set_tuning(0.3, cluster, 0)
+                got = api.CVPMeshPlanner(mm).waveFrontPropagation(f, sp)
+                check_cvp(got, ref)
+    # inflation + layers on the irregular mesh
+    le = np.where(np.linalg.norm(pos[:, :2] - [3.0, 3.0], axis=1) < 0.5)[0].astype(np.uint32)
+    ref = om.inflation(ed, le); got = api.InflationLayer(mm).waveCostInflation(le)
+    check_inflation(got, ref, 0.4)
+    le2 = np.where(np.linalg.norm(pos[:, :2] - pos[om.V - 1, :2], axis=1) < 0.25)[0].astype(np.uint32)   # around the hub
+    ref = om.inflation(ed, le2); got = api.InflationLayer(mm).waveCostInflation(le2)
+    check_inflation(got, ref, 0.4)
+    refl = om.layers(); gotl = mm.computeLayers()
+    for name in ("height_diff", "ridge", "border"):
+        assert (gotl[name].view(np.uint32) == refl[name].view(np.uint32)).all(), name
+    assert np.allclose(gotl["roughness"], refl["roughness"], rtol=LAYER_RTOL, atol=1e-6)
+    mm.close()
+
+
+def test_disconnected_and_tiny_meshes(api, oracle_mod):
+    """two disconnected components (unreachable part stays +inf / pred self), and the single-triangle mesh of the
+    reference's own test (inflation_layer_test.cpp:7-23)"""
+    pos1, faces1 = mesh_case(20, False)
+    pos2 = pos1 + np.array([10.0, 0, 0], np.float32)
+    pos = np.concatenate([pos1, pos2]); faces = np.concatenate([faces1, faces1 + len(pos1)]).astype(np.uint32)
+    om = oracle_mod.OracleMesh(pos, faces); mm = api.MeshMap(pos, faces)
+    ed = om.edge_distances(); vc = np.zeros(om.V, np.float32); mm.setCosts(vc, ed)
+    ref = om.cvp(ed, vc, 10, pos[faces[10]].mean(0)); got = api.CVPMeshPlanner(mm).waveFrontPropagation(10, pos[faces[10]].mean(0))
+    check_cvp(got, ref)
+    assert np.isinf(got["dist"][len(pos1):]).all() and (got["pred"][len(pos1):] == np.arange(len(pos1), om.V)).all()
+    refd = om.dijkstra(ed, vc, 5, robot_vertex=len(pos1) + 3); gotd = api.DijkstraMeshPlanner(mm).dijkstra(5, len(pos1) + 3)
+    assert refd["outcome"] == gotd["outcome"] == 54
+    assert (gotd["dist"].view(np.uint32) == refd["dist"].view(np.uint32)).all()
+    mm.close()
+    tri_pos = np.array([[0, 0, 0], [0.5, 0, 0], [0, 0.5, 0]], np.float32); tri = np.array([[0, 1, 2]], np.uint32)
+    om = oracle_mod.OracleMesh(tri_pos, tri); mm = api.MeshMap(tri_pos, tri)
+    ed = om.edge_distances(); mm.setCosts(np.zeros(3, np.float32), ed)
+    got = api.DijkstraMeshPlanner(mm).dijkstra(0)
+    assert got["dist"].tolist() == [0.0, 0.5, 0.5] and got["pred"].tolist() == [0, 0, 0]
+    got = api.CVPMeshPlanner(mm).waveFrontPropagation(0, np.array([0.1, 0.1, 0.0], np.float32))
+    ref = om.cvp(ed, np.zeros(3, np.float32), 0, np.array([0.1, 0.1, 0.0], np.float32))
+    assert (got["dist"] == ref["dist"]).all()
+    got = api.InflationLayer(mm, 0.5, 1.5, 1.0, 0.9, 1.0).waveCostInflation(np.array([0, 1], np.uint32))
+    assert got["dist"][2] > 0 and np.isfinite(got["dist"][2])          # two lethal corners reach the third
+    mm.close()
+
+
+def test_cancel_returns_canceled(api, oracle_mod):
+    """mnb_cancel from another thread while a plan runs -> MBF CANCELED (51) (cvp_mesh_planner.cpp:142-146, 888-892)"""
+    import threading, time
+    pos, faces, om, mm, ed, vc, w = setup(api, oracle_mod, 700, True)
+    mm.set_tuning(0.02, 1, 0)          # tiny band + one CTA: a deliberately slow plan (tens of ms)
+    v, f, sp = centre_seed(pos, faces)
+    outcomes = []
+    t = threading.Thread(target=lambda: outcomes.append(api.CVPMeshPlanner(mm).waveFrontPropagation(f, sp)["outcome"]))
+    t.start(); time.sleep(0.004); mm.cancel(); t.join()
+    assert outcomes[0] in (51, 0)      # canceled unless the plan had already finished
+    mm.set_tuning(0.3, -1, 0)
+    assert api.CVPMeshPlanner(mm).waveFrontPropagation(f, sp)["outcome"] == 0     # the flag is reset per plan (cvp:679)
+    mm.close()
