@@ -173,13 +173,15 @@ class CVPMeshPlanner:
         self.cost_limit = cost_limit                # cvp_mesh_planner.h:201-212
         self.goal_dist_offset = goal_dist_offset
 
-    def waveFrontPropagation(self, seed_face: int, seed_pos, robot_face: int = -1):
+    def waveFrontPropagation(self, seed_face: int, seed_pos, robot_face: int = -1, out=None):
+        """out: optional dict of preallocated host arrays (dist f32, pred u32, direction f32, cutting_face i32), e.g.
+        views of pinned memory, that receive the results"""
         m = self.map
         sp = np.ascontiguousarray(seed_pos, dtype=np.float32)
-        dist = np.empty(m.V, dtype=np.float32)
-        pred = np.empty(m.V, dtype=np.uint32)
-        direction = np.empty(m.V, dtype=np.float32)
-        cut = np.empty(m.V, dtype=np.int32)
+        dist = out["dist"] if out else np.empty(m.V, dtype=np.float32)
+        pred = out["pred"] if out else np.empty(m.V, dtype=np.uint32)
+        direction = out["direction"] if out else np.empty(m.V, dtype=np.float32)
+        cut = out["cutting_face"] if out else np.empty(m.V, dtype=np.int32)
         rc = m._check(m.L.mnb_cvp(m._ctx, int(seed_face), _p(sp), int(robot_face), float(self.cost_limit),
                                   float(self.goal_dist_offset), _p(dist), _p(pred), _p(direction), _p(cut)))
         return dict(outcome=rc, dist=dist, pred=pred, direction=direction, cutting_face=cut, **m.stats())

@@ -56,6 +56,16 @@ __global__ void k_gather_corner_w(const uint4* __restrict__ cor_eid, const float
   out[k] = make_float4(w[e.x], w[e.y], w[e.z], 0.0f);
 }
 
+// static half of the CVP unfolding per ELL slot {p, hc, t0a, -} in double (CvpEllProblem::face_geo): depends on the
+// installed edge weights only, so it is computed once per mnb_set_costs instead of once per recompute
+__global__ void k_corner_geo(const float4* __restrict__ w, size_t N, double4* __restrict__ out) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= N) return;
+  const float4 ww = w[k];
+  const CvpEllProblem::FaceGeo g = CvpEllProblem::face_geo((double)ww.z, (double)ww.y, (double)ww.x);
+  out[k] = make_double4(g.p, g.hc, g.t0a, 0.0);
+}
+
 // per-directed-edge records {neighbour, weight bits}
 __global__ void k_gather_adj_w(const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ eid,
                                const float* __restrict__ w, size_t NA, uint2* __restrict__ out) {
@@ -86,7 +96,7 @@ struct CvpKernelArgs {
   const float* pos;
   const uint32_t* faces;
   const uint32_t* cor_ptr; const int4* cor_idx; const float4* cor_w;
-  const int4* ell_idx; const float4* ell_w;
+  const int4* ell_idx; const float4* ell_w; const double4* ell_geo;
   const float* cost; const uint8_t* invalid;
   WaveWorkspace ws;
   uint32_t n_queries;
@@ -152,7 +162,7 @@ __global__ void __launch_bounds__(512, MNB_CVP_MINBLOCKS) k_cvp(const CvpKernelA
     const uint32_t s0 = a.faces[3 * (size_t)sf], s1 = a.faces[3 * (size_t)sf + 1], s2 = a.faces[3 * (size_t)sf + 2];
     CvpEllProblem prob;
     prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_w = a.cor_w; prob.cost = a.cost; prob.invalid = a.invalid;
-    prob.ell_idx = a.ell_idx; prob.ell_w = a.ell_w;
+    prob.ell_idx = a.ell_idx; prob.ell_w = a.ell_w; prob.ell_geo = a.ell_geo;
     prob.state = state; prob.minor_arr = a.ws.minor + (size_t)g * V; prob.chg = chg; prob.deferred_m = __uint_as_float(INF_BITS); prob.pred = nullptr; prob.dir = nullptr; prob.cut = nullptr; prob.cost_limit = a.cost_limit;
     prob.s0 = s0; prob.s1 = s1; prob.s2 = s2; prob.seed_noexpand = 0;
     float sd[3];
@@ -229,7 +239,7 @@ __global__ void __launch_bounds__(512, MNB_GRID_MINBLOCKS) k_cvp_grid(const CvpK
   const uint32_t s0 = a.faces[3 * (size_t)sf], s1 = a.faces[3 * (size_t)sf + 1], s2 = a.faces[3 * (size_t)sf + 2];
   CvpEllProblem prob;
   prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_w = a.cor_w; prob.cost = a.cost; prob.invalid = a.invalid;
-  prob.ell_idx = a.ell_idx; prob.ell_w = a.ell_w;
+  prob.ell_idx = a.ell_idx; prob.ell_w = a.ell_w; prob.ell_geo = a.ell_geo;
   prob.state = state; prob.minor_arr = a.ws.minor; prob.chg = a.ws.chg; prob.deferred_m = __uint_as_float(INF_BITS); prob.pred = nullptr; prob.dir = nullptr; prob.cut = nullptr; prob.cost_limit = a.cost_limit;
   prob.s0 = s0; prob.s1 = s1; prob.s2 = s2; prob.seed_noexpand = 0;
   float sd[3];
@@ -562,7 +572,7 @@ struct mnb_ctx {
   float* d_pos = nullptr; uint32_t* d_faces = nullptr; uint32_t* d_edges = nullptr;
   uint32_t* d_cor_ptr = nullptr; int4* d_cor_idx = nullptr; uint4* d_cor_eid = nullptr;
   float4* d_cor_w = nullptr; float4* d_cor_wd = nullptr;
-  int4* d_ell_idx = nullptr; uint4* d_ell_eid = nullptr; float4* d_ell_w = nullptr; float4* d_ell_wd = nullptr;
+  int4* d_ell_idx = nullptr; uint4* d_ell_eid = nullptr; float4* d_ell_w = nullptr; float4* d_ell_wd = nullptr; double4* d_ell_geo = nullptr;
   uint32_t* d_adj_ptr = nullptr; uint32_t* d_adj_nbr = nullptr; uint32_t* d_adj_eid = nullptr; uint2* d_adj_nw = nullptr;
   float* d_edge_dist = nullptr; float* d_edge_w = nullptr; float* d_cost = nullptr; uint8_t* d_invalid = nullptr;
   bool has_invalid = false, costs_set = false;
@@ -602,7 +612,7 @@ static void dfree(T*& p) { if (p) cudaFree(p); p = nullptr; }
 
 static void free_mesh(mnb_ctx* c) {
   dfree(c->d_pos); dfree(c->d_faces); dfree(c->d_edges); dfree(c->d_cor_ptr); dfree(c->d_cor_idx); dfree(c->d_cor_eid);
-  dfree(c->d_cor_w); dfree(c->d_cor_wd); dfree(c->d_ell_idx); dfree(c->d_ell_eid); dfree(c->d_ell_w); dfree(c->d_ell_wd); dfree(c->d_adj_ptr); dfree(c->d_adj_nbr); dfree(c->d_adj_eid); dfree(c->d_adj_nw);
+  dfree(c->d_cor_w); dfree(c->d_cor_wd); dfree(c->d_ell_idx); dfree(c->d_ell_eid); dfree(c->d_ell_w); dfree(c->d_ell_wd); dfree(c->d_ell_geo); dfree(c->d_adj_ptr); dfree(c->d_adj_nbr); dfree(c->d_adj_eid); dfree(c->d_adj_nw);
   dfree(c->d_edge_dist); dfree(c->d_edge_w); dfree(c->d_cost); dfree(c->d_invalid);
   dfree(c->ws.state); dfree(c->ws.minor); dfree(c->ws.chg); dfree(c->ws.mark); dfree(c->ws.list0); dfree(c->ws.list1); dfree(c->ws.ctl);
   c->ws_groups = 0;
@@ -735,6 +745,7 @@ int32_t mnb_set_mesh(mnb_ctx* ctx, uint32_t V, uint32_t F, const float* pos, con
       eidx[(size_t)v * ELL_W].w = (int)(ke - kb);
     }
     CK(dalloc(&ctx->d_ell_idx, NE)); CK(dalloc(&ctx->d_ell_eid, NE)); CK(dalloc(&ctx->d_ell_w, NE)); CK(dalloc(&ctx->d_ell_wd, NE));
+    CK(dalloc(&ctx->d_ell_geo, NE));
     CK(cudaMemcpyAsync(ctx->d_ell_idx, eidx.data(), sizeof(int4) * NE, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_ell_eid, eeid.data(), sizeof(uint4) * NE, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -775,6 +786,7 @@ int32_t mnb_get_edge_distances(mnb_ctx* ctx, float* out) {
 static int32_t install_weights(mnb_ctx* ctx) {
   k_gather_corner_w<<<(unsigned)((ctx->NC + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_cor_eid, ctx->d_edge_w, ctx->NC, ctx->d_cor_w);
   k_gather_corner_w<<<(unsigned)(((size_t)ctx->V * ELL_W + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_ell_eid, ctx->d_edge_w, (size_t)ctx->V * ELL_W, ctx->d_ell_w);
+  k_corner_geo<<<(unsigned)(((size_t)ctx->V * ELL_W + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_ell_w, (size_t)ctx->V * ELL_W, ctx->d_ell_geo);
   k_gather_adj_w<<<(unsigned)((ctx->NA + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_adj_nbr, ctx->d_adj_eid, ctx->d_edge_w, ctx->NA, ctx->d_adj_nw);
   CK(cudaGetLastError());
   ctx->costs_set = true;
@@ -878,7 +890,7 @@ static int32_t ensure_seeds(mnb_ctx* ctx, uint32_t n) {
 
 static void fill_cvp_args(mnb_ctx* ctx, CvpKernelArgs& a) {
   a.V = ctx->V; a.pos = ctx->d_pos; a.faces = ctx->d_faces; a.cor_ptr = ctx->d_cor_ptr; a.cor_idx = ctx->d_cor_idx;
-  a.cor_w = ctx->d_cor_w; a.ell_idx = ctx->d_ell_idx; a.ell_w = ctx->d_ell_w; a.cost = ctx->d_cost; a.invalid = ctx->has_invalid ? ctx->d_invalid : nullptr; a.ws = ctx->ws;
+  a.cor_w = ctx->d_cor_w; a.ell_idx = ctx->d_ell_idx; a.ell_w = ctx->d_ell_w; a.ell_geo = ctx->d_ell_geo; a.cost = ctx->d_cost; a.invalid = ctx->has_invalid ? ctx->d_invalid : nullptr; a.ws = ctx->ws;
   a.seed_faces = ctx->d_seed_faces; a.seed_pos = ctx->d_seed_pos; a.delta = ctx->delta; a.next_query = ctx->d_next_query;
   a.cancel_flag = ctx->d_cancel; a.max_rounds = watchdog_rounds(ctx->V);
 }

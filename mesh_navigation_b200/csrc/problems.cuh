@@ -228,6 +228,7 @@ constexpr int ELL_EMPTY = -1;
 struct CvpEllProblem : CvpProblem {
   const int4* __restrict__ ell_idx;
   const float4* __restrict__ ell_w;
+  const double4* __restrict__ ell_geo;   // {p, hc, t0a, -} per slot, precomputed from ell_w (k_corner_geo)
 
   // face evaluation without a current label: U = unfolded distance, X = value the reference would
   // store (U when the angle test passes, else the edge fallback).  accept(cur) <=> U < cur && X < cur.
@@ -322,7 +323,9 @@ struct CvpEllProblem : CvpProblem {
       // issue the four loads, then do the label-independent half of the unfolding while they are in flight
       const uint4 sa = __ldcg(&state[v1]), sb = __ldcg(&state[v2]);
       mk1 = __ldcg(&mark[v1]); mk2 = __ldcg(&mark[v2]);
-      const FaceGeo g = face_geo((double)w.z, (double)w.y, (double)w.x);
+      const double2* gp = reinterpret_cast<const double2*>(ell_geo) + 2 * ((size_t)c * ELL_W + j);
+      const double2 g01 = __ldg(gp), g23 = __ldg(gp + 1);
+      FaceGeo g; g.p = g01.x; g.hc = g01.y; g.t0a = g23.x;
       Label a, b;
       a.d = __uint_as_float(sa.x); a.t.a1 = __uint_as_float(sa.y); a.t.a2 = __uint_as_float(sa.z); a.t.a3 = __uint_as_float(sa.w & 0x7fffffffu);
       a.t.minor = (sa.w >> 31) ? __ldcg(&minor_arr[v1]) : 2u * v1;
@@ -336,20 +339,35 @@ struct CvpEllProblem : CvpProblem {
       }
     }
     // Common case: every firing face of the warp has a plain pop time (a2 == a3 == 0, default minor = 2*Tv):
-    // the event order is the 64-bit key (a1, Tv).  Cascade members (rare) take the general 128-bit path.
+    // the event order is (a1, Tv).  Cascade members (rare) take the general 128-bit path.  Invalid lanes carry
+    // the maximal key so that no validity flag has to travel with the shuffles.
     const bool plain = !valid || (T.a2 == 0.0f && T.a3 == 0.0f && T.minor == 2u * Tv);
     const bool all_plain = __all_sync(FULL, plain);
-    const unsigned long long hi = all_plain ? (((unsigned long long)__float_as_uint(T.a1) << 32) | Tv)
-                                            : (((unsigned long long)__float_as_uint(T.a1) << 32) | __float_as_uint(T.a2));
+    const uint32_t k1 = valid ? __float_as_uint(T.a1) : 0xffffffffu;          // pop times are >= 0: bit order = value order
+    const unsigned long long hi = valid ? (all_plain ? (((unsigned long long)k1 << 32) | Tv)
+                                                     : (((unsigned long long)k1 << 32) | __float_as_uint(T.a2)))
+                                        : ~0ull;
     const unsigned long long lo = ((unsigned long long)__float_as_uint(T.a3) << 32) | T.minor;
     int rank = 0;
     if (all_plain) {
+      // 32-bit pass on a1 alone; two firing faces with bit-identical a1 (exact float tie between different source
+      // vertices) are rare -- only then is the (a1, Tv) pass needed
+      bool tie = false;
 #pragma unroll
       for (int d = 1; d < 8; ++d) {
         const int src = (int)((j + d) & 7);
-        const unsigned long long ohi = __shfl_sync(FULL, hi, src, 8);
-        const int ovalid = __shfl_sync(FULL, (int)valid, src, 8);
-        if (ovalid && (ohi < hi || (ohi == hi && (uint32_t)src < j))) ++rank;
+        const uint32_t ok1 = __shfl_sync(FULL, k1, src, 8);
+        rank += (ok1 < k1) ? 1 : 0;
+        tie |= (ok1 == k1) && valid;
+      }
+      if (__any_sync(FULL, tie)) {
+        rank = 0;
+#pragma unroll
+        for (int d = 1; d < 8; ++d) {
+          const int src = (int)((j + d) & 7);
+          const unsigned long long ohi = __shfl_sync(FULL, hi, src, 8);
+          if (ohi < hi || (ohi == hi && (uint32_t)src < j)) ++rank;
+        }
       }
     } else {
 #pragma unroll
@@ -357,20 +375,16 @@ struct CvpEllProblem : CvpProblem {
         const int src = (int)((j + d) & 7);
         const unsigned long long ohi = __shfl_sync(FULL, hi, src, 8);
         const unsigned long long olo = __shfl_sync(FULL, lo, src, 8);
-        const int ovalid = __shfl_sync(FULL, (int)valid, src, 8);
-        if (ovalid && (ohi < hi || (ohi == hi && (olo < lo || (olo == lo && (uint32_t)src < j))))) ++rank;
+        if (ohi < hi || (ohi == hi && (olo < lo || (olo == lo && (uint32_t)src < j)))) ++rank;
       }
     }
     if (!valid) rank = 99;
-    const unsigned vmask = (__ballot_sync(FULL, valid) >> sh) & 0xFFu;
-    // the replay loop runs to the largest face count among the 4 groups of the warp (idle iterations are masked)
-    int nmax = __popc(vmask);
-    nmax = max(nmax, __shfl_xor_sync(FULL, nmax, 8));
-    nmax = max(nmax, __shfl_xor_sync(FULL, nmax, 16));
+    const int nvalid = __popc((__ballot_sync(FULL, valid) >> sh) & 0xFFu);
     float cur = INF;
     EvTime tc = ev_normal(INF, c);
-    bool open = true;                                   // c has not been popped yet
-    for (int r = 0; r < nmax; ++r) {
+    bool open = nvalid > 0;                             // c has not been popped yet and faces remain
+    for (int r = 0; r < (int)ELL_W; ++r) {
+      if (!__any_sync(FULL, open)) break;               // every group of the warp is done
       const unsigned who = (__ballot_sync(FULL, rank == r) >> sh) & 0xFFu;
       const int src = who ? (__ffs(who) - 1) : 0;
       const unsigned long long whi = __shfl_sync(FULL, hi, src, 8);
@@ -378,7 +392,8 @@ struct CvpEllProblem : CvpProblem {
       if (!all_plain) wlo = __shfl_sync(FULL, lo, src, 8);
       const double Uw = __shfl_sync(FULL, U, src, 8);
       const double Xw = __shfl_sync(FULL, X, src, 8);
-      if (!who || !open) continue;
+      if (!who) open = false;                           // ranks are dense: no face with rank r -> none beyond
+      if (!open) continue;
       EvTime Tw;
       Tw.a1 = __uint_as_float((uint32_t)(whi >> 32));
       if (all_plain) { Tw.a2 = 0.0f; Tw.a3 = 0.0f; Tw.minor = 2u * (uint32_t)whi; }
