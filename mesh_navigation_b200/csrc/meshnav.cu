@@ -134,8 +134,11 @@ __device__ __forceinline__ void ctl_reset(GroupCtl* ctl, unsigned int n0, float 
 #ifndef MNB_CVP_MINBLOCKS
 #define MNB_CVP_MINBLOCKS 1
 #endif
+#ifndef MNB_CVP_THREADS
+#define MNB_CVP_THREADS 512
+#endif
 template <int CS>
-__global__ void __launch_bounds__(512, MNB_CVP_MINBLOCKS) k_cvp(const CvpKernelArgs a) {
+__global__ void __launch_bounds__(MNB_CVP_THREADS, MNB_CVP_MINBLOCKS) k_cvp(const CvpKernelArgs a) {
   __shared__ Stage st;
   uint32_t g, gthreads, gtid;
   group_coords<CS>(g, gthreads, gtid);
@@ -846,12 +849,13 @@ static cudaError_t launch_cluster(void (*kern)(const KArgs), const KArgs& args, 
 static int32_t launch_cvp(mnb_ctx* ctx, const CvpKernelArgs& a, int cs, unsigned groups) {
   cudaError_t e;
   const unsigned blocks = groups * cs;
+  const int threads = MNB_CVP_THREADS;
   switch (cs) {
-    case 1: e = launch_cluster(k_cvp<1>, a, 1, blocks, ctx->threads, ctx->stream); break;
-    case 2: e = launch_cluster(k_cvp<2>, a, 2, blocks, ctx->threads, ctx->stream); break;
-    case 4: e = launch_cluster(k_cvp<4>, a, 4, blocks, ctx->threads, ctx->stream); break;
-    case 8: e = launch_cluster(k_cvp<8>, a, 8, blocks, ctx->threads, ctx->stream); break;
-    default: e = launch_cluster(k_cvp<16>, a, 16, blocks, ctx->threads, ctx->stream); break;
+    case 1: e = launch_cluster(k_cvp<1>, a, 1, blocks, threads, ctx->stream); break;
+    case 2: e = launch_cluster(k_cvp<2>, a, 2, blocks, threads, ctx->stream); break;
+    case 4: e = launch_cluster(k_cvp<4>, a, 4, blocks, threads, ctx->stream); break;
+    case 8: e = launch_cluster(k_cvp<8>, a, 8, blocks, threads, ctx->stream); break;
+    default: e = launch_cluster(k_cvp<16>, a, 16, blocks, threads, ctx->stream); break;
   }
   if (e != cudaSuccess) { ctx->err = std::string("cvp launch: ") + cudaGetErrorString(e); return MNB_E_CUDA; }
   return MNB_OK;
@@ -972,7 +976,7 @@ int32_t mnb_cvp_batch(mnb_ctx* ctx, uint32_t n, const uint32_t* seed_faces, cons
   CK(cudaSetDevice(ctx->device));
   const int cs = ctx->batch_cluster;
   int per_sm = 1;
-  if (cs == 1) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cvp<1>, ctx->threads, 0)); if (per_sm < 1) per_sm = 1; if (per_sm > 2) per_sm = 2; }
+  if (cs == 1) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cvp<1>, MNB_CVP_THREADS, 0)); if (per_sm < 1) per_sm = 1; if (per_sm > 2) per_sm = 2; }
   unsigned groups = (unsigned)(ctx->sm_count * per_sm / cs);
   if (groups > n) groups = n;
   if (groups == 0) groups = 1;
