@@ -146,6 +146,26 @@ int32_t mnb_compute_layers(mnb_ctx* ctx, const mnb_layer_params* params, const f
 /* lvr2::calcVertexNormals equivalent (mesh_map.cpp:374): normalised sum of incident face normals */
 int32_t mnb_get_vertex_normals(mnb_ctx* ctx, float* out_normals /* 3V */);
 
+/* ---- vector-field epilogues -----------------------------------------------------------------------
+ * DijkstraMeshPlanner::computeVectorMap (dijkstra_mesh_planner.cpp:189-209): direction == NULL, cutting_face == NULL:
+ *   out[v] = normalize(p[pred[v]] - p[v]).
+ * CVPMeshPlanner::computeVectorMap (cvp_mesh_planner.cpp:204-239): the vector is additionally rotated about the vertex
+ *   normal by direction[v]; vertices without a cutting face are skipped.
+ * out_vec: 3V floats, NaN = "no entry in the sparse vector map" (pred[v] == v or no cutting face). */
+int32_t mnb_vector_map(mnb_ctx* ctx, const uint32_t* pred /* V */, const float* direction /* V or NULL */,
+                       const int32_t* cutting_face /* V or NULL */, float* out_vec /* 3V */);
+
+/* ---- vector-field back-tracking -------------------------------------------------------------------
+ * The tail of CVPMeshPlanner::waveFrontPropagation (cvp_mesh_planner.cpp:920-951): follows the vector field of the
+ * LAST successful mnb_cvp on this context (kept on the device) from the robot position down to the wave's seed with
+ * MeshMap::meshAhead (mesh_map.cpp:1070-1108) in steps of step_width.  Points are returned in walk order
+ * (robot first, seed last = the order of the final plan after cvp:100 path.reverse()).  In device-pointer mode
+ * the result arrays of that mnb_cvp must still be alive.  Layer vector fields (AbstractLayer::vectorAt) are zero.
+ * Returns MNB_SUCCESS / MNB_NO_PATH_FOUND / MNB_CANCELED; MNB_E_STATE if max_points is exhausted. */
+int32_t mnb_cvp_backtrack(mnb_ctx* ctx, const float robot_pos[3], uint32_t robot_face, double step_width, uint32_t max_points,
+                          float* path_pos /* 3*max_points */, uint32_t* path_face /* max_points or NULL */,
+                          uint32_t* n_points);
+
 /* ---- cancel (CVPMeshPlanner::cancel / DijkstraMeshPlanner::cancel) ------- */
 int32_t mnb_cancel(mnb_ctx* ctx);
 

@@ -15,6 +15,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../meshnav_b200.h"
@@ -165,15 +166,10 @@ class DijkstraMeshPlanner : public MeshPlanner {
     return SUCCESS;
   }
 
-  // dijkstra_mesh_planner.cpp:189-209
+  // dijkstra_mesh_planner.cpp:189-209 (GPU epilogue; NaN row = no entry in the sparse map)
   void computeVectorMap() {
-    const uint32_t V = mesh_map_->numVertices();
-    vector_map_.assign(V, Vector{});
-    for (uint32_t v3 = 0; v3 < V; ++v3) {
-      const uint32_t v1 = predecessors_[v3];
-      if (v1 == v3) continue;
-      vector_map_[v3] = normalized(mesh_map_->vertexPosition(v1) - mesh_map_->vertexPosition(v3));
-    }
+    vector_map_.assign(mesh_map_->numVertices(), Vector{});
+    mnb_vector_map(mesh_map_->ctx(), predecessors_.data(), nullptr, nullptr, &vector_map_[0].x);
   }
   const std::vector<float>& potential() const { return potential_; }
   const std::vector<uint32_t>& predecessors() const { return predecessors_; }
@@ -193,21 +189,56 @@ class CVPMeshPlanner : public MeshPlanner {
   }
   bool cancel() override { return mnb_cancel(mesh_map_->ctx()) == MNB_OK; }                               // cvp:142-146
 
-  // cvp_mesh_planner.cpp:62-140.  Round 1 builds the wavefront (potential / predecessors / direction / cutting
-  // faces); the vector-field back-tracking of :920-951 (MeshMap::meshAhead) is a SURVEY 8f "next" row, so the
-  // returned plan holds the two end poses only and `cost` is the potential at the robot's face.
+  // cvp_mesh_planner.cpp:62-140: wavefront seeded at the goal, then the vector-field back-tracking of :920-951
+  // (MeshMap::meshAhead) on the device; `path` comes back in plan order (robot first), so the reference's
+  // path.reverse() (:100) is already applied.  Poses: position + direction to the next point (:104-120).
   uint32_t makePlan(const PoseStamped& start, const PoseStamped& goal, double /*tolerance*/, std::vector<PoseStamped>& plan,
                     double& cost, std::string& message) override {
-    const uint32_t outcome = waveFrontPropagation(goal.position, start.position, message);               // :89
+    std::vector<std::pair<Vector, uint32_t>> path;
+    const uint32_t outcome = waveFrontPropagation(goal.position, start.position, path, message);         // :89
     cost = 0;
-    if (outcome == SUCCESS) {
-      const int64_t rf = mesh_map_->getContainingFace(start.position, 0.4f);
-      float c = 0; for (int k = 0; k < 3; ++k) c += potential_[mesh_map_->faces()[3 * (size_t)rf + k]] / 3.0f;
-      cost = c;
-      plan.push_back(start); plan.push_back(goal);
+    if (!path.empty()) {
+      Vector vec = path.front().first;                                                                    // :104-120
+      for (size_t i = 1; i < path.size(); ++i) {
+        const Vector next = path[i].first;
+        PoseStamped pose; pose.position = vec; pose.direction = normalized(next - vec);
+        cost += length(next - vec);
+        vec = next;
+        plan.push_back(pose);
+      }
+      PoseStamped pose; pose.position = vec; pose.direction = plan.empty() ? goal.direction : plan.back().direction;
+      plan.push_back(pose);
     }
     return outcome;
   }
+
+  // cvp_mesh_planner.cpp:651-970 including the back-tracking; path in plan order (robot ... wave seed)
+  uint32_t waveFrontPropagation(const Vector& start, const Vector& goal, std::vector<std::pair<Vector, uint32_t>>& path,
+                                std::string& message) {
+    path.clear();
+    const uint32_t outcome = waveFrontPropagation(start, goal, message);
+    if (outcome != SUCCESS) return outcome;
+    computeVectorMap();                                                                                   // :897
+    const int64_t goal_face = mesh_map_->getContainingFace(goal, 0.4f);
+    const uint32_t max_points = 1u << 16;
+    std::vector<float> pp(3 * (size_t)max_points); std::vector<uint32_t> pf(max_points);
+    uint32_t n = 0;
+    const float gp[3] = {goal.x, goal.y, goal.z};
+    const int32_t rc = mnb_cvp_backtrack(mesh_map_->ctx(), gp, (uint32_t)goal_face, config_.step_width, max_points, pp.data(),
+                                         pf.data(), &n);
+    if (rc < 0) { message = mnb_last_error(mesh_map_->ctx()); return INTERNAL_ERROR; }
+    if (rc == NO_PATH_FOUND) { message = "Could not find a valid path, while back-tracking from the goal"; return NO_PATH_FOUND; }   // :938-941
+    if (rc != SUCCESS) return (uint32_t)rc;
+    for (uint32_t i = 0; i < n; ++i) path.push_back({Vector{pp[3 * i], pp[3 * i + 1], pp[3 * i + 2]}, pf[i]});
+    return SUCCESS;
+  }
+
+  // cvp_mesh_planner.cpp:204-239 (GPU epilogue; NaN row = no entry in the sparse map)
+  void computeVectorMap() {
+    vector_map_.assign(mesh_map_->numVertices(), Vector{});
+    mnb_vector_map(mesh_map_->ctx(), predecessors_.data(), direction_.data(), cutting_faces_.data(), &vector_map_[0].x);
+  }
+  const std::vector<Vector>& getVectorMap() const { return vector_map_; }                                // :200-203
 
   // cvp_mesh_planner.cpp:241-247, 651-970 (propagation part)
   uint32_t waveFrontPropagation(const Vector& start, const Vector& goal, std::string& message) {
@@ -233,6 +264,7 @@ class CVPMeshPlanner : public MeshPlanner {
  private:
   std::string name_; std::shared_ptr<MeshMap> mesh_map_;
   std::vector<float> potential_, direction_; std::vector<uint32_t> predecessors_; std::vector<int32_t> cutting_faces_;
+  std::vector<Vector> vector_map_;
 };
 
 // mesh_layers::InflationLayer -- waveCostInflation + fading (inflation_layer.cpp:315-491)

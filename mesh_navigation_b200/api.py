@@ -120,6 +120,15 @@ class MeshMap:
         r.update(combined=comb, lethal_mask=mask, **self.stats())
         return r
 
+    def vectorMap(self, pred, direction=None, cutting_face=None) -> np.ndarray:
+        """computeVectorMap of the planners (dijkstra:189-209 with direction=None, cvp:204-239 otherwise)"""
+        pr = np.ascontiguousarray(pred, dtype=np.uint32)
+        di = None if direction is None else np.ascontiguousarray(direction, dtype=np.float32)
+        cu = None if cutting_face is None else np.ascontiguousarray(cutting_face, dtype=np.int32)
+        out = np.empty((self.V, 3), dtype=np.float32)
+        self._check(self.L.mnb_vector_map(self._ctx, _p(pr), _p(di), _p(cu), _p(out)))
+        return out
+
     def stats(self) -> dict:
         s = _lib.Stats()
         self._check(self.L.mnb_get_stats(self._ctx, C.byref(s)))
@@ -164,6 +173,9 @@ class DijkstraMeshPlanner:
                                        float(self.goal_dist_offset), _p(dist), _p(pred)))
         return dict(outcome=rc, dist=dist, pred=pred, **m.stats())
 
+    def computeVectorMap(self, pred):
+        return self.map.vectorMap(pred)
+
 
 class CVPMeshPlanner:
     """cvp_mesh_planner::CVPMeshPlanner -- wavefront part (waveFrontPropagation():651-886)."""
@@ -185,6 +197,36 @@ class CVPMeshPlanner:
         rc = m._check(m.L.mnb_cvp(m._ctx, int(seed_face), _p(sp), int(robot_face), float(self.cost_limit),
                                   float(self.goal_dist_offset), _p(dist), _p(pred), _p(direction), _p(cut)))
         return dict(outcome=rc, dist=dist, pred=pred, direction=direction, cutting_face=cut, **m.stats())
+
+    def computeVectorMap(self, pred, direction, cutting_face):
+        return self.map.vectorMap(pred, direction, cutting_face)
+
+    def backtrack(self, robot_pos, robot_face: int, step_width: float = 0.4, max_points: int = 1 << 16):
+        """vector-field back-tracking of the last waveFrontPropagation (cvp:920-951 / MeshMap::meshAhead), on the GPU;
+        returns the poses in plan order (robot first, wave seed last)"""
+        m = self.map
+        rp = np.ascontiguousarray(robot_pos, dtype=np.float32)
+        pos = np.empty((max_points, 3), dtype=np.float32); face = np.empty(max_points, dtype=np.uint32)
+        n = C.c_uint32(0)
+        rc = m._check(m.L.mnb_cvp_backtrack(m._ctx, _p(rp), int(robot_face), float(step_width), int(max_points), _p(pos),
+                                            _p(face), C.byref(n)))
+        return dict(outcome=rc, positions=pos[:n.value].copy(), faces=face[:n.value].copy(), **m.stats())
+
+    def makePlan(self, start_pos, start_face: int, goal_pos, goal_face: int, step_width: float = 0.4):
+        """CVPMeshPlanner::makePlan (cvp:62-140): the wave is seeded at the GOAL and runs until the robot (start) face is
+        fixed; only the path comes back to the host.  cost = sum of the segment lengths (cvp:104-120)"""
+        m = self.map
+        sp = np.ascontiguousarray(goal_pos, dtype=np.float32)
+        rc = m._check(m.L.mnb_cvp(m._ctx, int(goal_face), _p(sp), int(start_face), float(self.cost_limit),
+                                  float(self.goal_dist_offset), None, None, None, None))
+        st = m.stats()
+        if rc != 0:
+            return dict(outcome=rc, positions=np.empty((0, 3), np.float32), faces=np.empty(0, np.uint32), cost=0.0, **st)
+        bt = self.backtrack(start_pos, start_face, step_width)
+        p = bt["positions"]
+        cost = float(np.linalg.norm(np.diff(p, axis=0), axis=1).sum()) if len(p) > 1 else 0.0
+        bt.update(cost=cost, wavefront_ms=st["kernel_ms"])
+        return bt
 
     def waveFrontPropagationBatch(self, seed_faces, seed_pos):
         m = self.map

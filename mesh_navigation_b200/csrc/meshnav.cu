@@ -504,6 +504,156 @@ __global__ void __launch_bounds__(128) k_layers(const LayerKernelArgs a) {
 }
 
 // ============================================================================
+// Vector-field epilogues: DijkstraMeshPlanner::computeVectorMap (dijkstra_mesh_planner.cpp:189-209) and
+// CVPMeshPlanner::computeVectorMap (cvp_mesh_planner.cpp:204-239).  NaN = "no entry in the sparse map".
+// ============================================================================
+struct F3 { float x, y, z; };
+__device__ __forceinline__ F3 f3sub(F3 a, F3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ F3 f3cross(F3 a, F3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ float f3dot(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ F3 f3load(const float* __restrict__ p, uint32_t v) { return {p[3 * (size_t)v], p[3 * (size_t)v + 1], p[3 * (size_t)v + 2]}; }
+__device__ __forceinline__ F3 f3normalized(F3 v) {
+  const float l = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+  if (l > 0) { v.x /= l; v.y /= l; v.z /= l; }
+  return v;
+}
+
+// one entry of the planners' vector map; false = "no entry" (pred == self or no cutting face)
+__device__ __forceinline__ bool vertex_vector(const float* __restrict__ pos, const float* __restrict__ vn,
+                                              const uint32_t* __restrict__ pred, const float* __restrict__ direction,
+                                              const int32_t* __restrict__ cut, uint32_t v3, F3& out) {
+  const uint32_t v1 = pred[v3];
+  if (v1 == v3 || (cut && cut[v3] < 0)) return false;
+  F3 v = f3sub(f3load(pos, v1), f3load(pos, v3));
+  if (direction) {   // rotate about the vertex normal by the stored angle (Rodrigues; lvr2 BaseVector::rotated)
+    const F3 n = f3load(vn, v3);
+    const double alpha = (double)direction[v3];
+    const float sina = (float)sin(alpha), cosa = (float)cos(alpha);
+    const float ndotv = f3dot(n, v);
+    const F3 c = f3cross(n, v);
+    v = {v.x * cosa + c.x * sina + n.x * ndotv * (1.0f - cosa), v.y * cosa + c.y * sina + n.y * ndotv * (1.0f - cosa),
+         v.z * cosa + c.z * sina + n.z * ndotv * (1.0f - cosa)};
+  }
+  out = f3normalized(v);
+  return true;
+}
+
+__global__ void k_vector_map(const float* __restrict__ pos, const float* __restrict__ vn, const uint32_t* __restrict__ pred,
+                             const float* __restrict__ direction, const int32_t* __restrict__ cut, uint32_t V,
+                             float* __restrict__ out) {
+  const uint32_t v3 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v3 >= V) return;
+  const float nan = __int_as_float(0x7fc00000);
+  F3 v{nan, nan, nan};
+  vertex_vector(pos, vn, pred, direction, cut, v3, v);
+  float* o = out + 3 * (size_t)v3;
+  o[0] = v.x; o[1] = v.y; o[2] = v.z;
+}
+
+// ============================================================================
+// Vector-field back-tracking (cvp_mesh_planner.cpp:920-951): MeshMap::meshAhead (mesh_map.cpp:1070-1108),
+// searchNeighbourFaces (:999-1068), directionAtPosition (:625-650), projectedBarycentricCoords (util.cpp:313-347).
+// A strictly sequential walk of a few hundred steps: one thread follows the field on the device-resident result of
+// the last plan, so a makePlan moves a few KB of poses over PCIe instead of four V-sized arrays.
+// ============================================================================
+struct BacktrackArgs {
+  const float* pos; const float* vn; const uint32_t* faces; const uint32_t* cor_ptr; const int4* cor_idx;
+  const uint32_t* pred; const float* direction; const int32_t* cut;
+  float start[3]; uint32_t start_face; float goal[3]; uint32_t goal_face;
+  double step_width; uint32_t max_points;
+  float* path_pos; uint32_t* path_face; int32_t* result /* [0] outcome, [1] n_points */; const int* cancel_flag;
+};
+
+__device__ __forceinline__ bool projected_barycentric(F3 p, F3 a, F3 b, F3 c, float bary[3], float& dist) {
+  const F3 u = f3sub(b, a), v = f3sub(c, a), w = f3sub(p, a), n = f3cross(u, v);
+  const float oneOver4ASquared = (float)(1.0 / (double)f3dot(n, n));
+  const float gamma = f3dot(f3cross(u, w), n) * oneOver4ASquared;
+  const float beta = f3dot(f3cross(w, v), n) * oneOver4ASquared;
+  const float alpha = 1 - gamma - beta;
+  bary[0] = alpha; bary[1] = beta; bary[2] = gamma;
+  dist = f3dot(n, w) / sqrtf(f3dot(n, n));
+  const float EPSILON = 0.01f;
+  return (0 - EPSILON <= alpha) && (alpha <= 1 + EPSILON) && (0 - EPSILON <= beta) && (beta <= 1 + EPSILON) &&
+         (0 - EPSILON <= gamma) && (gamma <= 1 + EPSILON);
+}
+
+constexpr int BT_LIST_CAP = 4096;
+
+__global__ void __launch_bounds__(32) k_backtrack(BacktrackArgs a) {
+  __shared__ uint32_t possible[BT_LIST_CAP];
+  if (threadIdx.x != 0) return;
+  uint32_t n = 0;
+  auto push = [&](F3 p, uint32_t f) {
+    if (n < a.max_points) { a.path_pos[3 * n] = p.x; a.path_pos[3 * n + 1] = p.y; a.path_pos[3 * n + 2] = p.z; a.path_face[n] = f; }
+    ++n;
+  };
+  uint32_t face = a.goal_face;
+  F3 pos{a.goal[0], a.goal[1], a.goal[2]};
+  const F3 st{a.start[0], a.start[1], a.start[2]};
+  const float step = (float)a.step_width;
+  push(pos, face);
+  int32_t outcome = MNB_SUCCESS;
+  for (;;) {
+    const F3 d = f3sub(pos, st);
+    if (!((double)f3dot(d, d) > a.step_width)) break;                            // cvp:925 (distance2 vs step_width, as written)
+    if (a.cancel_flag && *(volatile const int*)a.cancel_flag) { outcome = MNB_CANCELED; break; }
+    if (n + 1 >= a.max_points) { outcome = MNB_E_STATE; break; }
+    // ---- meshAhead ----
+    float bary[3], dist;
+    const uint32_t* t = a.faces + 3 * (size_t)face;
+    bool ok = projected_barycentric(pos, f3load(a.pos, t[0]), f3load(a.pos, t[1]), f3load(a.pos, t[2]), bary, dist);
+    if (!ok) {                                                                    // searchNeighbourFaces(pos, face, step, 0.4)
+      F3 center{0, 0, 0};
+      for (int k = 0; k < 3; ++k) { const F3 q = f3load(a.pos, t[k]); center = {center.x + q.x, center.y + q.y, center.z + q.z}; }
+      center = {center.x / 3, center.y / 3, center.z / 3};
+      float vcm = 0;
+      for (int k = 0; k < 3; ++k) { const F3 e = f3sub(f3load(a.pos, t[k]), center); vcm = fmaxf(vcm, sqrtf(f3dot(e, e))); }
+      const float ext = step + vcm, rsq = ext * ext;
+      uint32_t cnt = 1; possible[0] = face;
+      bool overflow = false;
+      for (uint32_t it = 0; it < cnt && !ok; ++it) {
+        const uint32_t* q = a.faces + 3 * (size_t)possible[it];
+        if (projected_barycentric(pos, f3load(a.pos, q[0]), f3load(a.pos, q[1]), f3load(a.pos, q[2]), bary, dist) && fabsf(dist) < 0.4f) {
+          face = possible[it]; ok = true; break;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const F3 e = f3sub(center, f3load(a.pos, q[k]));
+          if (!(f3dot(e, e) < rsq)) continue;
+          for (uint32_t j = a.cor_ptr[q[k]]; j < a.cor_ptr[q[k] + 1]; ++j) {
+            const uint32_t nf = (uint32_t)a.cor_idx[j].z;
+            bool seen = false;
+            for (uint32_t s = 0; s < cnt; ++s) if (possible[s] == nf) { seen = true; break; }
+            if (seen) continue;
+            if (cnt >= BT_LIST_CAP) { overflow = true; continue; }
+            possible[cnt++] = nf;
+          }
+        }
+      }
+      if (!ok) { outcome = overflow ? MNB_E_STATE : MNB_NO_PATH_FOUND; break; }
+      t = a.faces + 3 * (size_t)face;
+      const F3 A = f3load(a.pos, t[0]), B = f3load(a.pos, t[1]), C = f3load(a.pos, t[2]);   // project onto the surface
+      pos = {A.x * bary[0] + B.x * bary[1] + C.x * bary[2], A.y * bary[0] + B.y * bary[1] + C.y * bary[2],
+             A.z * bary[0] + B.z * bary[1] + C.z * bary[2]};
+    }
+    // ---- directionAtPosition ----
+    bool any = false;
+    F3 vec{0, 0, 0};
+    for (int k = 0; k < 3; ++k) {
+      F3 e;
+      if (!vertex_vector(a.pos, a.vn, a.pred, a.direction, a.cut, t[k], e)) continue;
+      any = true;
+      vec = {vec.x + e.x * bary[k], vec.y + e.y * bary[k], vec.z + e.z * bary[k]};
+    }
+    if (!any || !(isfinite(vec.x) && isfinite(vec.y) && isfinite(vec.z))) { outcome = MNB_NO_PATH_FOUND; break; }
+    const F3 dir = f3normalized(f3normalized(vec));      // .normalized(); += zero layer fields; .normalize()
+    pos = {pos.x + dir.x * step, pos.y + dir.y * step, pos.z + dir.z * step};
+    push(pos, face);
+  }
+  if (outcome == MNB_SUCCESS) push(st, a.start_face);                            // cvp:951
+  a.result[0] = outcome; a.result[1] = (int32_t)n;
+}
+
+// ============================================================================
 // InflationLayer::waveCostInflation (inflation_layer.cpp:341-491): whole-grid cooperative kernel
 // (multi-source: few, very wide rounds) + fading epilogue (:482-490, :315-339)
 // ============================================================================
@@ -591,6 +741,10 @@ struct mnb_ctx {
   float* d_face_normals = nullptr; float* d_vertex_normals = nullptr; uint8_t* d_border = nullptr;
   float* d_layer_costs = nullptr; float* d_layer_combined = nullptr; uint8_t* d_layer_mask = nullptr; float* d_clearance = nullptr;
   unsigned int* d_overflow = nullptr;
+  // device-resident result of the last single CVP plan (for mnb_cvp_backtrack)
+  const uint32_t* last_pred = nullptr; const float* last_dir = nullptr; const int32_t* last_cut = nullptr;
+  uint32_t last_seed_face = 0; float last_seed_pos[3] = {0, 0, 0}; bool last_valid = false;
+  float* d_path_pos = nullptr; uint32_t* d_path_face = nullptr; int32_t* d_bt_result = nullptr; uint32_t path_cap = 0;
   uint32_t* d_lethals = nullptr; uint32_t lethal_cap = 0; uint8_t* d_infl_invalid = nullptr; float* d_out_cost = nullptr;
   // tuning
   float delta = 0.3f; int cluster = -1 /* -1: whole-grid cooperative kernel for single plans */; int batch_cluster = 1; int threads = 512;
@@ -621,6 +775,7 @@ static void free_mesh(mnb_ctx* c) {
   c->ws_groups = 0;
   dfree(c->d_out_dist); c->out_dist_cap = 0; dfree(c->d_out_pred); dfree(c->d_out_dir); dfree(c->d_out_cut);
   dfree(c->d_infl_invalid); dfree(c->d_out_cost);
+  dfree(c->d_path_pos); dfree(c->d_path_face); dfree(c->d_bt_result); c->path_cap = 0; c->last_valid = false;
   dfree(c->d_face_normals); dfree(c->d_vertex_normals); dfree(c->d_border); dfree(c->d_layer_costs); dfree(c->d_layer_combined);
   dfree(c->d_layer_mask); dfree(c->d_clearance); dfree(c->d_overflow);
   c->costs_set = false;
@@ -958,8 +1113,12 @@ int32_t mnb_cvp(mnb_ctx* ctx, uint32_t seed_face, const float seed_pos[3], int64
     for (int k = 0; k < 3; ++k)
       CK(cudaMemcpyAsync(&rp[k], a.out_pred + rf[k], sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   }
+  ctx->last_valid = false;
   if ((rc = finish_stats(ctx, 1, 2)) != MNB_OK) return rc;
   if (ctx->h_cancel && *ctx->h_cancel) return MNB_CANCELED;
+  ctx->last_pred = a.out_pred; ctx->last_dir = a.out_dir; ctx->last_cut = a.out_cut; ctx->last_seed_face = seed_face;
+  for (int k = 0; k < 3; ++k) ctx->last_seed_pos[k] = seed_pos[k];
+  ctx->last_valid = true;
   if (robot_face >= 0) {
     bool any = false;
     for (int k = 0; k < 3; ++k) if (rp[k] != rf[k]) any = true;
@@ -1099,6 +1258,69 @@ int32_t mnb_compute_layers(mnb_ctx* ctx, const mnb_layer_params* params, const f
   ctx->stats = mnb_stats{}; ctx->stats.kernel_ms = ms; ctx->stats.kernel_launches = 1; ctx->stats.settled = ctx->V;
   if (ovf) { ctx->err = "layer neighbourhood exceeds the per-vertex scratch (radius too large for the mesh resolution)"; return MNB_E_NOMEM; }
   return MNB_OK;
+}
+
+int32_t mnb_vector_map(mnb_ctx* ctx, const uint32_t* pred, const float* direction, const int32_t* cutting_face, float* out_vec) {
+  if (!ctx || !ctx->V || !pred || !out_vec) return MNB_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const size_t V = ctx->V;
+  const bool dev = ctx->ptr_mode == MNB_PTR_DEVICE;
+  const uint32_t* d_pred = pred; const float* d_dir = direction; const int32_t* d_cut = cutting_face; float* d_out = out_vec;
+  float* tmp_out = nullptr; uint32_t* tmp_pred = nullptr; float* tmp_dir = nullptr; int32_t* tmp_cut = nullptr;
+  if (!dev) {
+    CK(dalloc(&tmp_out, 3 * V)); CK(dalloc(&tmp_pred, V));
+    CK(cudaMemcpyAsync(tmp_pred, pred, sizeof(uint32_t) * V, cudaMemcpyHostToDevice, ctx->stream));
+    d_pred = tmp_pred; d_out = tmp_out;
+    if (direction) { CK(dalloc(&tmp_dir, V)); CK(cudaMemcpyAsync(tmp_dir, direction, sizeof(float) * V, cudaMemcpyHostToDevice, ctx->stream)); d_dir = tmp_dir; }
+    if (cutting_face) { CK(dalloc(&tmp_cut, V)); CK(cudaMemcpyAsync(tmp_cut, cutting_face, sizeof(int32_t) * V, cudaMemcpyHostToDevice, ctx->stream)); d_cut = tmp_cut; }
+  }
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  k_vector_map<<<(ctx->V + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_pos, ctx->d_vertex_normals, d_pred, d_dir, d_cut, ctx->V, d_out);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (!dev) CK(cudaMemcpyAsync(out_vec, d_out, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  dfree(tmp_out); dfree(tmp_pred); dfree(tmp_dir); dfree(tmp_cut);
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->stats = mnb_stats{}; ctx->stats.kernel_ms = ms; ctx->stats.kernel_launches = 1; ctx->stats.settled = ctx->V;
+  return MNB_OK;
+}
+
+int32_t mnb_cvp_backtrack(mnb_ctx* ctx, const float robot_pos[3], uint32_t robot_face, double step_width, uint32_t max_points,
+                          float* path_pos, uint32_t* path_face, uint32_t* n_points) {
+  if (!ctx || !ctx->V || !robot_pos || !path_pos || !n_points || max_points < 2) return MNB_E_ARG;
+  if (!ctx->last_valid) { ctx->err = "mnb_cvp_backtrack needs a preceding successful mnb_cvp on this context"; return MNB_E_STATE; }
+  if (robot_face >= ctx->F) return MNB_INVALID_GOAL;
+  CK(cudaSetDevice(ctx->device));
+  if (max_points > ctx->path_cap) {
+    dfree(ctx->d_path_pos); dfree(ctx->d_path_face); ctx->path_cap = 0;
+    CK(dalloc(&ctx->d_path_pos, 3 * (size_t)max_points)); CK(dalloc(&ctx->d_path_face, (size_t)max_points));
+    ctx->path_cap = max_points;
+  }
+  if (!ctx->d_bt_result) CK(dalloc(&ctx->d_bt_result, (size_t)2));
+  BacktrackArgs a{};
+  a.pos = ctx->d_pos; a.vn = ctx->d_vertex_normals; a.faces = ctx->d_faces; a.cor_ptr = ctx->d_cor_ptr; a.cor_idx = ctx->d_cor_idx;
+  a.pred = ctx->last_pred; a.direction = ctx->last_dir; a.cut = ctx->last_cut;
+  for (int k = 0; k < 3; ++k) { a.start[k] = ctx->last_seed_pos[k]; a.goal[k] = robot_pos[k]; }
+  a.start_face = ctx->last_seed_face; a.goal_face = robot_face; a.step_width = step_width; a.max_points = max_points;
+  a.path_pos = ctx->d_path_pos; a.path_face = ctx->d_path_face; a.result = ctx->d_bt_result; a.cancel_flag = ctx->d_cancel;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  k_backtrack<<<1, 32, 0, ctx->stream>>>(a);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  int32_t res[2] = {0, 0};
+  CK(cudaMemcpyAsync(res, ctx->d_bt_result, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const uint32_t n = (uint32_t)res[1] < max_points ? (uint32_t)res[1] : max_points;
+  *n_points = n;
+  const cudaMemcpyKind kind = ctx->ptr_mode == MNB_PTR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  CK(cudaMemcpyAsync(path_pos, ctx->d_path_pos, sizeof(float) * 3 * (size_t)n, kind, ctx->stream));
+  if (path_face) CK(cudaMemcpyAsync(path_face, ctx->d_path_face, sizeof(uint32_t) * (size_t)n, kind, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->stats = mnb_stats{}; ctx->stats.kernel_ms = ms; ctx->stats.kernel_launches = 1; ctx->stats.settled = n;
+  if (res[0] == MNB_E_STATE) { ctx->err = "back-tracking exceeded max_points (cyclic vector field?) or the face search list"; return MNB_E_STATE; }
+  return res[0];
 }
 
 // debugging aid (not part of the public header): raw labels {d, a1, a2, a3|flag} of wavefront group 0

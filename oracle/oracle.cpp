@@ -36,6 +36,7 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <unordered_set>
 #include <vector>
 
 namespace {
@@ -790,3 +791,161 @@ extern "C" void orc_layers(void* h, const OrcLayerParams* P, const float* vertex
 }
 
 
+
+// ---------------------------------------------------------------------------
+// DijkstraMeshPlanner::computeVectorMap  dijkstra_mesh_planner.cpp:189-209
+// vector_map[v3] = normalize(p[pred[v3]] - p[v3]) for pred != self; NaN = "not in the sparse map".
+// ---------------------------------------------------------------------------
+extern "C" void orc_dijkstra_vector_map(void* h, const uint32_t* predecessors, float* vector_map /*3V*/) {
+  OrcMesh& m = *(OrcMesh*)h;
+  const float nan = std::numeric_limits<float>::quiet_NaN();
+  for (uint32_t v3 = 0; v3 < m.V; ++v3) {
+    float* o = &vector_map[3 * (size_t)v3];
+    const uint32_t v1 = predecessors[v3];
+    if (v1 == v3) { o[0] = o[1] = o[2] = nan; continue; }
+    float d[3]; vsub(&m.pos[3 * (size_t)v1], &m.pos[3 * (size_t)v3], d);
+    vnormalize(d);
+    o[0] = d[0]; o[1] = d[1]; o[2] = d[2];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// CVPMeshPlanner::computeVectorMap  cvp_mesh_planner.cpp:204-239
+// vector_map[v3] = normalize(rotated(p[pred] - p[v3], axis = vertex_normal[v3], angle = direction[v3])), skipped if
+// pred == self or no cutting face.  lvr2::BaseVector::rotated is un-vendored: restated as the Rodrigues rotation
+// with sin/cos evaluated in double (the angle parameter is `const double&`) -- PARITY UNPINNED.
+// ---------------------------------------------------------------------------
+extern "C" void orc_cvp_vector_map(void* h, const float* vertex_normals, const uint32_t* predecessors, const float* direction,
+                                   const int32_t* cutting_faces, float* vector_map /*3V*/) {
+  OrcMesh& m = *(OrcMesh*)h;
+  const float nan = std::numeric_limits<float>::quiet_NaN();
+  for (uint32_t v3 = 0; v3 < m.V; ++v3) {
+    float* o = &vector_map[3 * (size_t)v3];
+    const uint32_t v1 = predecessors[v3];
+    if (v1 == v3 || cutting_faces[v3] < 0) { o[0] = o[1] = o[2] = nan; continue; }     // :218, :224
+    float v[3]; vsub(&m.pos[3 * (size_t)v1], &m.pos[3 * (size_t)v3], v);
+    const float* n = &vertex_normals[3 * (size_t)v3];
+    const double alpha = direction[v3];
+    const float sina = (float)sin(alpha), cosa = (float)cos(alpha);
+    const float ndotv = n[0] * v[0] + n[1] * v[1] + n[2] * v[2];
+    const float cx = n[1] * v[2] - n[2] * v[1], cy = n[2] * v[0] - n[0] * v[2], cz = n[0] * v[1] - n[1] * v[0];
+    float r[3] = {v[0] * cosa + cx * sina + n[0] * ndotv * (1.0f - cosa),
+                  v[1] * cosa + cy * sina + n[1] * ndotv * (1.0f - cosa),
+                  v[2] * cosa + cz * sina + n[2] * ndotv * (1.0f - cosa)};
+    vnormalize(r);
+    o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Vector-field back-tracking: CVPMeshPlanner::waveFrontPropagation cvp_mesh_planner.cpp:920-951 over
+// MeshMap::meshAhead mesh_map.cpp:1070-1108, searchNeighbourFaces :999-1068, directionAtPosition :625-650 and
+// projectedBarycentricCoords util.cpp:313-347.  Layer vector fields (AbstractLayer::vectorAt) contribute zero
+// (no layer with a repulsive field is built yet -- SURVEY f4).  lvr2's getFacesOfVertex order is un-vendored:
+// ascending face id here -- PARITY UNPINNED for the (rare) case of two faces both passing the inside test.
+// vector_map: 3V floats, NaN row = no entry.  The walk starts at the robot (the wave's `goal`) and ends at the
+// wave's seed (`start`); points are written in walk order.  Returns 0 SUCCESS / 54 NO_PATH_FOUND / -1 cap hit.
+// ---------------------------------------------------------------------------
+namespace {
+struct V3 { float x, y, z; };
+inline V3 sub3(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 cross3(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline float dot3(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline V3 P(const OrcMesh& m, uint32_t v) { return {m.pos[3 * (size_t)v], m.pos[3 * (size_t)v + 1], m.pos[3 * (size_t)v + 2]}; }
+
+// util.cpp:313-347
+inline bool projectedBarycentricCoords(V3 p, V3 a, V3 b, V3 c, float bary[3], float& dist) {
+  const V3 u = sub3(b, a), v = sub3(c, a), w = sub3(p, a), n = cross3(u, v);
+  const float oneOver4ASquared = (float)(1.0 / (double)dot3(n, n));
+  const float gamma = dot3(cross3(u, w), n) * oneOver4ASquared;
+  const float beta = dot3(cross3(w, v), n) * oneOver4ASquared;
+  const float alpha = 1 - gamma - beta;
+  bary[0] = alpha; bary[1] = beta; bary[2] = gamma;
+  dist = dot3(n, w) / std::sqrt(dot3(n, n));
+  const float EPSILON = 0.01f;
+  return (0 - EPSILON <= alpha) && (alpha <= 1 + EPSILON) && (0 - EPSILON <= beta) && (beta <= 1 + EPSILON) &&
+         (0 - EPSILON <= gamma) && (gamma <= 1 + EPSILON);
+}
+
+// mesh_map.cpp:999-1068
+inline bool searchNeighbourFaces(const OrcMesh& m, V3 pos, uint32_t face, float max_radius, float max_dist, uint32_t& face_out,
+                                 float bary[3]) {
+  std::vector<uint32_t> possible{face};
+  const uint32_t* fv = &m.faces[3 * (size_t)face];
+  V3 center{0, 0, 0};
+  for (int k = 0; k < 3; ++k) { const V3 q = P(m, fv[k]); center = {center.x + q.x, center.y + q.y, center.z + q.z}; }
+  center = {center.x / 3, center.y / 3, center.z / 3};
+  float vertex_center_max = 0;
+  for (int k = 0; k < 3; ++k) { const V3 d = sub3(P(m, fv[k]), center); vertex_center_max = std::max(vertex_center_max, std::sqrt(dot3(d, d))); }
+  const float ext_radius = max_radius + vertex_center_max;
+  const float max_radius_sq = ext_radius * ext_radius;
+  std::unordered_set<uint32_t> in_list{face};
+  for (size_t it = 0; it < possible.size(); ++it) {
+    const uint32_t* t = &m.faces[3 * (size_t)possible[it]];
+    float dist;
+    if (projectedBarycentricCoords(pos, P(m, t[0]), P(m, t[1]), P(m, t[2]), bary, dist) && std::fabs(dist) < max_dist) {
+      face_out = possible[it];
+      return true;
+    }
+    for (int k = 0; k < 3; ++k) {
+      const V3 d = sub3(center, P(m, t[k]));
+      if (dot3(d, d) < max_radius_sq)
+        for (uint32_t j = m.vf_ptr[t[k]]; j < m.vf_ptr[t[k] + 1]; ++j)
+          if (in_list.insert(m.vf_face[j]).second) possible.push_back(m.vf_face[j]);
+    }
+  }
+  return false;
+}
+
+// mesh_map.cpp:1070-1108 (+ directionAtPosition :625-650)
+inline bool meshAhead(const OrcMesh& m, const float* vector_map, V3& pos, uint32_t& face, float step_size) {
+  float bary[3], dist;
+  const uint32_t* t = &m.faces[3 * (size_t)face];
+  if (projectedBarycentricCoords(pos, P(m, t[0]), P(m, t[1]), P(m, t[2]), bary, dist)) {
+  } else if (searchNeighbourFaces(m, pos, face, step_size, 0.4f, face, bary)) {
+    t = &m.faces[3 * (size_t)face];
+    const V3 a = P(m, t[0]), b = P(m, t[1]), c = P(m, t[2]);      // linearCombineBarycentricCoords util.h:179-184
+    pos = {a.x * bary[0] + b.x * bary[1] + c.x * bary[2], a.y * bary[0] + b.y * bary[1] + c.y * bary[2],
+           a.z * bary[0] + b.z * bary[1] + c.z * bary[2]};
+  } else {
+    return false;
+  }
+  bool any = false;
+  V3 vec{0, 0, 0};
+  for (int k = 0; k < 3; ++k) {
+    const float* e = &vector_map[3 * (size_t)t[k]];
+    if (std::isnan(e[0])) continue;
+    any = true;
+    vec = {vec.x + e[0] * bary[k], vec.y + e[1] * bary[k], vec.z + e[2] * bary[k]};
+  }
+  if (!any || !(std::isfinite(vec.x) && std::isfinite(vec.y) && std::isfinite(vec.z))) return false;
+  float d[3] = {vec.x, vec.y, vec.z};
+  vnormalize(d);          // opt_dir.normalized()
+  vnormalize(d);          // dir += (zero layer fields); dir.normalize()
+  pos = {pos.x + d[0] * step_size, pos.y + d[1] * step_size, pos.z + d[2] * step_size};
+  return true;
+}
+}  // namespace
+
+extern "C" int32_t orc_cvp_backtrack(void* h, const float* vector_map, const float start[3], uint32_t start_face, const float goal[3],
+                                     uint32_t goal_face, double step_width, uint32_t max_points, float* path_pos, uint32_t* path_face,
+                                     uint32_t* n_points) {
+  const OrcMesh& m = *(OrcMesh*)h;
+  uint32_t n = 0;
+  auto push = [&](V3 p, uint32_t f) { if (n < max_points) { path_pos[3 * n] = p.x; path_pos[3 * n + 1] = p.y; path_pos[3 * n + 2] = p.z; path_face[n] = f; } ++n; };
+  uint32_t current_face = goal_face;                                                    // :920
+  V3 current_pos{goal[0], goal[1], goal[2]};
+  const V3 st{start[0], start[1], start[2]};
+  push(current_pos, current_face);
+  const float sw = (float)step_width;
+  for (;;) {
+    const V3 d = sub3(current_pos, st);
+    if (!((double)dot3(d, d) > step_width)) break;                                      // :925 distance2 vs step_width
+    if (n + 1 >= max_points) { *n_points = n; return -1; }
+    if (!meshAhead(m, vector_map, current_pos, current_face, sw)) { *n_points = n; return 54; }   // :938-941
+    push(current_pos, current_face);
+  }
+  push(st, start_face);                                                                 // :951
+  *n_points = n;
+  return 0;
+}

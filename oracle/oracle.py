@@ -53,6 +53,10 @@ def lib():
         L.orc_fading.argtypes = [dbl, dbl, dbl, dbl, dbl, f32]
         L.orc_sethian_update.restype = f32
         L.orc_sethian_update.argtypes = [f32] * 6
+        L.orc_cvp_backtrack.restype = C.c_int32
+        L.orc_cvp_backtrack.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_uint32, C.c_double, C.c_uint32, vp, vp, vp]
+        L.orc_dijkstra_vector_map.argtypes = [vp, vp, vp]
+        L.orc_cvp_vector_map.argtypes = [vp, vp, vp, vp, vp, vp]
         L.orc_normals.argtypes = [vp, vp, vp]
         L.orc_layers.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.orc_inflation.argtypes = [vp, vp, vp, vp, u32, dbl, dbl, dbl, dbl, dbl, C.c_int, vp, vp, vp, vp]
@@ -181,6 +185,36 @@ def _layers(self, params=None, clearance=None):
 
 
 OracleMesh.layers = _layers
+
+
+def _dijkstra_vector_map(self, pred):
+    out = np.empty((self.V, 3), np.float32)
+    lib().orc_dijkstra_vector_map(self._h, _p(np.ascontiguousarray(pred, dtype=np.uint32)), _p(out))
+    return out
+
+
+def _cvp_vector_map(self, vertex_normals, pred, direction, cutting_face):
+    out = np.empty((self.V, 3), np.float32)
+    lib().orc_cvp_vector_map(self._h, _p(np.ascontiguousarray(vertex_normals, dtype=np.float32)),
+                             _p(np.ascontiguousarray(pred, dtype=np.uint32)), _p(np.ascontiguousarray(direction, dtype=np.float32)),
+                             _p(np.ascontiguousarray(cutting_face, dtype=np.int32)), _p(out))
+    return out
+
+
+def _cvp_backtrack(self, vector_map, start, start_face, goal, goal_face, step_width=0.4, max_points=100000):
+    """cvp:920-951: walk from `goal` (robot) down the field to `start` (wave seed); returns (outcome, positions, faces)"""
+    vm = np.ascontiguousarray(vector_map, dtype=np.float32)
+    st = np.ascontiguousarray(start, dtype=np.float32); go = np.ascontiguousarray(goal, dtype=np.float32)
+    pp = np.empty((max_points, 3), np.float32); pf = np.empty(max_points, np.uint32); n = C.c_uint32(0)
+    rc = lib().orc_cvp_backtrack(self._h, _p(vm), _p(st), int(start_face), _p(go), int(goal_face), float(step_width),
+                                 int(max_points), _p(pp), _p(pf), C.byref(n))
+    k = min(n.value, max_points)
+    return rc, pp[:k].copy(), pf[:k].copy()
+
+
+OracleMesh.cvp_backtrack = _cvp_backtrack
+OracleMesh.dijkstra_vector_map = _dijkstra_vector_map
+OracleMesh.cvp_vector_map = _cvp_vector_map
 
 
 def fading(distance, inscribed_radius=0.25, inflation_radius=0.4, lethal_value=1.0, inscribed_value=0.99,

@@ -17,6 +17,8 @@ void orc_edge_distances(void* h, float* out);
 uint32_t orc_dijkstra(void* h, const float* edge_weights, const float* vertex_costs, const uint8_t* invalid, uint32_t seed_vertex,
                       int64_t robot_vertex, double cost_limit, double goal_dist_offset, int canonical_ties, float* distances,
                       uint32_t* predecessors, double* stats);
+int32_t orc_cvp_backtrack(void* h, const float* vector_map, const float start[3], uint32_t start_face, const float goal[3],
+                          uint32_t goal_face, double step_width, uint32_t max_points, float* path_pos, uint32_t* path_face, uint32_t* n_points);
 uint32_t orc_cvp(void* h, const float* edge_weights, const float* vertex_costs, const uint8_t* invalid, uint32_t seed_face,
                  const float* seed_pos, int64_t robot_face, double cost_limit, double goal_dist_offset, int canonical_ties,
                  float* distances, uint32_t* predecessors, float* direction, int32_t* cutting_faces, double* stats);
@@ -72,7 +74,19 @@ int main() {
   CHECK(cvp.makePlan(robot, goal, 0.1, plan, cost, msg) == NO_PATH_FOUND);
   std::fill(map->vertexCosts().begin(), map->vertexCosts().end(), 0.0f);
   plan.clear();
-  CHECK(cvp.makePlan(robot, goal, 0.1, plan, cost, msg) == SUCCESS && cost > 6.0);
+  CHECK(cvp.makePlan(robot, goal, 0.1, plan, cost, msg) == SUCCESS && cost > 6.0 && cost < 8.5);
+  // vector-field back-tracking (cvp:920-951): robot first, goal last, steps of step_width, smoother than the edge path
+  CHECK(plan.size() > 12 && length(plan.front().position - robot.position) == 0.0f && length(plan.back().position - goal.position) == 0.0f);
+  for (size_t i = 0; i + 2 < plan.size(); ++i) CHECK(length(plan[i + 1].position - plan[i].position) < 0.65f);
+  {
+    // the same walk by the oracle on the GPU's vector map is bit-identical
+    const int64_t sfo = map->getContainingFace(goal.position, 0.4f), rfo = map->getContainingFace(robot.position, 0.4f);
+    std::vector<float> pp(3 * 4096); std::vector<uint32_t> pf(4096); uint32_t np = 0;
+    const float s3[3] = {goal.position.x, goal.position.y, goal.position.z}, g3[3] = {robot.position.x, robot.position.y, robot.position.z};
+    CHECK(orc_cvp_backtrack(om, &cvp.getVectorMap()[0].x, s3, (uint32_t)sfo, g3, (uint32_t)rfo, 0.4, 4096, pp.data(), pf.data(), &np) == 0);
+    CHECK(np == plan.size());
+    for (uint32_t i = 0; i < np; ++i) CHECK(std::memcmp(&pp[3 * i], &plan[i].position.x, 12) == 0);
+  }
   std::vector<float> cd(V), cdir(V); std::vector<uint32_t> cp(V); std::vector<int32_t> cc(V);
   const int64_t sf = map->getContainingFace(goal.position, 0.4f), rf = map->getContainingFace(robot.position, 0.4f);
   const float sp[3] = {goal.position.x, goal.position.y, goal.position.z};

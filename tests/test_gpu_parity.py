@@ -401,3 +401,93 @@ def test_cancel_returns_canceled(api, oracle_mod):
     mm.set_tuning(0.3, -1, 0)
     assert api.CVPMeshPlanner(mm).waveFrontPropagation(f, sp)["outcome"] == 0     # the flag is reset per plan (cvp:679)
     mm.close()
+
+
+def test_vector_maps(api, oracle_mod):
+    """a2 DijkstraMeshPlanner::computeVectorMap (:189-209) and a6 CVPMeshPlanner::computeVectorMap (:204-239)"""
+    pos, faces, om, mm, ed, vc, w = setup(api, oracle_mod, 150, True)
+    v, f, sp = centre_seed(pos, faces, (0.4, 0.6))
+    gd = api.DijkstraMeshPlanner(mm).dijkstra(v)
+    ref = om.dijkstra_vector_map(gd["pred"]); got = api.DijkstraMeshPlanner(mm).computeVectorMap(gd["pred"])
+    assert (np.isnan(ref) == np.isnan(got)).all() and np.isnan(got[v]).all()
+    ok = ~np.isnan(ref)
+    assert (got[ok].view(np.uint32) == ref[ok].view(np.uint32)).all()                 # no transcendental: bit-identical
+    gc = api.CVPMeshPlanner(mm).waveFrontPropagation(f, sp)
+    vn = om.layers()["vertex_normals"]
+    ref = om.cvp_vector_map(vn, gc["pred"], gc["direction"], gc["cutting_face"])
+    got = api.CVPMeshPlanner(mm).computeVectorMap(gc["pred"], gc["direction"], gc["cutting_face"])
+    assert (np.isnan(ref) == np.isnan(got)).all()
+    ok = ~np.isnan(ref)
+    assert np.abs(got[ok] - ref[ok]).max() <= 2e-6                                     # sin/cos: CUDA vs glibc, last-bit
+    assert np.allclose(np.linalg.norm(got.reshape(-1, 3)[~np.isnan(got).any(1)], axis=1), 1.0, atol=1e-5)
+    # the field points down the potential: following it one edge towards the predecessor lowers the potential
+    nz = gc["pred"] != np.arange(om.V)
+    assert (gc["dist"][gc["pred"][nz]] < gc["dist"][nz] + 1e-6).mean() > 0.99
+    mm.close()
+
+
+def _backtrack_case(api, oracle_mod, n, weighted, seed_uv, robot_uv, terrain=True):
+    costs = (lambda p: 0.45 + 0.45 * np.sin(3.0 * p[:, 0]) * np.cos(2.0 * p[:, 1])) if weighted else None
+    pos, faces, om, mm, ed, vc, w = setup(api, oracle_mod, n, True, costs=costs, factor=1.0 if weighted else 0.0)
+    sv, sf, sp = centre_seed(pos, faces, seed_uv)
+    rv, rf, rp = centre_seed(pos, faces, robot_uv)
+    pl = api.CVPMeshPlanner(mm)
+    g = pl.waveFrontPropagation(sf, sp, rf)
+    assert g["outcome"] == 0
+    vm = pl.computeVectorMap(g["pred"], g["direction"], g["cutting_face"])
+    bt = pl.backtrack(rp, rf)
+    # oracle walk on the GPU's vector map: same float arithmetic, no transcendental -> bit-identical
+    rc, opos, oface = om.cvp_backtrack(vm, sp, sf, rp, rf, 0.4)
+    return pos, faces, om, mm, pl, g, vm, bt, (rc, opos, oface), (sf, sp, rf, rp, vc, w)
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_backtrack_parity(api, oracle_mod, weighted):
+    """f1: cvp:920-951 back-tracking over MeshMap::meshAhead; GPU walk == oracle walk on the same field"""
+    pos, faces, om, mm, pl, g, vm, bt, (rc, opos, oface), (sf, sp, rf, rp, vc, w) = _backtrack_case(
+        api, oracle_mod, 200, weighted, (0.2, 0.25), (0.8, 0.7))
+    assert rc == 0 and bt["outcome"] == 0
+    assert len(bt["positions"]) == len(opos) and len(opos) > 10
+    assert (bt["positions"].view(np.uint32) == opos.view(np.uint32)).all()
+    assert (bt["faces"] == oface).all()
+    p = bt["positions"]
+    assert (p[0] == rp).all() and (p[-1] == sp).all() and bt["faces"][0] == rf and bt["faces"][-1] == sf
+    seg = np.linalg.norm(np.diff(p, axis=0), axis=1)
+    assert seg[:-1].max() <= 0.4 * 1.5 + 1e-3          # step_width (+ the projection onto a neighbour face)
+    # the walk descends the potential: path length ~ potential at the robot (geodesic), never shorter than the chord
+    length = seg.sum()
+    chord = np.linalg.norm(rp - sp)
+    pot_robot = g["dist"][faces[rf]].mean()
+    assert chord * 0.999 <= length
+    if not weighted:
+        assert length <= pot_robot * 1.10 + 0.8
+    # end-to-end with the oracle's own wavefront + vector map (sin/cos last-bit differences only)
+    o = om.cvp(w, vc, sf, sp, rf)
+    ovm = om.cvp_vector_map(om.layers()["vertex_normals"], o["pred"], o["direction"], o["cutting_face"])
+    rc2, opos2, _ = om.cvp_backtrack(ovm, sp, sf, rp, rf, 0.4)
+    assert rc2 == 0 and len(opos2) == len(p)
+    assert np.abs(opos2 - p).max() <= 1e-3
+    mm.close()
+
+
+def test_make_plan_path_only(api, oracle_mod):
+    """makePlan keeps the four V-sized maps on the device; the path alone crosses PCIe"""
+    pos, faces, om, mm, ed, vc, w = setup(api, oracle_mod, 160, False)
+    gv, gf, gp = centre_seed(pos, faces, (0.75, 0.3))
+    sv, sf, sp = centre_seed(pos, faces, (0.15, 0.8))
+    pl = api.CVPMeshPlanner(mm)
+    r = pl.makePlan(sp, sf, gp, gf)
+    assert r["outcome"] == 0 and (r["positions"][0] == sp).all() and (r["positions"][-1] == gp).all()
+    g = pl.waveFrontPropagation(gf, gp, sf)
+    vm = pl.computeVectorMap(g["pred"], g["direction"], g["cutting_face"])
+    rc, opos, oface = om.cvp_backtrack(vm, gp, gf, sp, sf, 0.4)
+    assert rc == 0 and (opos.view(np.uint32) == r["positions"].view(np.uint32)).all()
+    assert abs(r["cost"] - np.linalg.norm(np.diff(opos, axis=0), axis=1).sum()) < 1e-3
+    mm.close()
+
+
+def test_backtrack_needs_plan(api, oracle_mod):
+    pos, faces, om, mm, ed, vc, w = setup(api, oracle_mod, 40, False)
+    with pytest.raises(RuntimeError):
+        api.CVPMeshPlanner(mm).backtrack(pos[0], 0)
+    mm.close()
