@@ -146,6 +146,14 @@ int32_t mnb_compute_layers(mnb_ctx* ctx, const mnb_layer_params* params, const f
 /* lvr2::calcVertexNormals equivalent (mesh_map.cpp:374): normalised sum of incident face normals */
 int32_t mnb_get_vertex_normals(mnb_ctx* ctx, float* out_normals /* 3V */);
 
+/* ---- localisation -----------------------------------------------------------------------------------
+ * MeshMap::getNearestVertexHandle (mesh_map.cpp:1161-1174) and MeshMap::searchContainingFace / getContainingFace
+ * (mesh_map.cpp:1110-1159) for n query points at once: out_vertex[q] = nearest vertex (exhaustive, ties to the lowest
+ * id), out_face[q] = the incident face of that vertex containing the projected point (-1: none), out_bary its
+ * barycentric coordinates.  Any of the outputs may be NULL. */
+int32_t mnb_locate(mnb_ctx* ctx, uint32_t n, const float* points /* 3n */, uint32_t* out_vertex /* n */,
+                   int32_t* out_face /* n */, float* out_bary /* 3n */);
+
 /* ---- vector-field epilogues -----------------------------------------------------------------------
  * DijkstraMeshPlanner::computeVectorMap (dijkstra_mesh_planner.cpp:189-209): direction == NULL, cutting_face == NULL:
  *   out[v] = normalize(p[pred[v]] - p[v]).

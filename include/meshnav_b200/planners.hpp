@@ -71,27 +71,23 @@ class MeshMap {
   // pushes vertex_costs / edge_weights / invalid the way the planners read them (cvp:245,663-664)
   bool syncCosts() { return mnb_set_costs(ctx_, vertex_costs_.data(), edge_weights_.data(), invalid_.data()) == MNB_OK; }
 
-  // MeshMap::getNearestVertexHandle (mesh_map.cpp:1161-1174): exhaustive 1-NN on the host (SURVEY f2 "next" row)
+  // MeshMap::getNearestVertexHandle (mesh_map.cpp:1161-1174): one streamed pass over the device-resident positions
   int64_t getNearestVertexHandle(const Vector& p) const {
-    int64_t best = -1; float bd = std::numeric_limits<float>::infinity();
-    for (uint32_t v = 0; v < numVertices(); ++v) { const float d = length(vertexPosition(v) - p); if (d < bd) { bd = d; best = v; } }
-    return best;
+    uint32_t v = 0;
+    return mnb_locate(ctx_, 1, &p.x, &v, nullptr, nullptr) == MNB_OK ? (int64_t)v : -1;
   }
-  // MeshMap::getContainingFace (mesh_map.cpp:1110-1159), simplified: a face of the nearest vertex whose
-  // centroid is closest to the point; max_dist as in the reference call (cvp:673, 0.4 m)
-  int64_t getContainingFace(const Vector& p, float max_dist) const {
-    const int64_t v = getNearestVertexHandle(p);
-    if (v < 0 || length(vertexPosition((uint32_t)v) - p) > max_dist) return -1;
-    int64_t best = -1; float bd = std::numeric_limits<float>::infinity();
-    for (uint32_t f = 0; f < numFaces(); ++f) {
-      const uint32_t* t = &faces_[3 * (size_t)f];
-      if (t[0] != (uint32_t)v && t[1] != (uint32_t)v && t[2] != (uint32_t)v) continue;
-      const Vector a = vertexPosition(t[0]), b = vertexPosition(t[1]), c = vertexPosition(t[2]);
-      const Vector cen{(a.x + b.x + c.x) / 3, (a.y + b.y + c.y) / 3, (a.z + b.z + c.z) / 3};
-      const float d = length(cen - p);
-      if (d < bd) { bd = d; best = f; }
-    }
-    return best;
+  // MeshMap::getContainingFace / searchContainingFace (mesh_map.cpp:1110-1159); like the reference, max_dist is
+  // accepted but not consulted.  -1 = no containing face.
+  int64_t getContainingFace(const Vector& p, float /*max_dist*/) const {
+    int32_t f = -1;
+    return mnb_locate(ctx_, 1, &p.x, nullptr, &f, nullptr) == MNB_OK ? (int64_t)f : -1;
+  }
+  // MeshMap::searchContainingFace (mesh_map.cpp:1120-1159) with the barycentric coordinates
+  bool searchContainingFace(const Vector& p, uint32_t& face, float bary[3]) const {
+    int32_t f = -1;
+    if (mnb_locate(ctx_, 1, &p.x, nullptr, &f, bary) != MNB_OK || f < 0) return false;
+    face = (uint32_t)f;
+    return true;
   }
 
  private:

@@ -120,6 +120,22 @@ class MeshMap:
         r.update(combined=comb, lethal_mask=mask, **self.stats())
         return r
 
+    def locate(self, points):
+        """getNearestVertexHandle + searchContainingFace (mesh_map.cpp:1110-1174) for a batch of points ->
+        (nearest vertex u32[n], containing face i32[n] (-1 none), barycentric coords f32[n,3])"""
+        pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+        n = pts.shape[0]
+        nv = np.empty(n, np.uint32); fc = np.empty(n, np.int32); ba = np.empty((n, 3), np.float32)
+        self._check(self.L.mnb_locate(self._ctx, n, _p(pts), _p(nv), _p(fc), _p(ba)))
+        return nv, fc, ba
+
+    def getNearestVertexHandle(self, p) -> int:
+        return int(self.locate(p)[0][0])
+
+    def getContainingFace(self, p, max_dist: float = 0.4) -> int:
+        """-1 = no containing face; max_dist is accepted and (like the reference, mesh_map.cpp:1120-1159) not consulted"""
+        return int(self.locate(p)[1][0])
+
     def vectorMap(self, pred, direction=None, cutting_face=None) -> np.ndarray:
         """computeVectorMap of the planners (dijkstra:189-209 with direction=None, cvp:204-239 otherwise)"""
         pr = np.ascontiguousarray(pred, dtype=np.uint32)

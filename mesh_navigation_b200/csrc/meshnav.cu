@@ -654,6 +654,73 @@ __global__ void __launch_bounds__(32) k_backtrack(BacktrackArgs a) {
 }
 
 // ============================================================================
+// Localisation: MeshMap::getNearestVertexHandle (mesh_map.cpp:1161-1174; the reference walks a nanoflann KD-tree,
+// here the 12 B/vertex position array is streamed once for ALL queries of the call -- HBM-bound, ~8 us per 5M-vertex
+// pass) and MeshMap::searchContainingFace (mesh_map.cpp:1120-1159).
+// Key = (squared distance bits << 32) | vertex id: non-negative floats order like their bit patterns, so one 64-bit
+// atomicMin yields the nearest vertex with ties to the lowest id.
+// ============================================================================
+constexpr int LOC_Q = 32;       // queries per pass (registers)
+
+__global__ void __launch_bounds__(256) k_nearest_vertex(const float* __restrict__ pos, uint32_t V, const float* __restrict__ points,
+                                                        uint32_t q0, uint32_t nq, unsigned long long* __restrict__ keys) {
+  __shared__ float sq[3 * LOC_Q];
+  __shared__ unsigned long long sbest[LOC_Q];
+  if (threadIdx.x < 3 * nq) sq[threadIdx.x] = points[3 * (size_t)q0 + threadIdx.x];
+  if (threadIdx.x < LOC_Q) sbest[threadIdx.x] = ~0ull;
+  __syncthreads();
+  unsigned long long best[LOC_Q];
+#pragma unroll
+  for (int q = 0; q < LOC_Q; ++q) best[q] = ~0ull;
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+    const float x = pos[3 * (size_t)v], y = pos[3 * (size_t)v + 1], z = pos[3 * (size_t)v + 2];
+#pragma unroll
+    for (int q = 0; q < LOC_Q; ++q) {
+      if (q < (int)nq) {
+        const float dx = sq[3 * q] - x, dy = sq[3 * q + 1] - y, dz = sq[3 * q + 2] - z;
+        const float d = dx * dx + dy * dy + dz * dz;
+        const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | v;
+        if (!(d != d) && key < best[q]) best[q] = key;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < LOC_Q; ++q) {
+    if (q < (int)nq) {
+      unsigned long long b = best[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o); b = t < b ? t : b; }
+      if ((threadIdx.x & 31) == 0 && b != ~0ull) atomicMin(&sbest[q], b);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < nq && sbest[threadIdx.x] != ~0ull) atomicMin(&keys[q0 + threadIdx.x], sbest[threadIdx.x]);
+}
+
+__global__ void k_containing_face(const float* __restrict__ pos, const uint32_t* __restrict__ faces, const uint32_t* __restrict__ cor_ptr,
+                                  const int4* __restrict__ cor_idx, const float* __restrict__ points, uint32_t n,
+                                  const unsigned long long* __restrict__ keys, uint32_t* __restrict__ out_vertex,
+                                  int32_t* __restrict__ out_face, float* __restrict__ out_bary) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const uint32_t best = (uint32_t)(keys[q] & 0xffffffffu);
+  if (out_vertex) out_vertex[q] = best;
+  const F3 p = f3load(points, q);
+  float lowest = 3.402823466e+38f;
+  int32_t bf = -1; float bb[3] = {0, 0, 0};
+  for (uint32_t k = cor_ptr[best]; k < cor_ptr[best + 1]; ++k) {
+    const uint32_t f = (uint32_t)cor_idx[k].z;
+    const uint32_t* t = faces + 3 * (size_t)f;
+    float cb[3], dist = 0;
+    if (projected_barycentric(p, f3load(pos, t[0]), f3load(pos, t[1]), f3load(pos, t[2]), cb, dist) && dist < lowest) {
+      lowest = dist; bf = (int32_t)f; bb[0] = cb[0]; bb[1] = cb[1]; bb[2] = cb[2];
+    }
+  }
+  if (out_face) out_face[q] = bf;
+  if (out_bary) { out_bary[3 * (size_t)q] = bb[0]; out_bary[3 * (size_t)q + 1] = bb[1]; out_bary[3 * (size_t)q + 2] = bb[2]; }
+}
+
+// ============================================================================
 // InflationLayer::waveCostInflation (inflation_layer.cpp:341-491): whole-grid cooperative kernel
 // (multi-source: few, very wide rounds) + fading epilogue (:482-490, :315-339)
 // ============================================================================
@@ -1321,6 +1388,41 @@ int32_t mnb_cvp_backtrack(mnb_ctx* ctx, const float robot_pos[3], uint32_t robot
   ctx->stats = mnb_stats{}; ctx->stats.kernel_ms = ms; ctx->stats.kernel_launches = 1; ctx->stats.settled = n;
   if (res[0] == MNB_E_STATE) { ctx->err = "back-tracking exceeded max_points (cyclic vector field?) or the face search list"; return MNB_E_STATE; }
   return res[0];
+}
+
+int32_t mnb_locate(mnb_ctx* ctx, uint32_t n, const float* points, uint32_t* out_vertex, int32_t* out_face, float* out_bary) {
+  if (!ctx || !ctx->V || !points || n == 0) return MNB_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const bool dev = ctx->ptr_mode == MNB_PTR_DEVICE;
+  float* d_pts = nullptr; unsigned long long* d_keys = nullptr; uint32_t* d_v = nullptr; int32_t* d_f = nullptr; float* d_b = nullptr;
+  CK(dalloc(&d_keys, (size_t)n));
+  CK(cudaMemsetAsync(d_keys, 0xff, sizeof(unsigned long long) * (size_t)n, ctx->stream));
+  const float* pts = points;
+  if (!dev) {
+    CK(dalloc(&d_pts, 3 * (size_t)n)); CK(dalloc(&d_v, (size_t)n)); CK(dalloc(&d_f, (size_t)n)); CK(dalloc(&d_b, 3 * (size_t)n));
+    CK(cudaMemcpyAsync(d_pts, points, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    pts = d_pts;
+  }
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  const uint32_t want = (ctx->V + 255) / 256, cap = (uint32_t)ctx->sm_count * 8;
+  const uint32_t blocks = want < cap ? want : cap;
+  uint32_t launches = 0;
+  for (uint32_t q0 = 0; q0 < n; q0 += LOC_Q, ++launches)
+    k_nearest_vertex<<<blocks, 256, 0, ctx->stream>>>(ctx->d_pos, ctx->V, pts, q0, n - q0 < (uint32_t)LOC_Q ? n - q0 : (uint32_t)LOC_Q, d_keys);
+  k_containing_face<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_pos, ctx->d_faces, ctx->d_cor_ptr, ctx->d_cor_idx, pts, n, d_keys,
+                                                           dev ? out_vertex : d_v, dev ? out_face : d_f, dev ? out_bary : d_b);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (!dev) {
+    if (out_vertex) CK(cudaMemcpyAsync(out_vertex, d_v, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_face) CK(cudaMemcpyAsync(out_face, d_f, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_bary) CK(cudaMemcpyAsync(out_bary, d_b, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  dfree(d_pts); dfree(d_keys); dfree(d_v); dfree(d_f); dfree(d_b);
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->stats = mnb_stats{}; ctx->stats.kernel_ms = ms; ctx->stats.kernel_launches = launches + 1; ctx->stats.settled = n;
+  return MNB_OK;
 }
 
 // debugging aid (not part of the public header): raw labels {d, a1, a2, a3|flag} of wavefront group 0

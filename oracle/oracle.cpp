@@ -949,3 +949,36 @@ extern "C" int32_t orc_cvp_backtrack(void* h, const float* vector_map, const flo
   *n_points = n;
   return 0;
 }
+
+// ---------------------------------------------------------------------------
+// Localisation: MeshMap::getNearestVertexHandle mesh_map.cpp:1161-1174 (nanoflann 1-NN, L2_Simple: squared
+// distance accumulated x, y, z in float; un-vendored -> exhaustive scan, ties to the lowest vertex id, PARITY
+// UNPINNED for exact ties) and MeshMap::searchContainingFace mesh_map.cpp:1120-1159 (faces of the nearest vertex,
+// ascending face id; the one with the lowest SIGNED plane distance among those passing the inside test; max_dist
+// is not consulted by the reference).  face = -1: none.
+// ---------------------------------------------------------------------------
+extern "C" void orc_locate(void* h, uint32_t n, const float* points, uint32_t* nearest_vertex, int32_t* face, float* bary /*3n*/) {
+  const OrcMesh& m = *(OrcMesh*)h;
+  for (uint32_t q = 0; q < n; ++q) {
+    const V3 p{points[3 * (size_t)q], points[3 * (size_t)q + 1], points[3 * (size_t)q + 2]};
+    uint32_t best = 0; float bd = std::numeric_limits<float>::infinity();
+    for (uint32_t v = 0; v < m.V; ++v) {
+      const float dx = p.x - m.pos[3 * (size_t)v], dy = p.y - m.pos[3 * (size_t)v + 1], dz = p.z - m.pos[3 * (size_t)v + 2];
+      const float d = dx * dx + dy * dy + dz * dz;
+      if (d < bd) { bd = d; best = v; }
+    }
+    nearest_vertex[q] = best;
+    float lowest = std::numeric_limits<float>::max();
+    int32_t bf = -1; float bb[3] = {0, 0, 0};
+    for (uint32_t k = m.vf_ptr[best]; k < m.vf_ptr[best + 1]; ++k) {
+      const uint32_t f = m.vf_face[k];
+      const uint32_t* t = &m.faces[3 * (size_t)f];
+      float cb[3], dist = 0;
+      if (projectedBarycentricCoords(p, P(m, t[0]), P(m, t[1]), P(m, t[2]), cb, dist) && dist < lowest) {
+        lowest = dist; bf = (int32_t)f; bb[0] = cb[0]; bb[1] = cb[1]; bb[2] = cb[2];
+      }
+    }
+    face[q] = bf;
+    if (bary) { bary[3 * (size_t)q] = bb[0]; bary[3 * (size_t)q + 1] = bb[1]; bary[3 * (size_t)q + 2] = bb[2]; }
+  }
+}

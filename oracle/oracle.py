@@ -53,6 +53,7 @@ def lib():
         L.orc_fading.argtypes = [dbl, dbl, dbl, dbl, dbl, f32]
         L.orc_sethian_update.restype = f32
         L.orc_sethian_update.argtypes = [f32] * 6
+        L.orc_locate.argtypes = [vp, C.c_uint32, vp, vp, vp, vp]
         L.orc_cvp_backtrack.restype = C.c_int32
         L.orc_cvp_backtrack.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_uint32, C.c_double, C.c_uint32, vp, vp, vp]
         L.orc_dijkstra_vector_map.argtypes = [vp, vp, vp]
@@ -212,6 +213,16 @@ def _cvp_backtrack(self, vector_map, start, start_face, goal, goal_face, step_wi
     return rc, pp[:k].copy(), pf[:k].copy()
 
 
+def _locate(self, points):
+    """getNearestVertexHandle + searchContainingFace (mesh_map.cpp:1120-1174) -> (vertex, face or -1, bary)"""
+    pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+    n = pts.shape[0]
+    nv = np.empty(n, np.uint32); fc = np.empty(n, np.int32); ba = np.empty((n, 3), np.float32)
+    lib().orc_locate(self._h, n, _p(pts), _p(nv), _p(fc), _p(ba))
+    return nv, fc, ba
+
+
+OracleMesh.locate = _locate
 OracleMesh.cvp_backtrack = _cvp_backtrack
 OracleMesh.dijkstra_vector_map = _dijkstra_vector_map
 OracleMesh.cvp_vector_map = _cvp_vector_map

@@ -491,3 +491,27 @@ def test_backtrack_needs_plan(api, oracle_mod):
     with pytest.raises(RuntimeError):
         api.CVPMeshPlanner(mm).backtrack(pos[0], 0)
     mm.close()
+
+
+@pytest.mark.parametrize("n,nq", [(120, 1), (200, 77), (64, 300)])
+def test_locate_parity(api, oracle_mod, n, nq):
+    """f2: getNearestVertexHandle (mesh_map.cpp:1161-1174) + searchContainingFace (:1120-1159), batched on the GPU"""
+    pos, faces, om, mm, ed, vc, w = setup(api, oracle_mod, n, True)
+    rng = np.random.default_rng(5)
+    fsel = rng.integers(0, faces.shape[0], nq)
+    b = rng.dirichlet((1, 1, 1), nq).astype(np.float32)
+    pts = (pos[faces[fsel]] * b[:, :, None]).sum(1).astype(np.float32)
+    pts[:, 2] += rng.normal(0, 0.05, nq).astype(np.float32)            # off the surface
+    pts[::7] += np.float32(50.0)                                        # far outside: nearest vertex yes, face no
+    pts[::5] = pos[rng.integers(0, pos.shape[0], len(pts[::5]))]        # exactly on vertices
+    ov, of, ob = om.locate(pts)
+    gv, gf, gb = mm.locate(pts)
+    assert (gv == ov).all() and (gf == of).all()
+    assert (gb.view(np.uint32) == ob.view(np.uint32)).all()
+    assert (of[::7][np.arange(len(of[::7])) % 5 != 0] == -1).all() or nq < 8
+    inside = of >= 0
+    assert inside.mean() > 0.5 or nq == 1
+    # the reported face really contains the projected point
+    assert (gb[inside] >= -0.0100001).all() and (gb[inside] <= 1.0100001).all()
+    assert mm.getNearestVertexHandle(pts[0]) == ov[0] and mm.getContainingFace(pts[0]) == of[0]
+    mm.close()
