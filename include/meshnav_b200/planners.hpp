@@ -27,10 +27,36 @@ inline Vector operator-(const Vector& a, const Vector& b) { return {a.x - b.x, a
 inline float length(const Vector& v) { return std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z); }
 inline Vector normalized(const Vector& v) { const float l = length(v); return l > 0 ? Vector{v.x / l, v.y / l, v.z / l} : v; }
 
+struct Quaternion { double x = 0, y = 0, z = 0, w = 1; };            // geometry_msgs::msg::Quaternion
 struct PoseStamped {                                                // geometry_msgs::msg::PoseStamped (position + heading)
   Vector position;
   Vector direction;                                                 // unit vector along the path (orientation's x axis)
+  Quaternion orientation;                                           // x axis along `direction`, z axis along the surface normal
 };
+inline Vector cross(const Vector& a, const Vector& b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+// mesh_map::calculatePoseFromDirection (mesh_map/src/util.cpp:267-287): basis ez = n, ey = n x dir, ex = ey x n (each
+// normalised), columns of the rotation matrix; quaternion by tf2::Matrix3x3::getRotation (un-vendored ROS dependency,
+// restated: trace / largest-diagonal branches) followed by normalize().
+inline Quaternion calculatePoseFromDirection(const Vector& direction, const Vector& normal) {
+  const Vector ez = normalized(normal), ey = normalized(cross(normal, direction)), ex = normalized(cross(ey, normal));
+  const double m[3][3] = {{ex.x, ey.x, ez.x}, {ex.y, ey.y, ez.y}, {ex.z, ey.z, ez.z}};
+  double t[4];
+  const double trace = m[0][0] + m[1][1] + m[2][2];
+  if (trace > 0.0) {
+    double s = std::sqrt(trace + 1.0);
+    t[3] = s * 0.5; s = 0.5 / s;
+    t[0] = (m[2][1] - m[1][2]) * s; t[1] = (m[0][2] - m[2][0]) * s; t[2] = (m[1][0] - m[0][1]) * s;
+  } else {
+    const int i = m[0][0] < m[1][1] ? (m[1][1] < m[2][2] ? 2 : 1) : (m[0][0] < m[2][2] ? 2 : 0);
+    const int j = (i + 1) % 3, k = (i + 2) % 3;
+    double s = std::sqrt(m[i][i] - m[j][j] - m[k][k] + 1.0);
+    t[i] = s * 0.5; s = 0.5 / s;
+    t[3] = (m[k][j] - m[j][k]) * s; t[j] = (m[j][i] + m[i][j]) * s; t[k] = (m[k][i] + m[i][k]) * s;
+  }
+  const double l = std::sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2] + t[3] * t[3]);
+  return {t[0] / l, t[1] / l, t[2] / l, t[3] / l};
+}
 
 // outcome codes: mbf_msgs::action::GetPath::Result (dijkstra_mesh_planner.h:72-85)
 enum : uint32_t { SUCCESS = 0, CANCELED = 51, INVALID_START = 52, INVALID_GOAL = 53, NO_PATH_FOUND = 54, INTERNAL_ERROR = 59 };
@@ -58,6 +84,11 @@ class MeshMap {
   mnb_ctx* ctx() const { return ctx_; }
   Vector vertexPosition(uint32_t v) const { return {pos_[3 * v], pos_[3 * v + 1], pos_[3 * v + 2]}; }
   const std::vector<uint32_t>& faces() const { return faces_; }
+  // MeshMap::faceNormals()[f] (lvr2::calcFaceNormals, mesh_map.cpp:351): normalize(cross(p1 - p0, p2 - p0))
+  Vector faceNormal(uint32_t f) const {
+    const Vector p0 = vertexPosition(faces_[3 * (size_t)f]), p1 = vertexPosition(faces_[3 * (size_t)f + 1]), p2 = vertexPosition(faces_[3 * (size_t)f + 2]);
+    return normalized(cross(p1 - p0, p2 - p0));
+  }
   std::vector<float>& vertexCosts() { return vertex_costs_; }          // MeshMap::vertexCosts()
   std::vector<float>& edgeWeights() { return edge_weights_; }          // MeshMap::edgeWeights()
   const std::vector<float>& edgeDistances() const { return edge_distances_; }
@@ -198,11 +229,13 @@ class CVPMeshPlanner : public MeshPlanner {
       for (size_t i = 1; i < path.size(); ++i) {
         const Vector next = path[i].first;
         PoseStamped pose; pose.position = vec; pose.direction = normalized(next - vec);
+        pose.orientation = calculatePoseFromDirection(next - vec, mesh_map_->faceNormal(path[i - 1].second));   // :112 calculatePoseFromPosition
         cost += length(next - vec);
         vec = next;
         plan.push_back(pose);
       }
-      PoseStamped pose; pose.position = vec; pose.direction = plan.empty() ? goal.direction : plan.back().direction;
+      PoseStamped pose = goal; pose.position = vec;                                                       // :121-125 goal pose, caller's orientation
+      if (!plan.empty() && length(goal.direction) == 0.0f) pose.direction = plan.back().direction;
       plan.push_back(pose);
     }
     return outcome;

@@ -98,17 +98,35 @@ __device__ __forceinline__ void group_sync(unsigned int* bar = nullptr) {
 // per-CTA staging of appends to the next candidate list
 struct Stage {
   static constexpr int CAP = 3072;
+  static constexpr int SW_CAP = 1024;     // stage slots that take part in the in-round sweeps
   uint32_t buf[CAP];
   unsigned int n;
   unsigned int base;
   unsigned int m_tau;
   unsigned int lo;
+  // in-round sweeps (run_band_rounds_sub8): version of the slot's vertex at its last evaluation, dirty list
+  uint32_t seen[SW_CAP];
+  uint16_t dl[SW_CAP];
+  unsigned int dn;
 };
+constexpr uint32_t SEEN_NEVER = 0xffffffffu;
 
-__device__ __forceinline__ void stage_push(Stage& st, uint32_t v, uint32_t* list_next, unsigned int* count_next) {
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ unsigned int stage_push(Stage& st, uint32_t v, uint32_t* list_next, unsigned int* count_next) {
   const unsigned int p = atomicAdd(&st.n, 1u);
   if (p < Stage::CAP) st.buf[p] = v;
   else list_next[atomicAdd(count_next, 1u)] = v;  // overflow: straight to global
+  return p;
+}
+// same, and registers the slot for the in-round sweeps with the version its vertex had at the last evaluation
+__device__ __forceinline__ void stage_push_seen(Stage& st, uint32_t v, uint32_t seen, uint32_t* list_next, unsigned int* count_next) {
+  const unsigned int p = stage_push(st, v, list_next, count_next);
+  if (p < Stage::SW_CAP) st.seen[p] = seen;
 }
 
 // flush the CTA stage to the global list (all threads of the CTA call this)
@@ -246,12 +264,13 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
 // Same round loop with 8 lanes per candidate (problem provides replay_sub8 / activate via its ELL row).
 // Used by the whole-grid single-plan kernel where per-round LATENCY is what matters.
 // -----------------------------------------------------------------------------
-template <int CS, class P>
+template <int CS, bool SW, class P>
 __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_t* list1, uint32_t* mark,
                                      Stage& st, const float delta, const uint32_t gthreads, const uint32_t gtid,
                                      const int has_robot, const uint32_t r0, const uint32_t r1, const uint32_t r2,
                                      const double goal_dist_offset, const volatile int* cancel_flag,
-                                     const float band_end_init, const uint32_t max_rounds) {
+                                     const float band_end_init, const uint32_t max_rounds, const int n_sweeps_arg) {
+  const int n_sweeps = SW ? n_sweeps_arg : 0;
   float band_end_prev = band_end_init;
   unsigned long long my_recomputes = 0, my_settled = 0;
   float lo_best = -1.0f; int stagnant = 0;       // best (largest) earliest-unsettled pop time seen so far
@@ -287,23 +306,73 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
     }
     const long long tp0 = clock64();
     float my_mtau = __uint_as_float(INF_BITS), my_lo = __uint_as_float(INF_BITS);
+    // One evaluation of candidate c by its 8-lane group (every lane of the WARP calls this; idle groups pass
+    // has = false so that the sub-warp shuffles can use compile-time full masks).  `fresh` = main pass (c comes from
+    // the round's list and is pushed to the stage); otherwise c already sits in the stage (in-round sweep).
+    auto evaluate = [&](bool has, const uint32_t c, const Label& old, const int4& ix, const float4& w, const uint32_t mk,
+                        const uint32_t v0, const bool fresh) {
+      const float d = old.d, tau = old.t.a1;
+      float nd; EvTime nt; int deg; uint32_t mk1 = MARK_FIXED, mk2 = MARK_FIXED;
+      prob.replay_sub8(c, j, has, ix, w, band_end, goal, r, mark, nd, nt, deg, mk1, mk2);
+      const bool changed = has && (__float_as_uint(nd) != __float_as_uint(d) || !ev_eq(nt, old.t));
+      if (has && j == 0) {
+        my_recomputes++;
+        if (changed) {
+          prob.store_label(c, nd, nt, __float_as_uint(d) != INF_BITS, r);
+          my_mtau = fminf(my_mtau, fminf(tau, nt.a1));
+        }
+        my_lo = fminf(my_lo, nt.a1);
+        if (fresh) { if constexpr (SW) stage_push_seen(st, c, v0, list_n, &ctl->count[next]); else stage_push(st, c, list_n, &ctl->count[next]); }
+      }
+      if constexpr (SW) if (n_sweeps > 0) {
+        // tell the vertices that read c's label (its face neighbours) that it changed by bumping their version.
+        // No fence / release-acquire pairing on purpose: the sweeps are opportunistic -- a neighbour that polls the
+        // bump but still reads the old label merely misses one in-round update; the next round's main pass
+        // recomputes every candidate and the change is accounted in m_tau, so exactness never depends on it.
+        __syncwarp();
+        if (changed) {
+          if (ix.x != -1 && deg <= 8) { atomicAdd(&prob.ver[ix.x], 1u); atomicAdd(&prob.ver[ix.y], 1u); }
+          if (j == 0 && deg > 8) prob.activate(c, [&](uint32_t x) { atomicAdd(&prob.ver[x], 1u); });
+        }
+      }
+      if (has && __float_as_uint(nd) != INF_BITS && mk == MARK_CAND) {
+        // every lane pulls the two source vertices of its own corner into the candidate set; their marks
+        // were fetched together with their labels, so only genuinely new vertices cost an atomic
+        if (ix.x != -1) {
+          if (mk1 == MARK_NONE && prob.eligible((uint32_t)ix.x) && atomicCAS(&mark[ix.x], MARK_NONE, MARK_CAND) == MARK_NONE)
+            { if constexpr (SW) stage_push_seen(st, (uint32_t)ix.x, SEEN_NEVER, list_n, &ctl->count[next]); else stage_push(st, (uint32_t)ix.x, list_n, &ctl->count[next]); }
+          if (mk2 == MARK_NONE && prob.eligible((uint32_t)ix.y) && atomicCAS(&mark[ix.y], MARK_NONE, MARK_CAND) == MARK_NONE)
+            { if constexpr (SW) stage_push_seen(st, (uint32_t)ix.y, SEEN_NEVER, list_n, &ctl->count[next]); else stage_push(st, (uint32_t)ix.y, list_n, &ctl->count[next]); }
+        }
+        if (j == 0 && deg > 8)
+          prob.activate(c, [&](uint32_t x) {
+            if (__ldcg(&mark[x]) == MARK_NONE && prob.eligible(x) && atomicCAS(&mark[x], MARK_NONE, MARK_CAND) == MARK_NONE)
+              { if constexpr (SW) stage_push_seen(st, x, SEEN_NEVER, list_n, &ctl->count[next]); else stage_push(st, x, list_n, &ctl->count[next]); }
+          });
+        if (j == 0) mark[c] = MARK_CAND_ACT;
+      }
+    };
     // warp-uniform trip count: every lane of the warp runs every iteration (idle groups carry has = false) so
     // that the sub-warp shuffles below can use compile-time full masks (no MATCH.ANY / WARPSYNC sequences)
     // the candidates are dealt to the CTAs of the group in equal contiguous chunks and packed into the
     // lowest warps of each CTA: a round's cost is the instruction stream of its busiest SM, so an even
     // spread (instead of filling the first CTAs completely) is what shortens the round
-    const unsigned int chunk = (n + nblk - 1) / nblk;
-    const unsigned int cbeg = min(n, blk * chunk), cend = min(n, cbeg + chunk);
-    for (unsigned int ib = cbeg + (threadIdx.x >> 5) * 4u; ib < cend; ib += (blockDim.x >> 3)) {
-      const unsigned int i = ib + ((threadIdx.x & 31) >> 3);
-      bool has = i < cend;
+    // ... and dealt round-robin (candidate i -> CTA i mod nblk): the list is ordered by flush time, i.e. by how busy the
+    // producing CTA was, so contiguous chunks would hand all the "hot" candidates (the ones whose labels are still
+    // moving) to a few CTAs while the rest idle at the barrier
+    const unsigned int cnt = n > blk ? (n - blk + nblk - 1) / nblk : 0u;
+    for (unsigned int qb = (threadIdx.x >> 5) * 4u; qb < cnt; qb += (blockDim.x >> 3)) {
+      const unsigned int q = qb + ((threadIdx.x & 31) >> 3);
+      bool has = q < cnt;
       uint32_t c = 0;
-      if (has) c = __ldcg(&list_r[i]);
-      // issue the three independent loads of the candidate together: its label and its ELL row
+      if (has) c = __ldcg(&list_r[(size_t)q * nblk + blk]);
+      // issue the independent loads of the candidate together: its label, its ELL row, its mark (and version)
       Label old = prob.load_label(has ? c : 0u);
       int4 ix = prob.load_row_idx(has ? c : 0u, j);
       float4 w = prob.load_row_w(has ? c : 0u, j);
       const uint32_t mk = __ldcg(&mark[has ? c : 0u]);
+      uint32_t v0 = 0;
+      if constexpr (SW) if (n_sweeps > 0) v0 = __ldcg(&prob.ver[has ? c : 0u]);
       const float d = old.d, tau = old.t.a1;
       if (has && tau < m_prev && tau < band_end_prev) {
         if (j == 0) {
@@ -323,35 +392,38 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
         }
         has = false;
       }
-      float nd; EvTime nt; int deg; uint32_t mk1 = MARK_FIXED, mk2 = MARK_FIXED;
-      prob.replay_sub8(c, j, has, ix, w, band_end, goal, r, mark, nd, nt, deg, mk1, mk2);
-      if (has) {
-        if (j == 0) {
-          my_recomputes++;
-          if (__float_as_uint(nd) != __float_as_uint(d) || !ev_eq(nt, old.t)) {
-            prob.store_label(c, nd, nt, __float_as_uint(d) != INF_BITS, r);
-            my_mtau = fminf(my_mtau, fminf(tau, nt.a1));
-          }
-          my_lo = fminf(my_lo, nt.a1);
-          stage_push(st, c, list_n, &ctl->count[next]);
-        }
-        if (__float_as_uint(nd) != INF_BITS && mk == MARK_CAND) {
-          // every lane pulls the two source vertices of its own corner into the candidate set; their marks
-          // were fetched together with their labels, so only genuinely new vertices cost an atomic
-          if (ix.x != -1) {
-            if (mk1 == MARK_NONE && prob.eligible((uint32_t)ix.x) && atomicCAS(&mark[ix.x], MARK_NONE, MARK_CAND) == MARK_NONE)
-              stage_push(st, (uint32_t)ix.x, list_n, &ctl->count[next]);
-            if (mk2 == MARK_NONE && prob.eligible((uint32_t)ix.y) && atomicCAS(&mark[ix.y], MARK_NONE, MARK_CAND) == MARK_NONE)
-              stage_push(st, (uint32_t)ix.y, list_n, &ctl->count[next]);
-          }
-          if (j == 0 && deg > 8)
-            prob.activate(c, [&](uint32_t x) {
-              if (__ldcg(&mark[x]) == MARK_NONE && prob.eligible(x) && atomicCAS(&mark[x], MARK_NONE, MARK_CAND) == MARK_NONE)
-                stage_push(st, x, list_n, &ctl->count[next]);
-            });
-          if (j == 0) mark[c] = MARK_CAND_ACT;
-        }
+      evaluate(has, c, old, ix, w, mk, v0, true);
+    }
+    // ---- in-round sweeps: the CTA keeps relaxing the candidates it staged (survivors + newly activated) whose
+    // inputs changed since their last evaluation, so a dependency chain advances several hops per barrier ----
+    const long long tps = clock64();
+    if (gtid == 0) { ctl->t_ph[0] += (unsigned long long)(tps - tp0); ctl->t_ph[2] += cnt; }
+    if constexpr (SW) for (int sw = 0; sw < n_sweeps; ++sw) {
+      const long long tq0 = clock64();
+      __syncthreads();
+      const unsigned int ns = min(st.n, (unsigned int)Stage::SW_CAP);
+      for (unsigned int i = threadIdx.x; i < ns; i += blockDim.x) {
+        const uint32_t c = st.buf[i];
+        const uint32_t v0 = __ldcg(&prob.ver[c]);
+        if (v0 != st.seen[i]) { st.seen[i] = v0; st.dl[atomicAdd(&st.dn, 1u)] = (uint16_t)i; }
       }
+      __syncthreads();
+      const unsigned int dn = st.dn;
+      __syncthreads();
+      if (threadIdx.x == 0) st.dn = 0;
+      const long long tq1 = clock64();
+      if (gtid == 0) { ctl->t_ph[3] += dn; ctl->t_ph[4] += ns; ctl->t_ph[5] += (unsigned long long)(tq1 - tq0); }
+      for (unsigned int ib = (threadIdx.x >> 5) * 4u; ib < dn; ib += (blockDim.x >> 3)) {
+        const unsigned int i = ib + ((threadIdx.x & 31) >> 3);
+        const bool has = i < dn;
+        const uint32_t c = has ? st.buf[st.dl[i]] : 0u;
+        Label old = prob.load_label(c);
+        int4 ix = prob.load_row_idx(c, j);
+        float4 w = prob.load_row_w(c, j);
+        const uint32_t mk = __ldcg(&mark[c]);
+        evaluate(has, c, old, ix, w, mk, 0u, false);
+      }
+      if (gtid == 0) ctl->t_ph[6] += (unsigned long long)(clock64() - tq1);
     }
     {
       my_mtau = fminf(my_mtau, prob.deferred_m);      // deferred back-steps are pending changes

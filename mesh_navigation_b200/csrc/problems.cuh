@@ -40,6 +40,7 @@ struct CvpProblem {
 
   uint32_t* minor_arr;                  // overflow minors (only read when the label's flag bit is set)
   uint32_t* chg;                        // 1 + round of the last RE-label of a vertex (0 = never)
+  uint32_t* ver;                        // input version: bumped whenever a face neighbour is re-labelled (in-round sweeps)
   mutable float deferred_m;             // smallest trigger time of a back-step deferred in this round
   int strict;                           // set by the engine once it has detected stagnation (see backstep_ok)
 

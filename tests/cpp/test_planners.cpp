@@ -78,6 +78,14 @@ int main() {
   // vector-field back-tracking (cvp:920-951): robot first, goal last, steps of step_width, smoother than the edge path
   CHECK(plan.size() > 12 && length(plan.front().position - robot.position) == 0.0f && length(plan.back().position - goal.position) == 0.0f);
   for (size_t i = 0; i + 2 < plan.size(); ++i) CHECK(length(plan[i + 1].position - plan[i].position) < 0.65f);
+  for (size_t i = 0; i + 1 < plan.size(); ++i) {
+    // pose orientation (util.cpp:267-298): unit quaternion whose x axis is the path direction projected into the face plane
+    const Quaternion& q = plan[i].orientation;
+    CHECK(std::fabs(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w - 1.0) < 1e-9);
+    const double xx = 1 - 2 * (q.y * q.y + q.z * q.z), xy = 2 * (q.x * q.y + q.z * q.w), xz = 2 * (q.x * q.z - q.y * q.w);
+    const Vector d = plan[i].direction;
+    CHECK(xx * d.x + xy * d.y + xz * d.z > 0.9);
+  }
   {
     // the same walk by the oracle on the GPU's vector map is bit-identical
     const int64_t sfo = map->getContainingFace(goal.position, 0.4f), rfo = map->getContainingFace(robot.position, 0.4f);

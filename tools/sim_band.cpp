@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -45,7 +46,7 @@ struct Sim {
 
   int seed_index(uint32_t v) const { return v == s[0] ? 0 : (v == s[1] ? 1 : (v == s[2] ? 2 : -1)); }
 
-  std::vector<uint32_t> chg; uint32_t round = 0; mutable float blocked_m = FINF;
+  std::vector<uint32_t> chg; uint32_t round = 0; mutable float blocked_m = FINF; mutable bool deferred_flag = false;
   bool face_time(uint32_t v1, uint32_t v2, Tm3& T, uint32_t& tv) const {
     const Lab &a = L[v1], &b = L[v2];
     if (!(a.d < band_end) || !(b.d < band_end)) return false;
@@ -96,7 +97,7 @@ struct Sim {
       const uint32_t k = cs[i].k;
       if (cvp_update_t<false>(cs[i].u1, cs[i].u2, cur, w[T.cor_ea[k]], w[T.cor_eb[k]], w[T.cor_ec[k]], r)) {
         // a back-step label is only taken from a trigger that has been stable for a whole round
-        if (!(r.value > cs[i].T.a[0]) && !(chg[cs[i].tv] < round)) { blocked_m = std::fmin(blocked_m, cs[i].T.a[0]); continue; }
+        if (!(r.value > cs[i].T.a[0]) && !(chg[cs[i].tv] < round)) { blocked_m = std::fmin(blocked_m, cs[i].T.a[0]); deferred_flag = true; continue; }
         cur = r.value;
         const Tm3& F = cs[i].T;
         // monotonic stack of water levels: keep the levels above the new key, then the key itself
@@ -148,7 +149,10 @@ extern "C" int sim_cvp_band(uint32_t V, uint32_t F, const uint32_t* faces, const
   }
   for (int k = 0; k < 3; ++k) activate(S.s[k], cand);
 
-  size_t rounds = 0, recomputes = 0;
+  size_t rounds = 0, recomputes = 0, dirty_recomputes = 0, clean_but_changed = 0;
+  const int n_sweeps = getenv("SIM_SWEEPS") ? atoi(getenv("SIM_SWEEPS")) : 0;
+  std::vector<uint32_t> chg_stamp(V, 0), eval_stamp(V, 0); uint32_t stamp = 1;
+  std::vector<uint32_t> dst(V, 0xffffffffu), evr(V, 0xffffffffu); std::vector<float> wake(V, 0.0f); size_t skipped = 0, skip_wrong = 0;
   float m_prev = 0.0f, lo_prev = seed_min, band_end_prev = std::nextafter(seed_max, FINF);
   const size_t max_rounds = 2 * (size_t)V + 64;
   std::vector<Lab> nl;
@@ -159,7 +163,7 @@ extern "C" int sim_cvp_band(uint32_t V, uint32_t F, const uint32_t* faces, const
     float band_end = (float)(lo_prev + (float)delta);
     if (!(band_end > band_end_prev)) band_end = band_end_prev;
     S.band_end = band_end; S.round = (uint32_t)rounds;
-    next.clear();
+    next.clear(); ++stamp;
     float m = FINF, lo = FINF; S.blocked_m = FINF;
     // Jacobi: decide "fixed" on the labels of the previous round, recompute the rest from old labels
     nl.resize(cand.size());
@@ -168,7 +172,20 @@ extern "C" int sim_cvp_band(uint32_t V, uint32_t F, const uint32_t* faces, const
       const uint32_t c = cand[i];
       const Lab old = S.L[c];
       if (old.t.a[0] < m_prev && old.t.a[0] < band_end_prev) { fixed_now[i] = 1; continue; }
+      S.deferred_flag = false;
       nl[i] = S.replay(c); recomputes++;
+      {
+        // push-stamp skip rule (validation only: we still recompute and check the prediction)
+        const bool need = evr[c] == 0xffffffffu || dst[c] != 0xffffffffu && dst[c] >= evr[c] || band_end > wake[c];
+        if (!need) { skipped++; if (nl[i].d != old.d || !teq(nl[i].t, old.t)) skip_wrong++; }
+        evr[c] = S.deferred_flag ? 0xffffffffu : (uint32_t)rounds;
+        float wk = FINF;
+        for (uint32_t k = S.T.vcor_ptr[c]; k < S.T.vcor_ptr[c + 1]; ++k) {
+          const float da = S.L[S.T.cor_v1[k]].d, db = S.L[S.T.cor_v2[k]].d;
+          if ((!(da < band_end) || !(db < band_end)) && da < FINF && db < FINF) wk = std::fmin(wk, std::fmax(da, db));
+        }
+        wake[c] = wk;
+      }
     }
     for (size_t i = 0; i < cand.size(); ++i) {
       const uint32_t c = cand[i];
@@ -177,17 +194,52 @@ extern "C" int sim_cvp_band(uint32_t V, uint32_t F, const uint32_t* faces, const
       if (nl[i].d != old.d || !teq(nl[i].t, old.t)) {
         m = std::fmin(m, std::fmin(old.t.a[0], nl[i].t.a[0]));
         if (old.d < FINF) S.chg[c] = (uint32_t)rounds + 1;   // first-time labelling is not a re-label
-        S.L[c] = nl[i];
+        S.L[c] = nl[i]; chg_stamp[c] = stamp;
+        for (uint32_t k = S.T.vcor_ptr[c]; k < S.T.vcor_ptr[c + 1]; ++k) { dst[S.T.cor_v1[k]] = (uint32_t)rounds; dst[S.T.cor_v2[k]] = (uint32_t)rounds; }
       }
+      eval_stamp[c] = stamp;
       lo = std::fmin(lo, nl[i].d);
       next.push_back(c);
       if (nl[i].d < FINF && mark[c] == 1) { mark[c] = 3; activate(c, next); }
     }
+    // ---- inner sweeps (experiment): extra Jacobi passes over the surviving list inside the same round ----
+    for (int sw = 0; sw < n_sweeps; ++sw) {
+      ++stamp;
+      const size_t ns = next.size();
+      std::vector<Lab> nl2(ns); std::vector<uint8_t> ev(ns, 0);
+      for (size_t i = 0; i < ns; ++i) {
+        const uint32_t c = next[i];
+        // dirty rule: some corner source changed at or after my last evaluation
+        bool dirty = false;
+        for (uint32_t k = S.T.vcor_ptr[c]; k < S.T.vcor_ptr[c + 1] && !dirty; ++k)
+          dirty = chg_stamp[S.T.cor_v1[k]] >= eval_stamp[c] || chg_stamp[S.T.cor_v2[k]] >= eval_stamp[c];
+        nl2[i] = S.replay(c); ev[i] = 1;
+        if (dirty) { dirty_recomputes++; }
+        else if (nl2[i].d != S.L[c].d || !teq(nl2[i].t, S.L[c].t)) clean_but_changed++;
+      }
+      bool any = false;
+      for (size_t i = 0; i < ns; ++i) {
+        const uint32_t c = next[i];
+        const Lab old = S.L[c];
+        eval_stamp[c] = stamp;
+        if (nl2[i].d != old.d || !teq(nl2[i].t, old.t)) {
+          any = true;
+          m = std::fmin(m, std::fmin(old.t.a[0], nl2[i].t.a[0]));
+          if (old.d < FINF) S.chg[c] = (uint32_t)rounds + 1;
+          S.L[c] = nl2[i]; chg_stamp[c] = stamp;
+        }
+        if (nl2[i].d < FINF && mark[c] == 1) { mark[c] = 3; activate(c, next); }
+      }
+      if (!any) break;
+    }
+    if (n_sweeps > 0) { lo = FINF; for (uint32_t c : next) lo = std::fmin(lo, S.L[c].d); }
     cand.swap(next);
     m = std::fmin(m, S.blocked_m);   // a deferred back-step is a pending change at its trigger's pop time
     m_prev = m; lo_prev = lo; band_end_prev = band_end;
     rounds++;
   }
+  fprintf(stderr, "[sim] push-stamp skip: skipped/V=%.2f of recomputes/V=%.2f wrong=%zu\n", (double)skipped / V, (double)recomputes / V, skip_wrong);
+  if (getenv("SIM_SWEEPS")) fprintf(stderr, "[sim] sweeps=%d dirty_recomputes/V=%.2f clean_but_changed=%zu\n", n_sweeps, (double)dirty_recomputes / V, clean_but_changed);
   for (uint32_t v = 0; v < V; ++v) out_dist[v] = S.L[v].d;
   g_last = S.L;
   if (stats) { stats[0] = (double)rounds; stats[1] = (double)recomputes; stats[3] = (double)S.same_inputs / (double)(S.total_replays ? S.total_replays : 1); }
