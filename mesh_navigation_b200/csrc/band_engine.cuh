@@ -104,10 +104,14 @@ struct Stage {
   unsigned int base;
   unsigned int m_tau;
   unsigned int lo;
-  // in-round sweeps (run_band_rounds_sub8): version of the slot's vertex at its last evaluation, dirty list
-  uint32_t seen[SW_CAP];
-  uint16_t dl[SW_CAP];
-  unsigned int dn;
+};
+// in-round sweeps (run_band_rounds_sub8<.., true>): per stage slot, the version of its vertex at the last evaluation
+// and a copy of its label; the per-sweep dirty list.  Lives in the shared memory of the whole-grid kernel only.
+struct SweepStage {
+  uint32_t seen[Stage::SW_CAP];
+  uint4 lab[Stage::SW_CAP];     // the slot vertex's own label (only its owner CTA writes it during a round)
+  uint16_t dl[Stage::SW_CAP];
+  unsigned int dn[2];           // dirty-list length, double-buffered over sweeps
 };
 constexpr uint32_t SEEN_NEVER = 0xffffffffu;
 
@@ -124,9 +128,10 @@ __device__ __forceinline__ unsigned int stage_push(Stage& st, uint32_t v, uint32
   return p;
 }
 // same, and registers the slot for the in-round sweeps with the version its vertex had at the last evaluation
-__device__ __forceinline__ void stage_push_seen(Stage& st, uint32_t v, uint32_t seen, uint32_t* list_next, unsigned int* count_next) {
+__device__ __forceinline__ void stage_push_seen(Stage& st, SweepStage& ss, uint32_t v, uint32_t seen, const uint4& label_bits,
+                                                uint32_t* list_next, unsigned int* count_next) {
   const unsigned int p = stage_push(st, v, list_next, count_next);
-  if (p < Stage::SW_CAP) st.seen[p] = seen;
+  if (p < Stage::SW_CAP) { ss.seen[p] = seen; ss.lab[p] = label_bits; }
 }
 
 // flush the CTA stage to the global list (all threads of the CTA call this)
@@ -269,7 +274,8 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
                                      Stage& st, const float delta, const uint32_t gthreads, const uint32_t gtid,
                                      const int has_robot, const uint32_t r0, const uint32_t r1, const uint32_t r2,
                                      const double goal_dist_offset, const volatile int* cancel_flag,
-                                     const float band_end_init, const uint32_t max_rounds, const int n_sweeps_arg) {
+                                     const float band_end_init, const uint32_t max_rounds, const int n_sweeps_arg,
+                                     SweepStage* ss) {
   const int n_sweeps = SW ? n_sweeps_arg : 0;
   float band_end_prev = band_end_init;
   unsigned long long my_recomputes = 0, my_settled = 0;
@@ -310,7 +316,7 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
     // has = false so that the sub-warp shuffles can use compile-time full masks).  `fresh` = main pass (c comes from
     // the round's list and is pushed to the stage); otherwise c already sits in the stage (in-round sweep).
     auto evaluate = [&](bool has, const uint32_t c, const Label& old, const int4& ix, const float4& w, const uint32_t mk,
-                        const uint32_t v0, const bool fresh) {
+                        const uint32_t v0, const bool fresh, const uint32_t slot) {
       const float d = old.d, tau = old.t.a1;
       float nd; EvTime nt; int deg; uint32_t mk1 = MARK_FIXED, mk2 = MARK_FIXED;
       prob.replay_sub8(c, j, has, ix, w, band_end, goal, r, mark, nd, nt, deg, mk1, mk2);
@@ -322,7 +328,12 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
           my_mtau = fminf(my_mtau, fminf(tau, nt.a1));
         }
         my_lo = fminf(my_lo, nt.a1);
-        if (fresh) { if constexpr (SW) stage_push_seen(st, c, v0, list_n, &ctl->count[next]); else stage_push(st, c, list_n, &ctl->count[next]); }
+        if constexpr (SW) {
+          if (fresh) stage_push_seen(st, *ss, c, v0, prob.pack_label(c, nd, nt), list_n, &ctl->count[next]);
+          else if (changed) ss->lab[slot] = prob.pack_label(c, nd, nt);
+        } else {
+          stage_push(st, c, list_n, &ctl->count[next]);
+        }
       }
       if constexpr (SW) if (n_sweeps > 0) {
         // tell the vertices that read c's label (its face neighbours) that it changed by bumping their version.
@@ -331,7 +342,7 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
         // recomputes every candidate and the change is accounted in m_tau, so exactness never depends on it.
         __syncwarp();
         if (changed) {
-          if (ix.x != -1 && deg <= 8) { atomicAdd(&prob.ver[ix.x], 1u); atomicAdd(&prob.ver[ix.y], 1u); }
+          if (ix.x != -1 && deg <= 8) { atomicAdd(&prob.ver[ix.x], 1u); if constexpr (P::TWO_SOURCES) atomicAdd(&prob.ver[ix.y], 1u); }
           if (j == 0 && deg > 8) prob.activate(c, [&](uint32_t x) { atomicAdd(&prob.ver[x], 1u); });
         }
       }
@@ -340,14 +351,14 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
         // were fetched together with their labels, so only genuinely new vertices cost an atomic
         if (ix.x != -1) {
           if (mk1 == MARK_NONE && prob.eligible((uint32_t)ix.x) && atomicCAS(&mark[ix.x], MARK_NONE, MARK_CAND) == MARK_NONE)
-            { if constexpr (SW) stage_push_seen(st, (uint32_t)ix.x, SEEN_NEVER, list_n, &ctl->count[next]); else stage_push(st, (uint32_t)ix.x, list_n, &ctl->count[next]); }
-          if (mk2 == MARK_NONE && prob.eligible((uint32_t)ix.y) && atomicCAS(&mark[ix.y], MARK_NONE, MARK_CAND) == MARK_NONE)
-            { if constexpr (SW) stage_push_seen(st, (uint32_t)ix.y, SEEN_NEVER, list_n, &ctl->count[next]); else stage_push(st, (uint32_t)ix.y, list_n, &ctl->count[next]); }
+            { if constexpr (SW) stage_push_seen(st, *ss, (uint32_t)ix.x, SEEN_NEVER, state_inf(), list_n, &ctl->count[next]); else stage_push(st, (uint32_t)ix.x, list_n, &ctl->count[next]); }
+          if (P::TWO_SOURCES && mk2 == MARK_NONE && prob.eligible((uint32_t)ix.y) && atomicCAS(&mark[ix.y], MARK_NONE, MARK_CAND) == MARK_NONE)
+            { if constexpr (SW) stage_push_seen(st, *ss, (uint32_t)ix.y, SEEN_NEVER, state_inf(), list_n, &ctl->count[next]); else stage_push(st, (uint32_t)ix.y, list_n, &ctl->count[next]); }
         }
         if (j == 0 && deg > 8)
           prob.activate(c, [&](uint32_t x) {
             if (__ldcg(&mark[x]) == MARK_NONE && prob.eligible(x) && atomicCAS(&mark[x], MARK_NONE, MARK_CAND) == MARK_NONE)
-              { if constexpr (SW) stage_push_seen(st, x, SEEN_NEVER, list_n, &ctl->count[next]); else stage_push(st, x, list_n, &ctl->count[next]); }
+              { if constexpr (SW) stage_push_seen(st, *ss, x, SEEN_NEVER, state_inf(), list_n, &ctl->count[next]); else stage_push(st, x, list_n, &ctl->count[next]); }
           });
         if (j == 0) mark[c] = MARK_CAND_ACT;
       }
@@ -392,7 +403,7 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
         }
         has = false;
       }
-      evaluate(has, c, old, ix, w, mk, v0, true);
+      evaluate(has, c, old, ix, w, mk, v0, true, 0u);
     }
     // ---- in-round sweeps: the CTA keeps relaxing the candidates it staged (survivors + newly activated) whose
     // inputs changed since their last evaluation, so a dependency chain advances several hops per barrier ----
@@ -400,28 +411,30 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
     if (gtid == 0) { ctl->t_ph[0] += (unsigned long long)(tps - tp0); ctl->t_ph[2] += cnt; }
     if constexpr (SW) for (int sw = 0; sw < n_sweeps; ++sw) {
       const long long tq0 = clock64();
-      __syncthreads();
+      __syncthreads();                       // stage pushes / label-cache writes of the previous phase are visible
       const unsigned int ns = min(st.n, (unsigned int)Stage::SW_CAP);
+      unsigned int* dcur = &ss->dn[sw & 1];
+      if (threadIdx.x == 0) ss->dn[(sw + 1) & 1] = 0;
       for (unsigned int i = threadIdx.x; i < ns; i += blockDim.x) {
         const uint32_t c = st.buf[i];
         const uint32_t v0 = __ldcg(&prob.ver[c]);
-        if (v0 != st.seen[i]) { st.seen[i] = v0; st.dl[atomicAdd(&st.dn, 1u)] = (uint16_t)i; }
+        if (v0 != ss->seen[i]) { ss->seen[i] = v0; ss->dl[atomicAdd(dcur, 1u)] = (uint16_t)i; }
       }
       __syncthreads();
-      const unsigned int dn = st.dn;
-      __syncthreads();
-      if (threadIdx.x == 0) st.dn = 0;
+      const unsigned int dn = *dcur;
       const long long tq1 = clock64();
       if (gtid == 0) { ctl->t_ph[3] += dn; ctl->t_ph[4] += ns; ctl->t_ph[5] += (unsigned long long)(tq1 - tq0); }
       for (unsigned int ib = (threadIdx.x >> 5) * 4u; ib < dn; ib += (blockDim.x >> 3)) {
         const unsigned int i = ib + ((threadIdx.x & 31) >> 3);
         const bool has = i < dn;
-        const uint32_t c = has ? st.buf[st.dl[i]] : 0u;
-        Label old = prob.load_label(c);
+        const uint32_t slot = has ? ss->dl[i] : 0u;
+        const uint32_t c = has ? st.buf[slot] : 0u;
+        // own label from the CTA's cache, ELL row through L1: the source labels are the only L2 trip of the chain
+        const Label old = has ? prob.unpack_label(c, ss->lab[slot]) : prob.unpack_label(0u, state_inf());
         int4 ix = prob.load_row_idx(c, j);
         float4 w = prob.load_row_w(c, j);
         const uint32_t mk = __ldcg(&mark[c]);
-        evaluate(has, c, old, ix, w, mk, 0u, false);
+        evaluate(has, c, old, ix, w, mk, 0u, false, slot);
       }
       if (gtid == 0) ctl->t_ph[6] += (unsigned long long)(clock64() - tq1);
     }

@@ -74,6 +74,18 @@ __global__ void k_gather_adj_w(const uint32_t* __restrict__ nbr, const uint32_t*
   out[k] = make_uint2(nbr[k], __float_as_uint(w[eid[k]]));
 }
 
+// ELL view of the same records for the 8-lanes-per-candidate Dijkstra: row v = 8 x {neighbour | -1, weight bits, -, degree}
+__global__ void k_build_ell_adj(const uint32_t* __restrict__ adj_ptr, const uint2* __restrict__ adj_nw, uint32_t V,
+                                uint4* __restrict__ out) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)V * ELL_W) return;
+  const uint32_t v = (uint32_t)(t / ELL_W), j = (uint32_t)(t % ELL_W);
+  const uint32_t kb = adj_ptr[v], deg = adj_ptr[v + 1] - kb;
+  uint4 r = make_uint4(0xffffffffu, INF_BITS, 0u, deg);
+  if (j < deg) { const uint2 nw = adj_nw[kb + j]; r.x = nw.x; r.y = nw.y; }
+  out[t] = r;
+}
+
 // ============================================================================
 // wavefront kernels
 // ============================================================================
@@ -150,7 +162,7 @@ __global__ void __launch_bounds__(MNB_CVP_THREADS, MNB_CVP_MINBLOCKS) k_cvp(cons
   uint32_t* list0 = a.ws.list0 + (size_t)g * V;
   uint32_t* list1 = a.ws.list1 + (size_t)g * V;
   GroupCtl* ctl = a.ws.ctl + g;
-  if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; st.dn = 0; }
+  if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; }
   __syncthreads();
 
   for (;;) {
@@ -215,7 +227,7 @@ __global__ void __launch_bounds__(MNB_CVP_THREADS, MNB_CVP_MINBLOCKS) k_cvp(cons
     float delta = a.delta;
     if (has_robot && a.goal_dist_offset < (double)delta) delta = (float)fmax(a.goal_dist_offset, 1e-4);
     run_band_rounds_sub8<CS, false>(prob, ctl, list0, list1, mark, st, delta, gthreads, gtid, has_robot, r0, r1, r2,
-                        a.goal_dist_offset, a.cancel_flag, nextafterf(seed_max, __uint_as_float(INF_BITS)), a.max_rounds, sweeps);
+                        a.goal_dist_offset, a.cancel_flag, nextafterf(seed_max, __uint_as_float(INF_BITS)), a.max_rounds, sweeps, nullptr);
     group_sync<CS>();
     if (a.out_dist) {
       float* od = a.out_dist + (size_t)q * V;
@@ -232,12 +244,13 @@ __global__ void __launch_bounds__(MNB_CVP_THREADS, MNB_CVP_MINBLOCKS) k_cvp(cons
 #endif
 __global__ void __launch_bounds__(512, MNB_GRID_MINBLOCKS) k_cvp_grid(const CvpKernelArgs a) {
   __shared__ Stage st;
+  __shared__ SweepStage sws;
   uint32_t g, gthreads, gtid;
   group_coords<0>(g, gthreads, gtid);
   const uint32_t V = a.V;
   uint4* state = a.ws.state; uint32_t* mark = a.ws.mark; uint32_t* list0 = a.ws.list0; uint32_t* list1 = a.ws.list1;
   GroupCtl* ctl = a.ws.ctl;
-  if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; st.dn = 0; }
+  if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; sws.dn[0] = 0; sws.dn[1] = 0; }
   __syncthreads();
   for (uint32_t v = gtid; v < V; v += gthreads) { state[v] = state_inf(); mark[v] = MARK_NONE; a.ws.chg[v] = 0u; a.ws.ver[v] = 0u; }
   group_sync<0>(ctl->barrier);
@@ -290,7 +303,7 @@ __global__ void __launch_bounds__(512, MNB_GRID_MINBLOCKS) k_cvp_grid(const CvpK
   int sweeps = a.sweeps;
   if (sweeps < 0) sweeps = delta < 0.45f ? 0 : min(15, (int)(delta / 0.16f));
   run_band_rounds_sub8<0, true>(prob, ctl, list0, list1, mark, st, delta, gthreads, gtid, has_robot, r0, r1, r2,
-                          a.goal_dist_offset, a.cancel_flag, nextafterf(seed_max, __uint_as_float(INF_BITS)), a.max_rounds, sweeps);
+                          a.goal_dist_offset, a.cancel_flag, nextafterf(seed_max, __uint_as_float(INF_BITS)), a.max_rounds, sweeps, &sws);
   group_sync<0>(ctl->barrier);
   if (a.out_dist)
     for (uint32_t v = gtid; v < V; v += gthreads) a.out_dist[v] = __uint_as_float(state[v].x);
@@ -335,6 +348,7 @@ struct DijkstraKernelArgs {
   float* out_dist; uint32_t* out_pred;
   const int* cancel_flag;
   uint32_t max_rounds;
+  const uint4* ell_adj; int sweeps;   // whole-grid kernel only
 };
 
 template <int CS>
@@ -371,6 +385,48 @@ __global__ void __launch_bounds__(512, 1) k_dijkstra(const DijkstraKernelArgs a)
   run_band_rounds<CS>(prob, ctl, list0, list1, mark, st, delta, gthreads, gtid, has_robot, rv, rv, rv,
                       a.goal_dist_offset, a.cancel_flag, 1e-30f, a.max_rounds);
   group_sync<CS>();
+  for (uint32_t v = gtid; v < V; v += gthreads) a.out_dist[v] = __uint_as_float(state[v].x);
+}
+
+// Single Dijkstra plan on the whole GPU: 8 lanes per candidate (one edge each), wide band + in-round sweeps,
+// same engine instance as k_cvp_grid.
+__global__ void __launch_bounds__(512, 1) k_dijkstra_grid(const DijkstraKernelArgs a) {
+  __shared__ Stage st;
+  __shared__ SweepStage sws;
+  uint32_t g, gthreads, gtid;
+  group_coords<0>(g, gthreads, gtid);
+  const uint32_t V = a.V;
+  uint4* state = a.ws.state;
+  uint32_t* mark = a.ws.mark; uint32_t* list0 = a.ws.list0; uint32_t* list1 = a.ws.list1;
+  GroupCtl* ctl = a.ws.ctl;
+  if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; sws.dn[0] = 0; sws.dn[1] = 0; }
+  __syncthreads();
+  for (uint32_t v = gtid; v < V; v += gthreads) { state[v] = state_inf(); mark[v] = MARK_NONE; a.out_pred[v] = v; a.ws.ver[v] = 0u; }
+  group_sync<0>(ctl->barrier);
+  DijkstraEllProblem prob;
+  prob.adj_ptr = a.adj_ptr; prob.adj_nw = a.adj_nw; prob.cost = a.cost; prob.invalid = a.invalid;
+  prob.state = state; prob.pred = a.out_pred; prob.cost_limit = a.cost_limit; prob.deferred_m = __uint_as_float(INF_BITS);
+  prob.strict = 0; prob.ell_adj = a.ell_adj; prob.ver = a.ws.ver;
+  const int has_robot = a.robot_vertex >= 0;
+  const uint32_t rv = has_robot ? (uint32_t)a.robot_vertex : 0xffffffffu;
+  if (gtid == 0) {
+    state[a.seed_vertex] = make_uint4(0u, 0u, 0u, 0u);     // dijkstra:276 (d = 0, tau = 0)
+    mark[a.seed_vertex] = MARK_FIXED;
+    unsigned int n0 = 0;
+    prob.activate(a.seed_vertex, [&](uint32_t x) {
+      if (mark[x] == MARK_NONE && prob.eligible(x)) { mark[x] = MARK_CAND; list0[n0++] = x; }
+    });
+    ctl_reset(ctl, n0, 0.0f);
+    if (has_robot) ctl->robot_left = 1;
+  }
+  group_sync<0>(ctl->barrier);
+  float delta = a.delta;
+  if (has_robot && a.goal_dist_offset < (double)delta) delta = (float)fmax(a.goal_dist_offset, 1e-4);
+  int sweeps = a.sweeps;
+  if (sweeps < 0) sweeps = delta < 0.45f ? 0 : min(15, (int)(delta / 0.16f));
+  run_band_rounds_sub8<0, true>(prob, ctl, list0, list1, mark, st, delta, gthreads, gtid, has_robot, rv, rv, rv,
+                                a.goal_dist_offset, a.cancel_flag, 1e-30f, a.max_rounds, sweeps, &sws);
+  group_sync<0>(ctl->barrier);
   for (uint32_t v = gtid; v < V; v += gthreads) a.out_dist[v] = __uint_as_float(state[v].x);
 }
 
@@ -799,7 +855,7 @@ struct mnb_ctx {
   uint32_t* d_cor_ptr = nullptr; int4* d_cor_idx = nullptr; uint4* d_cor_eid = nullptr;
   float4* d_cor_w = nullptr; float4* d_cor_wd = nullptr;
   int4* d_ell_idx = nullptr; uint4* d_ell_eid = nullptr; float4* d_ell_w = nullptr; float4* d_ell_wd = nullptr; double4* d_ell_geo = nullptr;
-  uint32_t* d_adj_ptr = nullptr; uint32_t* d_adj_nbr = nullptr; uint32_t* d_adj_eid = nullptr; uint2* d_adj_nw = nullptr;
+  uint32_t* d_adj_ptr = nullptr; uint32_t* d_adj_nbr = nullptr; uint32_t* d_adj_eid = nullptr; uint2* d_adj_nw = nullptr; uint4* d_ell_adj = nullptr;
   float* d_edge_dist = nullptr; float* d_edge_w = nullptr; float* d_cost = nullptr; uint8_t* d_invalid = nullptr;
   bool has_invalid = false, costs_set = false;
   // workspace
@@ -824,6 +880,7 @@ struct mnb_ctx {
   int grid_blocks_per_sm = 0;
   int sweeps = -1;             // in-round sweeps of the whole-grid single-plan kernel; -1 = derived from the band width
   float grid_delta = 1.8f;     // band width of the whole-grid single-plan kernel (wide band + in-round sweeps)
+  float dijkstra_grid_delta = 3.0f;
   mnb_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -844,7 +901,7 @@ static void dfree(T*& p) { if (p) cudaFree(p); p = nullptr; }
 
 static void free_mesh(mnb_ctx* c) {
   dfree(c->d_pos); dfree(c->d_faces); dfree(c->d_edges); dfree(c->d_cor_ptr); dfree(c->d_cor_idx); dfree(c->d_cor_eid);
-  dfree(c->d_cor_w); dfree(c->d_cor_wd); dfree(c->d_ell_idx); dfree(c->d_ell_eid); dfree(c->d_ell_w); dfree(c->d_ell_wd); dfree(c->d_ell_geo); dfree(c->d_adj_ptr); dfree(c->d_adj_nbr); dfree(c->d_adj_eid); dfree(c->d_adj_nw);
+  dfree(c->d_cor_w); dfree(c->d_cor_wd); dfree(c->d_ell_idx); dfree(c->d_ell_eid); dfree(c->d_ell_w); dfree(c->d_ell_wd); dfree(c->d_ell_geo); dfree(c->d_adj_ptr); dfree(c->d_adj_nbr); dfree(c->d_adj_eid); dfree(c->d_adj_nw); dfree(c->d_ell_adj);
   dfree(c->d_edge_dist); dfree(c->d_edge_w); dfree(c->d_cost); dfree(c->d_invalid);
   dfree(c->ws.state); dfree(c->ws.minor); dfree(c->ws.chg); dfree(c->ws.ver); dfree(c->ws.mark); dfree(c->ws.list0); dfree(c->ws.list1); dfree(c->ws.ctl);
   c->ws_groups = 0;
@@ -917,7 +974,7 @@ uint32_t mnb_num_edges(mnb_ctx* ctx) { return ctx ? ctx->E : 0; }
 
 int32_t mnb_set_tuning(mnb_ctx* ctx, float band_delta, int32_t cluster_size, int32_t threads_per_cta) {
   if (!ctx) return MNB_E_ARG;
-  if (band_delta > 0) { ctx->delta = band_delta; ctx->grid_delta = band_delta; }
+  if (band_delta > 0) { ctx->delta = band_delta; ctx->grid_delta = band_delta; ctx->dijkstra_grid_delta = band_delta; }
   if (cluster_size == 1 || cluster_size == 2 || cluster_size == 4 || cluster_size == 8 || cluster_size == 16) {
     ctx->cluster = cluster_size;
     ctx->batch_cluster = cluster_size > 8 ? 8 : cluster_size;
@@ -951,7 +1008,7 @@ int32_t mnb_set_mesh(mnb_ctx* ctx, uint32_t V, uint32_t F, const float* pos, con
   CK(dalloc(&ctx->d_pos, 3 * (size_t)V)); CK(dalloc(&ctx->d_faces, 3 * (size_t)F)); CK(dalloc(&ctx->d_edges, 2 * (size_t)T.E));
   CK(dalloc(&ctx->d_cor_ptr, (size_t)V + 1)); CK(dalloc(&ctx->d_cor_idx, NC)); CK(dalloc(&ctx->d_cor_eid, NC));
   CK(dalloc(&ctx->d_cor_w, NC)); CK(dalloc(&ctx->d_cor_wd, NC));
-  CK(dalloc(&ctx->d_adj_ptr, (size_t)V + 1)); CK(dalloc(&ctx->d_adj_nbr, NA)); CK(dalloc(&ctx->d_adj_eid, NA)); CK(dalloc(&ctx->d_adj_nw, NA));
+  CK(dalloc(&ctx->d_adj_ptr, (size_t)V + 1)); CK(dalloc(&ctx->d_adj_nbr, NA)); CK(dalloc(&ctx->d_adj_eid, NA)); CK(dalloc(&ctx->d_adj_nw, NA)); CK(dalloc(&ctx->d_ell_adj, (size_t)V * ELL_W));
   CK(dalloc(&ctx->d_edge_dist, (size_t)T.E)); CK(dalloc(&ctx->d_edge_w, (size_t)T.E)); CK(dalloc(&ctx->d_cost, (size_t)V));
   CK(dalloc(&ctx->d_invalid, (size_t)V));
   CK(cudaMemcpyAsync(ctx->d_pos, pos, sizeof(float) * 3 * (size_t)V, cudaMemcpyHostToDevice, ctx->stream));
@@ -1022,6 +1079,7 @@ static int32_t install_weights(mnb_ctx* ctx) {
   k_gather_corner_w<<<(unsigned)(((size_t)ctx->V * ELL_W + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_ell_eid, ctx->d_edge_w, (size_t)ctx->V * ELL_W, ctx->d_ell_w);
   k_corner_geo<<<(unsigned)(((size_t)ctx->V * ELL_W + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_ell_w, (size_t)ctx->V * ELL_W, ctx->d_ell_geo);
   k_gather_adj_w<<<(unsigned)((ctx->NA + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_adj_nbr, ctx->d_adj_eid, ctx->d_edge_w, ctx->NA, ctx->d_adj_nw);
+  k_build_ell_adj<<<(unsigned)(((size_t)ctx->V * ELL_W + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_adj_ptr, ctx->d_adj_nw, ctx->V, ctx->d_ell_adj);
   CK(cudaGetLastError());
   ctx->costs_set = true;
   return MNB_OK;
@@ -1266,8 +1324,9 @@ int32_t mnb_dijkstra(mnb_ctx* ctx, uint32_t seed_vertex, int64_t robot_vertex, d
   cudaError_t e;
   const int cs = ctx->cluster;
   if (cs == -1) {   // single plan on the whole GPU (cooperative launch, one CTA per SM)
+    a.delta = ctx->dijkstra_grid_delta; a.ell_adj = ctx->d_ell_adj; a.sweeps = ctx->sweeps;
     void* kargs[] = {(void*)&a};
-    e = cudaLaunchCooperativeKernel((const void*)k_dijkstra<0>, dim3(ctx->sm_count), dim3(ctx->threads), kargs, 0, ctx->stream);
+    e = cudaLaunchCooperativeKernel((const void*)k_dijkstra_grid, dim3(ctx->sm_count), dim3(512), kargs, 0, ctx->stream);
   } else
   switch (cs) {
     case 1: e = launch_cluster(k_dijkstra<1>, a, 1, 1, ctx->threads, ctx->stream); break;

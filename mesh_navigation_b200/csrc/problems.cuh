@@ -51,6 +51,18 @@ struct CvpProblem {
     l.t.minor = (s.w >> 31) ? __ldcg(&minor_arr[v]) : 2u * v;
     return l;
   }
+  // the 16-byte word of a label as store_label() writes it / its decoding (minor overflow lives in minor_arr)
+  __device__ __forceinline__ uint4 pack_label(uint32_t c, float d, const EvTime& t) const {
+    uint32_t w = __float_as_uint(t.a3);
+    if (t.minor != 2u * c) w |= 0x80000000u;
+    return make_uint4(__float_as_uint(d), __float_as_uint(t.a1), __float_as_uint(t.a2), w);
+  }
+  __device__ __forceinline__ Label unpack_label(uint32_t v, const uint4& s) const {
+    Label l; l.d = __uint_as_float(s.x); l.t.a1 = __uint_as_float(s.y); l.t.a2 = __uint_as_float(s.z);
+    l.t.a3 = __uint_as_float(s.w & 0x7fffffffu);
+    l.t.minor = (s.w >> 31) ? __ldcg(&minor_arr[v]) : 2u * v;
+    return l;
+  }
   __device__ __forceinline__ void store_label(uint32_t c, float d, const EvTime& t, bool relabel, uint32_t round) const {
     uint32_t w = __float_as_uint(t.a3);
     if (t.minor != 2u * c) { __stcg(&minor_arr[c], t.minor); w |= 0x80000000u; }
@@ -227,6 +239,7 @@ constexpr uint32_t ELL_W = 8;
 constexpr int ELL_EMPTY = -1;
 
 struct CvpEllProblem : CvpProblem {
+  static constexpr bool TWO_SOURCES = true;   // an ELL slot names the two source vertices of a face
   const int4* __restrict__ ell_idx;
   const float4* __restrict__ ell_w;
   const double4* __restrict__ ell_geo;   // {p, hc, t0a, -} per slot, precomputed from ell_w (k_corner_geo)
@@ -587,6 +600,82 @@ struct DijkstraProblem {
     __stcg(&state[c], make_uint4(__float_as_uint(nd), __float_as_uint(ntau), 0u, 0u));
     pred[c] = best_u;
     return true;
+  }
+};
+
+
+// ---------------------------------------------------------------------------
+// Dijkstra, 8 lanes per candidate: the adjacency lives in an ELL table, row c = 8 slots x {neighbour, weight bits,
+// -, degree} (one 128-byte line), each lane relaxes one edge and the lexicographic argmin (tmp, du, u) -- the
+// reference's strict `<` in pop order (dijkstra:331-335) -- is taken with three shuffle steps.  Vertices with more
+// than 8 neighbours take the CSR loop on lane 0.
+// ---------------------------------------------------------------------------
+struct DijkstraEllProblem : DijkstraProblem {
+  static constexpr bool TWO_SOURCES = false;
+  const uint4* __restrict__ ell_adj;
+  uint32_t* ver;
+
+  __device__ __forceinline__ int4 load_row_idx(uint32_t c, uint32_t j) const {
+    const uint4 r = __ldg(&ell_adj[(size_t)c * ELL_W + j]);
+    return make_int4((int)r.x, (int)r.y, 0, (int)r.w);            // {neighbour or -1, weight bits, -, degree}
+  }
+  __device__ __forceinline__ float4 load_row_w(uint32_t, uint32_t) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ uint4 pack_label(uint32_t, float d, const EvTime& t) const {
+    return make_uint4(__float_as_uint(d), __float_as_uint(t.a1), 0u, 0u);
+  }
+  __device__ __forceinline__ Label unpack_label(uint32_t v, const uint4& s) const {
+    Label l; l.d = __uint_as_float(s.x); l.t = ev_normal(__uint_as_float(s.y), v);
+    return l;
+  }
+  __device__ __forceinline__ void store_label(uint32_t c, float d, const EvTime& t, bool, uint32_t) const {
+    __stcg(&state[c], make_uint4(__float_as_uint(d), __float_as_uint(t.a1), 0u, 0u));
+  }
+  // one relaxation candidate of the argmin; returns true if (tmp, du, u) precedes (best, best_du, best_u)
+  __device__ __forceinline__ static bool better(float tmp, float du, uint32_t u, float best, float best_du, uint32_t best_u) {
+    return tmp < best || (tmp == best && __float_as_uint(tmp) != INF_BITS && (du < best_du || (du == best_du && u < best_u)));
+  }
+  __device__ __noinline__ void replay_serial(uint32_t c, float band_end, float goal, float& best, uint32_t& best_u) const {
+    const uint32_t kb = adj_ptr[c], ke = adj_ptr[c + 1];
+    best = __uint_as_float(INF_BITS); float best_du = best; best_u = c;
+    for (uint32_t k = kb; k < ke; ++k) {
+      const uint2 nw = __ldg(&adj_nw[k]);
+      const uint32_t u = nw.x;
+      const float du = __uint_as_float(__ldcg(&state[u]).x);
+      if (!(du < band_end) || du > goal || (double)__ldg(&cost[u]) > cost_limit) continue;     // :299, :302
+      const float tmp = __fadd_rn(du, __uint_as_float(nw.y));                                   // :331
+      if (better(tmp, du, u, best, best_du, best_u)) { best = tmp; best_du = du; best_u = u; }
+    }
+  }
+  __device__ __forceinline__ void replay_sub8(uint32_t c, uint32_t j, bool has, const int4& ix, const float4&, float band_end,
+                                              float goal, uint32_t /*round*/, const uint32_t* mark, float& nd, EvTime& nt, int& deg_out,
+                                              uint32_t& mk1, uint32_t& mk2) const {
+    constexpr unsigned FULL = 0xffffffffu;
+    const float INF = __uint_as_float(INF_BITS);
+    const int deg = __shfl_sync(FULL, ix.w, 0, 8);
+    deg_out = deg;
+    const bool big = has && deg > (int)ELL_W;
+    float tmp = INF, du = INF; uint32_t u = 0xffffffffu;
+    if (has && !big && ix.x != ELL_EMPTY) {
+      u = (uint32_t)ix.x;
+      du = __uint_as_float(__ldcg(reinterpret_cast<const uint32_t*>(state) + 4 * (size_t)u));
+      mk1 = __ldcg(&mark[u]);
+      const float cu = __ldg(&cost[u]);
+      if (du < band_end && !(du > goal) && !((double)cu > cost_limit))                         // :299, :302
+        tmp = __fadd_rn(du, __int_as_float(ix.y));                                             // :331
+      else du = INF;
+    }
+    mk2 = MARK_FIXED;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const float ot = __shfl_xor_sync(FULL, tmp, o, 8), od = __shfl_xor_sync(FULL, du, o, 8);
+      const uint32_t ou = __shfl_xor_sync(FULL, u, o, 8);
+      if (better(ot, od, ou, tmp, du, u)) { tmp = ot; du = od; u = ou; }
+    }
+    if (big && j == 0) replay_serial(c, band_end, goal, tmp, u);
+    if (__ballot_sync(FULL, big)) { tmp = __shfl_sync(FULL, tmp, 0, 8); u = __shfl_sync(FULL, u, 0, 8); }
+    nd = tmp; nt = ev_normal(tmp, c);
+    // predecessor of the winning relaxation (it can change among exact ties without the potential changing)
+    if (has && j == 0 && __float_as_uint(tmp) != INF_BITS) pred[c] = u;
   }
 };
 

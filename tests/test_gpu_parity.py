@@ -40,7 +40,7 @@ def test_edge_distances_bit_exact(api, oracle_mod):
     mm.close()
 
 
-@pytest.mark.parametrize("n,terrain,cluster", [(100, False, 1), (100, False, 8), (64, True, 2), (200, True, 16), (150, True, 4)])
+@pytest.mark.parametrize("n,terrain,cluster", [(100, False, 1), (100, False, 8), (64, True, 2), (200, True, 16), (150, True, 4), (120, False, -1), (300, True, -1)])
 def test_dijkstra_bit_exact(api, oracle_mod, n, terrain, cluster):
     """config 1: DijkstraMeshPlanner single goal, 10k planar mesh (+ terrain variants)"""
     pos, faces, om, mm, ed, vc, w = setup(api, oracle_mod, n, terrain)
