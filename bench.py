@@ -79,6 +79,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(workload):
+    """dram bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture"""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
 def build_workload(n):
     from mesh_navigation_b200 import synth
     pos, faces = synth.grid_mesh(n, n, terrain=True, seed=42)
@@ -178,6 +187,7 @@ def main():
     ap.add_argument("--batch-goals", type=int, default=1024, help="goals of the batched leg (config 4); 0 disables it")
     ap.add_argument("--batch-size", type=int, default=1000, help="grid side of the batched leg's mesh")
     ap.add_argument("--batch-steps", type=int, default=2)
+    ap.add_argument("--no-other-kernels", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -321,6 +331,41 @@ def main():
         del res
         bm.close()
 
+    # ---- the other hot-path kernels on the same mesh (rank 0, one run each after a warm-up; SURVEY 8a rows a1/a7/a10 + f1/f2) ----
+    other = None
+    if rank == 0 and not args.no_other_kernels:
+        from mesh_navigation_b200 import synth
+        from mesh_navigation_b200.api import DijkstraMeshPlanner, InflationLayer
+        hbm0 = peaks()[0]
+        other = {}
+        seed_v = int(faces[sf][0])
+        for rep in range(2):
+            D = DijkstraMeshPlanner(mm).dijkstra(seed_v)
+        other["dijkstra_full_field"] = {"kernel_ms": D["kernel_ms"], "rounds": int(D["rounds"]), "vertices_per_s": V / (D["kernel_ms"] * 1e-3),
+                                        "hbm_frac": 92 * V / (D["kernel_ms"] * 1e-3) / 1e9 / hbm0}
+        for rep in range(2):
+            Ly = mm.computeLayers()
+        other["fused_layers"] = {"kernel_ms": Ly["kernel_ms"], "hbm_frac": 837 * V / (Ly["kernel_ms"] * 1e-3) / 1e9 / hbm0}
+        le = np.union1d(np.where(Ly["lethal_mask"] != 0)[0], synth.disc_lethals_grid(pos, n, n, 1000, 0.3)).astype(np.uint32)
+        for rep in range(2):
+            I = InflationLayer(mm).waveCostInflation(le)
+        nin = int(np.isfinite(I["dist"]).sum())
+        other["inflation"] = {"kernel_ms": I["kernel_ms"], "rounds": int(I["rounds"]), "lethal_vertices": int(le.size), "labelled_vertices": nin,
+                              "hbm_frac": 212 * nin / (I["kernel_ms"] * 1e-3) / 1e9 / hbm0}
+        del Ly, I
+        # a whole makePlan through the host API: localisation of both poses, wavefront until the robot face is fixed,
+        # vector-field back-tracking on the device; only the path crosses PCIe
+        corner = lambda u, v: pos[int(v * (n - 1)) * n + int(u * (n - 1))]
+        pts = np.stack([corner(0.1, 0.1), corner(0.9, 0.9)]).astype(np.float32)
+        mm.setCosts(vc, ed)
+        for rep in range(2):
+            t0 = time.perf_counter()
+            nv, fc, ba = mm.locate(pts)
+            mp = planner.makePlan(pts[0], int(fc[0]), pts[1], int(fc[1]))
+            tmp = time.perf_counter() - t0
+        other["make_plan_corner_to_corner"] = {"wall_ms": 1e3 * tmp, "wavefront_kernel_ms": mp.get("wavefront_ms"), "path_points": int(len(mp["positions"])),
+                                               "path_length_m": mp["cost"], "outcome": int(mp["outcome"])}
+
     if rank == 0:
         hbm, which = peaks()
         k_ms = float(np.mean(kernel_ms))
@@ -335,14 +380,16 @@ def main():
             "e2e": {"value": e2e_value, "unit": "vertices/s", "h2d_bytes_per_step": int(4 * V + 4 * E),
                     "d2h_bytes_per_step": int(16 * V), "steps": e2e_steps},
             "gpu_launches": int(args.steps * st["kernel_launches"]),
-            "roofline": {"bound": "hbm", "kernel": "k_cvp", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                         "frac": achieved / hbm, "traffic": None, "peak_source": which,
+            "roofline": {"bound": "hbm", "kernel": "k_cvp_grid", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                         "frac": achieved / hbm, "traffic": ncu_traffic(f"cvp_full_field_terrain_{n}x{n}"), "peak_source": which,
                          "kernel_ms": k_ms, "rounds": int(st["rounds"]), "recomputes_per_vertex": st["recomputes"] / V,
                          "note": "single wavefront is dependency-latency bound (SURVEY.md H3)"},
             "clocks": clocks,
         }
         if batched:
             line["batched"] = batched
+        if other:
+            line["other_kernels"] = other
         if not args.no_cpu_baseline:
             from oracle import oracle as O
             om = O.OracleMesh(pos, faces)            # same mesh, same goal as the timed plans

@@ -639,14 +639,31 @@ __device__ __forceinline__ bool projected_barycentric(F3 p, F3 a, F3 b, F3 c, fl
          (0 - EPSILON <= gamma) && (gamma <= 1 + EPSILON);
 }
 
-constexpr int BT_LIST_CAP = 4096;
+// One warp walks the path.  The scalar parts (position, current face, direction blend) are computed redundantly by
+// all lanes; searchNeighbourFaces -- a breadth-first list of up to a few hundred faces per step -- is spread over
+// the lanes 32 faces at a time: containment tests in parallel, expansions gathered per lane, deduplicated through a
+// shared-memory hash set and appended in exactly the order the sequential loop of mesh_map.cpp:1031-1063 would
+// produce (lane-major sequence numbers + atomicMin decide which duplicate came first), so the face that is returned
+// is the same one.
+constexpr int BT_LIST_CAP = 4096;      // faces in the search list
+constexpr int BT_HASH_CAP = 8192;      // open-addressing set over face ids (power of two)
+constexpr int BT_MAXC = 64;            // expansion candidates of one listed face (<= sum of its vertices' face counts)
+struct BtShared {
+  uint32_t list[BT_LIST_CAP];
+  uint32_t hkey[BT_HASH_CAP];
+  uint32_t hseq[BT_HASH_CAP];
+  uint32_t cand[32][BT_MAXC];
+  uint16_t cslot[32][BT_MAXC];
+};
 
 __global__ void __launch_bounds__(32) k_backtrack(BacktrackArgs a) {
-  __shared__ uint32_t possible[BT_LIST_CAP];
-  if (threadIdx.x != 0) return;
+  extern __shared__ __align__(16) unsigned char bt_raw[];
+  BtShared& S = *reinterpret_cast<BtShared*>(bt_raw);
+  constexpr unsigned FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x;
   uint32_t n = 0;
   auto push = [&](F3 p, uint32_t f) {
-    if (n < a.max_points) { a.path_pos[3 * n] = p.x; a.path_pos[3 * n + 1] = p.y; a.path_pos[3 * n + 2] = p.z; a.path_face[n] = f; }
+    if (lane == 0 && n < a.max_points) { a.path_pos[3 * n] = p.x; a.path_pos[3 * n + 1] = p.y; a.path_pos[3 * n + 2] = p.z; a.path_face[n] = f; }
     ++n;
   };
   uint32_t face = a.goal_face;
@@ -671,25 +688,83 @@ __global__ void __launch_bounds__(32) k_backtrack(BacktrackArgs a) {
       float vcm = 0;
       for (int k = 0; k < 3; ++k) { const F3 e = f3sub(f3load(a.pos, t[k]), center); vcm = fmaxf(vcm, sqrtf(f3dot(e, e))); }
       const float ext = step + vcm, rsq = ext * ext;
-      uint32_t cnt = 1; possible[0] = face;
+      for (uint32_t i = lane; i < (uint32_t)BT_HASH_CAP; i += 32) { S.hkey[i] = 0xffffffffu; S.hseq[i] = 0xffffffffu; }
+      __syncwarp();
+      auto slot_of = [](uint32_t key) { return (key * 2654435761u) >> (32 - 13); };
+      static_assert(BT_HASH_CAP == (1 << 13), "hash shift");
+      if (lane == 0) {
+        S.list[0] = face;
+        const uint32_t h = slot_of(face); S.hkey[h] = face; S.hseq[h] = 0u;
+      }
+      __syncwarp();
+      uint32_t cnt = 1, it = 0;
       bool overflow = false;
-      for (uint32_t it = 0; it < cnt && !ok; ++it) {
-        const uint32_t* q = a.faces + 3 * (size_t)possible[it];
-        if (projected_barycentric(pos, f3load(a.pos, q[0]), f3load(a.pos, q[1]), f3load(a.pos, q[2]), bary, dist) && fabsf(dist) < 0.4f) {
-          face = possible[it]; ok = true; break;
+      while (it < cnt && !ok) {
+        const uint32_t chunk = min(32u, cnt - it);
+        const bool act = lane < chunk;
+        const uint32_t f = act ? S.list[it + lane] : 0u;
+        const uint32_t* q = a.faces + 3 * (size_t)f;
+        const uint32_t q0 = q[0], q1 = q[1], q2 = q[2];
+        const F3 P0 = f3load(a.pos, q0), P1 = f3load(a.pos, q1), P2 = f3load(a.pos, q2);
+        float lb[3], ld;
+        const bool pass = act && projected_barycentric(pos, P0, P1, P2, lb, ld) && fabsf(ld) < 0.4f;
+        const unsigned pm = __ballot_sync(FULL, pass);
+        if (pm) {
+          const int L = __ffs(pm) - 1;
+          face = __shfl_sync(FULL, f, L);
+          bary[0] = __shfl_sync(FULL, lb[0], L); bary[1] = __shfl_sync(FULL, lb[1], L); bary[2] = __shfl_sync(FULL, lb[2], L);
+          ok = true;
+          break;
         }
-        for (int k = 0; k < 3; ++k) {
-          const F3 e = f3sub(center, f3load(a.pos, q[k]));
-          if (!(f3dot(e, e) < rsq)) continue;
-          for (uint32_t j = a.cor_ptr[q[k]]; j < a.cor_ptr[q[k] + 1]; ++j) {
-            const uint32_t nf = (uint32_t)a.cor_idx[j].z;
-            bool seen = false;
-            for (uint32_t s = 0; s < cnt; ++s) if (possible[s] == nf) { seen = true; break; }
-            if (seen) continue;
-            if (cnt >= BT_LIST_CAP) { overflow = true; continue; }
-            possible[cnt++] = nf;
+        // expansion candidates of my face, in the reference's order: vertex 0, 1, 2; faces of the vertex in CSR order
+        uint32_t nc = 0;
+        if (act) {
+          const uint32_t qv[3] = {q0, q1, q2};
+          const F3 PV[3] = {P0, P1, P2};
+          for (int k = 0; k < 3; ++k) {
+            const F3 e = f3sub(center, PV[k]);
+            if (!(f3dot(e, e) < rsq)) continue;
+            for (uint32_t jx = a.cor_ptr[qv[k]]; jx < a.cor_ptr[qv[k] + 1]; ++jx) {
+              if (nc < (uint32_t)BT_MAXC) S.cand[lane][nc] = (uint32_t)a.cor_idx[jx].z;
+              ++nc;
+            }
           }
         }
+        if (__any_sync(FULL, nc > (uint32_t)BT_MAXC)) { overflow = true; break; }
+        __syncwarp();
+        // insert all candidates; among duplicates the smallest sequence number (= first in sequential order) wins
+        for (uint32_t i = 0; i < nc; ++i) {
+          const uint32_t key = S.cand[lane][i], seq = lane * (uint32_t)BT_MAXC + i + 1u;
+          uint32_t h = slot_of(key);
+          for (;;) {
+            const uint32_t old = atomicCAS(&S.hkey[h], 0xffffffffu, key);
+            if (old == 0xffffffffu || old == key) break;
+            h = (h + 1u) & (uint32_t)(BT_HASH_CAP - 1);
+          }
+          atomicMin(&S.hseq[h], seq);
+          S.cslot[lane][i] = (uint16_t)h;
+        }
+        __syncwarp();
+        uint32_t newc = 0;
+        for (uint32_t i = 0; i < nc; ++i) newc += (S.hseq[S.cslot[lane][i]] == lane * (uint32_t)BT_MAXC + i + 1u) ? 1u : 0u;
+        uint32_t incl = newc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if ((int)lane >= o) incl += v; }
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        if (cnt + total > (uint32_t)BT_LIST_CAP) { overflow = true; break; }
+        uint32_t w = cnt + incl - newc;
+        __syncwarp();
+        for (uint32_t i = 0; i < nc; ++i) {
+          const uint32_t h = S.cslot[lane][i];
+          if (S.hseq[h] == lane * (uint32_t)BT_MAXC + i + 1u) S.list[w++] = S.cand[lane][i];
+        }
+        __syncwarp();
+        for (uint32_t i = 0; i < nc; ++i) {            // commit: members of the list can never be "new" again
+          const uint32_t h = S.cslot[lane][i];
+          if (S.hseq[h] == lane * (uint32_t)BT_MAXC + i + 1u) S.hseq[h] = 0u;
+        }
+        __syncwarp();
+        cnt += total; it += chunk;
       }
       if (!ok) { outcome = overflow ? MNB_E_STATE : MNB_NO_PATH_FOUND; break; }
       t = a.faces + 3 * (size_t)face;
@@ -712,7 +787,7 @@ __global__ void __launch_bounds__(32) k_backtrack(BacktrackArgs a) {
     push(pos, face);
   }
   if (outcome == MNB_SUCCESS) push(st, a.start_face);                            // cvp:951
-  a.result[0] = outcome; a.result[1] = (int32_t)n;
+  if (lane == 0) { a.result[0] = outcome; a.result[1] = (int32_t)n; }
 }
 
 // ============================================================================
@@ -1442,7 +1517,8 @@ int32_t mnb_cvp_backtrack(mnb_ctx* ctx, const float robot_pos[3], uint32_t robot
   a.start_face = ctx->last_seed_face; a.goal_face = robot_face; a.step_width = step_width; a.max_points = max_points;
   a.path_pos = ctx->d_path_pos; a.path_face = ctx->d_path_face; a.result = ctx->d_bt_result; a.cancel_flag = ctx->d_cancel;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  k_backtrack<<<1, 32, 0, ctx->stream>>>(a);
+  CK(cudaFuncSetAttribute(k_backtrack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BtShared)));
+  k_backtrack<<<1, 32, sizeof(BtShared), ctx->stream>>>(a);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   int32_t res[2] = {0, 0};

@@ -183,3 +183,21 @@ def batch_goal_vertices(V: int, n: int, seed: int = 1234, blocked=None) -> np.nd
 def nearest_vertex(pos: np.ndarray, p) -> int:
     d = pos.astype(np.float64) - np.asarray(p, dtype=np.float64)[None, :]
     return int(np.argmin(np.einsum("ij,ij->i", d, d)))
+
+
+def disc_lethals_grid(pos: np.ndarray, nx: int, ny: int, n_discs: int, radius: float, h: float = 0.1, seed: int = 7) -> np.ndarray:
+    """Synthetic obstacle lethals of SURVEY 8d config 3 on a grid_mesh: vertices within `radius` (xy) of n_discs
+    centre vertices drawn from PCG32(seed).  Same set as the exhaustive scan (tests/util.disc_lethals), but only the
+    index window around each centre is examined."""
+    V = nx * ny
+    centres = pcg32_stream(seed, n_discs, V)
+    k = int(np.ceil(radius / h)) + 2                      # jitter is +-0.2 h per vertex
+    di, dj = np.meshgrid(np.arange(-k, k + 1), np.arange(-k, k + 1), indexing="xy")
+    ci, cj = centres % nx, centres // nx
+    ii = ci[:, None] + di.ravel()[None, :]
+    jj = cj[:, None] + dj.ravel()[None, :]
+    ok = (ii >= 0) & (ii < nx) & (jj >= 0) & (jj < ny)
+    idx = np.where(ok, jj * nx + ii, 0)
+    d = pos[idx, :2] - pos[centres, None, :2]
+    inside = ok & (np.abs(d).max(2) <= radius) & ((d ** 2).sum(2) <= radius * radius)
+    return np.unique(idx[inside]).astype(np.uint32)
