@@ -275,8 +275,9 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
                                      const int has_robot, const uint32_t r0, const uint32_t r1, const uint32_t r2,
                                      const double goal_dist_offset, const volatile int* cancel_flag,
                                      const float band_end_init, const uint32_t max_rounds, const int n_sweeps_arg,
-                                     SweepStage* ss) {
+                                     SweepStage* ss, const uint32_t n_vertices) {
   const int n_sweeps = SW ? n_sweeps_arg : 0;
+  bool rescanned = false;
   float band_end_prev = band_end_init;
   unsigned long long my_recomputes = 0, my_settled = 0;
   float lo_best = -1.0f; int stagnant = 0;       // best (largest) earliest-unsettled pop time seen so far
@@ -292,8 +293,12 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
     const unsigned int goal_b = __ldcg(&ctl->goal_ring[r & 1]);
     const float goal = __uint_as_float(goal_b);
     const unsigned int stop = __ldcg(&ctl->stop_ring[r & 1]);
-    if (n == 0 || stop || r > max_rounds) break;   // r is group-uniform: the watchdog cannot deadlock the barrier
-    if (r > 0 && __float_as_uint(m_prev) == INF_BITS &&
+    // the round in which the goal cutoff first becomes visible must run even if nothing else is left to do: it puts the
+    // vertices that settled beyond the cutoff back into the list (see below)
+    const bool need_rescan = has_robot && goal_b != INF_BITS && !rescanned;
+    if (stop || r > max_rounds) break;             // r is group-uniform: the watchdog cannot deadlock the barrier
+    if (!need_rescan && n == 0) break;
+    if (!need_rescan && r > 0 && __float_as_uint(m_prev) == INF_BITS &&
         (__float_as_uint(lo_prev) == INF_BITS || lo_prev > goal)) break;
     // stagnation watch (all values are group-uniform): labels keep changing but the earliest unsettled pop
     // time does not move -> a dependency cycle between a trigger and its back-step child; arm the strict rule
@@ -310,8 +315,28 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
       atomicMin(&ctl->goal_ring[(r + 1) & 1], goal_b);                 // carry the cutoff into the next round
       ctl->stop_ring[(r + 1) & 1] = (stop || (cancel_flag && (r & 31) == 0 && *cancel_flag)) ? 1u : 0u;
     }
+    // Goal cutoff (cvp:754 / dijkstra:299) with a band wider than goal_dist_offset: labels computed before the cutoff
+    // is known may rest on sources that turn out to lie beyond it.  Once it is known, (1) vertices beyond it never
+    // settle any more -- they are recomputed under the cutoff until nothing changes -- and (2) the ones that had already
+    // settled are put back into the candidate list by one sweep over the vertex array (their labels only depend on
+    // vertices inside the cutoff, which are unaffected, so a single recompute repairs them).
+    const float settle_cap = (has_robot && goal_b != INF_BITS) ? nextafterf(goal, __uint_as_float(INF_BITS)) : __uint_as_float(INF_BITS);
+    bool requeued = false;
+    if (need_rescan) {
+      rescanned = true;
+      for (uint32_t v = gtid; v < n_vertices; v += gthreads) {
+        if (__ldcg(&mark[v]) != MARK_FIXED) continue;
+        const float tv = __uint_as_float(__ldcg(&prob.state[v]).y);
+        if (tv > goal) {
+          mark[v] = MARK_CAND_ACT;
+          if constexpr (SW) stage_push_seen(st, *ss, v, SEEN_NEVER, __ldcg(&prob.state[v]), list_n, &ctl->count[next]);
+          else stage_push(st, v, list_n, &ctl->count[next]);
+          requeued = true;
+        }
+      }
+    }
     const long long tp0 = clock64();
-    float my_mtau = __uint_as_float(INF_BITS), my_lo = __uint_as_float(INF_BITS);
+    float my_mtau = requeued ? goal : __uint_as_float(INF_BITS), my_lo = requeued ? goal : __uint_as_float(INF_BITS);   // a pending change
     // One evaluation of candidate c by its 8-lane group (every lane of the WARP calls this; idle groups pass
     // has = false so that the sub-warp shuffles can use compile-time full masks).  `fresh` = main pass (c comes from
     // the round's list and is pushed to the stage); otherwise c already sits in the stage (in-round sweep).
@@ -385,7 +410,7 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
       uint32_t v0 = 0;
       if constexpr (SW) if (n_sweeps > 0) v0 = __ldcg(&prob.ver[has ? c : 0u]);
       const float d = old.d, tau = old.t.a1;
-      if (has && tau < m_prev && tau < band_end_prev) {
+      if (has && tau < m_prev && tau < band_end_prev && tau < settle_cap) {
         if (j == 0) {
           mark[c] = MARK_FIXED;
           my_settled++;

@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(MNB_CVP_THREADS, MNB_CVP_MINBLOCKS) k_cvp(cons
     float delta = a.delta;
     if (has_robot && a.goal_dist_offset < (double)delta) delta = (float)fmax(a.goal_dist_offset, 1e-4);
     run_band_rounds_sub8<CS, false>(prob, ctl, list0, list1, mark, st, delta, gthreads, gtid, has_robot, r0, r1, r2,
-                        a.goal_dist_offset, a.cancel_flag, nextafterf(seed_max, __uint_as_float(INF_BITS)), a.max_rounds, sweeps, nullptr);
+                        a.goal_dist_offset, a.cancel_flag, nextafterf(seed_max, __uint_as_float(INF_BITS)), a.max_rounds, sweeps, nullptr, V);
     group_sync<CS>();
     if (a.out_dist) {
       float* od = a.out_dist + (size_t)q * V;
@@ -297,13 +297,12 @@ __global__ void __launch_bounds__(512, MNB_GRID_MINBLOCKS) k_cvp_grid(const CvpK
     }
   }
   group_sync<0>(ctl->barrier);
-  float delta = a.delta;
-  if (has_robot && a.goal_dist_offset < (double)delta) delta = (float)fmax(a.goal_dist_offset, 1e-4);
+  const float delta = a.delta;      // not clamped to goal_dist_offset: the engine caps settling instead (settle_cap)
   // in-round sweeps pay off once the band is several dependency hops deep (one hop ~ 0.15 m of potential on these meshes)
   int sweeps = a.sweeps;
   if (sweeps < 0) sweeps = delta < 0.45f ? 0 : min(15, (int)(delta / 0.16f));
   run_band_rounds_sub8<0, true>(prob, ctl, list0, list1, mark, st, delta, gthreads, gtid, has_robot, r0, r1, r2,
-                          a.goal_dist_offset, a.cancel_flag, nextafterf(seed_max, __uint_as_float(INF_BITS)), a.max_rounds, sweeps, &sws);
+                          a.goal_dist_offset, a.cancel_flag, nextafterf(seed_max, __uint_as_float(INF_BITS)), a.max_rounds, sweeps, &sws, V);
   group_sync<0>(ctl->barrier);
   if (a.out_dist)
     for (uint32_t v = gtid; v < V; v += gthreads) a.out_dist[v] = __uint_as_float(state[v].x);
@@ -420,12 +419,11 @@ __global__ void __launch_bounds__(512, 1) k_dijkstra_grid(const DijkstraKernelAr
     if (has_robot) ctl->robot_left = 1;
   }
   group_sync<0>(ctl->barrier);
-  float delta = a.delta;
-  if (has_robot && a.goal_dist_offset < (double)delta) delta = (float)fmax(a.goal_dist_offset, 1e-4);
+  const float delta = a.delta;      // not clamped to goal_dist_offset: the engine caps settling instead (settle_cap)
   int sweeps = a.sweeps;
   if (sweeps < 0) sweeps = delta < 0.45f ? 0 : min(15, (int)(delta / 0.16f));
   run_band_rounds_sub8<0, true>(prob, ctl, list0, list1, mark, st, delta, gthreads, gtid, has_robot, rv, rv, rv,
-                                a.goal_dist_offset, a.cancel_flag, 1e-30f, a.max_rounds, sweeps, &sws);
+                                a.goal_dist_offset, a.cancel_flag, 1e-30f, a.max_rounds, sweeps, &sws, V);
   group_sync<0>(ctl->barrier);
   for (uint32_t v = gtid; v < V; v += gthreads) a.out_dist[v] = __uint_as_float(state[v].x);
 }

@@ -675,7 +675,8 @@ struct DijkstraEllProblem : DijkstraProblem {
     if (__ballot_sync(FULL, big)) { tmp = __shfl_sync(FULL, tmp, 0, 8); u = __shfl_sync(FULL, u, 0, 8); }
     nd = tmp; nt = ev_normal(tmp, c);
     // predecessor of the winning relaxation (it can change among exact ties without the potential changing)
-    if (has && j == 0 && __float_as_uint(tmp) != INF_BITS) pred[c] = u;
+    // (a label can also fall back to +inf when the goal cutoff removes its sources: predecessor = self, dijkstra:269)
+    if (has && j == 0) pred[c] = __float_as_uint(tmp) != INF_BITS ? u : c;
   }
 };
 

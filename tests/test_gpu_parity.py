@@ -515,3 +515,25 @@ def test_locate_parity(api, oracle_mod, n, nq):
     assert (gb[inside] >= -0.0100001).all() and (gb[inside] <= 1.0100001).all()
     assert mm.getNearestVertexHandle(pts[0]) == ov[0] and mm.getContainingFace(pts[0]) == of[0]
     mm.close()
+
+
+@pytest.mark.parametrize("n", [24, 48, 90])
+def test_goal_cutoff_small_mesh_wide_band(api, oracle_mod, n):
+    """goal cutoff (cvp:754,763-771 / dijkstra:293-300) when the band is wider than the whole mesh: everything settles
+    before the cutoff is known and the vertices beyond it have to be put back and recomputed"""
+    pos, faces, om, mm, ed, vc, w = setup(api, oracle_mod, n, True)
+    sv, sf, sp = centre_seed(pos, faces, (0.3, 0.3))
+    rv, rf, rp = centre_seed(pos, faces, (0.55, 0.6))
+    ref = om.dijkstra(w, vc, sv, rv)
+    got = api.DijkstraMeshPlanner(mm).dijkstra(sv, rv)
+    assert got["outcome"] == ref["outcome"] == 0
+    assert (got["dist"].view(np.uint32) == ref["dist"].view(np.uint32)).all()
+    assert (got["pred"] == ref["pred"]).all()
+    assert np.isinf(ref["dist"]).any() or n < 60          # the cutoff really cut something off
+    ref = om.cvp(w, vc, sf, sp, rf)
+    got = api.CVPMeshPlanner(mm).waveFrontPropagation(sf, sp, rf)
+    assert got["outcome"] == ref["outcome"] == 0
+    assert rel_err(got["dist"], ref["dist"]).max() <= 1e-4
+    assert (got["dist"].view(np.uint32) == ref["dist"].view(np.uint32)).all()
+    assert (got["pred"] == ref["pred"]).all()
+    mm.close()
