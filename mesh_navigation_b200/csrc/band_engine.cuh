@@ -304,7 +304,14 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
     // time does not move -> a dependency cycle between a trigger and its back-step child; arm the strict rule
     if (r > 0 && __float_as_uint(m_prev) != INF_BITS && !(lo_prev > lo_best)) { if (++stagnant >= STAGNATION_ROUNDS) prob.strict = 1; }
     else { stagnant = 0; if (lo_prev > lo_best) lo_best = lo_prev; }
-    float band_end = lo_prev + delta;
+    // the sweeps work on the first SW_CAP stage slots of a CTA: on very long fronts (tens of millions of vertices) the
+    // band is narrowed so that a CTA's share of the list still fits (group-uniform, exactness does not depend on it)
+    float delta_r = delta;
+    if constexpr (SW) {
+      const float fit = (float)nblk * (0.8f * (float)Stage::SW_CAP);
+      if ((float)n > fit) delta_r = fmaxf(0.25f * delta, delta * fit / (float)n);
+    }
+    float band_end = lo_prev + delta_r;
     if (!(band_end > band_end_prev)) band_end = band_end_prev;
     uint32_t* list_r = (r & 1) ? list1 : list0;
     uint32_t* list_n = (r & 1) ? list0 : list1;
