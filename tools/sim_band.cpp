@@ -22,6 +22,9 @@ using namespace mnb;
 namespace {
 constexpr float FINF = std::numeric_limits<float>::infinity();
 
+#ifndef SIM_ANGLES
+#define SIM_ANGLES false
+#endif
 constexpr int MAXL = 12;
 static int g_levels = 3;   // the CUDA labels track 3 water levels
 struct Tm3 { float a[MAXL]; uint32_t minor; };
@@ -95,7 +98,7 @@ struct Sim {
       if (!tless(cs[i].T, tc)) break;
       CvpResult r;
       const uint32_t k = cs[i].k;
-      if (cvp_update_t<false>(cs[i].u1, cs[i].u2, cur, w[T.cor_ea[k]], w[T.cor_eb[k]], w[T.cor_ec[k]], r)) {
+      if (cvp_update_t<SIM_ANGLES>(cs[i].u1, cs[i].u2, cur, w[T.cor_ea[k]], w[T.cor_eb[k]], w[T.cor_ec[k]], r)) {
         // a back-step label is only taken from a trigger that has been stable for a whole round
         if (!(r.value > cs[i].T.a[0]) && !(chg[cs[i].tv] < round)) { blocked_m = std::fmin(blocked_m, cs[i].T.a[0]); deferred_flag = true; continue; }
         cur = r.value;
