@@ -36,10 +36,21 @@ def run_case(name):
         le = disc_lethals(pos, 3, 0.25, seed=5)
         r = m.inflation(ed, le)
         return dict(dist=r["dist"], cost=r["cost"])
+    if name.startswith("path"):
+        # f1/f2 rows: vector map, back-tracking walk and localisation on the same cost-weighted terrain
+        rv, rf, rp = centre_seed(pos, faces, (0.85, 0.2))
+        r = m.cvp(w, vc, f, sp, rf)
+        vn = m.layers()["vertex_normals"]
+        vm = m.cvp_vector_map(vn, r["pred"], r["direction"], r["cutting_face"])
+        rc, pp, pf = m.cvp_backtrack(vm, sp, f, rp, rf, 0.4)
+        q = np.stack([rp, sp, pos[17] + np.float32(0.02), pos[faces[100]].mean(0) + np.float32([0, 0, 0.05])]).astype(np.float32)
+        nv, fc, ba = m.locate(q)
+        return dict(vector_map=vm, outcome=np.int32(rc), path_pos=pp, path_face=pf, loc_vertex=nv, loc_face=fc, loc_bary=ba,
+                    dijkstra_vector_map=m.dijkstra_vector_map(m.dijkstra(w, vc, v)["pred"]))
     raise KeyError(name)
 
 
 if __name__ == "__main__":
-    for n in ["cvp_planar30", "cvp_terrain30", "dijkstra_terrain30", "inflation_terrain30"]:
+    for n in ["cvp_planar30", "cvp_terrain30", "dijkstra_terrain30", "inflation_terrain30", "path_terrain30"]:
         np.savez_compressed(os.path.join(HERE, n + ".npz"), **run_case(n))
         print("wrote", n)

@@ -119,7 +119,7 @@ def test_goal_cutoff_and_no_path(oracle_mod):
     assert m.cvp(ed, vc, f, sp, robot_face=rf)["outcome"] == 0
 
 
-@pytest.mark.parametrize("name", ["cvp_planar30", "cvp_terrain30", "dijkstra_terrain30", "inflation_terrain30"])
+@pytest.mark.parametrize("name", ["cvp_planar30", "cvp_terrain30", "dijkstra_terrain30", "inflation_terrain30", "path_terrain30"])
 def test_committed_fixtures(oracle_mod, name):
     """Fixtures under tests/golden were generated by tests/golden/make_fixtures.py from this oracle
     (the reference cannot run here); they guard the oracle against silent changes."""
@@ -131,3 +131,42 @@ def test_committed_fixtures(oracle_mod, name):
     for k in gold.files:
         a, b = gold[k], now[k]
         assert a.shape == b.shape and (a.view(np.uint32) == b.view(np.uint32)).all(), f"{name}:{k} drifted"
+
+
+def test_next_rows_sanity(oracle_mod):
+    """f1/f2 restatements (cvp:204-239, 920-951; mesh_map.cpp:999-1174; util.cpp:313-347): derived properties on a planar
+    mesh -- parity for these rows is unpinned by the reference (no test there), so these are sanity bounds."""
+    from tests.util import centre_seed, mesh_case
+    pos, faces = mesh_case(60, False)
+    m = oracle_mod.OracleMesh(pos, faces)
+    ed = m.edge_distances(); vc = np.zeros(m.V, np.float32)
+    sv, sf, sp = centre_seed(pos, faces, (0.2, 0.3))
+    rv, rf, rp = centre_seed(pos, faces, (0.8, 0.75))
+    r = m.cvp(ed, vc, sf, sp, rf)
+    assert r["outcome"] == 0
+    vn = m.layers()["vertex_normals"]
+    vm = m.cvp_vector_map(vn, r["pred"], r["direction"], r["cutting_face"])
+    has = ~np.isnan(vm).any(1)
+    assert np.allclose(np.linalg.norm(vm[has], axis=1), 1.0, atol=1e-5)
+    # on a plane the field points straight at the seed (continuous vector field: that is the point of the CVP)
+    to_seed = sp[None, :2] - pos[has, :2]
+    far = np.linalg.norm(to_seed, axis=1) > 0.5
+    cosang = (vm[has][far, :2] * to_seed[far]).sum(1) / np.linalg.norm(to_seed[far], axis=1)
+    assert np.median(cosang) > 0.999 and np.percentile(cosang, 5) > 0.98 and cosang.min() > 0.5   # edge fallbacks at the rim
+    # Dijkstra's field only knows edge directions
+    dj = m.dijkstra(ed, vc, sv)
+    dvm = m.dijkstra_vector_map(dj["pred"])
+    assert np.isnan(dvm[sv]).all() and np.allclose(np.linalg.norm(dvm[~np.isnan(dvm).any(1)], axis=1), 1.0, atol=1e-5)
+    # back-tracking: robot -> seed, steps of step_width, nearly the straight line on a plane
+    rc, pp, pf = m.cvp_backtrack(vm, sp, sf, rp, rf, 0.4)
+    assert rc == 0 and (pp[0] == rp).all() and (pp[-1] == sp).all() and pf[0] == rf and pf[-1] == sf
+    seg = np.linalg.norm(np.diff(pp, axis=0), axis=1)
+    assert np.allclose(seg[:-1], 0.4, atol=2e-3) and seg[-1] <= np.sqrt(0.4) + 1e-3      # cvp:925 compares distance^2 with step_width
+    chord = np.linalg.norm(rp - sp)
+    assert chord <= seg.sum() <= 1.02 * chord + 0.4
+    # localisation: a point inside a face is found in that face with its barycentric coordinates
+    f = 1234; b = np.float32([0.2, 0.5, 0.3])
+    q = (pos[faces[f]] * b[:, None]).sum(0)
+    nv, fc, ba = m.locate(np.stack([q, pos[77], q + np.float32([100, 0, 0])]))
+    assert fc[0] == f and np.allclose(ba[0], b, atol=1e-4) and nv[1] == 77 and fc[2] == -1
+    assert nv[0] in faces[f]
