@@ -115,12 +115,6 @@ struct SweepStage {
 };
 constexpr uint32_t SEEN_NEVER = 0xffffffffu;
 
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
 __device__ __forceinline__ unsigned int stage_push(Stage& st, uint32_t v, uint32_t* list_next, unsigned int* count_next) {
   const unsigned int p = atomicAdd(&st.n, 1u);
   if (p < Stage::CAP) st.buf[p] = v;

@@ -17,6 +17,18 @@
 
 using namespace mnb;
 
+// Kernel launches go through one macro: the CPU interpreter behind the `-m "not gpu"` logic tests (tests/emu/) compiles
+// this very file with g++, which has no <<<>>>.  MNB_EMU_ACTIVE is only ever defined by tests/emu/cuda_runtime.h; the
+// shipped library is built by nvcc without it and contains no host execution path for any kernel.
+#ifdef MNB_EMU_ACTIVE
+#define MNB_LAUNCH(kern, grid, block, smem, stream, ...) \
+  emu::launch(kern, (unsigned)(grid), (unsigned)(block), (size_t)(smem), 1u, false, __VA_ARGS__)
+#define MNB_DYNAMIC_SMEM(name) unsigned char* name = emu::g_cta.dyn_smem
+#else
+#define MNB_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define MNB_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
 // ============================================================================
 // small map kernels
 // ============================================================================
@@ -715,7 +727,7 @@ struct BtShared {
 };
 
 __global__ void __launch_bounds__(32) k_backtrack(BacktrackArgs a) {
-  extern __shared__ __align__(16) unsigned char bt_raw[];
+  MNB_DYNAMIC_SMEM(bt_raw);
   BtShared& S = *reinterpret_cast<BtShared*>(bt_raw);
   constexpr unsigned FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x;
@@ -1180,11 +1192,11 @@ int32_t mnb_set_mesh(mnb_ctx* ctx, uint32_t V, uint32_t F, const float* pos, con
   std::vector<uint32_t>().swap(T.vadj_nbr); std::vector<uint32_t>().swap(T.vadj_eid); std::vector<uint32_t>().swap(T.face_edges);
   CK(dalloc(&ctx->d_face_normals, 3 * (size_t)F)); CK(dalloc(&ctx->d_vertex_normals, 3 * (size_t)V)); CK(dalloc(&ctx->d_border, (size_t)V));
   CK(cudaMemcpyAsync(ctx->d_border, T.border.data(), (size_t)V, cudaMemcpyHostToDevice, ctx->stream));
-  k_face_normals<<<(F + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_pos, ctx->d_faces, F, ctx->d_face_normals);
-  k_vertex_normals<<<(V + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_cor_ptr, ctx->d_cor_idx, ctx->d_face_normals, V, ctx->d_vertex_normals);
-  k_edge_dist<<<(T.E + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_pos, ctx->d_edges, T.E, ctx->d_edge_dist);
-  k_gather_corner_w<<<(unsigned)((NC + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_cor_eid, ctx->d_edge_dist, NC, ctx->d_cor_wd);
-  k_gather_corner_w<<<(unsigned)(((size_t)V * ELL_W + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_ell_eid, ctx->d_edge_dist, (size_t)V * ELL_W, ctx->d_ell_wd);
+  MNB_LAUNCH(k_face_normals, (F + 255) / 256, 256, 0, ctx->stream, ctx->d_pos, ctx->d_faces, F, ctx->d_face_normals);
+  MNB_LAUNCH(k_vertex_normals, (V + 255) / 256, 256, 0, ctx->stream, ctx->d_cor_ptr, ctx->d_cor_idx, ctx->d_face_normals, V, ctx->d_vertex_normals);
+  MNB_LAUNCH(k_edge_dist, (T.E + 255) / 256, 256, 0, ctx->stream, ctx->d_pos, ctx->d_edges, T.E, ctx->d_edge_dist);
+  MNB_LAUNCH(k_gather_corner_w, (unsigned)((NC + 255) / 256), 256, 0, ctx->stream, ctx->d_cor_eid, ctx->d_edge_dist, NC, ctx->d_cor_wd);
+  MNB_LAUNCH(k_gather_corner_w, (unsigned)(((size_t)V * ELL_W + 255) / 256), 256, 0, ctx->stream, ctx->d_ell_eid, ctx->d_edge_dist, (size_t)V * ELL_W, ctx->d_ell_wd);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(ctx->stream));
   return MNB_OK;
@@ -1208,11 +1220,11 @@ int32_t mnb_get_edge_distances(mnb_ctx* ctx, float* out) {
 }
 
 static int32_t install_weights(mnb_ctx* ctx) {
-  k_gather_corner_w<<<(unsigned)((ctx->NC + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_cor_eid, ctx->d_edge_w, ctx->NC, ctx->d_cor_w);
-  k_gather_corner_w<<<(unsigned)(((size_t)ctx->V * ELL_W + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_ell_eid, ctx->d_edge_w, (size_t)ctx->V * ELL_W, ctx->d_ell_w);
-  k_corner_geo<<<(unsigned)(((size_t)ctx->V * ELL_W + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_ell_w, (size_t)ctx->V * ELL_W, ctx->d_ell_geo);
-  k_gather_adj_w<<<(unsigned)((ctx->NA + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_adj_nbr, ctx->d_adj_eid, ctx->d_edge_w, ctx->NA, ctx->d_adj_nw);
-  k_build_ell_adj<<<(unsigned)(((size_t)ctx->V * ELL_W + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_adj_ptr, ctx->d_adj_nw, ctx->V, ctx->d_ell_adj);
+  MNB_LAUNCH(k_gather_corner_w, (unsigned)((ctx->NC + 255) / 256), 256, 0, ctx->stream, ctx->d_cor_eid, ctx->d_edge_w, ctx->NC, ctx->d_cor_w);
+  MNB_LAUNCH(k_gather_corner_w, (unsigned)(((size_t)ctx->V * ELL_W + 255) / 256), 256, 0, ctx->stream, ctx->d_ell_eid, ctx->d_edge_w, (size_t)ctx->V * ELL_W, ctx->d_ell_w);
+  MNB_LAUNCH(k_corner_geo, (unsigned)(((size_t)ctx->V * ELL_W + 255) / 256), 256, 0, ctx->stream, ctx->d_ell_w, (size_t)ctx->V * ELL_W, ctx->d_ell_geo);
+  MNB_LAUNCH(k_gather_adj_w, (unsigned)((ctx->NA + 255) / 256), 256, 0, ctx->stream, ctx->d_adj_nbr, ctx->d_adj_eid, ctx->d_edge_w, ctx->NA, ctx->d_adj_nw);
+  MNB_LAUNCH(k_build_ell_adj, (unsigned)(((size_t)ctx->V * ELL_W + 255) / 256), 256, 0, ctx->stream, ctx->d_adj_ptr, ctx->d_adj_nw, ctx->V, ctx->d_ell_adj);
   CK(cudaGetLastError());
   ctx->costs_set = true;
   return MNB_OK;
@@ -1222,7 +1234,7 @@ int32_t mnb_compute_edge_weights(mnb_ctx* ctx, const float* vertex_costs, double
   if (!ctx || !vertex_costs || !ctx->V) return MNB_E_ARG;
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpyAsync(ctx->d_cost, vertex_costs, sizeof(float) * (size_t)ctx->V, in_kind(ctx), ctx->stream));
-  k_edge_weights<<<(ctx->E + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_cost, ctx->d_edges, ctx->d_edge_dist, edge_cost_factor, ctx->E, ctx->d_edge_w);
+  MNB_LAUNCH(k_edge_weights, (ctx->E + 255) / 256, 256, 0, ctx->stream, ctx->d_cost, ctx->d_edges, ctx->d_edge_dist, edge_cost_factor, ctx->E, ctx->d_edge_w);
   CK(cudaGetLastError());
   int32_t rc = install_weights(ctx);
   if (rc != MNB_OK) return rc;
@@ -1266,6 +1278,18 @@ static cudaError_t launch_cluster(void (*kern)(const KArgs), const KArgs& args, 
     if (e != cudaSuccess) return e;
   }
   return cudaLaunchKernelEx(&cfg, kern, args);
+}
+
+// cooperative (grid-synchronising) launch of a kernel that takes one argument struct
+template <class KArgs>
+static cudaError_t launch_cooperative(void (*kern)(const KArgs), const KArgs& args, unsigned blocks, int threads, cudaStream_t stream) {
+#ifdef MNB_EMU_ACTIVE
+  (void)stream;
+  return emu::launch(kern, blocks, (unsigned)threads, (size_t)0, 1u, true, args);
+#else
+  void* kargs[] = {(void*)&args};
+  return cudaLaunchCooperativeKernel((const void*)kern, dim3(blocks), dim3(threads), kargs, 0, stream);
+#endif
 }
 
 static int32_t launch_cvp(mnb_ctx* ctx, const CvpKernelArgs& a, int cs, unsigned groups) {
@@ -1359,13 +1383,11 @@ int32_t mnb_cvp(mnb_ctx* ctx, uint32_t seed_face, const float seed_pos[3], int64
       ctx->grid_blocks_per_sm = nb > MNB_GRID_MINBLOCKS ? MNB_GRID_MINBLOCKS : nb;
       if (nb <= 0) { ctx->err = "k_cvp_grid cannot be resident"; return MNB_E_CUDA; }
     }
-    void* kargs[] = {(void*)&a};
-    CK(cudaLaunchCooperativeKernel((const void*)k_cvp_grid, dim3(ctx->sm_count * ctx->grid_blocks_per_sm), dim3(ctx->threads),
-                                   kargs, 0, ctx->stream));
+    CK(launch_cooperative(k_cvp_grid, a, (unsigned)(ctx->sm_count * ctx->grid_blocks_per_sm), ctx->threads, ctx->stream));
   } else {
     if ((rc = launch_cvp(ctx, a, ctx->cluster, 1)) != MNB_OK) return rc;
   }
-  k_cvp_epilogue<<<(ctx->V + 255) / 256, 256, 0, ctx->stream>>>(a, ctx->ws.ctl);
+  MNB_LAUNCH(k_cvp_epilogue, (ctx->V + 255) / 256, 256, 0, ctx->stream, a, ctx->ws.ctl);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   if (!dev) {
@@ -1458,8 +1480,7 @@ int32_t mnb_dijkstra(mnb_ctx* ctx, uint32_t seed_vertex, int64_t robot_vertex, d
   const int cs = ctx->cluster;
   if (cs == -1) {   // single plan on the whole GPU (cooperative launch, one CTA per SM)
     a.delta = ctx->dijkstra_grid_delta; a.ell_adj = ctx->d_ell_adj; a.sweeps = ctx->sweeps;
-    void* kargs[] = {(void*)&a};
-    e = cudaLaunchCooperativeKernel((const void*)k_dijkstra_grid, dim3(ctx->sm_count), dim3(512), kargs, 0, ctx->stream);
+    e = launch_cooperative(k_dijkstra_grid, a, (unsigned)ctx->sm_count, 512, ctx->stream);
   } else
   switch (cs) {
     case 1: e = launch_cluster(k_dijkstra<1>, a, 1, 1, ctx->threads, ctx->stream); break;
@@ -1513,7 +1534,7 @@ int32_t mnb_compute_layers(mnb_ctx* ctx, const mnb_layer_params* params, const f
   a.lethal_mask = (dev && out_lethal_mask) ? out_lethal_mask : ctx->d_layer_mask;
   a.overflow = ctx->d_overflow;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  k_layers<<<(ctx->V + 127) / 128, 128, 0, ctx->stream>>>(a);
+  MNB_LAUNCH(k_layers, (ctx->V + 127) / 128, 128, 0, ctx->stream, a);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   if (!dev) {
@@ -1545,7 +1566,7 @@ int32_t mnb_vector_map(mnb_ctx* ctx, const uint32_t* pred, const float* directio
     if (cutting_face) { CK(dalloc(&tmp_cut, V)); CK(cudaMemcpyAsync(tmp_cut, cutting_face, sizeof(int32_t) * V, cudaMemcpyHostToDevice, ctx->stream)); d_cut = tmp_cut; }
   }
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  k_vector_map<<<(ctx->V + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_pos, ctx->d_vertex_normals, d_pred, d_dir, d_cut, ctx->V, d_out);
+  MNB_LAUNCH(k_vector_map, (ctx->V + 255) / 256, 256, 0, ctx->stream, ctx->d_pos, ctx->d_vertex_normals, d_pred, d_dir, d_cut, ctx->V, d_out);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   if (!dev) CK(cudaMemcpyAsync(out_vec, d_out, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1576,7 +1597,7 @@ int32_t mnb_cvp_backtrack(mnb_ctx* ctx, const float robot_pos[3], uint32_t robot
   a.path_pos = ctx->d_path_pos; a.path_face = ctx->d_path_face; a.result = ctx->d_bt_result; a.cancel_flag = ctx->d_cancel;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   CK(cudaFuncSetAttribute(k_backtrack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BtShared)));
-  k_backtrack<<<1, 32, sizeof(BtShared), ctx->stream>>>(a);
+  MNB_LAUNCH(k_backtrack, 1, 32, sizeof(BtShared), ctx->stream, a);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   int32_t res[2] = {0, 0};
@@ -1612,8 +1633,8 @@ int32_t mnb_locate(mnb_ctx* ctx, uint32_t n, const float* points, uint32_t* out_
   const uint32_t blocks = want < cap ? want : cap;
   uint32_t launches = 0;
   for (uint32_t q0 = 0; q0 < n; q0 += LOC_Q, ++launches)
-    k_nearest_vertex<<<blocks, 256, 0, ctx->stream>>>(ctx->d_pos, ctx->V, pts, q0, n - q0 < (uint32_t)LOC_Q ? n - q0 : (uint32_t)LOC_Q, d_keys);
-  k_containing_face<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_pos, ctx->d_faces, ctx->d_cor_ptr, ctx->d_cor_idx, pts, n, d_keys,
+    MNB_LAUNCH(k_nearest_vertex, blocks, 256, 0, ctx->stream, ctx->d_pos, ctx->V, pts, q0, n - q0 < (uint32_t)LOC_Q ? n - q0 : (uint32_t)LOC_Q, d_keys);
+  MNB_LAUNCH(k_containing_face, (n + 127) / 128, 128, 0, ctx->stream, ctx->d_pos, ctx->d_faces, ctx->d_cor_ptr, ctx->d_cor_idx, pts, n, d_keys,
                                                            dev ? out_vertex : d_v, dev ? out_face : d_f, dev ? out_bary : d_b);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -1666,8 +1687,7 @@ int32_t mnb_inflate(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, const uin
   a.out_cost = (dev && out_cost) ? out_cost : ctx->d_out_cost;
   a.max_rounds = watchdog_rounds(ctx->V);
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  void* kargs[] = {(void*)&a};
-  CK(cudaLaunchCooperativeKernel((const void*)k_inflate, dim3(ctx->sm_count), dim3(ctx->threads), kargs, 0, ctx->stream));
+  CK(launch_cooperative(k_inflate, a, (unsigned)ctx->sm_count, ctx->threads, ctx->stream));
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   if (!dev) {
     if (out_dist) CK(cudaMemcpyAsync(out_dist, a.out_dist, sizeof(float) * (size_t)ctx->V, cudaMemcpyDeviceToHost, ctx->stream));

@@ -49,3 +49,17 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
                 src = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_product_never_loads_the_cpu_interpreter():
+    """tests/emu (the CPU interpreter of the kernels, test infrastructure) must stay out of the product: the package never
+    names it, and the shipped library contains no interpreter symbols (MNB_EMU_ACTIVE is only defined by tests/emu)."""
+    pkg = os.path.join(ROOT, "mesh_navigation_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "libmeshnav_emu" not in src and "tests.emu" not in src and "tests/emu" not in src, f
+    blob = open(os.path.join(pkg, "libmeshnav_b200.so"), "rb").read()
+    assert b"mnb_emu_switch" not in blob and b"mnb-emu" not in blob
+    assert b"sm_100" in blob, "the shipped library carries no sm_100a code"
