@@ -43,20 +43,26 @@ namespace cg = cooperative_groups;
 constexpr uint32_t INF_BITS = 0x7f800000u;
 constexpr int STAGNATION_ROUNDS = 24;
 
-// pop time of a vertex: monotonic stack of water levels a1 > a2 > a3 (0 = unused) + tie-break minor
-struct EvTime { float a1, a2, a3; uint32_t minor; };
+// pop time of a vertex: monotonic stack of water levels a1 > a2 > a3 (0 = unused) + tie-break minor.
+// `root` orders labels that share the bit-identical first level a1 = K: a vertex that pops at its own key carries its
+// own id (the oracle's canonical heap order (key, id)); the members of a cascade carry the id of the cascade's root
+// trigger t, so that they pop after every (K, id < t), right after (K, t) itself (a2 == 0 sorts first) and before every
+// (K, id > t) -- float32 potentials collide millions of times on 10M-vertex meshes, and without `root` a cascade under a
+// tied key was ordered after ALL plain labels of that key.
+struct EvTime { float a1, a2, a3; uint32_t minor, root; };
 __device__ __forceinline__ bool ev_less(const EvTime& x, const EvTime& y) {
   if (x.a1 != y.a1) return x.a1 < y.a1;
+  if (x.root != y.root) return x.root < y.root;
   if (x.a2 != y.a2) return x.a2 < y.a2;
   if (x.a3 != y.a3) return x.a3 < y.a3;
   return x.minor < y.minor;
 }
 __device__ __forceinline__ bool ev_eq(const EvTime& x, const EvTime& y) {
   return __float_as_uint(x.a1) == __float_as_uint(y.a1) && __float_as_uint(x.a2) == __float_as_uint(y.a2) &&
-         __float_as_uint(x.a3) == __float_as_uint(y.a3) && x.minor == y.minor;
+         __float_as_uint(x.a3) == __float_as_uint(y.a3) && x.minor == y.minor && x.root == y.root;
 }
-__device__ __forceinline__ EvTime ev_normal(float key, uint32_t id) { EvTime t; t.a1 = key; t.a2 = 0.0f; t.a3 = 0.0f; t.minor = 2u * id; return t; }
-// per-vertex label: one 16-byte word {d, a1, a2, a3 | overflow flag}
+__device__ __forceinline__ EvTime ev_normal(float key, uint32_t id) { EvTime t; t.a1 = key; t.a2 = 0.0f; t.a3 = 0.0f; t.minor = 2u * id; t.root = id; return t; }
+// per-vertex label: one 16-byte word {d, a1, a2 | root flag, a3 | minor flag}; flagged roots / minors live in side arrays
 struct Label { float d; EvTime t; };
 __device__ __forceinline__ uint4 state_inf() { return make_uint4(INF_BITS, INF_BITS, 0u, 0u); }
 

@@ -39,35 +39,34 @@ struct CvpProblem {
   static constexpr int MAXF = 12;
 
   uint32_t* minor_arr;                  // overflow minors (only read when the label's flag bit is set)
+  uint32_t* root_arr;                   // cascade roots (only read when the label's flag bit is set)
   uint32_t* chg;                        // 1 + round of the last RE-label of a vertex (0 = never)
   uint32_t* ver;                        // input version: bumped whenever a face neighbour is re-labelled (in-round sweeps)
   mutable float deferred_m;             // smallest trigger time of a back-step deferred in this round
   int strict;                           // set by the engine once it has detected stagnation (see backstep_ok)
 
-  __device__ __forceinline__ Label load_label(uint32_t v) const {
-    const uint4 s = __ldcg(&state[v]);
-    Label l; l.d = __uint_as_float(s.x); l.t.a1 = __uint_as_float(s.y); l.t.a2 = __uint_as_float(s.z);
-    l.t.a3 = __uint_as_float(s.w & 0x7fffffffu);
-    l.t.minor = (s.w >> 31) ? __ldcg(&minor_arr[v]) : 2u * v;
-    return l;
-  }
-  // the 16-byte word of a label as store_label() writes it / its decoding (minor overflow lives in minor_arr)
-  __device__ __forceinline__ uint4 pack_label(uint32_t c, float d, const EvTime& t) const {
-    uint32_t w = __float_as_uint(t.a3);
-    if (t.minor != 2u * c) w |= 0x80000000u;
-    return make_uint4(__float_as_uint(d), __float_as_uint(t.a1), __float_as_uint(t.a2), w);
-  }
+  // decoding of the 16-byte label word: sign bit of .z = "root differs from the vertex id, see root_arr",
+  // sign bit of .w = "minor differs from 2*id, see minor_arr" (pop-time levels are >= 0, so both bits are free)
   __device__ __forceinline__ Label unpack_label(uint32_t v, const uint4& s) const {
-    Label l; l.d = __uint_as_float(s.x); l.t.a1 = __uint_as_float(s.y); l.t.a2 = __uint_as_float(s.z);
+    Label l; l.d = __uint_as_float(s.x); l.t.a1 = __uint_as_float(s.y); l.t.a2 = __uint_as_float(s.z & 0x7fffffffu);
     l.t.a3 = __uint_as_float(s.w & 0x7fffffffu);
+    l.t.root = (s.z >> 31) ? __ldcg(&root_arr[v]) : v;
     l.t.minor = (s.w >> 31) ? __ldcg(&minor_arr[v]) : 2u * v;
     return l;
+  }
+  __device__ __forceinline__ Label load_label(uint32_t v) const { return unpack_label(v, __ldcg(&state[v])); }
+  // the 16-byte word of a label as store_label() writes it (flagged root / minor live in the side arrays)
+  __device__ __forceinline__ uint4 pack_label(uint32_t c, float d, const EvTime& t) const {
+    uint32_t z = __float_as_uint(t.a2), w = __float_as_uint(t.a3);
+    if (t.root != c) z |= 0x80000000u;
+    if (t.minor != 2u * c) w |= 0x80000000u;
+    return make_uint4(__float_as_uint(d), __float_as_uint(t.a1), z, w);
   }
   __device__ __forceinline__ void store_label(uint32_t c, float d, const EvTime& t, bool relabel, uint32_t round) const {
-    uint32_t w = __float_as_uint(t.a3);
-    if (t.minor != 2u * c) { __stcg(&minor_arr[c], t.minor); w |= 0x80000000u; }
+    if (t.root != c) __stcg(&root_arr[c], t.root);
+    if (t.minor != 2u * c) __stcg(&minor_arr[c], t.minor);
     if (relabel) __stcg(&chg[c], round + 1u);
-    __stcg(&state[c], make_uint4(__float_as_uint(d), __float_as_uint(t.a1), __float_as_uint(t.a2), w));
+    __stcg(&state[c], pack_label(c, d, t));
   }
   // A non-causal (back-step) label X <= T.a1 may only be taken from a trigger whose label was not
   // re-labelled during the previous round.  Without this a trigger and its own back-step child can feed
@@ -144,9 +143,12 @@ struct CvpProblem {
   // one accepted update with value X from a face that fired at time F: pop time of c
   // (monotonic stack: keep the trigger's water levels that are >= X, then X itself)
   __device__ __forceinline__ static EvTime accept_time(uint32_t c, float X, const EvTime& F) {
-    EvTime t; t.a2 = 0.0f; t.a3 = 0.0f; t.minor = 2u * c;
-    if (X > F.a1) { t.a1 = X; return t; }                         // above water: pops at its own key
-    t.a1 = F.a1;
+    EvTime t; t.a2 = 0.0f; t.a3 = 0.0f; t.minor = 2u * c; t.root = c;
+    // above water: pops at its own key.  X == F.a1 exactly: c enters the heap with the key of the cascade's root trigger
+    // and pops in (key, id) order among the vertices of that key that are still queued -- all of them have ids above the
+    // root's -- i.e. as a plain label if its id is above the root's, else right after the cascade
+    if (X > F.a1 || (X == F.a1 && c > F.root)) { t.a1 = X; return t; }
+    t.a1 = F.a1; t.root = F.root;                                 // member of the trigger's cascade
     if (X > F.a2) { t.a2 = X; return t; }
     t.a2 = F.a2;
     if (X > F.a3) { t.a3 = X; return t; }
@@ -340,11 +342,7 @@ struct CvpEllProblem : CvpProblem {
       const double2* gp = reinterpret_cast<const double2*>(ell_geo) + 2 * ((size_t)c * ELL_W + j);
       const double2 g01 = __ldg(gp), g23 = __ldg(gp + 1);
       FaceGeo g; g.p = g01.x; g.hc = g01.y; g.t0a = g23.x;
-      Label a, b;
-      a.d = __uint_as_float(sa.x); a.t.a1 = __uint_as_float(sa.y); a.t.a2 = __uint_as_float(sa.z); a.t.a3 = __uint_as_float(sa.w & 0x7fffffffu);
-      a.t.minor = (sa.w >> 31) ? __ldcg(&minor_arr[v1]) : 2u * v1;
-      b.d = __uint_as_float(sb.x); b.t.a1 = __uint_as_float(sb.y); b.t.a2 = __uint_as_float(sb.z); b.t.a3 = __uint_as_float(sb.w & 0x7fffffffu);
-      b.t.minor = (sb.w >> 31) ? __ldcg(&minor_arr[v2]) : 2u * v2;
+      const Label a = unpack_label(v1, sa), b = unpack_label(v2, sb);
       valid = face_time(v1, v2, a, b, band_end, goal, T, Tv);
       if (valid) {
         eval_face_geo((double)a.d, (double)b.d, (double)w.z, (double)w.y, (double)w.x, g, U, X);
@@ -352,16 +350,15 @@ struct CvpEllProblem : CvpProblem {
         if (!backstep_ok((float)X, T, Tv, round)) X = (double)INF;
       }
     }
-    // Common case: every firing face of the warp has a plain pop time (a2 == a3 == 0, default minor = 2*Tv):
-    // the event order is (a1, Tv).  Cascade members (rare) take the general 128-bit path.  Invalid lanes carry
-    // the maximal key so that no validity flag has to travel with the shuffles.
-    const bool plain = !valid || (T.a2 == 0.0f && T.a3 == 0.0f && T.minor == 2u * Tv);
+    // Common case: every firing face of the warp has a plain pop time (a2 == a3 == 0, default minor, root = Tv):
+    // the event order is (a1, Tv).  Cascade members (rare) take the general path on (a1, root, a2, a3, minor).  Invalid
+    // lanes carry the maximal key so that no validity flag has to travel with the shuffles.
+    const bool plain = !valid || (T.a2 == 0.0f && T.a3 == 0.0f && T.minor == 2u * Tv && T.root == Tv);
     const bool all_plain = __all_sync(FULL, plain);
     const uint32_t k1 = valid ? __float_as_uint(T.a1) : 0xffffffffu;          // pop times are >= 0: bit order = value order
-    const unsigned long long hi = valid ? (all_plain ? (((unsigned long long)k1 << 32) | Tv)
-                                                     : (((unsigned long long)k1 << 32) | __float_as_uint(T.a2)))
-                                        : ~0ull;
-    const unsigned long long lo = ((unsigned long long)__float_as_uint(T.a3) << 32) | T.minor;
+    const unsigned long long hi = valid ? (((unsigned long long)k1 << 32) | T.root) : ~0ull;          // plain: root == Tv
+    const unsigned long long mid = ((unsigned long long)__float_as_uint(T.a2) << 32) | __float_as_uint(T.a3);
+    const uint32_t lo = T.minor;
     int rank = 0;
     if (all_plain) {
       // 32-bit pass on a1 alone; two firing faces with bit-identical a1 (exact float tie between different source
@@ -388,8 +385,9 @@ struct CvpEllProblem : CvpProblem {
       for (int d = 1; d < 8; ++d) {
         const int src = (int)((j + d) & 7);
         const unsigned long long ohi = __shfl_sync(FULL, hi, src, 8);
-        const unsigned long long olo = __shfl_sync(FULL, lo, src, 8);
-        if (ohi < hi || (ohi == hi && (olo < lo || (olo == lo && (uint32_t)src < j)))) ++rank;
+        const unsigned long long omid = __shfl_sync(FULL, mid, src, 8);
+        const uint32_t olo = __shfl_sync(FULL, lo, src, 8);
+        if (ohi < hi || (ohi == hi && (omid < mid || (omid == mid && (olo < lo || (olo == lo && (uint32_t)src < j)))))) ++rank;
       }
     }
     if (!valid) rank = 99;
@@ -402,16 +400,16 @@ struct CvpEllProblem : CvpProblem {
       const unsigned who = (__ballot_sync(FULL, rank == r) >> sh) & 0xFFu;
       const int src = who ? (__ffs(who) - 1) : 0;
       const unsigned long long whi = __shfl_sync(FULL, hi, src, 8);
-      unsigned long long wlo = 0;
-      if (!all_plain) wlo = __shfl_sync(FULL, lo, src, 8);
+      unsigned long long wmid = 0; uint32_t wlo = 0;
+      if (!all_plain) { wmid = __shfl_sync(FULL, mid, src, 8); wlo = __shfl_sync(FULL, lo, src, 8); }
       const double Uw = __shfl_sync(FULL, U, src, 8);
       const double Xw = __shfl_sync(FULL, X, src, 8);
       if (!who) open = false;                           // ranks are dense: no face with rank r -> none beyond
       if (!open) continue;
       EvTime Tw;
-      Tw.a1 = __uint_as_float((uint32_t)(whi >> 32));
+      Tw.a1 = __uint_as_float((uint32_t)(whi >> 32)); Tw.root = (uint32_t)whi;
       if (all_plain) { Tw.a2 = 0.0f; Tw.a3 = 0.0f; Tw.minor = 2u * (uint32_t)whi; }
-      else { Tw.a2 = __uint_as_float((uint32_t)whi); Tw.a3 = __uint_as_float((uint32_t)(wlo >> 32)); Tw.minor = (uint32_t)wlo; }
+      else { Tw.a2 = __uint_as_float((uint32_t)(wmid >> 32)); Tw.a3 = __uint_as_float((uint32_t)wmid); Tw.minor = wlo; }
       if (!ev_less(Tw, tc)) { open = false; continue; }
       const double cd = (double)cur;
       if (Uw < cd && Xw < cd) { cur = (float)Xw; tc = accept_time(c, cur, Tw); }
@@ -423,7 +421,7 @@ struct CvpEllProblem : CvpProblem {
     if (anybig) {
       cur = __shfl_sync(FULL, cur, 0, 8);
       tc.a1 = __shfl_sync(FULL, tc.a1, 0, 8); tc.a2 = __shfl_sync(FULL, tc.a2, 0, 8);
-      tc.a3 = __shfl_sync(FULL, tc.a3, 0, 8); tc.minor = __shfl_sync(FULL, tc.minor, 0, 8);
+      tc.a3 = __shfl_sync(FULL, tc.a3, 0, 8); tc.minor = __shfl_sync(FULL, tc.minor, 0, 8); tc.root = __shfl_sync(FULL, tc.root, 0, 8);
     }
     nd = cur; nt = tc;
   }
@@ -447,6 +445,7 @@ struct InflationProblem {
   const uint8_t* __restrict__ invalid;  // may be null
   uint4* state;
   uint32_t* minor_arr;
+  uint32_t* root_arr;
   uint32_t* chg;
   mutable float deferred_m;
   int strict;
@@ -454,18 +453,20 @@ struct InflationProblem {
 
   static constexpr int MAXF = 12;
 
-  __device__ __forceinline__ Label load_label(uint32_t v) const {
+  __device__ __forceinline__ Label load_label(uint32_t v) const {       // same label word as CvpProblem
     const uint4 s = __ldcg(&state[v]);
-    Label l; l.d = __uint_as_float(s.x); l.t.a1 = __uint_as_float(s.y); l.t.a2 = __uint_as_float(s.z);
+    Label l; l.d = __uint_as_float(s.x); l.t.a1 = __uint_as_float(s.y); l.t.a2 = __uint_as_float(s.z & 0x7fffffffu);
     l.t.a3 = __uint_as_float(s.w & 0x7fffffffu);
+    l.t.root = (s.z >> 31) ? __ldcg(&root_arr[v]) : v;
     l.t.minor = (s.w >> 31) ? __ldcg(&minor_arr[v]) : 2u * v;
     return l;
   }
   __device__ __forceinline__ void store_label(uint32_t c, float d, const EvTime& t, bool relabel, uint32_t round) const {
-    uint32_t w = __float_as_uint(t.a3);
+    uint32_t z = __float_as_uint(t.a2), w = __float_as_uint(t.a3);
+    if (t.root != c) { __stcg(&root_arr[c], t.root); z |= 0x80000000u; }
     if (t.minor != 2u * c) { __stcg(&minor_arr[c], t.minor); w |= 0x80000000u; }
     if (relabel) __stcg(&chg[c], round + 1u);
-    __stcg(&state[c], make_uint4(__float_as_uint(d), __float_as_uint(t.a1), __float_as_uint(t.a2), w));
+    __stcg(&state[c], make_uint4(__float_as_uint(d), __float_as_uint(t.a1), z, w));
   }
   __device__ __forceinline__ bool backstep_ok(float X, const EvTime& T, uint32_t Tv, uint32_t round) const {   // see CvpProblem
     if (!strict || X > T.a1) return true;
