@@ -174,6 +174,38 @@ int32_t mnb_cvp_backtrack(mnb_ctx* ctx, const float robot_pos[3], uint32_t robot
                           float* path_pos /* 3*max_points */, uint32_t* path_face /* max_points or NULL */,
                           uint32_t* n_points);
 
+/* ---- incremental updates: the sensor-rate callers of the hot path ----------------------------------
+ * NaN marks "no entry" in a sparse lvr2 cost map; `changed` plays the std::set<VertexHandle> of the reference
+ * (any order, duplicates allowed).  All three work on the changed vertices only. */
+
+/* MeshMap::layerChanged (mesh_map.cpp:455-492) + MeshMap::updateEdgeWeights (mesh_map.cpp:563-618):
+ *   vertex_costs[v] = cost_map.get(v).value_or(default_value) for v in changed, then the weights of the edges incident
+ *   to a changed vertex are recomputed with the formula of computeEdgeWeights -- and, exactly as in the reference
+ *   (:568-572), NOT AT ALL when edge_cost_factor == 0.  The planners' derived tables are refreshed for those edges only
+ *   (no V- or E-sized pass, no re-upload).  costs_indexed_by_vertex == 0: costs[i] is the new cost of changed[i];
+ *   != 0: costs is the layer's V-sized map and default_value replaces NaN entries.  Needs mnb_set_costs /
+ *   mnb_compute_edge_weights first. */
+int32_t mnb_update_vertex_costs(mnb_ctx* ctx, uint32_t n_changed, const uint32_t* changed, const float* costs,
+                                int32_t costs_indexed_by_vertex, float default_value, double edge_cost_factor);
+/* the installed per-plan inputs (MeshMap::vertexCosts() / edgeWeights()); either may be NULL */
+int32_t mnb_get_costs(mnb_ctx* ctx, float* out_vertex_costs /* V */, float* out_edge_weights /* E */);
+
+/* MaxCombinationLayer::onInputChanged (combination_layer.cpp:87-147) for the changed vertices:
+ *   io_costs[v] = max(0, max_i (layer_costs[i][v] or defaults[i]));  io_lethal[v] = OR_i layer_lethal[i][v].
+ * layer_costs / layer_lethal are HOST arrays of n_layers (<= 8) pointers to V-sized maps (host or device per the
+ * pointer mode); layer_lethal, any of its entries and io_lethal may be NULL; defaults is a host array. */
+int32_t mnb_max_combination_update(mnb_ctx* ctx, uint32_t n_layers, const float* const* layer_costs, const float* defaults,
+                                   const uint8_t* const* layer_lethal, uint32_t n_changed, const uint32_t* changed,
+                                   float* io_costs /* V */, uint8_t* io_lethal /* V or NULL */);
+
+/* InflationLayer::onInputChanged (inflation_layer.cpp:97-179): re-runs waveCostInflation from `lethals` (the reference
+ * does a full re-inflation here too, :143-151) and reports the update set handed to notifyChange (:154-176): the
+ * vertices that carry a riskiness value now or carried one after the previous mnb_inflate / mnb_inflation_update on this
+ * context, ascending.  out_changed: room for V ids (may be NULL); *n_changed (host) receives the count. */
+int32_t mnb_inflation_update(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, const uint8_t* invalid /* V or NULL */,
+                             const mnb_inflation_params* params, float* out_dist, float* out_cost,
+                             uint32_t* out_changed /* V */, uint32_t* n_changed);
+
 /* ---- cancel (CVPMeshPlanner::cancel / DijkstraMeshPlanner::cancel) ------- */
 int32_t mnb_cancel(mnb_ctx* ctx);
 

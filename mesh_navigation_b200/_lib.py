@@ -48,6 +48,7 @@ EXPORTS = [
     "mnb_num_vertices", "mnb_num_faces", "mnb_num_edges", "mnb_get_edges", "mnb_get_edge_distances",
     "mnb_compute_edge_weights", "mnb_set_costs", "mnb_dijkstra", "mnb_cvp", "mnb_cvp_batch", "mnb_inflate",
     "mnb_cancel", "mnb_get_stats", "mnb_set_tuning", "mnb_compute_layers", "mnb_get_vertex_normals", "mnb_vector_map", "mnb_cvp_backtrack", "mnb_locate",
+    "mnb_update_vertex_costs", "mnb_get_costs", "mnb_max_combination_update", "mnb_inflation_update",
 ]
 
 _lib = None
@@ -84,6 +85,12 @@ def load():
     L.mnb_locate.restype = i32; L.mnb_locate.argtypes = [vp, u32, vp, vp, vp, vp]
     L.mnb_cvp_backtrack.restype = i32
     L.mnb_cvp_backtrack.argtypes = [vp, vp, C.c_uint32, C.c_double, C.c_uint32, vp, vp, vp]
+    L.mnb_update_vertex_costs.restype = i32; L.mnb_update_vertex_costs.argtypes = [vp, u32, vp, vp, i32, f32, dbl]
+    L.mnb_get_costs.restype = i32; L.mnb_get_costs.argtypes = [vp, vp, vp]
+    L.mnb_max_combination_update.restype = i32
+    L.mnb_max_combination_update.argtypes = [vp, u32, vp, vp, vp, u32, vp, vp, vp]
+    L.mnb_inflation_update.restype = i32
+    L.mnb_inflation_update.argtypes = [vp, vp, u32, vp, C.POINTER(InflationParams), vp, vp, vp, C.POINTER(C.c_uint32)]
     L.mnb_cancel.restype = i32; L.mnb_cancel.argtypes = [vp]
     L.mnb_get_stats.restype = i32; L.mnb_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.mnb_set_tuning.restype = i32; L.mnb_set_tuning.argtypes = [vp, f32, i32, i32]

@@ -103,6 +103,39 @@ class MeshMap:
         assert vc.size == self.V and ew.size == self.E
         self._check(self.L.mnb_set_costs(self._ctx, _p(vc), _p(ew), _p(inv)))
 
+    # -- incremental updates ---------------------------------
+    def layerChanged(self, changed, costs, edge_cost_factor: float, by_vertex: bool = False, default_value: float = 0.0):
+        """MeshMap::layerChanged + updateEdgeWeights (mesh_map.cpp:455-492, 563-618) for the changed vertices only.
+        costs: one value per changed vertex, or (by_vertex) the default layer's V-sized map with NaN = no entry"""
+        if self.device_pointers:
+            ch, n = changed
+            return self._check(self.L.mnb_update_vertex_costs(self._ctx, int(n), _p(ch), _p(costs), int(by_vertex),
+                                                              float(default_value), float(edge_cost_factor)))
+        ch = np.ascontiguousarray(changed, dtype=np.uint32)
+        co = np.ascontiguousarray(costs, dtype=np.float32)
+        assert co.size == (self.V if by_vertex else ch.size)
+        return self._check(self.L.mnb_update_vertex_costs(self._ctx, ch.size, _p(ch), _p(co), int(by_vertex),
+                                                          float(default_value), float(edge_cost_factor)))
+
+    def costs(self):
+        """(vertex_costs, edge_weights) as installed on the device"""
+        vc = np.empty(self.V, dtype=np.float32); ew = np.empty(self.E, dtype=np.float32)
+        self._check(self.L.mnb_get_costs(self._ctx, _p(vc), _p(ew)))
+        return vc, ew
+
+    def maxCombinationUpdate(self, layer_costs, defaults, layer_lethals, changed, io_costs, io_lethal=None):
+        """MaxCombinationLayer::onInputChanged (combination_layer.cpp:87-147): io_costs / io_lethal updated in place"""
+        n = len(layer_costs)
+        lcs = [np.ascontiguousarray(a, dtype=np.float32) for a in layer_costs]
+        lls = [None if a is None else np.ascontiguousarray(a, dtype=np.uint8) for a in (layer_lethals or [None] * n)]
+        cp = (C.c_void_p * n)(*[a.ctypes.data for a in lcs])
+        lp = (C.c_void_p * n)(*[None if a is None else a.ctypes.data for a in lls])
+        df = np.ascontiguousarray(defaults, dtype=np.float32)
+        ch = np.ascontiguousarray(changed, dtype=np.uint32)
+        assert io_costs.dtype == np.float32 and io_costs.flags.c_contiguous and io_costs.size == self.V
+        self._check(self.L.mnb_max_combination_update(self._ctx, n, cp, _p(df), lp, ch.size, _p(ch), _p(io_costs), _p(io_lethal)))
+        return io_costs, io_lethal
+
     def vertexNormals(self) -> np.ndarray:
         out = np.empty((self.V, 3), dtype=np.float32)
         self._check(self.L.mnb_get_vertex_normals(self._ctx, _p(out)))
@@ -270,3 +303,17 @@ class InflationLayer:
         cost = np.empty(m.V, dtype=np.float32)
         m._check(m.L.mnb_inflate(m._ctx, _p(le), le.size, _p(inv), C.byref(self.config), _p(dist), _p(cost)))
         return dict(dist=dist, cost=cost, **m.stats())
+
+    def onInputChanged(self, lethals, invalid=None):
+        """InflationLayer::onInputChanged (inflation_layer.cpp:97-179): full re-inflation + the update set
+        (vertices with a riskiness entry now or after the previous inflation on this map, ascending)"""
+        m = self.map
+        le = np.ascontiguousarray(lethals, dtype=np.uint32)
+        inv = None if invalid is None else np.ascontiguousarray(invalid, dtype=np.uint8)
+        dist = np.empty(m.V, dtype=np.float32)
+        cost = np.empty(m.V, dtype=np.float32)
+        changed = np.empty(m.V, dtype=np.uint32)
+        n = C.c_uint32(0)
+        m._check(m.L.mnb_inflation_update(m._ctx, _p(le), le.size, _p(inv), C.byref(self.config), _p(dist), _p(cost),
+                                          _p(changed), C.byref(n)))
+        return dict(dist=dist, cost=cost, changed=changed[:n.value].copy(), **m.stats())

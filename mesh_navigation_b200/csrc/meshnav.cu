@@ -984,6 +984,197 @@ __global__ void __launch_bounds__(512, 1) k_inflate(const InflateKernelArgs a) {
   }
 }
 
+
+// ============================================================================
+// Incremental updates: MeshMap::layerChanged + updateEdgeWeights (mesh_map.cpp:455-492, 563-618),
+// MaxCombinationLayer::onInputChanged (combination_layer.cpp:87-147), the update set of InflationLayer::onInputChanged
+// (inflation_layer.cpp:154-164).  Work is proportional to the changed set: 8 lanes per changed vertex walk its incident
+// edges / faces and patch only the table entries that hold one of those edges' weights.
+// ============================================================================
+__global__ void k_update_costs(const uint32_t* __restrict__ changed, uint32_t n, const float* __restrict__ costs, int by_vertex,
+                               float default_value, uint32_t V, float* __restrict__ cost) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t v = changed[i];
+  if (v >= V) return;
+  float c = by_vertex ? costs[v] : costs[i];
+  if (by_vertex && c != c) c = default_value;                 // cost_map.get(vH).value_or(default_value), mesh_map.cpp:486
+  cost[v] = c;
+}
+
+__global__ void k_update_edge_weights(const uint32_t* __restrict__ changed, uint32_t n, uint32_t V, const uint32_t* __restrict__ adj_ptr,
+                                      const uint32_t* __restrict__ adj_eid, const uint32_t* __restrict__ edges,
+                                      const float* __restrict__ cost, const float* __restrict__ dist, double factor,
+                                      float* __restrict__ w) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)n * ELL_W) return;
+  const uint32_t v = changed[t / ELL_W], j = (uint32_t)(t % ELL_W);
+  if (v >= V) return;
+  for (uint32_t k = adj_ptr[v] + j; k < adj_ptr[v + 1]; k += ELL_W) {            // getEdgesOfVertex, mesh_map.cpp:580
+    const uint32_t e = adj_eid[k];
+    const float c1 = cost[edges[2 * (size_t)e]], c2 = cost[edges[2 * (size_t)e + 1]];
+    if (isinf(c1) || isinf(c2)) {                                                // :598
+      w[e] = __uint_as_float(INF_BITS);
+    } else {
+      const float vertex_dist = dist[e];
+      const float edge_cost = (float)((double)(vertex_dist * (c1 + c2)) / 2.0);  // :609
+      w[e] = (float)((double)vertex_dist + factor * (double)edge_cost);          // :611
+    }
+  }
+}
+
+struct RefreshArgs {
+  const uint32_t* changed; uint32_t n, V;
+  const uint32_t* faces;
+  const uint32_t* cor_ptr; const int4* cor_idx; const uint4* cor_eid;
+  const uint32_t* adj_ptr; const uint32_t* adj_nbr; const uint32_t* adj_eid;
+  const float* w;
+  float4* cor_w; float4* ell_w; double4* ell_geo; uint2* adj_nw; uint4* ell_adj;
+};
+// every table entry that stores the weight of an edge incident to a changed vertex: the corner records (CSR + ELL +
+// precomputed unfolding geometry) of all three vertices of each incident face, and both directions of the adjacency
+__global__ void k_refresh_weight_tables(const RefreshArgs a) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)a.n * ELL_W) return;
+  const uint32_t v = a.changed[t / ELL_W], j = (uint32_t)(t % ELL_W);
+  if (v >= a.V) return;
+  for (uint32_t k = a.cor_ptr[v] + j; k < a.cor_ptr[v + 1]; k += ELL_W) {
+    const uint32_t f = (uint32_t)a.cor_idx[k].z;
+    for (int c = 0; c < 3; ++c) {
+      const uint32_t x = a.faces[3 * (size_t)f + c];
+      const uint32_t kb = a.cor_ptr[x], ke = a.cor_ptr[x + 1];
+      for (uint32_t kk = kb; kk < ke; ++kk) {
+        if ((uint32_t)a.cor_idx[kk].z != f) continue;
+        const uint4 e = a.cor_eid[kk];
+        const float4 ww = make_float4(a.w[e.x], a.w[e.y], a.w[e.z], 0.0f);
+        a.cor_w[kk] = ww;
+        if (kk - kb < ELL_W) {
+          const size_t s = (size_t)x * ELL_W + (kk - kb);
+          a.ell_w[s] = ww;
+          const CvpEllProblem::FaceGeo g = CvpEllProblem::face_geo((double)ww.z, (double)ww.y, (double)ww.x);
+          a.ell_geo[s] = make_double4(g.p, g.hc, g.t0a, 0.0);
+        }
+        break;
+      }
+    }
+  }
+  const uint32_t ab = a.adj_ptr[v];
+  for (uint32_t k = ab + j; k < a.adj_ptr[v + 1]; k += ELL_W) {
+    const uint32_t u = a.adj_nbr[k], wb = __float_as_uint(a.w[a.adj_eid[k]]);
+    a.adj_nw[k] = make_uint2(u, wb);
+    if (k - ab < ELL_W) reinterpret_cast<uint32_t*>(&a.ell_adj[(size_t)v * ELL_W + (k - ab)])[1] = wb;
+    const uint32_t ub = a.adj_ptr[u], ue = a.adj_ptr[u + 1];
+    for (uint32_t kk = ub; kk < ue; ++kk) {
+      if (a.adj_nbr[kk] != v) continue;
+      a.adj_nw[kk] = make_uint2(v, wb);
+      if (kk - ub < ELL_W) reinterpret_cast<uint32_t*>(&a.ell_adj[(size_t)u * ELL_W + (kk - ub)])[1] = wb;
+      break;
+    }
+  }
+}
+
+constexpr int COMB_MAX_LAYERS = 8;
+struct CombineArgs {
+  const float* costs[COMB_MAX_LAYERS]; const uint8_t* lethal[COMB_MAX_LAYERS]; float def[COMB_MAX_LAYERS];
+  uint32_t n_layers;
+  const uint32_t* changed; uint32_t n, V;
+  float* io_costs; uint8_t* io_lethal;
+};
+__global__ void k_max_combination_update(const CombineArgs a) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const uint32_t v = a.changed[i];
+  if (v >= a.V) return;
+  float cost = 0.0f; bool lethal = false;
+  for (uint32_t l = 0; l < a.n_layers; ++l) {
+    float tmp = a.costs[l][v];
+    if (tmp != tmp) tmp = a.def[l];                        // cm.get(v).value_or(def), combination_layer.cpp:116
+    cost = fmaxf(tmp, cost);                               // std::max(tmp, cost): NaN never enters (tmp is not NaN... unless def is)
+    lethal = lethal || (a.lethal[l] && a.lethal[l][v]);
+  }
+  a.io_costs[v] = cost;
+  if (a.io_lethal) a.io_lethal[v] = lethal ? 1 : 0;
+}
+
+// update set of InflationLayer::onInputChanged: keys(new riskiness) U keys(old riskiness), ascending.
+// Ordered compaction in three small kernels: per-tile counts, one-CTA exclusive scan of the tile counts, ordered write.
+constexpr int US_TILE = 2048;    // vertices per CTA (256 threads x 8)
+__device__ __forceinline__ bool in_update_set(const float* __restrict__ nw, const float* __restrict__ old, uint32_t v) {
+  const float a = nw[v];
+  if (a == a) return true;
+  if (old) { const float b = old[v]; return b == b; }
+  return false;
+}
+__global__ void __launch_bounds__(256) k_update_set_count(const float* __restrict__ nw, const float* __restrict__ old, uint32_t V,
+                                                          unsigned int* __restrict__ tile_count) {
+  __shared__ unsigned int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  unsigned int mine = 0;
+  const uint32_t base = blockIdx.x * (uint32_t)US_TILE;
+  for (int r = 0; r < US_TILE / 256; ++r) {
+    const uint32_t v = base + r * 256 + threadIdx.x;
+    if (v < V && in_update_set(nw, old, v)) mine++;
+  }
+  const unsigned int wsum = __reduce_add_sync(0xffffffffu, mine);
+  if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(&cnt, wsum);
+  __syncthreads();
+  if (threadIdx.x == 0) tile_count[blockIdx.x] = cnt;
+}
+__global__ void __launch_bounds__(1024) k_update_set_scan(unsigned int* __restrict__ tile_count, uint32_t n_tiles, unsigned int* __restrict__ total) {
+  __shared__ unsigned int warp_sum[32];
+  __shared__ unsigned int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_tiles; base += blockDim.x) {
+    const uint32_t i = base + threadIdx.x;
+    const unsigned int x = i < n_tiles ? tile_count[i] : 0u;
+    unsigned int incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, incl, o); if ((int)(threadIdx.x & 31) >= o) incl += y; }
+    if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const unsigned int ws = threadIdx.x < (blockDim.x >> 5) ? warp_sum[threadIdx.x] : 0u;
+      unsigned int wi = ws;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, wi, o); if ((int)threadIdx.x >= o) wi += y; }
+      warp_sum[threadIdx.x] = wi - ws;                      // exclusive prefix of the warp sums
+    }
+    __syncthreads();
+    const unsigned int excl = carry + warp_sum[threadIdx.x >> 5] + incl - x;
+    if (i < n_tiles) tile_count[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = excl + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(256) k_update_set_write(const float* __restrict__ nw, const float* __restrict__ old, uint32_t V,
+                                                          const unsigned int* __restrict__ tile_offset, uint32_t* __restrict__ out) {
+  __shared__ unsigned int warp_base[8];
+  __shared__ unsigned int run;
+  if (threadIdx.x == 0) run = tile_offset[blockIdx.x];
+  __syncthreads();
+  const uint32_t base = blockIdx.x * (uint32_t)US_TILE;
+  for (int r = 0; r < US_TILE / 256; ++r) {
+    const uint32_t v = base + r * 256 + threadIdx.x;
+    const bool in = v < V && in_update_set(nw, old, v);
+    const unsigned int bal = __ballot_sync(0xffffffffu, in);
+    const unsigned int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) warp_base[wid] = __popc(bal);
+    __syncthreads();
+    unsigned int before = 0;
+    for (unsigned int q = 0; q < wid; ++q) before += warp_base[q];
+    unsigned int row_total = 0;
+    for (unsigned int q = 0; q < 8; ++q) row_total += warp_base[q];
+    if (in) out[run + before + __popc(bal & ((1u << lane) - 1u))] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) run += row_total;
+    __syncthreads();
+  }
+}
+
 // ============================================================================
 // host side
 // ============================================================================
@@ -1021,6 +1212,10 @@ struct mnb_ctx {
   uint32_t last_seed_face = 0; float last_seed_pos[3] = {0, 0, 0}; bool last_valid = false;
   float* d_path_pos = nullptr; uint32_t* d_path_face = nullptr; int32_t* d_bt_result = nullptr; uint32_t path_cap = 0;
   uint32_t* d_lethals = nullptr; uint32_t lethal_cap = 0; uint8_t* d_infl_invalid = nullptr; float* d_out_cost = nullptr;
+  // incremental updates
+  float* d_prev_risk = nullptr; bool prev_risk_valid = false;     // riskiness map of the previous inflation (NaN = no entry)
+  uint32_t* d_upd_ids = nullptr; float* d_upd_costs = nullptr; size_t upd_cap = 0; size_t upd_cost_cap = 0;
+  uint32_t* d_changed = nullptr; unsigned int* d_tile_count = nullptr; unsigned int* d_total = nullptr;
   // tuning
   float delta = 0.3f; int cluster = -1 /* -1: whole-grid cooperative kernel for single plans */; int batch_cluster = 1; int threads = 512;
   int grid_blocks_per_sm = 0;
@@ -1053,6 +1248,8 @@ static void free_mesh(mnb_ctx* c) {
   c->ws_groups = 0;
   dfree(c->d_out_dist); c->out_dist_cap = 0; dfree(c->d_out_pred); dfree(c->d_out_dir); dfree(c->d_out_cut);
   dfree(c->d_infl_invalid); dfree(c->d_out_cost);
+  dfree(c->d_prev_risk); c->prev_risk_valid = false; dfree(c->d_upd_ids); dfree(c->d_upd_costs); c->upd_cap = 0; c->upd_cost_cap = 0;
+  dfree(c->d_changed); dfree(c->d_tile_count); dfree(c->d_total);
   dfree(c->d_path_pos); dfree(c->d_path_face); dfree(c->d_bt_result); c->path_cap = 0; c->last_valid = false;
   dfree(c->d_face_normals); dfree(c->d_vertex_normals); dfree(c->d_border); dfree(c->d_layer_costs); dfree(c->d_layer_combined);
   dfree(c->d_layer_mask); dfree(c->d_clearance); dfree(c->d_overflow);
@@ -1661,8 +1858,12 @@ int32_t mnb_debug_get_labels(mnb_ctx* ctx, uint32_t* out4v) {
   return MNB_OK;
 }
 
-int32_t mnb_inflate(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, const uint8_t* invalid,
-                    const mnb_inflation_params* params, float* out_dist, float* out_cost) {
+}  // extern "C"
+
+// InflationLayer::waveCostInflation; with want_update additionally the update set of InflationLayer::onInputChanged
+static int32_t inflate_impl(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, const uint8_t* invalid,
+                            const mnb_inflation_params* params, float* out_dist, float* out_cost, bool want_update,
+                            uint32_t* out_changed, uint32_t* n_changed) {
   if (!ctx || !ctx->V || !params || (n && !lethals)) return MNB_E_ARG;
   CK(cudaSetDevice(ctx->device));
   int32_t rc;
@@ -1694,7 +1895,149 @@ int32_t mnb_inflate(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, const uin
     if (out_dist) CK(cudaMemcpyAsync(out_dist, a.out_dist, sizeof(float) * (size_t)ctx->V, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_cost) CK(cudaMemcpyAsync(out_cost, a.out_cost, sizeof(float) * (size_t)ctx->V, cudaMemcpyDeviceToHost, ctx->stream));
   }
-  return finish_stats(ctx, 1, 1);
+  int32_t rc2 = finish_stats(ctx, 1, 1);
+  if (rc2 != MNB_OK) return rc2;
+  // the riskiness map of this run is the "previous" one of the next mnb_inflation_update (riskiness_ = std::move(new_costs))
+  const size_t V = ctx->V;
+  if (want_update) {
+    const uint32_t n_tiles = (uint32_t)((V + US_TILE - 1) / US_TILE);
+    if (!ctx->d_changed) { CK(dalloc(&ctx->d_changed, V)); CK(dalloc(&ctx->d_tile_count, (size_t)n_tiles)); CK(dalloc(&ctx->d_total, (size_t)1)); }
+    const float* old = ctx->prev_risk_valid ? ctx->d_prev_risk : nullptr;
+    uint32_t* d_out = (dev && out_changed) ? out_changed : ctx->d_changed;
+    MNB_LAUNCH(k_update_set_count, n_tiles, 256, 0, ctx->stream, (const float*)a.out_cost, old, ctx->V, ctx->d_tile_count);
+    MNB_LAUNCH(k_update_set_scan, 1, 1024, 0, ctx->stream, ctx->d_tile_count, n_tiles, ctx->d_total);
+    MNB_LAUNCH(k_update_set_write, n_tiles, 256, 0, ctx->stream, (const float*)a.out_cost, old, ctx->V, (const unsigned int*)ctx->d_tile_count, d_out);
+    CK(cudaGetLastError());
+    unsigned int total = 0;
+    CK(cudaMemcpyAsync(&total, ctx->d_total, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_changed) *n_changed = total;
+    if (!dev && out_changed && total) CK(cudaMemcpyAsync(out_changed, d_out, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.kernel_launches += 3;
+  }
+  if (!ctx->d_prev_risk) CK(dalloc(&ctx->d_prev_risk, V));
+  CK(cudaMemcpyAsync(ctx->d_prev_risk, a.out_cost, sizeof(float) * V, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->prev_risk_valid = true;
+  return MNB_OK;
+}
+
+extern "C" {
+
+int32_t mnb_inflate(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, const uint8_t* invalid,
+                    const mnb_inflation_params* params, float* out_dist, float* out_cost) {
+  return inflate_impl(ctx, lethals, n, invalid, params, out_dist, out_cost, false, nullptr, nullptr);
+}
+
+int32_t mnb_inflation_update(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, const uint8_t* invalid,
+                             const mnb_inflation_params* params, float* out_dist, float* out_cost, uint32_t* out_changed,
+                             uint32_t* n_changed) {
+  if (!n_changed) return MNB_E_ARG;
+  return inflate_impl(ctx, lethals, n, invalid, params, out_dist, out_cost, true, out_changed, n_changed);
+}
+
+int32_t mnb_get_costs(mnb_ctx* ctx, float* out_vertex_costs, float* out_edge_weights) {
+  if (!ctx || !ctx->V) return MNB_E_ARG;
+  if (!ctx->costs_set) { ctx->err = "costs not set"; return MNB_E_STATE; }
+  CK(cudaSetDevice(ctx->device));
+  if (out_vertex_costs) CK(cudaMemcpyAsync(out_vertex_costs, ctx->d_cost, sizeof(float) * (size_t)ctx->V, out_kind(ctx), ctx->stream));
+  if (out_edge_weights) CK(cudaMemcpyAsync(out_edge_weights, ctx->d_edge_w, sizeof(float) * (size_t)ctx->E, out_kind(ctx), ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MNB_OK;
+}
+
+int32_t mnb_update_vertex_costs(mnb_ctx* ctx, uint32_t n_changed, const uint32_t* changed, const float* costs,
+                                int32_t costs_indexed_by_vertex, float default_value, double edge_cost_factor) {
+  if (!ctx || !ctx->V || (n_changed && (!changed || !costs))) return MNB_E_ARG;
+  if (!ctx->costs_set) { ctx->err = "mnb_update_vertex_costs needs mnb_set_costs / mnb_compute_edge_weights first"; return MNB_E_STATE; }
+  if (n_changed == 0) return MNB_OK;
+  CK(cudaSetDevice(ctx->device));
+  const bool dev = ctx->ptr_mode == MNB_PTR_DEVICE;
+  const uint32_t* d_ids = changed; const float* d_costs = costs;
+  if (!dev) {
+    const size_t nc = costs_indexed_by_vertex ? (size_t)ctx->V : (size_t)n_changed;
+    if (n_changed > ctx->upd_cap) { dfree(ctx->d_upd_ids); ctx->upd_cap = 0; CK(dalloc(&ctx->d_upd_ids, (size_t)n_changed)); ctx->upd_cap = n_changed; }
+    if (nc > ctx->upd_cost_cap) { dfree(ctx->d_upd_costs); ctx->upd_cost_cap = 0; CK(dalloc(&ctx->d_upd_costs, nc)); ctx->upd_cost_cap = nc; }
+    CK(cudaMemcpyAsync(ctx->d_upd_ids, changed, sizeof(uint32_t) * (size_t)n_changed, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_upd_costs, costs, sizeof(float) * nc, cudaMemcpyHostToDevice, ctx->stream));
+    d_ids = ctx->d_upd_ids; d_costs = ctx->d_upd_costs;
+  }
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  unsigned launches = 1;
+  MNB_LAUNCH(k_update_costs, (n_changed + 255) / 256, 256, 0, ctx->stream, d_ids, n_changed, d_costs, (int)(costs_indexed_by_vertex != 0),
+             default_value, ctx->V, ctx->d_cost);
+  if (edge_cost_factor != 0) {                       // mesh_map.cpp:568-572: no edge update at all for a zero factor
+    const unsigned blocks = (unsigned)(((size_t)n_changed * ELL_W + 255) / 256);
+    MNB_LAUNCH(k_update_edge_weights, blocks, 256, 0, ctx->stream, d_ids, n_changed, ctx->V, (const uint32_t*)ctx->d_adj_ptr,
+               (const uint32_t*)ctx->d_adj_eid, (const uint32_t*)ctx->d_edges, (const float*)ctx->d_cost, (const float*)ctx->d_edge_dist,
+               edge_cost_factor, ctx->d_edge_w);
+    RefreshArgs r{};
+    r.changed = d_ids; r.n = n_changed; r.V = ctx->V; r.faces = ctx->d_faces; r.cor_ptr = ctx->d_cor_ptr; r.cor_idx = ctx->d_cor_idx;
+    r.cor_eid = ctx->d_cor_eid; r.adj_ptr = ctx->d_adj_ptr; r.adj_nbr = ctx->d_adj_nbr; r.adj_eid = ctx->d_adj_eid; r.w = ctx->d_edge_w;
+    r.cor_w = ctx->d_cor_w; r.ell_w = ctx->d_ell_w; r.ell_geo = ctx->d_ell_geo; r.adj_nw = ctx->d_adj_nw; r.ell_adj = ctx->d_ell_adj;
+    MNB_LAUNCH(k_refresh_weight_tables, blocks, 256, 0, ctx->stream, r);
+    launches = 3;
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->stats = mnb_stats{}; ctx->stats.kernel_ms = ms; ctx->stats.kernel_launches = launches; ctx->stats.settled = n_changed;
+  ctx->last_valid = false;                           // the device-resident plan no longer belongs to the installed costs
+  return MNB_OK;
+}
+
+int32_t mnb_max_combination_update(mnb_ctx* ctx, uint32_t n_layers, const float* const* layer_costs, const float* defaults,
+                                   const uint8_t* const* layer_lethal, uint32_t n_changed, const uint32_t* changed,
+                                   float* io_costs, uint8_t* io_lethal) {
+  if (!ctx || !ctx->V || n_layers == 0 || n_layers > (uint32_t)COMB_MAX_LAYERS || !layer_costs || !defaults || !io_costs ||
+      (n_changed && !changed)) return MNB_E_ARG;
+  for (uint32_t l = 0; l < n_layers; ++l) if (!layer_costs[l]) return MNB_E_ARG;
+  if (n_changed == 0) return MNB_OK;
+  CK(cudaSetDevice(ctx->device));
+  const bool dev = ctx->ptr_mode == MNB_PTR_DEVICE;
+  const size_t V = ctx->V;
+  CombineArgs a{};
+  a.n_layers = n_layers; a.n = n_changed; a.V = ctx->V;
+  std::vector<void*> tmp;                             // host-pointer mode: device copies of the maps
+  auto cleanup = [&]() { for (void* q : tmp) cudaFree(q); };
+  auto up = [&](const void* h, size_t bytes, void** d) -> cudaError_t {
+    cudaError_t e = cudaMalloc(d, bytes ? bytes : 1); if (e != cudaSuccess) return e;
+    tmp.push_back(*d);
+    return cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  };
+  cudaError_t e = cudaSuccess;
+  for (uint32_t l = 0; l < n_layers && e == cudaSuccess; ++l) {
+    a.def[l] = defaults[l];
+    if (dev) { a.costs[l] = layer_costs[l]; a.lethal[l] = layer_lethal ? layer_lethal[l] : nullptr; continue; }
+    void* d = nullptr;
+    e = up(layer_costs[l], sizeof(float) * V, &d); a.costs[l] = (const float*)d;
+    if (e == cudaSuccess && layer_lethal && layer_lethal[l]) { e = up(layer_lethal[l], V, &d); a.lethal[l] = (const uint8_t*)d; }
+  }
+  void* d_ids = nullptr; void* d_io = nullptr; void* d_il = nullptr;
+  if (!dev && e == cudaSuccess) {
+    e = up(changed, sizeof(uint32_t) * (size_t)n_changed, &d_ids);
+    if (e == cudaSuccess) e = up(io_costs, sizeof(float) * V, &d_io);
+    if (e == cudaSuccess && io_lethal) e = up(io_lethal, V, &d_il);
+  }
+  if (e != cudaSuccess) { cleanup(); ctx->err = std::string("mnb_max_combination_update: ") + cudaGetErrorString(e); return MNB_E_CUDA; }
+  a.changed = dev ? changed : (const uint32_t*)d_ids;
+  a.io_costs = dev ? io_costs : (float*)d_io;
+  a.io_lethal = dev ? io_lethal : (uint8_t*)d_il;
+  cudaEventRecord(ctx->ev0, ctx->stream);
+  MNB_LAUNCH(k_max_combination_update, (n_changed + 255) / 256, 256, 0, ctx->stream, a);
+  e = cudaGetLastError();
+  cudaEventRecord(ctx->ev1, ctx->stream);
+  if (e == cudaSuccess && !dev) {
+    e = cudaMemcpyAsync(io_costs, a.io_costs, sizeof(float) * V, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && io_lethal) e = cudaMemcpyAsync(io_lethal, a.io_lethal, V, cudaMemcpyDeviceToHost, ctx->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cleanup();
+  if (e != cudaSuccess) { ctx->err = std::string("mnb_max_combination_update: ") + cudaGetErrorString(e); return MNB_E_CUDA; }
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->stats = mnb_stats{}; ctx->stats.kernel_ms = ms; ctx->stats.kernel_launches = 1; ctx->stats.settled = n_changed;
+  return MNB_OK;
 }
 
 }  // extern "C"

@@ -982,3 +982,74 @@ extern "C" void orc_locate(void* h, uint32_t n, const float* points, uint32_t* n
     if (bary) { bary[3 * (size_t)q] = bb[0]; bary[3 * (size_t)q + 1] = bb[1]; bary[3 * (size_t)q + 2] = bb[2]; }
   }
 }
+
+// ---------------------------------------------------------------------------
+// Incremental updates: the sensor-rate callers of the hot path.  NaN = "no entry in the sparse
+// lvr2 map"; `changed` plays the std::set<VertexHandle> (ascending, unique).
+// ---------------------------------------------------------------------------
+// MeshMap::layerChanged  mesh_map.cpp:455-492, the vertex-cost part :478-487:
+//   vertex_costs.insert(vH, cost_map.get(vH).value_or(default_value)) for vH in changes
+extern "C" void orc_layer_changed(const float* layer_costs, float default_value, const uint32_t* changed, uint32_t n,
+                                  float* vertex_costs) {
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t vH = changed[i];
+    vertex_costs[vH] = std::isnan(layer_costs[vH]) ? default_value : layer_costs[vH];
+  }
+}
+
+// MeshMap::updateEdgeWeights  mesh_map.cpp:563-618: only the edges incident to a changed vertex are recomputed, and
+// NOTHING is recomputed when edge_cost_factor == 0 (:568-572) -- unlike computeEdgeWeights, an endpoint cost that
+// became +inf then leaves the old weight in place.
+extern "C" void orc_update_edge_weights(void* h, const float* vertex_costs, const float* edge_distances, double edge_cost_factor,
+                                        const uint32_t* changed, uint32_t n, float* edge_weights) {
+  OrcMesh* m = (OrcMesh*)h;
+  if (0 == edge_cost_factor) return;                                                 // :568
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t changedH = changed[i];
+    for (uint32_t k = m->ve_ptr[changedH]; k < m->ve_ptr[changedH + 1]; ++k) {       // getEdgesOfVertex :580
+      const uint32_t eH = m->ve_edge[k];
+      const float v1cost = vertex_costs[m->edges[2 * (size_t)eH]];
+      const float v2cost = vertex_costs[m->edges[2 * (size_t)eH + 1]];
+      if (std::isinf(v1cost) || std::isinf(v2cost)) {                                // :598
+        edge_weights[eH] = FINF;
+      } else {
+        const float vertex_dist = edge_distances[eH];
+        const float edge_cost = vertex_dist * (v1cost + v2cost) / 2.0;               // :609
+        edge_weights[eH] = vertex_dist + edge_cost_factor * edge_cost;               // :611
+      }
+    }
+  }
+}
+
+// MaxCombinationLayer::onInputChanged  combination_layer.cpp:87-147: for every changed vertex
+//   cost = max over the input layers of (value or the layer's default), starting from 0 (:109-118);
+//   lethal = the vertex is in the lethal set of any input (:122-139).
+extern "C" void orc_max_combination_update(uint32_t n_layers, const float* const* layer_costs, const float* defaults,
+                                           const uint8_t* const* layer_lethals, const uint32_t* changed, uint32_t n,
+                                           float* costs, uint8_t* lethals) {
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t v = changed[i];
+    float cost = 0;
+    for (uint32_t l = 0; l < n_layers; ++l) {
+      const float tmp = std::isnan(layer_costs[l][v]) ? defaults[l] : layer_costs[l][v];
+      cost = std::max(tmp, cost);
+    }
+    costs[v] = cost;
+  }
+  if (lethals)
+    for (uint32_t i = 0; i < n; ++i) {
+      const uint32_t v = changed[i];
+      bool lethal = false;
+      for (uint32_t l = 0; l < n_layers; ++l) lethal = lethal || (layer_lethals[l] && layer_lethals[l][v]);
+      lethals[v] = lethal ? 1 : 0;
+    }
+}
+
+// InflationLayer::onInputChanged  inflation_layer.cpp:154-164: the update set handed to notifyChange is the union of the
+// keys of the new and of the previous riskiness map (std::set: ascending).  Returns its size.
+extern "C" uint32_t orc_inflation_update_set(uint32_t V, const float* new_costs, const float* old_costs, uint32_t* out) {
+  uint32_t n = 0;
+  for (uint32_t v = 0; v < V; ++v)
+    if (!std::isnan(new_costs[v]) || (old_costs && !std::isnan(old_costs[v]))) out[n++] = v;
+  return n;
+}

@@ -61,6 +61,11 @@ def lib():
         L.orc_normals.argtypes = [vp, vp, vp]
         L.orc_layers.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.orc_inflation.argtypes = [vp, vp, vp, vp, u32, dbl, dbl, dbl, dbl, dbl, C.c_int, vp, vp, vp, vp]
+        L.orc_layer_changed.argtypes = [vp, f32, vp, u32, vp]
+        L.orc_update_edge_weights.argtypes = [vp, vp, vp, dbl, vp, u32, vp]
+        L.orc_max_combination_update.argtypes = [u32, vp, vp, vp, vp, u32, vp, vp]
+        L.orc_inflation_update_set.restype = u32
+        L.orc_inflation_update_set.argtypes = [u32, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -158,6 +163,51 @@ class OracleMesh:
                     updates=int(stats[2]))
 
 
+def _layer_changed(layer_costs, default_value, changed, vertex_costs):
+    """MeshMap::layerChanged (mesh_map.cpp:478-487): vertex_costs updated in place for the changed vertices."""
+    lc = np.ascontiguousarray(layer_costs, dtype=np.float32)
+    ch = np.unique(np.ascontiguousarray(changed, dtype=np.uint32))
+    assert vertex_costs.dtype == np.float32 and vertex_costs.flags.c_contiguous
+    lib().orc_layer_changed(_p(lc), C.c_float(default_value), _p(ch), ch.size, _p(vertex_costs))
+    return vertex_costs
+
+
+def _update_edge_weights(self, vertex_costs, edge_distances, edge_cost_factor, changed, edge_weights):
+    """MeshMap::updateEdgeWeights (mesh_map.cpp:563-618): edge_weights updated in place."""
+    vc = np.ascontiguousarray(vertex_costs, dtype=np.float32)
+    ed = np.ascontiguousarray(edge_distances, dtype=np.float32)
+    ch = np.unique(np.ascontiguousarray(changed, dtype=np.uint32))
+    assert edge_weights.dtype == np.float32 and edge_weights.flags.c_contiguous
+    lib().orc_update_edge_weights(self._h, _p(vc), _p(ed), C.c_double(edge_cost_factor), _p(ch), ch.size, _p(edge_weights))
+    return edge_weights
+
+
+def max_combination_update(layer_costs, defaults, layer_lethals, changed, costs, lethals=None):
+    """MaxCombinationLayer::onInputChanged (combination_layer.cpp:87-147): costs / lethals updated in place."""
+    L = len(layer_costs)
+    lcs = [np.ascontiguousarray(a, dtype=np.float32) for a in layer_costs]
+    lls = [None if a is None else np.ascontiguousarray(a, dtype=np.uint8) for a in layer_lethals]
+    cp = (C.c_void_p * L)(*[a.ctypes.data for a in lcs])
+    lp = (C.c_void_p * L)(*[None if a is None else a.ctypes.data for a in lls])
+    df = np.ascontiguousarray(defaults, dtype=np.float32)
+    ch = np.unique(np.ascontiguousarray(changed, dtype=np.uint32))
+    lib().orc_max_combination_update(L, cp, _p(df), lp, _p(ch), ch.size, _p(costs), _p(lethals))
+    return costs, lethals
+
+
+def inflation_update_set(new_costs, old_costs=None):
+    """InflationLayer::onInputChanged (inflation_layer.cpp:154-164): keys(new) U keys(old), ascending."""
+    nc = np.ascontiguousarray(new_costs, dtype=np.float32)
+    oc = None if old_costs is None else np.ascontiguousarray(old_costs, dtype=np.float32)
+    out = np.empty(nc.size, dtype=np.uint32)
+    lib().orc_inflation_update_set.restype = C.c_uint32
+    n = lib().orc_inflation_update_set(nc.size, _p(nc), _p(oc), _p(out))
+    return out[:n].copy()
+
+
+layer_changed = _layer_changed
+
+
 class LayerParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "height_diff_threshold", "height_diff_radius", "roughness_threshold", "roughness_radius", "steepness_threshold",
@@ -186,6 +236,7 @@ def _layers(self, params=None, clearance=None):
 
 
 OracleMesh.layers = _layers
+OracleMesh.update_edge_weights = _update_edge_weights
 
 
 def _dijkstra_vector_map(self, pred):

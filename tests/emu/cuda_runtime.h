@@ -424,6 +424,13 @@ static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
   for (int l = 0; l < 32; ++l) if ((alive >> l) & 1u) r = std::max(r, (unsigned)s[l]);
   return r;
 }
+static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
+  const uint64_t* s = emu::warp_exchange(mask, v);
+  const unsigned alive = emu::g_cta.warps[emu::g_cta.cur->tid >> 5].alive;
+  unsigned r = 0;
+  for (int l = 0; l < 32; ++l) if ((alive >> l) & 1u) r += (unsigned)s[l];
+  return r;
+}
 static inline unsigned __activemask() { return emu::g_cta.warps[emu::g_cta.cur->tid >> 5].alive; }
 
 // ====================================================================================================================

@@ -15,14 +15,16 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 RUNNER = os.path.join(ROOT, "tests", "emu", "run_suite.py")
 
-# (pytest -k expression) groups of tests/test_gpu_parity.py; the 1M-vertex property test stays GPU-only
+# (test file, pytest -k expression) groups; the 1M-vertex property test stays GPU-only
+PARITY = "test_gpu_parity.py"
 GROUPS = [
-    "dijkstra or edge_distances or goal_cutoff_small",
-    "cvp_full_field or cvp_seed or cvp_costs",
-    "cvp_cost_weighted or cvp_batch",
-    "inflation or layers or config3",
-    "irregular or disconnected or vector_maps or backtrack or make_plan or locate",
-    "cancel",
+    (PARITY, "dijkstra or edge_distances or goal_cutoff_small"),
+    (PARITY, "cvp_full_field or cvp_seed or cvp_costs"),
+    (PARITY, "cvp_cost_weighted or cvp_batch"),
+    (PARITY, "inflation or layers or config3"),
+    (PARITY, "irregular or disconnected or vector_maps or backtrack or make_plan or locate"),
+    (PARITY, "cancel"),
+    ("test_gpu_updates.py", "layer_changed or max_combination or on_input_changed"),
 ]
 
 
@@ -32,10 +34,10 @@ def emu_lib():
     return os.path.join(ROOT, "tests", "emu", "libmeshnav_emu.so")
 
 
-@pytest.mark.parametrize("expr", GROUPS)
-def test_gpu_parity_suite_on_the_cpu_interpreter(emu_lib, expr):
+@pytest.mark.parametrize("fname,expr", GROUPS)
+def test_gpu_parity_suite_on_the_cpu_interpreter(emu_lib, fname, expr):
     env = dict(os.environ, MNB_EMU_SMS="4")
-    r = subprocess.run([sys.executable, RUNNER, os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q",
+    r = subprocess.run([sys.executable, RUNNER, os.path.join(ROOT, "tests", fname), "-m", "gpu", "-x", "-q",
                         "-p", "no:cacheprovider", "-k", f"({expr}) and not large_mesh"],
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     tail = (r.stdout + r.stderr)[-3000:]
@@ -45,9 +47,10 @@ def test_gpu_parity_suite_on_the_cpu_interpreter(emu_lib, expr):
 
 def test_every_parity_test_is_in_a_group():
     """the groups above must cover the whole GPU suite (minus the 1M-vertex test)"""
-    src = open(os.path.join(ROOT, "tests", "test_gpu_parity.py")).read()
     import re
-    names = re.findall(r"^def (test_\w+)", src, flags=re.M)
-    words = [w for g in GROUPS for w in g.split(" or ")]
-    missing = [n for n in names if "large_mesh" not in n and not any(w in n for w in words)]
-    assert not missing, f"not covered by any interpreter group: {missing}"
+    for fname in sorted({f for f, _ in GROUPS}):
+        src = open(os.path.join(ROOT, "tests", fname)).read()
+        names = re.findall(r"^def (test_\w+)", src, flags=re.M)
+        words = [w for f, g in GROUPS if f == fname for w in g.split(" or ")]
+        missing = [n for n in names if "large_mesh" not in n and not any(w in n for w in words)]
+        assert not missing, f"{fname}: not covered by any interpreter group: {missing}"
