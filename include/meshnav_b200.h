@@ -206,6 +206,19 @@ int32_t mnb_inflation_update(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, 
                              const mnb_inflation_params* params, float* out_dist, float* out_cost,
                              uint32_t* out_changed /* V */, uint32_t* n_changed);
 
+/* ---- InflationLayer repulsive vector field -------------------------------------------------------------------------
+ * vector_map_ as InflationLayer::waveFrontUpdate accumulates it (inflation_layer.cpp:277-308) for the LAST mnb_inflate /
+ * mnb_inflation_update on this context; zero = no entry.  Derived from that wave's final labels, which live in the
+ * workspace the planners share: call it before the next planner call on the context (MNB_E_STATE otherwise).  The field
+ * and distances_ stay resident on the device.  out_vectors (3V) may be NULL. */
+int32_t mnb_inflation_vector_map(mnb_ctx* ctx, float* out_vectors);
+/* InflationLayer::vectorAt(vertices, barycentric_coords) (inflation_layer.cpp:493-521) of the resident field for n samples:
+ * faces_q[n] face ids, bary[3n] -> out[3n]. */
+int32_t mnb_inflation_vector_at(mnb_ctx* ctx, uint32_t n, const uint32_t* faces_q, const float* bary, float* out);
+/* MeshMap::meshAhead adds every layer's vectorAt to the planner's direction (mesh_map.cpp:1097-1102): enable != 0 makes
+ * mnb_cvp_backtrack add the resident inflation field (config_.repulsive_field, inflation_layer.h:247). */
+int32_t mnb_set_repulsive_field(mnb_ctx* ctx, int32_t enable);
+
 /* ---- cancel (CVPMeshPlanner::cancel / DijkstraMeshPlanner::cancel) ------- */
 int32_t mnb_cancel(mnb_ctx* ctx);
 

@@ -304,6 +304,25 @@ class InflationLayer:
         m._check(m.L.mnb_inflate(m._ctx, _p(le), le.size, _p(inv), C.byref(self.config), _p(dist), _p(cost)))
         return dict(dist=dist, cost=cost, **m.stats())
 
+    def vectorMap(self) -> np.ndarray:
+        """vector_map_ of the last wave (inflation_layer.cpp:277-308), [V,3], zero = no entry; call before the next plan"""
+        m = self.map
+        out = np.empty((m.V, 3), dtype=np.float32)
+        m._check(m.L.mnb_inflation_vector_map(m._ctx, _p(out)))
+        return out
+
+    def vectorAt(self, faces_q, bary) -> np.ndarray:
+        """InflationLayer::vectorAt(vertices, barycentric_coords) (inflation_layer.cpp:493-521) for n samples"""
+        m = self.map
+        fq = np.ascontiguousarray(faces_q, dtype=np.uint32); ba = np.ascontiguousarray(bary, dtype=np.float32).reshape(-1, 3)
+        out = np.empty((fq.size, 3), dtype=np.float32)
+        m._check(m.L.mnb_inflation_vector_at(m._ctx, fq.size, _p(fq), _p(ba), _p(out)))
+        return out
+
+    def setRepulsiveField(self, on: bool):
+        """config_.repulsive_field: meshAhead (the planners' back-tracking) adds this layer's vectorAt"""
+        self.map._check(self.map.L.mnb_set_repulsive_field(self.map._ctx, int(bool(on))))
+
     def onInputChanged(self, lethals, invalid=None):
         """InflationLayer::onInputChanged (inflation_layer.cpp:97-179): full re-inflation + the update set
         (vertices with a riskiness entry now or after the previous inflation on this map, ascending)"""

@@ -683,6 +683,161 @@ __global__ void k_vector_map(const float* __restrict__ pos, const float* __restr
   o[0] = v.x; o[1] = v.y; o[2] = v.z;
 }
 
+
+// ============================================================================
+// InflationLayer repulsive vector field, vector_map_ (inflation_layer.cpp:277-308), from the final labels of k_inflate.
+// The reference accumulates it inside the sequential loop; the result factors into two phases (oracle: orc_inflation):
+//  (1) while the lethal vertices pop (all at key 0, in id order) every face with exactly two lethal vertices adds its
+//      direction to the vectors of its three vertices, once per (popping vertex, incident edge of the face, side of the
+//      edge) -- `vec = (vec + dir).normalized()` in exactly that order (:277-295).  Per vertex this is an ordered fold over
+//      at most 4 events per incident face: gathered, sorted by (popping vertex, edge position, side) and folded here.
+//  (2) afterwards a vertex' vector is overwritten by every accepted update with a non-lethal source,
+//      (vec[v1]*(u3-u1) + vec[v2]*(u3-u2)).normalized() (:301-308): the LAST accepted face of the event-ordered replay
+//      decides; its sources popped earlier, so their vectors are final -- evaluated by fixed-point iteration over the
+//      (acyclic) source relation.
+// ============================================================================
+struct InflVecArgs {
+  uint32_t V;
+  const float* pos; const uint32_t* faces;
+  const uint32_t* cor_ptr; const int4* cor_idx; const float4* cor_wd;
+  const uint32_t* adj_ptr; const uint32_t* adj_nbr;
+  const uint8_t* invalid;
+  WaveWorkspace ws;
+  float max_distance;
+  float* vec;                  // 3V, zero = no entry
+  int4* src;                   // {v1, v2, bits(u3-u1), bits(u3-u2)}; v1 = -1: no overwrite
+  unsigned int* flag;          // [0] a vector changed in this sweep, [1] scratch overflow
+};
+constexpr int IV_MAXF = 24, IV_MAXE = 4 * IV_MAXF;
+
+__device__ __forceinline__ float iv_len(const float* __restrict__ pos, uint32_t p, uint32_t q) {   // == k_edge_dist
+  const float dx = pos[3 * (size_t)p] - pos[3 * (size_t)q], dy = pos[3 * (size_t)p + 1] - pos[3 * (size_t)q + 1],
+              dz = pos[3 * (size_t)p + 2] - pos[3 * (size_t)q + 2];
+  return sqrtf(dx * dx + dy * dy + dz * dz);
+}
+
+__global__ void __launch_bounds__(128) k_infl_vec_lethal(const InflVecArgs a) {
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= a.V) return;
+  float* out = a.vec + 3 * (size_t)x;
+  out[0] = 0.0f; out[1] = 0.0f; out[2] = 0.0f;
+  unsigned long long key[IV_MAXE]; uint8_t ev_face[IV_MAXE];
+  F3 fdir[IV_MAXF];
+  int ne = 0, nf = 0;
+  for (uint32_t k = a.cor_ptr[x]; k < a.cor_ptr[x + 1]; ++k) {
+    const uint32_t f = (uint32_t)a.cor_idx[k].z;
+    const uint32_t fa = a.faces[3 * (size_t)f], fb = a.faces[3 * (size_t)f + 1], fc = a.faces[3 * (size_t)f + 2];
+    const bool la = __uint_as_float(a.ws.state[fa].x) == 0.0f, lb = __uint_as_float(a.ws.state[fb].x) == 0.0f,
+               lc = __uint_as_float(a.ws.state[fc].x) == 0.0f;
+    uint32_t w1, w2, w3;                                       // argument order of waveFrontUpdate (:445-470)
+    if (la && lb && !lc) { w1 = fa; w2 = fb; w3 = fc; }
+    else if (la && !lb && lc) { w1 = fc; w2 = fa; w3 = fb; }
+    else if (!la && lb && lc) { w1 = fb; w2 = fc; w3 = fa; }
+    else continue;
+    const float cand = inflation_candidate(0.0f, 0.0f, iv_len(a.pos, w2, w3), iv_len(a.pos, w1, w3), iv_len(a.pos, w1, w2));
+    if (__float_as_uint(cand) == INF_BITS) continue;           // :271 non-finite update: the call returns before the vectors
+    if (nf >= IV_MAXF) { atomicAdd(&a.flag[1], 1u); return; }
+    const F3 p1 = f3load(a.pos, w1), p2 = f3load(a.pos, w2), p3 = f3load(a.pos, w3);
+    fdir[nf] = f3normalized(F3{(p3.x - p2.x) + (p3.x - p1.x), (p3.y - p2.y) + (p3.y - p1.y), (p3.z - p2.z) + (p3.z - p1.z)});
+    const uint32_t lv[2] = {w1, w2};
+    for (int s = 0; s < 2; ++s) {
+      const uint32_t p = lv[s];                                // the popping lethal vertex
+      if (a.invalid && a.invalid[p]) continue;                 // pops but does not expand (:417)
+      const uint32_t others[2] = {p == w1 ? w2 : w1, w3};
+      for (int t = 0; t < 2; ++t) {
+        const uint32_t q = others[t];
+        uint32_t epos = 0;                                     // position of edge (p,q) among p's edges (ascending edge id)
+        for (uint32_t kk = a.adj_ptr[p]; kk < a.adj_ptr[p + 1]; ++kk) if (a.adj_nbr[kk] == q) { epos = kk - a.adj_ptr[p]; break; }
+        uint32_t side = 0;                                     // an edge lists its faces in ascending id
+        for (uint32_t kk = a.cor_ptr[p]; kk < a.cor_ptr[p + 1]; ++kk) {
+          const int4 ix = a.cor_idx[kk];
+          if ((uint32_t)ix.z != f && ((uint32_t)ix.x == q || (uint32_t)ix.y == q)) { side = (uint32_t)ix.z < f ? 1u : 0u; break; }
+        }
+        key[ne] = ((unsigned long long)p << 32) | ((unsigned long long)epos << 1) | side;
+        ev_face[ne] = (uint8_t)nf; ++ne;
+      }
+    }
+    ++nf;
+  }
+  if (ne == 0) return;
+  F3 v{0.0f, 0.0f, 0.0f};
+  for (int i = 0; i < ne; ++i) {                               // selection sort: <= 96 events, usually 4-16
+    int b = i;
+    for (int j = i + 1; j < ne; ++j) if (key[j] < key[b]) b = j;
+    const unsigned long long kb = key[b]; const uint8_t fbi = ev_face[b];
+    key[b] = key[i]; ev_face[b] = ev_face[i]; key[i] = kb; ev_face[i] = fbi;
+    const F3 d = fdir[fbi];
+    v = f3normalized(F3{v.x + d.x, v.y + d.y, v.z + d.z});
+  }
+  out[0] = v.x; out[1] = v.y; out[2] = v.z;
+}
+
+__global__ void __launch_bounds__(128) k_infl_vec_sources(const InflVecArgs a) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.V) return;
+  int4 r = make_int4(-1, -1, 0, 0);
+  const float d = __uint_as_float(a.ws.state[c].x);
+  if (d != 0.0f && __float_as_uint(d) != INF_BITS) {
+    InflationProblem prob;
+    prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_wd = a.cor_wd; prob.invalid = a.invalid;
+    prob.state = a.ws.state; prob.minor_arr = a.ws.minor; prob.root_arr = a.ws.root; prob.chg = a.ws.chg;
+    prob.deferred_m = __uint_as_float(INF_BITS); prob.strict = 0; prob.max_distance = a.max_distance;
+    float nd, wu1, wu2; EvTime tc; int win;
+    prob.replay(c, __uint_as_float(INF_BITS), 0xfffffff0u /* final labels: nothing is deferred */, nd, tc, win, wu1, wu2);
+    if (win >= 0 && (wu1 != 0.0f || wu2 != 0.0f)) {           // :301 (an update from two lethal sources keeps the phase-1 vector)
+      const int4 ix = a.cor_idx[win];
+      r = make_int4(ix.x, ix.y, __float_as_int(nd - wu1), __float_as_int(nd - wu2));
+    }
+  }
+  a.src[c] = r;
+}
+
+__global__ void __launch_bounds__(256) k_infl_vec_sweep(const InflVecArgs a) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.V) return;
+  const int4 r = a.src[c];
+  if (r.x < 0) return;
+  const float d31 = __int_as_float(r.z), d32 = __int_as_float(r.w);
+  const float* va = a.vec + 3 * (size_t)r.x; const float* vb = a.vec + 3 * (size_t)r.y;
+  const F3 v = f3normalized(F3{va[0] * d31 + vb[0] * d32, va[1] * d31 + vb[1] * d32, va[2] * d31 + vb[2] * d32});   // :306
+  float* out = a.vec + 3 * (size_t)c;
+  if (__float_as_uint(out[0]) != __float_as_uint(v.x) || __float_as_uint(out[1]) != __float_as_uint(v.y) ||
+      __float_as_uint(out[2]) != __float_as_uint(v.z)) {
+    out[0] = v.x; out[1] = v.y; out[2] = v.z;
+    a.flag[0] = 1u;
+  }
+}
+
+// InflationLayer::vectorAt(vertices, barycentric_coords) (inflation_layer.cpp:493-521); see oracle inflationVectorAt
+struct RepulsiveField {
+  const float* dist; const float* vec;   // null = no repulsive layer
+  float inscribed_radius_f; double inscribed_radius, inflation_radius; float lethal_value, inscribed_value;
+};
+__device__ __forceinline__ F3 inflation_vector_at(const RepulsiveField& L, const uint32_t* __restrict__ t, const float bary[3]) {
+  const float d0 = L.dist[t[0]], d1 = L.dist[t[1]], d2 = L.dist[t[2]];
+  if (!isfinite(d0) || !isfinite(d1) || !isfinite(d2)) return F3{0.0f, 0.0f, 0.0f};
+  const float distance = d0 * bary[0] + d1 * bary[1] + d2 * bary[2];
+  if ((double)distance > L.inflation_radius) return F3{0.0f, 0.0f, 0.0f};
+  const F3 va = f3load(L.vec, t[0]), vb = f3load(L.vec, t[1]), vc = f3load(L.vec, t[2]);
+  const F3 v{va.x * bary[0] + vb.x * bary[1] + vc.x * bary[2], va.y * bary[0] + vb.y * bary[1] + vc.y * bary[2],
+             va.z * bary[0] + vb.z * bary[1] + vc.z * bary[2]};
+  if ((double)distance > L.inscribed_radius) {
+    const float alpha = (float)(((double)sqrtf(distance) - L.inscribed_radius) / (L.inflation_radius - L.inscribed_radius) * 3.14159265358979323846);
+    const float s1 = L.inscribed_value, s2 = cosf(alpha) + 1, s3 = 2.0f;
+    return F3{v.x * s1 * s2 / s3, v.y * s1 * s2 / s3, v.z * s1 * s2 / s3};
+  }
+  const float s = distance > 0 ? L.inscribed_value : L.lethal_value;
+  return F3{v.x * s, v.y * s, v.z * s};
+}
+__global__ void k_inflation_vector_at(const RepulsiveField L, const uint32_t* __restrict__ faces, uint32_t n,
+                                      const uint32_t* __restrict__ faces_q, const float* __restrict__ bary, float* __restrict__ out) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const float b[3] = {bary[3 * (size_t)q], bary[3 * (size_t)q + 1], bary[3 * (size_t)q + 2]};
+  const F3 v = inflation_vector_at(L, faces + 3 * (size_t)faces_q[q], b);
+  out[3 * (size_t)q] = v.x; out[3 * (size_t)q + 1] = v.y; out[3 * (size_t)q + 2] = v.z;
+}
+
 // ============================================================================
 // Vector-field back-tracking (cvp_mesh_planner.cpp:920-951): MeshMap::meshAhead (mesh_map.cpp:1070-1108),
 // searchNeighbourFaces (:999-1068), directionAtPosition (:625-650), projectedBarycentricCoords (util.cpp:313-347).
@@ -695,6 +850,7 @@ struct BacktrackArgs {
   float start[3]; uint32_t start_face; float goal[3]; uint32_t goal_face;
   double step_width; uint32_t max_points;
   float* path_pos; uint32_t* path_face; int32_t* result /* [0] outcome, [1] n_points */; const int* cancel_flag;
+  RepulsiveField layer;        // InflationLayer::vectorAt added in meshAhead (mesh_map.cpp:1097-1102); dist == null: none
 };
 
 __device__ __forceinline__ bool projected_barycentric(F3 p, F3 a, F3 b, F3 c, float bary[3], float& dist) {
@@ -853,7 +1009,9 @@ __global__ void __launch_bounds__(32) k_backtrack(BacktrackArgs a) {
       vec = {vec.x + e.x * bary[k], vec.y + e.y * bary[k], vec.z + e.z * bary[k]};
     }
     if (!any || !(isfinite(vec.x) && isfinite(vec.y) && isfinite(vec.z))) { outcome = MNB_NO_PATH_FOUND; break; }
-    const F3 dir = f3normalized(f3normalized(vec));      // .normalized(); += zero layer fields; .normalize()
+    F3 dir = f3normalized(vec);                          // opt_dir.get().normalized()
+    if (a.layer.dist) { const F3 lv = inflation_vector_at(a.layer, t, bary); dir = F3{dir.x + lv.x, dir.y + lv.y, dir.z + lv.z}; }
+    dir = f3normalized(dir);                             // dir += layer->vectorAt(...); dir.normalize()
     pos = {pos.x + dir.x * step, pos.y + dir.y * step, pos.z + dir.z * step};
     push(pos, face);
   }
@@ -1212,6 +1370,10 @@ struct mnb_ctx {
   uint32_t last_seed_face = 0; float last_seed_pos[3] = {0, 0, 0}; bool last_valid = false;
   float* d_path_pos = nullptr; uint32_t* d_path_face = nullptr; int32_t* d_bt_result = nullptr; uint32_t path_cap = 0;
   uint32_t* d_lethals = nullptr; uint32_t lethal_cap = 0; uint8_t* d_infl_invalid = nullptr; float* d_out_cost = nullptr;
+  // repulsive vector field of the last inflation (InflationLayer::vector_map_ / distances_)
+  bool infl_labels_valid = false, infl_had_invalid = false, infl_field_valid = false, repulsive_on = false;
+  mnb_inflation_params infl_params{};
+  float* d_infl_vec = nullptr; float* d_infl_dist = nullptr; int4* d_infl_src = nullptr; unsigned int* d_infl_flag = nullptr;
   // incremental updates
   float* d_prev_risk = nullptr; bool prev_risk_valid = false;     // riskiness map of the previous inflation (NaN = no entry)
   uint32_t* d_upd_ids = nullptr; float* d_upd_costs = nullptr; size_t upd_cap = 0; size_t upd_cost_cap = 0;
@@ -1248,6 +1410,8 @@ static void free_mesh(mnb_ctx* c) {
   c->ws_groups = 0;
   dfree(c->d_out_dist); c->out_dist_cap = 0; dfree(c->d_out_pred); dfree(c->d_out_dir); dfree(c->d_out_cut);
   dfree(c->d_infl_invalid); dfree(c->d_out_cost);
+  dfree(c->d_infl_vec); dfree(c->d_infl_dist); dfree(c->d_infl_src); dfree(c->d_infl_flag);
+  c->infl_labels_valid = false; c->infl_field_valid = false; c->repulsive_on = false;
   dfree(c->d_prev_risk); c->prev_risk_valid = false; dfree(c->d_upd_ids); dfree(c->d_upd_costs); c->upd_cap = 0; c->upd_cost_cap = 0;
   dfree(c->d_changed); dfree(c->d_tile_count); dfree(c->d_total);
   dfree(c->d_path_pos); dfree(c->d_path_face); dfree(c->d_bt_result); c->path_cap = 0; c->last_valid = false;
@@ -1462,6 +1626,89 @@ int32_t mnb_cancel(mnb_ctx* ctx) {
 
 }  // extern "C"
 
+
+static RepulsiveField repulsive_field_of(mnb_ctx* ctx) {
+  RepulsiveField L{};
+  L.dist = ctx->d_infl_dist; L.vec = ctx->d_infl_vec;
+  L.inscribed_radius = ctx->infl_params.inscribed_radius; L.inflation_radius = ctx->infl_params.inflation_radius;
+  L.inscribed_radius_f = (float)ctx->infl_params.inscribed_radius;
+  L.lethal_value = (float)ctx->infl_params.lethal_value; L.inscribed_value = (float)ctx->infl_params.inscribed_value;
+  return L;
+}
+
+extern "C" {
+
+int32_t mnb_inflation_vector_map(mnb_ctx* ctx, float* out_vectors) {
+  if (!ctx || !ctx->V) return MNB_E_ARG;
+  if (!ctx->infl_labels_valid) {
+    ctx->err = "mnb_inflation_vector_map needs the labels of the last mnb_inflate / mnb_inflation_update: call it before the next planner call on this context";
+    return MNB_E_STATE;
+  }
+  CK(cudaSetDevice(ctx->device));
+  const size_t V = ctx->V;
+  if (!ctx->d_infl_vec) { CK(dalloc(&ctx->d_infl_vec, 3 * V)); CK(dalloc(&ctx->d_infl_src, V)); CK(dalloc(&ctx->d_infl_flag, (size_t)2)); }
+  InflVecArgs a{};
+  a.V = ctx->V; a.pos = ctx->d_pos; a.faces = ctx->d_faces; a.cor_ptr = ctx->d_cor_ptr; a.cor_idx = ctx->d_cor_idx; a.cor_wd = ctx->d_cor_wd;
+  a.adj_ptr = ctx->d_adj_ptr; a.adj_nbr = ctx->d_adj_nbr; a.invalid = ctx->infl_had_invalid ? ctx->d_infl_invalid : nullptr; a.ws = ctx->ws;
+  a.max_distance = (float)ctx->infl_params.inflation_radius; a.vec = ctx->d_infl_vec; a.src = ctx->d_infl_src; a.flag = ctx->d_infl_flag;
+  CK(cudaMemsetAsync(ctx->d_infl_flag, 0, 2 * sizeof(unsigned int), ctx->stream));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  MNB_LAUNCH(k_infl_vec_lethal, (ctx->V + 127) / 128, 128, 0, ctx->stream, a);
+  MNB_LAUNCH(k_infl_vec_sources, (ctx->V + 127) / 128, 128, 0, ctx->stream, a);
+  CK(cudaGetLastError());
+  unsigned launches = 2;
+  // fixed point over the acyclic source relation: its depth is bounded by the number of rounds the wave took
+  const unsigned max_sweeps = (unsigned)ctx->stats.rounds + 8u;
+  unsigned int flag[2] = {1u, 0u};
+  for (unsigned it = 0; it < max_sweeps && flag[0]; ++it, ++launches) {
+    CK(cudaMemsetAsync(ctx->d_infl_flag, 0, sizeof(unsigned int), ctx->stream));
+    MNB_LAUNCH(k_infl_vec_sweep, (ctx->V + 255) / 256, 256, 0, ctx->stream, a);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(flag, ctx->d_infl_flag, sizeof(flag), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (flag[1]) { ctx->err = "inflation vector field: a vertex has more than 24 faces with two lethal vertices"; return MNB_E_NOMEM; }
+  if (flag[0]) { ctx->err = "inflation vector field did not reach its fixed point"; return MNB_E_STATE; }
+  if (out_vectors) CK(cudaMemcpyAsync(out_vectors, ctx->d_infl_vec, sizeof(float) * 3 * V, out_kind(ctx), ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const uint64_t wave_rounds = ctx->stats.rounds;
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->stats = mnb_stats{}; ctx->stats.kernel_ms = ms; ctx->stats.kernel_launches = launches; ctx->stats.settled = ctx->V; ctx->stats.rounds = wave_rounds;
+  ctx->infl_field_valid = true;
+  return MNB_OK;
+}
+
+int32_t mnb_set_repulsive_field(mnb_ctx* ctx, int32_t enable) {
+  if (!ctx) return MNB_E_ARG;
+  if (enable && !ctx->infl_field_valid) { ctx->err = "mnb_set_repulsive_field needs mnb_inflation_vector_map first"; return MNB_E_STATE; }
+  ctx->repulsive_on = enable != 0;
+  return MNB_OK;
+}
+
+int32_t mnb_inflation_vector_at(mnb_ctx* ctx, uint32_t n, const uint32_t* faces_q, const float* bary, float* out) {
+  if (!ctx || !ctx->V || !faces_q || !bary || !out || n == 0) return MNB_E_ARG;
+  if (!ctx->infl_field_valid) { ctx->err = "mnb_inflation_vector_at needs mnb_inflation_vector_map first"; return MNB_E_STATE; }
+  for (uint32_t i = 0; ctx->ptr_mode == MNB_PTR_HOST && i < n; ++i) if (faces_q[i] >= ctx->F) return MNB_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const bool dev = ctx->ptr_mode == MNB_PTR_DEVICE;
+  uint32_t* d_f = nullptr; float* d_b = nullptr; float* d_o = nullptr;
+  if (!dev) {
+    CK(dalloc(&d_f, (size_t)n)); CK(dalloc(&d_b, 3 * (size_t)n)); CK(dalloc(&d_o, 3 * (size_t)n));
+    CK(cudaMemcpyAsync(d_f, faces_q, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_b, bary, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  MNB_LAUNCH(k_inflation_vector_at, (n + 127) / 128, 128, 0, ctx->stream, repulsive_field_of(ctx), (const uint32_t*)ctx->d_faces, n,
+             dev ? faces_q : (const uint32_t*)d_f, dev ? bary : (const float*)d_b, dev ? out : d_o);
+  CK(cudaGetLastError());
+  if (!dev) CK(cudaMemcpyAsync(out, d_o, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  dfree(d_f); dfree(d_b); dfree(d_o);
+  return MNB_OK;
+}
+
+}  // extern "C"
+
 template <class KArgs>
 static cudaError_t launch_cluster(void (*kern)(const KArgs), const KArgs& args, int cs, unsigned blocks, int threads,
                                   cudaStream_t stream) {
@@ -1558,6 +1805,7 @@ int32_t mnb_cvp(mnb_ctx* ctx, uint32_t seed_face, const float seed_pos[3], int64
   const bool dev = ctx->ptr_mode == MNB_PTR_DEVICE;
   if ((rc = ensure_out(ctx, dev ? 0 : (size_t)ctx->V, true)) != MNB_OK) return rc;
   if (ctx->h_cancel) *ctx->h_cancel = 0;     // cvp:679 "reset cancel planning"
+  ctx->infl_labels_valid = false;            // the wavefront workspace is shared with the inflation wave
   CK(cudaMemcpyAsync(ctx->d_seed_faces, &seed_face, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_seed_pos, seed_pos, 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(ctx->d_next_query, 0, sizeof(unsigned int), ctx->stream));
@@ -1634,6 +1882,7 @@ int32_t mnb_cvp_batch(mnb_ctx* ctx, uint32_t n, const uint32_t* seed_faces, cons
   const bool dev = ctx->ptr_mode == MNB_PTR_DEVICE;
   if ((rc = ensure_out(ctx, dev ? 0 : (size_t)n * ctx->V, false)) != MNB_OK) return rc;
   if (ctx->h_cancel) *ctx->h_cancel = 0;
+  ctx->infl_labels_valid = false;
   CK(cudaMemcpyAsync(ctx->d_seed_faces, seed_faces, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_seed_pos, seed_pos, 3 * sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(ctx->d_next_query, 0, sizeof(unsigned int), ctx->stream));
@@ -1664,6 +1913,7 @@ int32_t mnb_dijkstra(mnb_ctx* ctx, uint32_t seed_vertex, int64_t robot_vertex, d
   const bool dev = ctx->ptr_mode == MNB_PTR_DEVICE;
   if ((rc = ensure_out(ctx, (size_t)ctx->V, true)) != MNB_OK) return rc;
   if (ctx->h_cancel) *ctx->h_cancel = 0;     // dijkstra:238
+  ctx->infl_labels_valid = false;
   CK(cudaMemsetAsync(ctx->ws.ctl, 0, sizeof(GroupCtl), ctx->stream));
   DijkstraKernelArgs a{};
   a.V = ctx->V; a.adj_ptr = ctx->d_adj_ptr; a.adj_nw = ctx->d_adj_nw; a.cost = ctx->d_cost;
@@ -1793,6 +2043,8 @@ int32_t mnb_cvp_backtrack(mnb_ctx* ctx, const float robot_pos[3], uint32_t robot
   for (int k = 0; k < 3; ++k) { a.start[k] = ctx->last_seed_pos[k]; a.goal[k] = robot_pos[k]; }
   a.start_face = ctx->last_seed_face; a.goal_face = robot_face; a.step_width = step_width; a.max_points = max_points;
   a.path_pos = ctx->d_path_pos; a.path_face = ctx->d_path_face; a.result = ctx->d_bt_result; a.cancel_flag = ctx->d_cancel;
+  a.layer = RepulsiveField{};
+  if (ctx->repulsive_on && ctx->infl_field_valid) a.layer = repulsive_field_of(ctx);
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   CK(cudaFuncSetAttribute(k_backtrack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BtShared)));
   MNB_LAUNCH(k_backtrack, 1, 32, sizeof(BtShared), ctx->stream, a);
@@ -1919,6 +2171,10 @@ static int32_t inflate_impl(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, c
   CK(cudaMemcpyAsync(ctx->d_prev_risk, a.out_cost, sizeof(float) * V, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->prev_risk_valid = true;
+  ctx->infl_labels_valid = true; ctx->infl_had_invalid = invalid != nullptr; ctx->infl_params = *params; ctx->infl_field_valid = false;
+  if (!ctx->d_infl_dist) CK(dalloc(&ctx->d_infl_dist, V));
+  CK(cudaMemcpyAsync(ctx->d_infl_dist, a.out_dist, sizeof(float) * V, cudaMemcpyDeviceToDevice, ctx->stream));   // distances_
+  CK(cudaStreamSynchronize(ctx->stream));
   return MNB_OK;
 }
 

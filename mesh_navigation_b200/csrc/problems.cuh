@@ -510,7 +510,10 @@ struct InflationProblem {
     return true;
   }
 
-  __device__ __forceinline__ bool recompute(uint32_t c, float band_end, float /*goal*/, uint32_t round, const Label& old, float& nd, float& ntau) {
+  // event-ordered replay of the faces around c; win = corner record of the LAST accepted update (-1: none), with the
+  // source distances and the candidate it was accepted with (the repulsive vector field is derived from it)
+  __device__ __forceinline__ void replay(uint32_t c, float band_end, uint32_t round, float& nd, EvTime& tc_out, int& win,
+                                         float& wu1, float& wu2) const {
     const uint32_t kb = cor_ptr[c], ke = cor_ptr[c + 1];
     EvTime Tt[MAXF]; float U1[MAXF], U2[MAXF]; uint32_t K[MAXF], TV[MAXF];
     int n = 0;
@@ -522,6 +525,7 @@ struct InflationProblem {
     const float INF = __uint_as_float(INF_BITS);
     float cur = INF;
     EvTime tc = ev_normal(INF, c);                         // pop time = heap key; +inf while not inserted
+    win = -1; wu1 = 0.0f; wu2 = 0.0f;
     // an invalid vertex is popped but never fixed (:417-422): it keeps receiving updates from every face
     const bool never_fixed = invalid && invalid[c];
     for (int i = 0; i < n; ++i) {
@@ -534,11 +538,17 @@ struct InflationProblem {
       const float4 w = __ldg(&cor_wd[k]);
       const float cand = inflation_candidate(u1, u2, w.z, w.y, w.x);   // a = |v2c|, b = |v1c|, c = |v1v2|
       if (cand < cur && backstep_ok(cand, T, Tv, round)) {                                    // :297 (non-finite candidates were mapped to +inf)
-        cur = cand;
+        cur = cand; win = (int)k; wu1 = u1; wu2 = u2;
         if (u1 <= max_distance && u2 <= max_distance) tc = CvpProblem::accept_time(c, cand, T);   // :310 -> pq.insert(c, cand)
       }
     }
-    nd = cur; ntau = tc.a1;
+    nd = cur; tc_out = tc;
+  }
+
+  __device__ __forceinline__ bool recompute(uint32_t c, float band_end, float /*goal*/, uint32_t round, const Label& old, float& nd, float& ntau) {
+    EvTime tc; int win; float wu1, wu2;
+    replay(c, band_end, round, nd, tc, win, wu1, wu2);
+    ntau = tc.a1;
     if (__float_as_uint(nd) == __float_as_uint(old.d) && ev_eq(tc, old.t)) return false;
     store_label(c, nd, tc, __float_as_uint(old.d) != INF_BITS, round);
     return true;

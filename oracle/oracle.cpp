@@ -898,7 +898,33 @@ inline bool searchNeighbourFaces(const OrcMesh& m, V3 pos, uint32_t face, float 
 }
 
 // mesh_map.cpp:1070-1108 (+ directionAtPosition :625-650)
-inline bool meshAhead(const OrcMesh& m, const float* vector_map, V3& pos, uint32_t& face, float step_size) {
+// InflationLayer::vectorAt(vertices, barycentric_coords)  inflation_layer.cpp:493-521.  lvr2's BaseVector<float> is
+// un-vendored: `vec * double` is taken as a float scale; a face vertex without a distance entry (the reference would
+// panic inside lvr2's DenseVertexMap::operator[]) yields the zero vector.  PARITY UNPINNED.
+struct RepulsiveField {
+  const float* distances;      // V, +inf = no entry
+  const float* vectors;        // 3V, zero = no entry
+  double inscribed_radius, inflation_radius, lethal_value, inscribed_value;
+};
+inline V3 inflationVectorAt(const RepulsiveField& L, const uint32_t* t, const float* bary) {
+  const float d0 = L.distances[t[0]], d1 = L.distances[t[1]], d2 = L.distances[t[2]];
+  if (!std::isfinite(d0) || !std::isfinite(d1) || !std::isfinite(d2)) return V3{0, 0, 0};
+  const float distance = d0 * bary[0] + d1 * bary[1] + d2 * bary[2];                 // util.h:179-184
+  if (distance > L.inflation_radius) return V3{0, 0, 0};
+  const float* a = &L.vectors[3 * (size_t)t[0]]; const float* b = &L.vectors[3 * (size_t)t[1]]; const float* c = &L.vectors[3 * (size_t)t[2]];
+  V3 v{a[0] * bary[0] + b[0] * bary[1] + c[0] * bary[2], a[1] * bary[0] + b[1] * bary[1] + c[1] * bary[2],
+       a[2] * bary[0] + b[2] * bary[1] + c[2] * bary[2]};
+  if (distance > L.inscribed_radius) {                                               // :505-511
+    const float alpha = (std::sqrt(distance) - L.inscribed_radius) / (L.inflation_radius - L.inscribed_radius) * M_PI;
+    const float s1 = (float)L.inscribed_value, s2 = std::cos(alpha) + 1, s3 = 2.0f;
+    return V3{v.x * s1 * s2 / s3, v.y * s1 * s2 / s3, v.z * s1 * s2 / s3};
+  }
+  const float s = distance > 0 ? (float)L.inscribed_value : (float)L.lethal_value;   // :514-520
+  return V3{v.x * s, v.y * s, v.z * s};
+}
+
+inline bool meshAhead(const OrcMesh& m, const float* vector_map, V3& pos, uint32_t& face, float step_size,
+                      const RepulsiveField* layer = nullptr) {
   float bary[3], dist;
   const uint32_t* t = &m.faces[3 * (size_t)face];
   if (projectedBarycentricCoords(pos, P(m, t[0]), P(m, t[1]), P(m, t[2]), bary, dist)) {
@@ -921,16 +947,47 @@ inline bool meshAhead(const OrcMesh& m, const float* vector_map, V3& pos, uint32
   if (!any || !(std::isfinite(vec.x) && std::isfinite(vec.y) && std::isfinite(vec.z))) return false;
   float d[3] = {vec.x, vec.y, vec.z};
   vnormalize(d);          // opt_dir.normalized()
-  vnormalize(d);          // dir += (zero layer fields); dir.normalize()
+  if (layer) {            // dir += layer->vectorAt(handels, bary_coords) for every layer (mesh_map.cpp:1097-1102)
+    const V3 lv = inflationVectorAt(*layer, t, bary);
+    d[0] += lv.x; d[1] += lv.y; d[2] += lv.z;
+  }
+  vnormalize(d);          // dir.normalize()
   pos = {pos.x + d[0] * step_size, pos.y + d[1] * step_size, pos.z + d[2] * step_size};
   return true;
 }
 }  // namespace
 
+static int32_t backtrackImpl(const OrcMesh& m, const float* vector_map, const float start[3], uint32_t start_face, const float goal[3],
+                             uint32_t goal_face, double step_width, uint32_t max_points, float* path_pos, uint32_t* path_face,
+                             uint32_t* n_points, const RepulsiveField* layer);
 extern "C" int32_t orc_cvp_backtrack(void* h, const float* vector_map, const float start[3], uint32_t start_face, const float goal[3],
                                      uint32_t goal_face, double step_width, uint32_t max_points, float* path_pos, uint32_t* path_face,
                                      uint32_t* n_points) {
+  return backtrackImpl(*(OrcMesh*)h, vector_map, start, start_face, goal, goal_face, step_width, max_points, path_pos, path_face, n_points, nullptr);
+}
+// same walk with the InflationLayer's repulsive field added in meshAhead (mesh_map.cpp:1097-1102)
+extern "C" int32_t orc_cvp_backtrack_repulsive(void* h, const float* vector_map, const float start[3], uint32_t start_face,
+                                               const float goal[3], uint32_t goal_face, double step_width, uint32_t max_points,
+                                               float* path_pos, uint32_t* path_face, uint32_t* n_points,
+                                               const float* infl_distances, const float* infl_vectors, double inscribed_radius,
+                                               double inflation_radius, double lethal_value, double inscribed_value) {
+  RepulsiveField L{infl_distances, infl_vectors, inscribed_radius, inflation_radius, lethal_value, inscribed_value};
+  return backtrackImpl(*(OrcMesh*)h, vector_map, start, start_face, goal, goal_face, step_width, max_points, path_pos, path_face, n_points, &L);
+}
+// InflationLayer::vectorAt for n (face, barycentric) samples
+extern "C" void orc_inflation_vector_at(void* h, uint32_t n, const uint32_t* faces_q, const float* bary, const float* infl_distances,
+                                        const float* infl_vectors, double inscribed_radius, double inflation_radius,
+                                        double lethal_value, double inscribed_value, float* out /*3n*/) {
   const OrcMesh& m = *(OrcMesh*)h;
+  RepulsiveField L{infl_distances, infl_vectors, inscribed_radius, inflation_radius, lethal_value, inscribed_value};
+  for (uint32_t q = 0; q < n; ++q) {
+    const V3 v = inflationVectorAt(L, &m.faces[3 * (size_t)faces_q[q]], &bary[3 * (size_t)q]);
+    out[3 * (size_t)q] = v.x; out[3 * (size_t)q + 1] = v.y; out[3 * (size_t)q + 2] = v.z;
+  }
+}
+static int32_t backtrackImpl(const OrcMesh& m, const float* vector_map, const float start[3], uint32_t start_face, const float goal[3],
+                             uint32_t goal_face, double step_width, uint32_t max_points, float* path_pos, uint32_t* path_face,
+                             uint32_t* n_points, const RepulsiveField* layer) {
   uint32_t n = 0;
   auto push = [&](V3 p, uint32_t f) { if (n < max_points) { path_pos[3 * n] = p.x; path_pos[3 * n + 1] = p.y; path_pos[3 * n + 2] = p.z; path_face[n] = f; } ++n; };
   uint32_t current_face = goal_face;                                                    // :920
@@ -942,7 +999,7 @@ extern "C" int32_t orc_cvp_backtrack(void* h, const float* vector_map, const flo
     const V3 d = sub3(current_pos, st);
     if (!((double)dot3(d, d) > step_width)) break;                                      // :925 distance2 vs step_width
     if (n + 1 >= max_points) { *n_points = n; return -1; }
-    if (!meshAhead(m, vector_map, current_pos, current_face, sw)) { *n_points = n; return 54; }   // :938-941
+    if (!meshAhead(m, vector_map, current_pos, current_face, sw, layer)) { *n_points = n; return 54; }   // :938-941
     push(current_pos, current_face);
   }
   push(st, start_face);                                                                 // :951

@@ -253,11 +253,25 @@ def _cvp_vector_map(self, vertex_normals, pred, direction, cutting_face):
     return out
 
 
-def _cvp_backtrack(self, vector_map, start, start_face, goal, goal_face, step_width=0.4, max_points=100000):
-    """cvp:920-951: walk from `goal` (robot) down the field to `start` (wave seed); returns (outcome, positions, faces)"""
+def _cvp_backtrack(self, vector_map, start, start_face, goal, goal_face, step_width=0.4, max_points=100000, repulsive=None):
+    """cvp:920-951: walk from `goal` (robot) down the field to `start` (wave seed); returns (outcome, positions, faces).
+    repulsive: optional dict(dist, vectors, inscribed_radius, inflation_radius, lethal_value, inscribed_value) -- the
+    InflationLayer field meshAhead adds (mesh_map.cpp:1097-1102, inflation_layer.cpp:493-521)"""
     vm = np.ascontiguousarray(vector_map, dtype=np.float32)
     st = np.ascontiguousarray(start, dtype=np.float32); go = np.ascontiguousarray(goal, dtype=np.float32)
     pp = np.empty((max_points, 3), np.float32); pf = np.empty(max_points, np.uint32); n = C.c_uint32(0)
+    if repulsive is not None:
+        rd = np.ascontiguousarray(repulsive["dist"], dtype=np.float32); rv = np.ascontiguousarray(repulsive["vectors"], dtype=np.float32)
+        f = lib().orc_cvp_backtrack_repulsive
+        f.restype = C.c_int32
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_double, C.c_uint32, C.c_void_p,
+                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
+        rc = f(self._h, _p(vm), _p(st), int(start_face), _p(go), int(goal_face), float(step_width), int(max_points), _p(pp),
+               _p(pf), C.byref(n), _p(rd), _p(rv), float(repulsive.get("inscribed_radius", 0.25)),
+               float(repulsive.get("inflation_radius", 0.4)), float(repulsive.get("lethal_value", 1.0)),
+               float(repulsive.get("inscribed_value", 0.99)))
+        k = min(n.value, max_points)
+        return rc, pp[:k].copy(), pf[:k].copy()
     rc = lib().orc_cvp_backtrack(self._h, _p(vm), _p(st), int(start_face), _p(go), int(goal_face), float(step_width),
                                  int(max_points), _p(pp), _p(pf), C.byref(n))
     k = min(n.value, max_points)
@@ -273,6 +287,21 @@ def _locate(self, points):
     return nv, fc, ba
 
 
+def _inflation_vector_at(self, faces_q, bary, dist, vectors, inscribed_radius=0.25, inflation_radius=0.4, lethal_value=1.0,
+                         inscribed_value=0.99):
+    """InflationLayer::vectorAt(vertices, barycentric_coords) (inflation_layer.cpp:493-521) for n samples"""
+    fq = np.ascontiguousarray(faces_q, dtype=np.uint32); ba = np.ascontiguousarray(bary, dtype=np.float32).reshape(-1, 3)
+    rd = np.ascontiguousarray(dist, dtype=np.float32); rv = np.ascontiguousarray(vectors, dtype=np.float32)
+    out = np.empty((fq.size, 3), np.float32)
+    f = lib().orc_inflation_vector_at
+    f.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double,
+                  C.c_double, C.c_void_p]
+    f(self._h, fq.size, _p(fq), _p(ba), _p(rd), _p(rv), float(inscribed_radius), float(inflation_radius), float(lethal_value),
+      float(inscribed_value), _p(out))
+    return out
+
+
+OracleMesh.inflation_vector_at = _inflation_vector_at
 OracleMesh.locate = _locate
 OracleMesh.cvp_backtrack = _cvp_backtrack
 OracleMesh.dijkstra_vector_map = _dijkstra_vector_map

@@ -136,3 +136,81 @@ def test_inflation_on_input_changed_chain(api, oracle_mod):
         gc = api.CVPMeshPlanner(mm, cost_limit=0.9).waveFrontPropagation(f, sp)
         assert (gc["dist"].view(np.uint32) == oc["dist"].view(np.uint32)).all(), f"cycle {cyc}: plan differs"
     mm.close()
+
+
+@pytest.mark.parametrize("n,terrain,discs,rad,with_invalid", [(64, True, 6, 0.3, False), (90, False, 12, 0.25, True), (40, True, 2, 0.6, False)])
+def test_inflation_vector_field(api, oracle_mod, n, terrain, discs, rad, with_invalid):
+    """InflationLayer::vector_map_ (inflation_layer.cpp:277-308): the order-dependent accumulation of the sequential loop,
+    reproduced from the final labels (ordered fold over the lethal-phase events + last accepted face)"""
+    O = oracle_mod
+    pos, faces = mesh_case(n, terrain)
+    om = O.OracleMesh(pos, faces)
+    ed = om.edge_distances()
+    lethals = disc_lethals(pos, discs, rad, seed=3)
+    invalid = None
+    if with_invalid:
+        rng = np.random.default_rng(2)
+        invalid = (rng.random(om.V) < 0.03).astype(np.uint8)
+        invalid[lethals[::3]] = 1                     # lethal AND invalid: fixed at the start, never expands
+    ref = om.inflation(ed, lethals, invalid=invalid, inflation_radius=0.6, with_vectors=True)
+    mm = api.MeshMap(pos, faces)
+    infl = api.InflationLayer(mm, inflation_radius=0.6)
+    got = infl.waveCostInflation(lethals, invalid)
+    assert (got["dist"].view(np.uint32) == ref["dist"].view(np.uint32)).all()
+    vec = infl.vectorMap()
+    assert np.abs(ref["vectors"]).sum() > 0
+    bad = np.where((vec.view(np.uint32) != ref["vectors"].view(np.uint32)).any(1))[0]
+    assert bad.size == 0, f"{bad.size} vectors differ, first {bad[:5]}: {vec[bad[:3]]} vs {ref['vectors'][bad[:3]]}"
+    # vectorAt on random (face, barycentric) samples
+    rng = np.random.default_rng(9)
+    fq = rng.integers(0, om.F, 500).astype(np.uint32)
+    b = rng.random((500, 3)).astype(np.float32); b /= b.sum(1, keepdims=True)
+    gv = infl.vectorAt(fq, b)
+    rv = om.inflation_vector_at(fq, b, ref["dist"], ref["vectors"], inflation_radius=0.6)
+    assert np.abs(rv).sum() > 0
+    assert np.allclose(gv, rv, rtol=0, atol=2e-6)
+    # the labels are gone after a plan: asking again must fail loudly, the resident field stays usable
+    mm.setCosts(np.zeros(om.V, np.float32), ed)
+    v, f, sp = centre_seed(pos, faces, (0.5, 0.5))
+    api.CVPMeshPlanner(mm).waveFrontPropagation(f, sp)
+    with pytest.raises(api.MeshNavError):
+        infl.vectorMap()
+    assert np.allclose(infl.vectorAt(fq[:10], b[:10]), rv[:10], rtol=0, atol=2e-6)
+    mm.close()
+
+
+def test_backtrack_with_repulsive_field(api, oracle_mod):
+    """MeshMap::meshAhead adds the layers' vectorAt (mesh_map.cpp:1097-1102): the walk bends away from the obstacles"""
+    O = oracle_mod
+    n = 80
+    pos, faces = mesh_case(n, True)
+    om = O.OracleMesh(pos, faces)
+    ed = om.edge_distances()
+    lethals = disc_lethals(pos, 40, 0.3, seed=12)
+    ref_i = om.inflation(ed, lethals, with_vectors=True)
+    vc = np.zeros(om.V, np.float32)              # the plan ignores the obstacles: the walk crosses the inflated zones
+    w = om.edge_weights(vc, ed, 0.0)
+    mm = api.MeshMap(pos, faces)
+    infl = api.InflationLayer(mm)
+    infl.waveCostInflation(lethals)
+    infl.vectorMap()
+    mm.setCosts(vc, w)
+    planner = api.CVPMeshPlanner(mm, cost_limit=0.95)
+    v, gf, gp = centre_seed(pos, faces, (0.15, 0.2))
+    rv, rf, rp = centre_seed(pos, faces, (0.85, 0.8))
+    plan = planner.waveFrontPropagation(gf, gp, rf)
+    assert plan["outcome"] == 0
+    vm = planner.computeVectorMap(plan["pred"], plan["direction"], plan["cutting_face"])
+    plain = planner.backtrack(rp, rf)
+    infl.setRepulsiveField(True)
+    bent = planner.backtrack(rp, rf)
+    infl.setRepulsiveField(False)
+    rep = dict(dist=ref_i["dist"], vectors=ref_i["vectors"])
+    rc0, p0, f0 = om.cvp_backtrack(vm, gp, gf, rp, rf)
+    rc1, p1, f1 = om.cvp_backtrack(vm, gp, gf, rp, rf, repulsive=rep)
+    assert plain["outcome"] == rc0 == 0 and bent["outcome"] == rc1
+    assert plain["positions"].shape == p0.shape and np.allclose(plain["positions"], p0, atol=1e-3)
+    assert bent["positions"].shape == p1.shape and np.allclose(bent["positions"], p1, atol=2e-3)
+    k = min(len(p0), len(p1))
+    assert np.abs(p0[:k] - p1[:k]).max() > 1e-3, "the repulsive field left the path unchanged"
+    mm.close()
