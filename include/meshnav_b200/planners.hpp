@@ -8,6 +8,7 @@
 // this image; the pluginlib shims that wrap these classes are sketched in INTEGRATION.md).
 // All compute happens in libmeshnav_b200.so on the GPU.  Header-only; link with -lmeshnav_b200.
 #pragma once
+#include <array>
 #include <cmath>
 #include <cstdint>
 #include <limits>
@@ -101,6 +102,16 @@ class MeshMap {
   }
   // pushes vertex_costs / edge_weights / invalid the way the planners read them (cvp:245,663-664)
   bool syncCosts() { return mnb_set_costs(ctx_, vertex_costs_.data(), edge_weights_.data(), invalid_.data()) == MNB_OK; }
+
+  // MeshMap::layerChanged (mesh_map.cpp:455-492): vertex_costs of the changed vertices from the default layer's cost map
+  // (NaN = no entry -> default_value), then updateEdgeWeights (:563-618) -- on the device only the table entries of the
+  // incident edges are patched; the host copies are refreshed from the device.
+  bool layerChanged(const std::vector<uint32_t>& changes, const std::vector<float>& layer_costs, float default_value) {
+    if (layer_costs.size() != vertex_costs_.size()) return false;
+    if (mnb_update_vertex_costs(ctx_, (uint32_t)changes.size(), changes.data(), layer_costs.data(), 1, default_value, edge_cost_factor) != MNB_OK)
+      return false;
+    return mnb_get_costs(ctx_, vertex_costs_.data(), edge_weights_.data()) == MNB_OK;
+  }
 
   // MeshMap::getNearestVertexHandle (mesh_map.cpp:1161-1174): one streamed pass over the device-resident positions
   int64_t getNearestVertexHandle(const Vector& p) const {
@@ -315,8 +326,40 @@ class InflationLayer {
                        cost_out.data()) == MNB_OK;
   }
 
+  // InflationLayer::onInputChanged (inflation_layer.cpp:97-179): full re-inflation from the input layer's lethals; `update`
+  // receives the set handed to notifyChange (:154-176).  riskiness_ / distances_ are kept as members like in the reference.
+  bool onInputChanged(const std::vector<uint32_t>& lethals, std::vector<uint32_t>& update) {
+    const uint32_t V = map_->numVertices();
+    riskiness_.assign(V, 0.0f); distances_.assign(V, 0.0f); update.assign(V, 0u);
+    const mnb_inflation_params p{config_.inscribed_radius, config_.inflation_radius, config_.lethal_value,
+                                 config_.inscribed_value, config_.cost_scaling_factor};
+    uint32_t n = 0;
+    if (mnb_inflation_update(map_->ctx(), lethals.data(), (uint32_t)lethals.size(), map_->invalid().data(), &p, distances_.data(),
+                             riskiness_.data(), update.data(), &n) != MNB_OK) return false;
+    update.resize(n);
+    return true;
+  }
+  const std::vector<float>& costs() const { return riskiness_; }      // AbstractLayer::costs(): NaN = no entry
+  float defaultValue() const { return 0; }                            // inflation_layer.h:74-77
+
+  // vector_map_ of the last wave (inflation_layer.cpp:277-308); call before the next plan on the same map
+  bool vectorMap(std::vector<Vector>& out) {
+    std::vector<float> raw(3 * (size_t)map_->numVertices());
+    if (mnb_inflation_vector_map(map_->ctx(), raw.data()) != MNB_OK) return false;
+    out.resize(map_->numVertices());
+    for (size_t v = 0; v < out.size(); ++v) out[v] = {raw[3 * v], raw[3 * v + 1], raw[3 * v + 2]};
+    return true;
+  }
+  // InflationLayer::vectorAt(vertices, barycentric_coords) (inflation_layer.cpp:493-521)
+  Vector vectorAt(uint32_t face, const std::array<float, 3>& barycentric_coords) {
+    Vector v;
+    mnb_inflation_vector_at(map_->ctx(), 1, &face, barycentric_coords.data(), &v.x);
+    return v;
+  }
+
  private:
   std::shared_ptr<MeshMap> map_;
+  std::vector<float> riskiness_, distances_;
 };
 
 }  // namespace meshnav_b200

@@ -118,6 +118,35 @@ int main() {
   size_t inflated = 0; for (uint32_t v = 0; v < V; ++v) if (std::isfinite(dist[v]) && dist[v] > 0 && dist[v] <= 0.4f) { inflated++; CHECK(risk[v] > 0 && risk[v] <= 0.99f); }
   CHECK(inflated > 20);
   for (uint32_t v : lethals) CHECK(dist[v] == 0.0f && risk[v] == 1.0f);
+
+  // ---- dynamic obstacle cycle: onInputChanged -> layerChanged ----
+  std::vector<uint32_t> update;
+  std::vector<uint32_t> moved; for (uint32_t v = 0; v < V; ++v) if (std::hypot(pos[3 * v] - 5.0f, pos[3 * v + 1] - 3.0f) < 0.3f) moved.push_back(v);
+  CHECK(infl.onInputChanged(moved, update));
+  // update = vertices with a riskiness entry now or after the previous wave: a superset of both lethal sets
+  std::vector<uint8_t> in_update(V, 0); for (uint32_t v : update) { CHECK(v < V); in_update[v] = 1; }
+  for (uint32_t v : lethals) CHECK(in_update[v]);
+  for (uint32_t v : moved) CHECK(in_update[v]);
+  for (size_t i = 1; i < update.size(); ++i) CHECK(update[i - 1] < update[i]);            // ascending like std::set
+  std::vector<Vector> field; CHECK(infl.vectorMap(field));
+  size_t with_vec = 0; for (uint32_t v = 0; v < V; ++v) if (field[v].x != 0 || field[v].y != 0 || field[v].z != 0) with_vec++;
+  CHECK(with_vec > 20);
+  map->edge_cost_factor = 1.0;
+  CHECK(map->computeEdgeWeights()); CHECK(map->syncCosts());
+  const std::vector<float> w_before = map->edgeWeights();
+  CHECK(map->layerChanged(update, infl.costs(), infl.defaultValue()));
+  size_t changed_w = 0; for (size_t e = 0; e < w_before.size(); ++e) if (w_before[e] != map->edgeWeights()[e]) changed_w++;
+  CHECK(changed_w > 20);
+  for (uint32_t v : moved) CHECK(map->vertexCosts()[v] == 1.0f);
+  for (uint32_t v : lethals) CHECK(map->vertexCosts()[v] == 0.0f);                         // no entry any more -> default value
+  {  // the patched tables plan exactly like a fresh install of the same arrays
+    auto fresh = std::make_shared<MeshMap>(pos, faces);
+    fresh->vertexCosts() = map->vertexCosts(); fresh->edgeWeights() = map->edgeWeights(); CHECK(fresh->syncCosts());
+    std::vector<float> d1(V), d2(V); std::vector<uint32_t> p1(V), p2(V);
+    CHECK(mnb_dijkstra(map->ctx(), seed_v, -1, 2.0, 0.3, d1.data(), p1.data()) == 0);
+    CHECK(mnb_dijkstra(fresh->ctx(), seed_v, -1, 2.0, 0.3, d2.data(), p2.data()) == 0);
+    CHECK(std::memcmp(d1.data(), d2.data(), sizeof(float) * V) == 0 && p1 == p2);
+  }
   orc_mesh_destroy(om);
   std::printf("cpp host mirror ok: dijkstra bit-exact, cvp max rel %.2e, %zu inflated vertices\n", maxrel, inflated);
   return 0;

@@ -54,3 +54,18 @@ def test_every_parity_test_is_in_a_group():
         words = [w for f, g in GROUPS if f == fname for w in g.split(" or ")]
         missing = [n for n in names if "large_mesh" not in n and not any(w in n for w in words)]
         assert not missing, f"{fname}: not covered by any interpreter group: {missing}"
+
+
+def test_cpp_host_mirror_on_the_cpu_interpreter(emu_lib, tmp_path, oracle_mod):
+    """tests/cpp/test_planners.cpp (the C++ mirror of the reference's plugin interface, include/meshnav_b200/planners.hpp)
+    linked against the interpreted kernels instead of libmeshnav_b200.so"""
+    link_dir = tmp_path / "lib"
+    link_dir.mkdir()
+    os.symlink(emu_lib, link_dir / "libmeshnav_b200.so")
+    exe = str(tmp_path / "test_planners")
+    orc = os.path.join(ROOT, "oracle")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_planners.cpp"),
+                           f"-L{link_dir}", "-lmeshnav_b200", f"-L{orc}", "-loracle", f"-Wl,-rpath,{link_dir}", f"-Wl,-rpath,{orc}"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=dict(os.environ, MNB_EMU_SMS="4"))
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "cpp host mirror ok" in out.stdout
