@@ -1372,7 +1372,7 @@ struct mnb_ctx {
   uint32_t* d_lethals = nullptr; uint32_t lethal_cap = 0; uint8_t* d_infl_invalid = nullptr; float* d_out_cost = nullptr;
   // repulsive vector field of the last inflation (InflationLayer::vector_map_ / distances_)
   bool infl_labels_valid = false, infl_had_invalid = false, infl_field_valid = false, repulsive_on = false;
-  mnb_inflation_params infl_params{};
+  mnb_inflation_params infl_params{}; uint64_t infl_rounds = 0;
   float* d_infl_vec = nullptr; float* d_infl_dist = nullptr; int4* d_infl_src = nullptr; unsigned int* d_infl_flag = nullptr;
   // incremental updates
   float* d_prev_risk = nullptr; bool prev_risk_valid = false;     // riskiness map of the previous inflation (NaN = no entry)
@@ -1658,7 +1658,7 @@ int32_t mnb_inflation_vector_map(mnb_ctx* ctx, float* out_vectors) {
   CK(cudaGetLastError());
   unsigned launches = 2;
   // fixed point over the acyclic source relation: its depth is bounded by the number of rounds the wave took
-  const unsigned max_sweeps = (unsigned)ctx->stats.rounds + 8u;
+  const unsigned max_sweeps = (unsigned)ctx->infl_rounds + 8u;
   unsigned int flag[2] = {1u, 0u};
   for (unsigned it = 0; it < max_sweeps && flag[0]; ++it, ++launches) {
     CK(cudaMemsetAsync(ctx->d_infl_flag, 0, sizeof(unsigned int), ctx->stream));
@@ -1672,7 +1672,7 @@ int32_t mnb_inflation_vector_map(mnb_ctx* ctx, float* out_vectors) {
   if (flag[0]) { ctx->err = "inflation vector field did not reach its fixed point"; return MNB_E_STATE; }
   if (out_vectors) CK(cudaMemcpyAsync(out_vectors, ctx->d_infl_vec, sizeof(float) * 3 * V, out_kind(ctx), ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  const uint64_t wave_rounds = ctx->stats.rounds;
+  const uint64_t wave_rounds = ctx->infl_rounds;
   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   ctx->stats = mnb_stats{}; ctx->stats.kernel_ms = ms; ctx->stats.kernel_launches = launches; ctx->stats.settled = ctx->V; ctx->stats.rounds = wave_rounds;
   ctx->infl_field_valid = true;
@@ -2171,7 +2171,7 @@ static int32_t inflate_impl(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, c
   CK(cudaMemcpyAsync(ctx->d_prev_risk, a.out_cost, sizeof(float) * V, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->prev_risk_valid = true;
-  ctx->infl_labels_valid = true; ctx->infl_had_invalid = invalid != nullptr; ctx->infl_params = *params; ctx->infl_field_valid = false;
+  ctx->infl_labels_valid = true; ctx->infl_had_invalid = invalid != nullptr; ctx->infl_params = *params; ctx->infl_field_valid = false; ctx->infl_rounds = ctx->stats.rounds;
   if (!ctx->d_infl_dist) CK(dalloc(&ctx->d_infl_dist, V));
   CK(cudaMemcpyAsync(ctx->d_infl_dist, a.out_dist, sizeof(float) * V, cudaMemcpyDeviceToDevice, ctx->stream));   // distances_
   CK(cudaStreamSynchronize(ctx->stream));
