@@ -229,6 +229,7 @@ typedef struct mnb_stats {
   uint64_t settled;         /* vertices with a finite final label */
   uint64_t kernel_launches; /* kernels launched by the last call */
   float kernel_ms;          /* CUDA-event time of the wavefront kernel(s) of the last call */
+  uint64_t skipped;         /* candidate-rounds that kept their label without a recompute (clean-candidate skip) */
 } mnb_stats;
 int32_t mnb_get_stats(mnb_ctx* ctx, mnb_stats* out);
 /* tuning knobs: band width delta (metres) and CTAs per wavefront cluster (1,2,4,8,16) */

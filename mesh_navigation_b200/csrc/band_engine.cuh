@@ -82,6 +82,7 @@ struct GroupCtl {               // one per wavefront group, global memory
   int robot_left;               // robot-face vertices not yet settled
   unsigned int query;           // batch: query index owned by the group
   unsigned long long rounds, recomputes, settled;
+  unsigned long long skipped;   // candidate-rounds that kept their label without a recompute (clean-candidate skip)
   unsigned int strict_armed;    // wavefronts that had to arm the strict back-step rule
   unsigned int watchdog;        // a wavefront hit the round watchdog (reported as non-convergence)
   unsigned long long t_work, t_flush, t_sync;   // clock cycles of thread 0 of the group: candidate loop / stage flush / barrier
@@ -279,7 +280,7 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
   const int n_sweeps = SW ? n_sweeps_arg : 0;
   bool rescanned = false;
   float band_end_prev = band_end_init;
-  unsigned long long my_recomputes = 0, my_settled = 0;
+  unsigned long long my_recomputes = 0, my_settled = 0, my_skipped = 0;
   float lo_best = -1.0f; int stagnant = 0;       // best (largest) earliest-unsettled pop time seen so far
   prob.strict = 0;
   const uint32_t j = threadIdx.x & 7;
@@ -322,6 +323,13 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
       atomicMin(&ctl->goal_ring[(r + 1) & 1], goal_b);                 // carry the cutoff into the next round
       ctl->stop_ring[(r + 1) & 1] = (stop || (cancel_flag && (r & 31) == 0 && *cancel_flag)) ? 1u : 0u;
     }
+    // Clean-candidate skip (group-uniform switch): a label is a pure function of the source labels, the band end (only
+    // through sources beyond it), the goal cutoff and -- in strict mode -- the round number.  Plans with a goal cutoff
+    // and strict rounds recompute everything; otherwise a candidate none of whose sources was re-labelled in or after the
+    // round of its own last evaluation, and whose relevant sources beyond the band end are still beyond it, keeps its
+    // label without being recomputed.
+    bool skip_ok = false;
+    if constexpr (P::CAN_SKIP) skip_ok = prob.skip_clean && !has_robot && !prob.strict;
     // Goal cutoff (cvp:754 / dijkstra:299) with a band wider than goal_dist_offset: labels computed before the cutoff
     // is known may rest on sources that turn out to lie beyond it.  Once it is known, (1) vertices beyond it never
     // settle any more -- they are recomputed under the cutoff until nothing changes -- and (2) the ones that had already
@@ -350,9 +358,18 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
     auto evaluate = [&](bool has, const uint32_t c, const Label& old, const int4& ix, const float4& w, const uint32_t mk,
                         const uint32_t v0, const bool fresh, const uint32_t slot) {
       const float d = old.d, tau = old.t.a1;
-      float nd; EvTime nt; int deg; uint32_t mk1 = MARK_FIXED, mk2 = MARK_FIXED;
-      prob.replay_sub8(c, j, has, ix, w, band_end, goal, r, mark, nd, nt, deg, mk1, mk2);
+      float nd; EvTime nt; int deg; uint32_t mk1 = MARK_FIXED, mk2 = MARK_FIXED; float excl = 0.0f;
+      prob.replay_sub8(c, j, has, ix, w, band_end, goal, r, mark, nd, nt, deg, mk1, mk2, excl);
       const bool changed = has && (__float_as_uint(nd) != __float_as_uint(d) || !ev_eq(nt, old.t));
+      if constexpr (P::CAN_SKIP) if (skip_ok) {
+        // stamps of the clean-candidate skip: c was evaluated in this round; its face neighbours have a source that was
+        // re-labelled in this round (plain stores: every writer of a round stores the same value, rounds are barrier-ordered)
+        if (has && j == 0) { __stcg(&prob.last_eval[c], r + 1u); __stcg(&prob.excl_min[c], __float_as_uint(excl)); }
+        if (changed) {
+          if (ix.x != -1 && deg <= 8) { __stcg(&prob.dirty_round[ix.x], r + 1u); if constexpr (P::TWO_SOURCES) __stcg(&prob.dirty_round[ix.y], r + 1u); }
+          if (j == 0 && deg > 8) prob.activate(c, [&](uint32_t x) { __stcg(&prob.dirty_round[x], r + 1u); });
+        }
+      }
       if (has && j == 0) {
         my_recomputes++;
         if (changed) {
@@ -435,6 +452,20 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
         }
         has = false;
       }
+      if constexpr (P::CAN_SKIP) if (skip_ok && has) {
+        const uint32_t le = __ldcg(&prob.last_eval[c]), dr = __ldcg(&prob.dirty_round[c]);
+        const float em = __uint_as_float(__ldcg(&prob.excl_min[c]));
+        if (le != 0u && dr < le && !(band_end > em)) {
+          // clean: survives with its label as it is (the 8 lanes of the group agree: same loads)
+          if (j == 0) {
+            my_lo = fminf(my_lo, tau);
+            my_skipped++;
+            if constexpr (SW) stage_push_seen(st, *ss, c, v0, prob.pack_label(c, old.d, old.t), list_n, &ctl->count[next]);
+            else stage_push(st, c, list_n, &ctl->count[next]);
+          }
+          has = false;
+        }
+      }
       evaluate(has, c, old, ix, w, mk, v0, true, 0u);
     }
     // ---- in-round sweeps: the CTA keeps relaxing the candidates it staged (survivors + newly activated) whose
@@ -490,6 +521,7 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
   }
   atomicAdd(&ctl->recomputes, my_recomputes);
   atomicAdd(&ctl->settled, my_settled);
+  if (my_skipped) atomicAdd(&ctl->skipped, my_skipped);
   if (gtid == 0) {
     ctl->rounds += r;
     if (prob.strict) ctl->strict_armed += 1;

@@ -242,6 +242,16 @@ constexpr int ELL_EMPTY = -1;
 
 struct CvpEllProblem : CvpProblem {
   static constexpr bool TWO_SOURCES = true;   // an ELL slot names the two source vertices of a face
+  // Clean-candidate skip (band_engine.cuh): a candidate's label is a pure function of its sources' labels (+ the band end
+  // through `d < band_end`); it is re-evaluated only if a source was re-labelled in or after the round of its last
+  // evaluation.  Both stamps are 1-based round numbers and only ever compared across a group barrier.
+  static constexpr bool CAN_SKIP = true;
+  uint32_t* last_eval;     // round + 1 of the last evaluation; 0 = never evaluated
+  uint32_t* dirty_round;   // round + 1 of the last re-label of a face neighbour; 0 = never
+  uint32_t* excl_min;      // float bits: smallest finite source label that lay beyond the band end at the last evaluation and
+                           // could still fire before the candidate pops (d <= its pop time); +inf: none.  The candidate is
+                           // re-evaluated once the band end passes it.
+  int skip_clean;          // runtime switch (0: every candidate is recomputed every round)
   const int4* __restrict__ ell_idx;
   const float4* __restrict__ ell_w;
   const double4* __restrict__ ell_geo;   // {p, hc, t0a, -} per slot, precomputed from ell_w (k_corner_geo)
@@ -323,13 +333,14 @@ struct CvpEllProblem : CvpProblem {
   // activation marks of the lane's two source vertices (fetched together with their labels).
   __device__ __forceinline__ void replay_sub8(uint32_t c, uint32_t j, bool has, const int4& ix, const float4& w, float band_end,
                                               float goal, uint32_t round, const uint32_t* mark, float& nd, EvTime& nt, int& deg_out,
-                                              uint32_t& mk1, uint32_t& mk2) const {
+                                              uint32_t& mk1, uint32_t& mk2, float& excl_min_out) const {
     constexpr unsigned FULL = 0xffffffffu;
     const float INF = __uint_as_float(INF_BITS);
     const int deg = __shfl_sync(FULL, ix.w, 0, 8);
     deg_out = deg;
     const bool big = has && deg > (int)ELL_W;
     bool valid = has && !big && ix.x != ELL_EMPTY;
+    float excl = INF;                                   // smallest finite source label of this lane's face beyond the band end
     EvTime T = ev_normal(INF, 0x7fffffffu);
     uint32_t Tv = 0x7fffffffu;
     double U = 0.0, X = 0.0;
@@ -343,6 +354,8 @@ struct CvpEllProblem : CvpProblem {
       const double2 g01 = __ldg(gp), g23 = __ldg(gp + 1);
       FaceGeo g; g.p = g01.x; g.hc = g01.y; g.t0a = g23.x;
       const Label a = unpack_label(v1, sa), b = unpack_label(v2, sb);
+      if (__float_as_uint(a.d) != INF_BITS && !(a.d < band_end)) excl = a.d;
+      if (__float_as_uint(b.d) != INF_BITS && !(b.d < band_end)) excl = fminf(excl, b.d);
       valid = face_time(v1, v2, a, b, band_end, goal, T, Tv);
       if (valid) {
         eval_face_geo((double)a.d, (double)b.d, (double)w.z, (double)w.y, (double)w.x, g, U, X);
@@ -416,6 +429,14 @@ struct CvpEllProblem : CvpProblem {
     }
     if (big) {   // rare: more than 8 faces -> CSR path on the group's first lane, result broadcast below
       if (j == 0) replay_serial(c, band_end, goal, round, cur, tc);
+    }
+    {
+      // a source beyond the band end matters only if its face could fire before c pops: the face time's first level is
+      // >= the source's label, so labels above c's pop time are irrelevant until c itself is re-labelled
+      float e = (excl <= tc.a1) ? excl : INF;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) e = fminf(e, __shfl_xor_sync(FULL, e, o, 8));
+      excl_min_out = big ? 0.0f : e;                    // CSR path: not tracked per source, re-evaluated every round
     }
     const unsigned anybig = __ballot_sync(FULL, big);
     if (anybig) {
@@ -623,6 +644,8 @@ struct DijkstraProblem {
 // ---------------------------------------------------------------------------
 struct DijkstraEllProblem : DijkstraProblem {
   static constexpr bool TWO_SOURCES = false;
+  static constexpr bool CAN_SKIP = false;     // one relaxation is as cheap as the bookkeeping of skipping it
+  uint32_t* last_eval = nullptr; uint32_t* dirty_round = nullptr; uint32_t* excl_min = nullptr; int skip_clean = 0;
   const uint4* __restrict__ ell_adj;
   uint32_t* ver;
 
@@ -659,7 +682,8 @@ struct DijkstraEllProblem : DijkstraProblem {
   }
   __device__ __forceinline__ void replay_sub8(uint32_t c, uint32_t j, bool has, const int4& ix, const float4&, float band_end,
                                               float goal, uint32_t /*round*/, const uint32_t* mark, float& nd, EvTime& nt, int& deg_out,
-                                              uint32_t& mk1, uint32_t& mk2) const {
+                                              uint32_t& mk1, uint32_t& mk2, float& excl_min_out) const {
+    excl_min_out = 0.0f;
     constexpr unsigned FULL = 0xffffffffu;
     const float INF = __uint_as_float(INF_BITS);
     const int deg = __shfl_sync(FULL, ix.w, 0, 8);
