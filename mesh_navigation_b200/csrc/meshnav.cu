@@ -166,7 +166,7 @@ __device__ __forceinline__ void ctl_reset(GroupCtl* ctl, unsigned int n0, float 
 #ifndef MNB_CVP_THREADS
 #define MNB_CVP_THREADS 512
 #endif
-template <int CS>
+template <int CS, bool SKIP>
 __global__ void __launch_bounds__(MNB_CVP_THREADS, MNB_CVP_MINBLOCKS) k_cvp(const CvpKernelArgs a) {
   __shared__ Stage st;
   uint32_t g, gthreads, gtid;
@@ -194,12 +194,12 @@ __global__ void __launch_bounds__(MNB_CVP_THREADS, MNB_CVP_MINBLOCKS) k_cvp(cons
 
     const uint32_t sf = a.seed_faces[q];
     const uint32_t s0 = a.faces[3 * (size_t)sf], s1 = a.faces[3 * (size_t)sf + 1], s2 = a.faces[3 * (size_t)sf + 2];
-    CvpEllProblem prob;
+    CvpEllProblemT<SKIP> prob;
     prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_w = a.cor_w; prob.cost = a.cost; prob.invalid = a.invalid;
     prob.ell_idx = a.ell_idx; prob.ell_w = a.ell_w; prob.ell_geo = a.ell_geo;
     prob.state = state; prob.minor_arr = a.ws.minor + (size_t)g * V; prob.root_arr = a.ws.root + (size_t)g * V; prob.chg = chg; prob.ver = a.ws.ver; prob.deferred_m = __uint_as_float(INF_BITS); prob.pred = nullptr; prob.dir = nullptr; prob.cut = nullptr; prob.cost_limit = a.cost_limit;
     prob.s0 = s0; prob.s1 = s1; prob.s2 = s2; prob.seed_noexpand = 0;
-    prob.last_eval = last_eval; prob.dirty_round = dirty; prob.excl_min = a.ws.excl + (size_t)g * V; prob.skip_clean = a.skip_clean;
+    prob.last_eval = last_eval; prob.dirty_round = dirty; prob.excl_min = a.ws.excl + (size_t)g * V; prob.skip_clean = SKIP ? 1 : 0;
     float sd[3];
     {
       const uint32_t sv[3] = {s0, s1, s2};
@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(MNB_CVP_THREADS, MNB_CVP_MINBLOCKS) k_cvp(cons
 #ifndef MNB_GRID_MINBLOCKS
 #define MNB_GRID_MINBLOCKS 1
 #endif
+template <bool SKIP>
 __global__ void __launch_bounds__(512, MNB_GRID_MINBLOCKS) k_cvp_grid(const CvpKernelArgs a) {
   __shared__ Stage st;
   __shared__ SweepStage sws;
@@ -273,12 +274,12 @@ __global__ void __launch_bounds__(512, MNB_GRID_MINBLOCKS) k_cvp_grid(const CvpK
   group_sync<0>(ctl->barrier);
   const uint32_t sf = a.seed_faces[0];
   const uint32_t s0 = a.faces[3 * (size_t)sf], s1 = a.faces[3 * (size_t)sf + 1], s2 = a.faces[3 * (size_t)sf + 2];
-  CvpEllProblem prob;
+  CvpEllProblemT<SKIP> prob;
   prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_w = a.cor_w; prob.cost = a.cost; prob.invalid = a.invalid;
   prob.ell_idx = a.ell_idx; prob.ell_w = a.ell_w; prob.ell_geo = a.ell_geo;
   prob.state = state; prob.minor_arr = a.ws.minor; prob.root_arr = a.ws.root; prob.chg = a.ws.chg; prob.ver = a.ws.ver; prob.deferred_m = __uint_as_float(INF_BITS); prob.pred = nullptr; prob.dir = nullptr; prob.cut = nullptr; prob.cost_limit = a.cost_limit;
   prob.s0 = s0; prob.s1 = s1; prob.s2 = s2; prob.seed_noexpand = 0;
-  prob.last_eval = a.ws.last_eval; prob.dirty_round = a.ws.dirty; prob.excl_min = a.ws.excl; prob.skip_clean = a.skip_clean;
+  prob.last_eval = a.ws.last_eval; prob.dirty_round = a.ws.dirty; prob.excl_min = a.ws.excl; prob.skip_clean = SKIP ? 1 : 0;
   float sd[3];
   {
     const uint32_t sv[3] = {s0, s1, s2};
@@ -1750,11 +1751,11 @@ static int32_t launch_cvp(mnb_ctx* ctx, const CvpKernelArgs& a, int cs, unsigned
   const unsigned blocks = groups * cs;
   const int threads = MNB_CVP_THREADS;
   switch (cs) {
-    case 1: e = launch_cluster(k_cvp<1>, a, 1, blocks, threads, ctx->stream); break;
-    case 2: e = launch_cluster(k_cvp<2>, a, 2, blocks, threads, ctx->stream); break;
-    case 4: e = launch_cluster(k_cvp<4>, a, 4, blocks, threads, ctx->stream); break;
-    case 8: e = launch_cluster(k_cvp<8>, a, 8, blocks, threads, ctx->stream); break;
-    default: e = launch_cluster(k_cvp<16>, a, 16, blocks, threads, ctx->stream); break;
+    case 1: e = a.skip_clean ? launch_cluster(k_cvp<1, true>, a, 1, blocks, threads, ctx->stream) : launch_cluster(k_cvp<1, false>, a, 1, blocks, threads, ctx->stream); break;
+    case 2: e = launch_cluster(k_cvp<2, false>, a, 2, blocks, threads, ctx->stream); break;     // (the skip variant is built for the two
+    case 4: e = launch_cluster(k_cvp<4, false>, a, 4, blocks, threads, ctx->stream); break;     //  default configurations only: per-CTA batches
+    case 8: e = launch_cluster(k_cvp<8, false>, a, 8, blocks, threads, ctx->stream); break;     //  and the whole-grid single plan)
+    default: e = launch_cluster(k_cvp<16, false>, a, 16, blocks, threads, ctx->stream); break;
   }
   if (e != cudaSuccess) { ctx->err = std::string("cvp launch: ") + cudaGetErrorString(e); return MNB_E_CUDA; }
   return MNB_OK;
@@ -1834,11 +1835,12 @@ int32_t mnb_cvp(mnb_ctx* ctx, uint32_t seed_face, const float seed_pos[3], int64
     a.delta = ctx->grid_delta;
     if (ctx->grid_blocks_per_sm == 0) {
       int nb = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_cvp_grid, ctx->threads, 0));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_cvp_grid<false>, ctx->threads, 0));
       ctx->grid_blocks_per_sm = nb > MNB_GRID_MINBLOCKS ? MNB_GRID_MINBLOCKS : nb;
       if (nb <= 0) { ctx->err = "k_cvp_grid cannot be resident"; return MNB_E_CUDA; }
     }
-    CK(launch_cooperative(k_cvp_grid, a, (unsigned)(ctx->sm_count * ctx->grid_blocks_per_sm), ctx->threads, ctx->stream));
+    if (a.skip_clean) CK(launch_cooperative(k_cvp_grid<true>, a, (unsigned)(ctx->sm_count * ctx->grid_blocks_per_sm), ctx->threads, ctx->stream));
+    else CK(launch_cooperative(k_cvp_grid<false>, a, (unsigned)(ctx->sm_count * ctx->grid_blocks_per_sm), ctx->threads, ctx->stream));
   } else {
     if ((rc = launch_cvp(ctx, a, ctx->cluster, 1)) != MNB_OK) return rc;
   }
@@ -1881,7 +1883,7 @@ int32_t mnb_cvp_batch(mnb_ctx* ctx, uint32_t n, const uint32_t* seed_faces, cons
   CK(cudaSetDevice(ctx->device));
   const int cs = ctx->batch_cluster;
   int per_sm = 1;
-  if (cs == 1) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cvp<1>, MNB_CVP_THREADS, 0)); if (per_sm < 1) per_sm = 1; if (per_sm > 2) per_sm = 2; }
+  if (cs == 1) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cvp<1, false>, MNB_CVP_THREADS, 0)); if (per_sm < 1) per_sm = 1; if (per_sm > 2) per_sm = 2; }
   unsigned groups = (unsigned)(ctx->sm_count * per_sm / cs);
   if (groups > n) groups = n;
   if (groups == 0) groups = 1;

@@ -240,12 +240,13 @@ struct CvpProblem {
 constexpr uint32_t ELL_W = 8;
 constexpr int ELL_EMPTY = -1;
 
-struct CvpEllProblem : CvpProblem {
+template <bool SKIP>
+struct CvpEllProblemT : CvpProblem {
   static constexpr bool TWO_SOURCES = true;   // an ELL slot names the two source vertices of a face
   // Clean-candidate skip (band_engine.cuh): a candidate's label is a pure function of its sources' labels (+ the band end
   // through `d < band_end`); it is re-evaluated only if a source was re-labelled in or after the round of its last
   // evaluation.  Both stamps are 1-based round numbers and only ever compared across a group barrier.
-  static constexpr bool CAN_SKIP = true;
+  static constexpr bool CAN_SKIP = SKIP;      // compile-time: the default instantiation carries none of the bookkeeping
   uint32_t* last_eval;     // round + 1 of the last evaluation; 0 = never evaluated
   uint32_t* dirty_round;   // round + 1 of the last re-label of a face neighbour; 0 = never
   uint32_t* excl_min;      // float bits: smallest finite source label that lay beyond the band end at the last evaluation and
@@ -354,8 +355,10 @@ struct CvpEllProblem : CvpProblem {
       const double2 g01 = __ldg(gp), g23 = __ldg(gp + 1);
       FaceGeo g; g.p = g01.x; g.hc = g01.y; g.t0a = g23.x;
       const Label a = unpack_label(v1, sa), b = unpack_label(v2, sb);
-      if (__float_as_uint(a.d) != INF_BITS && !(a.d < band_end)) excl = a.d;
-      if (__float_as_uint(b.d) != INF_BITS && !(b.d < band_end)) excl = fminf(excl, b.d);
+      if constexpr (SKIP) {
+        if (__float_as_uint(a.d) != INF_BITS && !(a.d < band_end)) excl = a.d;
+        if (__float_as_uint(b.d) != INF_BITS && !(b.d < band_end)) excl = fminf(excl, b.d);
+      }
       valid = face_time(v1, v2, a, b, band_end, goal, T, Tv);
       if (valid) {
         eval_face_geo((double)a.d, (double)b.d, (double)w.z, (double)w.y, (double)w.x, g, U, X);
@@ -430,7 +433,8 @@ struct CvpEllProblem : CvpProblem {
     if (big) {   // rare: more than 8 faces -> CSR path on the group's first lane, result broadcast below
       if (j == 0) replay_serial(c, band_end, goal, round, cur, tc);
     }
-    {
+    if constexpr (!SKIP) excl_min_out = 0.0f;
+    else {
       // a source beyond the band end matters only if its face could fire before c pops: the face time's first level is
       // >= the source's label, so labels above c's pop time are irrelevant until c itself is re-labelled
       float e = (excl <= tc.a1) ? excl : INF;
@@ -447,6 +451,9 @@ struct CvpEllProblem : CvpProblem {
     nd = cur; nt = tc;
   }
 };
+
+using CvpEllProblem = CvpEllProblemT<false>;
+using CvpEllSkipProblem = CvpEllProblemT<true>;
 
 // ---------------------------------------------------------------------------
 // Inflation: multi-source FMM from the lethal set (InflationLayer::waveCostInflation,
