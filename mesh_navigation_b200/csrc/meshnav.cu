@@ -600,6 +600,68 @@ __device__ __forceinline__ void walk(const LayerKernelArgs& a, uint32_t v, float
   }
 }
 
+// Variant with the `seen` hash set and the traversal stack in SHARED memory (slot-major, one bank per thread: conflict
+// free) instead of thread-local memory: 1536 resident threads x ~0.9 KB of randomly probed local memory does not fit the
+// L1, so every probe of the local-memory version is an L2 trip.  Same traversal, same visiting order, same sums.
+// Opt-in (MNB_LAYERS_SMEM=1) until it has been timed on a B200.
+constexpr int LS_THREADS = 128, LS_STACK = 48;
+template <int WHICH>
+__device__ __forceinline__ void walk_smem(const LayerKernelArgs& a, uint32_t v, float radius, float& zmin, float& zmax,
+                                          float& rsum, int& rcnt, float& value, int& num, uint32_t* __restrict__ ht,
+                                          uint32_t* __restrict__ stack) {
+  // ht[slot * LS_THREADS], stack[i * LS_THREADS]: both already offset by threadIdx.x
+#pragma unroll 8
+  for (int i = 0; i < NB_HASH; ++i) ht[i * LS_THREADS] = 0xffffffffu;
+  const float zmin0 = zmin, zmax0 = zmax, rsum0 = rsum, value0 = value; const int rcnt0 = rcnt, num0 = num;
+  int ns = 0, sp = 0;
+  ht[((v * 2654435761u) >> 25) * LS_THREADS] = v; ns = 1; stack[(sp++) * LS_THREADS] = v;
+  const float px = a.pos[3 * (size_t)v], py = a.pos[3 * (size_t)v + 1], pz = a.pos[3 * (size_t)v + 2];
+  const float nvx = a.vn[3 * (size_t)v], nvy = a.vn[3 * (size_t)v + 1], nvz = a.vn[3 * (size_t)v + 2];
+  const float rx = px + nvx, ry = py + nvy, rz = pz + nvz;
+  bool overflow = false;
+  while (sp > 0 && !overflow) {
+    const uint32_t u = stack[(--sp) * LS_THREADS];
+    for (uint32_t k = a.adj_ptr[u]; k < a.adj_ptr[u + 1]; ++k) {
+      const uint32_t n = a.adj_nbr[k];
+      uint32_t h = (n * 2654435761u) >> 25;
+      bool was = false;
+      for (;;) {
+        const uint32_t e = ht[h * LS_THREADS];
+        if (e == n) { was = true; break; }
+        if (e == 0xffffffffu) break;
+        h = (h + 1u) & (uint32_t)(NB_HASH - 1);
+      }
+      if (was) continue;
+      if (ns >= NB_HSEEN) { overflow = true; break; }
+      ht[h * LS_THREADS] = n; ++ns;
+      const float qx = a.pos[3 * (size_t)n], qy = a.pos[3 * (size_t)n + 1], qz = a.pos[3 * (size_t)n + 2];
+      const float dx = qx - px, dy = qy - py, dz = qz - pz;
+      if (sqrtf(dx * dx + dy * dy + dz * dz) < radius) {
+        if (WHICH & 1) { zmin = fminf(zmin, qz); zmax = fmaxf(zmax, qz); }
+        if (WHICH & 6) {
+          const float nnx = a.vn[3 * (size_t)n], nny = a.vn[3 * (size_t)n + 1], nnz = a.vn[3 * (size_t)n + 2];
+          if (WHICH & 2) {
+            float dot = nvx * nnx + nvy * nny + nvz * nnz;
+            dot = fminf(1.0f, fmaxf(-1.0f, dot));
+            rsum = rsum + acosf(dot); rcnt++;
+          }
+          if (WHICH & 4) {
+            const float cx = (qx + nnx) - rx, cy = (qy + nny) - ry, cz = (qz + nnz) - rz;
+            value += sqrtf(cx * cx + cy * cy + cz * cz); num++;
+          }
+        }
+        if (sp >= LS_STACK) { overflow = true; break; }
+        stack[(sp++) * LS_THREADS] = n;
+      }
+    }
+  }
+  if (overflow) {
+    zmin = zmin0; zmax = zmax0; rsum = rsum0; value = value0; rcnt = rcnt0; num = num0;
+    walk_linear<WHICH>(a, v, radius, zmin, zmax, rsum, rcnt, value, num);
+  }
+}
+
+template <bool SMEM>
 __global__ void __launch_bounds__(128) k_layers(const LayerKernelArgs a) {
   const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= a.V) return;
@@ -607,7 +669,18 @@ __global__ void __launch_bounds__(128) k_layers(const LayerKernelArgs a) {
   const float pz = a.pos[3 * (size_t)v + 2];
   float zmin = pz, zmax = pz, rsum = 0.0f, value = 0.0f; int rcnt = 0, num = 0;
   const float r_hd = (float)P.height_diff_radius, r_ro = (float)P.roughness_radius, r_ri = (float)P.ridge_radius;
-  if (r_hd == r_ro && r_ro == r_ri) {
+  if constexpr (SMEM) {
+    MNB_DYNAMIC_SMEM(ls_raw);
+    uint32_t* ht = reinterpret_cast<uint32_t*>(ls_raw) + threadIdx.x;
+    uint32_t* stack = ht + NB_HASH * LS_THREADS;
+    if (r_hd == r_ro && r_ro == r_ri) {
+      walk_smem<7>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+    } else {
+      walk_smem<1>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+      walk_smem<2>(a, v, r_ro, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+      walk_smem<4>(a, v, r_ri, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+    }
+  } else if (r_hd == r_ro && r_ro == r_ri) {
     walk<7>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num);
   } else {
     walk<1>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num);
@@ -1387,6 +1460,7 @@ struct mnb_ctx {
   // tuning
   float delta = 0.3f; int cluster = -1 /* -1: whole-grid cooperative kernel for single plans */; int batch_cluster = 1; int threads = 512;
   int grid_blocks_per_sm = 0;
+  int layers_smem = 0;         // k_layers with the seen-set / stack in shared memory (MNB_LAYERS_SMEM=1, mnb_debug_set_layers_smem)
   int skip_clean = 0;          // clean-candidate skip of the CVP kernels (band_engine.cuh): bit-identical on the kernel interpreter,
                                // not yet timed on a B200 -> opt-in (MNB_SKIP_CLEAN=1 / mnb_debug_set_skip_clean)
   int sweeps = -1;             // in-round sweeps of the whole-grid single-plan kernel; -1 = derived from the band width
@@ -1452,6 +1526,7 @@ int32_t mnb_create(int32_t device, mnb_ctx** out_ctx) {
   if (cudaSetDevice(device) != cudaSuccess) return MNB_E_CUDA;
   mnb_ctx* c = new mnb_ctx();
   c->device = device; c->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("MNB_LAYERS_SMEM")) c->layers_smem = atoi(e) != 0;                                   // experiment knob
   if (const char* e = getenv("MNB_SKIP_CLEAN")) c->skip_clean = atoi(e) != 0;                                     // experiment knob
   if (const char* e = getenv("MNB_SWEEPS")) { const int k = atoi(e); if (k >= -1 && k <= 64) c->sweeps = k; }   // experiment knob
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MNB_E_CUDA; }
@@ -1993,7 +2068,13 @@ int32_t mnb_compute_layers(mnb_ctx* ctx, const mnb_layer_params* params, const f
   a.lethal_mask = (dev && out_lethal_mask) ? out_lethal_mask : ctx->d_layer_mask;
   a.overflow = ctx->d_overflow;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  MNB_LAUNCH(k_layers, (ctx->V + 127) / 128, 128, 0, ctx->stream, a);
+  if (ctx->layers_smem) {
+    const size_t smem = sizeof(uint32_t) * (size_t)(NB_HASH + LS_STACK) * LS_THREADS;       // 88 KB: two CTAs per SM
+    CK(cudaFuncSetAttribute(k_layers<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MNB_LAUNCH(k_layers<true>, (ctx->V + LS_THREADS - 1) / LS_THREADS, LS_THREADS, smem, ctx->stream, a);
+  } else {
+    MNB_LAUNCH(k_layers<false>, (ctx->V + 127) / 128, 128, 0, ctx->stream, a);
+  }
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   if (!dev) {
@@ -2114,6 +2195,7 @@ int32_t mnb_locate(mnb_ctx* ctx, uint32_t n, const float* points, uint32_t* out_
 // experiment knob (not part of the public header): in-round sweeps of the whole-grid single-plan kernel
 int32_t mnb_debug_set_sweeps(mnb_ctx* ctx, int32_t k) { if (!ctx || k < -1 || k > 64) return MNB_E_ARG; ctx->sweeps = k; return MNB_OK; }
 
+int32_t mnb_debug_set_layers_smem(mnb_ctx* ctx, int32_t on) { if (!ctx) return MNB_E_ARG; ctx->layers_smem = on != 0; return MNB_OK; }
 int32_t mnb_debug_set_skip_clean(mnb_ctx* ctx, int32_t on) { if (!ctx) return MNB_E_ARG; ctx->skip_clean = on != 0; return MNB_OK; }
 
 // debugging aid (not part of the public header): raw labels {d, a1, a2, a3|flag} of wavefront group 0

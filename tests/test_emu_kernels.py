@@ -24,7 +24,7 @@ GROUPS = [
     (PARITY, "inflation or layers or config3"),
     (PARITY, "irregular or disconnected or vector_maps or backtrack or make_plan or locate"),
     (PARITY, "cancel"),
-    ("test_gpu_updates.py", "layer_changed or max_combination or on_input_changed or vector_field or repulsive or clean_candidate"),
+    ("test_gpu_updates.py", "layer_changed or max_combination or on_input_changed or vector_field or repulsive or clean_candidate or shared_memory_variant"),
 ]
 
 

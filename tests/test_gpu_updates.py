@@ -256,3 +256,26 @@ def test_clean_candidate_skip_is_exact(api, oracle_mod, n, factor):
     refc = om.cvp(w, vc, f, sp, robot_face=rf)
     assert cut["skipped"] == 0 and (cut["dist"].view(np.uint32) == refc["dist"].view(np.uint32)).all()
     mm.close()
+
+
+def test_layers_shared_memory_variant_is_identical(api, oracle_mod):
+    """opt-in k_layers<true> (seen-set and stack of the neighbourhood walk in shared memory): same traversal order, so every
+    output is bit-identical to the default kernel, including on an irregular mesh whose hub overflows into the fallback"""
+    import ctypes as C
+    from tests.util import delaunay_mesh
+    for pos, faces in (mesh_case(70, True), delaunay_mesh(1500, seed=5)):
+        mm = api.MeshMap(pos, faces)
+        mm.L.mnb_debug_set_layers_smem.argtypes = [C.c_void_p, C.c_int32]
+        P = api._lib.LayerParams.defaults()
+        base = mm.computeLayers(P)
+        mm.L.mnb_debug_set_layers_smem(mm._ctx, 1)
+        got = mm.computeLayers(P)
+        for k in list(api._lib.LAYER_NAMES) + ["combined"]:
+            assert (got[k].view(np.uint32) == base[k].view(np.uint32)).all(), k
+        assert (got["lethal_mask"] == base["lethal_mask"]).all()
+        P2 = api._lib.LayerParams.defaults(); P2.roughness_radius = 0.2; P2.ridge_radius = 0.45      # three separate walks
+        mm.L.mnb_debug_set_layers_smem(mm._ctx, 0); b2 = mm.computeLayers(P2)
+        mm.L.mnb_debug_set_layers_smem(mm._ctx, 1); g2 = mm.computeLayers(P2)
+        for k in list(api._lib.LAYER_NAMES) + ["combined"]:
+            assert (g2[k].view(np.uint32) == b2[k].view(np.uint32)).all(), k
+        mm.close()
