@@ -337,10 +337,21 @@ static inline void run_cta(unsigned bx, unsigned nblocks, unsigned nthreads, voi
     for (int k = 0; k < 6; ++k) *--sp = nullptr;               // rbp rbx r12 r13 r14 r15
     f.sp = sp;
   }
+  // MNB_EMU_SHUFFLE=<seed>: the warps of a CTA are visited in a pseudo-random order that changes on every scheduler pass
+  // and a warp is preempted after a random number of lane activations: exposes code that silently depends on "warp 0 runs
+  // first" or on a warp running from barrier to barrier undisturbed (a missing __syncthreads shows up as a parity failure)
+  static const char* shuffle_env = getenv("MNB_EMU_SHUFFLE");
+  uint64_t rng = shuffle_env ? (0x9E3779B97F4A7C15ull * (uint64_t)(atoll(shuffle_env) + 1) + bx) : 0;
+  auto next_rand = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+  int order[MAX_THREADS / 32];
+  for (int w = 0; w < nwarps; ++w) order[w] = w;
   int remaining = (int)nthreads;
   while (remaining > 0) {
     bool progress = false;
-    for (int w = 0; w < nwarps; ++w) {
+    if (rng) for (int w = nwarps - 1; w > 0; --w) { const int k = (int)(next_rand() % (uint64_t)(w + 1)); std::swap(order[w], order[k]); }
+    for (int wi = 0; wi < nwarps; ++wi) {
+      const int w = order[wi];
+      int budget = rng ? 1 + (int)(next_rand() % 3) : 1 << 30;       // passes over the warp before it is preempted
       bool ran;
       do {
         ran = false;
@@ -356,7 +367,7 @@ static inline void run_cta(unsigned bx, unsigned nblocks, unsigned nthreads, voi
           ran = true; progress = true;
           if (f.state == F_DONE) remaining--;
         }
-      } while (ran);
+      } while (ran && --budget > 0);
     }
     if (!progress) {
       fprintf(stderr, "[mnb-emu] deadlock in block %u: %d threads left, barrier %u/%d arrived\n", bx, remaining, c.bar_arrived, c.alive);

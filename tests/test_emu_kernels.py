@@ -26,6 +26,12 @@ GROUPS = [
     (PARITY, "cancel"),
     ("test_gpu_updates.py", "layer_changed or max_combination or on_input_changed or vector_field or repulsive or clean_candidate or shared_memory_variant"),
 ]
+# the same tests under a randomised warp schedule (MNB_EMU_SHUFFLE, see tests/emu/cuda_runtime.h): warps are visited in a
+# different order on every scheduler pass and preempted at collectives, which turns a missing barrier into a failure
+SHUFFLED = [
+    ("test_gpu_updates.py", "layer_changed or on_input_changed or vector_field or clean_candidate", "1"),
+    (PARITY, "cvp_full_field or dijkstra_bit_exact or inflation_wave or backtrack or locate", "2"),
+]
 
 
 @pytest.fixture(scope="module")
@@ -43,6 +49,16 @@ def test_gpu_parity_suite_on_the_cpu_interpreter(emu_lib, fname, expr):
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, f"interpreted kernels disagree with the oracle:\n{tail}"
     assert " passed" in r.stdout and "failed" not in r.stdout, tail
+
+
+@pytest.mark.parametrize("fname,expr,seed", SHUFFLED)
+def test_gpu_suite_under_a_randomised_warp_schedule(emu_lib, fname, expr, seed):
+    env = dict(os.environ, MNB_EMU_SMS="4", MNB_EMU_SHUFFLE=seed)
+    r = subprocess.run([sys.executable, RUNNER, os.path.join(ROOT, "tests", fname), "-m", "gpu", "-x", "-q",
+                        "-p", "no:cacheprovider", "-k", f"({expr}) and not large_mesh"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0 and " passed" in r.stdout, f"schedule-dependent result (seed {seed}):\n{tail}"
 
 
 def test_every_parity_test_is_in_a_group():
