@@ -47,10 +47,25 @@ def run_case(name):
         nv, fc, ba = m.locate(q)
         return dict(vector_map=vm, outcome=np.int32(rc), path_pos=pp, path_face=pf, loc_vertex=nv, loc_face=fc, loc_bary=ba,
                     dijkstra_vector_map=m.dijkstra_vector_map(m.dijkstra(w, vc, v)["pred"]))
+    if name.startswith("dynamic"):
+        # f3/f4 rows: two obstacle configurations in a row -- repulsive field, update set, incremental cost / weight update
+        le0 = disc_lethals(pos, 3, 0.25, seed=5); le1 = disc_lethals(pos, 3, 0.25, seed=6)
+        inv = (rng.random(m.V) < 0.02).astype(np.uint8)
+        i0 = m.inflation(ed, le0, invalid=inv, with_vectors=True)
+        i1 = m.inflation(ed, le1, invalid=inv, with_vectors=True)
+        upd = O.inflation_update_set(i1["cost"], i0["cost"])
+        final = vc.copy()
+        O.max_combination_update([vc, i1["cost"]], [0.0, 0.0], [None, None], upd, final, None)
+        vc2 = vc.copy(); O.layer_changed(final, 0.0, upd, vc2)
+        w2 = w.copy(); m.update_edge_weights(vc2, ed, 1.0, upd, w2)
+        fq = np.arange(0, m.F, 7, dtype=np.uint32); b = np.tile(np.float32([0.5, 0.3, 0.2]), (fq.size, 1))
+        at = m.inflation_vector_at(fq, b, i1["dist"], i1["vectors"])
+        return dict(vectors0=i0["vectors"], vectors1=i1["vectors"], update_set=upd, final=final, vertex_costs=vc2, edge_weights=w2,
+                    vector_at=at)
     raise KeyError(name)
 
 
 if __name__ == "__main__":
-    for n in ["cvp_planar30", "cvp_terrain30", "dijkstra_terrain30", "inflation_terrain30", "path_terrain30"]:
+    for n in ["cvp_planar30", "cvp_terrain30", "dijkstra_terrain30", "inflation_terrain30", "path_terrain30", "dynamic_terrain30"]:
         np.savez_compressed(os.path.join(HERE, n + ".npz"), **run_case(n))
         print("wrote", n)

@@ -119,7 +119,8 @@ def test_goal_cutoff_and_no_path(oracle_mod):
     assert m.cvp(ed, vc, f, sp, robot_face=rf)["outcome"] == 0
 
 
-@pytest.mark.parametrize("name", ["cvp_planar30", "cvp_terrain30", "dijkstra_terrain30", "inflation_terrain30", "path_terrain30"])
+@pytest.mark.parametrize("name", ["cvp_planar30", "cvp_terrain30", "dijkstra_terrain30", "inflation_terrain30", "path_terrain30",
+                                  "dynamic_terrain30"])
 def test_committed_fixtures(oracle_mod, name):
     """Fixtures under tests/golden were generated by tests/golden/make_fixtures.py from this oracle
     (the reference cannot run here); they guard the oracle against silent changes."""
@@ -170,3 +171,78 @@ def test_next_rows_sanity(oracle_mod):
     nv, fc, ba = m.locate(np.stack([q, pos[77], q + np.float32([100, 0, 0])]))
     assert fc[0] == f and np.allclose(ba[0], b, atol=1e-4) and nv[1] == 77 and fc[2] == -1
     assert nv[0] in faces[f]
+
+
+def test_incremental_update_restatements(oracle_mod):
+    """f3 restatements on hand-checkable inputs: MeshMap::layerChanged + updateEdgeWeights (mesh_map.cpp:455-492, 563-618),
+    MaxCombinationLayer::onInputChanged (combination_layer.cpp:87-147), the update set of InflationLayer::onInputChanged
+    (inflation_layer.cpp:154-164).  Unpinned by the reference (it has no test for them): derived values."""
+    O = oracle_mod
+    pos = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], np.float32)         # unit square, two triangles
+    faces = np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+    m = O.OracleMesh(pos, faces)
+    edges = m.edges.tolist()
+    e = {tuple(x): i for i, x in enumerate(edges)}
+    assert sorted(e) == [(0, 1), (0, 2), (0, 3), (1, 2), (2, 3)]
+    ed = m.edge_distances()
+    assert ed[e[(0, 2)]] == np.float32(np.sqrt(np.float32(2.0)))
+    vc = np.float32([0.0, 0.5, 0.25, 1.0])
+    w = m.edge_weights(vc, ed, 2.0)
+    # computeEdgeWeights: w = d + f * (d * (c1 + c2) / 2)
+    assert w[e[(0, 1)]] == np.float32(1.0 + 2.0 * (1.0 * 0.5 / 2.0))
+    assert w[e[(2, 3)]] == np.float32(1.0 + 2.0 * (1.0 * 1.25 / 2.0))
+    # layerChanged: vertex 1 gets a new cost, vertex 3 loses its entry (-> default)
+    layer = np.float32([np.nan, 0.75, np.nan, np.nan])
+    vc2 = vc.copy(); O.layer_changed(layer, 0.125, np.uint32([1, 3]), vc2)
+    assert vc2.tolist() == [0.0, 0.75, 0.25, 0.125]
+    w2 = w.copy(); m.update_edge_weights(vc2, ed, 2.0, np.uint32([1, 3]), w2)
+    assert w2[e[(0, 1)]] == np.float32(1.0 + 2.0 * (0.75 / 2.0)) and w2[e[(1, 2)]] == np.float32(1.0 + 2.0 * (1.0 / 2.0))
+    assert w2[e[(0, 3)]] == np.float32(1.0 + 2.0 * (0.125 / 2.0)) and w2[e[(2, 3)]] == np.float32(1.0 + 2.0 * (0.375 / 2.0))
+    assert w2[e[(0, 2)]] == w[e[(0, 2)]]                                                # not incident to a changed vertex
+    assert (w2.view(np.uint32) == m.edge_weights(vc2, ed, 2.0).view(np.uint32)).all()  # == full recompute
+    # +inf endpoint -> +inf weight (:598); a zero factor returns before touching anything (:568-572), unlike computeEdgeWeights
+    vc3 = vc2.copy(); vc3[1] = np.inf
+    w3 = w2.copy(); m.update_edge_weights(vc3, ed, 2.0, np.uint32([1]), w3)
+    assert np.isinf(w3[e[(0, 1)]]) and np.isinf(w3[e[(1, 2)]]) and np.isfinite(w3[e[(0, 2)]])
+    w4 = w2.copy(); m.update_edge_weights(vc3, ed, 0.0, np.uint32([1]), w4)
+    assert (w4 == w2).all() and np.isinf(m.edge_weights(vc3, ed, 0.0)[e[(0, 1)]])
+    # MaxCombination: max over layers of (value or default), starting from 0; lethal = any
+    a = np.float32([0.2, -1.0, np.nan, 0.4]); b = np.float32([np.nan, np.nan, np.nan, 0.9])
+    costs = np.float32([9, 9, 9, 9]); leth = np.uint8([5, 5, 5, 5])
+    O.max_combination_update([a, b], [0.0, 0.3], [np.uint8([0, 0, 1, 0]), None], np.uint32([0, 1, 2]), costs, leth)
+    assert costs.tolist() == [np.float32(0.3), np.float32(0.3), np.float32(0.3), 9.0] and leth.tolist() == [0, 0, 1, 5]
+    O.max_combination_update([a, b], [0.0, 0.3], [None, None], np.uint32([3]), costs, leth)
+    assert costs[3] == np.float32(0.9) and leth[3] == 0
+    # update set: keys(new) U keys(old)
+    new = np.float32([np.nan, 1.0, np.nan, 0.5]); old = np.float32([0.1, np.nan, np.nan, 0.2])
+    assert O.inflation_update_set(new, old).tolist() == [0, 1, 3] and O.inflation_update_set(new).tolist() == [1, 3]
+
+
+def test_repulsive_field_restatement(oracle_mod):
+    """f4 restatement (inflation_layer.cpp:277-308, 493-521) on the reference test's triangle: v0, v1 lethal, v2 free.
+    The face is visited from both lethal vertices through both of their edges: 4 accumulations of the same direction, each
+    followed by a normalisation -> every vertex ends with dir = normalize((p2-p1) + (p2-p0))."""
+    O = oracle_mod
+    m = triangle(O)
+    ed = m.edge_distances()
+    r = m.inflation(ed, np.uint32([0, 1]), inflation_radius=1.5, inscribed_radius=0.7, with_vectors=True)
+    # Sethian update with both sources at 0 and the literal sin-theta (not sin^2) of inflation_layer.cpp:195:
+    # a = |v1v2| = sqrt(0.5), b = 0.5, cos = sin = sqrt(0.5): f2 = 0.25, f1 = 0, f0 = -0.25 * 0.5 * sqrt(0.5) -> t = sqrt(-f0 * f2) / f2
+    t = np.sqrt(0.25 * 0.5 * np.sqrt(0.5) * 0.25) / 0.25
+    assert abs(float(r["dist"][2]) - t) < 1e-6 and abs(t - 0.5946035575) < 1e-9
+    d = np.float32([-0.5, 1.0, 0.0]); d = d / np.sqrt((d * d).sum(dtype=np.float32))
+    for v in range(3):
+        assert np.allclose(r["vectors"][v], d, atol=1e-6), v
+    # vectorAt at the three vertices (barycentric unit vectors): lethal -> lethal_value, 0 < d <= inscribed -> inscribed_value
+    at = m.inflation_vector_at(np.uint32([0, 0, 0]), np.eye(3, dtype=np.float32), r["dist"], r["vectors"], 0.7, 1.5, 1.0, 0.9)
+    assert np.allclose(at[0], d * 1.0, atol=1e-6) and np.allclose(at[2], d * 0.9, atol=1e-6)
+    # between the radii: inscribed_value * (cos(alpha) + 1) / 2 with alpha = (sqrt(d) - r_in) / (r_infl - r_in) * pi  (sqrt as written, :508)
+    at2 = m.inflation_vector_at(np.uint32([0]), np.float32([[0, 0, 1]]), r["dist"], r["vectors"], 0.25, 1.5, 1.0, 0.9)
+    alpha = np.float32((np.sqrt(r["dist"][2]) - 0.25) / (1.5 - 0.25) * np.pi)
+    assert np.allclose(at2[0], d * np.float32(0.9) * (np.cos(alpha) + 1) / 2, atol=1e-6)
+    # beyond the inflation radius / a vertex without an entry: zero
+    far = m.inflation_vector_at(np.uint32([0]), np.float32([[0, 0, 1]]), r["dist"], r["vectors"], 0.1, 0.3, 1.0, 0.9)
+    assert (far == 0).all()
+    rn = m.inflation(ed, np.uint32([0]), inflation_radius=0.1, with_vectors=True)     # v2 is never reached
+    assert np.isinf(rn["dist"][2])
+    assert (m.inflation_vector_at(np.uint32([0]), np.float32([[0.3, 0.3, 0.4]]), rn["dist"], rn["vectors"]) == 0).all()
