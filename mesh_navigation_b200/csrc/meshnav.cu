@@ -778,7 +778,7 @@ __global__ void k_vector_map(const float* __restrict__ pos, const float* __restr
 struct InflVecArgs {
   uint32_t V;
   const float* pos; const uint32_t* faces;
-  const uint32_t* cor_ptr; const int4* cor_idx; const float4* cor_wd;
+  const uint32_t* cor_ptr; const int4* cor_idx; const float4* cor_wd; const uint4* cor_eid;
   const uint32_t* adj_ptr; const uint32_t* adj_nbr;
   const uint8_t* invalid;
   WaveWorkspace ws;
@@ -858,7 +858,7 @@ __global__ void __launch_bounds__(128) k_infl_vec_sources(const InflVecArgs a) {
   const float d = __uint_as_float(a.ws.state[c].x);
   if (d != 0.0f && __float_as_uint(d) != INF_BITS) {
     InflationProblem prob;
-    prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_wd = a.cor_wd; prob.invalid = a.invalid;
+    prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_wd = a.cor_wd; prob.cor_eid = a.cor_eid; prob.invalid = a.invalid;
     prob.state = a.ws.state; prob.minor_arr = a.ws.minor; prob.root_arr = a.ws.root; prob.chg = a.ws.chg;
     prob.deferred_m = __uint_as_float(INF_BITS); prob.strict = 0; prob.max_distance = a.max_distance;
     float nd, wu1, wu2; EvTime tc; int win;
@@ -1171,7 +1171,7 @@ __global__ void k_containing_face(const float* __restrict__ pos, const uint32_t*
 // ============================================================================
 struct InflateKernelArgs {
   uint32_t V;
-  const uint32_t* cor_ptr; const int4* cor_idx; const float4* cor_wd;
+  const uint32_t* cor_ptr; const int4* cor_idx; const float4* cor_wd; const uint4* cor_eid;
   const uint8_t* invalid;
   WaveWorkspace ws;
   const uint32_t* lethals; uint32_t n_lethals;
@@ -1199,7 +1199,7 @@ __global__ void __launch_bounds__(512, 1) k_inflate(const InflateKernelArgs a) {
   if (gtid == 0) ctl_reset(ctl, 0, 0.0f);
   group_sync<0>(ctl->barrier);
   InflationProblem prob;
-  prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_wd = a.cor_wd; prob.invalid = a.invalid;
+  prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_wd = a.cor_wd; prob.cor_eid = a.cor_eid; prob.invalid = a.invalid;
   prob.state = state; prob.minor_arr = a.ws.minor; prob.root_arr = a.ws.root; prob.chg = a.ws.chg; prob.deferred_m = __uint_as_float(INF_BITS); prob.max_distance = a.max_distance;
   for (uint32_t i = gtid; i < a.n_lethals; i += gthreads) {
     const uint32_t v = a.lethals[i];
@@ -1612,7 +1612,7 @@ int32_t mnb_set_mesh(mnb_ctx* ctx, uint32_t V, uint32_t F, const float* pos, con
   {
     std::vector<int4> idx(NC); std::vector<uint4> eid(NC);
     for (size_t k = 0; k < NC; ++k) {
-      idx[k] = make_int4((int)T.cor_v1[k], (int)T.cor_v2[k], (int)T.cor_face[k], 0);
+      idx[k] = make_int4((int)T.cor_v1[k], (int)T.cor_v2[k], (int)T.cor_face[k], (int)T.cor_side[k]);   // .w: edge-side bits (topology.hpp)
       eid[k] = make_uint4(T.cor_ec[k], T.cor_eb[k], T.cor_ea[k], 0);
     }
     CK(cudaMemcpyAsync(ctx->d_cor_idx, idx.data(), sizeof(int4) * NC, cudaMemcpyHostToDevice, ctx->stream));
@@ -1635,6 +1635,7 @@ int32_t mnb_set_mesh(mnb_ctx* ctx, uint32_t V, uint32_t F, const float* pos, con
   // the host copies of the big per-corner arrays are no longer needed
   std::vector<uint32_t>().swap(T.cor_v1); std::vector<uint32_t>().swap(T.cor_v2); std::vector<uint32_t>().swap(T.cor_face);
   std::vector<uint32_t>().swap(T.cor_ec); std::vector<uint32_t>().swap(T.cor_eb); std::vector<uint32_t>().swap(T.cor_ea);
+  std::vector<uint8_t>().swap(T.cor_side);
   std::vector<uint32_t>().swap(T.vadj_nbr); std::vector<uint32_t>().swap(T.vadj_eid); std::vector<uint32_t>().swap(T.face_edges);
   CK(dalloc(&ctx->d_face_normals, 3 * (size_t)F)); CK(dalloc(&ctx->d_vertex_normals, 3 * (size_t)V)); CK(dalloc(&ctx->d_border, (size_t)V));
   CK(cudaMemcpyAsync(ctx->d_border, T.border.data(), (size_t)V, cudaMemcpyHostToDevice, ctx->stream));
@@ -1733,7 +1734,7 @@ int32_t mnb_inflation_vector_map(mnb_ctx* ctx, float* out_vectors) {
   if (!ctx->d_infl_vec) { CK(dalloc(&ctx->d_infl_vec, 3 * V)); CK(dalloc(&ctx->d_infl_src, V)); CK(dalloc(&ctx->d_infl_flag, (size_t)2)); }
   InflVecArgs a{};
   a.V = ctx->V; a.pos = ctx->d_pos; a.faces = ctx->d_faces; a.cor_ptr = ctx->d_cor_ptr; a.cor_idx = ctx->d_cor_idx; a.cor_wd = ctx->d_cor_wd;
-  a.adj_ptr = ctx->d_adj_ptr; a.adj_nbr = ctx->d_adj_nbr; a.invalid = ctx->infl_had_invalid ? ctx->d_infl_invalid : nullptr; a.ws = ctx->ws;
+  a.cor_eid = ctx->d_cor_eid; a.adj_ptr = ctx->d_adj_ptr; a.adj_nbr = ctx->d_adj_nbr; a.invalid = ctx->infl_had_invalid ? ctx->d_infl_invalid : nullptr; a.ws = ctx->ws;
   a.max_distance = (float)ctx->infl_params.inflation_radius; a.vec = ctx->d_infl_vec; a.src = ctx->d_infl_src; a.flag = ctx->d_infl_flag;
   CK(cudaMemsetAsync(ctx->d_infl_flag, 0, 2 * sizeof(unsigned int), ctx->stream));
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -2226,7 +2227,7 @@ static int32_t inflate_impl(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, c
   }
   CK(cudaMemsetAsync(ctx->ws.ctl, 0, sizeof(GroupCtl), ctx->stream));
   InflateKernelArgs a{};
-  a.V = ctx->V; a.cor_ptr = ctx->d_cor_ptr; a.cor_idx = ctx->d_cor_idx; a.cor_wd = ctx->d_cor_wd;
+  a.V = ctx->V; a.cor_ptr = ctx->d_cor_ptr; a.cor_idx = ctx->d_cor_idx; a.cor_wd = ctx->d_cor_wd; a.cor_eid = ctx->d_cor_eid;
   a.invalid = invalid ? ctx->d_infl_invalid : nullptr; a.ws = ctx->ws; a.lethals = ctx->d_lethals; a.n_lethals = n;
   a.max_distance = (float)params->inflation_radius;      // double -> `const float&` parameter (inflation_layer.cpp:240,450)
   a.params.inscribed_radius = params->inscribed_radius; a.params.inflation_radius = params->inflation_radius;

@@ -470,6 +470,7 @@ struct InflationProblem {
   const uint32_t* __restrict__ cor_ptr;
   const int4* __restrict__ cor_idx;
   const float4* __restrict__ cor_wd;
+  const uint4* __restrict__ cor_eid;    // {edge(v1,v2), edge(v1,c), edge(v2,c), -} per corner record
   const uint8_t* __restrict__ invalid;  // may be null
   uint4* state;
   uint32_t* minor_arr;
@@ -540,12 +541,65 @@ struct InflationProblem {
 
   // event-ordered replay of the faces around c; win = corner record of the LAST accepted update (-1: none), with the
   // source distances and the candidate it was accepted with (the repulsive vector field is derived from it)
+  // Faces that fire at the same pop (same popping vertex p = Tv; the two faces on either side of the edge (p, c) always
+  // do) are visited in the order of the reference's neighbour loop (inflation_layer.cpp:423-427): p's edges in ascending
+  // id, for each edge the lower-id face first; a face is reached through the first of its two edges at p.  The order
+  // decides which of two exactly equal candidates is "accepted" (strict <, :297) -- i.e. the repulsive vector -- and the
+  // heap key when only one of the faces has both sources inside the radius (:310).
+  __device__ __forceinline__ uint32_t visit_key(uint32_t k, uint32_t p) const {
+    const int4 ix = __ldg(&cor_idx[k]);
+    const uint4 e = __ldg(&cor_eid[k]);
+    const uint32_t k_ec = (e.x << 1) | ((uint32_t)ix.w & 1u);                       // edge(v1,v2) is at p either way
+    const uint32_t k_pc = (uint32_t)ix.x == p ? ((e.y << 1) | (((uint32_t)ix.w >> 1) & 1u))    // p == v1: edge(v1,c)
+                                              : ((e.z << 1) | (((uint32_t)ix.w >> 2) & 1u));   // p == v2: edge(v2,c)
+    return k_ec < k_pc ? k_ec : k_pc;
+  }
+  // true if entry (T1, k1) precedes (T2, k2) in the reference's call order
+  __device__ __forceinline__ bool fires_before(const EvTime& T1, uint32_t k1, uint32_t p1, const EvTime& T2, uint32_t k2, uint32_t p2) const {
+    if (!ev_eq(T1, T2)) return ev_less(T1, T2);
+    if (p1 != p2) return k1 < k2;                            // (cannot happen: equal pop times name the same vertex)
+    return visit_key(k1, p1) < visit_key(k2, p2);
+  }
+
+  // vertices with more than MAXF incident faces: repeated selection of the next face in call order by rescanning the
+  // corner list (O(deg^2), rare) -- same rule as the buffered loop below
+  __device__ __noinline__ void replay_big(uint32_t c, float band_end, uint32_t round, float& nd, EvTime& tc_out, int& win,
+                                          float& wu1, float& wu2) const {
+    const uint32_t kb = cor_ptr[c], ke = cor_ptr[c + 1];
+    const float INF = __uint_as_float(INF_BITS);
+    float cur = INF;
+    EvTime tc = ev_normal(INF, c);
+    win = -1; wu1 = 0.0f; wu2 = 0.0f;
+    const bool never_fixed = invalid && invalid[c];
+    EvTime lastT = ev_normal(0.0f, 0); uint32_t lastK = 0, lastTv = 0; bool have_last = false;
+    for (;;) {
+      EvTime bT = lastT; float bu1 = 0, bu2 = 0; uint32_t bk = 0, bTv = 0; bool found = false;
+      for (uint32_t k = kb; k < ke; ++k) {
+        EvTime T; float u1, u2; uint32_t Tv;
+        if (!corner_time(k, band_end, T, Tv, u1, u2)) continue;
+        if (have_last && (k == lastK || !fires_before(lastT, lastK, lastTv, T, k, Tv))) continue;
+        if (!found || fires_before(T, k, Tv, bT, bk, bTv)) { bT = T; bk = k; bTv = Tv; bu1 = u1; bu2 = u2; found = true; }
+      }
+      if (!found) break;
+      if (!never_fixed && !ev_less(bT, tc)) break;
+      const float4 w = __ldg(&cor_wd[bk]);
+      const float cand = inflation_candidate(bu1, bu2, w.z, w.y, w.x);
+      if (cand < cur && backstep_ok(cand, bT, bTv, round)) {
+        cur = cand; win = (int)bk; wu1 = bu1; wu2 = bu2;
+        if (bu1 <= max_distance && bu2 <= max_distance) tc = CvpProblem::accept_time(c, cand, bT);
+      }
+      lastT = bT; lastK = bk; lastTv = bTv; have_last = true;
+    }
+    nd = cur; tc_out = tc;
+  }
+
   __device__ __forceinline__ void replay(uint32_t c, float band_end, uint32_t round, float& nd, EvTime& tc_out, int& win,
                                          float& wu1, float& wu2) const {
     const uint32_t kb = cor_ptr[c], ke = cor_ptr[c + 1];
+    if (ke - kb > (uint32_t)MAXF) { replay_big(c, band_end, round, nd, tc_out, win, wu1, wu2); return; }
     EvTime Tt[MAXF]; float U1[MAXF], U2[MAXF]; uint32_t K[MAXF], TV[MAXF];
     int n = 0;
-    for (uint32_t k = kb; k < ke && n < MAXF; ++k) {   // vertices with more than MAXF usable faces: surplus ignored (mnb_set_mesh reports the max degree)
+    for (uint32_t k = kb; k < ke && n < MAXF; ++k) {
       EvTime T; float u1, u2; uint32_t Tv;
       if (!corner_time(k, band_end, T, Tv, u1, u2)) continue;
       Tt[n] = T; U1[n] = u1; U2[n] = u2; K[n] = k; TV[n] = Tv; ++n;
@@ -559,7 +613,7 @@ struct InflationProblem {
     for (int i = 0; i < n; ++i) {
       int b = i;
       for (int j = i + 1; j < n; ++j)
-        if (ev_less(Tt[j], Tt[b]) || (ev_eq(Tt[j], Tt[b]) && K[j] < K[b])) b = j;
+        if (fires_before(Tt[j], K[j], TV[j], Tt[b], K[b], TV[b])) b = j;
       const EvTime T = Tt[b]; const float u1 = U1[b], u2 = U2[b]; const uint32_t k = K[b], Tv = TV[b];
       Tt[b] = Tt[i]; U1[b] = U1[i]; U2[b] = U2[i]; K[b] = K[i]; TV[b] = TV[i];
       if (!never_fixed && !ev_less(T, tc)) break;          // c was popped (and fixed) before this face fires

@@ -30,6 +30,8 @@ struct HostTopology {
   std::vector<uint32_t> face_edges;  // 3F: edge(v0,v1), edge(v1,v2), edge(v2,v0)
   std::vector<uint32_t> vadj_ptr, vadj_nbr, vadj_eid;
   std::vector<uint32_t> vcor_ptr, cor_v1, cor_v2, cor_face, cor_ec, cor_eb, cor_ea;
+  std::vector<uint8_t> cor_side;     // per corner record, bit i = this face is NOT the lowest-id face of edge i (0: ec, 1: eb, 2: ea),
+                                     // i.e. the second face pmp lists for the halfedge pair (inflation_layer.cpp:427)
   std::vector<uint8_t> border;       // 1 = vertex lies on an edge with a single face
 
   static inline uint64_t ekey(uint32_t a, uint32_t b) {
@@ -74,12 +76,14 @@ struct HostTopology {
     };
     face_edges.resize(3 * (size_t)F);
     std::vector<uint8_t> edge_face_cnt(E, 0);
+    std::vector<uint32_t> edge_first_face(E, 0xffffffffu);
     for (uint32_t f = 0; f < F; ++f) {
       const uint32_t* v = faces + 3 * (size_t)f;
       for (int k = 0; k < 3; ++k) {
         const uint32_t e = find_edge(v[k], v[(k + 1) % 3]);
         face_edges[3 * (size_t)f + k] = e;
         if (edge_face_cnt[e] < 255) edge_face_cnt[e]++;
+        if (edge_first_face[e] == 0xffffffffu) edge_first_face[e] = f;
       }
     }
     border.assign(V, 0);
@@ -103,7 +107,7 @@ struct HostTopology {
     for (uint32_t v = 0; v < V; ++v) vcor_ptr[v + 1] += vcor_ptr[v];
     const size_t NC = vcor_ptr[V];
     cor_v1.resize(NC); cor_v2.resize(NC); cor_face.resize(NC);
-    cor_ec.resize(NC); cor_eb.resize(NC); cor_ea.resize(NC);
+    cor_ec.resize(NC); cor_eb.resize(NC); cor_ea.resize(NC); cor_side.resize(NC);
     {
       std::vector<uint32_t> cur(vcor_ptr.begin(), vcor_ptr.end() - 1);
       for (uint32_t f = 0; f < F; ++f) {
@@ -117,6 +121,8 @@ struct HostTopology {
           cor_ec[slot] = fe[(k + 1) % 3];  // edge(v1,v2)
           cor_eb[slot] = fe[k];            // edge(v3,v1)
           cor_ea[slot] = fe[(k + 2) % 3];  // edge(v2,v3)
+          cor_side[slot] = (uint8_t)((edge_first_face[cor_ec[slot]] != f ? 1 : 0) | (edge_first_face[cor_eb[slot]] != f ? 2 : 0) |
+                                     (edge_first_face[cor_ea[slot]] != f ? 4 : 0));
         }
       }
     }

@@ -279,3 +279,29 @@ def test_layers_shared_memory_variant_is_identical(api, oracle_mod):
         for k in list(api._lib.LAYER_NAMES) + ["combined"]:
             assert (g2[k].view(np.uint32) == b2[k].view(np.uint32)).all(), k
         mm.close()
+
+
+def test_inflation_high_degree_vertex(api, oracle_mod):
+    """a non-lethal hub with 24 incident faces, all of them usable (every ring vertex labelled): the wave must consider
+    all of them, not just the first 12 of the corner list"""
+    from tests.util import delaunay_mesh
+    pos, faces = delaunay_mesh(3000, seed=11)
+    om = oracle_mod.OracleMesh(pos, faces)
+    hub = om.V - 1
+    assert np.bincount(faces.reshape(-1))[hub] >= 24
+    ed = om.edge_distances()
+    mm = api.MeshMap(pos, faces)
+    c = pos[hub, :2]
+    for k, ang in enumerate(np.linspace(0.3, 6.0, 7)):
+        # lethal patch just outside the hub's ring (radius 0.22), from different sides: the winning face of the hub changes
+        centre = c + 0.42 * np.array([np.cos(ang), np.sin(ang)])
+        le = np.where(np.linalg.norm(pos[:, :2] - centre, axis=1) < 0.17)[0].astype(np.uint32)
+        assert le.size > 0 and hub not in le
+        ref = om.inflation(ed, le, inflation_radius=1.2, with_vectors=True)
+        infl = api.InflationLayer(mm, inflation_radius=1.2)
+        got = infl.waveCostInflation(le)
+        assert np.isfinite(ref["dist"][hub])
+        assert (got["dist"].view(np.uint32) == ref["dist"].view(np.uint32)).all(), (k, got["dist"][hub], ref["dist"][hub])
+        vec = infl.vectorMap()
+        assert (vec.view(np.uint32) == ref["vectors"].view(np.uint32)).all(), k
+    mm.close()
