@@ -1,0 +1,276 @@
+// Fused geometric cost layers + MaxCombination + lethal masks, face / vertex normals.
+// (part of libmeshnav_b200.so: included by meshnav.cu, which holds the C ABI and all host code)
+#pragma once
+#include "launch.cuh"
+#include "../../include/meshnav_b200.h"
+#include "band_engine.cuh"
+
+using namespace mnb;
+
+// ============================================================================
+// Fused geometric cost layers (mesh_layers: HeightDiff, Roughness, Steepness, Ridge, Clearance cost
+// mapping, Border) + MaxCombinationLayer + lethal masks: ONE pass over the radius neighbourhood per
+// vertex instead of the reference's three independent visitLocalVertexNeighborhood runs with
+// std::set bookkeeping (ridge_layer.cpp:166-175, height_diff_layer.cpp:108, roughness_layer.cpp:143).
+// Definitions of the lvr2 pieces: see oracle/oracle.cpp (orc_layers).
+// ============================================================================
+__global__ void k_face_normals(const float* __restrict__ pos, const uint32_t* __restrict__ faces, uint32_t F,
+                               float* __restrict__ fn) {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const float* p0 = pos + 3 * (size_t)faces[3 * (size_t)f];
+  const float* p1 = pos + 3 * (size_t)faces[3 * (size_t)f + 1];
+  const float* p2 = pos + 3 * (size_t)faces[3 * (size_t)f + 2];
+  const float ax = p1[0] - p0[0], ay = p1[1] - p0[1], az = p1[2] - p0[2];
+  const float bx = p2[0] - p0[0], by = p2[1] - p0[1], bz = p2[2] - p0[2];
+  float nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+  const float l = sqrtf(nx * nx + ny * ny + nz * nz);
+  if (l > 0) { nx /= l; ny /= l; nz /= l; }
+  fn[3 * (size_t)f] = nx; fn[3 * (size_t)f + 1] = ny; fn[3 * (size_t)f + 2] = nz;
+}
+
+__global__ void k_vertex_normals(const uint32_t* __restrict__ cor_ptr, const int4* __restrict__ cor_idx,
+                                 const float* __restrict__ fn, uint32_t V, float* __restrict__ vn) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  float nx = 0, ny = 0, nz = 0;
+  for (uint32_t k = cor_ptr[v]; k < cor_ptr[v + 1]; ++k) {
+    const int f = cor_idx[k].z;
+    nx = nx + fn[3 * (size_t)f]; ny = ny + fn[3 * (size_t)f + 1]; nz = nz + fn[3 * (size_t)f + 2];
+  }
+  const float l = sqrtf(nx * nx + ny * ny + nz * nz);
+  if (l > 0) { nx /= l; ny /= l; nz /= l; }
+  vn[3 * (size_t)v] = nx; vn[3 * (size_t)v + 1] = ny; vn[3 * (size_t)v + 2] = nz;
+}
+
+struct LayerKernelArgs {
+  uint32_t V;
+  const float* pos; const float* vn;
+  const uint32_t* adj_ptr; const uint32_t* adj_nbr;
+  const uint8_t* border;
+  const float* clearance;      // may be null
+  mnb_layer_params P;
+  float* costs;                // 6 x V
+  float* combined; uint8_t* lethal_mask;
+  unsigned int* overflow;      // neighbourhood larger than the per-thread scratch
+};
+
+constexpr int NB_SEEN = 320, NB_STACK = 160;
+
+// (fallback for neighbourhoods that overflow the hashed set below: linear `seen` list, any size up to NB_SEEN)
+// traversal shared by the three radius layers; WHICH selects the accumulators that are active (bit0 height
+// diff, bit1 roughness, bit2 ridge) so that layers with equal radii share one walk
+template <int WHICH>
+__device__ __noinline__ void walk_linear(const LayerKernelArgs& a, uint32_t v, float radius, float& zmin, float& zmax,
+                                     float& rsum, int& rcnt, float& value, int& num) {
+  uint32_t seen[NB_SEEN]; uint32_t stack[NB_STACK];
+  int ns = 0, sp = 0;
+  seen[ns++] = v; stack[sp++] = v;
+  const float px = a.pos[3 * (size_t)v], py = a.pos[3 * (size_t)v + 1], pz = a.pos[3 * (size_t)v + 2];
+  const float nvx = a.vn[3 * (size_t)v], nvy = a.vn[3 * (size_t)v + 1], nvz = a.vn[3 * (size_t)v + 2];
+  const float rx = px + nvx, ry = py + nvy, rz = pz + nvz;
+  while (sp > 0) {
+    const uint32_t u = stack[--sp];
+    for (uint32_t k = a.adj_ptr[u]; k < a.adj_ptr[u + 1]; ++k) {
+      const uint32_t n = a.adj_nbr[k];
+      bool was = false;
+      for (int s = 0; s < ns; ++s) if (seen[s] == n) { was = true; break; }
+      if (was) continue;
+      if (ns >= NB_SEEN) { atomicAdd(a.overflow, 1u); return; }
+      seen[ns++] = n;
+      const float qx = a.pos[3 * (size_t)n], qy = a.pos[3 * (size_t)n + 1], qz = a.pos[3 * (size_t)n + 2];
+      const float dx = qx - px, dy = qy - py, dz = qz - pz;
+      if (sqrtf(dx * dx + dy * dy + dz * dz) < radius) {
+        if (WHICH & 1) { zmin = fminf(zmin, qz); zmax = fmaxf(zmax, qz); }
+        if (WHICH & 6) {
+          const float nnx = a.vn[3 * (size_t)n], nny = a.vn[3 * (size_t)n + 1], nnz = a.vn[3 * (size_t)n + 2];
+          if (WHICH & 2) {
+            float dot = nvx * nnx + nvy * nny + nvz * nnz;
+            dot = fminf(1.0f, fmaxf(-1.0f, dot));
+            rsum = rsum + acosf(dot); rcnt++;
+          }
+          if (WHICH & 4) {
+            const float cx = (qx + nnx) - rx, cy = (qy + nny) - ry, cz = (qz + nnz) - rz;
+            value += sqrtf(cx * cx + cy * cy + cz * cz); num++;
+          }
+        }
+        if (sp >= NB_STACK) { atomicAdd(a.overflow, 1u); return; }
+        stack[sp++] = n;
+      }
+    }
+  }
+}
+
+
+// Same traversal, same visiting order (so the float sums are bit-identical to the oracle's), but the `seen` set is a
+// 128-entry open-addressing hash in local memory instead of a linear list: ~2 probes per membership test instead of
+// ~24 compares.  Neighbourhoods with more than NB_HSEEN seen vertices fall back to walk_linear.
+constexpr int NB_HASH = 128, NB_HSEEN = 96;
+template <int WHICH>
+__device__ __forceinline__ void walk(const LayerKernelArgs& a, uint32_t v, float radius, float& zmin, float& zmax,
+                                     float& rsum, int& rcnt, float& value, int& num) {
+  uint32_t ht[NB_HASH]; uint32_t stack[NB_HSEEN];
+#pragma unroll 8
+  for (int i = 0; i < NB_HASH; ++i) ht[i] = 0xffffffffu;
+  const float zmin0 = zmin, zmax0 = zmax, rsum0 = rsum, value0 = value; const int rcnt0 = rcnt, num0 = num;
+  int ns = 0, sp = 0;
+  ht[(v * 2654435761u) >> 25] = v; ns = 1; stack[sp++] = v;
+  const float px = a.pos[3 * (size_t)v], py = a.pos[3 * (size_t)v + 1], pz = a.pos[3 * (size_t)v + 2];
+  const float nvx = a.vn[3 * (size_t)v], nvy = a.vn[3 * (size_t)v + 1], nvz = a.vn[3 * (size_t)v + 2];
+  const float rx = px + nvx, ry = py + nvy, rz = pz + nvz;
+  bool overflow = false;
+  while (sp > 0 && !overflow) {
+    const uint32_t u = stack[--sp];
+    for (uint32_t k = a.adj_ptr[u]; k < a.adj_ptr[u + 1]; ++k) {
+      const uint32_t n = a.adj_nbr[k];
+      uint32_t h = (n * 2654435761u) >> 25;
+      bool was = false;
+      for (;;) {
+        const uint32_t e = ht[h];
+        if (e == n) { was = true; break; }
+        if (e == 0xffffffffu) break;
+        h = (h + 1u) & (uint32_t)(NB_HASH - 1);
+      }
+      if (was) continue;
+      if (ns >= NB_HSEEN) { overflow = true; break; }
+      ht[h] = n; ++ns;
+      const float qx = a.pos[3 * (size_t)n], qy = a.pos[3 * (size_t)n + 1], qz = a.pos[3 * (size_t)n + 2];
+      const float dx = qx - px, dy = qy - py, dz = qz - pz;
+      if (sqrtf(dx * dx + dy * dy + dz * dz) < radius) {
+        if (WHICH & 1) { zmin = fminf(zmin, qz); zmax = fmaxf(zmax, qz); }
+        if (WHICH & 6) {
+          const float nnx = a.vn[3 * (size_t)n], nny = a.vn[3 * (size_t)n + 1], nnz = a.vn[3 * (size_t)n + 2];
+          if (WHICH & 2) {
+            float dot = nvx * nnx + nvy * nny + nvz * nnz;
+            dot = fminf(1.0f, fmaxf(-1.0f, dot));
+            rsum = rsum + acosf(dot); rcnt++;
+          }
+          if (WHICH & 4) {
+            const float cx = (qx + nnx) - rx, cy = (qy + nny) - ry, cz = (qz + nnz) - rz;
+            value += sqrtf(cx * cx + cy * cy + cz * cz); num++;
+          }
+        }
+        stack[sp++] = n;            // sp <= ns <= NB_HSEEN
+      }
+    }
+  }
+  if (overflow) {
+    zmin = zmin0; zmax = zmax0; rsum = rsum0; value = value0; rcnt = rcnt0; num = num0;
+    walk_linear<WHICH>(a, v, radius, zmin, zmax, rsum, rcnt, value, num);
+  }
+}
+
+// Variant with the `seen` hash set and the traversal stack in SHARED memory (slot-major, one bank per thread: conflict
+// free) instead of thread-local memory: 1536 resident threads x ~0.9 KB of randomly probed local memory does not fit the
+// L1, so every probe of the local-memory version is an L2 trip.  Same traversal, same visiting order, same sums.
+// Opt-in (MNB_LAYERS_SMEM=1) until it has been timed on a B200.
+constexpr int LS_THREADS = 128, LS_STACK = 48;
+template <int WHICH>
+__device__ __forceinline__ void walk_smem(const LayerKernelArgs& a, uint32_t v, float radius, float& zmin, float& zmax,
+                                          float& rsum, int& rcnt, float& value, int& num, uint32_t* __restrict__ ht,
+                                          uint32_t* __restrict__ stack) {
+  // ht[slot * LS_THREADS], stack[i * LS_THREADS]: both already offset by threadIdx.x
+#pragma unroll 8
+  for (int i = 0; i < NB_HASH; ++i) ht[i * LS_THREADS] = 0xffffffffu;
+  const float zmin0 = zmin, zmax0 = zmax, rsum0 = rsum, value0 = value; const int rcnt0 = rcnt, num0 = num;
+  int ns = 0, sp = 0;
+  ht[((v * 2654435761u) >> 25) * LS_THREADS] = v; ns = 1; stack[(sp++) * LS_THREADS] = v;
+  const float px = a.pos[3 * (size_t)v], py = a.pos[3 * (size_t)v + 1], pz = a.pos[3 * (size_t)v + 2];
+  const float nvx = a.vn[3 * (size_t)v], nvy = a.vn[3 * (size_t)v + 1], nvz = a.vn[3 * (size_t)v + 2];
+  const float rx = px + nvx, ry = py + nvy, rz = pz + nvz;
+  bool overflow = false;
+  while (sp > 0 && !overflow) {
+    const uint32_t u = stack[(--sp) * LS_THREADS];
+    for (uint32_t k = a.adj_ptr[u]; k < a.adj_ptr[u + 1]; ++k) {
+      const uint32_t n = a.adj_nbr[k];
+      uint32_t h = (n * 2654435761u) >> 25;
+      bool was = false;
+      for (;;) {
+        const uint32_t e = ht[h * LS_THREADS];
+        if (e == n) { was = true; break; }
+        if (e == 0xffffffffu) break;
+        h = (h + 1u) & (uint32_t)(NB_HASH - 1);
+      }
+      if (was) continue;
+      if (ns >= NB_HSEEN) { overflow = true; break; }
+      ht[h * LS_THREADS] = n; ++ns;
+      const float qx = a.pos[3 * (size_t)n], qy = a.pos[3 * (size_t)n + 1], qz = a.pos[3 * (size_t)n + 2];
+      const float dx = qx - px, dy = qy - py, dz = qz - pz;
+      if (sqrtf(dx * dx + dy * dy + dz * dz) < radius) {
+        if (WHICH & 1) { zmin = fminf(zmin, qz); zmax = fmaxf(zmax, qz); }
+        if (WHICH & 6) {
+          const float nnx = a.vn[3 * (size_t)n], nny = a.vn[3 * (size_t)n + 1], nnz = a.vn[3 * (size_t)n + 2];
+          if (WHICH & 2) {
+            float dot = nvx * nnx + nvy * nny + nvz * nnz;
+            dot = fminf(1.0f, fmaxf(-1.0f, dot));
+            rsum = rsum + acosf(dot); rcnt++;
+          }
+          if (WHICH & 4) {
+            const float cx = (qx + nnx) - rx, cy = (qy + nny) - ry, cz = (qz + nnz) - rz;
+            value += sqrtf(cx * cx + cy * cy + cz * cz); num++;
+          }
+        }
+        if (sp >= LS_STACK) { overflow = true; break; }
+        stack[(sp++) * LS_THREADS] = n;
+      }
+    }
+  }
+  if (overflow) {
+    zmin = zmin0; zmax = zmax0; rsum = rsum0; value = value0; rcnt = rcnt0; num = num0;
+    walk_linear<WHICH>(a, v, radius, zmin, zmax, rsum, rcnt, value, num);
+  }
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(128) k_layers(const LayerKernelArgs a) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= a.V) return;
+  const mnb_layer_params& P = a.P;
+  const float pz = a.pos[3 * (size_t)v + 2];
+  float zmin = pz, zmax = pz, rsum = 0.0f, value = 0.0f; int rcnt = 0, num = 0;
+  const float r_hd = (float)P.height_diff_radius, r_ro = (float)P.roughness_radius, r_ri = (float)P.ridge_radius;
+  if constexpr (SMEM) {
+    MNB_DYNAMIC_SMEM(ls_raw);
+    uint32_t* ht = reinterpret_cast<uint32_t*>(ls_raw) + threadIdx.x;
+    uint32_t* stack = ht + NB_HASH * LS_THREADS;
+    if (r_hd == r_ro && r_ro == r_ri) {
+      walk_smem<7>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+    } else {
+      walk_smem<1>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+      walk_smem<2>(a, v, r_ro, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+      walk_smem<4>(a, v, r_ri, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+    }
+  } else if (r_hd == r_ro && r_ro == r_ri) {
+    walk<7>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num);
+  } else {
+    walk<1>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num);
+    walk<2>(a, v, r_ro, zmin, zmax, rsum, rcnt, value, num);
+    walk<4>(a, v, r_ri, zmin, zmax, rsum, rcnt, value, num);
+  }
+  const float hd = zmax - zmin;
+  const float ro = rcnt ? rsum / (float)rcnt : 0.0f;
+  const float st = acosf(a.vn[3 * (size_t)v + 2]);                               // steepness_layer.cpp:165
+  const float ri = num == 0 ? (float)(P.ridge_threshold + 0.1) : value / num;     // ridge_layer.cpp:177-184
+  const float cl = a.clearance ? a.clearance[v] : __uint_as_float(INF_BITS);
+  float cc; bool cl_lethal = false;                                              // clearance_layer.cpp:77-96
+  const double inflated_height = P.clearance_robot_height + P.clearance_height_inflation;
+  if (cl < P.clearance_robot_height) { cc = 1.0f; cl_lethal = true; }
+  else if (cl < inflated_height) {
+    const double diff = (cl - P.clearance_robot_height) / P.clearance_height_inflation;
+    cc = (float)((cos(diff * 3.14159265358979323846) + 1.0) / 2.0);
+  } else cc = 0.0f;
+  const float bo = a.border[v] ? (float)P.border_cost : 0.0f;
+  const size_t V = a.V;
+  if (a.costs) {
+    a.costs[v] = hd; a.costs[V + v] = ro; a.costs[2 * V + v] = st; a.costs[3 * V + v] = ri; a.costs[4 * V + v] = cc; a.costs[5 * V + v] = bo;
+  }
+  uint8_t mask = 0;
+  if (hd > P.height_diff_threshold) mask |= 1;
+  if (ro > P.roughness_threshold) mask |= 2;
+  if (st > P.steepness_threshold) mask |= 4;
+  if (ri > P.ridge_threshold) mask |= 8;
+  if (cl_lethal) mask |= 16;
+  if (bo > P.border_threshold) mask |= 32;
+  if (a.lethal_mask) a.lethal_mask[v] = mask;
+  if (a.combined) a.combined[v] = fmaxf(fmaxf(fmaxf(0.0f, hd), fmaxf(ro, st)), fmaxf(fmaxf(ri, cc), bo));   // combination_layer.cpp:60-71
+}
