@@ -198,6 +198,13 @@ int32_t mnb_max_combination_update(mnb_ctx* ctx, uint32_t n_layers, const float*
                                    const uint8_t* const* layer_lethal, uint32_t n_changed, const uint32_t* changed,
                                    float* io_costs /* V */, uint8_t* io_lethal /* V or NULL */);
 
+/* AvgCombinationLayer::onInputChanged / computeLayer (combination_layer.cpp:185-302) for the changed vertices:
+ *   io_costs[v] = sum_i weights[i] * (layer_costs[i][v] or defaults[i]), accumulated in layer order in float;
+ *   io_lethal[v] = OR_i layer_lethal[i][v].  weights = AbstractLayer::combinationWeight() of the inputs (host array). */
+int32_t mnb_avg_combination_update(mnb_ctx* ctx, uint32_t n_layers, const float* const* layer_costs, const float* defaults,
+                                   const float* weights, const uint8_t* const* layer_lethal, uint32_t n_changed,
+                                   const uint32_t* changed, float* io_costs /* V */, uint8_t* io_lethal /* V or NULL */);
+
 /* InflationLayer::onInputChanged (inflation_layer.cpp:97-179): re-runs waveCostInflation from `lethals` (the reference
  * does a full re-inflation here too, :143-151) and reports the update set handed to notifyChange (:154-176): the
  * vertices that carry a riskiness value now or carried one after the previous mnb_inflate / mnb_inflation_update on this

@@ -48,7 +48,7 @@ EXPORTS = [
     "mnb_num_vertices", "mnb_num_faces", "mnb_num_edges", "mnb_get_edges", "mnb_get_edge_distances",
     "mnb_compute_edge_weights", "mnb_set_costs", "mnb_dijkstra", "mnb_cvp", "mnb_cvp_batch", "mnb_inflate",
     "mnb_cancel", "mnb_get_stats", "mnb_set_tuning", "mnb_compute_layers", "mnb_get_vertex_normals", "mnb_vector_map", "mnb_cvp_backtrack", "mnb_locate",
-    "mnb_update_vertex_costs", "mnb_get_costs", "mnb_max_combination_update", "mnb_inflation_update",
+    "mnb_update_vertex_costs", "mnb_get_costs", "mnb_max_combination_update", "mnb_avg_combination_update", "mnb_inflation_update",
     "mnb_inflation_vector_map", "mnb_inflation_vector_at", "mnb_set_repulsive_field",
 ]
 
@@ -90,6 +90,8 @@ def load():
     L.mnb_get_costs.restype = i32; L.mnb_get_costs.argtypes = [vp, vp, vp]
     L.mnb_max_combination_update.restype = i32
     L.mnb_max_combination_update.argtypes = [vp, u32, vp, vp, vp, u32, vp, vp, vp]
+    L.mnb_avg_combination_update.restype = i32
+    L.mnb_avg_combination_update.argtypes = [vp, u32, vp, vp, vp, vp, u32, vp, vp, vp]
     L.mnb_inflation_update.restype = i32
     L.mnb_inflation_update.argtypes = [vp, vp, u32, vp, C.POINTER(InflationParams), vp, vp, vp, C.POINTER(C.c_uint32)]
     L.mnb_inflation_vector_map.restype = i32; L.mnb_inflation_vector_map.argtypes = [vp, vp]

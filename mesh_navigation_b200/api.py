@@ -123,8 +123,9 @@ class MeshMap:
         self._check(self.L.mnb_get_costs(self._ctx, _p(vc), _p(ew)))
         return vc, ew
 
-    def maxCombinationUpdate(self, layer_costs, defaults, layer_lethals, changed, io_costs, io_lethal=None):
-        """MaxCombinationLayer::onInputChanged (combination_layer.cpp:87-147): io_costs / io_lethal updated in place"""
+    def maxCombinationUpdate(self, layer_costs, defaults, layer_lethals, changed, io_costs, io_lethal=None, weights=None):
+        """MaxCombinationLayer::onInputChanged (combination_layer.cpp:87-147), or with `weights`
+        AvgCombinationLayer::onInputChanged (:250-302): io_costs / io_lethal updated in place"""
         n = len(layer_costs)
         lcs = [np.ascontiguousarray(a, dtype=np.float32) for a in layer_costs]
         lls = [None if a is None else np.ascontiguousarray(a, dtype=np.uint8) for a in (layer_lethals or [None] * n)]
@@ -133,8 +134,15 @@ class MeshMap:
         df = np.ascontiguousarray(defaults, dtype=np.float32)
         ch = np.ascontiguousarray(changed, dtype=np.uint32)
         assert io_costs.dtype == np.float32 and io_costs.flags.c_contiguous and io_costs.size == self.V
-        self._check(self.L.mnb_max_combination_update(self._ctx, n, cp, _p(df), lp, ch.size, _p(ch), _p(io_costs), _p(io_lethal)))
+        if weights is not None:
+            wt = np.ascontiguousarray(weights, dtype=np.float32)
+            self._check(self.L.mnb_avg_combination_update(self._ctx, n, cp, _p(df), _p(wt), lp, ch.size, _p(ch), _p(io_costs), _p(io_lethal)))
+        else:
+            self._check(self.L.mnb_max_combination_update(self._ctx, n, cp, _p(df), lp, ch.size, _p(ch), _p(io_costs), _p(io_lethal)))
         return io_costs, io_lethal
+
+    def avgCombinationUpdate(self, layer_costs, defaults, weights, layer_lethals, changed, io_costs, io_lethal=None):
+        return self.maxCombinationUpdate(layer_costs, defaults, layer_lethals, changed, io_costs, io_lethal, weights=weights)
 
     def vertexNormals(self) -> np.ndarray:
         out = np.empty((self.V, 3), dtype=np.float32)

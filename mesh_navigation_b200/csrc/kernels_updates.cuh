@@ -97,6 +97,7 @@ __global__ void k_refresh_weight_tables(const RefreshArgs a) {
 constexpr int COMB_MAX_LAYERS = 8;
 struct CombineArgs {
   const float* costs[COMB_MAX_LAYERS]; const uint8_t* lethal[COMB_MAX_LAYERS]; float def[COMB_MAX_LAYERS];
+  float weight[COMB_MAX_LAYERS]; int average;      // AvgCombinationLayer: weighted sum in layer order (combination_layer.cpp:264-271)
   uint32_t n_layers;
   const uint32_t* changed; uint32_t n, V;
   float* io_costs; uint8_t* io_lethal;
@@ -110,7 +111,8 @@ __global__ void k_max_combination_update(const CombineArgs a) {
   for (uint32_t l = 0; l < a.n_layers; ++l) {
     float tmp = a.costs[l][v];
     if (tmp != tmp) tmp = a.def[l];                        // cm.get(v).value_or(def), combination_layer.cpp:116
-    cost = fmaxf(tmp, cost);                               // std::max(tmp, cost): NaN never enters (tmp is not NaN... unless def is)
+    if (a.average) cost = cost + a.weight[l] * tmp;        // cost += combinationWeight * value (:269), float, no contraction
+    else cost = fmaxf(tmp, cost);                          // std::max(tmp, cost) (:117)
     lethal = lethal || (a.lethal[l] && a.lethal[l][v]);
   }
   a.io_costs[v] = cost;

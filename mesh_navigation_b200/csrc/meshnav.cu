@@ -951,9 +951,11 @@ int32_t mnb_update_vertex_costs(mnb_ctx* ctx, uint32_t n_changed, const uint32_t
   return MNB_OK;
 }
 
-int32_t mnb_max_combination_update(mnb_ctx* ctx, uint32_t n_layers, const float* const* layer_costs, const float* defaults,
-                                   const uint8_t* const* layer_lethal, uint32_t n_changed, const uint32_t* changed,
-                                   float* io_costs, uint8_t* io_lethal) {
+}  // extern "C"
+
+static int32_t combination_update(mnb_ctx* ctx, uint32_t n_layers, const float* const* layer_costs, const float* defaults,
+                                  const float* weights /* null: MaxCombinationLayer */, const uint8_t* const* layer_lethal,
+                                  uint32_t n_changed, const uint32_t* changed, float* io_costs, uint8_t* io_lethal) {
   if (!ctx || !ctx->V || n_layers == 0 || n_layers > (uint32_t)COMB_MAX_LAYERS || !layer_costs || !defaults || !io_costs ||
       (n_changed && !changed)) return MNB_E_ARG;
   for (uint32_t l = 0; l < n_layers; ++l) if (!layer_costs[l]) return MNB_E_ARG;
@@ -962,7 +964,8 @@ int32_t mnb_max_combination_update(mnb_ctx* ctx, uint32_t n_layers, const float*
   const bool dev = ctx->ptr_mode == MNB_PTR_DEVICE;
   const size_t V = ctx->V;
   CombineArgs a{};
-  a.n_layers = n_layers; a.n = n_changed; a.V = ctx->V;
+  a.n_layers = n_layers; a.n = n_changed; a.V = ctx->V; a.average = weights ? 1 : 0;
+  for (uint32_t l = 0; l < n_layers; ++l) a.weight[l] = weights ? weights[l] : 1.0f;
   std::vector<void*> tmp;                             // host-pointer mode: device copies of the maps
   auto cleanup = [&]() { for (void* q : tmp) cudaFree(q); };
   auto up = [&](const void* h, size_t bytes, void** d) -> cudaError_t {
@@ -1002,6 +1005,21 @@ int32_t mnb_max_combination_update(mnb_ctx* ctx, uint32_t n_layers, const float*
   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   ctx->stats = mnb_stats{}; ctx->stats.kernel_ms = ms; ctx->stats.kernel_launches = 1; ctx->stats.settled = n_changed;
   return MNB_OK;
+}
+
+extern "C" {
+
+int32_t mnb_max_combination_update(mnb_ctx* ctx, uint32_t n_layers, const float* const* layer_costs, const float* defaults,
+                                   const uint8_t* const* layer_lethal, uint32_t n_changed, const uint32_t* changed,
+                                   float* io_costs, uint8_t* io_lethal) {
+  return combination_update(ctx, n_layers, layer_costs, defaults, nullptr, layer_lethal, n_changed, changed, io_costs, io_lethal);
+}
+
+int32_t mnb_avg_combination_update(mnb_ctx* ctx, uint32_t n_layers, const float* const* layer_costs, const float* defaults,
+                                   const float* weights, const uint8_t* const* layer_lethal, uint32_t n_changed,
+                                   const uint32_t* changed, float* io_costs, uint8_t* io_lethal) {
+  if (!weights) return MNB_E_ARG;
+  return combination_update(ctx, n_layers, layer_costs, defaults, weights, layer_lethal, n_changed, changed, io_costs, io_lethal);
 }
 
 }  // extern "C"

@@ -1102,6 +1102,28 @@ extern "C" void orc_max_combination_update(uint32_t n_layers, const float* const
     }
 }
 
+// AvgCombinationLayer::onInputChanged  combination_layer.cpp:250-302 (== computeLayer :185-248 on a costs_ map that still
+// holds its initial default 0, :177-181): cost = sum over the input layers, in order, of combinationWeight * (value or
+// default), float accumulation; lethal = the vertex is in the lethal set of any input.
+extern "C" void orc_avg_combination_update(uint32_t n_layers, const float* const* layer_costs, const float* defaults,
+                                           const float* weights, const uint8_t* const* layer_lethals, const uint32_t* changed,
+                                           uint32_t n, float* costs, uint8_t* lethals) {
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t v = changed[i];
+    float cost = 0;
+    for (uint32_t l = 0; l < n_layers; ++l)
+      cost += weights[l] * (std::isnan(layer_costs[l][v]) ? defaults[l] : layer_costs[l][v]);      // :269
+    costs[v] = cost;
+  }
+  if (lethals)
+    for (uint32_t i = 0; i < n; ++i) {
+      const uint32_t v = changed[i];
+      bool lethal = false;
+      for (uint32_t l = 0; l < n_layers; ++l) lethal = lethal || (layer_lethals[l] && layer_lethals[l][v]);
+      lethals[v] = lethal ? 1 : 0;
+    }
+}
+
 // InflationLayer::onInputChanged  inflation_layer.cpp:154-164: the update set handed to notifyChange is the union of the
 // keys of the new and of the previous riskiness map (std::set: ascending).  Returns its size.
 extern "C" uint32_t orc_inflation_update_set(uint32_t V, const float* new_costs, const float* old_costs, uint32_t* out) {

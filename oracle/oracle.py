@@ -195,6 +195,21 @@ def max_combination_update(layer_costs, defaults, layer_lethals, changed, costs,
     return costs, lethals
 
 
+def avg_combination_update(layer_costs, defaults, weights, layer_lethals, changed, costs, lethals=None):
+    """AvgCombinationLayer::onInputChanged / computeLayer (combination_layer.cpp:185-302): costs / lethals updated in place."""
+    L = len(layer_costs)
+    lcs = [np.ascontiguousarray(a, dtype=np.float32) for a in layer_costs]
+    lls = [None if a is None else np.ascontiguousarray(a, dtype=np.uint8) for a in layer_lethals]
+    cp = (C.c_void_p * L)(*[a.ctypes.data for a in lcs])
+    lp = (C.c_void_p * L)(*[None if a is None else a.ctypes.data for a in lls])
+    df = np.ascontiguousarray(defaults, dtype=np.float32); wt = np.ascontiguousarray(weights, dtype=np.float32)
+    ch = np.unique(np.ascontiguousarray(changed, dtype=np.uint32))
+    f = lib().orc_avg_combination_update
+    f.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    f(L, cp, _p(df), _p(wt), lp, _p(ch), ch.size, _p(costs), _p(lethals))
+    return costs, lethals
+
+
 def inflation_update_set(new_costs, old_costs=None):
     """InflationLayer::onInputChanged (inflation_layer.cpp:154-164): keys(new) U keys(old), ascending."""
     nc = np.ascontiguousarray(new_costs, dtype=np.float32)

@@ -90,6 +90,15 @@ def test_max_combination_update(api, oracle_mod):
     assert (got_c.view(np.uint32) == ref_c.view(np.uint32)).all() and (got_l == ref_l).all()
     untouched = np.setdiff1d(np.arange(V), changed)
     assert (got_c[untouched] == -1.0).all() and (got_l[untouched] == 7).all()
+    # AvgCombinationLayer (combination_layer.cpp:185-302): weighted sum in layer order; all vertices = computeLayer
+    wts = [0.5, 0.3, 0.2]
+    allv = np.arange(V, dtype=np.uint32)
+    ref_a = np.zeros(V, np.float32); ref_al = np.zeros(V, np.uint8)
+    O.avg_combination_update([la, lb, lc], [0.0, 0.1, 0.25], wts, [leth_a, leth_b, None], allv, ref_a, ref_al)
+    got_a = np.zeros(V, np.float32); got_al = np.zeros(V, np.uint8)
+    mm.avgCombinationUpdate([la, lb, lc], [0.0, 0.1, 0.25], wts, [leth_a, leth_b, None], allv, got_a, got_al)
+    assert (got_a.view(np.uint32) == ref_a.view(np.uint32)).all() and (got_al == ref_al).all()
+    assert (ref_al == (leth_a | leth_b)).all()
     mm.close()
 
 

@@ -213,6 +213,12 @@ def test_incremental_update_restatements(oracle_mod):
     assert costs.tolist() == [np.float32(0.3), np.float32(0.3), np.float32(0.3), 9.0] and leth.tolist() == [0, 0, 1, 5]
     O.max_combination_update([a, b], [0.0, 0.3], [None, None], np.uint32([3]), costs, leth)
     assert costs[3] == np.float32(0.9) and leth[3] == 0
+    # AvgCombination (combination_layer.cpp:264-271): weighted sum in layer order, float
+    avg = np.float32([9, 9, 9, 9]); al = np.uint8([5, 5, 5, 5])
+    O.avg_combination_update([a, b], [0.0, 0.3], [0.5, 2.0], [np.uint8([0, 0, 1, 0]), None], np.uint32([0, 2, 3]), avg, al)
+    assert avg[0] == np.float32(0.5) * np.float32(0.2) + np.float32(2.0) * np.float32(0.3)
+    assert avg[2] == np.float32(0.5) * np.float32(0.0) + np.float32(2.0) * np.float32(0.3) and avg[1] == 9.0
+    assert avg[3] == np.float32(0.5) * np.float32(0.4) + np.float32(2.0) * np.float32(0.9) and al.tolist() == [0, 5, 1, 0]
     # update set: keys(new) U keys(old)
     new = np.float32([np.nan, 1.0, np.nan, 0.5]); old = np.float32([0.1, np.nan, np.nan, 0.2])
     assert O.inflation_update_set(new, old).tolist() == [0, 1, 3] and O.inflation_update_set(new).tolist() == [1, 3]
