@@ -53,7 +53,25 @@ struct LayerKernelArgs {
   float* costs;                // 6 x V
   float* combined; uint8_t* lethal_mask;
   unsigned int* overflow;      // neighbourhood larger than the per-thread scratch
+  // packed copies for k_layers<true>: one 16-byte load per position / normal, one 32-byte row of neighbour ids per vertex
+  const float4* pos4; const float4* vn4; const uint4* nbr8;
 };
+
+// k_layers<true> reads packed copies of the same data: every per-thread (scattered) load instruction costs 32 L1
+// wavefronts whatever its width, so {x,y,z} as three 4-byte loads and a neighbour list behind two CSR pointers triple the
+// wavefront count of the walk, which is what bounds the kernel.
+constexpr uint32_t NBR8_EMPTY = 0xffffffffu, NBR8_BIG = 0xfffffffeu;
+__global__ void k_pack_layers(const float* __restrict__ pos, const float* __restrict__ vn, const uint32_t* __restrict__ adj_ptr,
+                              const uint32_t* __restrict__ adj_nbr, uint32_t V, float4* __restrict__ pos4, float4* __restrict__ vn4,
+                              uint32_t* __restrict__ nbr8) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  pos4[v] = make_float4(pos[3 * (size_t)v], pos[3 * (size_t)v + 1], pos[3 * (size_t)v + 2], 0.0f);
+  vn4[v] = make_float4(vn[3 * (size_t)v], vn[3 * (size_t)v + 1], vn[3 * (size_t)v + 2], 0.0f);
+  const uint32_t kb = adj_ptr[v], deg = adj_ptr[v + 1] - kb;
+  for (uint32_t j = 0; j < 8; ++j)      // CSR order (ascending edge id) is kept: the traversal order must not change
+    nbr8[8 * (size_t)v + j] = deg > 8 ? NBR8_BIG : (j < deg ? adj_nbr[kb + j] : NBR8_EMPTY);
+}
 
 constexpr int NB_SEEN = 320, NB_STACK = 160;
 
@@ -175,44 +193,57 @@ __device__ __forceinline__ void walk_smem(const LayerKernelArgs& a, uint32_t v, 
   const float zmin0 = zmin, zmax0 = zmax, rsum0 = rsum, value0 = value; const int rcnt0 = rcnt, num0 = num;
   int ns = 0, sp = 0;
   ht[((v * 2654435761u) >> 25) * LS_THREADS] = v; ns = 1; stack[(sp++) * LS_THREADS] = v;
-  const float px = a.pos[3 * (size_t)v], py = a.pos[3 * (size_t)v + 1], pz = a.pos[3 * (size_t)v + 2];
-  const float nvx = a.vn[3 * (size_t)v], nvy = a.vn[3 * (size_t)v + 1], nvz = a.vn[3 * (size_t)v + 2];
+  const float4 pv = __ldg(&a.pos4[v]), nv = __ldg(&a.vn4[v]);
+  const float px = pv.x, py = pv.y, pz = pv.z;
+  const float nvx = nv.x, nvy = nv.y, nvz = nv.z;
   const float rx = px + nvx, ry = py + nvy, rz = pz + nvz;
   bool overflow = false;
+  // one neighbour of the vertex being expanded: same body as walk<>, on the packed arrays
+  auto visit = [&](uint32_t n) {
+    uint32_t h = (n * 2654435761u) >> 25;
+    for (;;) {
+      const uint32_t e = ht[h * LS_THREADS];
+      if (e == n) return;
+      if (e == 0xffffffffu) break;
+      h = (h + 1u) & (uint32_t)(NB_HASH - 1);
+    }
+    if (ns >= NB_HSEEN) { overflow = true; return; }
+    ht[h * LS_THREADS] = n; ++ns;
+    const float4 q = __ldg(&a.pos4[n]);
+    const float qx = q.x, qy = q.y, qz = q.z;
+    const float dx = qx - px, dy = qy - py, dz = qz - pz;
+    if (sqrtf(dx * dx + dy * dy + dz * dz) < radius) {
+      if (WHICH & 1) { zmin = fminf(zmin, qz); zmax = fmaxf(zmax, qz); }
+      if (WHICH & 6) {
+        const float4 nn = __ldg(&a.vn4[n]);
+        const float nnx = nn.x, nny = nn.y, nnz = nn.z;
+        if (WHICH & 2) {
+          float dot = nvx * nnx + nvy * nny + nvz * nnz;
+          dot = fminf(1.0f, fmaxf(-1.0f, dot));
+          rsum = rsum + acosf(dot); rcnt++;
+        }
+        if (WHICH & 4) {
+          const float cx = (qx + nnx) - rx, cy = (qy + nny) - ry, cz = (qz + nnz) - rz;
+          value += sqrtf(cx * cx + cy * cy + cz * cz); num++;
+        }
+      }
+      if (sp >= LS_STACK) { overflow = true; return; }
+      stack[(sp++) * LS_THREADS] = n;
+    }
+  };
   while (sp > 0 && !overflow) {
     const uint32_t u = stack[(--sp) * LS_THREADS];
-    for (uint32_t k = a.adj_ptr[u]; k < a.adj_ptr[u + 1]; ++k) {
-      const uint32_t n = a.adj_nbr[k];
-      uint32_t h = (n * 2654435761u) >> 25;
-      bool was = false;
-      for (;;) {
-        const uint32_t e = ht[h * LS_THREADS];
-        if (e == n) { was = true; break; }
-        if (e == 0xffffffffu) break;
-        h = (h + 1u) & (uint32_t)(NB_HASH - 1);
-      }
-      if (was) continue;
-      if (ns >= NB_HSEEN) { overflow = true; break; }
-      ht[h * LS_THREADS] = n; ++ns;
-      const float qx = a.pos[3 * (size_t)n], qy = a.pos[3 * (size_t)n + 1], qz = a.pos[3 * (size_t)n + 2];
-      const float dx = qx - px, dy = qy - py, dz = qz - pz;
-      if (sqrtf(dx * dx + dy * dy + dz * dz) < radius) {
-        if (WHICH & 1) { zmin = fminf(zmin, qz); zmax = fmaxf(zmax, qz); }
-        if (WHICH & 6) {
-          const float nnx = a.vn[3 * (size_t)n], nny = a.vn[3 * (size_t)n + 1], nnz = a.vn[3 * (size_t)n + 2];
-          if (WHICH & 2) {
-            float dot = nvx * nnx + nvy * nny + nvz * nnz;
-            dot = fminf(1.0f, fmaxf(-1.0f, dot));
-            rsum = rsum + acosf(dot); rcnt++;
-          }
-          if (WHICH & 4) {
-            const float cx = (qx + nnx) - rx, cy = (qy + nny) - ry, cz = (qz + nnz) - rz;
-            value += sqrtf(cx * cx + cy * cy + cz * cz); num++;
-          }
-        }
-        if (sp >= LS_STACK) { overflow = true; break; }
-        stack[(sp++) * LS_THREADS] = n;
-      }
+    const uint4 r0 = __ldg(&a.nbr8[2 * (size_t)u]);
+    if (r0.x == NBR8_BIG) {                       // more than 8 neighbours: CSR row
+      for (uint32_t k = a.adj_ptr[u]; k < a.adj_ptr[u + 1] && !overflow; ++k) visit(a.adj_nbr[k]);
+      continue;
+    }
+    const uint4 r1 = __ldg(&a.nbr8[2 * (size_t)u + 1]);
+    const uint32_t ids[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (ids[j] == NBR8_EMPTY || overflow) break;
+      visit(ids[j]);
     }
   }
   if (overflow) {
