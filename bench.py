@@ -418,11 +418,46 @@ def main():
             return {"wall_ms": 1e3 * tmp, "wavefront_kernel_ms": mp.get("wavefront_ms"), "path_points": int(len(mp["positions"])),
                     "path_length_m": mp["cost"], "outcome": int(mp["outcome"])}
 
+        def leg_optin_variants():
+            """A/B of the opt-in kernel variants that were written and verified on the CPU interpreter of the kernels after the
+            round's GPU budget was spent: each is run next to the default kernel on the bench mesh and
+            compared bit for bit.  Run last: nothing above depends on them."""
+            import ctypes as C
+            out = {}
+            for f in ("mnb_debug_set_skip_clean", "mnb_debug_set_layers_smem"):
+                getattr(mm.L, f).argtypes = [C.c_void_p, C.c_int32]
+            mm.setCosts(vc, ed)
+            base = planner.waveFrontPropagation(sf, sp)
+            mm.L.mnb_debug_set_skip_clean(mm._ctx, 1)
+            try:
+                best = None
+                for rep in range(3):
+                    g = planner.waveFrontPropagation(sf, sp)
+                    best = g["kernel_ms"] if best is None else min(best, g["kernel_ms"])
+                out["cvp_clean_candidate_skip"] = {
+                    "kernel_ms": best, "default_kernel_ms": base["kernel_ms"], "recomputes_per_vertex": g["recomputes"] / V,
+                    "default_recomputes_per_vertex": base["recomputes"] / V, "skipped_per_vertex": g["skipped"] / V,
+                    "identical_to_default": bool((g["dist"].view(np.uint32) == base["dist"].view(np.uint32)).all())}
+            finally:
+                mm.L.mnb_debug_set_skip_clean(mm._ctx, 0)
+            Lb = mm.computeLayers()
+            mm.L.mnb_debug_set_layers_smem(mm._ctx, 1)
+            try:
+                for rep in range(2):
+                    Ls = mm.computeLayers()
+                same = all(bool((Ls[k].view(np.uint32) == Lb[k].view(np.uint32)).all()) for k in ("height_diff", "roughness", "steepness", "ridge", "combined"))
+                out["layers_shared_memory_packed"] = {"kernel_ms": Ls["kernel_ms"], "default_kernel_ms": Lb["kernel_ms"],
+                                                      "hbm_frac": 837 * V / (Ls["kernel_ms"] * 1e-3) / 1e9 / hbm0, "identical_to_default": same}
+            finally:
+                mm.L.mnb_debug_set_layers_smem(mm._ctx, 0)
+            return out
+
         leg("dijkstra_full_field", leg_dijkstra)
         leg("fused_layers", leg_layers)
         leg("inflation", leg_inflation)
         leg("dynamic_obstacle_update", leg_dynamic_update)
         leg("make_plan_corner_to_corner", leg_make_plan)
+        leg("optin_variants", leg_optin_variants)
         shared.clear()
 
     if rank == 0:
