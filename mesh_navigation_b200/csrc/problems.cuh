@@ -253,6 +253,10 @@ struct CvpEllProblemT : CvpProblem {
                            // could still fire before the candidate pops (d <= its pop time); +inf: none.  The candidate is
                            // re-evaluated once the band end passes it.
   int skip_clean;          // runtime switch (0: every candidate is recomputed every round)
+  // activation marks of the two source vertices: fetched together with their labels (whole-grid single plan: one L2 trip
+  // less on the evaluation that activates, which is on the wave's critical path) or only by that one evaluation
+  // (throughput-bound batches: two scattered 4-byte loads = 64 L1 wavefronts per warp less on every other evaluation)
+  bool prefetch_marks;
   const int4* __restrict__ ell_idx;
   const float4* __restrict__ ell_w;
   const double4* __restrict__ ell_geo;   // {p, hc, t0a, -} per slot, precomputed from ell_w (k_corner_geo)
@@ -350,7 +354,7 @@ struct CvpEllProblemT : CvpProblem {
       const uint32_t v1 = (uint32_t)ix.x, v2 = (uint32_t)ix.y;
       // issue the four loads, then do the label-independent half of the unfolding while they are in flight
       const uint4 sa = __ldcg(&state[v1]), sb = __ldcg(&state[v2]);
-      mk1 = __ldcg(&mark[v1]); mk2 = __ldcg(&mark[v2]);
+      if (prefetch_marks) { mk1 = __ldcg(&mark[v1]); mk2 = __ldcg(&mark[v2]); }
       const double2* gp = reinterpret_cast<const double2*>(ell_geo) + 2 * ((size_t)c * ELL_W + j);
       const double2 g01 = __ldg(gp), g23 = __ldg(gp + 1);
       FaceGeo g; g.p = g01.x; g.hc = g01.y; g.t0a = g23.x;
@@ -707,6 +711,7 @@ struct DijkstraEllProblem : DijkstraProblem {
   static constexpr bool TWO_SOURCES = false;
   static constexpr bool CAN_SKIP = false;     // one relaxation is as cheap as the bookkeeping of skipping it
   uint32_t* last_eval = nullptr; uint32_t* dirty_round = nullptr; uint32_t* excl_min = nullptr; int skip_clean = 0;
+  static constexpr bool prefetch_marks = true;
   const uint4* __restrict__ ell_adj;
   uint32_t* ver;
 
