@@ -370,69 +370,87 @@ struct CvpEllProblemT : CvpProblem {
         if (!backstep_ok((float)X, T, Tv, round)) X = (double)INF;
       }
     }
-    // Common case: every firing face of the warp has a plain pop time (a2 == a3 == 0, default minor, root = Tv):
-    // the event order is (a1, Tv).  Cascade members (rare) take the general path on (a1, root, a2, a3, minor).  Invalid
-    // lanes carry the maximal key so that no validity flag has to travel with the shuffles.
-    const bool plain = !valid || (T.a2 == 0.0f && T.a3 == 0.0f && T.minor == 2u * Tv && T.root == Tv);
-    const bool all_plain = __all_sync(FULL, plain);
-    const uint32_t k1 = valid ? __float_as_uint(T.a1) : 0xffffffffu;          // pop times are >= 0: bit order = value order
-    const unsigned long long hi = valid ? (((unsigned long long)k1 << 32) | T.root) : ~0ull;          // plain: root == Tv
-    const unsigned long long mid = ((unsigned long long)__float_as_uint(T.a2) << 32) | __float_as_uint(T.a3);
-    const uint32_t lo = T.minor;
-    int rank = 0;
-    if (all_plain) {
-      // 32-bit pass on a1 alone; two firing faces with bit-identical a1 (exact float tie between different source
-      // vertices) are rare -- only then is the (a1, Tv) pass needed
-      bool tie = false;
+    float cur = INF;
+    EvTime tc = ev_normal(INF, c);
+    // Fast path (the norm on geometric weights).  A face is CAUSAL if its value exceeds its own pop time (the label it hands
+    // out pops at its own key, accept_time) and U <= X (the accept test is then X < cur).  Let m = min (float)X over the
+    // causal faces of c.  If every other firing face has a pop time above m, the event-ordered replay collapses to m:
+    //   * the causal face i* with value m fires before c pops (T.a1 < m <= every earlier cur) and nothing lowers m later;
+    //   * a non-causal face j with T_j.a1 > m comes after i* in event order (T_i*.a1 < m < T_j.a1), when c -- key <= m --
+    //     has already popped: it is never applied;
+    //   * rejected / unreached causal faces have float values >= m (rounding is monotone).
+    // So d = m and c pops at (m, c): no ranking, no replay loop.  Faces "looking backwards" (sources farther from the seed
+    // than c, T > X) are the common non-causal case and are all of the harmless kind.
+    const float Xf = (float)X;
+    const bool causal = valid && Xf > T.a1 && U <= X;
+    float m = causal ? Xf : INF;
 #pragma unroll
-      for (int d = 1; d < 8; ++d) {
-        const int src = (int)((j + d) & 7);
-        const uint32_t ok1 = __shfl_sync(FULL, k1, src, 8);
-        rank += (ok1 < k1) ? 1 : 0;
-        tie |= (ok1 == k1) && valid;
-      }
-      if (__any_sync(FULL, tie)) {
-        rank = 0;
-#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(FULL, m, o, 8));
+    if (__all_sync(FULL, !valid || causal || T.a1 > m)) {
+      cur = m; tc = ev_normal(m, c);
+    } else {
+      // Common case: every firing face of the warp has a plain pop time (a2 == a3 == 0, default minor, root = Tv):
+      // the event order is (a1, Tv).  Cascade members (rare) take the general path on (a1, root, a2, a3, minor).  Invalid
+      // lanes carry the maximal key so that no validity flag has to travel with the shuffles.
+      const bool plain = !valid || (T.a2 == 0.0f && T.a3 == 0.0f && T.minor == 2u * Tv && T.root == Tv);
+      const bool all_plain = __all_sync(FULL, plain);
+      const uint32_t k1 = valid ? __float_as_uint(T.a1) : 0xffffffffu;          // pop times are >= 0: bit order = value order
+      const unsigned long long hi = valid ? (((unsigned long long)k1 << 32) | T.root) : ~0ull;          // plain: root == Tv
+      const unsigned long long mid = ((unsigned long long)__float_as_uint(T.a2) << 32) | __float_as_uint(T.a3);
+      const uint32_t lo = T.minor;
+      int rank = 0;
+      if (all_plain) {
+        // 32-bit pass on a1 alone; two firing faces with bit-identical a1 (exact float tie between different source
+        // vertices) are rare -- only then is the (a1, Tv) pass needed
+        bool tie = false;
+  #pragma unroll
+        for (int d = 1; d < 8; ++d) {
+          const int src = (int)((j + d) & 7);
+          const uint32_t ok1 = __shfl_sync(FULL, k1, src, 8);
+          rank += (ok1 < k1) ? 1 : 0;
+          tie |= (ok1 == k1) && valid;
+        }
+        if (__any_sync(FULL, tie)) {
+          rank = 0;
+  #pragma unroll
+          for (int d = 1; d < 8; ++d) {
+            const int src = (int)((j + d) & 7);
+            const unsigned long long ohi = __shfl_sync(FULL, hi, src, 8);
+            if (ohi < hi || (ohi == hi && (uint32_t)src < j)) ++rank;
+          }
+        }
+      } else {
+  #pragma unroll
         for (int d = 1; d < 8; ++d) {
           const int src = (int)((j + d) & 7);
           const unsigned long long ohi = __shfl_sync(FULL, hi, src, 8);
-          if (ohi < hi || (ohi == hi && (uint32_t)src < j)) ++rank;
+          const unsigned long long omid = __shfl_sync(FULL, mid, src, 8);
+          const uint32_t olo = __shfl_sync(FULL, lo, src, 8);
+          if (ohi < hi || (ohi == hi && (omid < mid || (omid == mid && (olo < lo || (olo == lo && (uint32_t)src < j)))))) ++rank;
         }
       }
-    } else {
-#pragma unroll
-      for (int d = 1; d < 8; ++d) {
-        const int src = (int)((j + d) & 7);
-        const unsigned long long ohi = __shfl_sync(FULL, hi, src, 8);
-        const unsigned long long omid = __shfl_sync(FULL, mid, src, 8);
-        const uint32_t olo = __shfl_sync(FULL, lo, src, 8);
-        if (ohi < hi || (ohi == hi && (omid < mid || (omid == mid && (olo < lo || (olo == lo && (uint32_t)src < j)))))) ++rank;
+      if (!valid) rank = 99;
+      const int nvalid = __popc((__ballot_sync(FULL, valid) >> sh) & 0xFFu);
+      bool open = nvalid > 0;                             // c has not been popped yet and faces remain
+      for (int r = 0; r < (int)ELL_W; ++r) {
+        if (!__any_sync(FULL, open)) break;               // every group of the warp is done
+        const unsigned who = (__ballot_sync(FULL, rank == r) >> sh) & 0xFFu;
+        const int src = who ? (__ffs(who) - 1) : 0;
+        const unsigned long long whi = __shfl_sync(FULL, hi, src, 8);
+        unsigned long long wmid = 0; uint32_t wlo = 0;
+        if (!all_plain) { wmid = __shfl_sync(FULL, mid, src, 8); wlo = __shfl_sync(FULL, lo, src, 8); }
+        const double Uw = __shfl_sync(FULL, U, src, 8);
+        const double Xw = __shfl_sync(FULL, X, src, 8);
+        if (!who) open = false;                           // ranks are dense: no face with rank r -> none beyond
+        if (!open) continue;
+        EvTime Tw;
+        Tw.a1 = __uint_as_float((uint32_t)(whi >> 32)); Tw.root = (uint32_t)whi;
+        if (all_plain) { Tw.a2 = 0.0f; Tw.a3 = 0.0f; Tw.minor = 2u * (uint32_t)whi; }
+        else { Tw.a2 = __uint_as_float((uint32_t)(wmid >> 32)); Tw.a3 = __uint_as_float((uint32_t)wmid); Tw.minor = wlo; }
+        if (!ev_less(Tw, tc)) { open = false; continue; }
+        const double cd = (double)cur;
+        if (Uw < cd && Xw < cd) { cur = (float)Xw; tc = accept_time(c, cur, Tw); }
       }
-    }
-    if (!valid) rank = 99;
-    const int nvalid = __popc((__ballot_sync(FULL, valid) >> sh) & 0xFFu);
-    float cur = INF;
-    EvTime tc = ev_normal(INF, c);
-    bool open = nvalid > 0;                             // c has not been popped yet and faces remain
-    for (int r = 0; r < (int)ELL_W; ++r) {
-      if (!__any_sync(FULL, open)) break;               // every group of the warp is done
-      const unsigned who = (__ballot_sync(FULL, rank == r) >> sh) & 0xFFu;
-      const int src = who ? (__ffs(who) - 1) : 0;
-      const unsigned long long whi = __shfl_sync(FULL, hi, src, 8);
-      unsigned long long wmid = 0; uint32_t wlo = 0;
-      if (!all_plain) { wmid = __shfl_sync(FULL, mid, src, 8); wlo = __shfl_sync(FULL, lo, src, 8); }
-      const double Uw = __shfl_sync(FULL, U, src, 8);
-      const double Xw = __shfl_sync(FULL, X, src, 8);
-      if (!who) open = false;                           // ranks are dense: no face with rank r -> none beyond
-      if (!open) continue;
-      EvTime Tw;
-      Tw.a1 = __uint_as_float((uint32_t)(whi >> 32)); Tw.root = (uint32_t)whi;
-      if (all_plain) { Tw.a2 = 0.0f; Tw.a3 = 0.0f; Tw.minor = 2u * (uint32_t)whi; }
-      else { Tw.a2 = __uint_as_float((uint32_t)(wmid >> 32)); Tw.a3 = __uint_as_float((uint32_t)wmid); Tw.minor = wlo; }
-      if (!ev_less(Tw, tc)) { open = false; continue; }
-      const double cd = (double)cur;
-      if (Uw < cd && Xw < cd) { cur = (float)Xw; tc = accept_time(c, cur, Tw); }
     }
     if (big) {   // rare: more than 8 faces -> CSR path on the group's first lane, result broadcast below
       if (j == 0) replay_serial(c, band_end, goal, round, cur, tc);
