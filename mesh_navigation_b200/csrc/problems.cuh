@@ -649,9 +649,40 @@ struct InflationProblem {
     nd = cur; tc_out = tc;
   }
 
+  // Same collapse as CvpEllProblemT::replay_sub8's fast path: if every firing face either is causal (candidate above its own
+  // pop time) with both sources inside the radius (so the accepted value is also the heap key, :310), or fires after the
+  // smallest causal candidate m, the call-ordered replay yields d = m and the pop time (m, c) -- no sorting of the faces,
+  // no visit keys.  Returns false if the general replay is needed.
+  __device__ __forceinline__ bool replay_fast(uint32_t c, float band_end, float& nd, EvTime& tc_out) const {
+    const uint32_t kb = cor_ptr[c], ke = cor_ptr[c + 1];
+    if (ke - kb > (uint32_t)MAXF || (invalid && invalid[c])) return false;
+    const float INF = __uint_as_float(INF_BITS);
+    float Ta[MAXF];
+    int n = 0;
+    float m = INF;
+    for (uint32_t k = kb; k < ke; ++k) {
+      EvTime T; float u1, u2; uint32_t Tv;
+      if (!corner_time(k, band_end, T, Tv, u1, u2)) continue;
+      const float4 w = __ldg(&cor_wd[k]);
+      const float cand = inflation_candidate(u1, u2, w.z, w.y, w.x);
+      if (cand > T.a1) {                                               // causal
+        if (!(u1 <= max_distance && u2 <= max_distance)) return false;   // accepted without (re)insertion: heap key != distance
+        m = fminf(m, cand);
+        Ta[n] = -1.0f;
+      } else {
+        Ta[n] = T.a1;
+      }
+      ++n;
+    }
+    for (int i = 0; i < n; ++i)
+      if (Ta[i] >= 0.0f && !(Ta[i] > m)) return false;                 // a non-causal face that could fire before c pops
+    nd = m; tc_out = ev_normal(m, c);
+    return true;
+  }
+
   __device__ __forceinline__ bool recompute(uint32_t c, float band_end, float /*goal*/, uint32_t round, const Label& old, float& nd, float& ntau) {
     EvTime tc; int win; float wu1, wu2;
-    replay(c, band_end, round, nd, tc, win, wu1, wu2);
+    if (strict || !replay_fast(c, band_end, nd, tc)) replay(c, band_end, round, nd, tc, win, wu1, wu2);
     ntau = tc.a1;
     if (__float_as_uint(nd) == __float_as_uint(old.d) && ev_eq(tc, old.t)) return false;
     store_label(c, nd, tc, __float_as_uint(old.d) != INF_BITS, round);
