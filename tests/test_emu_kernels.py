@@ -85,3 +85,26 @@ def test_cpp_host_mirror_on_the_cpu_interpreter(emu_lib, tmp_path, oracle_mod):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=dict(os.environ, MNB_EMU_SMS="4"))
     assert out.returncode == 0, out.stdout + out.stderr
     assert "cpp host mirror ok" in out.stdout
+
+
+def test_bench_orchestration_on_the_cpu_interpreter(emu_lib):
+    """bench.py's B200 arm, every leg, executed end to end on the interpreter at toy sizes (tests/emu/run_bench_on_emu.py):
+    the JSON line must carry the contract's keys and no secondary leg may have fallen into its error branch"""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "run_bench_on_emu.py"), "--size", "90", "--batch-size", "50",
+                        "--batch-goals", "4", "--batch-steps", "1", "--steps", "1", "--warmup", "1"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "e2e", "gpu_launches", "roofline", "clocks", "cpu_baseline", "batched", "other_kernels"):
+        assert k in line, k
+    assert line["metric"] == "vertex-relaxations/sec" and "workload" in line["config"] and line["gpu_launches"] > 0
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in line["roofline"], k
+    assert "error" not in line["batched"], line["batched"]
+    for name, leg in line["other_kernels"].items():
+        assert "error" not in leg, (name, leg)
+    assert line["other_kernels"]["dynamic_obstacle_update"]["incremental_equals_full"] is True
+    v = line["other_kernels"]["optin_variants"]
+    assert v["cvp_clean_candidate_skip"]["identical_to_default"] and v["layers_shared_memory_packed"]["identical_to_default"]
