@@ -108,3 +108,12 @@ def test_bench_orchestration_on_the_cpu_interpreter(emu_lib):
     assert line["other_kernels"]["dynamic_obstacle_update"]["incremental_equals_full"] is True
     v = line["other_kernels"]["optin_variants"]
     assert v["cvp_clean_candidate_skip"]["identical_to_default"] and v["layers_shared_memory_packed"]["identical_to_default"]
+
+
+def test_smoke_entry_on_the_cpu_interpreter(emu_lib):
+    """__graft_entry__.smoke() (the driver's GPU smoke check) with the binding pointed at the interpreted kernels"""
+    code = ("import sys; sys.path.insert(0, %r); from mesh_navigation_b200 import _lib; _lib.LIB_PATH = %r; "
+            "import __graft_entry__ as g; g.smoke()") % (ROOT, emu_lib)
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, MNB_EMU_SMS="4"))
+    assert r.returncode == 0 and "smoke ok" in r.stdout, (r.stdout + r.stderr)[-2000:]
