@@ -834,6 +834,7 @@ static int32_t inflate_impl(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, c
                             uint32_t* out_changed, uint32_t* n_changed) {
   if (!ctx || !ctx->V || !params || (n && !lethals)) return MNB_E_ARG;
   CK(cudaSetDevice(ctx->device));
+  ctx->infl_labels_valid = false;
   int32_t rc;
   if ((rc = ensure_workspace(ctx, 1)) != MNB_OK) return rc;
   const bool dev = ctx->ptr_mode == MNB_PTR_DEVICE;
@@ -955,7 +956,6 @@ int32_t mnb_update_vertex_costs(mnb_ctx* ctx, uint32_t n_changed, const uint32_t
   CK(cudaStreamSynchronize(ctx->stream));
   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   ctx->stats = mnb_stats{}; ctx->stats.kernel_ms = ms; ctx->stats.kernel_launches = launches; ctx->stats.settled = n_changed;
-  ctx->last_valid = false;                           // the device-resident plan no longer belongs to the installed costs
   return MNB_OK;
 }
 
