@@ -314,3 +314,50 @@ def test_inflation_high_degree_vertex(api, oracle_mod):
         vec = infl.vectorMap()
         assert (vec.view(np.uint32) == ref["vectors"].view(np.uint32)).all(), k
     mm.close()
+
+
+def test_update_api_edge_cases(api, oracle_mod):
+    """empty / out-of-range / out-of-order uses of the incremental entry points fail loudly or are no-ops, as documented"""
+    import ctypes as C
+    pos, faces = mesh_case(30, True)
+    om = oracle_mod.OracleMesh(pos, faces)
+    V = om.V
+    mm = api.MeshMap(pos, faces)
+    L, ctx = mm.L, mm._ctx
+    ids = np.array([1, 2], np.uint32); vals = np.array([0.5, 0.25], np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    # before the planner inputs exist
+    assert L.mnb_update_vertex_costs(ctx, 2, p(ids), p(vals), 0, 0.0, 1.0) == -3                 # MNB_E_STATE
+    assert L.mnb_get_costs(ctx, None, None) == -3
+    assert L.mnb_inflation_vector_map(ctx, None) == -3 and L.mnb_set_repulsive_field(ctx, 1) == -3
+    assert L.mnb_set_repulsive_field(ctx, 0) == 0
+    ed = om.edge_distances(); vc = np.zeros(V, np.float32)
+    mm.setCosts(vc, ed)
+    # nothing changed / ids beyond V are ignored / duplicates are fine
+    assert L.mnb_update_vertex_costs(ctx, 0, None, None, 0, 0.0, 1.0) == 0
+    assert L.mnb_update_vertex_costs(ctx, 2, None, p(vals), 0, 0.0, 1.0) == -1                  # MNB_E_ARG
+    wild = np.array([5, V + 7, 5, 0xffffffff], np.uint32); wv = np.array([0.3, 9.0, 0.3, 9.0], np.float32)
+    mm.layerChanged(wild, wv, 2.0)
+    gvc, gw = mm.costs()
+    vc_ref = vc.copy(); vc_ref[5] = 0.3
+    w_ref = ed.copy(); om.update_edge_weights(vc_ref, ed, 2.0, np.array([5], np.uint32), w_ref)
+    assert (gvc.view(np.uint32) == vc_ref.view(np.uint32)).all() and (gw.view(np.uint32) == w_ref.view(np.uint32)).all()
+    # combination: layer count limits
+    lc = (C.c_void_p * 1)(p(vc)); df = np.zeros(9, np.float32); io = np.zeros(V, np.float32)
+    assert L.mnb_max_combination_update(ctx, 0, lc, p(df), None, 2, p(ids), p(io), None) == -1
+    assert L.mnb_max_combination_update(ctx, 9, lc, p(df), None, 2, p(ids), p(io), None) == -1
+    assert L.mnb_max_combination_update(ctx, 1, lc, p(df), None, 0, None, p(io), None) == 0
+    # an inflation without lethals labels nothing; its update set is whatever the previous wave had labelled
+    infl = api.InflationLayer(mm)
+    r0 = infl.onInputChanged(np.empty(0, np.uint32))
+    assert np.isnan(r0["cost"]).all() and np.isinf(r0["dist"]).all() and r0["changed"].size == 0
+    assert (infl.vectorMap() == 0).all()
+    le = np.array([100, 101, 130, V + 3], np.uint32)                                             # out-of-range lethal: ignored (:412)
+    r1 = infl.onInputChanged(le)
+    ref = om.inflation(ed, le[:3])
+    assert (r1["dist"].view(np.uint32) == ref["dist"].view(np.uint32)).all()
+    keys1 = np.where(~np.isnan(ref["cost"]))[0]
+    assert (r1["changed"] == keys1).all()
+    r2 = infl.onInputChanged(np.empty(0, np.uint32))
+    assert np.isnan(r2["cost"]).all() and (r2["changed"] == keys1).all()                         # the vanished entries are reported
+    mm.close()
