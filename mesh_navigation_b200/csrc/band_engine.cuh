@@ -18,7 +18,7 @@
 //     That vertex-local replay reproduces the sequential result including the
 //     non-causal "back-steps" of the CVP unfolding update; the
 //     CPU simulator of exactly this rule is bit-identical to the oracle on the
-//     10k / 1M meshes (tools/sim_band.cpp).
+//     10k / 1M meshes, and these very sources run on a CPU interpreter in the test-suite (tests/emu).
 //   * candidates within a sliding band [lo, lo+delta) of potentials are
 //     recomputed every round; everything whose tau lies strictly below the
 //     smallest tau that changed in the round is a converged prefix and leaves
