@@ -174,7 +174,7 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
                                 const double goal_dist_offset, const volatile int* cancel_flag,
                                 const float band_end_init, const uint32_t max_rounds) {
   float band_end_prev = band_end_init;  // > every seed potential: seeds are available from round 0
-  unsigned long long my_recomputes = 0, my_settled = 0;
+  unsigned long long my_recomputes = 0, my_settled = 0, my_skipped = 0;
   float lo_best = -1.0f; int stagnant = 0;       // best (largest) earliest-unsettled pop time seen so far
   prob.strict = 0;
   uint32_t r = 0;
@@ -204,6 +204,8 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
       atomicMin(&ctl->goal_ring[(r + 1) & 1], goal_b);                 // carry the cutoff into the next round
       ctl->stop_ring[(r + 1) & 1] = (stop || (cancel_flag && (r & 31) == 0 && *cancel_flag)) ? 1u : 0u;
     }
+    bool skip_ok = false;
+    if constexpr (P::CAN_SKIP) skip_ok = prob.skip_clean && !has_robot && !prob.strict && __float_as_uint(delta) == INF_BITS;
     float my_mtau = __uint_as_float(INF_BITS), my_lo = __uint_as_float(INF_BITS);
     for (unsigned int i = gtid; i < n; i += gthreads) {
       const uint32_t c = __ldcg(&list_r[i]);
@@ -228,8 +230,23 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
         continue;
       }
       float nd, ntau;
+      if constexpr (P::CAN_SKIP) if (skip_ok) {
+        // clean-candidate skip (see run_band_rounds_sub8): no source of c was re-labelled in or after the round of c's last
+        // evaluation -> same inputs, same label.  (delta = inf here: no source is ever excluded by the band end.)
+        const uint32_t le = __ldcg(&prob.last_eval[c]), dr = __ldcg(&prob.dirty_round[c]);
+        if (le != 0u && dr < le) {
+          my_lo = fminf(my_lo, tau); my_skipped++;
+          stage_push(st, c, list_n, &ctl->count[next]);
+          continue;
+        }
+      }
       my_recomputes++;
-      if (prob.recompute(c, band_end, goal, r, old, nd, ntau)) my_mtau = fminf(my_mtau, fminf(tau, ntau));
+      const bool changed = prob.recompute(c, band_end, goal, r, old, nd, ntau);
+      if (changed) my_mtau = fminf(my_mtau, fminf(tau, ntau));
+      if constexpr (P::CAN_SKIP) if (skip_ok) {
+        __stcg(&prob.last_eval[c], r + 1u);
+        if (changed) prob.activate(c, [&](uint32_t x) { __stcg(&prob.dirty_round[x], r + 1u); });
+      }
       my_lo = fminf(my_lo, ntau);      // smallest pop time still in flight: the band follows it
       stage_push(st, c, list_n, &ctl->count[next]);
       // a vertex that holds a finite label pulls its neighbours into the candidate set (once)
@@ -258,6 +275,7 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
   // statistics
   atomicAdd(&ctl->recomputes, my_recomputes);
   atomicAdd(&ctl->settled, my_settled);
+  if (my_skipped) atomicAdd(&ctl->skipped, my_skipped);
   if (gtid == 0) {
     ctl->rounds += r;
     if (prob.strict) ctl->strict_armed += 1;

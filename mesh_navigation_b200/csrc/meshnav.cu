@@ -73,6 +73,7 @@ struct mnb_ctx {
   // tuning
   float delta = 0.3f; int cluster = -1 /* -1: whole-grid cooperative kernel for single plans */; int batch_cluster = 1; int threads = 512;
   int grid_blocks_per_sm = 0;
+  int infl_skip_clean = 1;     // clean-candidate skip of the inflation wave (MNB_INFL_SKIP=0 turns it off)
   int layers_smem = 0;         // k_layers with the seen-set / stack in shared memory (MNB_LAYERS_SMEM=1, mnb_debug_set_layers_smem)
   int skip_clean = 0;          // clean-candidate skip of the CVP kernels (band_engine.cuh): bit-identical on the kernel interpreter,
                                // not yet timed on a B200 -> opt-in (MNB_SKIP_CLEAN=1 / mnb_debug_set_skip_clean)
@@ -139,6 +140,7 @@ int32_t mnb_create(int32_t device, mnb_ctx** out_ctx) {
   if (cudaSetDevice(device) != cudaSuccess) return MNB_E_CUDA;
   mnb_ctx* c = new mnb_ctx();
   c->device = device; c->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("MNB_INFL_SKIP")) c->infl_skip_clean = atoi(e) != 0;                                 // experiment knob
   if (const char* e = getenv("MNB_LAYERS_SMEM")) c->layers_smem = atoi(e) != 0;                                   // experiment knob
   if (const char* e = getenv("MNB_SKIP_CLEAN")) c->skip_clean = atoi(e) != 0;                                     // experiment knob
   if (const char* e = getenv("MNB_SWEEPS")) { const int k = atoi(e); if (k >= -1 && k <= 64) c->sweeps = k; }   // experiment knob
@@ -856,7 +858,7 @@ static int32_t inflate_impl(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, c
   a.params.cost_scaling_factor = params->cost_scaling_factor;
   a.out_dist = (dev && out_dist) ? out_dist : ctx->d_out_dist;
   a.out_cost = (dev && out_cost) ? out_cost : ctx->d_out_cost;
-  a.max_rounds = watchdog_rounds(ctx->V);
+  a.max_rounds = watchdog_rounds(ctx->V); a.skip_clean = ctx->infl_skip_clean;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   CK(launch_cooperative(k_inflate, a, (unsigned)ctx->sm_count, ctx->threads, ctx->stream));
   CK(cudaEventRecord(ctx->ev1, ctx->stream));

@@ -23,6 +23,7 @@ namespace mnb {
 // Times compare lexicographically.
 // ---------------------------------------------------------------------------
 struct CvpProblem {
+  static constexpr bool CAN_SKIP = false;   // (the 8-lane CvpEllProblemT carries its own switch)
   const uint32_t* __restrict__ cor_ptr;
   const int4* __restrict__ cor_idx;
   const float4* __restrict__ cor_w;
@@ -489,6 +490,8 @@ using CvpEllSkipProblem = CvpEllProblemT<true>;
 // Corner weights are edge_distances (:383), record {|v1v2|, |v1c|, |v2c|}.
 // ---------------------------------------------------------------------------
 struct InflationProblem {
+  static constexpr bool CAN_SKIP = true;    // clean-candidate skip in run_band_rounds (delta = inf, no goal cutoff)
+  uint32_t* last_eval; uint32_t* dirty_round; int skip_clean;
   const uint32_t* __restrict__ cor_ptr;
   const int4* __restrict__ cor_idx;
   const float4* __restrict__ cor_wd;
@@ -698,6 +701,7 @@ struct InflationProblem {
 //   adj_nw[k] = {neighbour id, float bits of the edge weight}
 // ---------------------------------------------------------------------------
 struct DijkstraProblem {
+  static constexpr bool CAN_SKIP = false;
   const uint32_t* __restrict__ adj_ptr;
   const uint2* __restrict__ adj_nw;
   const float* __restrict__ cost;
