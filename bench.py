@@ -424,8 +424,20 @@ def main():
             compared bit for bit.  Run last: nothing above depends on them."""
             import ctypes as C
             out = {}
-            for f in ("mnb_debug_set_skip_clean", "mnb_debug_set_layers_smem"):
+            for f in ("mnb_debug_set_skip_clean", "mnb_debug_set_layers_smem", "mnb_debug_set_infl_skip"):
                 getattr(mm.L, f).argtypes = [C.c_void_p, C.c_int32]
+            # the inflation wave's clean-candidate skip is ON by default: time it against the all-candidates-every-round loop
+            le = shared.get("lethals")
+            if le is not None:
+                res = {}
+                for on in (1, 0, 1, 0):
+                    mm.L.mnb_debug_set_infl_skip(mm._ctx, on)
+                    I = InflationLayer(mm).waveCostInflation(le)
+                    res[on] = (I["kernel_ms"], I["recomputes"], I["dist"])
+                mm.L.mnb_debug_set_infl_skip(mm._ctx, 1)
+                out["inflation_clean_candidate_skip"] = {
+                    "kernel_ms": res[1][0], "without_skip_kernel_ms": res[0][0], "recomputes": int(res[1][1]), "without_skip_recomputes": int(res[0][1]),
+                    "identical": bool((res[1][2].view(np.uint32) == res[0][2].view(np.uint32)).all())}
             mm.setCosts(vc, ed)
             base = planner.waveFrontPropagation(sf, sp)
             mm.L.mnb_debug_set_skip_clean(mm._ctx, 1)

@@ -818,6 +818,7 @@ int32_t mnb_locate(mnb_ctx* ctx, uint32_t n, const float* points, uint32_t* out_
 // experiment knob (not part of the public header): in-round sweeps of the whole-grid single-plan kernel
 int32_t mnb_debug_set_sweeps(mnb_ctx* ctx, int32_t k) { if (!ctx || k < -1 || k > 64) return MNB_E_ARG; ctx->sweeps = k; return MNB_OK; }
 
+int32_t mnb_debug_set_infl_skip(mnb_ctx* ctx, int32_t on) { if (!ctx) return MNB_E_ARG; ctx->infl_skip_clean = on != 0; return MNB_OK; }
 int32_t mnb_debug_set_layers_smem(mnb_ctx* ctx, int32_t on) { if (!ctx) return MNB_E_ARG; ctx->layers_smem = on != 0; return MNB_OK; }
 int32_t mnb_debug_set_skip_clean(mnb_ctx* ctx, int32_t on) { if (!ctx) return MNB_E_ARG; ctx->skip_clean = on != 0; return MNB_OK; }
 
