@@ -203,7 +203,7 @@ constexpr size_t STACK_BYTES = 256 * 1024;
 enum { F_RUNNABLE = 0, F_WAIT_WARP = 1, F_WAIT_CTA = 2, F_DONE = 3 };
 
 struct Fiber { void* sp; int tid; int state; unsigned wait_gen; };
-struct Warp { unsigned arrived, gen, alive; uint64_t slot[2][32]; };
+struct Warp { unsigned arrived, gen, alive; unsigned part[2]; uint64_t slot[2][32]; };   // part: lanes that took part in the collective of that buffer
 struct ProcBarrier { unsigned count, gen, n, pad; };
 struct LaunchCtl {                 // lives in the shared arena, one per forked launch
   ProcBarrier grid;
@@ -236,11 +236,13 @@ constexpr size_t DYN_SMEM_BYTES = 256 * 1024;
 
 static inline void yield_to_scheduler() { mnb_emu_switch(&g_cta.cur->sp, g_cta.sched_sp); }
 
-static inline void warp_complete(Warp& w) { w.arrived = 0; w.gen++; }
+static inline void warp_complete(Warp& w) { w.part[w.gen & 1u] = w.alive; w.arrived = 0; w.gen++; }
 
 // All lanes named by `mask` (minus lanes that already returned from the kernel) must call the same collective.
-// Returns the slot array holding every lane's contribution.
-static inline const uint64_t* warp_exchange(unsigned mask, uint64_t mine) {
+// Returns the slot array holding every lane's contribution; *part receives the lanes that took part (a lane may be resumed
+// long after the collective completed, when other lanes have already left the kernel: the live mask of THAT moment is the
+// wrong one to reduce over).
+static inline const uint64_t* warp_exchange(unsigned mask, uint64_t mine, unsigned* part = nullptr) {
   Fiber* f = g_cta.cur;
   const int lane = f->tid & 31;
   Warp& w = g_cta.warps[f->tid >> 5];
@@ -254,6 +256,7 @@ static inline const uint64_t* warp_exchange(unsigned mask, uint64_t mine) {
     f->state = F_WAIT_WARP; f->wait_gen = w.gen;
     yield_to_scheduler();
   }
+  if (part) *part = w.part[buf];
   return w.slot[buf];
 }
 
@@ -410,34 +413,36 @@ template <class T> static inline T __shfl_down_sync(unsigned mask, T v, unsigned
   return emu::from_u64<T>(s[src < (lane & ~(width - 1)) + width ? src : lane]);
 }
 static inline unsigned __ballot_sync(unsigned mask, int pred) {
-  const uint64_t* s = emu::warp_exchange(mask, pred ? 1u : 0u);
-  const unsigned alive = emu::g_cta.warps[emu::g_cta.cur->tid >> 5].alive;   // lanes that returned contribute 0
+  unsigned alive = 0;                                                        // lanes that returned before the vote contribute 0
+  const uint64_t* s = emu::warp_exchange(mask, pred ? 1u : 0u, &alive);
   unsigned r = 0;
   for (int l = 0; l < 32; ++l) if (((alive >> l) & 1u) && s[l]) r |= 1u << l;
   return r & mask;
 }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 static inline int __all_sync(unsigned mask, int pred) {
-  const unsigned alive = emu::g_cta.warps[emu::g_cta.cur->tid >> 5].alive;
-  return __ballot_sync(mask, pred) == (mask & alive);
+  unsigned alive = 0;
+  const uint64_t* s = emu::warp_exchange(mask, pred ? 1u : 0u, &alive);
+  for (int l = 0; l < 32; ++l) if (((alive >> l) & 1u) && !s[l]) return 0;
+  return 1;
 }
 static inline unsigned __reduce_min_sync(unsigned mask, unsigned v) {
-  const uint64_t* s = emu::warp_exchange(mask, v);
-  const unsigned alive = emu::g_cta.warps[emu::g_cta.cur->tid >> 5].alive;
+  unsigned alive = 0;
+  const uint64_t* s = emu::warp_exchange(mask, v, &alive);
   unsigned r = 0xffffffffu;
   for (int l = 0; l < 32; ++l) if ((alive >> l) & 1u) r = std::min(r, (unsigned)s[l]);
   return r;
 }
 static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
-  const uint64_t* s = emu::warp_exchange(mask, v);
-  const unsigned alive = emu::g_cta.warps[emu::g_cta.cur->tid >> 5].alive;
+  unsigned alive = 0;
+  const uint64_t* s = emu::warp_exchange(mask, v, &alive);
   unsigned r = 0;
   for (int l = 0; l < 32; ++l) if ((alive >> l) & 1u) r = std::max(r, (unsigned)s[l]);
   return r;
 }
 static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
-  const uint64_t* s = emu::warp_exchange(mask, v);
-  const unsigned alive = emu::g_cta.warps[emu::g_cta.cur->tid >> 5].alive;
+  unsigned alive = 0;
+  const uint64_t* s = emu::warp_exchange(mask, v, &alive);
   unsigned r = 0;
   for (int l = 0; l < 32; ++l) if ((alive >> l) & 1u) r += (unsigned)s[l];
   return r;

@@ -117,3 +117,16 @@ def test_smoke_entry_on_the_cpu_interpreter(emu_lib):
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600,
                        env=dict(os.environ, MNB_EMU_SMS="4"))
     assert r.returncode == 0 and "smoke ok" in r.stdout, (r.stdout + r.stderr)[-2000:]
+
+
+def test_interpreter_self_test(tmp_path):
+    """the interpreter's warp / block / grid primitives against the semantics the CUDA programming guide documents
+    (tests/emu/selftest/selftest.cu): segment shuffles, votes and reductions with exited lanes, 64-bit payloads, block
+    barriers with exited threads, a cooperative launch with grid barriers and global atomics across CTA processes"""
+    exe = str(tmp_path / "emu_selftest")
+    emu = os.path.join(ROOT, "tests", "emu")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-strict-aliasing", "-Wno-unknown-pragmas",
+                           "-Wno-attributes", f"-I{emu}", "-x", "c++", os.path.join(emu, "selftest", "selftest.cu"), "-o", exe])
+    for env in ({}, {"MNB_EMU_SHUFFLE": "5"}):
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=dict(os.environ, **env))
+        assert r.returncode == 0 and "interpreter self-test ok" in r.stdout, r.stdout + r.stderr
