@@ -161,11 +161,24 @@ void buildTopology(OrcMesh& m, const uint32_t* edges_in, uint32_t E_in) {
   };
   m.face_edges.resize(3 * (size_t)F);
   m.edge_faces.assign(2 * (size_t)m.E, -1);
-  for (uint32_t f = 0; f < F; ++f) {
-    const uint32_t* v = &m.faces[3 * (size_t)f];
+  {
+    // edge of every half-edge: sort the 3F (key, slot) pairs once and walk them against the sorted edge keys (same result
+    // as a find_edge() binary search per half-edge, several times faster on multi-million-vertex meshes)
+    std::vector<std::pair<uint64_t, uint32_t>> half(3 * (size_t)F);
+    for (uint32_t f = 0; f < F; ++f) {
+      const uint32_t* v = &m.faces[3 * (size_t)f];
+      for (int k = 0; k < 3; ++k) half[3 * (size_t)f + k] = {ekey(v[k], v[(k + 1) % 3]), 3 * f + (uint32_t)k};
+    }
+    std::sort(half.begin(), half.end());
+    size_t c = 0;
+    for (const auto& h : half) {
+      while (c < lut.size() && lut[c].first < h.first) ++c;
+      m.face_edges[h.second] = (c < lut.size() && lut[c].first == h.first) ? lut[c].second : find_edge(h.first >> 32, (uint32_t)h.first);
+    }
+  }
+  for (uint32_t f = 0; f < F; ++f) {            // faces in ascending id: the lower face id takes side 0 of an edge
     for (int k = 0; k < 3; ++k) {
-      uint32_t e = find_edge(v[k], v[(k + 1) % 3]);
-      m.face_edges[3 * (size_t)f + k] = e;
+      const uint32_t e = m.face_edges[3 * (size_t)f + k];
       if (m.edge_faces[2 * (size_t)e] < 0) m.edge_faces[2 * (size_t)e] = (int32_t)f;
       else m.edge_faces[2 * (size_t)e + 1] = (int32_t)f;
     }
