@@ -29,6 +29,16 @@ for skip in (0, 1, 0, 1):
     print(f"[single {n}x{n}] skip_clean={skip}: kernel {best:.2f} ms rounds {g['rounds']} recomputes/V {g['recomputes']/mm.V:.2f} "
           f"skipped/V {g['skipped']/mm.V:.2f} dist!=default {int((g['dist'].view(np.uint32) != ref.view(np.uint32)).sum())}", flush=True)
 mm.L.mnb_debug_set_skip_clean(mm._ctx, 0)
+# band width / in-round sweeps were tuned (1.8 m / 15) before the causal collapse made an evaluation cheaper: re-scan
+mm.L.mnb_debug_set_sweeps.argtypes = [C.c_void_p, C.c_int32]
+for (k, delta) in ((15, 1.8), (10, 1.2), (20, 2.4), (30, 3.6), (24, 1.8), (8, 1.8), (0, 0.3)):
+    mm.L.mnb_debug_set_sweeps(mm._ctx, k); mm.set_tuning(delta, 0, 0)
+    best = 1e9
+    for it in range(2):
+        g = pl.waveFrontPropagation(sf, sp); best = min(best, g['kernel_ms'])
+    print(f"[single {n}x{n}] sweeps={k} delta={delta}: kernel {best:.2f} ms rounds {g['rounds']} recomputes/V {g['recomputes']/mm.V:.2f} "
+          f"dist!=default {int((g['dist'].view(np.uint32) != ref.view(np.uint32)).sum())}", flush=True)
+mm.L.mnb_debug_set_sweeps(mm._ctx, -1); mm.set_tuning(1.8, 0, 0)
 for smem in (0, 1, 0, 1):
     mm.L.mnb_debug_set_layers_smem(mm._ctx, smem)
     for it in range(2):
@@ -77,4 +87,13 @@ for skip in (0, 1, 0, 1):
     if bref is None: bref = cur.copy()
     print(f"[batch 296 x 1M] skip_clean={skip}: {1e3*dt:.1f} ms -> {296/dt:.1f} plans/s, kernel {st['kernel_ms']:.1f} ms, recomputes/V {st['recomputes']/296/bm.V:.2f} "
           f"skipped/V {st['skipped']/296/bm.V:.2f} first 8 fields != default: {int((cur.view(np.uint32) != bref.view(np.uint32)).sum())}", flush=True)
+bm.L.mnb_debug_set_skip_clean(bm._ctx, 0)
+for delta in (0.2, 0.3, 0.45, 0.6):
+    bm.set_tuning(delta, 1, 0)
+    bm.use_device_pointers(True)
+    for rep in range(2):
+        t = time.perf_counter(); bm.cvp_batch_dev(sfs, sps, 1.0, out.data_ptr()); torch.cuda.synchronize(); dt = time.perf_counter() - t
+    bm.use_device_pointers(False)
+    st = bm.stats()
+    print(f"[batch 296 x 1M] delta={delta}: {1e3*dt:.1f} ms -> {296/dt:.1f} plans/s, recomputes/V {st['recomputes']/296/bm.V:.2f} rounds/plan {st['rounds']/296:.0f}", flush=True)
 bm.close()
