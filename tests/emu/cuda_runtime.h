@@ -23,6 +23,7 @@
 #include <sched.h>
 #include <signal.h>
 #include <sys/mman.h>
+#include <sys/prctl.h>
 #include <sys/wait.h>
 #include <unistd.h>
 
@@ -525,7 +526,11 @@ static inline cudaError_t launch(Kern kern, unsigned grid, unsigned block, size_
   bool failed = false;
   for (unsigned bx = 0; bx < grid && !failed; ++bx) {
     const pid_t pid = fork();
-    if (pid == 0) { run_cta(bx, grid, block, invoke, &ictx, lc, cluster > 1 ? cluster : 1); _exit(0); }
+    if (pid == 0) {
+      prctl(PR_SET_PDEATHSIG, SIGKILL);          // a CTA process must not outlive (and spin without) the test process
+      run_cta(bx, grid, block, invoke, &ictx, lc, cluster > 1 ? cluster : 1);
+      _exit(0);
+    }
     if (pid < 0) failed = true; else pids[bx] = pid;
   }
   if (failed) __atomic_store_n(&lc->abort_flag, 1, __ATOMIC_RELAXED);
