@@ -97,7 +97,11 @@ __global__ void __launch_bounds__(MNB_CVP_THREADS, MNB_CVP_MINBLOCKS) k_cvp(cons
     uint32_t* chg = a.ws.chg + (size_t)g * V;
     const int sweeps = 0;                            // in-round sweeps are compiled into the whole-grid kernel only
     uint32_t* last_eval = a.ws.last_eval + (size_t)g * V; uint32_t* dirty = a.ws.dirty + (size_t)g * V;
-    for (uint32_t v = gtid; v < V; v += gthreads) { state[v] = state_inf(); mark[v] = MARK_NONE; chg[v] = 0u; last_eval[v] = 0u; dirty[v] = 0u; if (sweeps) a.ws.ver[v] = 0u; }
+    for (uint32_t v = gtid; v < V; v += gthreads) {
+      state[v] = state_inf(); mark[v] = MARK_NONE; chg[v] = 0u;
+      if constexpr (SKIP) { last_eval[v] = 0u; dirty[v] = 0u; }
+      if (sweeps) a.ws.ver[v] = 0u;
+    }
     group_sync<CS>();
 
     const uint32_t sf = a.seed_faces[q];
@@ -178,7 +182,10 @@ __global__ void __launch_bounds__(512, MNB_GRID_MINBLOCKS) k_cvp_grid(const CvpK
   GroupCtl* ctl = a.ws.ctl;
   if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; sws.dn[0] = 0; sws.dn[1] = 0; }
   __syncthreads();
-  for (uint32_t v = gtid; v < V; v += gthreads) { state[v] = state_inf(); mark[v] = MARK_NONE; a.ws.chg[v] = 0u; a.ws.ver[v] = 0u; a.ws.last_eval[v] = 0u; a.ws.dirty[v] = 0u; }
+  for (uint32_t v = gtid; v < V; v += gthreads) {
+    state[v] = state_inf(); mark[v] = MARK_NONE; a.ws.chg[v] = 0u; a.ws.ver[v] = 0u;
+    if constexpr (SKIP) { a.ws.last_eval[v] = 0u; a.ws.dirty[v] = 0u; }
+  }
   group_sync<0>(ctl->barrier);
   const uint32_t sf = a.seed_faces[0];
   const uint32_t s0 = a.faces[3 * (size_t)sf], s1 = a.faces[3 * (size_t)sf + 1], s2 = a.faces[3 * (size_t)sf + 2];
