@@ -252,3 +252,33 @@ def test_repulsive_field_restatement(oracle_mod):
     rn = m.inflation(ed, np.uint32([0]), inflation_radius=0.1, with_vectors=True)     # v2 is never reached
     assert np.isinf(rn["dist"][2])
     assert (m.inflation_vector_at(np.uint32([0]), np.float32([[0.3, 0.3, 0.4]]), rn["dist"], rn["vectors"]) == 0).all()
+
+
+def test_dijkstra_against_an_independent_implementation(oracle_mod):
+    """the oracle's DijkstraMeshPlanner restatement against scipy.sparse.csgraph.dijkstra (float64, independent code) on
+    config 1 (10k planar mesh) and a cost-weighted terrain: same shortest-path distances up to float32 accumulation, and
+    the oracle's predecessor tree reproduces its own distances edge by edge"""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import dijkstra as sp_dijkstra
+    rng = np.random.default_rng(2)
+    for n, terrain, factor in ((100, False, 0.0), (80, True, 1.5)):
+        pos, faces = mesh_case(n, terrain)
+        m = oracle_mod.OracleMesh(pos, faces)
+        ed = m.edge_distances()
+        vc = (rng.random(m.V) * 0.8).astype(np.float32) if factor else np.zeros(m.V, np.float32)
+        w = m.edge_weights(vc, ed, factor)
+        v, f, sp = centre_seed(pos, faces, (0.25, 0.25))
+        r = m.dijkstra(w, vc, v, cost_limit=10.0)
+        e = m.edges.astype(np.int64)
+        g = coo_matrix((np.r_[w, w].astype(np.float64), (np.r_[e[:, 0], e[:, 1]], np.r_[e[:, 1], e[:, 0]])), shape=(m.V, m.V)).tocsr()
+        ref = sp_dijkstra(g, directed=False, indices=v)
+        assert np.isfinite(r["dist"]).all()
+        assert np.allclose(r["dist"], ref, rtol=2e-6, atol=1e-6)
+        # the predecessor tree is consistent: d[v] == fl(d[pred] + w(pred, v)) in float32, root = the seed
+        ekey = {(int(a), int(b)): i for i, (a, b) in enumerate(m.edges.tolist())}
+        p = r["pred"]
+        assert p[v] == v
+        idx = np.where(np.arange(m.V) != v)[0][::7]
+        for x in idx:
+            a, b = (int(p[x]), int(x)) if p[x] < x else (int(x), int(p[x]))
+            assert r["dist"][x] == np.float32(r["dist"][p[x]] + w[ekey[(a, b)]])
