@@ -191,7 +191,7 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
         (__float_as_uint(lo_prev) == INF_BITS || lo_prev > goal)) break;
     // stagnation watch (all values are group-uniform): labels keep changing but the earliest unsettled pop
     // time does not move -> a dependency cycle between a trigger and its back-step child; arm the strict rule
-    if (r > 0 && __float_as_uint(m_prev) != INF_BITS && !(lo_prev > lo_best)) { if (++stagnant >= STAGNATION_ROUNDS) prob.strict = 1; }
+    if (r > 0 && __float_as_uint(m_prev) != INF_BITS && !(lo_prev > lo_best)) { if (++stagnant >= P::STAGNATION) prob.strict = 1; }
     else { stagnant = 0; if (lo_prev > lo_best) lo_best = lo_prev; }
     float band_end = lo_prev + delta;
     if (!(band_end > band_end_prev)) band_end = band_end_prev;
@@ -205,7 +205,7 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
       ctl->stop_ring[(r + 1) & 1] = (stop || (cancel_flag && (r & 31) == 0 && *cancel_flag)) ? 1u : 0u;
     }
     bool skip_ok = false;
-    if constexpr (P::CAN_SKIP) skip_ok = prob.skip_clean && !has_robot && !prob.strict && __float_as_uint(delta) == INF_BITS;
+    if constexpr (P::CAN_SKIP) skip_ok = prob.skip_clean && !has_robot && (P::SKIP_IN_STRICT || !prob.strict) && __float_as_uint(delta) == INF_BITS;
     float my_mtau = __uint_as_float(INF_BITS), my_lo = __uint_as_float(INF_BITS);
     for (unsigned int i = gtid; i < n; i += gthreads) {
       const uint32_t c = __ldcg(&list_r[i]);
@@ -241,10 +241,11 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
         }
       }
       my_recomputes++;
+      if constexpr (P::CAN_SKIP) prob.deferred_flag = false;
       const bool changed = prob.recompute(c, band_end, goal, r, old, nd, ntau);
       if (changed) my_mtau = fminf(my_mtau, fminf(tau, ntau));
       if constexpr (P::CAN_SKIP) if (skip_ok) {
-        __stcg(&prob.last_eval[c], r + 1u);
+        __stcg(&prob.last_eval[c], prob.deferred_flag ? 0u : r + 1u);
         if (changed) prob.activate(c, [&](uint32_t x) { __stcg(&prob.dirty_round[x], r + 1u); });
       }
       my_lo = fminf(my_lo, ntau);      // smallest pop time still in flight: the band follows it

@@ -24,6 +24,7 @@ namespace mnb {
 // ---------------------------------------------------------------------------
 struct CvpProblem {
   static constexpr bool CAN_SKIP = false;   // (the 8-lane CvpEllProblemT carries its own switch)
+  static constexpr int STAGNATION = STAGNATION_ROUNDS;
   const uint32_t* __restrict__ cor_ptr;
   const int4* __restrict__ cor_idx;
   const float4* __restrict__ cor_w;
@@ -491,7 +492,17 @@ using CvpEllSkipProblem = CvpEllProblemT<true>;
 // ---------------------------------------------------------------------------
 struct InflationProblem {
   static constexpr bool CAN_SKIP = true;    // clean-candidate skip in run_band_rounds (delta = inf, no goal cutoff)
+  // The Sethian fallback produces trigger / back-step-child cycles on ordinary inputs (config 3: one pair oscillated for
+  // 27 of 41 rounds until the strict rule armed); the wave is only a few hops deep and every round is a grid barrier, so the
+  // strict rule is armed after 2 rounds without progress instead of the engine's 24 (strict rounds keep the clean-candidate
+  // skip, see SKIP_IN_STRICT, so arming early costs nothing).
+  static constexpr int STAGNATION = 2;
   uint32_t* last_eval; uint32_t* dirty_round; int skip_clean;
+  // In strict rounds a label also depends on the round number, but only through a deferral: an evaluation that deferred
+  // nothing rests on triggers that were stable, and a trigger that is re-labelled later marks its face neighbours dirty.
+  // So the skip stays valid in strict rounds as long as an evaluation that deferred is never remembered as "evaluated".
+  static constexpr bool SKIP_IN_STRICT = true;
+  mutable bool deferred_flag;
   const uint32_t* __restrict__ cor_ptr;
   const int4* __restrict__ cor_idx;
   const float4* __restrict__ cor_wd;
@@ -526,6 +537,7 @@ struct InflationProblem {
     if (!strict || X > T.a1) return true;
     if (__ldcg(&chg[Tv]) < round) return true;
     deferred_m = fminf(deferred_m, T.a1);
+    deferred_flag = true;                 // this evaluation depends on the round number: it must be repeated (clean skip)
     return false;
   }
   __device__ __forceinline__ bool eligible(uint32_t) const { return true; }   // no cost / validity test on the target
@@ -685,7 +697,7 @@ struct InflationProblem {
 
   __device__ __forceinline__ bool recompute(uint32_t c, float band_end, float /*goal*/, uint32_t round, const Label& old, float& nd, float& ntau) {
     EvTime tc; int win; float wu1, wu2;
-    if (strict || !replay_fast(c, band_end, nd, tc)) replay(c, band_end, round, nd, tc, win, wu1, wu2);
+    if (!replay_fast(c, band_end, nd, tc)) replay(c, band_end, round, nd, tc, win, wu1, wu2);   // (the collapse accepts no back-step: valid in strict rounds too)
     ntau = tc.a1;
     if (__float_as_uint(nd) == __float_as_uint(old.d) && ev_eq(tc, old.t)) return false;
     store_label(c, nd, tc, __float_as_uint(old.d) != INF_BITS, round);
@@ -702,6 +714,7 @@ struct InflationProblem {
 // ---------------------------------------------------------------------------
 struct DijkstraProblem {
   static constexpr bool CAN_SKIP = false;
+  static constexpr int STAGNATION = STAGNATION_ROUNDS;
   const uint32_t* __restrict__ adj_ptr;
   const uint2* __restrict__ adj_nw;
   const float* __restrict__ cost;
