@@ -79,6 +79,11 @@ struct GroupCtl {               // one per wavefront group, global memory
   unsigned int goal_ring[2];    // float bits, monotonically decreasing (atomicMin)
   unsigned int stop_ring[2];
   unsigned int goal_bits;       // final goal_dist, published after the last round
+  // pop time of the vertex that armed the cutoff (a1 bits, root, a2 bits, a3 bits, minor): a vertex beyond goal_dist that
+  // popped BEFORE that moment did expand in the reference (cvp:754 tests the goal_dist of the moment of the pop), which
+  // happens when the arming robot vertex is a cascade member that pops late with a small potential.  Written once by the
+  // thread that arms, read from the next round on.
+  unsigned int goal_time[5];
   int robot_left;               // robot-face vertices not yet settled
   unsigned int query;           // batch: query index owned by the group
   unsigned long long rounds, recomputes, settled;
@@ -185,6 +190,11 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
     const float lo_prev = __uint_as_float(__ldcg(&ctl->lo[prev]));
     const unsigned int goal_b = __ldcg(&ctl->goal_ring[r & 1]);
     const float goal = __uint_as_float(goal_b);
+    if constexpr (P::HAS_GOAL_TIME) if (has_robot && goal_b != INF_BITS) {
+      prob.goal_t.a1 = __uint_as_float(__ldcg(&ctl->goal_time[0])); prob.goal_t.root = __ldcg(&ctl->goal_time[1]);
+      prob.goal_t.a2 = __uint_as_float(__ldcg(&ctl->goal_time[2])); prob.goal_t.a3 = __uint_as_float(__ldcg(&ctl->goal_time[3]));
+      prob.goal_t.minor = __ldcg(&ctl->goal_time[4]);
+    }
     const unsigned int stop = __ldcg(&ctl->stop_ring[r & 1]);
     if (n == 0 || stop || r > max_rounds) break;   // r is group-uniform: the watchdog cannot deadlock the barrier
     if (r > 0 && __float_as_uint(m_prev) == INF_BITS &&
@@ -227,6 +237,8 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
               const Label so = prob.load_label(rv[k]);
               if (ev_less(bt, so.t)) { bt = so.t; bd = so.d; }
             }
+            ctl->goal_time[0] = __float_as_uint(bt.a1); ctl->goal_time[1] = bt.root; ctl->goal_time[2] = __float_as_uint(bt.a2);
+            ctl->goal_time[3] = __float_as_uint(bt.a3); ctl->goal_time[4] = bt.minor;
             atomicMin(&ctl->goal_ring[(r + 1) & 1], __float_as_uint((float)((double)bd + goal_dist_offset)));
           }
         }
@@ -315,6 +327,11 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
     const float lo_prev = __uint_as_float(__ldcg(&ctl->lo[prev]));
     const unsigned int goal_b = __ldcg(&ctl->goal_ring[r & 1]);
     const float goal = __uint_as_float(goal_b);
+    if constexpr (P::HAS_GOAL_TIME) if (has_robot && goal_b != INF_BITS) {
+      prob.goal_t.a1 = __uint_as_float(__ldcg(&ctl->goal_time[0])); prob.goal_t.root = __ldcg(&ctl->goal_time[1]);
+      prob.goal_t.a2 = __uint_as_float(__ldcg(&ctl->goal_time[2])); prob.goal_t.a3 = __uint_as_float(__ldcg(&ctl->goal_time[3]));
+      prob.goal_t.minor = __ldcg(&ctl->goal_time[4]);
+    }
     const unsigned int stop = __ldcg(&ctl->stop_ring[r & 1]);
     // the round in which the goal cutoff first becomes visible must run even if nothing else is left to do: it puts the
     // vertices that settled beyond the cutoff back into the list (see below)
@@ -472,7 +489,9 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
                 const Label so = prob.load_label(rv[k]);
                 if (ev_less(bt, so.t)) { bt = so.t; bd = so.d; }
               }
-              atomicMin(&ctl->goal_ring[(r + 1) & 1], __float_as_uint((float)((double)bd + goal_dist_offset)));
+              ctl->goal_time[0] = __float_as_uint(bt.a1); ctl->goal_time[1] = bt.root; ctl->goal_time[2] = __float_as_uint(bt.a2);
+            ctl->goal_time[3] = __float_as_uint(bt.a3); ctl->goal_time[4] = bt.minor;
+            atomicMin(&ctl->goal_ring[(r + 1) & 1], __float_as_uint((float)((double)bd + goal_dist_offset)));
             }
           }
         }

@@ -66,6 +66,7 @@ __device__ __forceinline__ void ctl_reset(GroupCtl* ctl, unsigned int n0, float 
   ctl->lo[0] = INF_BITS; ctl->lo[1] = INF_BITS; ctl->lo[2] = __float_as_uint(seed_min);
   ctl->goal_ring[0] = INF_BITS; ctl->goal_ring[1] = INF_BITS; ctl->stop_ring[0] = 0; ctl->stop_ring[1] = 0;
   ctl->goal_bits = INF_BITS; ctl->robot_left = 0;
+  ctl->goal_time[0] = INF_BITS; ctl->goal_time[1] = 0u; ctl->goal_time[2] = 0u; ctl->goal_time[3] = 0u; ctl->goal_time[4] = 0u;
 }
 
 #ifndef MNB_CVP_MINBLOCKS
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(MNB_CVP_THREADS, MNB_CVP_MINBLOCKS) k_cvp(cons
     prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_w = a.cor_w; prob.cost = a.cost; prob.invalid = a.invalid;
     prob.ell_idx = a.ell_idx; prob.ell_w = a.ell_w; prob.ell_geo = a.ell_geo;
     prob.state = state; prob.minor_arr = a.ws.minor + (size_t)g * V; prob.root_arr = a.ws.root + (size_t)g * V; prob.chg = chg; prob.ver = a.ws.ver; prob.deferred_m = __uint_as_float(INF_BITS); prob.pred = nullptr; prob.dir = nullptr; prob.cut = nullptr; prob.cost_limit = a.cost_limit;
-    prob.s0 = s0; prob.s1 = s1; prob.s2 = s2; prob.seed_noexpand = 0;
+    prob.s0 = s0; prob.s1 = s1; prob.s2 = s2; prob.seed_noexpand = 0; prob.goal_t = ev_normal(__uint_as_float(INF_BITS), 0u);
     prob.last_eval = last_eval; prob.dirty_round = dirty; prob.excl_min = a.ws.excl + (size_t)g * V; prob.skip_clean = SKIP ? 1 : 0; prob.prefetch_marks = false;
     float sd[3];
     {
@@ -149,6 +150,9 @@ __global__ void __launch_bounds__(MNB_CVP_THREADS, MNB_CVP_MINBLOCKS) k_cvp(cons
         ctl->robot_left = left;
         if (left == 0) {  // robot face == seed face: cutoff armed when the last seed pops (cvp:763-771)
           ctl->goal_ring[0] = __float_as_uint((float)((double)seed_max + a.goal_dist_offset));
+          uint32_t sl = sv[0]; float sdl = sd[0];
+          for (int k = 1; k < 3; ++k) if (sd[k] > sdl || (sd[k] == sdl && sv[k] > sl)) { sl = sv[k]; sdl = sd[k]; }
+          ctl->goal_time[0] = __float_as_uint(sdl); ctl->goal_time[1] = sl; ctl->goal_time[4] = 2u * sl;
         }
       }
     }
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(512, MNB_GRID_MINBLOCKS) k_cvp_grid(const CvpK
   prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_w = a.cor_w; prob.cost = a.cost; prob.invalid = a.invalid;
   prob.ell_idx = a.ell_idx; prob.ell_w = a.ell_w; prob.ell_geo = a.ell_geo;
   prob.state = state; prob.minor_arr = a.ws.minor; prob.root_arr = a.ws.root; prob.chg = a.ws.chg; prob.ver = a.ws.ver; prob.deferred_m = __uint_as_float(INF_BITS); prob.pred = nullptr; prob.dir = nullptr; prob.cut = nullptr; prob.cost_limit = a.cost_limit;
-  prob.s0 = s0; prob.s1 = s1; prob.s2 = s2; prob.seed_noexpand = 0;
+  prob.s0 = s0; prob.s1 = s1; prob.s2 = s2; prob.seed_noexpand = 0; prob.goal_t = ev_normal(__uint_as_float(INF_BITS), 0u);
   prob.last_eval = a.ws.last_eval; prob.dirty_round = a.ws.dirty; prob.excl_min = a.ws.excl; prob.skip_clean = SKIP ? 1 : 0; prob.prefetch_marks = true;
   float sd[3];
   {
@@ -227,7 +231,12 @@ __global__ void __launch_bounds__(512, MNB_GRID_MINBLOCKS) k_cvp_grid(const CvpK
       int left = 0; const uint32_t rv[3] = {r0, r1, r2};
       for (int k = 0; k < 3; ++k) if (mark[rv[k]] != MARK_FIXED) left++;
       ctl->robot_left = left;
-      if (left == 0) ctl->goal_ring[0] = __float_as_uint((float)((double)seed_max + a.goal_dist_offset));
+      if (left == 0) {
+        ctl->goal_ring[0] = __float_as_uint((float)((double)seed_max + a.goal_dist_offset));
+        uint32_t sl = sv[0]; float sdl = sd[0];
+        for (int k = 1; k < 3; ++k) if (sd[k] > sdl || (sd[k] == sdl && sv[k] > sl)) { sl = sv[k]; sdl = sd[k]; }
+        ctl->goal_time[0] = __float_as_uint(sdl); ctl->goal_time[1] = sl; ctl->goal_time[4] = 2u * sl;
+      }
     }
   }
   group_sync<0>(ctl->barrier);
@@ -254,6 +263,8 @@ __global__ void __launch_bounds__(256) k_cvp_epilogue(const CvpKernelArgs a, con
   prob.state = a.ws.state; prob.minor_arr = a.ws.minor; prob.root_arr = a.ws.root; prob.chg = a.ws.chg; prob.ver = nullptr; prob.deferred_m = __uint_as_float(INF_BITS); prob.pred = a.out_pred; prob.dir = a.out_dir; prob.cut = a.out_cut; prob.cost_limit = a.cost_limit;
   prob.s0 = a.faces[3 * (size_t)sf]; prob.s1 = a.faces[3 * (size_t)sf + 1]; prob.s2 = a.faces[3 * (size_t)sf + 2];
   prob.seed_noexpand = 0;
+  prob.goal_t.a1 = __uint_as_float(ctl->goal_time[0]); prob.goal_t.root = ctl->goal_time[1]; prob.goal_t.a2 = __uint_as_float(ctl->goal_time[2]);
+  prob.goal_t.a3 = __uint_as_float(ctl->goal_time[3]); prob.goal_t.minor = ctl->goal_time[4];
   {
     const uint32_t sv[3] = {prob.s0, prob.s1, prob.s2};
     for (int k = 0; k < 3; ++k)

@@ -24,6 +24,8 @@ namespace mnb {
 // ---------------------------------------------------------------------------
 struct CvpProblem {
   static constexpr bool CAN_SKIP = false;   // (the 8-lane CvpEllProblemT carries its own switch)
+  static constexpr bool HAS_GOAL_TIME = true;
+  EvTime goal_t;                            // pop time of the vertex that armed the goal cutoff (GroupCtl::goal_time); +inf: not armed
   static constexpr int STAGNATION = STAGNATION_ROUNDS;
   const uint32_t* __restrict__ cor_ptr;
   const int4* __restrict__ cor_idx;
@@ -115,7 +117,11 @@ struct CvpProblem {
     }
     const int il = v1_later ? i1 : i2;
     if (il >= 0 && ((seed_noexpand >> il) & 1u)) return false;
-    if ((v1_later ? a.d : b.d) > goal) return false;                       // cvp:754
+    {   // cvp:754: the popping vertex does not expand if it lies beyond goal_dist -- the goal_dist of the moment it pops:
+        // a vertex that popped before the cutoff was armed expanded whatever its potential
+      const Label& L = v1_later ? a : b;
+      if (L.d > goal && !ev_less(L.t, goal_t)) return false;
+    }
     T = v1_later ? a.t : b.t; Tv = v1_later ? v1 : v2;
     return true;
   }
@@ -491,6 +497,7 @@ using CvpEllSkipProblem = CvpEllProblemT<true>;
 // Corner weights are edge_distances (:383), record {|v1v2|, |v1c|, |v2c|}.
 // ---------------------------------------------------------------------------
 struct InflationProblem {
+  static constexpr bool HAS_GOAL_TIME = false;
   static constexpr bool CAN_SKIP = true;    // clean-candidate skip in run_band_rounds (delta = inf, no goal cutoff)
   // The Sethian fallback produces trigger / back-step-child cycles on ordinary inputs (config 3: one pair oscillated for
   // 27 of 41 rounds until the strict rule armed); the wave is only a few hops deep and every round is a grid barrier, so the
@@ -713,6 +720,7 @@ struct InflationProblem {
 //   adj_nw[k] = {neighbour id, float bits of the edge weight}
 // ---------------------------------------------------------------------------
 struct DijkstraProblem {
+  static constexpr bool HAS_GOAL_TIME = false;    // edge weights >= 0: vertices pop in potential order, the test on the value is exact
   static constexpr bool CAN_SKIP = false;
   static constexpr int STAGNATION = STAGNATION_ROUNDS;
   const uint32_t* __restrict__ adj_ptr;

@@ -361,3 +361,51 @@ def test_update_api_edge_cases(api, oracle_mod):
     r2 = infl.onInputChanged(np.empty(0, np.uint32))
     assert np.isnan(r2["cost"]).all() and (r2["changed"] == keys1).all()                         # the vanished entries are reported
     mm.close()
+
+
+def _fuzz_case(name):
+    import os
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", f"fuzz_{name}.npz"))
+    return (d["pos"], d["faces"], d["vc"], d["w"], d["inv"], int(d["sf"]), d["sp"], int(d["rf"]), float(d["cl"]))
+
+
+def test_goal_cutoff_armed_by_a_cascade_member(api, oracle_mod):
+    """found by tools/emu_fuzz.py (cost-weighted Delaunay mesh, invalid vertices, cost-limit walls): the robot-face vertex that
+    arms the goal cutoff is a cascade member -- it pops late with a small potential -- so vertices beyond goal_dist had
+    already popped AND expanded (cvp:754 tests the goal_dist of the moment of the pop).  A time-independent cutoff left 178
+    vertices unreached and reported NO_PATH_FOUND where the reference finds the path."""
+    pos, faces, vc, w, inv, sf, sp, rf, cl = _fuzz_case("cutoff_cascade")
+    om = oracle_mod.OracleMesh(pos, faces)
+    ref = om.cvp(w, vc, sf, sp, rf, invalid=inv, cost_limit=cl)
+    assert ref["outcome"] == 0 and ref["backsteps"] > 0
+    goal_dist = ref["dist"][faces[rf]].max() + 0.3
+    assert (ref["dist"][np.isfinite(ref["dist"])] > goal_dist + 1.0).any()      # labelled well beyond the cutoff: expanded before it was armed
+    mm = api.MeshMap(pos, faces)
+    mm.setCosts(vc, w, inv)
+    for cluster, delta in ((-1, 0.0), (1, 0.3), (4, 0.1)):
+        mm.set_tuning(delta, cluster, 0)
+        got = api.CVPMeshPlanner(mm, cost_limit=cl).waveFrontPropagation(sf, sp, rf)
+        assert got["outcome"] == 0
+        assert (got["dist"].view(np.uint32) == ref["dist"].view(np.uint32)).all(), (cluster, delta)
+        assert (got["pred"] == ref["pred"]).all() and (got["cutting_face"] == ref["cutting_face"]).all()
+    mm.close()
+
+
+@pytest.mark.xfail(strict=True, reason="KNOWN LIMIT (DESIGN.md 7): cascades nested deeper than the 3 tracked water levels -- pockets behind "
+                                       "cost-limit walls that are flooded 'from behind' by a chain of back-steps -- are ordered by "
+                                       "creation; a handful of potentials in the pocket come out 0.1-3 % high")
+@pytest.mark.parametrize("name", ["deep_cascade_planar", "deep_cascade_delaunay"])
+def test_deeply_nested_cascade(api, oracle_mod, name):
+    """found by tools/emu_fuzz.py; strict xfail: turns into a failure the day the engine orders deep cascades exactly"""
+    pos, faces, vc, w, inv, sf, sp, rf, cl = _fuzz_case(name)
+    om = oracle_mod.OracleMesh(pos, faces)
+    ref = om.cvp(w, vc, sf, sp, rf, invalid=inv, cost_limit=cl)
+    mm = api.MeshMap(pos, faces)
+    mm.setCosts(vc, w, inv)
+    got = api.CVPMeshPlanner(mm, cost_limit=cl).waveFrontPropagation(sf, sp, rf)
+    mm.close()
+    fin = np.isfinite(ref["dist"])
+    assert np.array_equal(np.isfinite(got["dist"]), fin)                      # same reached set even now
+    rel = np.abs(got["dist"][fin] - ref["dist"][fin]) / ref["dist"][fin]
+    assert (rel > 1e-4).sum() <= 8 and rel.max() < 0.05                       # the size of the known deviation
+    assert rel.max() <= 1e-4                                                  # the bar (north star): not met on these inputs

@@ -15,41 +15,46 @@ from tests.util import delaunay_mesh, disc_lethals
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+ONLY = int(sys.argv[3]) if len(sys.argv) > 3 else -1      # replay a single case of the stream
 bad = 0
 for case in range(N):
-    kind = rng.choice(["grid", "grid", "planar", "nojitter", "delaunay"])
+    crng = np.random.default_rng(rng.integers(1 << 62))
+    if ONLY >= 0 and case != ONLY:
+        continue
+    kind = crng.choice(["grid", "grid", "planar", "nojitter", "delaunay"])
     if kind == "delaunay":
-        pos, faces = delaunay_mesh(int(rng.integers(800, 4000)), seed=int(rng.integers(1 << 30)), with_hub=bool(rng.integers(2)))
+        pos, faces = delaunay_mesh(int(crng.integers(800, 4000)), seed=int(crng.integers(1 << 30)), with_hub=bool(crng.integers(2)))
     else:
-        n = int(rng.integers(24, 140))
-        pos, faces = synth.grid_mesh(n, n, terrain=kind == "grid", seed=int(rng.integers(1 << 30)), jitter=0.0 if kind == "nojitter" else 0.2)
+        n = int(crng.integers(24, 140))
+        pos, faces = synth.grid_mesh(n, n, terrain=kind == "grid", seed=int(crng.integers(1 << 30)), jitter=0.0 if kind == "nojitter" else 0.2)
     om = O.OracleMesh(pos, faces); mm = api.MeshMap(pos, faces); V = om.V
     ed = om.edge_distances()
-    cm = rng.integers(3)
-    vc = np.zeros(V, np.float32) if cm == 0 else ((rng.random(V) * rng.choice([0.5, 0.9, 1.3])).astype(np.float32) if cm == 1 else
-                                                  (np.round(rng.random(V) * 4) / 4 * 0.8).astype(np.float32))
-    factor = float(rng.choice([0.0, 1.0, 2.5])) if cm else 0.0
-    inv = (rng.random(V) < 0.01).astype(np.uint8) if rng.integers(3) == 0 else None
+    cm = crng.integers(3)
+    vc = np.zeros(V, np.float32) if cm == 0 else ((crng.random(V) * crng.choice([0.5, 0.9, 1.3])).astype(np.float32) if cm == 1 else
+                                                  (np.round(crng.random(V) * 4) / 4 * 0.8).astype(np.float32))
+    factor = float(crng.choice([0.0, 1.0, 2.5])) if cm else 0.0
+    inv = (crng.random(V) < 0.01).astype(np.uint8) if crng.integers(3) == 0 else None
     w = om.edge_weights(vc, ed, factor)
     mm.setCosts(vc, w, inv)
-    sf = int(rng.integers(om.F)); sp = pos[faces[sf]].mean(0).astype(np.float32)
-    rf = int(rng.integers(om.F)) if rng.integers(3) == 0 else -1
-    cl = float(rng.choice([1.0, 0.8, 5.0]))
-    cluster = int(rng.choice([-1, -1, 1, 2, 4]))
-    mm.set_tuning(float(rng.choice([0.3, 0.1, 1.8])) if cluster != -1 else 0.0, cluster, 0)
+    sf = int(crng.integers(om.F)); sp = pos[faces[sf]].mean(0).astype(np.float32)
+    rf = int(crng.integers(om.F)) if crng.integers(3) == 0 else -1
+    cl = float(crng.choice([1.0, 0.8, 5.0]))
+    cluster = int(crng.choice([-1, -1, 1, 2, 4]))
+    mm.set_tuning(float(crng.choice([0.3, 0.1, 1.8])) if cluster != -1 else 0.0, cluster, 0)
     msg = []
     ref = om.cvp(w, vc, sf, sp, rf, invalid=inv, cost_limit=cl)
     got = api.CVPMeshPlanner(mm, cost_limit=cl).waveFrontPropagation(sf, sp, rf)
     if got["outcome"] != ref["outcome"] or (got["dist"].view(np.uint32) != ref["dist"].view(np.uint32)).any() or (got["pred"] != ref["pred"]).any() \
             or (got["cutting_face"] != ref["cutting_face"]).any():
-        msg.append(f"CVP outcome {got['outcome']}/{ref['outcome']} dist!= {(got['dist'].view(np.uint32) != ref['dist'].view(np.uint32)).sum()} pred!= {(got['pred'] != ref['pred']).sum()}")
+        msg.append(f"CVP outcome {got['outcome']}/{ref['outcome']} dist!= {(got['dist'].view(np.uint32) != ref['dist'].view(np.uint32)).sum()} pred!= {(got['pred'] != ref['pred']).sum()} "
+                   f"cut!= {(got['cutting_face'] != ref['cutting_face']).sum()} at {np.where(got['cutting_face'] != ref['cutting_face'])[0][:4].tolist()}")
     sv = int(faces[sf][0]); rv = int(faces[rf][0]) if rf >= 0 else -1
     refd = om.dijkstra(w, vc, sv, rv, invalid=inv, cost_limit=cl)
     gotd = api.DijkstraMeshPlanner(mm, cost_limit=cl).dijkstra(sv, rv)
     if gotd["outcome"] != refd["outcome"] or (gotd["dist"].view(np.uint32) != refd["dist"].view(np.uint32)).any() or (gotd["pred"] != refd["pred"]).any():
         msg.append(f"Dijkstra outcome {gotd['outcome']}/{refd['outcome']} dist!= {(gotd['dist'].view(np.uint32) != refd['dist'].view(np.uint32)).sum()}")
-    le = disc_lethals(pos, int(rng.integers(1, 8)), float(rng.choice([0.15, 0.3])), seed=int(rng.integers(1 << 30)))
-    rad = float(rng.choice([0.4, 0.7, 1.1]))
+    le = disc_lethals(pos, int(crng.integers(1, 8)), float(crng.choice([0.15, 0.3])), seed=int(crng.integers(1 << 30)))
+    rad = float(crng.choice([0.4, 0.7, 1.1]))
     refi = om.inflation(ed, le, invalid=inv, inflation_radius=rad, with_vectors=True)
     il = api.InflationLayer(mm, inflation_radius=rad)
     goti = il.waveCostInflation(le, inv); vec = il.vectorMap()
