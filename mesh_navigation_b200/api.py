@@ -190,7 +190,7 @@ class MeshMap:
         s = _lib.Stats()
         self._check(self.L.mnb_get_stats(self._ctx, C.byref(s)))
         return dict(rounds=s.rounds, recomputes=s.recomputes, settled=s.settled, kernel_launches=s.kernel_launches,
-                    kernel_ms=s.kernel_ms, skipped=s.skipped)
+                    kernel_ms=s.kernel_ms, skipped=s.skipped, deep_labels=s.deep_labels)
 
     def cancel(self):
         self._check(self.L.mnb_cancel(self._ctx))

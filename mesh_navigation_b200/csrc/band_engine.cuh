@@ -84,6 +84,7 @@ struct GroupCtl {               // one per wavefront group, global memory
   // happens when the arming robot vertex is a cascade member that pops late with a small potential.  Written once by the
   // thread that arms, read from the next round on.
   unsigned int goal_time[5];
+  unsigned int deep_labels;     // k_cvp_epilogue: finite labels with overflowed cascade levels
   int robot_left;               // robot-face vertices not yet settled
   unsigned int query;           // batch: query index owned by the group
   unsigned long long rounds, recomputes, settled;

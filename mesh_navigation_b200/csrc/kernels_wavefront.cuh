@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(512, MNB_GRID_MINBLOCKS) k_cvp_grid(const CvpK
 // predecessors_ / direction_ / cutting_faces_ (cvp:423-431,493-517) from the FINAL labels: every vertex
 // replays its faces once more in event order and evaluates the winning face with the literal acos form.
 // Done after the wavefront so that the stored angles use the final source potentials.
-__global__ void __launch_bounds__(256) k_cvp_epilogue(const CvpKernelArgs a, const GroupCtl* ctl) {
+__global__ void __launch_bounds__(256) k_cvp_epilogue(const CvpKernelArgs a, GroupCtl* ctl) {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.V) return;
   const uint32_t sf = a.seed_faces[0];
@@ -270,7 +270,11 @@ __global__ void __launch_bounds__(256) k_cvp_epilogue(const CvpKernelArgs a, con
     for (int k = 0; k < 3; ++k)
       if (((double)a.cost[sv[k]] >= a.cost_limit) || (a.invalid && a.invalid[sv[k]])) prob.seed_noexpand |= (1u << k);
   }
-  const float d = __uint_as_float(a.ws.state[c].x);
+  const uint4 lw = a.ws.state[c];
+  const float d = __uint_as_float(lw.x);
+  // diagnostic: labels whose pop time needed more than the 3 tracked cascade levels (ordered by creation beyond that,
+  // DESIGN.md 7) -- reported in mnb_stats so that a caller can tell when the result may deviate in a flooded pocket
+  if (__float_as_uint(d) != INF_BITS && (lw.w >> 31)) atomicAdd(&ctl->deep_labels, 1u);
   if (prob.seed_index(c) >= 0) {                         // cvp:719-728
     a.out_pred[c] = c; a.out_dir[c] = 0.0f; a.out_cut[c] = (int32_t)sf;
     return;

@@ -457,7 +457,8 @@ static int32_t finish_stats(mnb_ctx* ctx, unsigned groups, unsigned launches) {
   CK(cudaMemcpyAsync(h.data(), ctx->ws.ctl, sizeof(GroupCtl) * groups, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->stats.rounds = 0; ctx->stats.recomputes = 0; ctx->stats.settled = 0;
-  ctx->stats.skipped = 0;
+  ctx->stats.skipped = 0; ctx->stats.deep_labels = 0;
+  for (auto& c : h) ctx->stats.deep_labels += c.deep_labels;
   for (auto& c : h) { ctx->stats.rounds += c.rounds; ctx->stats.recomputes += c.recomputes; ctx->stats.settled += c.settled; ctx->stats.skipped += c.skipped; }
   ctx->stats.kernel_launches = launches;
   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->stats.kernel_ms = ms;
