@@ -489,6 +489,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_cvp_grid", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm, "traffic": ncu_traffic(f"cvp_full_field_terrain_{n}x{n}"), "peak_source": which,
                          "kernel_ms": k_ms, "rounds": int(st["rounds"]), "recomputes_per_vertex": st["recomputes"] / V,
+                         "deep_cascade_labels": int(st.get("deep_labels", 0)),
                          "note": "single wavefront is dependency-latency bound (SURVEY.md H3)"},
             "clocks": clocks,
         }
