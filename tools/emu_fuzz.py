@@ -25,7 +25,7 @@ for case in range(N):
     if kind == "delaunay":
         pos, faces = delaunay_mesh(int(crng.integers(800, 4000)), seed=int(crng.integers(1 << 30)), with_hub=bool(crng.integers(2)))
     else:
-        n = int(crng.integers(24, 140))
+        n = int(crng.integers(24, int(os.environ.get("FUZZ_MAX_N", "140"))))
         pos, faces = synth.grid_mesh(n, n, terrain=kind == "grid", seed=int(crng.integers(1 << 30)), jitter=0.0 if kind == "nojitter" else 0.2)
     om = O.OracleMesh(pos, faces); mm = api.MeshMap(pos, faces); V = om.V
     ed = om.edge_distances()
