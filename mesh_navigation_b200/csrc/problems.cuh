@@ -499,16 +499,17 @@ using CvpEllSkipProblem = CvpEllProblemT<true>;
 struct InflationProblem {
   static constexpr bool HAS_GOAL_TIME = false;
   static constexpr bool CAN_SKIP = true;    // clean-candidate skip in run_band_rounds (delta = inf, no goal cutoff)
-  // The Sethian fallback produces trigger / back-step-child cycles on ordinary inputs (config 3: one pair oscillated for
-  // 27 of 41 rounds until the strict rule armed); the wave is only a few hops deep and every round is a grid barrier, so the
-  // strict rule is armed after 2 rounds without progress instead of the engine's 24 (strict rounds keep the clean-candidate
-  // skip, see SKIP_IN_STRICT, so arming early costs nothing).
-  static constexpr int STAGNATION = 2;
+  // The Sethian fallback produces trigger / back-step-child cycles on ordinary inputs (config 3: one pair oscillates for 27
+  // of 41 rounds until the strict rule arms).  Arming the rule earlier (2-4 stagnant rounds) halves the round count but is
+  // NOT neutral: on meshes with exact key ties (unjittered grids) the early strict rounds converge to a different label
+  // (fuzz seed 51 case 56, 1 vertex) -- so the engine's threshold stays, and the stagnant rounds are made cheap by the
+  // clean-candidate skip instead (only the oscillating pair is recomputed).
+  static constexpr int STAGNATION = STAGNATION_ROUNDS;
   uint32_t* last_eval; uint32_t* dirty_round; int skip_clean;
   // In strict rounds a label also depends on the round number, but only through a deferral: an evaluation that deferred
   // nothing rests on triggers that were stable, and a trigger that is re-labelled later marks its face neighbours dirty.
   // So the skip stays valid in strict rounds as long as an evaluation that deferred is never remembered as "evaluated".
-  static constexpr bool SKIP_IN_STRICT = true;
+  static constexpr bool SKIP_IN_STRICT = false;   // (kept off: strict rounds are rare and recompute everything, as they always did)
   mutable bool deferred_flag;
   const uint32_t* __restrict__ cor_ptr;
   const int4* __restrict__ cor_idx;

@@ -410,3 +410,20 @@ def test_deeply_nested_cascade(api, oracle_mod, name):
     rel = np.abs(got["dist"][fin] - ref["dist"][fin]) / ref["dist"][fin]
     assert (rel > 1e-4).sum() <= 8 and rel.max() < 0.05                       # the size of the known deviation
     assert rel.max() <= 1e-4                                                  # the bar (north star): not met on these inputs
+
+
+@pytest.mark.xfail(strict=False, reason="OPEN (found by tools/emu_fuzz.py seed 52 case 54, present in the B200-measured kernels): one vertex of the "
+                                       "inflation wave keeps 0.1304 where the reference accepts a back-step to 0.1142 from a face that fires "
+                                       "at 0.1154 -- 14 % off at that vertex, everything else identical")
+def test_inflation_backstep_open_case(api, oracle_mod):
+    import os
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "fuzz_inflation_backstep.npz"))
+    pos, faces, le, rad = d["pos"], d["faces"], d["le"], float(d["rad"])
+    om = oracle_mod.OracleMesh(pos, faces)
+    ref = om.inflation(om.edge_distances(), le, inflation_radius=rad)
+    mm = api.MeshMap(pos, faces)
+    got = api.InflationLayer(mm, inflation_radius=rad).waveCostInflation(le)
+    mm.close()
+    bad = np.where(got["dist"].view(np.uint32) != ref["dist"].view(np.uint32))[0]
+    assert bad.size <= 1
+    assert bad.size == 0
