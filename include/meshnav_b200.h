@@ -237,7 +237,8 @@ typedef struct mnb_stats {
   uint64_t kernel_launches; /* kernels launched by the last call */
   float kernel_ms;          /* CUDA-event time of the wavefront kernel(s) of the last call */
   uint64_t skipped;         /* candidate-rounds that kept their label without a recompute (clean-candidate skip) */
-  uint64_t deep_labels;     /* mnb_cvp: labels whose pop time overflowed the 3 tracked cascade levels (0 = exact order guaranteed; > 0: members beyond level 3 were ordered by creation, which is usually but not always harmless) */
+  uint64_t deep_labels;     /* mnb_cvp: labels whose pop time has more than 3 nested cascade levels (informational: the order is exact at any depth; their level stacks live in the per-wavefront level pool) */
+  uint64_t pool_words;      /* words of the level pool used by the last wavefront call (max over concurrent wavefronts) */
 } mnb_stats;
 int32_t mnb_get_stats(mnb_ctx* ctx, mnb_stats* out);
 /* tuning knobs: band width delta (metres) and CTAs per wavefront cluster (1,2,4,8,16) */

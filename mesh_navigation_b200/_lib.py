@@ -39,7 +39,7 @@ LAYER_NAMES = ["height_diff", "roughness", "steepness", "ridge", "clearance", "b
 
 class Stats(C.Structure):
     _fields_ = [("rounds", C.c_uint64), ("recomputes", C.c_uint64), ("settled", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("kernel_ms", C.c_float), ("skipped", C.c_uint64), ("deep_labels", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("kernel_ms", C.c_float), ("skipped", C.c_uint64), ("deep_labels", C.c_uint64), ("pool_words", C.c_uint64)]
 
 
 # every symbol include/meshnav_b200.h declares (checked by tests/test_abi.py)

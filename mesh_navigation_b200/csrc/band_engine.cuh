@@ -43,28 +43,238 @@ namespace cg = cooperative_groups;
 constexpr uint32_t INF_BITS = 0x7f800000u;
 constexpr int STAGNATION_ROUNDS = 24;
 
-// pop time of a vertex: monotonic stack of water levels a1 > a2 > a3 (0 = unused) + tie-break minor.
-// `root` orders labels that share the bit-identical first level a1 = K: a vertex that pops at its own key carries its
-// own id (the oracle's canonical heap order (key, id)); the members of a cascade carry the id of the cascade's root
-// trigger t, so that they pop after every (K, id < t), right after (K, t) itself (a2 == 0 sorts first) and before every
-// (K, id > t) -- float32 potentials collide millions of times on 10M-vertex meshes, and without `root` a cascade under a
-// tied key was ordered after ALL plain labels of that key.
-struct EvTime { float a1, a2, a3; uint32_t minor, root; };
-__device__ __forceinline__ bool ev_less(const EvTime& x, const EvTime& y) {
-  if (x.a1 != y.a1) return x.a1 < y.a1;
-  if (x.root != y.root) return x.root < y.root;
-  if (x.a2 != y.a2) return x.a2 < y.a2;
-  if (x.a3 != y.a3) return x.a3 < y.a3;
-  return x.minor < y.minor;
-}
-__device__ __forceinline__ bool ev_eq(const EvTime& x, const EvTime& y) {
-  return __float_as_uint(x.a1) == __float_as_uint(y.a1) && __float_as_uint(x.a2) == __float_as_uint(y.a2) &&
-         __float_as_uint(x.a3) == __float_as_uint(y.a3) && x.minor == y.minor && x.root == y.root;
-}
-__device__ __forceinline__ EvTime ev_normal(float key, uint32_t id) { EvTime t; t.a1 = key; t.a2 = 0.0f; t.a3 = 0.0f; t.minor = 2u * id; t.root = id; return t; }
-// per-vertex label: one 16-byte word {d, a1, a2 | root flag, a3 | minor flag}; flagged roots / minors live in side arrays
+// Pop time of a vertex = the moment the sequential algorithm pops it, written as the stack of canonical heap keys
+// (key, vertex id) that were running maxima of the pop sequence at that moment ("water levels"):
+//     L1 > L2 > ... > Ln,   Ln = the vertex's own (key, id).
+// A vertex that pops at its own key has n = 1 (the oracle's canonical heap order).  A non-causal "back-step" label
+// (X, c) <= the pop time F of the face that hands it out is popped inside the cascade that runs below the water line:
+// it keeps the levels of F that are > (X, c) and appends (X, c) (problems.cuh, TimeAlg::accept).  Times compare
+// lexicographically, a proper prefix first (a trigger pops before the members of its cascade).  Cascades nest to any
+// depth; the representation is exact for all of them:
+//   * levels 1-3 keys live in the 16-byte label word {d, a1, a2, a3} (0 = level absent; pop keys are > 0 below level 1);
+//   * the id of level 1 ("root") lives in a side array when it differs from the vertex (sign bit of the a2 word);
+//   * n == 3: the id of level 2 is the side word `ext`;  n >= 4: ext = EXT_POOL | offset of a record
+//     [n, id2, id3, key4, id4, ..., keyn, idn] in the per-wavefront level pool (sign bit of the a3 word = "ext valid").
+// float32 potentials collide millions of times on 10M-vertex meshes, hence the ids at every level: without them a
+// cascade under a tied key was ordered after ALL plain labels of that key.
+constexpr uint32_t EXT_POOL = 0x80000000u;
+struct EvTime { float a1, a2, a3; uint32_t root, ext, self; };
+__device__ __forceinline__ EvTime ev_normal(float key, uint32_t id) { EvTime t; t.a1 = key; t.a2 = 0.0f; t.a3 = 0.0f; t.root = id; t.ext = 0u; t.self = id; return t; }
+// per-vertex label: one 16-byte word {d, a1, a2 | root flag, a3 | ext flag}
 struct Label { float d; EvTime t; };
 __device__ __forceinline__ uint4 state_inf() { return make_uint4(INF_BITS, INF_BITS, 0u, 0u); }
+
+// Comparison of pop times.  `pool` is the level pool of the wavefront (only dereferenced when two times tie through a
+// level whose id or key lives there -- never on the hot path).
+struct TimeAlg {
+  const uint32_t* pool = nullptr;
+  __device__ __forceinline__ uint32_t id2_of(const EvTime& t) const {      // id of level 2 (level 2 must exist)
+    return t.a3 == 0.0f ? t.self : ((t.ext & EXT_POOL) ? __ldcg(&pool[(t.ext & ~EXT_POOL) + 1]) : t.ext);
+  }
+  __device__ __forceinline__ uint32_t id3_of(const EvTime& t) const {      // id of level 3 (level 3 must exist)
+    return (t.ext & EXT_POOL) ? __ldcg(&pool[(t.ext & ~EXT_POOL) + 2]) : t.self;
+  }
+  __device__ __forceinline__ uint32_t levels_of(const EvTime& t) const {
+    return t.a2 == 0.0f ? 1u : (t.a3 == 0.0f ? 2u : ((t.ext & EXT_POOL) ? __ldcg(&pool[t.ext & ~EXT_POOL]) : 3u));
+  }
+  // levels 2.. tie on the key of level 2 (rare: same cascade, bit-identical keys or the same sub-trigger)
+  __device__ __noinline__ bool less_tail(const EvTime& x, const EvTime& y) const {
+    const uint32_t i2x = id2_of(x), i2y = id2_of(y);
+    if (i2x != i2y) return i2x < i2y;
+    if (x.a3 != y.a3) return x.a3 < y.a3;
+    if (x.a3 == 0.0f) return false;                                 // the same vertex
+    const uint32_t i3x = id3_of(x), i3y = id3_of(y);
+    if (i3x != i3y) return i3x < i3y;
+    const uint32_t nx = levels_of(x), ny = levels_of(y);
+    const uint32_t ox = x.ext & ~EXT_POOL, oy = y.ext & ~EXT_POOL;
+    for (uint32_t i = 4;; ++i) {
+      if (i > nx) return i <= ny;                                   // x is a prefix of y (or the same time)
+      if (i > ny) return false;
+      const uint32_t kx = __ldcg(&pool[ox + 3 + 2 * (i - 4)]), ky = __ldcg(&pool[oy + 3 + 2 * (i - 4)]);
+      if (kx != ky) return kx < ky;                                 // keys are > 0: bit order = value order
+      const uint32_t ix = __ldcg(&pool[ox + 4 + 2 * (i - 4)]), iy = __ldcg(&pool[oy + 4 + 2 * (i - 4)]);
+      if (ix != iy) return ix < iy;
+    }
+  }
+  __device__ __forceinline__ bool tless(const EvTime& x, const EvTime& y) const {
+    if (x.a1 != y.a1) return x.a1 < y.a1;
+    if (x.root != y.root) return x.root < y.root;
+    if (x.a2 != y.a2) return x.a2 < y.a2;                           // 0 = no level 2: a prefix sorts first
+    if (x.a2 == 0.0f) return false;                                 // both are the vertex (a1, root) itself
+    return less_tail(x, y);
+  }
+  __device__ __noinline__ bool eq_pool(const EvTime& x, const EvTime& y) const {
+    if (!(x.ext & y.ext & EXT_POOL)) return false;
+    const uint32_t ox = x.ext & ~EXT_POOL, oy = y.ext & ~EXT_POOL;
+    if (ox == oy) return true;
+    const uint32_t n = __ldcg(&pool[ox]);
+    if (n != __ldcg(&pool[oy])) return false;
+    for (uint32_t i = 1; i < 3 + 2 * (n - 3); ++i) if (__ldcg(&pool[ox + i]) != __ldcg(&pool[oy + i])) return false;
+    return true;
+  }
+  __device__ __forceinline__ bool teq(const EvTime& x, const EvTime& y) const {
+    if (__float_as_uint(x.a1) != __float_as_uint(y.a1) || __float_as_uint(x.a2) != __float_as_uint(y.a2) ||
+        __float_as_uint(x.a3) != __float_as_uint(y.a3) || x.root != y.root || x.self != y.self) return false;
+    if ((x.ext | y.ext) & EXT_POOL) return eq_pool(x, y);
+    return x.ext == y.ext;
+  }
+};
+
+// A pop time under construction (the serial replays of problems.cuh): either a plain EvTime (n <= 3: `t` is complete) or,
+// for n >= 4, a VIRTUAL stack -- levels 1-3 in t.{a1,root,a2,a3} + id2/id3, levels 4..n-1 taken from the pool record
+// `src` of the trigger it was derived from, level n = (last, t.self).  Only a label that really changed is written to
+// the pool (LabelStore::finish), so recomputing a deep label over and over allocates nothing.
+struct EvFull { EvTime t; uint32_t id2, id3, n, src; float last; };
+
+// Labels in global memory + the level pool (shared by the CVP and inflation problems)
+struct LabelStore : TimeAlg {
+  uint4* state;                         // {d bits, a1 bits, a2 bits | root flag, a3 bits | ext flag}
+  uint32_t* root_arr;                   // id of level 1 where it differs from the vertex (cascade members)
+  uint32_t* ext_arr;                    // n == 3: id of level 2;  n >= 4: EXT_POOL | pool offset
+  uint32_t* chg;                        // 1 + round of the last RE-label of a vertex (0 = never)
+  uint32_t* pool_w;                     // == pool (writable)
+  unsigned int* pool_top; unsigned int* pool_overflow; uint32_t pool_cap;
+
+  // decoding of the 16-byte label word: sign bit of .z = "level-1 id differs from the vertex, see root_arr",
+  // sign bit of .w = "ext_arr valid" (pop-time levels are >= 0, so both bits are free)
+  __device__ __forceinline__ Label unpack_label(uint32_t v, const uint4& s) const {
+    Label l; l.d = __uint_as_float(s.x); l.t.a1 = __uint_as_float(s.y); l.t.a2 = __uint_as_float(s.z & 0x7fffffffu);
+    l.t.a3 = __uint_as_float(s.w & 0x7fffffffu);
+    l.t.root = (s.z >> 31) ? __ldcg(&root_arr[v]) : v;
+    l.t.ext = (s.w >> 31) ? __ldcg(&ext_arr[v]) : 0u;
+    l.t.self = v;
+    return l;
+  }
+  __device__ __forceinline__ Label load_label(uint32_t v) const { return unpack_label(v, __ldcg(&state[v])); }
+  // the 16-byte word of a label as store_label() writes it
+  __device__ __forceinline__ uint4 pack_label(uint32_t c, float d, const EvTime& t) const {
+    uint32_t z = __float_as_uint(t.a2), w = __float_as_uint(t.a3);
+    if (t.root != c) z |= 0x80000000u;
+    if (t.a3 != 0.0f) w |= 0x80000000u;
+    return make_uint4(__float_as_uint(d), __float_as_uint(t.a1), z, w);
+  }
+  __device__ __forceinline__ void store_label(uint32_t c, float d, const EvTime& t, bool relabel, uint32_t round) const {
+    if (t.root != c) __stcg(&root_arr[c], t.root);
+    if (t.a3 != 0.0f) __stcg(&ext_arr[c], t.ext);
+    if (relabel) __stcg(&chg[c], round + 1u);
+    __stcg(&state[c], pack_label(c, d, t));
+  }
+
+  // (key bits, id) of level i of a materialised time
+  __device__ __forceinline__ void level_of(const EvTime& T, uint32_t i, uint32_t& kb, uint32_t& id) const {
+    if (i == 1) { kb = __float_as_uint(T.a1); id = T.root; }
+    else if (i == 2) { kb = __float_as_uint(T.a2); id = id2_of(T); }
+    else if (i == 3) { kb = __float_as_uint(T.a3); id = id3_of(T); }
+    else { const uint32_t o = (T.ext & ~EXT_POOL) + 3 + 2 * (i - 4); kb = __ldcg(&pool[o]); id = __ldcg(&pool[o + 1]); }
+  }
+  // Does the stack of T hold a level of vertex c?  Then T pops inside a cascade that c started, i.e. AFTER c: a face with
+  // that pop time cannot update c.  In a consistent state the time comparison says the same; while labels are still
+  // moving, T may rest on a former label of c (a "ghost" level), and accepting its back-step would let c and T support
+  // each other -- a stable fixed point of the pull iteration that the sequential order does not have (found by the
+  // randomised tests as soon as the stacks were exact).  Such a face does not fire; T itself is re-evaluated because its
+  // source c changed.
+  __device__ __noinline__ bool names_slow(const EvTime& T, uint32_t c) const {
+    if (T.root == c || id2_of(T) == c) return true;
+    if (T.a3 == 0.0f) return false;
+    if (id3_of(T) == c) return true;
+    const uint32_t n = levels_of(T);
+    for (uint32_t i = 4; i <= n; ++i) { uint32_t kb, id; level_of(T, i, kb, id); if (id == c) return true; }
+    return false;
+  }
+  __device__ __forceinline__ bool names(const EvTime& T, uint32_t c) const { return T.a2 != 0.0f && names_slow(T, c); }
+  // One accepted update with value X from a face that fired at time F: c enters the heap with key (X, c) at that moment
+  // and pops once everything smaller has popped -- its pop time keeps the levels of F that are > (X, c) and appends (X, c).
+  // X == F.a1 exactly: c pops in (key, id) order among the vertices of that key that are still queued -- as a plain label
+  // if its id is above the root's, else inside the cascade.
+  // Lean form: returns false (t untouched) if the result needs more than 3 levels.
+  __device__ __forceinline__ bool accept_lean(uint32_t c, float X, const EvTime& F, EvTime& t) const {
+    if (X > F.a1 || (X == F.a1 && c > F.root)) { t = ev_normal(X, c); return true; }        // above water: pops at its own key
+    if (F.a2 == 0.0f) { t = F; t.a2 = X; t.self = c; t.ext = 0u; return true; }             // first level of F's cascade
+    const uint32_t i2 = id2_of(F);
+    if (X > F.a2 || (X == F.a2 && c > i2)) { t.a1 = F.a1; t.root = F.root; t.a2 = X; t.a3 = 0.0f; t.ext = 0u; t.self = c; return true; }
+    if (F.a3 != 0.0f) {
+      const uint32_t i3 = id3_of(F);
+      if (!(X > F.a3 || (X == F.a3 && c > i3))) return false;                               // a fourth level (or more)
+    }
+    t.a1 = F.a1; t.root = F.root; t.a2 = F.a2; t.a3 = X; t.ext = i2; t.self = c;
+    return true;
+  }
+  __device__ __noinline__ void accept_deep(uint32_t c, float X, const EvTime& F, EvFull& o) const {
+    const uint32_t nF = levels_of(F), xb = __float_as_uint(X);
+    uint32_t k = 3;                                     // (accept_lean has established that levels 1-3 of F stay)
+    for (uint32_t i = 4; i <= nF; ++i) {
+      uint32_t kb, id; level_of(F, i, kb, id);
+      if (kb > xb || (kb == xb && id > c)) k = i; else break;
+    }
+    o.t.a1 = F.a1; o.t.root = F.root; o.t.a2 = F.a2; o.t.a3 = F.a3; o.t.ext = 0u; o.t.self = c;
+    o.id2 = id2_of(F); o.id3 = id3_of(F); o.n = k + 1; o.src = F.ext & ~EXT_POOL; o.last = X;
+  }
+  __device__ __forceinline__ void accept(uint32_t c, float X, const EvTime& F, EvFull& o) const {
+    if (accept_lean(c, X, F, o.t)) o.n = 1u;            // (any value <= 3: `t` is complete)
+    else accept_deep(c, X, F, o);
+  }
+  __device__ __forceinline__ static EvFull full_normal(float key, uint32_t c) { EvFull f; f.t = ev_normal(key, c); f.id2 = c; f.id3 = c; f.n = 1u; f.src = 0u; f.last = 0.0f; return f; }
+  // (key bits, id) of level i >= 4 of a virtual time
+  __device__ __forceinline__ void vlevel_of(const EvFull& x, uint32_t i, uint32_t& kb, uint32_t& id) const {
+    if (i == x.n) { kb = __float_as_uint(x.last); id = x.t.self; }
+    else { const uint32_t o = x.src + 3 + 2 * (i - 4); kb = __ldcg(&pool[o]); id = __ldcg(&pool[o + 1]); }
+  }
+  __device__ __noinline__ bool less_T_deep(const EvTime& T, const EvFull& x) const {
+    if (T.a1 != x.t.a1) return T.a1 < x.t.a1;
+    if (T.root != x.t.root) return T.root < x.t.root;
+    if (T.a2 == 0.0f) return true;                      // T is a proper prefix of x
+    if (T.a2 != x.t.a2) return T.a2 < x.t.a2;
+    const uint32_t i2 = id2_of(T);
+    if (i2 != x.id2) return i2 < x.id2;
+    if (T.a3 == 0.0f) return true;
+    if (T.a3 != x.t.a3) return T.a3 < x.t.a3;
+    const uint32_t i3 = id3_of(T);
+    if (i3 != x.id3) return i3 < x.id3;
+    const uint32_t nT = levels_of(T);
+    for (uint32_t i = 4;; ++i) {
+      if (i > x.n) return false;                        // x ended: x is a prefix of T (or the same time)
+      if (i > nT) return true;
+      uint32_t kt, it, kx, ixx; level_of(T, i, kt, it); vlevel_of(x, i, kx, ixx);
+      if (kt != kx) return kt < kx;
+      if (it != ixx) return it < ixx;
+    }
+  }
+  // is the materialised time T earlier than the time x under construction?
+  __device__ __forceinline__ bool less_T_full(const EvTime& T, const EvFull& x) const {
+    return x.n <= 3u ? tless(T, x.t) : less_T_deep(T, x);
+  }
+  __device__ __noinline__ bool eq_deep(const EvFull& x, const EvTime& T) const {
+    if (__float_as_uint(T.a1) != __float_as_uint(x.t.a1) || __float_as_uint(T.a2) != __float_as_uint(x.t.a2) ||
+        __float_as_uint(T.a3) != __float_as_uint(x.t.a3) || T.root != x.t.root || T.self != x.t.self || !(T.ext & EXT_POOL)) return false;
+    if (levels_of(T) != x.n || id2_of(T) != x.id2 || id3_of(T) != x.id3) return false;
+    for (uint32_t i = 4; i <= x.n; ++i) {
+      uint32_t kt, it, kx, ixx; level_of(T, i, kt, it); vlevel_of(x, i, kx, ixx);
+      if (kt != kx || it != ixx) return false;
+    }
+    return true;
+  }
+  __device__ __noinline__ EvTime materialise(const EvFull& x) const {
+    EvTime t = x.t;
+    const uint32_t need = 3u + 2u * (x.n - 3u);
+    const uint32_t off = atomicAdd(pool_top, need);
+    if (off + need > pool_cap || off + need < off) {    // pool exhausted: reported by the host as an error (no silent inexact result)
+      *pool_overflow = 1u;
+      t.ext = x.id2;                                    // (a well-formed 3-level time so that the wave still terminates)
+      return t;
+    }
+    pool_w[off] = x.n; pool_w[off + 1] = x.id2; pool_w[off + 2] = x.id3;
+    for (uint32_t i = 4; i <= x.n; ++i) { uint32_t kb, id; vlevel_of(x, i, kb, id); pool_w[off + 3 + 2 * (i - 4)] = kb; pool_w[off + 4 + 2 * (i - 4)] = id; }
+    __threadfence();                                    // the record before the label word that points to it
+    t.ext = EXT_POOL | off;
+    return t;
+  }
+  // the label time to store for c: the old one if nothing changed (no allocation), a fresh pool record otherwise
+  __device__ __forceinline__ EvTime finish(const EvFull& x, const EvTime& old_t) const {
+    if (x.n <= 3u) return x.t;
+    if (eq_deep(x, old_t)) return old_t;
+    return materialise(x);
+  }
+};
 
 // mark[] values
 constexpr uint32_t MARK_NONE = 0, MARK_CAND = 1, MARK_FIXED = 2, MARK_CAND_ACT = 3;
@@ -79,12 +289,14 @@ struct GroupCtl {               // one per wavefront group, global memory
   unsigned int goal_ring[2];    // float bits, monotonically decreasing (atomicMin)
   unsigned int stop_ring[2];
   unsigned int goal_bits;       // final goal_dist, published after the last round
-  // pop time of the vertex that armed the cutoff (a1 bits, root, a2 bits, a3 bits, minor): a vertex beyond goal_dist that
+  // pop time of the vertex that armed the cutoff (a1 bits, root, a2 bits, a3 bits, ext, vertex): a vertex beyond goal_dist that
   // popped BEFORE that moment did expand in the reference (cvp:754 tests the goal_dist of the moment of the pop), which
   // happens when the arming robot vertex is a cascade member that pops late with a small potential.  Written once by the
   // thread that arms, read from the next round on.
-  unsigned int goal_time[5];
-  unsigned int deep_labels;     // k_cvp_epilogue: finite labels with overflowed cascade levels
+  unsigned int goal_time[6];
+  unsigned int deep_labels;     // k_cvp_epilogue: finite labels whose pop time has more than 3 cascade levels (exact; informational)
+  unsigned int pool_top;        // bump allocator of the level pool (words)
+  unsigned int pool_overflow;   // a deep label did not fit into the level pool: reported as an error by the host
   int robot_left;               // robot-face vertices not yet settled
   unsigned int query;           // batch: query index owned by the group
   unsigned long long rounds, recomputes, settled;
@@ -194,7 +406,7 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
     if constexpr (P::HAS_GOAL_TIME) if (has_robot && goal_b != INF_BITS) {
       prob.goal_t.a1 = __uint_as_float(__ldcg(&ctl->goal_time[0])); prob.goal_t.root = __ldcg(&ctl->goal_time[1]);
       prob.goal_t.a2 = __uint_as_float(__ldcg(&ctl->goal_time[2])); prob.goal_t.a3 = __uint_as_float(__ldcg(&ctl->goal_time[3]));
-      prob.goal_t.minor = __ldcg(&ctl->goal_time[4]);
+      prob.goal_t.ext = __ldcg(&ctl->goal_time[4]); prob.goal_t.self = __ldcg(&ctl->goal_time[5]);
     }
     const unsigned int stop = __ldcg(&ctl->stop_ring[r & 1]);
     if (n == 0 || stop || r > max_rounds) break;   // r is group-uniform: the watchdog cannot deadlock the barrier
@@ -231,15 +443,15 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
         my_settled++;
         if (has_robot && (c == r0 || c == r1 || c == r2)) {
           if (atomicSub(&ctl->robot_left, 1) == 1) {
-            // c is not necessarily the last of the three in event order: take the latest (tau,minor)
+            // c is not necessarily the last of the three in event order: take the latest pop time
             float bd = d; EvTime bt = old.t;
             const uint32_t rv[3] = {r0, r1, r2};
             for (int k = 0; k < 3; ++k) {
               const Label so = prob.load_label(rv[k]);
-              if (ev_less(bt, so.t)) { bt = so.t; bd = so.d; }
+              if (prob.tless(bt, so.t)) { bt = so.t; bd = so.d; }
             }
             ctl->goal_time[0] = __float_as_uint(bt.a1); ctl->goal_time[1] = bt.root; ctl->goal_time[2] = __float_as_uint(bt.a2);
-            ctl->goal_time[3] = __float_as_uint(bt.a3); ctl->goal_time[4] = bt.minor;
+            ctl->goal_time[3] = __float_as_uint(bt.a3); ctl->goal_time[4] = bt.ext; ctl->goal_time[5] = bt.self;
             atomicMin(&ctl->goal_ring[(r + 1) & 1], __float_as_uint((float)((double)bd + goal_dist_offset)));
           }
         }
@@ -331,7 +543,7 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
     if constexpr (P::HAS_GOAL_TIME) if (has_robot && goal_b != INF_BITS) {
       prob.goal_t.a1 = __uint_as_float(__ldcg(&ctl->goal_time[0])); prob.goal_t.root = __ldcg(&ctl->goal_time[1]);
       prob.goal_t.a2 = __uint_as_float(__ldcg(&ctl->goal_time[2])); prob.goal_t.a3 = __uint_as_float(__ldcg(&ctl->goal_time[3]));
-      prob.goal_t.minor = __ldcg(&ctl->goal_time[4]);
+      prob.goal_t.ext = __ldcg(&ctl->goal_time[4]); prob.goal_t.self = __ldcg(&ctl->goal_time[5]);
     }
     const unsigned int stop = __ldcg(&ctl->stop_ring[r & 1]);
     // the round in which the goal cutoff first becomes visible must run even if nothing else is left to do: it puts the
@@ -402,8 +614,8 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
                         const uint32_t v0, const bool fresh, const uint32_t slot) {
       const float d = old.d, tau = old.t.a1;
       float nd; EvTime nt; int deg; uint32_t mk1 = MARK_FIXED, mk2 = MARK_FIXED; float excl = 0.0f;
-      prob.replay_sub8(c, j, has, ix, w, band_end, goal, r, mark, nd, nt, deg, mk1, mk2, excl);
-      const bool changed = has && (__float_as_uint(nd) != __float_as_uint(d) || !ev_eq(nt, old.t));
+      prob.replay_sub8(c, j, has, ix, w, band_end, goal, r, mark, old.t, nd, nt, deg, mk1, mk2, excl);
+      const bool changed = has && (__float_as_uint(nd) != __float_as_uint(d) || !prob.teq(nt, old.t));
       if constexpr (P::CAN_SKIP) if (skip_ok) {
         // stamps of the clean-candidate skip: c was evaluated in this round; its face neighbours have a source that was
         // re-labelled in this round (plain stores: every writer of a round stores the same value, rounds are barrier-ordered)
@@ -413,6 +625,10 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
           if (j == 0 && deg > 8) prob.activate(c, [&](uint32_t x) { __stcg(&prob.dirty_round[x], r + 1u); });
         }
       }
+#ifdef MNB_EMU_ACTIVE
+      if (has && j == 0 && getenv("MNB_DBG_V") && (c == (uint32_t)atoi(getenv("MNB_DBG_V")) || (getenv("MNB_DBG_V2") && c == (uint32_t)atoi(getenv("MNB_DBG_V2")))))
+        fprintf(stderr, "[r%u %s] c=%u old d=%.9g t=(%.9g,%u,%.9g,%.9g,ext %x) -> nd=%.9g nt=(%.9g,%u,%.9g,%.9g,ext %x) changed=%d strict=%d\n", r, fresh ? "main" : "sweep", c, old.d, old.t.a1, old.t.root, old.t.a2, old.t.a3, old.t.ext, nd, nt.a1, nt.root, nt.a2, nt.a3, nt.ext, (int)changed, prob.strict);
+#endif
       if (has && j == 0) {
         my_recomputes++;
         if (changed) {
@@ -488,10 +704,10 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
               const uint32_t rv[3] = {r0, r1, r2};
               for (int k = 0; k < 3; ++k) {
                 const Label so = prob.load_label(rv[k]);
-                if (ev_less(bt, so.t)) { bt = so.t; bd = so.d; }
+                if (prob.tless(bt, so.t)) { bt = so.t; bd = so.d; }
               }
               ctl->goal_time[0] = __float_as_uint(bt.a1); ctl->goal_time[1] = bt.root; ctl->goal_time[2] = __float_as_uint(bt.a2);
-            ctl->goal_time[3] = __float_as_uint(bt.a3); ctl->goal_time[4] = bt.minor;
+            ctl->goal_time[3] = __float_as_uint(bt.a3); ctl->goal_time[4] = bt.ext; ctl->goal_time[5] = bt.self;
             atomicMin(&ctl->goal_ring[(r + 1) & 1], __float_as_uint((float)((double)bd + goal_dist_offset)));
             }
           }

@@ -89,7 +89,9 @@ __global__ void __launch_bounds__(512, 1) k_inflate(const InflateKernelArgs a) {
   group_sync<0>(ctl->barrier);
   InflationProblem prob;
   prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_wd = a.cor_wd; prob.cor_eid = a.cor_eid; prob.invalid = a.invalid;
-  prob.state = state; prob.minor_arr = a.ws.minor; prob.root_arr = a.ws.root; prob.chg = a.ws.chg; prob.deferred_m = __uint_as_float(INF_BITS); prob.max_distance = a.max_distance;
+  prob.state = state; prob.ext_arr = a.ws.ext; prob.root_arr = a.ws.root; prob.chg = a.ws.chg;
+  prob.pool_w = a.ws.pool; prob.pool = prob.pool_w; prob.pool_cap = a.ws.pool_cap; prob.pool_top = &ctl->pool_top; prob.pool_overflow = &ctl->pool_overflow;
+  prob.deferred_m = __uint_as_float(INF_BITS); prob.max_distance = a.max_distance;
   prob.last_eval = a.ws.last_eval; prob.dirty_round = a.ws.dirty; prob.skip_clean = a.skip_clean; prob.deferred_flag = false;
   for (uint32_t i = gtid; i < a.n_lethals; i += gthreads) {
     const uint32_t v = a.lethals[i];
@@ -207,10 +209,11 @@ __global__ void __launch_bounds__(128) k_infl_vec_sources(const InflVecArgs a) {
   if (d != 0.0f && __float_as_uint(d) != INF_BITS) {
     InflationProblem prob;
     prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_wd = a.cor_wd; prob.cor_eid = a.cor_eid; prob.invalid = a.invalid;
-    prob.state = a.ws.state; prob.minor_arr = a.ws.minor; prob.root_arr = a.ws.root; prob.chg = a.ws.chg;
+    prob.state = a.ws.state; prob.ext_arr = a.ws.ext; prob.root_arr = a.ws.root; prob.chg = a.ws.chg;
+    prob.pool_w = a.ws.pool; prob.pool = prob.pool_w; prob.pool_cap = a.ws.pool_cap; prob.pool_top = &a.ws.ctl->pool_top; prob.pool_overflow = &a.ws.ctl->pool_overflow;
     prob.deferred_m = __uint_as_float(INF_BITS); prob.strict = 0; prob.max_distance = a.max_distance;
     prob.last_eval = nullptr; prob.dirty_round = nullptr; prob.skip_clean = 0; prob.deferred_flag = false;
-    float nd, wu1, wu2; EvTime tc; int win;
+    float nd, wu1, wu2; EvFull tc; int win;
     prob.replay(c, __uint_as_float(INF_BITS), 0xfffffff0u /* final labels: nothing is deferred */, nd, tc, win, wu1, wu2);
     if (win >= 0 && (wu1 != 0.0f || wu2 != 0.0f)) {           // :301 (an update from two lethal sources keeps the phase-1 vector)
       const int4 ix = a.cor_idx[win];

@@ -15,8 +15,10 @@ static inline uint32_t watchdog_rounds(uint32_t V) { return 200000u + 256u * (ui
 
 struct WaveWorkspace {     // per group (index g): state + g*V etc.
   uint4* state;
-  uint32_t* minor;
-  uint32_t* root;    // cascade roots of flagged labels (problems.cuh)
+  uint32_t* ext;     // level-2 ids / level-pool references of flagged labels (band_engine.cuh)
+  uint32_t* root;    // cascade roots of flagged labels
+  uint32_t* pool;    // level pool: records of pop times with more than 3 cascade levels, pool_cap words per group
+  uint32_t pool_cap;
   uint32_t* last_eval; uint32_t* dirty; uint32_t* excl;   // clean-candidate skip stamps (problems.cuh)
   uint32_t* chg;
   uint32_t* ver;     // single-plan only (V entries): input versions for the in-round sweeps
@@ -66,7 +68,8 @@ __device__ __forceinline__ void ctl_reset(GroupCtl* ctl, unsigned int n0, float 
   ctl->lo[0] = INF_BITS; ctl->lo[1] = INF_BITS; ctl->lo[2] = __float_as_uint(seed_min);
   ctl->goal_ring[0] = INF_BITS; ctl->goal_ring[1] = INF_BITS; ctl->stop_ring[0] = 0; ctl->stop_ring[1] = 0;
   ctl->goal_bits = INF_BITS; ctl->robot_left = 0;
-  ctl->goal_time[0] = INF_BITS; ctl->goal_time[1] = 0u; ctl->goal_time[2] = 0u; ctl->goal_time[3] = 0u; ctl->goal_time[4] = 0u;
+  ctl->goal_time[0] = INF_BITS; ctl->goal_time[1] = 0u; ctl->goal_time[2] = 0u; ctl->goal_time[3] = 0u; ctl->goal_time[4] = 0u; ctl->goal_time[5] = 0u;
+  ctl->pool_top = 0u;
 }
 
 #ifndef MNB_CVP_MINBLOCKS
@@ -110,7 +113,9 @@ __global__ void __launch_bounds__(MNB_CVP_THREADS, MNB_CVP_MINBLOCKS) k_cvp(cons
     CvpEllProblemT<SKIP> prob;
     prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_w = a.cor_w; prob.cost = a.cost; prob.invalid = a.invalid;
     prob.ell_idx = a.ell_idx; prob.ell_w = a.ell_w; prob.ell_geo = a.ell_geo;
-    prob.state = state; prob.minor_arr = a.ws.minor + (size_t)g * V; prob.root_arr = a.ws.root + (size_t)g * V; prob.chg = chg; prob.ver = a.ws.ver; prob.deferred_m = __uint_as_float(INF_BITS); prob.pred = nullptr; prob.dir = nullptr; prob.cut = nullptr; prob.cost_limit = a.cost_limit;
+    prob.state = state; prob.ext_arr = a.ws.ext + (size_t)g * V; prob.root_arr = a.ws.root + (size_t)g * V; prob.chg = chg;
+    prob.pool_w = a.ws.pool + (size_t)g * a.ws.pool_cap; prob.pool = prob.pool_w; prob.pool_cap = a.ws.pool_cap; prob.pool_top = &ctl->pool_top; prob.pool_overflow = &ctl->pool_overflow;
+    prob.ver = a.ws.ver; prob.deferred_m = __uint_as_float(INF_BITS); prob.pred = nullptr; prob.dir = nullptr; prob.cut = nullptr; prob.cost_limit = a.cost_limit;
     prob.s0 = s0; prob.s1 = s1; prob.s2 = s2; prob.seed_noexpand = 0; prob.goal_t = ev_normal(__uint_as_float(INF_BITS), 0u);
     prob.last_eval = last_eval; prob.dirty_round = dirty; prob.excl_min = a.ws.excl + (size_t)g * V; prob.skip_clean = SKIP ? 1 : 0; prob.prefetch_marks = false;
     float sd[3];
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(MNB_CVP_THREADS, MNB_CVP_MINBLOCKS) k_cvp(cons
           ctl->goal_ring[0] = __float_as_uint((float)((double)seed_max + a.goal_dist_offset));
           uint32_t sl = sv[0]; float sdl = sd[0];
           for (int k = 1; k < 3; ++k) if (sd[k] > sdl || (sd[k] == sdl && sv[k] > sl)) { sl = sv[k]; sdl = sd[k]; }
-          ctl->goal_time[0] = __float_as_uint(sdl); ctl->goal_time[1] = sl; ctl->goal_time[4] = 2u * sl;
+          ctl->goal_time[0] = __float_as_uint(sdl); ctl->goal_time[1] = sl; ctl->goal_time[5] = sl;
         }
       }
     }
@@ -196,7 +201,9 @@ __global__ void __launch_bounds__(512, MNB_GRID_MINBLOCKS) k_cvp_grid(const CvpK
   CvpEllProblemT<SKIP> prob;
   prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_w = a.cor_w; prob.cost = a.cost; prob.invalid = a.invalid;
   prob.ell_idx = a.ell_idx; prob.ell_w = a.ell_w; prob.ell_geo = a.ell_geo;
-  prob.state = state; prob.minor_arr = a.ws.minor; prob.root_arr = a.ws.root; prob.chg = a.ws.chg; prob.ver = a.ws.ver; prob.deferred_m = __uint_as_float(INF_BITS); prob.pred = nullptr; prob.dir = nullptr; prob.cut = nullptr; prob.cost_limit = a.cost_limit;
+  prob.state = state; prob.ext_arr = a.ws.ext; prob.root_arr = a.ws.root; prob.chg = a.ws.chg;
+  prob.pool_w = a.ws.pool; prob.pool = prob.pool_w; prob.pool_cap = a.ws.pool_cap; prob.pool_top = &ctl->pool_top; prob.pool_overflow = &ctl->pool_overflow;
+  prob.ver = a.ws.ver; prob.deferred_m = __uint_as_float(INF_BITS); prob.pred = nullptr; prob.dir = nullptr; prob.cut = nullptr; prob.cost_limit = a.cost_limit;
   prob.s0 = s0; prob.s1 = s1; prob.s2 = s2; prob.seed_noexpand = 0; prob.goal_t = ev_normal(__uint_as_float(INF_BITS), 0u);
   prob.last_eval = a.ws.last_eval; prob.dirty_round = a.ws.dirty; prob.excl_min = a.ws.excl; prob.skip_clean = SKIP ? 1 : 0; prob.prefetch_marks = true;
   float sd[3];
@@ -235,7 +242,7 @@ __global__ void __launch_bounds__(512, MNB_GRID_MINBLOCKS) k_cvp_grid(const CvpK
         ctl->goal_ring[0] = __float_as_uint((float)((double)seed_max + a.goal_dist_offset));
         uint32_t sl = sv[0]; float sdl = sd[0];
         for (int k = 1; k < 3; ++k) if (sd[k] > sdl || (sd[k] == sdl && sv[k] > sl)) { sl = sv[k]; sdl = sd[k]; }
-        ctl->goal_time[0] = __float_as_uint(sdl); ctl->goal_time[1] = sl; ctl->goal_time[4] = 2u * sl;
+        ctl->goal_time[0] = __float_as_uint(sdl); ctl->goal_time[1] = sl; ctl->goal_time[5] = sl;
       }
     }
   }
@@ -260,11 +267,13 @@ __global__ void __launch_bounds__(256) k_cvp_epilogue(const CvpKernelArgs a, Gro
   const uint32_t sf = a.seed_faces[0];
   CvpProblem prob;
   prob.cor_ptr = a.cor_ptr; prob.cor_idx = a.cor_idx; prob.cor_w = a.cor_w; prob.cost = a.cost; prob.invalid = a.invalid;
-  prob.state = a.ws.state; prob.minor_arr = a.ws.minor; prob.root_arr = a.ws.root; prob.chg = a.ws.chg; prob.ver = nullptr; prob.deferred_m = __uint_as_float(INF_BITS); prob.pred = a.out_pred; prob.dir = a.out_dir; prob.cut = a.out_cut; prob.cost_limit = a.cost_limit;
+  prob.state = a.ws.state; prob.ext_arr = a.ws.ext; prob.root_arr = a.ws.root; prob.chg = a.ws.chg;
+  prob.pool_w = a.ws.pool; prob.pool = prob.pool_w; prob.pool_cap = a.ws.pool_cap; prob.pool_top = &ctl->pool_top; prob.pool_overflow = &ctl->pool_overflow;
+  prob.ver = nullptr; prob.deferred_m = __uint_as_float(INF_BITS); prob.pred = a.out_pred; prob.dir = a.out_dir; prob.cut = a.out_cut; prob.cost_limit = a.cost_limit;
   prob.s0 = a.faces[3 * (size_t)sf]; prob.s1 = a.faces[3 * (size_t)sf + 1]; prob.s2 = a.faces[3 * (size_t)sf + 2];
   prob.seed_noexpand = 0;
   prob.goal_t.a1 = __uint_as_float(ctl->goal_time[0]); prob.goal_t.root = ctl->goal_time[1]; prob.goal_t.a2 = __uint_as_float(ctl->goal_time[2]);
-  prob.goal_t.a3 = __uint_as_float(ctl->goal_time[3]); prob.goal_t.minor = ctl->goal_time[4];
+  prob.goal_t.a3 = __uint_as_float(ctl->goal_time[3]); prob.goal_t.ext = ctl->goal_time[4]; prob.goal_t.self = ctl->goal_time[5];
   {
     const uint32_t sv[3] = {prob.s0, prob.s1, prob.s2};
     for (int k = 0; k < 3; ++k)
@@ -272,14 +281,13 @@ __global__ void __launch_bounds__(256) k_cvp_epilogue(const CvpKernelArgs a, Gro
   }
   const uint4 lw = a.ws.state[c];
   const float d = __uint_as_float(lw.x);
-  // diagnostic: labels whose pop time needed more than the 3 tracked cascade levels (ordered by creation beyond that,
-  // DESIGN.md 7) -- reported in mnb_stats so that a caller can tell when the result may deviate in a flooded pocket
-  if (__float_as_uint(d) != INF_BITS && (lw.w >> 31)) atomicAdd(&ctl->deep_labels, 1u);
+  // statistic: labels whose pop time has more than 3 cascade levels (their tails live in the level pool; exact)
+  if (__float_as_uint(d) != INF_BITS && (lw.w >> 31) && (a.ws.ext[c] & EXT_POOL)) atomicAdd(&ctl->deep_labels, 1u);
   if (prob.seed_index(c) >= 0) {                         // cvp:719-728
     a.out_pred[c] = c; a.out_dir[c] = 0.0f; a.out_cut[c] = (int32_t)sf;
     return;
   }
-  int win = -1; float nd, wu1 = 0, wu2 = 0; EvTime nt;
+  int win = -1; float nd, wu1 = 0, wu2 = 0; EvFull nt;
   if (__float_as_uint(d) != INF_BITS && prob.eligible(c))
     prob.replay(c, __uint_as_float(INF_BITS), __uint_as_float(ctl->goal_bits), 0xfffffff0u /* final labels: nothing is deferred */, nd, nt, win, wu1, wu2);
   prob.write_aux(c, win, wu1, wu2);

@@ -11,18 +11,15 @@ namespace mnb {
 // Reference: the face (v1,v2,c) updates c when the later of v1,v2 is popped and c
 // is the only non-fixed vertex (cvp_mesh_planner.cpp:790-866).
 //
-// Event (pop) time of a vertex = the monotonic stack of "water levels" (a1 > a2 > a3, minor):
-//   * a vertex whose label exceeds the pop time of the face that produced it pops at its own key:
-//     (d, 0, 0, 2*id)  ==  the oracle's canonical heap order (key, id);
-//   * the CVP unfolding update is not causal: a face fired at water level a1 can hand
-//     out a label X <= a1 ("back-step").  Such a vertex is popped inside the cascade that runs below
-//     the water line, in key order among the cascade's entries: its time keeps the trigger's levels
-//     that are >= X and appends X:  (a1, X) / (a1, a2, X); cascades nest (3 levels tracked, exact on
-//     every mesh tested incl. cost-weighted non-geometric weights; deeper ones fall back to
-//     "right after the trigger": minor(trigger)+1, kept in a side array).
-// Times compare lexicographically.
+// Event (pop) time of a vertex: the stack of water levels of band_engine.cuh (EvTime / TimeAlg / LabelStore), exact for
+// cascades of any depth:
+//   * a vertex whose label exceeds the pop time of the face that produced it pops at its own key (d, id)  ==  the
+//     oracle's canonical heap order;
+//   * the CVP unfolding update is not causal: a face fired at water level a1 can hand out a label
+//     X <= a1 ("back-step").  Such a vertex is popped inside the cascade that runs below the water line, in key order
+//     among the cascade's entries: its time keeps the trigger's levels that are > (X, c) and appends (X, c).
 // ---------------------------------------------------------------------------
-struct CvpProblem {
+struct CvpProblem : LabelStore {
   static constexpr bool CAN_SKIP = false;   // (the 8-lane CvpEllProblemT carries its own switch)
   static constexpr bool HAS_GOAL_TIME = true;
   EvTime goal_t;                            // pop time of the vertex that armed the goal cutoff (GroupCtl::goal_time); +inf: not armed
@@ -32,7 +29,6 @@ struct CvpProblem {
   const float4* __restrict__ cor_w;
   const float* __restrict__ cost;
   const uint8_t* __restrict__ invalid;  // may be null
-  uint4* state;                         // {d bits, tau bits, minor (0 = 2*id), -}
   uint32_t* pred;    // epilogue only
   float* dir;
   int32_t* cut;
@@ -42,36 +38,10 @@ struct CvpProblem {
 
   static constexpr int MAXF = 12;
 
-  uint32_t* minor_arr;                  // overflow minors (only read when the label's flag bit is set)
-  uint32_t* root_arr;                   // cascade roots (only read when the label's flag bit is set)
-  uint32_t* chg;                        // 1 + round of the last RE-label of a vertex (0 = never)
   uint32_t* ver;                        // input version: bumped whenever a face neighbour is re-labelled (in-round sweeps)
   mutable float deferred_m;             // smallest trigger time of a back-step deferred in this round
   int strict;                           // set by the engine once it has detected stagnation (see backstep_ok)
 
-  // decoding of the 16-byte label word: sign bit of .z = "root differs from the vertex id, see root_arr",
-  // sign bit of .w = "minor differs from 2*id, see minor_arr" (pop-time levels are >= 0, so both bits are free)
-  __device__ __forceinline__ Label unpack_label(uint32_t v, const uint4& s) const {
-    Label l; l.d = __uint_as_float(s.x); l.t.a1 = __uint_as_float(s.y); l.t.a2 = __uint_as_float(s.z & 0x7fffffffu);
-    l.t.a3 = __uint_as_float(s.w & 0x7fffffffu);
-    l.t.root = (s.z >> 31) ? __ldcg(&root_arr[v]) : v;
-    l.t.minor = (s.w >> 31) ? __ldcg(&minor_arr[v]) : 2u * v;
-    return l;
-  }
-  __device__ __forceinline__ Label load_label(uint32_t v) const { return unpack_label(v, __ldcg(&state[v])); }
-  // the 16-byte word of a label as store_label() writes it (flagged root / minor live in the side arrays)
-  __device__ __forceinline__ uint4 pack_label(uint32_t c, float d, const EvTime& t) const {
-    uint32_t z = __float_as_uint(t.a2), w = __float_as_uint(t.a3);
-    if (t.root != c) z |= 0x80000000u;
-    if (t.minor != 2u * c) w |= 0x80000000u;
-    return make_uint4(__float_as_uint(d), __float_as_uint(t.a1), z, w);
-  }
-  __device__ __forceinline__ void store_label(uint32_t c, float d, const EvTime& t, bool relabel, uint32_t round) const {
-    if (t.root != c) __stcg(&root_arr[c], t.root);
-    if (t.minor != 2u * c) __stcg(&minor_arr[c], t.minor);
-    if (relabel) __stcg(&chg[c], round + 1u);
-    __stcg(&state[c], pack_label(c, d, t));
-  }
   // A non-causal (back-step) label X <= T.a1 may only be taken from a trigger whose label was not
   // re-labelled during the previous round.  Without this a trigger and its own back-step child can feed
   // each other forever (a dependency cycle that has no counterpart in the sequential order); the deferred
@@ -101,12 +71,12 @@ struct CvpProblem {
   }
 
   // pop time (T, Tm) of the face with sources v1, v2; false if the face cannot fire
-  __device__ __forceinline__ bool face_time(uint32_t v1, uint32_t v2, const Label& a, const Label& b, float band_end,
+  __device__ __forceinline__ bool face_time(uint32_t c, uint32_t v1, uint32_t v2, const Label& a, const Label& b, float band_end,
                                             float goal, EvTime& T, uint32_t& Tv) const {
     if (!(a.d < band_end) || !(b.d < band_end)) return false;
     if (invalid && (invalid[v1] || invalid[v2])) return false;
     const int i1 = seed_index(v1), i2 = seed_index(v2);
-    const bool v1_later = ev_less(b.t, a.t);
+    const bool v1_later = tless(b.t, a.t);
     if (i1 >= 0 && i2 >= 0) {
       // both sources pre-fixed: the face fires at the FIRST of them that pops and expands
       const bool e1 = !((seed_noexpand >> i1) & 1u), e2 = !((seed_noexpand >> i2) & 1u);
@@ -115,22 +85,23 @@ struct CvpProblem {
       T = use1 ? a.t : b.t; Tv = use1 ? v1 : v2;
       return true;
     }
+    if (names(v1_later ? a.t : b.t, c)) return false;          // the face fires inside a cascade of c itself (LabelStore::names)
     const int il = v1_later ? i1 : i2;
     if (il >= 0 && ((seed_noexpand >> il) & 1u)) return false;
     {   // cvp:754: the popping vertex does not expand if it lies beyond goal_dist -- the goal_dist of the moment it pops:
         // a vertex that popped before the cutoff was armed expanded whatever its potential
       const Label& L = v1_later ? a : b;
-      if (L.d > goal && !ev_less(L.t, goal_t)) return false;
+      if (L.d > goal && !tless(L.t, goal_t)) return false;
     }
     T = v1_later ? a.t : b.t; Tv = v1_later ? v1 : v2;
     return true;
   }
 
-  __device__ __forceinline__ bool corner_time(uint32_t k, float band_end, float goal, EvTime& T, uint32_t& Tv, float& u1, float& u2) const {
+  __device__ __forceinline__ bool corner_time(uint32_t c, uint32_t k, float band_end, float goal, EvTime& T, uint32_t& Tv, float& u1, float& u2) const {
     const int4 ix = __ldg(&cor_idx[k]);
     const Label a = load_label((uint32_t)ix.x), b = load_label((uint32_t)ix.y);
     u1 = a.d; u2 = b.d;
-    return face_time((uint32_t)ix.x, (uint32_t)ix.y, a, b, band_end, goal, T, Tv);
+    return face_time(c, (uint32_t)ix.x, (uint32_t)ix.y, a, b, band_end, goal, T, Tv);
   }
 
   // predecessors_/direction_/cutting_faces_ of the winning face (cvp:493-517), literal acos form
@@ -148,54 +119,38 @@ struct CvpProblem {
     }
   }
 
-  // one accepted update with value X from a face that fired at time F: pop time of c
-  // (monotonic stack: keep the trigger's water levels that are >= X, then X itself)
-  __device__ __forceinline__ static EvTime accept_time(uint32_t c, float X, const EvTime& F) {
-    EvTime t; t.a2 = 0.0f; t.a3 = 0.0f; t.minor = 2u * c; t.root = c;
-    // above water: pops at its own key.  X == F.a1 exactly: c enters the heap with the key of the cascade's root trigger
-    // and pops in (key, id) order among the vertices of that key that are still queued -- all of them have ids above the
-    // root's -- i.e. as a plain label if its id is above the root's, else right after the cascade
-    if (X > F.a1 || (X == F.a1 && c > F.root)) { t.a1 = X; return t; }
-    t.a1 = F.a1; t.root = F.root;                                 // member of the trigger's cascade
-    if (X > F.a2) { t.a2 = X; return t; }
-    t.a2 = F.a2;
-    if (X > F.a3) { t.a3 = X; return t; }
-    t.a3 = F.a3; t.minor = F.minor + 1u;                          // deeper than tracked: right after the trigger
-    return t;
-  }
-
   // generic path for vertices with more than MAXF incident faces: repeated selection of the next
   // corner in (T, corner index) order by rescanning the corner list (O(deg^2), rare)
-  __device__ __noinline__ void replay_big(uint32_t c, float band_end, float goal, uint32_t round, float& nd, EvTime& nt, int& win,
+  __device__ __noinline__ void replay_big(uint32_t c, float band_end, float goal, uint32_t round, float& nd, EvFull& nt, int& win,
                                           float& wu1, float& wu2) const {
     const uint32_t kb = cor_ptr[c], ke = cor_ptr[c + 1];
     float cur = __uint_as_float(INF_BITS);
-    EvTime tc = ev_normal(cur, c);
+    EvFull tc = full_normal(cur, c);
     EvTime lastT = ev_normal(0.0f, 0); uint32_t lastK = 0; bool have_last = false;
     win = -1;
     for (;;) {
       EvTime bT = lastT; float bu1 = 0, bu2 = 0; uint32_t bk = 0, bTv = 0; bool found = false;
       for (uint32_t k = kb; k < ke; ++k) {
         EvTime T; float u1, u2; uint32_t Tv;
-        if (!corner_time(k, band_end, goal, T, Tv, u1, u2)) continue;
+        if (!corner_time(c, k, band_end, goal, T, Tv, u1, u2)) continue;
         if (have_last) {
-          const bool after = ev_less(lastT, T) || (ev_eq(lastT, T) && k > lastK);
+          const bool after = tless(lastT, T) || (teq(lastT, T) && k > lastK);
           if (!after) continue;
         }
-        if (!found || ev_less(T, bT) || (ev_eq(T, bT) && k < bk)) { bT = T; bk = k; bTv = Tv; bu1 = u1; bu2 = u2; found = true; }
+        if (!found || tless(T, bT) || (teq(T, bT) && k < bk)) { bT = T; bk = k; bTv = Tv; bu1 = u1; bu2 = u2; found = true; }
       }
       if (!found) break;
-      if (!ev_less(bT, tc)) break;
+      if (!less_T_full(bT, tc)) break;
       const float4 w = __ldg(&cor_w[bk]);
       CvpResult r;
-      if (cvp_update_t<false>(bu1, bu2, cur, w.z, w.y, w.x, r) && backstep_ok(r.value, bT, bTv, round)) { cur = r.value; tc = accept_time(c, r.value, bT); win = (int)bk; wu1 = bu1; wu2 = bu2; }
+      if (cvp_update_t<false>(bu1, bu2, cur, w.z, w.y, w.x, r) && backstep_ok(r.value, bT, bTv, round)) { cur = r.value; accept(c, r.value, bT, tc); win = (int)bk; wu1 = bu1; wu2 = bu2; }
       lastT = bT; lastK = bk; have_last = true;
     }
     nd = cur; nt = tc;
   }
 
   // event-ordered replay of the faces around c (see band_engine.cuh)
-  __device__ __forceinline__ void replay(uint32_t c, float band_end, float goal, uint32_t round, float& nd, EvTime& nt, int& win,
+  __device__ __forceinline__ void replay(uint32_t c, float band_end, float goal, uint32_t round, float& nd, EvFull& nt, int& win,
                                          float& wu1, float& wu2) const {
     const uint32_t kb = cor_ptr[c], ke = cor_ptr[c + 1];
     win = -1; wu1 = 0.0f; wu2 = 0.0f;
@@ -207,31 +162,32 @@ struct CvpProblem {
     int n = 0;
     for (uint32_t k = kb; k < ke; ++k) {
       EvTime T; float u1, u2; uint32_t Tv;
-      if (!corner_time(k, band_end, goal, T, Tv, u1, u2)) continue;
+      if (!corner_time(c, k, band_end, goal, T, Tv, u1, u2)) continue;
       Tt[n] = T; U1[n] = u1; U2[n] = u2; K[n] = k; TV[n] = Tv; ++n;
     }
     float cur = __uint_as_float(INF_BITS);
-    EvTime tc = ev_normal(cur, c);
+    EvFull tc = full_normal(cur, c);
     for (int i = 0; i < n; ++i) {
       int b = i;
       for (int j = i + 1; j < n; ++j)
-        if (ev_less(Tt[j], Tt[b]) || (ev_eq(Tt[j], Tt[b]) && K[j] < K[b])) b = j;
+        if (tless(Tt[j], Tt[b]) || (teq(Tt[j], Tt[b]) && K[j] < K[b])) b = j;
       const EvTime T = Tt[b]; const float u1 = U1[b], u2 = U2[b]; const uint32_t k = K[b], Tv = TV[b];
       Tt[b] = Tt[i]; U1[b] = U1[i]; U2[b] = U2[i]; K[b] = K[i]; TV[b] = TV[i];
-      if (!ev_less(T, tc)) break;   // c has been popped before this face fires
+      if (!less_T_full(T, tc)) break;   // c has been popped before this face fires
       const float4 w = __ldg(&cor_w[k]);
       CvpResult r;
-      if (cvp_update_t<false>(u1, u2, cur, w.z, w.y, w.x, r) && backstep_ok(r.value, T, Tv, round)) { cur = r.value; tc = accept_time(c, r.value, T); win = (int)k; wu1 = u1; wu2 = u2; }
+      if (cvp_update_t<false>(u1, u2, cur, w.z, w.y, w.x, r) && backstep_ok(r.value, T, Tv, round)) { cur = r.value; accept(c, r.value, T, tc); win = (int)k; wu1 = u1; wu2 = u2; }
     }
     nd = cur; nt = tc;
   }
 
   // engine hook: returns true if the label changed (and stores it)
   __device__ __forceinline__ bool recompute(uint32_t c, float band_end, float goal, uint32_t round, const Label& old, float& nd, float& ntau) {
-    int win; float wu1, wu2; EvTime nt;
-    replay(c, band_end, goal, round, nd, nt, win, wu1, wu2);
+    int win; float wu1, wu2; EvFull nf;
+    replay(c, band_end, goal, round, nd, nf, win, wu1, wu2);
+    const EvTime nt = finish(nf, old.t);
     ntau = nt.a1;
-    if (__float_as_uint(nd) == __float_as_uint(old.d) && ev_eq(nt, old.t)) return false;
+    if (__float_as_uint(nd) == __float_as_uint(old.d) && teq(nt, old.t)) return false;
     store_label(c, nd, nt, __float_as_uint(old.d) != INF_BITS, round);
     return true;
   }
@@ -300,9 +256,12 @@ struct CvpEllProblemT : CvpProblem {
     if (j == 0 && deg > (int)ELL_W) activate(c, push);   // faces beyond the 8 ELL slots
   }
 
-  __device__ __noinline__ void replay_serial(uint32_t c, float band_end, float goal, uint32_t round, float& nd, EvTime& nt) const {
-    int win; float a1, a2;
-    replay(c, band_end, goal, round, nd, nt, win, a1, a2);
+  // scalar replay on one lane (more than 8 faces, or a cascade deeper than 3 levels): returns the time to STORE (a deep
+  // label that did not change keeps its pool record, LabelStore::finish)
+  __device__ __noinline__ void replay_serial(uint32_t c, float band_end, float goal, uint32_t round, const EvTime& old_t, float& nd, EvTime& nt) const {
+    int win; float a1, a2; EvFull nf;
+    replay(c, band_end, goal, round, nd, nf, win, a1, a2);
+    nt = finish(nf, old_t);
   }
 
   __device__ __forceinline__ int4 load_row_idx(uint32_t c, uint32_t j) const { return __ldg(&ell_idx[(size_t)c * ELL_W + j]); }
@@ -345,13 +304,13 @@ struct CvpEllProblemT : CvpProblem {
   // compile-time full mask with width 8.  Lanes of a group return the same label.  mk1/mk2 return the
   // activation marks of the lane's two source vertices (fetched together with their labels).
   __device__ __forceinline__ void replay_sub8(uint32_t c, uint32_t j, bool has, const int4& ix, const float4& w, float band_end,
-                                              float goal, uint32_t round, const uint32_t* mark, float& nd, EvTime& nt, int& deg_out,
+                                              float goal, uint32_t round, const uint32_t* mark, const EvTime& old_t, float& nd, EvTime& nt, int& deg_out,
                                               uint32_t& mk1, uint32_t& mk2, float& excl_min_out) const {
     constexpr unsigned FULL = 0xffffffffu;
     const float INF = __uint_as_float(INF_BITS);
     const int deg = __shfl_sync(FULL, ix.w, 0, 8);
     deg_out = deg;
-    const bool big = has && deg > (int)ELL_W;
+    bool big = has && deg > (int)ELL_W;     // (also set below when the replay meets a cascade deeper than 3 levels)
     bool valid = has && !big && ix.x != ELL_EMPTY;
     float excl = INF;                                   // smallest finite source label of this lane's face beyond the band end
     EvTime T = ev_normal(INF, 0x7fffffffu);
@@ -371,7 +330,7 @@ struct CvpEllProblemT : CvpProblem {
         if (__float_as_uint(a.d) != INF_BITS && !(a.d < band_end)) excl = a.d;
         if (__float_as_uint(b.d) != INF_BITS && !(b.d < band_end)) excl = fminf(excl, b.d);
       }
-      valid = face_time(v1, v2, a, b, band_end, goal, T, Tv);
+      valid = face_time(c, v1, v2, a, b, band_end, goal, T, Tv);
       if (valid) {
         eval_face_geo((double)a.d, (double)b.d, (double)w.z, (double)w.y, (double)w.x, g, U, X);
         // back-step from a trigger that was re-labelled last round: defer (see backstep_ok)
@@ -397,15 +356,15 @@ struct CvpEllProblemT : CvpProblem {
     if (__all_sync(FULL, !valid || causal || T.a1 > m)) {
       cur = m; tc = ev_normal(m, c);
     } else {
-      // Common case: every firing face of the warp has a plain pop time (a2 == a3 == 0, default minor, root = Tv):
-      // the event order is (a1, Tv).  Cascade members (rare) take the general path on (a1, root, a2, a3, minor).  Invalid
-      // lanes carry the maximal key so that no validity flag has to travel with the shuffles.
-      const bool plain = !valid || (T.a2 == 0.0f && T.a3 == 0.0f && T.minor == 2u * Tv && T.root == Tv);
+      // Common case: every firing face of the warp has a plain pop time (one level, root = Tv): the event order is
+      // (a1, Tv).  Cascade members (rare) take the general path on the full stacks.  Invalid lanes carry the maximal key so
+      // that no validity flag has to travel with the shuffles.
+      const bool plain = !valid || (T.a2 == 0.0f && T.root == Tv);
       const bool all_plain = __all_sync(FULL, plain);
       const uint32_t k1 = valid ? __float_as_uint(T.a1) : 0xffffffffu;          // pop times are >= 0: bit order = value order
       const unsigned long long hi = valid ? (((unsigned long long)k1 << 32) | T.root) : ~0ull;          // plain: root == Tv
       const unsigned long long mid = ((unsigned long long)__float_as_uint(T.a2) << 32) | __float_as_uint(T.a3);
-      const uint32_t lo = T.minor;
+      const unsigned long long lo = ((unsigned long long)T.ext << 32) | Tv;     // (the trigger vertex = the time's own id)
       int rank = 0;
       if (all_plain) {
         // 32-bit pass on a1 alone; two firing faces with bit-identical a1 (exact float tie between different source
@@ -433,8 +392,13 @@ struct CvpEllProblemT : CvpProblem {
           const int src = (int)((j + d) & 7);
           const unsigned long long ohi = __shfl_sync(FULL, hi, src, 8);
           const unsigned long long omid = __shfl_sync(FULL, mid, src, 8);
-          const uint32_t olo = __shfl_sync(FULL, lo, src, 8);
-          if (ohi < hi || (ohi == hi && (omid < mid || (omid == mid && (olo < lo || (olo == lo && (uint32_t)src < j)))))) ++rank;
+          const unsigned long long olo = __shfl_sync(FULL, lo, src, 8);
+          if (ohi < hi) ++rank;
+          else if (ohi == hi && valid) {                  // same first level: compare the rest of the two stacks
+            EvTime O; O.a1 = T.a1; O.root = T.root; O.a2 = __uint_as_float((uint32_t)(omid >> 32)); O.a3 = __uint_as_float((uint32_t)omid);
+            O.ext = (uint32_t)(olo >> 32); O.self = (uint32_t)olo;
+            if (tless(O, T) || (!tless(T, O) && (uint32_t)src < j)) ++rank;
+          }
         }
       }
       if (!valid) rank = 99;
@@ -445,7 +409,7 @@ struct CvpEllProblemT : CvpProblem {
         const unsigned who = (__ballot_sync(FULL, rank == r) >> sh) & 0xFFu;
         const int src = who ? (__ffs(who) - 1) : 0;
         const unsigned long long whi = __shfl_sync(FULL, hi, src, 8);
-        unsigned long long wmid = 0; uint32_t wlo = 0;
+        unsigned long long wmid = 0, wlo = 0;
         if (!all_plain) { wmid = __shfl_sync(FULL, mid, src, 8); wlo = __shfl_sync(FULL, lo, src, 8); }
         const double Uw = __shfl_sync(FULL, U, src, 8);
         const double Xw = __shfl_sync(FULL, X, src, 8);
@@ -453,15 +417,18 @@ struct CvpEllProblemT : CvpProblem {
         if (!open) continue;
         EvTime Tw;
         Tw.a1 = __uint_as_float((uint32_t)(whi >> 32)); Tw.root = (uint32_t)whi;
-        if (all_plain) { Tw.a2 = 0.0f; Tw.a3 = 0.0f; Tw.minor = 2u * (uint32_t)whi; }
-        else { Tw.a2 = __uint_as_float((uint32_t)(wmid >> 32)); Tw.a3 = __uint_as_float((uint32_t)wmid); Tw.minor = wlo; }
-        if (!ev_less(Tw, tc)) { open = false; continue; }
+        if (all_plain) { Tw.a2 = 0.0f; Tw.a3 = 0.0f; Tw.ext = 0u; Tw.self = (uint32_t)whi; }
+        else { Tw.a2 = __uint_as_float((uint32_t)(wmid >> 32)); Tw.a3 = __uint_as_float((uint32_t)wmid); Tw.ext = (uint32_t)(wlo >> 32); Tw.self = (uint32_t)wlo; }
+        if (!tless(Tw, tc)) { open = false; continue; }
         const double cd = (double)cur;
-        if (Uw < cd && Xw < cd) { cur = (float)Xw; tc = accept_time(c, cur, Tw); }
+        if (Uw < cd && Xw < cd) {
+          cur = (float)Xw;
+          if (!accept_lean(c, cur, Tw, tc)) { big = true; open = false; }   // a fourth cascade level: scalar replay below
+        }
       }
     }
-    if (big) {   // rare: more than 8 faces -> CSR path on the group's first lane, result broadcast below
-      if (j == 0) replay_serial(c, band_end, goal, round, cur, tc);
+    if (big) {   // rare: more than 8 faces / a deep cascade -> scalar path on the group's first lane, result broadcast below
+      if (j == 0) replay_serial(c, band_end, goal, round, old_t, cur, tc);
     }
     if constexpr (!SKIP) excl_min_out = 0.0f;
     else {
@@ -476,7 +443,7 @@ struct CvpEllProblemT : CvpProblem {
     if (anybig) {
       cur = __shfl_sync(FULL, cur, 0, 8);
       tc.a1 = __shfl_sync(FULL, tc.a1, 0, 8); tc.a2 = __shfl_sync(FULL, tc.a2, 0, 8);
-      tc.a3 = __shfl_sync(FULL, tc.a3, 0, 8); tc.minor = __shfl_sync(FULL, tc.minor, 0, 8); tc.root = __shfl_sync(FULL, tc.root, 0, 8);
+      tc.a3 = __shfl_sync(FULL, tc.a3, 0, 8); tc.ext = __shfl_sync(FULL, tc.ext, 0, 8); tc.root = __shfl_sync(FULL, tc.root, 0, 8);
     }
     nd = cur; nt = tc;
   }
@@ -496,7 +463,7 @@ using CvpEllSkipProblem = CvpEllProblemT<true>;
 //   * invalid vertices pop but are not fixed and do not expand (:417-422) unless lethal (fixed at :400).
 // Corner weights are edge_distances (:383), record {|v1v2|, |v1c|, |v2c|}.
 // ---------------------------------------------------------------------------
-struct InflationProblem {
+struct InflationProblem : LabelStore {
   static constexpr bool HAS_GOAL_TIME = false;
   static constexpr bool CAN_SKIP = true;    // clean-candidate skip in run_band_rounds (delta = inf, no goal cutoff)
   // The Sethian fallback produces trigger / back-step-child cycles on ordinary inputs (config 3: one pair oscillates for 27
@@ -516,31 +483,12 @@ struct InflationProblem {
   const float4* __restrict__ cor_wd;
   const uint4* __restrict__ cor_eid;    // {edge(v1,v2), edge(v1,c), edge(v2,c), -} per corner record
   const uint8_t* __restrict__ invalid;  // may be null
-  uint4* state;
-  uint32_t* minor_arr;
-  uint32_t* root_arr;
-  uint32_t* chg;
   mutable float deferred_m;
   int strict;
   float max_distance;
 
   static constexpr int MAXF = 12;
 
-  __device__ __forceinline__ Label load_label(uint32_t v) const {       // same label word as CvpProblem
-    const uint4 s = __ldcg(&state[v]);
-    Label l; l.d = __uint_as_float(s.x); l.t.a1 = __uint_as_float(s.y); l.t.a2 = __uint_as_float(s.z & 0x7fffffffu);
-    l.t.a3 = __uint_as_float(s.w & 0x7fffffffu);
-    l.t.root = (s.z >> 31) ? __ldcg(&root_arr[v]) : v;
-    l.t.minor = (s.w >> 31) ? __ldcg(&minor_arr[v]) : 2u * v;
-    return l;
-  }
-  __device__ __forceinline__ void store_label(uint32_t c, float d, const EvTime& t, bool relabel, uint32_t round) const {
-    uint32_t z = __float_as_uint(t.a2), w = __float_as_uint(t.a3);
-    if (t.root != c) { __stcg(&root_arr[c], t.root); z |= 0x80000000u; }
-    if (t.minor != 2u * c) { __stcg(&minor_arr[c], t.minor); w |= 0x80000000u; }
-    if (relabel) __stcg(&chg[c], round + 1u);
-    __stcg(&state[c], make_uint4(__float_as_uint(d), __float_as_uint(t.a1), z, w));
-  }
   __device__ __forceinline__ bool backstep_ok(float X, const EvTime& T, uint32_t Tv, uint32_t round) const {   // see CvpProblem
     if (!strict || X > T.a1) return true;
     if (__ldcg(&chg[Tv]) < round) return true;
@@ -560,7 +508,7 @@ struct InflationProblem {
     }
   }
 
-  __device__ __forceinline__ bool corner_time(uint32_t k, float band_end, EvTime& T, uint32_t& Tv, float& u1, float& u2) const {
+  __device__ __forceinline__ bool corner_time(uint32_t c, uint32_t k, float band_end, EvTime& T, uint32_t& Tv, float& u1, float& u2) const {
     const int4 ix = __ldg(&cor_idx[k]);
     const uint32_t v1 = (uint32_t)ix.x, v2 = (uint32_t)ix.y;
     const Label a = load_label(v1), b = load_label(v2);
@@ -571,7 +519,7 @@ struct InflationProblem {
     const bool l1 = (u1 == 0.0f), l2 = (u2 == 0.0f);
     const bool i1 = invalid && invalid[v1], i2 = invalid && invalid[v2];
     if ((i1 && !l1) || (i2 && !l2)) return false;           // popped but never fixed (:417)
-    const bool v1_later = ev_less(b.t, a.t);
+    const bool v1_later = tless(b.t, a.t);
     if (l1 && l2) {                                          // both pre-fixed: first one that expands
       const bool e1 = !i1, e2 = !i2;
       if (!e1 && !e2) return false;
@@ -581,7 +529,7 @@ struct InflationProblem {
     }
     if (v1_later ? i1 : i2) return false;                    // the popping vertex must expand
     T = v1_later ? a.t : b.t; Tv = v1_later ? v1 : v2;
-    return true;
+    return !names(T, c);                                     // (a face inside a cascade of c itself cannot update c)
   }
 
   // event-ordered replay of the faces around c; win = corner record of the LAST accepted update (-1: none), with the
@@ -601,19 +549,19 @@ struct InflationProblem {
   }
   // true if entry (T1, k1) precedes (T2, k2) in the reference's call order
   __device__ __forceinline__ bool fires_before(const EvTime& T1, uint32_t k1, uint32_t p1, const EvTime& T2, uint32_t k2, uint32_t p2) const {
-    if (!ev_eq(T1, T2)) return ev_less(T1, T2);
+    if (!teq(T1, T2)) return tless(T1, T2);
     if (p1 != p2) return k1 < k2;                            // (cannot happen: equal pop times name the same vertex)
     return visit_key(k1, p1) < visit_key(k2, p2);
   }
 
   // vertices with more than MAXF incident faces: repeated selection of the next face in call order by rescanning the
   // corner list (O(deg^2), rare) -- same rule as the buffered loop below
-  __device__ __noinline__ void replay_big(uint32_t c, float band_end, uint32_t round, float& nd, EvTime& tc_out, int& win,
+  __device__ __noinline__ void replay_big(uint32_t c, float band_end, uint32_t round, float& nd, EvFull& tc_out, int& win,
                                           float& wu1, float& wu2) const {
     const uint32_t kb = cor_ptr[c], ke = cor_ptr[c + 1];
     const float INF = __uint_as_float(INF_BITS);
     float cur = INF;
-    EvTime tc = ev_normal(INF, c);
+    EvFull tc = full_normal(INF, c);
     win = -1; wu1 = 0.0f; wu2 = 0.0f;
     const bool never_fixed = invalid && invalid[c];
     EvTime lastT = ev_normal(0.0f, 0); uint32_t lastK = 0, lastTv = 0; bool have_last = false;
@@ -621,24 +569,24 @@ struct InflationProblem {
       EvTime bT = lastT; float bu1 = 0, bu2 = 0; uint32_t bk = 0, bTv = 0; bool found = false;
       for (uint32_t k = kb; k < ke; ++k) {
         EvTime T; float u1, u2; uint32_t Tv;
-        if (!corner_time(k, band_end, T, Tv, u1, u2)) continue;
+        if (!corner_time(c, k, band_end, T, Tv, u1, u2)) continue;
         if (have_last && (k == lastK || !fires_before(lastT, lastK, lastTv, T, k, Tv))) continue;
         if (!found || fires_before(T, k, Tv, bT, bk, bTv)) { bT = T; bk = k; bTv = Tv; bu1 = u1; bu2 = u2; found = true; }
       }
       if (!found) break;
-      if (!never_fixed && !ev_less(bT, tc)) break;
+      if (!never_fixed && !less_T_full(bT, tc)) break;
       const float4 w = __ldg(&cor_wd[bk]);
       const float cand = inflation_candidate(bu1, bu2, w.z, w.y, w.x);
       if (cand < cur && backstep_ok(cand, bT, bTv, round)) {
         cur = cand; win = (int)bk; wu1 = bu1; wu2 = bu2;
-        if (bu1 <= max_distance && bu2 <= max_distance) tc = CvpProblem::accept_time(c, cand, bT);
+        if (bu1 <= max_distance && bu2 <= max_distance) accept(c, cand, bT, tc);
       }
       lastT = bT; lastK = bk; lastTv = bTv; have_last = true;
     }
     nd = cur; tc_out = tc;
   }
 
-  __device__ __forceinline__ void replay(uint32_t c, float band_end, uint32_t round, float& nd, EvTime& tc_out, int& win,
+  __device__ __forceinline__ void replay(uint32_t c, float band_end, uint32_t round, float& nd, EvFull& tc_out, int& win,
                                          float& wu1, float& wu2) const {
     const uint32_t kb = cor_ptr[c], ke = cor_ptr[c + 1];
     if (ke - kb > (uint32_t)MAXF) { replay_big(c, band_end, round, nd, tc_out, win, wu1, wu2); return; }
@@ -646,12 +594,12 @@ struct InflationProblem {
     int n = 0;
     for (uint32_t k = kb; k < ke && n < MAXF; ++k) {
       EvTime T; float u1, u2; uint32_t Tv;
-      if (!corner_time(k, band_end, T, Tv, u1, u2)) continue;
+      if (!corner_time(c, k, band_end, T, Tv, u1, u2)) continue;
       Tt[n] = T; U1[n] = u1; U2[n] = u2; K[n] = k; TV[n] = Tv; ++n;
     }
     const float INF = __uint_as_float(INF_BITS);
     float cur = INF;
-    EvTime tc = ev_normal(INF, c);                         // pop time = heap key; +inf while not inserted
+    EvFull tc = full_normal(INF, c);                       // pop time = heap key; +inf while not inserted
     win = -1; wu1 = 0.0f; wu2 = 0.0f;
     // an invalid vertex is popped but never fixed (:417-422): it keeps receiving updates from every face
     const bool never_fixed = invalid && invalid[c];
@@ -661,12 +609,15 @@ struct InflationProblem {
         if (fires_before(Tt[j], K[j], TV[j], Tt[b], K[b], TV[b])) b = j;
       const EvTime T = Tt[b]; const float u1 = U1[b], u2 = U2[b]; const uint32_t k = K[b], Tv = TV[b];
       Tt[b] = Tt[i]; U1[b] = U1[i]; U2[b] = U2[i]; K[b] = K[i]; TV[b] = TV[i];
-      if (!never_fixed && !ev_less(T, tc)) break;          // c was popped (and fixed) before this face fires
+      if (!never_fixed && !less_T_full(T, tc)) break;      // c was popped (and fixed) before this face fires
       const float4 w = __ldg(&cor_wd[k]);
       const float cand = inflation_candidate(u1, u2, w.z, w.y, w.x);   // a = |v2c|, b = |v1c|, c = |v1v2|
+#ifdef MNB_EMU_ACTIVE
+      if (getenv("MNB_DBG_V") && c == (uint32_t)atoi(getenv("MNB_DBG_V"))) fprintf(stderr, "[r%u] c=%u face k=%u Tv=%u T=(%g,%u,%g,%g) u1=%g u2=%g cand=%g cur=%g tc=(%g,%u,%g) n=%d\n", round, c, k, Tv, T.a1, T.root, T.a2, T.a3, u1, u2, cand, cur, tc.t.a1, tc.t.root, tc.t.a2, n);
+#endif
       if (cand < cur && backstep_ok(cand, T, Tv, round)) {                                    // :297 (non-finite candidates were mapped to +inf)
         cur = cand; win = (int)k; wu1 = u1; wu2 = u2;
-        if (u1 <= max_distance && u2 <= max_distance) tc = CvpProblem::accept_time(c, cand, T);   // :310 -> pq.insert(c, cand)
+        if (u1 <= max_distance && u2 <= max_distance) accept(c, cand, T, tc);   // :310 -> pq.insert(c, cand)
       }
     }
     nd = cur; tc_out = tc;
@@ -685,7 +636,7 @@ struct InflationProblem {
     float m = INF;
     for (uint32_t k = kb; k < ke; ++k) {
       EvTime T; float u1, u2; uint32_t Tv;
-      if (!corner_time(k, band_end, T, Tv, u1, u2)) continue;
+      if (!corner_time(c, k, band_end, T, Tv, u1, u2)) continue;
       const float4 w = __ldg(&cor_wd[k]);
       const float cand = inflation_candidate(u1, u2, w.z, w.y, w.x);
       if (cand > T.a1) {                                               // causal
@@ -705,9 +656,13 @@ struct InflationProblem {
 
   __device__ __forceinline__ bool recompute(uint32_t c, float band_end, float /*goal*/, uint32_t round, const Label& old, float& nd, float& ntau) {
     EvTime tc; int win; float wu1, wu2;
-    if (!replay_fast(c, band_end, nd, tc)) replay(c, band_end, round, nd, tc, win, wu1, wu2);   // (the collapse accepts no back-step: valid in strict rounds too)
+    if (!replay_fast(c, band_end, nd, tc)) {   // (the collapse accepts no back-step: valid in strict rounds too)
+      EvFull tf;
+      replay(c, band_end, round, nd, tf, win, wu1, wu2);
+      tc = finish(tf, old.t);
+    }
     ntau = tc.a1;
-    if (__float_as_uint(nd) == __float_as_uint(old.d) && ev_eq(tc, old.t)) return false;
+    if (__float_as_uint(nd) == __float_as_uint(old.d) && teq(tc, old.t)) return false;
     store_label(c, nd, tc, __float_as_uint(old.d) != INF_BITS, round);
     return true;
   }
@@ -717,10 +672,10 @@ struct InflationProblem {
 // Dijkstra: d[c] = min over expandable neighbours u of fl(d[u] + w(u,c));
 // among equal sums the neighbour that pops first wins (strict '<' at
 // dijkstra_mesh_planner.cpp:332): order (d[u], u).  Edge weights are >= 0 so a
-// vertex always pops at its own key: tau = d, minor = 2*id.
+// vertex always pops at its own key: tau = d, one level.
 //   adj_nw[k] = {neighbour id, float bits of the edge weight}
 // ---------------------------------------------------------------------------
-struct DijkstraProblem {
+struct DijkstraProblem : TimeAlg {
   static constexpr bool HAS_GOAL_TIME = false;    // edge weights >= 0: vertices pop in potential order, the test on the value is exact
   static constexpr bool CAN_SKIP = false;
   static constexpr int STAGNATION = STAGNATION_ROUNDS;
@@ -822,7 +777,7 @@ struct DijkstraEllProblem : DijkstraProblem {
     }
   }
   __device__ __forceinline__ void replay_sub8(uint32_t c, uint32_t j, bool has, const int4& ix, const float4&, float band_end,
-                                              float goal, uint32_t /*round*/, const uint32_t* mark, float& nd, EvTime& nt, int& deg_out,
+                                              float goal, uint32_t /*round*/, const uint32_t* mark, const EvTime& /*old_t*/, float& nd, EvTime& nt, int& deg_out,
                                               uint32_t& mk1, uint32_t& mk2, float& excl_min_out) const {
     excl_min_out = 0.0f;
     constexpr unsigned FULL = 0xffffffffu;
