@@ -10,7 +10,16 @@ e2e       = same plan through the C ABI with HOST buffers: vertex_costs + edge_w
             (mnb_set_costs) and potential/pred/direction/cutting_face copied D2H every step.
 roofline  = dominant kernel k_cvp: algorithmic bytes (208 B / settled vertex) / its
             CUDA-event duration, against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
-cpu_baseline = the oracle (reference algorithm restated, 1 thread, as the reference is per plan).
+cpu_baseline = the oracle (reference algorithm restated, 1 thread, as the reference is per plan), rebuilt on the box
+            with -O3 -march=native.
+config.parity    = the potentials / predecessors of the TIMED 5M plan against the oracle's plan on the same input
+                   (canonical ties); a deviation above 1e-4 fails the run (exit code 3 after the line is printed).
+config.config3   = BASELINE config 3 as a plan: fused layers -> Max combination with the inflation of (layer lethals +
+                   1000 obstacle discs) -> vertex_costs -> computeEdgeWeights(edge_cost_factor 1) -> CVP with
+                   cost_limit 1 on those costs, timed, with its own parity block.
+config.batched   = BASELINE config 4 (1024 goals, 1M-vertex terrain, goal k -> rank k mod N, potentials all-gathered):
+                   plans/s, HBM fraction and 8 sampled fields against the oracle -- inside `config` because the driver
+                   keeps that object for every N.
 --impl reference: the oracle on the host cores, one independent plan per thread.
 """
 from __future__ import annotations
@@ -108,6 +117,25 @@ def goal_for_rank(pos, faces, n, rank):
     return f, pos[faces[f]].mean(0).astype(np.float32)
 
 
+def parity_block(got_dist, got_pred, ref, got_cut=None):
+    """GPU plan against the oracle plan of the same input: bit mismatches, largest relative deviation, predecessor /
+    cutting-face mismatches (north star: potentials within 1e-4 rel, indices exact)"""
+    gd, rd = np.asarray(got_dist), ref["dist"]
+    fin = np.isfinite(rd)
+    same_set = bool(np.array_equal(np.isfinite(gd), fin))
+    rel = np.abs(gd[fin] - rd[fin]) / np.maximum(rd[fin], 1e-30) if same_set else np.array([np.inf])
+    out = {"vertices_compared": int(rd.size), "reached_sets_equal": same_set,
+           "n_mismatch": int((gd.view(np.uint32) != rd.view(np.uint32)).sum()), "max_rel": float(rel.max()) if rel.size else 0.0,
+           "pred_mismatch": None if got_pred is None else int((np.asarray(got_pred).astype(np.int64) != ref["pred"].astype(np.int64)).sum())}
+    if got_cut is not None:
+        out["cutting_face_mismatch"] = int((np.asarray(got_cut).astype(np.int64) != ref["cutting_face"].astype(np.int64)).sum())
+    out["ok"] = bool(same_set and out["max_rel"] <= 1e-4 and not out["pred_mismatch"])
+    return out
+
+
+CONFIG_KEYS = ("workload", "vertices", "faces", "edges", "plans_per_step_per_gpu", "sharding", "l2", "parity", "config3", "batched")
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; lvr2 / ROS 2 cannot be installed offline)
     on the host cores, on the SAME workload as the B200 arm: one full-field CVP plan on the 5M-vertex terrain per
@@ -118,6 +146,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle as O
+    flags = O.use_native_build()             # -O3 -march=native, built on this host
     n = args.size
     pos, faces = build_workload(n)
     om = O.OracleMesh(pos, faces)
@@ -142,11 +171,13 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "vertices/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * prop / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64 update / f32 store", "data": "synthetic",
-        "config": {"workload": f"cvp_full_field_terrain_{n}x{n}", "vertices": om.V, "plans_per_step": 1,
-                   "note": "reference algorithm restated (oracle port; lvr2/ROS 2 not installable offline); "
-                           "timed region = heap loop (cvp_mesh_planner.cpp:744-894), wall per step "
-                           f"{1e3 * dt / args.steps:.0f} ms incl. array init"},
-        "cpu_baseline": {"value": value, "unit": "vertices/s", "cores": 1, "kind": "port",
+        "config": {"workload": f"cvp_full_field_terrain_{n}x{n}", "vertices": om.V, "faces": om.F, "edges": om.E,
+                   "plans_per_step_per_gpu": 1,
+                   "sharding": "host CPU, one thread per plan (the reference's loop is single-threaded per plan, mesh_planner_execution.cpp:55-66)",
+                   "l2": "n/a (CPU); timed region = heap loop (cvp_mesh_planner.cpp:744-894), wall per step "
+                         f"{1e3 * dt / args.steps:.0f} ms incl. array init",
+                   "parity": None, "config3": None, "batched": None},
+        "cpu_baseline": {"value": value, "unit": "vertices/s", "cores": 1, "kind": "port", "flags": flags,
                          "sample": f"{args.steps} full-field plans on the {n}x{n} terrain; the reference's loop is single-threaded per plan"},
         "e2e": {"value": value, "unit": "vertices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -167,9 +198,10 @@ def run_reference(args):
         th = [threading.Thread(target=work, args=(i,)) for i in range(nthreads)]
         [t.start() for t in th]; [t.join() for t in th]
         dtb = time.perf_counter() - t0
-        line["batched"] = {"plans_per_s": nthreads / dtb, "goals": nthreads, "mesh_vertices": int(bom.V), "cores": nthreads,
-                           "vertex_relaxations_per_s": nthreads * bom.V / dtb,
-                           "sample": f"{nthreads} concurrent full-field plans (one per host thread) on the {nb}x{nb} terrain"}
+        line["config"]["batched"] = {"plans_per_s": nthreads / dtb, "goals": nthreads, "mesh_vertices": int(bom.V), "cores": nthreads,
+                                     "vertex_relaxations_per_s": nthreads * bom.V / dtb, "ms_per_batch": 1e3 * dtb,
+                                     "sample": f"{nthreads} concurrent full-field plans (one per host thread, {cores} logical cores) on the {nb}x{nb} terrain"}
+        line["batched"] = line["config"]["batched"]
     print(json.dumps(line))
 
 
@@ -188,6 +220,9 @@ def main():
     ap.add_argument("--batch-goals", type=int, default=1024, help="goals of the batched leg (config 4); 0 disables it")
     ap.add_argument("--batch-size", type=int, default=1000, help="grid side of the batched leg's mesh")
     ap.add_argument("--batch-steps", type=int, default=2)
+    ap.add_argument("--batch-delta", type=float, default=0.0, help="band width of the batched leg (0 = library default)")
+    ap.add_argument("--batch-cluster", type=int, default=0, help="CTAs per wavefront of the batched leg (0 = chosen per call)")
+    ap.add_argument("--no-config3", action="store_true")
     ap.add_argument("--no-other-kernels", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -260,6 +295,10 @@ def main():
         dt_max = dt; total_settled = float(settled)
     clocks = sampler.stop(local)
     value = total_settled * args.steps / dt_max
+    # the result of the LAST TIMED plan, for the parity block (rank 0)
+    h_timed = None
+    if rank == 0 and not args.no_cpu_baseline:
+        h_timed = {"dist": d_dist.cpu().numpy(), "pred": d_pred.cpu().numpy().view(np.uint32), "cut": d_cut.cpu().numpy()}
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
     from mesh_navigation_b200.api import CVPMeshPlanner
@@ -296,40 +335,63 @@ def main():
           nb = args.batch_size
           bpos, bfaces = build_workload(nb)
           bm = MeshMap(bpos, bfaces, device=local)
-          bm.setCosts(np.zeros(bm.V, np.float32), bm.edgeDistances())
+          bed = bm.edgeDistances()
+          bm.setCosts(np.zeros(bm.V, np.float32), bed)
+          if args.batch_delta > 0 or args.batch_cluster:
+              bm.set_tuning(args.batch_delta, args.batch_cluster, 0)
           goals = synth.batch_goal_vertices(bm.V, args.batch_goals, seed=1234)
           gi, gj = np.minimum(goals % nb, nb - 2), np.minimum(goals // nb, nb - 2)
           sfs = (2 * (gj * (nb - 1) + gi)).astype(np.uint32)
           sps = bpos[bfaces[sfs]].mean(1).astype(np.float32)
           bm.use_device_pointers(True)
-          b_kernel_ms = []
+          b_kernel_ms, b_gather_ms = [], []
 
           def compute_chunk(idx, out):
               bm.cvp_batch_dev(sfs[idx], sps[idx], 1.0, out.data_ptr())
               b_kernel_ms.append(bm.stats()["kernel_ms"])
 
           def batch_step():
-              return PL.sharded_potentials(compute_chunk, args.batch_goals, bm.V, rank=rank, world=world, device=dev,
-                                           chunk=512, dist=dist if world > 1 else None, torch=torch)
+              tm = {}
+              res = PL.sharded_potentials(compute_chunk, args.batch_goals, bm.V, rank=rank, world=world, device=dev,
+                                          chunk=0, dist=dist if world > 1 else None, torch=torch, timings=tm)
+              b_gather_ms.append(tm.get("gather_ms", 0.0))
+              return res
 
-          batch_step(); sync_all()
-          b_kernel_ms.clear()
+          res = batch_step(); sync_all()
+          b_kernel_ms.clear(); b_gather_ms.clear()
           t0 = time.perf_counter()
           for _ in range(args.batch_steps):
+              del res
               res = batch_step()
           sync_all()
           dtb = time.perf_counter() - t0
-          tb = torch.tensor([dtb], dtype=torch.float64, device=dev)
+          tb = torch.tensor([dtb, sum(b_kernel_ms), sum(b_gather_ms)], dtype=torch.float64, device=dev)
           if world > 1:
               dist.all_reduce(tb, op=dist.ReduceOp.MAX)
           dtb = float(tb[0])
           bm.use_device_pointers(False)
           plans_s = args.batch_goals * args.batch_steps / dtb
-          b_achieved = CVP_BYTES_PER_VERTEX * bm.V * len(PL.shard_indices(args.batch_goals, rank, world)) * args.batch_steps / (sum(b_kernel_ms) * 1e-3) / 1e9
-          batched = {"plans_per_s": plans_s, "goals": args.batch_goals, "mesh_vertices": int(bm.V), "n_gpus": world,
+          my_goals = len(PL.shard_indices(args.batch_goals, rank, world))
+          b_achieved = CVP_BYTES_PER_VERTEX * bm.V * my_goals * args.batch_steps / (sum(b_kernel_ms) * 1e-3) / 1e9
+          batched = {"plans_per_s": plans_s, "goals": args.batch_goals, "goals_per_gpu": my_goals, "mesh_vertices": int(bm.V), "n_gpus": world,
                      "vertex_relaxations_per_s": plans_s * bm.V, "ms_per_batch": 1e3 * dtb / args.batch_steps,
-                     "scaling": "strong (fixed goal count)", "gather": "NCCL all_gather of float[goals][V], overlapped per chunk" if world > 1 else "none (single GPU)",
-                     "roofline_hbm_frac_rank0": b_achieved / peaks()[0], "achieved_gbs_rank0": b_achieved}
+                     "compute_ms_per_batch_max_rank": float(tb[1]) / args.batch_steps, "gather_ms_per_batch_max_rank": float(tb[2]) / args.batch_steps,
+                     "scaling": "strong (fixed goal count)",
+                     "gather": "one NCCL all_gather_into_tensor of float[goals][V] into the final buffer after the rank's batch call" if world > 1 else "none (single GPU)",
+                     "roofline_hbm_frac_rank0": b_achieved / peaks()[0], "achieved_gbs_rank0": b_achieved,
+                     "recomputes_per_vertex": bm.stats()["recomputes"] / max(1, my_goals) / bm.V}
+          if rank == 0 and not args.no_cpu_baseline:
+              # 8 of the fields against the oracle (every rank's shard is covered: the gathered buffer is in goal order)
+              from oracle import oracle as O
+              bom = O.OracleMesh(bpos, bfaces)
+              bvc = np.zeros(bm.V, np.float32)
+              rows = PL.goal_order_rows(res, args.batch_goals, bm.V) if world > 1 else res
+              samp = np.unique(np.linspace(0, args.batch_goals - 1, 8).astype(np.int64))
+              worst, nmis = 0.0, 0
+              for k in samp:
+                  pb = parity_block(rows[int(k)].cpu().numpy(), None, bom.cvp(bed, bvc, int(sfs[k]), sps[k]))
+                  worst = max(worst, pb["max_rel"]); nmis += pb["n_mismatch"]
+              batched["parity_sampled"] = {"fields": [int(k) for k in samp], "n_mismatch": int(nmis), "max_rel": worst, "ok": bool(worst <= 1e-4)}
           del res
           bm.close()
       except Exception as ex:      # a secondary leg must never cost the headline line (all ranks fail alike: no collective is left half-done)
@@ -360,7 +422,7 @@ def main():
         def leg_layers():
             for rep in range(2):
                 Ly = mm.computeLayers()
-            shared["lethal_mask"] = Ly["lethal_mask"]; shared["combined"] = Ly["combined"]
+            shared["lethal_mask"] = Ly["lethal_mask"]; shared["combined"] = Ly["combined"]; shared["layers_ms"] = Ly["kernel_ms"]
             return {"kernel_ms": Ly["kernel_ms"], "hbm_frac": 837 * V / (Ly["kernel_ms"] * 1e-3) / 1e9 / hbm0}
 
         def leg_inflation():
@@ -371,6 +433,49 @@ def main():
             nin = int(np.isfinite(I["dist"]).sum())
             return {"kernel_ms": I["kernel_ms"], "rounds": int(I["rounds"]), "lethal_vertices": int(le.size), "labelled_vertices": nin,
                     "hbm_frac": 212 * nin / (I["kernel_ms"] * 1e-3) / 1e9 / hbm0}
+
+        def leg_config3():
+            """BASELINE config 3 as a PLAN on the 5M map (mesh_map.cpp:437-448,539-553; inflation_layer.cpp:563-596): the
+            layer stack's costs (fused layers, Max-combined with the inflation of layer lethals + 1000 obstacle discs)
+            become vertex_costs, computeEdgeWeights(edge_cost_factor 1) the planner's weights, and a full-field CVP plan
+            with cost_limit 1 runs on them -- lethal walls, cost-weighted non-geometric weights, back-steps, cascades"""
+            static = shared["combined"]; le = shared["lethals"]
+            infl = InflationLayer(mm)
+            I = infl.waveCostInflation(le)
+            final = np.maximum(static, np.nan_to_num(I["cost"], nan=0.0)).astype(np.float32)    # MaxCombinationLayer, defaults 0
+            t0 = time.perf_counter(); w1 = mm.computeEdgeWeights(final, 1.0); t_w = time.perf_counter() - t0
+            free = np.where(final < 0.5)[0]
+            c0 = synth.nearest_vertex(pos, [n * 0.05, n * 0.05, float(pos[:, 2].mean())])
+            v = int(free[np.argmin(np.linalg.norm(pos[free] - pos[c0], axis=1))])
+            i, j = min(v % n, n - 2), min(v // n, n - 2)
+            f = 2 * (j * (n - 1) + i)
+            while not (final[faces[f]] < 1.0).all():
+                f += 1
+            spc = pos[faces[f]].mean(0).astype(np.float32)
+            pl3 = CVPMeshPlanner(mm, cost_limit=1.0)
+            best = None
+            for rep in range(3):
+                g = pl3.waveFrontPropagation(f, spc)
+                best = g["kernel_ms"] if best is None else min(best, g["kernel_ms"])
+            reached = int(np.isfinite(g["dist"]).sum())
+            out = {"stages_ms": {"fused_layers_kernel": shared.get("layers_ms"), "inflation_kernel": I["kernel_ms"], "edge_weights_wall": 1e3 * t_w, "cvp_kernel": best},
+                   "kernel_ms": best, "reached_vertices": reached, "vertices_per_s": reached / (best * 1e-3),
+                   "hbm_frac": CVP_BYTES_PER_VERTEX * reached / (best * 1e-3) / 1e9 / hbm0,
+                   "lethal_vertices": int((final >= 1.0).sum()), "rounds": int(g["rounds"]), "recomputes_per_vertex": g["recomputes"] / max(1, reached),
+                   "deep_cascade_labels": int(g.get("deep_labels", 0)), "level_pool_words": int(g.get("pool_words", 0)), "outcome": int(g["outcome"])}
+            if not args.no_cpu_baseline:
+                from oracle import oracle as O
+                om3 = O.OracleMesh(pos, faces)
+                wref = om3.edge_weights(final, ed, 1.0)
+                ref3 = om3.cvp(wref, final, f, spc, cost_limit=1.0)
+                pb = parity_block(g["dist"], g["pred"], ref3, g["cutting_face"])
+                pb["edge_weights_bit_identical"] = bool((w1.view(np.uint32) == wref.view(np.uint32)).all())
+                refi = om3.inflation(ed, le)
+                pb["inflation_dist_mismatch"] = int((I["dist"].view(np.uint32) != refi["dist"].view(np.uint32)).sum())
+                pb["oracle_backsteps"] = int(ref3["backsteps"]); pb["oracle_cvp_seconds"] = float(ref3["seconds"])
+                out["parity"] = pb
+            mm.setCosts(vc, ed)
+            return out
 
         def leg_dynamic_update():
             """one dynamic-obstacle cycle (SURVEY 3.4) on the 5M map: the 1000 discs move; InflationLayer::onInputChanged,
@@ -467,29 +572,38 @@ def main():
         leg("dijkstra_full_field", leg_dijkstra)
         leg("fused_layers", leg_layers)
         leg("inflation", leg_inflation)
+        if not args.no_config3:
+            leg("config3_plan", leg_config3)
         leg("dynamic_obstacle_update", leg_dynamic_update)
         leg("make_plan_corner_to_corner", leg_make_plan)
         leg("optin_variants", leg_optin_variants)
         shared.clear()
 
+    exit_code = 0
     if rank == 0:
         hbm, which = peaks()
         k_ms = float(np.mean(kernel_ms))
         achieved = CVP_BYTES_PER_VERTEX * settled / (k_ms * 1e-3) / 1e9
+        traffic = ncu_traffic(f"cvp_full_field_terrain_{n}x{n}")
+        config = {"workload": f"cvp_full_field_terrain_{n}x{n}", "vertices": V, "faces": mm.F, "edges": E,
+                  "plans_per_step_per_gpu": 1, "sharding": "one goal per GPU (distinct goals within 2% of the map centre: same wave depth on every rank), potentials all-gathered (NCCL)" if world > 1 else "single GPU",
+                  "l2": "256 MB buffer rewritten between timed iterations; working set (>500 MB) exceeds L2",
+                  "parity": None, "config3": (other or {}).get("config3_plan"), "batched": batched}
         line = {
             "metric": METRIC, "value": value, "unit": "vertices/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64 update / f32 store", "data": "synthetic",
-            "config": {"workload": f"cvp_full_field_terrain_{n}x{n}", "vertices": V, "faces": mm.F, "edges": E,
-                       "plans_per_step_per_gpu": 1, "sharding": "one goal per GPU (distinct goals within 2% of the map centre: same wave depth on every rank), potentials all-gathered (NCCL)" if world > 1 else "single GPU",
-                       "l2": "256 MB buffer rewritten between timed iterations; working set (>500 MB) exceeds L2"},
+            "config": config,
             "e2e": {"value": e2e_value, "unit": "vertices/s", "h2d_bytes_per_step": int(4 * V + 4 * E),
                     "d2h_bytes_per_step": int(16 * V), "steps": e2e_steps},
             "gpu_launches": int(args.steps * st["kernel_launches"]),
             "roofline": {"bound": "hbm", "kernel": "k_cvp_grid", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                         "frac": achieved / hbm, "traffic": ncu_traffic(f"cvp_full_field_terrain_{n}x{n}"), "peak_source": which,
+                         "frac": achieved / hbm, "traffic": traffic["bytes"] if isinstance(traffic, dict) else traffic,
+                         "traffic_source": traffic.get("source") if isinstance(traffic, dict) else None, "peak_source": which,
                          "kernel_ms": k_ms, "rounds": int(st["rounds"]), "recomputes_per_vertex": st["recomputes"] / V,
                          "deep_cascade_labels": int(st.get("deep_labels", 0)),
+                         "batched_plans_per_s": batched.get("plans_per_s") if batched else None,
+                         "batched_hbm_frac": batched.get("roofline_hbm_frac_rank0") if batched else None,
                          "note": "single wavefront is dependency-latency bound (SURVEY.md H3)"},
             "clocks": clocks,
         }
@@ -499,19 +613,31 @@ def main():
             line["other_kernels"] = other
         if not args.no_cpu_baseline:
             from oracle import oracle as O
+            flags = O.use_native_build()             # -O3 -march=native on this host
             om = O.OracleMesh(pos, faces)            # same mesh, same goal as the timed plans
             bed = om.edge_distances(); bvc = np.zeros(om.V, np.float32)
+            # parity of the TIMED plan: the oracle's plan on the same input in canonical tie order
+            ref = om.cvp(bed, bvc, sf, sp)
+            config["parity"] = parity_block(h_timed["dist"], h_timed["pred"], ref, h_timed["cut"])
+            config["parity"]["deep_cascade_labels"] = int(st.get("deep_labels", 0))
             tot_s, tot_v, reps = 0.0, 0, 0
             while tot_s < 6.0 and reps < 10:
                 r = om.cvp(bed, bvc, sf, sp, canonical_ties=False)
                 tot_s += r["seconds"]; tot_v += int(np.isfinite(r["dist"]).sum()); reps += 1
-            line["cpu_baseline"] = {"value": tot_v / tot_s, "unit": "vertices/s", "cores": 1, "kind": "port",
+            line["cpu_baseline"] = {"value": tot_v / tot_s, "unit": "vertices/s", "cores": 1, "kind": "port", "flags": flags,
                                     "sample": f"{reps} full-field CVP plans on the same {n}x{n} terrain (heap loop only); "
                                               "the reference's loop is single-threaded per plan"}
+            bad = [k for k, pbk in (("headline", config["parity"]), ("config3", (config["config3"] or {}).get("parity")),
+                                    ("batched", (batched or {}).get("parity_sampled"))) if pbk is not None and not pbk.get("ok", True)]
+            if bad:
+                line["parity_failed"] = bad
+                exit_code = 3
         print(json.dumps(line))
     mm.close()
     if world > 1:
         dist.destroy_process_group()
+    if exit_code:
+        sys.exit(exit_code)       # the line above is printed either way; a parity failure must not pass silently
 
 
 if __name__ == "__main__":

@@ -321,8 +321,9 @@ __device__ __forceinline__ void group_sync(unsigned int* bar = nullptr) {
 }
 
 // per-CTA staging of appends to the next candidate list
-struct Stage {
-  static constexpr int CAP = 3072;
+template <int CAP_>
+struct StageT {
+  static constexpr int CAP = CAP_;
   static constexpr int SW_CAP = 1024;     // stage slots that take part in the in-round sweeps
   uint32_t buf[CAP];
   unsigned int n;
@@ -330,6 +331,7 @@ struct Stage {
   unsigned int m_tau;
   unsigned int lo;
 };
+using Stage = StageT<3072>;
 // in-round sweeps (run_band_rounds_sub8<.., true>): per stage slot, the version of its vertex at the last evaluation
 // and a copy of its label; the per-sweep dirty list.  Lives in the shared memory of the whole-grid kernel only.
 struct SweepStage {
@@ -354,10 +356,11 @@ __device__ __forceinline__ void stage_push_seen(Stage& st, SweepStage& ss, uint3
 }
 
 // flush the CTA stage to the global list (all threads of the CTA call this)
-__device__ __forceinline__ void stage_flush(Stage& st, uint32_t* list_next, unsigned int* count_next,
+template <class S>
+__device__ __forceinline__ void stage_flush(S& st, uint32_t* list_next, unsigned int* count_next,
                                             unsigned int* g_m_tau, unsigned int* g_lo) {
   __syncthreads();
-  const unsigned int n = st.n < Stage::CAP ? st.n : Stage::CAP;
+  const unsigned int n = st.n < (unsigned)S::CAP ? st.n : (unsigned)S::CAP;
   if (threadIdx.x == 0) {
     st.base = n ? atomicAdd(count_next, n) : 0u;
     if (st.m_tau != INF_BITS) atomicMin(g_m_tau, st.m_tau);
@@ -437,7 +440,11 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
       const uint32_t c = __ldcg(&list_r[i]);
       const Label old = prob.load_label(c);
       const float d = old.d, tau = old.t.a1;
-      if (tau < m_prev && tau < band_end_prev) {
+      // a vertex that is never fixed (inflation: invalid vertices pop without being fixed, inflation_layer.cpp:417-422) keeps
+      // receiving updates from faces that fire AFTER its own pop: its label is not a function of earlier events only, so it
+      // stays a candidate until a whole round went by without any change, and it does not hold the band back
+      const bool nf = prob.never_fixed(c);
+      if (tau < m_prev && tau < band_end_prev && (!nf || __float_as_uint(m_prev) == INF_BITS)) {
         // converged prefix: the sequential algorithm has popped c with exactly this label
         mark[c] = MARK_FIXED;
         my_settled++;
@@ -463,7 +470,8 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
         // evaluation -> same inputs, same label.  (delta = inf here: no source is ever excluded by the band end.)
         const uint32_t le = __ldcg(&prob.last_eval[c]), dr = __ldcg(&prob.dirty_round[c]);
         if (le != 0u && dr < le) {
-          my_lo = fminf(my_lo, tau); my_skipped++;
+          if (!nf) my_lo = fminf(my_lo, tau);
+          my_skipped++;
           stage_push(st, c, list_n, &ctl->count[next]);
           continue;
         }
@@ -476,7 +484,7 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
         __stcg(&prob.last_eval[c], prob.deferred_flag ? 0u : r + 1u);
         if (changed) prob.activate(c, [&](uint32_t x) { __stcg(&prob.dirty_round[x], r + 1u); });
       }
-      my_lo = fminf(my_lo, ntau);      // smallest pop time still in flight: the band follows it
+      if (!nf) my_lo = fminf(my_lo, ntau);      // smallest pop time still in flight: the band follows it
       stage_push(st, c, list_n, &ctl->count[next]);
       // a vertex that holds a finite label pulls its neighbours into the candidate set (once)
       if (__float_as_uint(nd) != INF_BITS && __ldcg(&mark[c]) == MARK_CAND) {

@@ -20,6 +20,7 @@ struct WaveWorkspace {     // per group (index g): state + g*V etc.
   uint32_t* pool;    // level pool: records of pop times with more than 3 cascade levels, pool_cap words per group
   uint32_t pool_cap;
   uint32_t* last_eval; uint32_t* dirty; uint32_t* excl;   // clean-candidate skip stamps (problems.cuh)
+  uint4* skipw;      // clean-candidate words of the batch round loop (batch_engine.cuh)
   uint32_t* chg;
   uint32_t* ver;     // single-plan only (V entries): input versions for the in-round sweeps
   uint32_t* mark;
@@ -71,6 +72,8 @@ __device__ __forceinline__ void ctl_reset(GroupCtl* ctl, unsigned int n0, float 
   ctl->goal_time[0] = INF_BITS; ctl->goal_time[1] = 0u; ctl->goal_time[2] = 0u; ctl->goal_time[3] = 0u; ctl->goal_time[4] = 0u; ctl->goal_time[5] = 0u;
   ctl->pool_top = 0u;
 }
+
+#include "batch_engine.cuh"
 
 #ifndef MNB_CVP_MINBLOCKS
 #define MNB_CVP_MINBLOCKS 1
@@ -132,6 +135,7 @@ __global__ void __launch_bounds__(MNB_CVP_THREADS, MNB_CVP_MINBLOCKS) k_cvp(cons
     }
     const float seed_min = fminf(sd[0], fminf(sd[1], sd[2]));
     const float seed_max = fmaxf(sd[0], fmaxf(sd[1], sd[2]));
+    prob.seed_max_d = seed_max;
     uint32_t r0 = 0xffffffffu, r1 = 0xffffffffu, r2 = 0xffffffffu;
     const int has_robot = single && a.robot_face >= 0;
     if (has_robot) {
@@ -170,6 +174,84 @@ __global__ void __launch_bounds__(MNB_CVP_THREADS, MNB_CVP_MINBLOCKS) k_cvp(cons
     if (a.out_dist) {
       float* od = a.out_dist + (size_t)q * V;
       for (uint32_t v = gtid; v < V; v += gthreads) od[v] = __uint_as_float(state[v].x);
+    }
+    group_sync<CS>();
+  }
+}
+
+// Batches of full-field plans (mnb_cvp_batch): the lean round loop of batch_engine.cuh.  One wavefront per CTA (CS = 1) or
+// per cluster of CS CTAs; persistent groups pull goal indices from an atomic counter.
+#ifndef MNB_BATCH_THREADS
+#define MNB_BATCH_THREADS 512
+#endif
+#ifndef MNB_BATCH_MINBLOCKS
+#define MNB_BATCH_MINBLOCKS 2
+#endif
+template <int CS>
+__global__ void __launch_bounds__(MNB_BATCH_THREADS, MNB_BATCH_MINBLOCKS) k_cvp_batch(const CvpKernelArgs a) {
+  __shared__ BatchStage st;
+  __shared__ BatchWork wk;
+  uint32_t g, gthreads, gtid;
+  group_coords<CS>(g, gthreads, gtid);
+  const uint32_t V = a.V;
+  BatchGroup G;
+  G.state = a.ws.state + (size_t)g * V; G.root_arr = a.ws.root + (size_t)g * V; G.ext_arr = a.ws.ext + (size_t)g * V;
+  G.chg = a.ws.chg + (size_t)g * V; G.mark = a.ws.mark + (size_t)g * V; G.pool = a.ws.pool + (size_t)g * a.ws.pool_cap;
+  G.pool_cap = a.ws.pool_cap; G.ctl = a.ws.ctl + g; G.skipw = a.ws.skipw + (size_t)g * V;
+  uint32_t* list0 = a.ws.list0 + (size_t)g * V;
+  uint32_t* list1 = a.ws.list1 + (size_t)g * V;
+  GroupCtl* ctl = G.ctl;
+  if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; wk.n = 0; }
+  __syncthreads();
+  for (;;) {
+    if (gtid == 0) ctl->query = atomicAdd(a.next_query, 1u);
+    group_sync<CS>();
+    const uint32_t q = __ldcg(&ctl->query);
+    if (q >= a.n_queries) break;
+    for (uint32_t v = gtid; v < V; v += gthreads) { G.state[v] = state_inf(); G.mark[v] = MARK_NONE; G.chg[v] = 0u; G.skipw[v] = make_uint4(INF_BITS, INF_BITS, 0u, 0u); }
+    group_sync<CS>();
+    const uint32_t sf = a.seed_faces[q];
+    BatchSeeds sd;
+    sd.s0 = a.faces[3 * (size_t)sf]; sd.s1 = a.faces[3 * (size_t)sf + 1]; sd.s2 = a.faces[3 * (size_t)sf + 2]; sd.noexpand = 0;
+    float sdist[3];
+    {
+      const uint32_t sv[3] = {sd.s0, sd.s1, sd.s2};
+      for (int k = 0; k < 3; ++k) {   // cvp:719-728
+        const float dx = a.seed_pos[3 * (size_t)q] - a.pos[3 * (size_t)sv[k]];
+        const float dy = a.seed_pos[3 * (size_t)q + 1] - a.pos[3 * (size_t)sv[k] + 1];
+        const float dz = a.seed_pos[3 * (size_t)q + 2] - a.pos[3 * (size_t)sv[k] + 2];
+        sdist[k] = sqrtf(dx * dx + dy * dy + dz * dz);
+        if (((double)a.cost[sv[k]] >= a.cost_limit) || (a.invalid && a.invalid[sv[k]])) sd.noexpand |= (1u << k);  // cvp:757,760
+      }
+    }
+    const float seed_min = fminf(sdist[0], fminf(sdist[1], sdist[2]));
+    sd.seed_max = fmaxf(sdist[0], fmaxf(sdist[1], sdist[2]));
+    if (gtid == 0) {
+      const uint32_t sv[3] = {sd.s0, sd.s1, sd.s2};
+      for (int k = 0; k < 3; ++k) {
+        G.state[sv[k]] = make_uint4(__float_as_uint(sdist[k]), __float_as_uint(sdist[k]), 0u, 0u);
+        G.mark[sv[k]] = MARK_FIXED;
+      }
+      unsigned int n0 = 0;
+      for (int k = 0; k < 3; ++k) {
+        const uint32_t kb = a.cor_ptr[sv[k]], ke = a.cor_ptr[sv[k] + 1];
+        for (uint32_t kk = kb; kk < ke; ++kk) {
+          const int4 ix = a.cor_idx[kk];
+          const uint32_t xs[2] = {(uint32_t)ix.x, (uint32_t)ix.y};
+          for (int t = 0; t < 2; ++t) {
+            const uint32_t x = xs[t];
+            if (G.mark[x] == MARK_NONE && !(a.invalid && a.invalid[x]) && !((double)a.cost[x] >= a.cost_limit)) { G.mark[x] = MARK_CAND; list0[n0++] = x; }
+          }
+        }
+      }
+      ctl_reset(ctl, n0, seed_min);
+    }
+    group_sync<CS>();
+    run_band_rounds_batch<CS>(a, G, list0, list1, st, wk, a.delta, gthreads, gtid, sd, nextafterf(sd.seed_max, __uint_as_float(INF_BITS)));
+    group_sync<CS>();
+    if (a.out_dist) {
+      float* od = a.out_dist + (size_t)q * V;
+      for (uint32_t v = gtid; v < V; v += gthreads) od[v] = __uint_as_float(__ldcg(&G.state[v]).x);
     }
     group_sync<CS>();
   }
@@ -220,6 +302,7 @@ __global__ void __launch_bounds__(512, MNB_GRID_MINBLOCKS) k_cvp_grid(const CvpK
   }
   const float seed_min = fminf(sd[0], fminf(sd[1], sd[2]));
   const float seed_max = fmaxf(sd[0], fmaxf(sd[1], sd[2]));
+  prob.seed_max_d = seed_max;
   uint32_t r0 = 0xffffffffu, r1 = 0xffffffffu, r2 = 0xffffffffu;
   const int has_robot = a.robot_face >= 0;
   if (has_robot) {

@@ -71,7 +71,7 @@ struct mnb_ctx {
   uint32_t* d_upd_ids = nullptr; float* d_upd_costs = nullptr; size_t upd_cap = 0; size_t upd_cost_cap = 0;
   uint32_t* d_changed = nullptr; unsigned int* d_tile_count = nullptr; unsigned int* d_total = nullptr;
   // tuning
-  float delta = 0.3f; int cluster = -1 /* -1: whole-grid cooperative kernel for single plans */; int batch_cluster = 1; int threads = 512;
+  float delta = 0.3f; int cluster = -1 /* -1: whole-grid cooperative kernel for single plans */; int batch_cluster = 0 /* 0: chosen per call from the goal count */; int threads = 512;
   int grid_blocks_per_sm = 0;
   int infl_skip_clean = 1;     // clean-candidate skip of the inflation wave (MNB_INFL_SKIP=0 turns it off)
   int layers_smem = 0;         // k_layers with the seen-set / stack in shared memory (MNB_LAYERS_SMEM=1, mnb_debug_set_layers_smem)
@@ -102,7 +102,7 @@ static void free_mesh(mnb_ctx* c) {
   dfree(c->d_pos); dfree(c->d_faces); dfree(c->d_edges); dfree(c->d_cor_ptr); dfree(c->d_cor_idx); dfree(c->d_cor_eid);
   dfree(c->d_cor_w); dfree(c->d_cor_wd); dfree(c->d_ell_idx); dfree(c->d_ell_eid); dfree(c->d_ell_w); dfree(c->d_ell_wd); dfree(c->d_ell_geo); dfree(c->d_adj_ptr); dfree(c->d_adj_nbr); dfree(c->d_adj_eid); dfree(c->d_adj_nw); dfree(c->d_ell_adj);
   dfree(c->d_edge_dist); dfree(c->d_edge_w); dfree(c->d_cost); dfree(c->d_invalid);
-  dfree(c->ws.state); dfree(c->ws.ext); dfree(c->ws.pool); dfree(c->ws.root); dfree(c->ws.last_eval); dfree(c->ws.dirty); dfree(c->ws.excl); dfree(c->ws.chg); dfree(c->ws.ver); dfree(c->ws.mark); dfree(c->ws.list0); dfree(c->ws.list1); dfree(c->ws.ctl);
+  dfree(c->ws.state); dfree(c->ws.ext); dfree(c->ws.pool); dfree(c->ws.skipw); dfree(c->ws.root); dfree(c->ws.last_eval); dfree(c->ws.dirty); dfree(c->ws.excl); dfree(c->ws.chg); dfree(c->ws.ver); dfree(c->ws.mark); dfree(c->ws.list0); dfree(c->ws.list1); dfree(c->ws.ctl);
   c->ws_groups = 0;
   dfree(c->d_out_dist); c->out_dist_cap = 0; dfree(c->d_out_pred); dfree(c->d_out_dir); dfree(c->d_out_cut);
   dfree(c->d_infl_invalid); dfree(c->d_out_cost);
@@ -118,10 +118,10 @@ static void free_mesh(mnb_ctx* c) {
 
 static int32_t ensure_workspace(mnb_ctx* ctx, uint32_t groups) {
   if (groups <= ctx->ws_groups) return MNB_OK;
-  dfree(ctx->ws.state); dfree(ctx->ws.ext); dfree(ctx->ws.pool); dfree(ctx->ws.root); dfree(ctx->ws.last_eval); dfree(ctx->ws.dirty); dfree(ctx->ws.excl); dfree(ctx->ws.chg); dfree(ctx->ws.ver); dfree(ctx->ws.mark); dfree(ctx->ws.list0); dfree(ctx->ws.list1); dfree(ctx->ws.ctl);
+  dfree(ctx->ws.state); dfree(ctx->ws.ext); dfree(ctx->ws.pool); dfree(ctx->ws.skipw); dfree(ctx->ws.root); dfree(ctx->ws.last_eval); dfree(ctx->ws.dirty); dfree(ctx->ws.excl); dfree(ctx->ws.chg); dfree(ctx->ws.ver); dfree(ctx->ws.mark); dfree(ctx->ws.list0); dfree(ctx->ws.list1); dfree(ctx->ws.ctl);
   ctx->ws_groups = 0;
   const size_t n = (size_t)groups * ctx->V;
-  CK(dalloc(&ctx->ws.state, n)); CK(dalloc(&ctx->ws.ext, n)); CK(dalloc(&ctx->ws.root, n)); CK(dalloc(&ctx->ws.last_eval, n)); CK(dalloc(&ctx->ws.dirty, n)); CK(dalloc(&ctx->ws.excl, n)); CK(dalloc(&ctx->ws.chg, n)); CK(dalloc(&ctx->ws.ver, (size_t)ctx->V)); CK(dalloc(&ctx->ws.mark, n)); CK(dalloc(&ctx->ws.list0, n)); CK(dalloc(&ctx->ws.list1, n));
+  CK(dalloc(&ctx->ws.state, n)); CK(dalloc(&ctx->ws.ext, n)); CK(dalloc(&ctx->ws.skipw, n)); CK(dalloc(&ctx->ws.root, n)); CK(dalloc(&ctx->ws.last_eval, n)); CK(dalloc(&ctx->ws.dirty, n)); CK(dalloc(&ctx->ws.excl, n)); CK(dalloc(&ctx->ws.chg, n)); CK(dalloc(&ctx->ws.ver, (size_t)ctx->V)); CK(dalloc(&ctx->ws.mark, n)); CK(dalloc(&ctx->ws.list0, n)); CK(dalloc(&ctx->ws.list1, n));
   // level pool (band_engine.cuh): pop times with more than 3 cascade levels keep their tails here; 2 words per vertex
   // hold the deepest flooded pockets randomised testing has produced with room to spare; exhaustion is reported
   ctx->ws.pool_cap = (uint32_t)std::min<size_t>(std::max<size_t>(65536, 2 * (size_t)ctx->V), 0x7fffffffu);
@@ -579,10 +579,20 @@ int32_t mnb_cvp_batch(mnb_ctx* ctx, uint32_t n, const uint32_t* seed_faces, cons
   if (!ctx->costs_set) { ctx->err = "costs not set"; return MNB_E_STATE; }
   for (uint32_t i = 0; i < n; ++i) if (seed_faces[i] >= ctx->F) return MNB_INVALID_START;
   CK(cudaSetDevice(ctx->device));
-  const int cs = ctx->batch_cluster;
+  // resident CTAs per SM of the lean batch kernel (k_cvp_batch, batch_engine.cuh); MNB_BATCH_LEGACY=1 runs the generic
+  // round loop (k_cvp) instead -- kept for A/B measurements
+  static const bool legacy = getenv("MNB_BATCH_LEGACY") != nullptr;
   int per_sm = 1;
-  if (cs == 1) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cvp<1, false>, MNB_CVP_THREADS, 0)); if (per_sm < 1) per_sm = 1; if (per_sm > 2) per_sm = 2; }
-  unsigned groups = (unsigned)(ctx->sm_count * per_sm / cs);
+  if (legacy) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cvp<1, false>, MNB_CVP_THREADS, 0)); if (per_sm > 2) per_sm = 2; }
+  else { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cvp_batch<1>, MNB_BATCH_THREADS, 0)); if (per_sm > MNB_BATCH_MINBLOCKS) per_sm = MNB_BATCH_MINBLOCKS; }
+  if (per_sm < 1) per_sm = 1;
+  const unsigned slots = (unsigned)(ctx->sm_count * per_sm);
+  // CTAs per wavefront: one when the goals fill the machine; with fewer goals than CTA slots a cluster of CTAs shares a
+  // wavefront so that the SMs do not idle (strong scaling across GPUs hands every rank a fraction of the batch)
+  int cs = ctx->batch_cluster;
+  if (cs <= 0) { cs = 1; while (cs < 8 && (unsigned)(2 * cs) * n <= slots) cs *= 2; }
+  if (cs > 1) per_sm = std::max(1, std::min(per_sm, 2));
+  unsigned groups = slots / (unsigned)cs;
   if (groups > n) groups = n;
   if (groups == 0) groups = 1;
   int32_t rc;
@@ -602,7 +612,18 @@ int32_t mnb_cvp_batch(mnb_ctx* ctx, uint32_t n, const uint32_t* seed_faces, cons
   a.out_dist = dev ? out_dist : ctx->d_out_dist;
   a.out_pred = nullptr; a.out_dir = nullptr; a.out_cut = nullptr;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  if ((rc = launch_cvp(ctx, a, cs, groups)) != MNB_OK) return rc;
+  if (legacy) { if ((rc = launch_cvp(ctx, a, cs, groups)) != MNB_OK) return rc; }
+  else {
+    cudaError_t e;
+    const unsigned blocks = groups * (unsigned)cs;
+    switch (cs) {
+      case 1: e = launch_cluster(k_cvp_batch<1>, a, 1, blocks, MNB_BATCH_THREADS, ctx->stream); break;
+      case 2: e = launch_cluster(k_cvp_batch<2>, a, 2, blocks, MNB_BATCH_THREADS, ctx->stream); break;
+      case 4: e = launch_cluster(k_cvp_batch<4>, a, 4, blocks, MNB_BATCH_THREADS, ctx->stream); break;
+      default: e = launch_cluster(k_cvp_batch<8>, a, 8, blocks, MNB_BATCH_THREADS, ctx->stream); break;
+    }
+    if (e != cudaSuccess) { ctx->err = std::string("cvp batch launch: ") + cudaGetErrorString(e); return MNB_E_CUDA; }
+  }
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   if (!dev) CK(cudaMemcpyAsync(out_dist, a.out_dist, sizeof(float) * (size_t)n * ctx->V, cudaMemcpyDeviceToHost, ctx->stream));
   if ((rc = finish_stats(ctx, groups, 1)) != MNB_OK) return rc;

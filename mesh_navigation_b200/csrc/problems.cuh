@@ -35,6 +35,7 @@ struct CvpProblem : LabelStore {
   double cost_limit;
   uint32_t s0, s1, s2;       // seed vertices (pre-fixed, cvp:719-728)
   uint32_t seed_noexpand;    // bit k: seed k pops but does not expand (cvp:757,760)
+  float seed_max_d = __builtin_huge_valf();   // largest seed potential: labels above it are not seeds (filter in face_time)
 
   static constexpr int MAXF = 12;
 
@@ -58,6 +59,7 @@ struct CvpProblem : LabelStore {
     if (invalid && invalid[x]) return false;        // cvp:785 (no face with an invalid vertex)
     return !((double)cost[x] >= cost_limit);        // cvp:802,825,848
   }
+  __device__ __forceinline__ static bool never_fixed(uint32_t) { return false; }
   __device__ __forceinline__ int seed_index(uint32_t v) const { return v == s0 ? 0 : (v == s1 ? 1 : (v == s2 ? 2 : -1)); }
 
   template <class F>
@@ -70,30 +72,35 @@ struct CvpProblem : LabelStore {
     }
   }
 
-  // pop time (T, Tm) of the face with sources v1, v2; false if the face cannot fire
+  // does the vertex with label L expand when it pops?  cvp:754: not if it lies beyond goal_dist -- the goal_dist of the
+  // moment it pops: a vertex that popped before the cutoff was armed expanded whatever its potential
+  __device__ __forceinline__ bool expands(const Label& L, float goal) const { return !(L.d > goal && !tless(L.t, goal_t)); }
+  // pop time T of the face with sources v1, v2 (= the pop of Tv); false if the face cannot fire
   __device__ __forceinline__ bool face_time(uint32_t c, uint32_t v1, uint32_t v2, const Label& a, const Label& b, float band_end,
                                             float goal, EvTime& T, uint32_t& Tv) const {
     if (!(a.d < band_end) || !(b.d < band_end)) return false;
     if (invalid && (invalid[v1] || invalid[v2])) return false;
-    const int i1 = seed_index(v1), i2 = seed_index(v2);
     const bool v1_later = tless(b.t, a.t);
-    if (i1 >= 0 && i2 >= 0) {
-      // both sources pre-fixed: the face fires at the FIRST of them that pops and expands
-      const bool e1 = !((seed_noexpand >> i1) & 1u), e2 = !((seed_noexpand >> i2) & 1u);
-      if (!e1 && !e2) return false;
-      const bool use1 = e1 && (!e2 || !v1_later);
-      T = use1 ? a.t : b.t; Tv = use1 ? v1 : v2;
-      return true;
+    if (a.d <= seed_max_d || b.d <= seed_max_d) {               // (cheap filter: only labels this small can be seeds)
+      const int i1 = seed_index(v1), i2 = seed_index(v2);
+      if (i1 >= 0 || i2 >= 0) {
+        // Seeds are fixed BEFORE they pop (cvp:719-728).  The face fires at the pop of a source that expands while the other
+        // source is already fixed: a seed always is, a normal vertex once it has popped.  With a seed and a normal vertex v
+        // that is the pop of v -- even if v pops before the seed does (a neighbour closer to the goal point than the farthest
+        // seed; found by the randomised tests) -- or, if v does not expand, the seed's own pop when it comes later.
+        const bool e1 = expands(a, goal) && !(i1 >= 0 && ((seed_noexpand >> i1) & 1u));
+        const bool e2 = expands(b, goal) && !(i2 >= 0 && ((seed_noexpand >> i2) & 1u));
+        const bool fire1 = e1 && (i2 >= 0 || v1_later), fire2 = e2 && (i1 >= 0 || !v1_later);
+        if (!fire1 && !fire2) return false;
+        const bool use1 = fire1 && (!fire2 || !v1_later);       // both: the earlier pop
+        T = use1 ? a.t : b.t; Tv = use1 ? v1 : v2;
+        return !names(T, c);
+      }
     }
-    if (names(v1_later ? a.t : b.t, c)) return false;          // the face fires inside a cascade of c itself (LabelStore::names)
-    const int il = v1_later ? i1 : i2;
-    if (il >= 0 && ((seed_noexpand >> il) & 1u)) return false;
-    {   // cvp:754: the popping vertex does not expand if it lies beyond goal_dist -- the goal_dist of the moment it pops:
-        // a vertex that popped before the cutoff was armed expanded whatever its potential
-      const Label& L = v1_later ? a : b;
-      if (L.d > goal && !tless(L.t, goal_t)) return false;
-    }
-    T = v1_later ? a.t : b.t; Tv = v1_later ? v1 : v2;
+    const Label& L = v1_later ? a : b;                          // two normal sources: the later pop, if that vertex expands
+    if (names(L.t, c)) return false;                            // the face fires inside a cascade of c itself (LabelStore::names)
+    if (!expands(L, goal)) return false;
+    T = L.t; Tv = v1_later ? v1 : v2;
     return true;
   }
 
@@ -497,6 +504,7 @@ struct InflationProblem : LabelStore {
     return false;
   }
   __device__ __forceinline__ bool eligible(uint32_t) const { return true; }   // no cost / validity test on the target
+  __device__ __forceinline__ bool never_fixed(uint32_t c) const { return invalid && invalid[c]; }   // pops, but is not fixed (:417-422)
 
   template <class F>
   __device__ __forceinline__ void activate(uint32_t c, F push) const {
@@ -529,7 +537,9 @@ struct InflationProblem : LabelStore {
     }
     if (v1_later ? i1 : i2) return false;                    // the popping vertex must expand
     T = v1_later ? a.t : b.t; Tv = v1_later ? v1 : v2;
-    return !names(T, c);                                     // (a face inside a cascade of c itself cannot update c)
+    // a face inside a cascade of c itself cannot update c (LabelStore::names) -- unless c is never fixed: an invalid vertex
+    // pops without being fixed (:417-422) and keeps receiving updates from every face that fires later
+    return (invalid && invalid[c]) || !names(T, c);
   }
 
   // event-ordered replay of the faces around c; win = corner record of the LAST accepted update (-1: none), with the
@@ -695,6 +705,7 @@ struct DijkstraProblem : TimeAlg {
     return l;
   }
   __device__ __forceinline__ bool eligible(uint32_t x) const { return !(invalid && invalid[x]); }  // :328
+  __device__ __forceinline__ static bool never_fixed(uint32_t) { return false; }
 
   template <class F>
   __device__ __forceinline__ void activate(uint32_t c, F push) const {

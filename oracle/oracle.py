@@ -26,6 +26,26 @@ def build(force: bool = False) -> str:
 _lib = None
 
 
+def use_native_build() -> str:
+    """CPU-baseline legs of bench.py only: rebuild the oracle ON THIS HOST with `-O3 -march=native -DNDEBUG` (BASELINE.md
+    section 2) into oracle/_native/ and route every later call there.  The default liboracle.so is generic x86-64 because it
+    is built in the build container and travels to the GPU box; -ffp-contract=off is kept, so results do not change.
+    Returns the flag string actually in effect (the generic build if the native one cannot be compiled)."""
+    global _SO, _lib
+    out_dir = os.path.join(_HERE, "_native")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "liboracle_native.so")
+    flags = ["-O3", "-march=native", "-DNDEBUG", "-ffp-contract=off", "-fPIC", "-std=c++17"]
+    try:
+        subprocess.check_call(["g++"] + flags + ["-shared", "-o", so, os.path.join(_HERE, "oracle.cpp")],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300)
+        C.CDLL(so)                     # (an illegal-instruction build would have failed to compile, not to load; cheap check)
+        _SO, _lib = so, None
+        return "g++ " + " ".join(flags[:4])
+    except Exception:
+        return "g++ -O3 -DNDEBUG -ffp-contract=off (generic x86-64; native build failed)"
+
+
 def lib():
     global _lib
     if _lib is None:

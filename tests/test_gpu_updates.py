@@ -426,3 +426,66 @@ def test_inflation_backstep_deep_cascade(api, oracle_mod):
     mm.close()
     assert (got["dist"].view(np.uint32) == ref["dist"].view(np.uint32)).all()
     assert (vec.view(np.uint32) == ref["vectors"].view(np.uint32)).all()
+
+
+def test_seed_pops_after_its_neighbour(api, oracle_mod):
+    """found by tools/emu_fuzz.py (round 2, seed 202 case 13): a neighbour of the seed face lies closer to the goal point than
+    the farthest seed vertex, so it pops BEFORE that seed.  Seeds are fixed before they pop (cvp:719-728): the face (seed,
+    neighbour) -> c fires at the neighbour's pop, not at the later pop of the seed (which, here, does not even expand: it
+    lies on a cost-limit wall).  7 547 potentials downstream were off."""
+    pos, faces, vc, w, inv, sf, sp, rf, cl = _fuzz_case("seed_after_neighbour")
+    inv = inv if inv.size else None
+    om = oracle_mod.OracleMesh(pos, faces)
+    ref = om.cvp(w, vc, sf, sp, rf, invalid=inv, cost_limit=cl)
+    sd = ref["dist"][faces[sf]]
+    nb = np.unique(faces[np.isin(faces, faces[sf]).any(1)])
+    assert (ref["dist"][nb] < sd.max()).sum() > (sd < sd.max()).sum()          # a non-seed neighbour below the farthest seed
+    mm = api.MeshMap(pos, faces)
+    mm.setCosts(vc, w, inv)
+    for cluster, delta in ((-1, 0.0), (1, 0.3)):
+        mm.set_tuning(delta, cluster, 0)
+        got = api.CVPMeshPlanner(mm, cost_limit=cl).waveFrontPropagation(sf, sp, rf)
+        assert (got["dist"].view(np.uint32) == ref["dist"].view(np.uint32)).all(), (cluster, delta)
+        assert (got["pred"] == ref["pred"]).all() and (got["cutting_face"] == ref["cutting_face"]).all()
+    mm.close()
+
+
+def test_inflation_never_fixed_vertex_takes_late_updates(api, oracle_mod):
+    """found by tools/emu_fuzz.py (round 2, seed 204 case 130): an invalid vertex pops without being fixed
+    (inflation_layer.cpp:417-422), so a face that fires AFTER its pop still lowers it; the engine used to settle it
+    with the label of its own pop time"""
+    import os
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "fuzz_inflation_never_fixed.npz"))
+    pos, faces, le, rad, inv = d["pos"], d["faces"], d["le"], float(d["rad"]), d["inv"]
+    om = oracle_mod.OracleMesh(pos, faces)
+    ref = om.inflation(om.edge_distances(), le, invalid=inv, inflation_radius=rad, with_vectors=True)
+    mm = api.MeshMap(pos, faces)
+    il = api.InflationLayer(mm, inflation_radius=rad)
+    got = il.waveCostInflation(le, inv)
+    vec = il.vectorMap()
+    mm.close()
+    assert (got["dist"].view(np.uint32) == ref["dist"].view(np.uint32)).all()
+    assert (vec.view(np.uint32) == ref["vectors"].view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("name", ["deep_cascade_planar", "deep_cascade_delaunay", "cutoff_cascade", "seed_after_neighbour"])
+def test_batch_engine_on_the_hard_cases(api, oracle_mod, name):
+    """the lean batch round loop (batch_engine.cuh: k_cvp_batch) hands everything that is not a plain causal evaluation to the
+    generic 8-lane replay; on the fixtures that exercise those paths (cascades of any depth, cost-limit walls, invalid
+    vertices, seeds that pop late) every field of a batch must equal the oracle's bit for bit, for every cluster size"""
+    pos, faces, vc, w, inv, sf, sp, rf, cl = _fuzz_case(name)
+    inv = inv if inv.size else None
+    om = oracle_mod.OracleMesh(pos, faces)
+    rng = np.random.default_rng(5)
+    sfs = np.concatenate([[sf], rng.integers(0, om.F, 5)]).astype(np.uint32)
+    sps = np.stack([pos[faces[f]].mean(0) for f in sfs]).astype(np.float32); sps[0] = sp
+    refs = [om.cvp(w, vc, int(sfs[i]), sps[i], invalid=inv, cost_limit=cl)["dist"] for i in range(len(sfs))]
+    mm = api.MeshMap(pos, faces)
+    mm.setCosts(vc, w, inv)
+    for cluster, delta in ((1, 0.3), (2, 0.1), (4, 1.8), (8, 0.3)):
+        mm.set_tuning(delta, cluster, 0)
+        got = api.CVPMeshPlanner(mm, cost_limit=cl).waveFrontPropagationBatch(sfs, sps)
+        assert got["outcome"] == 0
+        for i in range(len(sfs)):
+            assert (got["dist"][i].view(np.uint32) == refs[i].view(np.uint32)).all(), (cluster, delta, i)
+    mm.close()

@@ -47,7 +47,7 @@ def _worker(rank, world, port, n_goals, V, chunk, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_goals,chunk", [(11, 2), (8, 64), (3, 1)])
+@pytest.mark.parametrize("n_goals,chunk", [(11, 2), (8, 64), (3, 1), (11, 0), (3, 0)])
 def test_sharded_gather_world2(n_goals, chunk):
     world, V = 2, 37
     ctx = mp.get_context("spawn")

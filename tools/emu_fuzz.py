@@ -48,6 +48,16 @@ for case in range(N):
             or (got["cutting_face"] != ref["cutting_face"]).any():
         msg.append(f"CVP outcome {got['outcome']}/{ref['outcome']} dist!= {(got['dist'].view(np.uint32) != ref['dist'].view(np.uint32)).sum()} pred!= {(got['pred'] != ref['pred']).sum()} "
                    f"cut!= {(got['cutting_face'] != ref['cutting_face']).sum()} at {np.where(got['cutting_face'] != ref['cutting_face'])[0][:4].tolist()}")
+    # the lean batch round loop (k_cvp_batch): three goals, random cluster size / band width
+    bsf = np.concatenate([[sf], crng.integers(0, om.F, 2)]).astype(np.uint32)
+    bsp = np.stack([pos[faces[f]].mean(0) for f in bsf]).astype(np.float32); bsp[0] = sp
+    bcl = int(crng.choice([1, 1, 2, 4])); mm.set_tuning(float(crng.choice([0.3, 0.1, 0.6])), bcl, 0)
+    gb = api.CVPMeshPlanner(mm, cost_limit=cl).waveFrontPropagationBatch(bsf, bsp)
+    for i in range(3):
+        rb = ref["dist"] if (i == 0 and rf < 0) else om.cvp(w, vc, int(bsf[i]), bsp[i], invalid=inv, cost_limit=cl)["dist"]
+        if (gb["dist"][i].view(np.uint32) != rb.view(np.uint32)).any():
+            msg.append(f"batch[{i}] cluster {bcl} dist!= {(gb['dist'][i].view(np.uint32) != rb.view(np.uint32)).sum()}")
+    mm.set_tuning(0.3, cluster if cluster != -1 else -1, 0)
     sv = int(faces[sf][0]); rv = int(faces[rf][0]) if rf >= 0 else -1
     refd = om.dijkstra(w, vc, sv, rv, invalid=inv, cost_limit=cl)
     gotd = api.DijkstraMeshPlanner(mm, cost_limit=cl).dijkstra(sv, rv)
@@ -63,6 +73,9 @@ for case in range(N):
     print(f"case {case}: {kind} V={V} costs={cm} factor={factor} invalid={inv is not None} robot={rf >= 0} cluster={cluster} cl={cl} radius={rad} lethals={le.size}: "
           + ("ok" if not msg else "MISMATCH " + "; ".join(msg)), flush=True)
     bad += bool(msg)
+    if msg and os.environ.get("FUZZ_DUMP"):      # keep the failing case as a fixture (tests/golden/fuzz_*.npz layout)
+        np.savez_compressed(os.path.join(os.environ["FUZZ_DUMP"], f"fuzz_case_{sys.argv[2] if len(sys.argv) > 2 else 0}_{case}.npz"), pos=pos, faces=faces, vc=vc, w=w,
+                            inv=inv if inv is not None else np.zeros(0, np.uint8), sf=sf, sp=sp, rf=rf, cl=cl, le=le, rad=rad)
     mm.close()
 print(f"{N - bad}/{N} cases bit-identical")
 sys.exit(1 if bad else 0)

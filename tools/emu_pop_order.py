@@ -13,9 +13,10 @@ from oracle import oracle as O
 from mesh_navigation_b200 import api
 
 name = sys.argv[1]
-d = np.load(f"tests/golden/fuzz_{name}.npz")
+d = np.load(name if name.endswith(".npz") else f"tests/golden/fuzz_{name}.npz")
 pos, faces, vc, w, inv, sf, sp, rf, cl = (d["pos"], d["faces"], d["vc"], d["w"], d["inv"], int(d["sf"]), d["sp"], int(d["rf"]), float(d["cl"]))
 if "norobot" in sys.argv: rf = -1
+if inv.size == 0: inv = None
 om = O.OracleMesh(pos, faces)
 pop = np.full(om.V, 0xffffffff, np.uint32)
 O._lib.orc_debug_set_pop_buffer(pop.ctypes.data_as(C.c_void_p))
@@ -27,7 +28,7 @@ mm.set_tuning(0.3 if cluster != -1 else 0.0, cluster, 0)
 got = api.CVPMeshPlanner(mm, cost_limit=cl).waveFrontPropagation(sf, sp, rf)
 V = om.V
 lab = np.zeros((V, 4), np.uint32); root = np.zeros(V, np.uint32); ext = np.zeros(V, np.uint32)
-NP = 1 << 16; pool = np.zeros(NP, np.uint32)
+NP = 1 << 20; pool = np.zeros(NP, np.uint32)
 L = mm.L
 p = lambda a: a.ctypes.data_as(C.c_void_p)
 L.mnb_debug_get_labels.argtypes = [C.c_void_p, C.c_void_p]
