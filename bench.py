@@ -426,7 +426,8 @@ def main():
             return {"kernel_ms": Ly["kernel_ms"], "hbm_frac": 837 * V / (Ly["kernel_ms"] * 1e-3) / 1e9 / hbm0}
 
         def leg_inflation():
-            le = np.union1d(np.where(shared["lethal_mask"] != 0)[0], synth.disc_lethals_grid(pos, n, n, 1000, 0.3)).astype(np.uint32)
+            n_discs = max(2, int(round(1000 * (n / 2240.0) ** 2)))         # 1000 obstacle discs on the 5M map, same density on smaller ones
+            le = np.union1d(np.where(shared["lethal_mask"] != 0)[0], synth.disc_lethals_grid(pos, n, n, n_discs, 0.3)).astype(np.uint32)
             shared["lethals"] = le
             for rep in range(2):
                 I = InflationLayer(mm).waveCostInflation(le)
@@ -445,11 +446,13 @@ def main():
             final = np.maximum(static, np.nan_to_num(I["cost"], nan=0.0)).astype(np.float32)    # MaxCombinationLayer, defaults 0
             t0 = time.perf_counter(); w1 = mm.computeEdgeWeights(final, 1.0); t_w = time.perf_counter() - t0
             free = np.where(final < 0.5)[0]
+            if free.size == 0:
+                free = np.argsort(final)[:16]
             c0 = synth.nearest_vertex(pos, [n * 0.05, n * 0.05, float(pos[:, 2].mean())])
             v = int(free[np.argmin(np.linalg.norm(pos[free] - pos[c0], axis=1))])
             i, j = min(v % n, n - 2), min(v // n, n - 2)
             f = 2 * (j * (n - 1) + i)
-            while not (final[faces[f]] < 1.0).all():
+            while not (final[faces[f]] < 1.0).all() and f + 1 < mm.F:
                 f += 1
             spc = pos[faces[f]].mean(0).astype(np.float32)
             pl3 = CVPMeshPlanner(mm, cost_limit=1.0)

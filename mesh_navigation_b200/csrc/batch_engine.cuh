@@ -104,103 +104,28 @@ __device__ __noinline__ void batch_notify_big(const Args& a, const BatchGroup& G
 }
 
 // Work queue of a CTA: the candidates of the current chunk that have to be evaluated (phase B below)
-struct BatchWork { static constexpr int CAP = 2048; uint32_t q[CAP]; unsigned int n; };
+struct BatchWork { static constexpr int CAP = 2048; uint32_t q[CAP]; uint32_t sq[CAP]; unsigned int n, ns; };
 
-// Preconditions as for run_band_rounds (band_engine.cuh); list entries of list0 carry no flag bits; skipw = {inf, inf, 0, 0}.
-//
-// A round has two phases per chunk of the CTA's share of the candidate list:
-//   A (one THREAD per candidate): settled?  clean?  A candidate is CLEAN -- its label cannot change, it is carried over
-//     without being evaluated -- if (1) no face neighbour was re-labelled during the previous round with a pop time that
-//     is not above the candidate's own (a face fires at or after the pop of its later source: a source that pops after
-//     the candidate, before and after its re-label, cannot reach it), and (2) no source that lay beyond the band end at
-//     the candidate's last evaluation has come inside since.  (1) is a per-vertex float "smallest relevant re-label"
-//     that neighbours lower with fire-and-forget atomicMin, double-buffered by round parity so that it is only ever read
-//     across the round barrier; (2) is one float per vertex written by its own last evaluation.  On the terrain 64 % of
-//     the evaluations of the plain round loop find nothing changed; this phase costs them ~25 thread-instructions.
-//   B (8 lanes per candidate): the evaluation proper, on the compacted work queue.
-template <int CS, class Args>
-__device__ __forceinline__ void run_band_rounds_batch(const Args& a, const BatchGroup& G, uint32_t* list0, uint32_t* list1, BatchStage& st,
-                                                      BatchWork& wk, const float delta, const uint32_t gthreads, const uint32_t gtid,
-                                                      const BatchSeeds& sd, const float band_end_init) {
+// Phase C of a round (see run_band_rounds_batch): 8 lanes per candidate, the general evaluation -- cascade members among
+// the sources, possible seeds, non-causal faces that may fire first, more than 8 faces, strict rounds.  A few percent of
+// the evaluations; kept out of line so that its register needs do not weigh on the throughput phases.
+template <class Args>
+__device__ __noinline__ void batch_general_phase(const Args& a, const BatchGroup& G, const BatchSeeds& sd, BatchStage& st, BatchWork& wk,
+                                                 uint32_t* list_n, unsigned int* count_next, const float band_end, const int strict, const uint32_t r,
+                                                 float& my_mtau_io, float& my_lo_io, unsigned int& my_recomputes_io) {
   constexpr unsigned FULL = 0xffffffffu;
   const float INF = __uint_as_float(INF_BITS);
-  GroupCtl* const ctl = G.ctl;
+  GroupCtl* const ctl = G.ctl; (void)ctl;
   uint32_t* const skw = reinterpret_cast<uint32_t*>(G.skipw);
   const uint32_t lane = threadIdx.x & 31, j = lane & 7, sh = lane & ~7u;
   const uint32_t lt = (1u << lane) - 1u;
-  const uint32_t nblk = gthreads / blockDim.x, blk = gtid / blockDim.x;
-  float band_end_prev = band_end_init;
-  unsigned int my_recomputes = 0, my_settled = 0, my_skipped = 0;     // per round (flushed to the 64-bit counters at its end)
-  float lo_best = -1.0f; int stagnant = 0, strict = 0;
-  uint32_t r = 0;
-  for (;; ++r) {
-    const uint32_t slot = r % 3, prev = (r + 2) % 3, next = (r + 1) % 3;
-    const unsigned int n = __ldcg(&ctl->count[slot]);
-    const float m_prev = __uint_as_float(__ldcg(&ctl->m_tau[prev]));
-    const float lo_prev = __uint_as_float(__ldcg(&ctl->lo[prev]));
-    const unsigned int stop = __ldcg(&ctl->stop_ring[r & 1]);
-    if (n == 0 || stop || r > a.max_rounds) break;           // r is group-uniform: the watchdog cannot deadlock the barrier
-    if (r > 0 && __float_as_uint(m_prev) == INF_BITS && __float_as_uint(lo_prev) == INF_BITS) break;
-    // stagnation watch (see run_band_rounds): labels keep changing but the earliest unsettled pop time does not move
-    if (r > 0 && __float_as_uint(m_prev) != INF_BITS && !(lo_prev > lo_best)) { if (++stagnant >= STAGNATION_ROUNDS) strict = 1; }
-    else { stagnant = 0; if (lo_prev > lo_best) lo_best = lo_prev; }
-    float band_end = lo_prev + delta;
-    if (!(band_end > band_end_prev)) band_end = band_end_prev;
-    const uint32_t* list_r = (r & 1) ? list1 : list0;
-    uint32_t* list_n = (r & 1) ? list0 : list1;
-    unsigned int* const count_next = &ctl->count[next];
-    if (gtid == 0) {
-      ctl->count[(r + 2) % 3] = 0;
-      ctl->m_tau[next] = INF_BITS;
-      ctl->lo[next] = INF_BITS;
-      ctl->stop_ring[(r + 1) & 1] = (stop || (a.cancel_flag && (r & 31) == 0 && *(const volatile int*)a.cancel_flag)) ? 1u : 0u;
-    }
-    const uint32_t buf_now = r & 1u, buf_prev = buf_now ^ 1u;      // re-labels of this round / of the previous round
-    float my_mtau = INF, my_lo = INF;
-    const unsigned int cnt = n > blk ? (n - blk + nblk - 1) / nblk : 0u;
-    for (unsigned int cb = 0; cb < cnt; cb += (unsigned)BatchWork::CAP) {
-      const unsigned int ce_end = min(cnt, cb + (unsigned)BatchWork::CAP);
-      // ---------------- phase A: one thread per candidate ----------------
-      for (unsigned int ib = cb + (threadIdx.x & ~31u); ib < ce_end; ib += blockDim.x) {
-        const unsigned int i = ib + lane;
-        const bool has = i < ce_end;
-        uint32_t ce = 0u; float tau = 0.0f; bool settled = false, clean = false;
-        if (has) {
-          ce = __ldcg(&list_r[(size_t)i * nblk + blk]);
-          const uint32_t c = ce & ~LIST_ACTIVATED;
-          tau = __uint_as_float(__ldcg(reinterpret_cast<const uint32_t*>(G.state) + 4 * (size_t)c + 1));
-          settled = tau < m_prev && tau < band_end_prev;   // converged prefix: the sequential algorithm has popped c with this label
-          if (!settled) {
-            const uint4 sk = __ldcg(&G.skipw[c]);
-            const uint32_t dmb = buf_prev ? sk.y : sk.x;
-            if (dmb != INF_BITS) __stcg(&skw[4 * (size_t)c + buf_prev], INF_BITS);      // consumed (nobody writes this buffer during this round)
-            clean = !strict && !(__uint_as_float(dmb) <= tau) && !(band_end > __uint_as_float(sk.z));
-          }
-        }
-        if (settled) my_settled++;
-        const bool keep = has && !settled && clean, work = has && !settled && !clean;
-        if (keep) { my_skipped++; my_lo = fminf(my_lo, tau); }
-        const unsigned km = __ballot_sync(FULL, keep), wm = __ballot_sync(FULL, work);
-        if (km) {
-          unsigned int base = 0;
-          if (lane == 0) base = atomicAdd(&st.n, (unsigned)__popc(km));
-          base = __shfl_sync(FULL, base, 0);
-          if (keep) batch_stage_write(st, base + __popc(km & lt), ce, list_n, count_next);
-        }
-        if (wm) {
-          unsigned int base = 0;
-          if (lane == 0) base = atomicAdd(&wk.n, (unsigned)__popc(wm));
-          base = __shfl_sync(FULL, base, 0);
-          if (work) wk.q[base + __popc(wm & lt)] = ce;
-        }
-      }
-      __syncthreads();
-      const unsigned int nw = wk.n;
-      // ---------------- phase B: 8 lanes per candidate that needs an evaluation ----------------
+  const uint32_t buf_now = r & 1u;
+  float my_mtau = my_mtau_io, my_lo = my_lo_io; unsigned int my_recomputes = my_recomputes_io;
+  const unsigned int nw = wk.ns;
       for (unsigned int qb = (threadIdx.x >> 5) * 4u; qb < nw; qb += (blockDim.x >> 3)) {
       const unsigned int q = qb + (lane >> 3);
       const bool has = q < nw;
-      const uint32_t ce = has ? wk.q[q] : 0u;
+      const uint32_t ce = has ? wk.sq[q] : 0u;
       const uint32_t c = ce & ~LIST_ACTIVATED;
       const bool activated = (ce & LIST_ACTIVATED) != 0u;
       const uint4 ob = __ldcg(&G.state[c]);
@@ -325,9 +250,193 @@ __device__ __forceinline__ void run_band_rounds_batch(const Args& a, const Batch
         }
         if (act_now && j == 0 && deg > (int)ELL_W) batch_activate_big(a, G, c, st, list_n, count_next);
       }
-      }   // phase B
+      }   // phase C
+  my_mtau_io = my_mtau; my_lo_io = my_lo; my_recomputes_io = my_recomputes;
+}
+
+
+// Preconditions as for run_band_rounds (band_engine.cuh); list entries of list0 carry no flag bits; skipw = {inf, inf, 0, 0}.
+//
+// A round has two phases per chunk of the CTA's share of the candidate list:
+//   A (one THREAD per candidate): settled?  clean?  A candidate is CLEAN -- its label cannot change, it is carried over
+//     without being evaluated -- if (1) no face neighbour was re-labelled during the previous round with a pop time that
+//     is not above the candidate's own (a face fires at or after the pop of its later source: a source that pops after
+//     the candidate, before and after its re-label, cannot reach it), and (2) no source that lay beyond the band end at
+//     the candidate's last evaluation has come inside since.  (1) is a per-vertex float "smallest relevant re-label"
+//     that neighbours lower with fire-and-forget atomicMin, double-buffered by round parity so that it is only ever read
+//     across the round barrier; (2) is one float per vertex written by its own last evaluation.  On the terrain 64 % of
+//     the evaluations of the plain round loop find nothing changed; this phase costs them ~25 thread-instructions.
+//   B (8 lanes per candidate): the evaluation proper, on the compacted work queue.
+template <int CS, class Args>
+__device__ __forceinline__ void run_band_rounds_batch(const Args& a, const BatchGroup& G, uint32_t* list0, uint32_t* list1, BatchStage& st,
+                                                      BatchWork& wk, const float delta, const uint32_t gthreads, const uint32_t gtid,
+                                                      const BatchSeeds& sd, const float band_end_init) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const float INF = __uint_as_float(INF_BITS);
+  GroupCtl* const ctl = G.ctl;
+  uint32_t* const skw = reinterpret_cast<uint32_t*>(G.skipw);
+  const uint32_t lane = threadIdx.x & 31, j = lane & 7, sh = lane & ~7u;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t nblk = gthreads / blockDim.x, blk = gtid / blockDim.x;
+  float band_end_prev = band_end_init;
+  unsigned int my_recomputes = 0, my_settled = 0, my_skipped = 0;     // per round (flushed to the 64-bit counters at its end)
+  float lo_best = -1.0f; int stagnant = 0, strict = 0;
+  uint32_t r = 0;
+  for (;; ++r) {
+    const uint32_t slot = r % 3, prev = (r + 2) % 3, next = (r + 1) % 3;
+    const unsigned int n = __ldcg(&ctl->count[slot]);
+    const float m_prev = __uint_as_float(__ldcg(&ctl->m_tau[prev]));
+    const float lo_prev = __uint_as_float(__ldcg(&ctl->lo[prev]));
+    const unsigned int stop = __ldcg(&ctl->stop_ring[r & 1]);
+    if (n == 0 || stop || r > a.max_rounds) break;           // r is group-uniform: the watchdog cannot deadlock the barrier
+    if (r > 0 && __float_as_uint(m_prev) == INF_BITS && __float_as_uint(lo_prev) == INF_BITS) break;
+    // stagnation watch (see run_band_rounds): labels keep changing but the earliest unsettled pop time does not move
+    if (r > 0 && __float_as_uint(m_prev) != INF_BITS && !(lo_prev > lo_best)) { if (++stagnant >= STAGNATION_ROUNDS) strict = 1; }
+    else { stagnant = 0; if (lo_prev > lo_best) lo_best = lo_prev; }
+    float band_end = lo_prev + delta;
+    if (!(band_end > band_end_prev)) band_end = band_end_prev;
+    const uint32_t* list_r = (r & 1) ? list1 : list0;
+    uint32_t* list_n = (r & 1) ? list0 : list1;
+    unsigned int* const count_next = &ctl->count[next];
+    if (gtid == 0) {
+      ctl->count[(r + 2) % 3] = 0;
+      ctl->m_tau[next] = INF_BITS;
+      ctl->lo[next] = INF_BITS;
+      ctl->stop_ring[(r + 1) & 1] = (stop || (a.cancel_flag && (r & 31) == 0 && *(const volatile int*)a.cancel_flag)) ? 1u : 0u;
+    }
+    const uint32_t buf_now = r & 1u, buf_prev = buf_now ^ 1u;      // re-labels of this round / of the previous round
+    float my_mtau = INF, my_lo = INF;
+    const unsigned int cnt = n > blk ? (n - blk + nblk - 1) / nblk : 0u;
+    for (unsigned int cb = 0; cb < cnt; cb += (unsigned)BatchWork::CAP) {
+      const unsigned int ce_end = min(cnt, cb + (unsigned)BatchWork::CAP);
+      // ---------------- phase A: one thread per candidate ----------------
+      for (unsigned int ib = cb + (threadIdx.x & ~31u); ib < ce_end; ib += blockDim.x) {
+        const unsigned int i = ib + lane;
+        const bool has = i < ce_end;
+        uint32_t ce = 0u; float tau = 0.0f; bool settled = false, clean = false;
+        if (has) {
+          ce = __ldcg(&list_r[(size_t)i * nblk + blk]);
+          const uint32_t c = ce & ~LIST_ACTIVATED;
+          tau = __uint_as_float(__ldcg(reinterpret_cast<const uint32_t*>(G.state) + 4 * (size_t)c + 1));
+          settled = tau < m_prev && tau < band_end_prev;   // converged prefix: the sequential algorithm has popped c with this label
+          if (!settled) {
+            const uint4 sk = __ldcg(&G.skipw[c]);
+            const uint32_t dmb = buf_prev ? sk.y : sk.x;
+            if (dmb != INF_BITS) __stcg(&skw[4 * (size_t)c + buf_prev], INF_BITS);      // consumed (nobody writes this buffer during this round)
+            clean = !strict && !(__uint_as_float(dmb) <= tau) && !(band_end > __uint_as_float(sk.z));
+          }
+        }
+        if (settled) my_settled++;
+        const bool keep = has && !settled && clean, work = has && !settled && !clean;
+        if (keep) { my_skipped++; my_lo = fminf(my_lo, tau); }
+        const unsigned km = __ballot_sync(FULL, keep), wm = __ballot_sync(FULL, work);
+        if (km) {
+          unsigned int base = 0;
+          if (lane == 0) base = atomicAdd(&st.n, (unsigned)__popc(km));
+          base = __shfl_sync(FULL, base, 0);
+          if (keep) batch_stage_write(st, base + __popc(km & lt), ce, list_n, count_next);
+        }
+        if (wm) {
+          unsigned int base = 0;
+          if (lane == 0) base = atomicAdd(&wk.n, (unsigned)__popc(wm));
+          base = __shfl_sync(FULL, base, 0);
+          if (work) wk.q[base + __popc(wm & lt)] = ce;
+        }
+      }
       __syncthreads();
-      if (threadIdx.x == 0) wk.n = 0;
+      const unsigned int nwork = wk.n;
+      // ---------------- phase B: one THREAD per candidate, plain causal evaluations only ----------------
+      // The throughput form of the evaluation: a thread walks the faces of its candidate (ELL row), every source label plain,
+      // no possible seed, and the causal collapse applies (CvpEllProblemT::replay_sub8): d = min over the causal faces.
+      // ~25 warp-instructions per candidate instead of ~140 for the 8-lane form, 32 candidates per warp in flight.  Anything
+      // else is deferred to phase C.
+      for (unsigned int ib = (threadIdx.x & ~31u); ib < nwork; ib += blockDim.x) {
+        const unsigned int i = ib + lane;
+        const bool has = i < nwork;
+        bool defer = false;
+        uint32_t ce = 0u, c = 0u; uint4 ob = make_uint4(0u, 0u, 0u, 0u);
+        float m = INF, tmin_nc = INF, excl = INF; int deg = 0;
+        if (has) {
+          ce = wk.q[i]; c = ce & ~LIST_ACTIVATED;
+          ob = __ldcg(&G.state[c]);
+          if (strict) defer = true;
+          for (int k = 0; k < (int)ELL_W && !defer; ++k) {
+            const int4 ix = __ldg(&a.ell_idx[(size_t)c * ELL_W + k]);
+            if (k == 0) { deg = ix.w; if (deg > (int)ELL_W) { defer = true; break; } }
+            if (ix.x == ELL_EMPTY) continue;
+            const uint32_t v1 = (uint32_t)ix.x, v2 = (uint32_t)ix.y;
+            const uint4 sa = __ldcg(&G.state[v1]), sb = __ldcg(&G.state[v2]);
+            const float da = __uint_as_float(sa.x), db = __uint_as_float(sb.x);
+            if (((sa.z | sa.w | sb.z | sb.w) >> 31) || da <= sd.seed_max || db <= sd.seed_max) { defer = true; break; }
+            if (a.invalid && (a.invalid[v1] || a.invalid[v2])) continue;
+            if (sa.x != INF_BITS && !(da < band_end)) excl = fminf(excl, da);
+            if (sb.x != INF_BITS && !(db < band_end)) excl = fminf(excl, db);
+            if (!(da < band_end) || !(db < band_end)) continue;
+            const float ta = __uint_as_float(sa.y), tb = __uint_as_float(sb.y);
+            const bool v1_later = tb < ta || (tb == ta && v2 < v1);
+            const float T1 = v1_later ? ta : tb;
+            const float4 w = __ldg(&a.ell_w[(size_t)c * ELL_W + k]);
+            const double2* gp = reinterpret_cast<const double2*>(a.ell_geo) + 2 * ((size_t)c * ELL_W + k);
+            const double2 g01 = __ldg(gp), g23 = __ldg(gp + 1);
+            CvpEllProblemT<false>::FaceGeo fg; fg.p = g01.x; fg.hc = g01.y; fg.t0a = g23.x;
+            double U, X;
+            CvpEllProblemT<false>::eval_face_geo((double)da, (double)db, (double)w.z, (double)w.y, (double)w.x, fg, U, X);
+            const float Xf = (float)X;
+            if (Xf > T1 && U <= X) m = fminf(m, Xf); else tmin_nc = fminf(tmin_nc, T1);
+          }
+          if (!defer && __float_as_uint(tmin_nc) != INF_BITS && !(tmin_nc > m)) defer = true;   // a non-causal face that may fire first
+        }
+        const bool done = has && !defer;
+        bool changed = false, act_now = false;
+        if (done) {
+          const float tau = __uint_as_float(ob.y);
+          const uint32_t mb = __float_as_uint(m);
+          changed = ob.x != mb || ob.y != mb || ob.z != 0u || ob.w != 0u;
+          if (changed) {
+            if (ob.x != INF_BITS) __stcg(&G.chg[c], r + 1u);
+            __stcg(&G.state[c], make_uint4(mb, mb, 0u, 0u));
+            my_mtau = fminf(my_mtau, fminf(tau, m));
+          }
+          __stcg(&skw[4 * (size_t)c + 2], __float_as_uint(excl <= m ? excl : INF));
+          my_recomputes++;
+          my_lo = fminf(my_lo, m);
+          act_now = !(ce & LIST_ACTIVATED) && mb != INF_BITS;
+          if (changed || act_now) {
+            // tell the face neighbours about the re-label (clean-candidate rule) / pull them into the candidate set (once)
+            const uint32_t kb = __float_as_uint(fminf(tau, m));
+            for (int k = 0; k < (int)ELL_W; ++k) {
+              const int4 ix = __ldg(&a.ell_idx[(size_t)c * ELL_W + k]);
+              if (ix.x == ELL_EMPTY) continue;
+              const uint32_t xs[2] = {(uint32_t)ix.x, (uint32_t)ix.y};
+#pragma unroll
+              for (int t = 0; t < 2; ++t) {
+                const uint32_t x = xs[t];
+                if (changed) atomicMin(&skw[4 * (size_t)x + buf_now], kb);
+                if (act_now && __ldcg(&G.mark[x]) == MARK_NONE && !(a.invalid && a.invalid[x]) && !((double)__ldg(&a.cost[x]) >= a.cost_limit) &&
+                    atomicCAS(&G.mark[x], MARK_NONE, MARK_CAND) == MARK_NONE)
+                  batch_stage_write(st, atomicAdd(&st.n, 1u), x, list_n, count_next);
+              }
+            }
+          }
+        }
+        const unsigned dm = __ballot_sync(FULL, done), fm = __ballot_sync(FULL, has && defer);
+        if (dm) {   // the candidate survives into the next round's list (one shared atomic per warp)
+          unsigned int base = 0;
+          if (lane == 0) base = atomicAdd(&st.n, (unsigned)__popc(dm));
+          base = __shfl_sync(FULL, base, 0);
+          if (done) batch_stage_write(st, base + __popc(dm & lt), c | (((ce & LIST_ACTIVATED) || act_now) ? LIST_ACTIVATED : 0u), list_n, count_next);
+        }
+        if (fm) {
+          unsigned int base = 0;
+          if (lane == 0) base = atomicAdd(&wk.ns, (unsigned)__popc(fm));
+          base = __shfl_sync(FULL, base, 0);
+          if (has && defer) wk.sq[base + __popc(fm & lt)] = ce;
+        }
+      }
+      __syncthreads();
+      if (wk.ns) batch_general_phase(a, G, sd, st, wk, list_n, count_next, band_end, strict, r, my_mtau, my_lo, my_recomputes);   // phase C (block-uniform branch)
+      __syncthreads();
+      if (threadIdx.x == 0) { wk.n = 0; wk.ns = 0; }
       __syncthreads();
     }     // chunks
     {

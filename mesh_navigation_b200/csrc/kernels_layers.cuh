@@ -252,32 +252,89 @@ __device__ __forceinline__ void walk_smem(const LayerKernelArgs& a, uint32_t v, 
   }
 }
 
-template <bool SMEM>
-__global__ void __launch_bounds__(128) k_layers(const LayerKernelArgs a) {
-  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= a.V) return;
-  const mnb_layer_params& P = a.P;
-  const float pz = a.pos[3 * (size_t)v + 2];
-  float zmin = pz, zmax = pz, rsum = 0.0f, value = 0.0f; int rcnt = 0, num = 0;
-  const float r_hd = (float)P.height_diff_radius, r_ro = (float)P.roughness_radius, r_ri = (float)P.ridge_radius;
-  if constexpr (SMEM) {
-    MNB_DYNAMIC_SMEM(ls_raw);
-    uint32_t* ht = reinterpret_cast<uint32_t*>(ls_raw) + threadIdx.x;
-    uint32_t* stack = ht + NB_HASH * LS_THREADS;
-    if (r_hd == r_ro && r_ro == r_ri) {
-      walk_smem<7>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num, ht, stack);
-    } else {
-      walk_smem<1>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num, ht, stack);
-      walk_smem<2>(a, v, r_ro, zmin, zmax, rsum, rcnt, value, num, ht, stack);
-      walk_smem<4>(a, v, r_ri, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+// Third form of the same traversal (same visiting order, same sums): memory-level parallelism instead of occupancy.  The
+// walk is a chain of dependent loads -- pop u, load u's neighbour row, then per neighbour: hash probe -> position ->
+// (inside the radius) normal -- ~13 L2 round trips per expanded vertex, which is what the 9.6 ms of the per-thread forms
+// are made of (round 2 ncu: 18 % issue utilisation, everything on the long scoreboard; the shared-memory hash alone
+// changed nothing).  Here the positions AND normals of all (up to 8) neighbours of u are requested up front, 16 independent
+// 16-byte loads in flight per thread, before the first hash probe; the sequential part then runs on registers.  Seen-set and
+// stack live in shared memory (slot-major: conflict free) with T threads per CTA.
+template <int WHICH, int T>
+__device__ __forceinline__ void walk_pf(const LayerKernelArgs& a, uint32_t v, float radius, float& zmin, float& zmax,
+                                        float& rsum, int& rcnt, float& value, int& num, uint32_t* __restrict__ ht,
+                                        uint32_t* __restrict__ stack) {
+#pragma unroll 8
+  for (int i = 0; i < NB_HASH; ++i) ht[i * T] = 0xffffffffu;
+  const float zmin0 = zmin, zmax0 = zmax, rsum0 = rsum, value0 = value; const int rcnt0 = rcnt, num0 = num;
+  int ns = 0, sp = 0;
+  ht[((v * 2654435761u) >> 25) * T] = v; ns = 1; stack[(sp++) * T] = v;
+  const float4 pv = __ldg(&a.pos4[v]), nv = __ldg(&a.vn4[v]);
+  const float px = pv.x, py = pv.y, pz = pv.z;
+  const float nvx = nv.x, nvy = nv.y, nvz = nv.z;
+  const float rx = px + nvx, ry = py + nvy, rz = pz + nvz;
+  bool overflow = false;
+  auto visit = [&](uint32_t n, const float4& q, const float4& nn) {
+    uint32_t h = (n * 2654435761u) >> 25;
+    for (;;) {
+      const uint32_t e = ht[h * T];
+      if (e == n) return;
+      if (e == 0xffffffffu) break;
+      h = (h + 1u) & (uint32_t)(NB_HASH - 1);
     }
-  } else if (r_hd == r_ro && r_ro == r_ri) {
-    walk<7>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num);
-  } else {
-    walk<1>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num);
-    walk<2>(a, v, r_ro, zmin, zmax, rsum, rcnt, value, num);
-    walk<4>(a, v, r_ri, zmin, zmax, rsum, rcnt, value, num);
+    if (ns >= NB_HSEEN) { overflow = true; return; }
+    ht[h * T] = n; ++ns;
+    const float qx = q.x, qy = q.y, qz = q.z;
+    const float dx = qx - px, dy = qy - py, dz = qz - pz;
+    if (sqrtf(dx * dx + dy * dy + dz * dz) < radius) {
+      if (WHICH & 1) { zmin = fminf(zmin, qz); zmax = fmaxf(zmax, qz); }
+      if (WHICH & 6) {
+        const float nnx = nn.x, nny = nn.y, nnz = nn.z;
+        if (WHICH & 2) {
+          float dot = nvx * nnx + nvy * nny + nvz * nnz;
+          dot = fminf(1.0f, fmaxf(-1.0f, dot));
+          rsum = rsum + acosf(dot); rcnt++;
+        }
+        if (WHICH & 4) {
+          const float cx = (qx + nnx) - rx, cy = (qy + nny) - ry, cz = (qz + nnz) - rz;
+          value += sqrtf(cx * cx + cy * cy + cz * cz); num++;
+        }
+      }
+      if (sp >= LS_STACK) { overflow = true; return; }
+      stack[(sp++) * T] = n;
+      mnb_prefetch_l2(a.nbr8 + 2 * (size_t)n);   // its row is needed when it is popped
+    }
+  };
+  while (sp > 0 && !overflow) {
+    const uint32_t u = stack[(--sp) * T];
+    const uint4 r0 = __ldg(&a.nbr8[2 * (size_t)u]);
+    if (r0.x == NBR8_BIG) {                       // more than 8 neighbours: CSR row, one at a time
+      for (uint32_t k = a.adj_ptr[u]; k < a.adj_ptr[u + 1] && !overflow; ++k) { const uint32_t n = a.adj_nbr[k]; visit(n, __ldg(&a.pos4[n]), __ldg(&a.vn4[n])); }
+      continue;
+    }
+    const uint4 r1 = __ldg(&a.nbr8[2 * (size_t)u + 1]);
+    const uint32_t ids[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    float4 q[8], nn[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {                 // all requests first ...
+      const uint32_t n = ids[j] == NBR8_EMPTY ? v : ids[j];
+      q[j] = __ldg(&a.pos4[n]);
+      if (WHICH & 6) nn[j] = __ldg(&a.vn4[n]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {                 // ... then the sequential part, in the reference's order
+      if (ids[j] == NBR8_EMPTY || overflow) break;
+      visit(ids[j], q[j], nn[j]);
+    }
   }
+  if (overflow) {
+    zmin = zmin0; zmax = zmax0; rsum = rsum0; value = value0; rcnt = rcnt0; num = num0;
+    walk_linear<WHICH>(a, v, radius, zmin, zmax, rsum, rcnt, value, num);
+  }
+}
+
+// per-vertex layer values from the accumulators of the walks, lethal bits, MaxCombination
+__device__ __forceinline__ void layers_epilogue(const LayerKernelArgs& a, uint32_t v, float zmin, float zmax, float rsum, int rcnt, float value, int num) {
+  const mnb_layer_params& P = a.P;
   const float hd = zmax - zmin;
   const float ro = rcnt ? rsum / (float)rcnt : 0.0f;
   const float st = acosf(a.vn[3 * (size_t)v + 2]);                               // steepness_layer.cpp:165
@@ -304,4 +361,55 @@ __global__ void __launch_bounds__(128) k_layers(const LayerKernelArgs a) {
   if (bo > P.border_threshold) mask |= 32;
   if (a.lethal_mask) a.lethal_mask[v] = mask;
   if (a.combined) a.combined[v] = fmaxf(fmaxf(fmaxf(0.0f, hd), fmaxf(ro, st)), fmaxf(fmaxf(ri, cc), bo));   // combination_layer.cpp:60-71
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(128) k_layers(const LayerKernelArgs a) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= a.V) return;
+  const mnb_layer_params& P = a.P;
+  const float pz = a.pos[3 * (size_t)v + 2];
+  float zmin = pz, zmax = pz, rsum = 0.0f, value = 0.0f; int rcnt = 0, num = 0;
+  const float r_hd = (float)P.height_diff_radius, r_ro = (float)P.roughness_radius, r_ri = (float)P.ridge_radius;
+  if constexpr (SMEM) {
+    MNB_DYNAMIC_SMEM(ls_raw);
+    uint32_t* ht = reinterpret_cast<uint32_t*>(ls_raw) + threadIdx.x;
+    uint32_t* stack = ht + NB_HASH * LS_THREADS;
+    if (r_hd == r_ro && r_ro == r_ri) {
+      walk_smem<7>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+    } else {
+      walk_smem<1>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+      walk_smem<2>(a, v, r_ro, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+      walk_smem<4>(a, v, r_ri, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+    }
+  } else if (r_hd == r_ro && r_ro == r_ri) {
+    walk<7>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num);
+  } else {
+    walk<1>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num);
+    walk<2>(a, v, r_ro, zmin, zmax, rsum, rcnt, value, num);
+    walk<4>(a, v, r_ri, zmin, zmax, rsum, rcnt, value, num);
+  }
+  layers_epilogue(a, v, zmin, zmax, rsum, rcnt, value, num);
+}
+
+// the prefetching form (walk_pf) with T threads per CTA; dynamic shared memory = (NB_HASH + LS_STACK) * 4 * T bytes
+template <int T>
+__global__ void __launch_bounds__(T) k_layers_pf(const LayerKernelArgs a) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= a.V) return;
+  const mnb_layer_params& P = a.P;
+  const float pz = a.pos[3 * (size_t)v + 2];
+  float zmin = pz, zmax = pz, rsum = 0.0f, value = 0.0f; int rcnt = 0, num = 0;
+  const float r_hd = (float)P.height_diff_radius, r_ro = (float)P.roughness_radius, r_ri = (float)P.ridge_radius;
+  MNB_DYNAMIC_SMEM(ls_raw);
+  uint32_t* ht = reinterpret_cast<uint32_t*>(ls_raw) + threadIdx.x;
+  uint32_t* stack = ht + NB_HASH * T;
+  if (r_hd == r_ro && r_ro == r_ri) {
+    walk_pf<7, T>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+  } else {
+    walk_pf<1, T>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+    walk_pf<2, T>(a, v, r_ro, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+    walk_pf<4, T>(a, v, r_ri, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+  }
+  layers_epilogue(a, v, zmin, zmax, rsum, rcnt, value, num);
 }

@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(MNB_BATCH_THREADS, MNB_BATCH_MINBLOCKS) k_cvp_
   uint32_t* list0 = a.ws.list0 + (size_t)g * V;
   uint32_t* list1 = a.ws.list1 + (size_t)g * V;
   GroupCtl* ctl = G.ctl;
-  if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; wk.n = 0; }
+  if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; wk.n = 0; wk.ns = 0; }
   __syncthreads();
   for (;;) {
     if (gtid == 0) ctl->query = atomicAdd(a.next_query, 1u);

@@ -11,3 +11,10 @@
 #define MNB_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define MNB_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
+
+// fire-and-forget prefetch of the line at p into the L2 (no register, no scoreboard); a no-op on the CPU interpreter
+#ifdef MNB_EMU_ACTIVE
+static inline void mnb_prefetch_l2(const void*) {}
+#else
+__device__ __forceinline__ void mnb_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif

@@ -276,17 +276,19 @@ def test_layers_shared_memory_variant_is_identical(api, oracle_mod):
         mm = api.MeshMap(pos, faces)
         mm.L.mnb_debug_set_layers_smem.argtypes = [C.c_void_p, C.c_int32]
         P = api._lib.LayerParams.defaults()
+        mm.L.mnb_debug_set_layers_smem(mm._ctx, 0)
         base = mm.computeLayers(P)
-        mm.L.mnb_debug_set_layers_smem(mm._ctx, 1)
-        got = mm.computeLayers(P)
-        for k in list(api._lib.LAYER_NAMES) + ["combined"]:
-            assert (got[k].view(np.uint32) == base[k].view(np.uint32)).all(), k
-        assert (got["lethal_mask"] == base["lethal_mask"]).all()
         P2 = api._lib.LayerParams.defaults(); P2.roughness_radius = 0.2; P2.ridge_radius = 0.45      # three separate walks
-        mm.L.mnb_debug_set_layers_smem(mm._ctx, 0); b2 = mm.computeLayers(P2)
-        mm.L.mnb_debug_set_layers_smem(mm._ctx, 1); g2 = mm.computeLayers(P2)
-        for k in list(api._lib.LAYER_NAMES) + ["combined"]:
-            assert (g2[k].view(np.uint32) == b2[k].view(np.uint32)).all(), k
+        b2 = mm.computeLayers(P2)
+        for mode in (1, 2, 3, 4):        # 1: shared-memory seen-set; 2-4: the prefetching walk with 64 / 128 / 32 threads per CTA
+            mm.L.mnb_debug_set_layers_smem(mm._ctx, mode)
+            got = mm.computeLayers(P)
+            for k in list(api._lib.LAYER_NAMES) + ["combined"]:
+                assert (got[k].view(np.uint32) == base[k].view(np.uint32)).all(), (mode, k)
+            assert (got["lethal_mask"] == base["lethal_mask"]).all()
+            g2 = mm.computeLayers(P2)
+            for k in list(api._lib.LAYER_NAMES) + ["combined"]:
+                assert (g2[k].view(np.uint32) == b2[k].view(np.uint32)).all(), (mode, k)
         mm.close()
 
 
