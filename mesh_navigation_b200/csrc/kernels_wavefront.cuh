@@ -182,10 +182,10 @@ __global__ void __launch_bounds__(MNB_CVP_THREADS, MNB_CVP_MINBLOCKS) k_cvp(cons
 // Batches of full-field plans (mnb_cvp_batch): the lean round loop of batch_engine.cuh.  One wavefront per CTA (CS = 1) or
 // per cluster of CS CTAs; persistent groups pull goal indices from an atomic counter.
 #ifndef MNB_BATCH_THREADS
-#define MNB_BATCH_THREADS 512
+#define MNB_BATCH_THREADS 256
 #endif
 #ifndef MNB_BATCH_MINBLOCKS
-#define MNB_BATCH_MINBLOCKS 2
+#define MNB_BATCH_MINBLOCKS 4
 #endif
 template <int CS>
 __global__ void __launch_bounds__(MNB_BATCH_THREADS, MNB_BATCH_MINBLOCKS) k_cvp_batch(const CvpKernelArgs a) {
