@@ -78,7 +78,10 @@ struct TimeAlg {
     return t.a2 == 0.0f ? 1u : (t.a3 == 0.0f ? 2u : ((t.ext & EXT_POOL) ? __ldcg(&pool[t.ext & ~EXT_POOL]) : 3u));
   }
   // levels 2.. tie on the key of level 2 (rare: same cascade, bit-identical keys or the same sub-trigger)
-  __device__ __noinline__ bool less_tail(const EvTime& x, const EvTime& y) const {
+  // (the out-of-line helpers take pop times BY VALUE: a by-reference argument of a __noinline__ callee forces the caller's
+  // variable into local memory for its whole lifetime -- labels a, b, T and tc of the hot path were stored to the stack on
+  // every evaluation while these took references, profiles/r02o)
+  __device__ __noinline__ bool less_tail(const EvTime x, const EvTime y) const {
     const uint32_t i2x = id2_of(x), i2y = id2_of(y);
     if (i2x != i2y) return i2x < i2y;
     if (x.a3 != y.a3) return x.a3 < y.a3;
@@ -103,7 +106,7 @@ struct TimeAlg {
     if (x.a2 == 0.0f) return false;                                 // both are the vertex (a1, root) itself
     return less_tail(x, y);
   }
-  __device__ __noinline__ bool eq_pool(const EvTime& x, const EvTime& y) const {
+  __device__ __noinline__ bool eq_pool(const EvTime x, const EvTime y) const {
     if (!(x.ext & y.ext & EXT_POOL)) return false;
     const uint32_t ox = x.ext & ~EXT_POOL, oy = y.ext & ~EXT_POOL;
     if (ox == oy) return true;
@@ -173,7 +176,7 @@ struct LabelStore : TimeAlg {
   // each other -- a stable fixed point of the pull iteration that the sequential order does not have (found by the
   // randomised tests as soon as the stacks were exact).  Such a face does not fire; T itself is re-evaluated because its
   // source c changed.
-  __device__ __noinline__ bool names_slow(const EvTime& T, uint32_t c) const {
+  __device__ __noinline__ bool names_slow(const EvTime T, uint32_t c) const {
     if (T.root == c || id2_of(T) == c) return true;
     if (T.a3 == 0.0f) return false;
     if (id3_of(T) == c) return true;
@@ -199,7 +202,7 @@ struct LabelStore : TimeAlg {
     t.a1 = F.a1; t.root = F.root; t.a2 = F.a2; t.a3 = X; t.ext = i2; t.self = c;
     return true;
   }
-  __device__ __noinline__ void accept_deep(uint32_t c, float X, const EvTime& F, EvFull& o) const {
+  __device__ __noinline__ void accept_deep(uint32_t c, float X, const EvTime F, EvFull& o) const {
     const uint32_t nF = levels_of(F), xb = __float_as_uint(X);
     uint32_t k = 3;                                     // (accept_lean has established that levels 1-3 of F stay)
     for (uint32_t i = 4; i <= nF; ++i) {
@@ -219,7 +222,7 @@ struct LabelStore : TimeAlg {
     if (i == x.n) { kb = __float_as_uint(x.last); id = x.t.self; }
     else { const uint32_t o = x.src + 3 + 2 * (i - 4); kb = __ldcg(&pool[o]); id = __ldcg(&pool[o + 1]); }
   }
-  __device__ __noinline__ bool less_T_deep(const EvTime& T, const EvFull& x) const {
+  __device__ __noinline__ bool less_T_deep(const EvTime T, const EvFull& x) const {
     if (T.a1 != x.t.a1) return T.a1 < x.t.a1;
     if (T.root != x.t.root) return T.root < x.t.root;
     if (T.a2 == 0.0f) return true;                      // T is a proper prefix of x
@@ -243,7 +246,7 @@ struct LabelStore : TimeAlg {
   __device__ __forceinline__ bool less_T_full(const EvTime& T, const EvFull& x) const {
     return x.n <= 3u ? tless(T, x.t) : less_T_deep(T, x);
   }
-  __device__ __noinline__ bool eq_deep(const EvFull& x, const EvTime& T) const {
+  __device__ __noinline__ bool eq_deep(const EvFull& x, const EvTime T) const {
     if (__float_as_uint(T.a1) != __float_as_uint(x.t.a1) || __float_as_uint(T.a2) != __float_as_uint(x.t.a2) ||
         __float_as_uint(T.a3) != __float_as_uint(x.t.a3) || T.root != x.t.root || T.self != x.t.self || !(T.ext & EXT_POOL)) return false;
     if (levels_of(T) != x.n || id2_of(T) != x.id2 || id3_of(T) != x.id3) return false;
@@ -613,7 +616,9 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
         }
       }
     }
+#ifdef MNB_GRID_TIMING
     const long long tp0 = clock64();
+#endif
     float my_mtau = requeued ? goal : __uint_as_float(INF_BITS), my_lo = requeued ? goal : __uint_as_float(INF_BITS);   // a pending change
     // One evaluation of candidate c by its 8-lane group (every lane of the WARP calls this; idle groups pass
     // has = false so that the sub-warp shuffles can use compile-time full masks).  `fresh` = main pass (c comes from
@@ -740,10 +745,16 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
     }
     // ---- in-round sweeps: the CTA keeps relaxing the candidates it staged (survivors + newly activated) whose
     // inputs changed since their last evaluation, so a dependency chain advances several hops per barrier ----
+#ifdef MNB_GRID_TIMING
     const long long tps = clock64();
+#endif
+#ifdef MNB_GRID_TIMING
     if (gtid == 0) { ctl->t_ph[0] += (unsigned long long)(tps - tp0); ctl->t_ph[2] += cnt; }
+#endif
     if constexpr (SW) for (int sw = 0; sw < n_sweeps; ++sw) {
+#ifdef MNB_GRID_TIMING
       const long long tq0 = clock64();
+#endif
       __syncthreads();                       // stage pushes / label-cache writes of the previous phase are visible
       const unsigned int ns = min(st.n, (unsigned int)Stage::SW_CAP);
       unsigned int* dcur = &ss->dn[sw & 1];
@@ -755,8 +766,12 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
       }
       __syncthreads();
       const unsigned int dn = *dcur;
+#ifdef MNB_GRID_TIMING
       const long long tq1 = clock64();
+#endif
+#ifdef MNB_GRID_TIMING
       if (gtid == 0) { ctl->t_ph[3] += dn; ctl->t_ph[4] += ns; ctl->t_ph[5] += (unsigned long long)(tq1 - tq0); }
+#endif
       for (unsigned int ib = (threadIdx.x >> 5) * 4u; ib < dn; ib += (blockDim.x >> 3)) {
         const unsigned int i = ib + ((threadIdx.x & 31) >> 3);
         const bool has = i < dn;
@@ -769,7 +784,9 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
         const uint32_t mk = __ldcg(&mark[c]);
         evaluate(has, c, old, ix, w, mk, 0u, false, slot);
       }
+#ifdef MNB_GRID_TIMING
       if (gtid == 0) ctl->t_ph[6] += (unsigned long long)(clock64() - tq1);
+#endif
     }
     {
       my_mtau = fminf(my_mtau, prob.deferred_m);      // deferred back-steps are pending changes
@@ -782,12 +799,18 @@ __device__ void run_band_rounds_sub8(P& prob, GroupCtl* ctl, uint32_t* list0, ui
       }
     }
     __syncthreads();
+#ifdef MNB_GRID_TIMING
     const long long tp1 = clock64();
+#endif
     stage_flush(st, list_n, &ctl->count[next], &ctl->m_tau[slot], &ctl->lo[slot]);
+#ifdef MNB_GRID_TIMING
     const long long tp2 = clock64();
+#endif
     band_end_prev = band_end;
     group_sync<CS>(ctl->barrier);
+#ifdef MNB_GRID_TIMING
     if (gtid == 0) { const long long tp3 = clock64(); ctl->t_work += (unsigned long long)(tp1 - tp0); ctl->t_flush += (unsigned long long)(tp2 - tp1); ctl->t_sync += (unsigned long long)(tp3 - tp2); }
+#endif
   }
   atomicAdd(&ctl->recomputes, my_recomputes);
   atomicAdd(&ctl->settled, my_settled);

@@ -435,7 +435,14 @@ struct CvpEllProblemT : CvpProblem {
       }
     }
     if (big) {   // rare: more than 8 faces / a deep cascade -> scalar path on the group's first lane, result broadcast below
-      if (j == 0) replay_serial(c, band_end, goal, round, old_t, cur, tc);
+      if (j == 0) {
+        // (by-reference arguments of a __noinline__ callee live in local memory: keep the address-taken copies inside this
+        // rare branch, or every update of cur / tc in the hot path above becomes a local store -- 4.5x the local stores of
+        // the whole kernel when that was overlooked, profiles/r02m)
+        const EvTime ot = old_t; float cs; EvTime ts;
+        replay_serial(c, band_end, goal, round, ot, cs, ts);
+        cur = cs; tc = ts;
+      }
     }
     if constexpr (!SKIP) excl_min_out = 0.0f;
     else {
@@ -813,7 +820,7 @@ struct DijkstraEllProblem : DijkstraProblem {
       const uint32_t ou = __shfl_xor_sync(FULL, u, o, 8);
       if (better(ot, od, ou, tmp, du, u)) { tmp = ot; du = od; u = ou; }
     }
-    if (big && j == 0) replay_serial(c, band_end, goal, tmp, u);
+    if (big && j == 0) { float ts; uint32_t us; replay_serial(c, band_end, goal, ts, us); tmp = ts; u = us; }   // (address-taken copies stay in the rare branch)
     if (__ballot_sync(FULL, big)) { tmp = __shfl_sync(FULL, tmp, 0, 8); u = __shfl_sync(FULL, u, 0, 8); }
     nd = tmp; nt = ev_normal(tmp, c);
     // predecessor of the winning relaxation (it can change among exact ties without the potential changing)
