@@ -43,6 +43,12 @@ __global__ void k_vertex_normals(const uint32_t* __restrict__ cor_ptr, const int
   vn[3 * (size_t)v] = nx; vn[3 * (size_t)v + 1] = ny; vn[3 * (size_t)v + 2] = nz;
 }
 
+// acos of a float as the layers use it (roughness: angle between normals, steepness_layer.cpp:165): evaluated in double and
+// rounded once.  The reference calls the float overload of its libm, whose last bit differs between libm versions and
+// from CUDA's acosf; lethal sets are threshold tests on these values, so both this kernel and the oracle use the value
+// that is well defined everywhere -- the correctly rounded one (double acos is accurate to < 2 ulp of double on both sides).
+__device__ __forceinline__ float acos_f(float x) { return (float)acos((double)x); }
+
 struct LayerKernelArgs {
   uint32_t V;
   const float* pos; const float* vn;
@@ -105,7 +111,7 @@ __device__ __noinline__ void walk_linear(const LayerKernelArgs& a, uint32_t v, f
           if (WHICH & 2) {
             float dot = nvx * nnx + nvy * nny + nvz * nnz;
             dot = fminf(1.0f, fmaxf(-1.0f, dot));
-            rsum = rsum + acosf(dot); rcnt++;
+            rsum = rsum + acos_f(dot); rcnt++;
           }
           if (WHICH & 4) {
             const float cx = (qx + nnx) - rx, cy = (qy + nny) - ry, cz = (qz + nnz) - rz;
@@ -161,7 +167,7 @@ __device__ __forceinline__ void walk(const LayerKernelArgs& a, uint32_t v, float
           if (WHICH & 2) {
             float dot = nvx * nnx + nvy * nny + nvz * nnz;
             dot = fminf(1.0f, fmaxf(-1.0f, dot));
-            rsum = rsum + acosf(dot); rcnt++;
+            rsum = rsum + acos_f(dot); rcnt++;
           }
           if (WHICH & 4) {
             const float cx = (qx + nnx) - rx, cy = (qy + nny) - ry, cz = (qz + nnz) - rz;
@@ -220,7 +226,7 @@ __device__ __forceinline__ void walk_smem(const LayerKernelArgs& a, uint32_t v, 
         if (WHICH & 2) {
           float dot = nvx * nnx + nvy * nny + nvz * nnz;
           dot = fminf(1.0f, fmaxf(-1.0f, dot));
-          rsum = rsum + acosf(dot); rcnt++;
+          rsum = rsum + acos_f(dot); rcnt++;
         }
         if (WHICH & 4) {
           const float cx = (qx + nnx) - rx, cy = (qy + nny) - ry, cz = (qz + nnz) - rz;
@@ -292,7 +298,7 @@ __device__ __forceinline__ void walk_pf(const LayerKernelArgs& a, uint32_t v, fl
         if (WHICH & 2) {
           float dot = nvx * nnx + nvy * nny + nvz * nnz;
           dot = fminf(1.0f, fmaxf(-1.0f, dot));
-          rsum = rsum + acosf(dot); rcnt++;
+          rsum = rsum + acos_f(dot); rcnt++;
         }
         if (WHICH & 4) {
           const float cx = (qx + nnx) - rx, cy = (qy + nny) - ry, cz = (qz + nnz) - rz;
@@ -337,7 +343,7 @@ __device__ __forceinline__ void layers_epilogue(const LayerKernelArgs& a, uint32
   const mnb_layer_params& P = a.P;
   const float hd = zmax - zmin;
   const float ro = rcnt ? rsum / (float)rcnt : 0.0f;
-  const float st = acosf(a.vn[3 * (size_t)v + 2]);                               // steepness_layer.cpp:165
+  const float st = acos_f(a.vn[3 * (size_t)v + 2]);                               // steepness_layer.cpp:165
   const float ri = num == 0 ? (float)(P.ridge_threshold + 0.1) : value / num;     // ridge_layer.cpp:177-184
   const float cl = a.clearance ? a.clearance[v] : __uint_as_float(INF_BITS);
   float cc; bool cl_lethal = false;                                              // clearance_layer.cpp:77-96

@@ -376,6 +376,14 @@ __global__ void __launch_bounds__(256) k_cvp_epilogue(const CvpKernelArgs a, Gro
   prob.write_aux(c, win, wu1, wu2);
 }
 
+// start == goal (dijkstra_mesh_planner.cpp:252-255): the maps as the reference leaves them after clearing (:241-249)
+__global__ void k_dijkstra_trivial(uint32_t V, uint32_t seed, float* __restrict__ dist, uint32_t* __restrict__ pred) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  if (dist) dist[v] = v == seed ? 0.0f : __uint_as_float(INF_BITS);
+  if (pred) pred[v] = v;
+}
+
 struct DijkstraKernelArgs {
   uint32_t V;
   const uint32_t* adj_ptr; const uint2* adj_nw;

@@ -131,6 +131,25 @@ static int32_t ensure_workspace(mnb_ctx* ctx, uint32_t groups) {
   return MNB_OK;
 }
 
+// Runs the body of a C-ABI entry point: std::bad_alloc (the host tables of a 50M-vertex map are tens of GB) becomes
+// MNB_E_NOMEM, anything else MNB_E_STATE; a failed mnb_set_mesh frees what it had built so that later calls see an empty
+// context instead of a half-built one.
+template <class F>
+static int32_t guarded(mnb_ctx* ctx, F body) {
+  try {
+    return body();
+  } catch (const std::bad_alloc&) {
+    if (ctx) ctx->err = "out of host memory";
+    return MNB_E_NOMEM;
+  } catch (const std::exception& ex) {
+    if (ctx) ctx->err = ex.what();
+    return MNB_E_STATE;
+  } catch (...) {
+    if (ctx) ctx->err = "unknown exception";
+    return MNB_E_STATE;
+  }
+}
+
 extern "C" {
 
 int32_t mnb_create(int32_t device, mnb_ctx** out_ctx) {
@@ -191,7 +210,7 @@ int32_t mnb_set_tuning(mnb_ctx* ctx, float band_delta, int32_t cluster_size, int
   } else if (cluster_size == -1) {
     ctx->cluster = -1;        // single plans on the whole grid (cooperative launch); batches keep their cluster size
   } else if (cluster_size != 0) return MNB_E_ARG;
-  if (threads_per_cta == 128 || threads_per_cta == 256 || threads_per_cta == 512) ctx->threads = threads_per_cta;
+  if (threads_per_cta == 128 || threads_per_cta == 256 || threads_per_cta == 512) { ctx->threads = threads_per_cta; ctx->grid_blocks_per_sm = 0; }
   else if (threads_per_cta != 0) return MNB_E_ARG;
   return MNB_OK;
 }
@@ -201,7 +220,7 @@ int32_t mnb_get_stats(mnb_ctx* ctx, mnb_stats* out) {
   *out = ctx->stats; return MNB_OK;
 }
 
-int32_t mnb_set_mesh(mnb_ctx* ctx, uint32_t V, uint32_t F, const float* pos, const uint32_t* faces,
+static int32_t impl_set_mesh(mnb_ctx* ctx, uint32_t V, uint32_t F, const float* pos, const uint32_t* faces,
                      const uint32_t* edges, uint32_t E) {
   if (!ctx || !pos || !faces || V == 0 || F == 0) return MNB_E_ARG;
   CK(cudaSetDevice(ctx->device));
@@ -296,7 +315,7 @@ static int32_t install_weights(mnb_ctx* ctx) {
   return MNB_OK;
 }
 
-int32_t mnb_compute_edge_weights(mnb_ctx* ctx, const float* vertex_costs, double edge_cost_factor, float* out_w) {
+static int32_t impl_compute_edge_weights(mnb_ctx* ctx, const float* vertex_costs, double edge_cost_factor, float* out_w) {
   if (!ctx || !vertex_costs || !ctx->V) return MNB_E_ARG;
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpyAsync(ctx->d_cost, vertex_costs, sizeof(float) * (size_t)ctx->V, in_kind(ctx), ctx->stream));
@@ -309,7 +328,7 @@ int32_t mnb_compute_edge_weights(mnb_ctx* ctx, const float* vertex_costs, double
   return MNB_OK;
 }
 
-int32_t mnb_set_costs(mnb_ctx* ctx, const float* vertex_costs, const float* edge_weights, const uint8_t* invalid) {
+static int32_t impl_set_costs(mnb_ctx* ctx, const float* vertex_costs, const float* edge_weights, const uint8_t* invalid) {
   if (!ctx || !vertex_costs || !edge_weights || !ctx->V) return MNB_E_ARG;
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpyAsync(ctx->d_cost, vertex_costs, sizeof(float) * (size_t)ctx->V, in_kind(ctx), ctx->stream));
@@ -342,7 +361,7 @@ static RepulsiveField repulsive_field_of(mnb_ctx* ctx) {
 
 extern "C" {
 
-int32_t mnb_inflation_vector_map(mnb_ctx* ctx, float* out_vectors) {
+static int32_t impl_inflation_vector_map(mnb_ctx* ctx, float* out_vectors) {
   if (!ctx || !ctx->V) return MNB_E_ARG;
   if (!ctx->infl_labels_valid) {
     ctx->err = "mnb_inflation_vector_map needs the labels of the last mnb_inflate / mnb_inflation_update: call it before the next planner call on this context";
@@ -390,7 +409,7 @@ int32_t mnb_set_repulsive_field(mnb_ctx* ctx, int32_t enable) {
   return MNB_OK;
 }
 
-int32_t mnb_inflation_vector_at(mnb_ctx* ctx, uint32_t n, const uint32_t* faces_q, const float* bary, float* out) {
+static int32_t impl_inflation_vector_at(mnb_ctx* ctx, uint32_t n, const uint32_t* faces_q, const float* bary, float* out) {
   if (!ctx || !ctx->V || !faces_q || !bary || !out || n == 0) return MNB_E_ARG;
   if (!ctx->infl_field_valid) { ctx->err = "mnb_inflation_vector_at needs mnb_inflation_vector_map first"; return MNB_E_STATE; }
   for (uint32_t i = 0; ctx->ptr_mode == MNB_PTR_HOST && i < n; ++i) if (faces_q[i] >= ctx->F) return MNB_E_ARG;
@@ -500,7 +519,7 @@ static void fill_cvp_args(mnb_ctx* ctx, CvpKernelArgs& a) {
 
 extern "C" {
 
-int32_t mnb_cvp(mnb_ctx* ctx, uint32_t seed_face, const float seed_pos[3], int64_t robot_face, double cost_limit,
+static int32_t impl_cvp(mnb_ctx* ctx, uint32_t seed_face, const float seed_pos[3], int64_t robot_face, double cost_limit,
                 double goal_dist_offset, float* out_dist, uint32_t* out_pred, float* out_direction, int32_t* out_cut) {
   if (!ctx || !seed_pos || !ctx->V) return MNB_E_ARG;
   if (!ctx->costs_set) { ctx->err = "mnb_set_costs / mnb_compute_edge_weights not called"; return MNB_E_STATE; }
@@ -533,7 +552,8 @@ int32_t mnb_cvp(mnb_ctx* ctx, uint32_t seed_face, const float seed_pos[3], int64
     a.delta = ctx->grid_delta;
     if (ctx->grid_blocks_per_sm == 0) {
       int nb = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_cvp_grid<false>, ctx->threads, 0));
+      if (a.skip_clean) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_cvp_grid<true>, ctx->threads, 0));
+      else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_cvp_grid<false>, ctx->threads, 0));
       ctx->grid_blocks_per_sm = nb > MNB_GRID_MINBLOCKS ? MNB_GRID_MINBLOCKS : nb;
       if (nb <= 0) { ctx->err = "k_cvp_grid cannot be resident"; return MNB_E_CUDA; }
     }
@@ -573,7 +593,7 @@ int32_t mnb_cvp(mnb_ctx* ctx, uint32_t seed_face, const float seed_pos[3], int64
   return MNB_SUCCESS;
 }
 
-int32_t mnb_cvp_batch(mnb_ctx* ctx, uint32_t n, const uint32_t* seed_faces, const float* seed_pos, double cost_limit,
+static int32_t impl_cvp_batch(mnb_ctx* ctx, uint32_t n, const uint32_t* seed_faces, const float* seed_pos, double cost_limit,
                       float* out_dist) {
   if (!ctx || !seed_faces || !seed_pos || !out_dist || !ctx->V || n == 0) return MNB_E_ARG;
   if (!ctx->costs_set) { ctx->err = "costs not set"; return MNB_E_STATE; }
@@ -631,7 +651,7 @@ int32_t mnb_cvp_batch(mnb_ctx* ctx, uint32_t n, const uint32_t* seed_faces, cons
   return MNB_SUCCESS;
 }
 
-int32_t mnb_dijkstra(mnb_ctx* ctx, uint32_t seed_vertex, int64_t robot_vertex, double cost_limit, double goal_dist_offset,
+static int32_t impl_dijkstra(mnb_ctx* ctx, uint32_t seed_vertex, int64_t robot_vertex, double cost_limit, double goal_dist_offset,
                      float* out_dist, uint32_t* out_pred) {
   if (!ctx || !ctx->V) return MNB_E_ARG;
   if (!ctx->costs_set) { ctx->err = "costs not set"; return MNB_E_STATE; }
@@ -652,7 +672,18 @@ int32_t mnb_dijkstra(mnb_ctx* ctx, uint32_t seed_vertex, int64_t robot_vertex, d
   a.out_dist = (dev && out_dist) ? out_dist : ctx->d_out_dist;
   a.out_pred = (dev && out_pred) ? out_pred : ctx->d_out_pred;
   a.cancel_flag = ctx->d_cancel; a.max_rounds = watchdog_rounds(ctx->V);
-  if (robot_vertex >= 0 && (uint32_t)robot_vertex == seed_vertex) return MNB_SUCCESS;   // dijkstra:252-255
+  if (robot_vertex >= 0 && (uint32_t)robot_vertex == seed_vertex) {   // dijkstra:252-255: "start == goal" returns before the wave
+    // the reference has cleared its maps by then (:241-249): distances +inf (seed 0), every vertex its own predecessor
+    MNB_LAUNCH(k_dijkstra_trivial, (ctx->V + 255) / 256, 256, 0, ctx->stream, ctx->V, seed_vertex, a.out_dist, a.out_pred);
+    CK(cudaGetLastError());
+    if (!dev) {
+      if (out_dist) CK(cudaMemcpyAsync(out_dist, a.out_dist, sizeof(float) * (size_t)ctx->V, cudaMemcpyDeviceToHost, ctx->stream));
+      if (out_pred) CK(cudaMemcpyAsync(out_pred, a.out_pred, sizeof(uint32_t) * (size_t)ctx->V, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats = mnb_stats{}; ctx->stats.kernel_launches = 1;
+    return MNB_SUCCESS;
+  }
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   cudaError_t e;
   const int cs = ctx->cluster;
@@ -689,7 +720,7 @@ int32_t mnb_get_vertex_normals(mnb_ctx* ctx, float* out) {
   return MNB_OK;
 }
 
-int32_t mnb_compute_layers(mnb_ctx* ctx, const mnb_layer_params* params, const float* clearance, float* out_costs,
+static int32_t impl_compute_layers(mnb_ctx* ctx, const mnb_layer_params* params, const float* clearance, float* out_costs,
                            float* out_combined, uint8_t* out_lethal_mask) {
   if (!ctx || !params || !ctx->V) return MNB_E_ARG;
   CK(cudaSetDevice(ctx->device));
@@ -750,7 +781,7 @@ int32_t mnb_compute_layers(mnb_ctx* ctx, const mnb_layer_params* params, const f
   return MNB_OK;
 }
 
-int32_t mnb_vector_map(mnb_ctx* ctx, const uint32_t* pred, const float* direction, const int32_t* cutting_face, float* out_vec) {
+static int32_t impl_vector_map(mnb_ctx* ctx, const uint32_t* pred, const float* direction, const int32_t* cutting_face, float* out_vec) {
   if (!ctx || !ctx->V || !pred || !out_vec) return MNB_E_ARG;
   CK(cudaSetDevice(ctx->device));
   const size_t V = ctx->V;
@@ -776,7 +807,7 @@ int32_t mnb_vector_map(mnb_ctx* ctx, const uint32_t* pred, const float* directio
   return MNB_OK;
 }
 
-int32_t mnb_cvp_backtrack(mnb_ctx* ctx, const float robot_pos[3], uint32_t robot_face, double step_width, uint32_t max_points,
+static int32_t impl_cvp_backtrack(mnb_ctx* ctx, const float robot_pos[3], uint32_t robot_face, double step_width, uint32_t max_points,
                           float* path_pos, uint32_t* path_face, uint32_t* n_points) {
   if (!ctx || !ctx->V || !robot_pos || !path_pos || !n_points || max_points < 2) return MNB_E_ARG;
   if (!ctx->last_valid) { ctx->err = "mnb_cvp_backtrack needs a preceding successful mnb_cvp on this context"; return MNB_E_STATE; }
@@ -816,7 +847,7 @@ int32_t mnb_cvp_backtrack(mnb_ctx* ctx, const float robot_pos[3], uint32_t robot
   return res[0];
 }
 
-int32_t mnb_locate(mnb_ctx* ctx, uint32_t n, const float* points, uint32_t* out_vertex, int32_t* out_face, float* out_bary) {
+static int32_t impl_locate(mnb_ctx* ctx, uint32_t n, const float* points, uint32_t* out_vertex, int32_t* out_face, float* out_bary) {
   if (!ctx || !ctx->V || !points || n == 0) return MNB_E_ARG;
   CK(cudaSetDevice(ctx->device));
   const bool dev = ctx->ptr_mode == MNB_PTR_DEVICE;
@@ -856,7 +887,7 @@ int32_t mnb_debug_set_sweeps(mnb_ctx* ctx, int32_t k) { if (!ctx || k < -1 || k 
 
 int32_t mnb_debug_set_infl_skip(mnb_ctx* ctx, int32_t on) { if (!ctx) return MNB_E_ARG; ctx->infl_skip_clean = on != 0; return MNB_OK; }
 int32_t mnb_debug_set_layers_smem(mnb_ctx* ctx, int32_t mode) { if (!ctx || mode < 0 || mode > 4) return MNB_E_ARG; ctx->layers_smem = mode; return MNB_OK; }
-int32_t mnb_debug_set_skip_clean(mnb_ctx* ctx, int32_t on) { if (!ctx) return MNB_E_ARG; ctx->skip_clean = on != 0; return MNB_OK; }
+int32_t mnb_debug_set_skip_clean(mnb_ctx* ctx, int32_t on) { if (!ctx) return MNB_E_ARG; ctx->skip_clean = on != 0; ctx->grid_blocks_per_sm = 0; return MNB_OK; }
 
 // debugging aid (not part of the public header): raw labels {d, a1, a2, a3|flag} of wavefront group 0
 int32_t mnb_debug_get_labels(mnb_ctx* ctx, uint32_t* out4v) {
@@ -946,12 +977,12 @@ static int32_t inflate_impl(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, c
 
 extern "C" {
 
-int32_t mnb_inflate(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, const uint8_t* invalid,
+static int32_t impl_inflate(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, const uint8_t* invalid,
                     const mnb_inflation_params* params, float* out_dist, float* out_cost) {
   return inflate_impl(ctx, lethals, n, invalid, params, out_dist, out_cost, false, nullptr, nullptr);
 }
 
-int32_t mnb_inflation_update(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, const uint8_t* invalid,
+static int32_t impl_inflation_update(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, const uint8_t* invalid,
                              const mnb_inflation_params* params, float* out_dist, float* out_cost, uint32_t* out_changed,
                              uint32_t* n_changed) {
   if (!n_changed) return MNB_E_ARG;
@@ -968,7 +999,7 @@ int32_t mnb_get_costs(mnb_ctx* ctx, float* out_vertex_costs, float* out_edge_wei
   return MNB_OK;
 }
 
-int32_t mnb_update_vertex_costs(mnb_ctx* ctx, uint32_t n_changed, const uint32_t* changed, const float* costs,
+static int32_t impl_update_vertex_costs(mnb_ctx* ctx, uint32_t n_changed, const uint32_t* changed, const float* costs,
                                 int32_t costs_indexed_by_vertex, float default_value, double edge_cost_factor) {
   if (!ctx || !ctx->V || (n_changed && (!changed || !costs))) return MNB_E_ARG;
   if (!ctx->costs_set) { ctx->err = "mnb_update_vertex_costs needs mnb_set_costs / mnb_compute_edge_weights first"; return MNB_E_STATE; }
@@ -1066,17 +1097,86 @@ static int32_t combination_update(mnb_ctx* ctx, uint32_t n_layers, const float* 
 
 extern "C" {
 
-int32_t mnb_max_combination_update(mnb_ctx* ctx, uint32_t n_layers, const float* const* layer_costs, const float* defaults,
+static int32_t impl_max_combination_update(mnb_ctx* ctx, uint32_t n_layers, const float* const* layer_costs, const float* defaults,
                                    const uint8_t* const* layer_lethal, uint32_t n_changed, const uint32_t* changed,
                                    float* io_costs, uint8_t* io_lethal) {
   return combination_update(ctx, n_layers, layer_costs, defaults, nullptr, layer_lethal, n_changed, changed, io_costs, io_lethal);
 }
 
-int32_t mnb_avg_combination_update(mnb_ctx* ctx, uint32_t n_layers, const float* const* layer_costs, const float* defaults,
+static int32_t impl_avg_combination_update(mnb_ctx* ctx, uint32_t n_layers, const float* const* layer_costs, const float* defaults,
                                    const float* weights, const uint8_t* const* layer_lethal, uint32_t n_changed,
                                    const uint32_t* changed, float* io_costs, uint8_t* io_lethal) {
   if (!weights) return MNB_E_ARG;
   return combination_update(ctx, n_layers, layer_costs, defaults, weights, layer_lethal, n_changed, changed, io_costs, io_lethal);
+}
+
+// ---- exception barrier: nothing propagates through the C ABI; a failed call leaves no half-built state behind ----
+int32_t mnb_set_mesh(mnb_ctx* ctx, uint32_t V, uint32_t F, const float* pos, const uint32_t* faces,
+                     const uint32_t* edges, uint32_t E) {
+  const int32_t rc = guarded(ctx, [&]() { return impl_set_mesh(ctx, V, F, pos, faces, edges, E); });
+  if (rc != MNB_OK && ctx) { free_mesh(ctx); ctx->V = 0; ctx->F = 0; ctx->E = 0; }      // no half-built context
+  return rc;
+}
+int32_t mnb_cvp(mnb_ctx* ctx, uint32_t seed_face, const float seed_pos[3], int64_t robot_face, double cost_limit,
+                double goal_dist_offset, float* out_dist, uint32_t* out_pred, float* out_direction, int32_t* out_cut) {
+  return guarded(ctx, [&]() { return impl_cvp(ctx, seed_face, seed_pos, robot_face, cost_limit, goal_dist_offset, out_dist, out_pred, out_direction, out_cut); });
+}
+int32_t mnb_cvp_batch(mnb_ctx* ctx, uint32_t n, const uint32_t* seed_faces, const float* seed_pos, double cost_limit,
+                      float* out_dist) {
+  return guarded(ctx, [&]() { return impl_cvp_batch(ctx, n, seed_faces, seed_pos, cost_limit, out_dist); });
+}
+int32_t mnb_dijkstra(mnb_ctx* ctx, uint32_t seed_vertex, int64_t robot_vertex, double cost_limit, double goal_dist_offset,
+                     float* out_dist, uint32_t* out_pred) {
+  return guarded(ctx, [&]() { return impl_dijkstra(ctx, seed_vertex, robot_vertex, cost_limit, goal_dist_offset, out_dist, out_pred); });
+}
+int32_t mnb_inflate(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, const uint8_t* invalid,
+                    const mnb_inflation_params* params, float* out_dist, float* out_cost) {
+  return guarded(ctx, [&]() { return impl_inflate(ctx, lethals, n, invalid, params, out_dist, out_cost); });
+}
+int32_t mnb_inflation_update(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, const uint8_t* invalid,
+                             const mnb_inflation_params* params, float* out_dist, float* out_cost, uint32_t* out_changed,
+                             uint32_t* n_changed) {
+  return guarded(ctx, [&]() { return impl_inflation_update(ctx, lethals, n, invalid, params, out_dist, out_cost, out_changed, n_changed); });
+}
+int32_t mnb_compute_layers(mnb_ctx* ctx, const mnb_layer_params* params, const float* clearance, float* out_costs,
+                           float* out_combined, uint8_t* out_lethal_mask) {
+  return guarded(ctx, [&]() { return impl_compute_layers(ctx, params, clearance, out_costs, out_combined, out_lethal_mask); });
+}
+int32_t mnb_set_costs(mnb_ctx* ctx, const float* vertex_costs, const float* edge_weights, const uint8_t* invalid) {
+  return guarded(ctx, [&]() { return impl_set_costs(ctx, vertex_costs, edge_weights, invalid); });
+}
+int32_t mnb_compute_edge_weights(mnb_ctx* ctx, const float* vertex_costs, double edge_cost_factor, float* out_w) {
+  return guarded(ctx, [&]() { return impl_compute_edge_weights(ctx, vertex_costs, edge_cost_factor, out_w); });
+}
+int32_t mnb_locate(mnb_ctx* ctx, uint32_t n, const float* points, uint32_t* out_vertex, int32_t* out_face, float* out_bary) {
+  return guarded(ctx, [&]() { return impl_locate(ctx, n, points, out_vertex, out_face, out_bary); });
+}
+int32_t mnb_vector_map(mnb_ctx* ctx, const uint32_t* pred, const float* direction, const int32_t* cutting_face, float* out_vec) {
+  return guarded(ctx, [&]() { return impl_vector_map(ctx, pred, direction, cutting_face, out_vec); });
+}
+int32_t mnb_inflation_vector_map(mnb_ctx* ctx, float* out_vectors) {
+  return guarded(ctx, [&]() { return impl_inflation_vector_map(ctx, out_vectors); });
+}
+int32_t mnb_inflation_vector_at(mnb_ctx* ctx, uint32_t n, const uint32_t* faces_q, const float* bary, float* out) {
+  return guarded(ctx, [&]() { return impl_inflation_vector_at(ctx, n, faces_q, bary, out); });
+}
+int32_t mnb_cvp_backtrack(mnb_ctx* ctx, const float robot_pos[3], uint32_t robot_face, double step_width, uint32_t max_points,
+                          float* path_pos, uint32_t* path_face, uint32_t* n_points) {
+  return guarded(ctx, [&]() { return impl_cvp_backtrack(ctx, robot_pos, robot_face, step_width, max_points, path_pos, path_face, n_points); });
+}
+int32_t mnb_update_vertex_costs(mnb_ctx* ctx, uint32_t n_changed, const uint32_t* changed, const float* costs,
+                                int32_t costs_indexed_by_vertex, float default_value, double edge_cost_factor) {
+  return guarded(ctx, [&]() { return impl_update_vertex_costs(ctx, n_changed, changed, costs, costs_indexed_by_vertex, default_value, edge_cost_factor); });
+}
+int32_t mnb_max_combination_update(mnb_ctx* ctx, uint32_t n_layers, const float* const* layer_costs, const float* defaults,
+                                   const uint8_t* const* layer_lethal, uint32_t n_changed, const uint32_t* changed,
+                                   float* io_costs, uint8_t* io_lethal) {
+  return guarded(ctx, [&]() { return impl_max_combination_update(ctx, n_layers, layer_costs, defaults, layer_lethal, n_changed, changed, io_costs, io_lethal); });
+}
+int32_t mnb_avg_combination_update(mnb_ctx* ctx, uint32_t n_layers, const float* const* layer_costs, const float* defaults,
+                                   const float* weights, const uint8_t* const* layer_lethal, uint32_t n_changed,
+                                   const uint32_t* changed, float* io_costs, uint8_t* io_lethal) {
+  return guarded(ctx, [&]() { return impl_avg_combination_update(ctx, n_layers, layer_costs, defaults, weights, layer_lethal, n_changed, changed, io_costs, io_lethal); });
 }
 
 }  // extern "C"

@@ -252,8 +252,8 @@ struct CvpEllProblemT : CvpProblem {
     int fb;
     if (fabs(t1a) > 1) fb = 1;
     else if (fabs(t2a) > 1) fb = 2;
-    else if (fabs(t0a) <= 1 && t1a > t0a && t2a > t0a) { X = u3tmp; return; }   // |t0a| > 1: acos(t0a) is NaN in the reference
-    else fb = (t1a > t2a) ? 1 : 2;
+    else if (fabs(t0a) <= 1 && acos_less(t1a, t0a) && acos_less(t2a, t0a)) { X = u3tmp; return; }   // |t0a| > 1: acos(t0a) is NaN in the reference
+    else fb = acos_less(t1a, t2a) ? 1 : 2;
     X = (fb == 1) ? (u1 + b) : (u2 + a);
   }
 
@@ -302,8 +302,8 @@ struct CvpEllProblemT : CvpProblem {
     int fb;
     if (fabs(t1a) > 1) fb = 1;
     else if (fabs(t2a) > 1) fb = 2;
-    else if (fabs(g.t0a) <= 1 && t1a > g.t0a && t2a > g.t0a) { X = u3tmp; return; }   // |t0a| > 1: acos(t0a) is NaN in the reference
-    else fb = (t1a > t2a) ? 1 : 2;
+    else if (fabs(g.t0a) <= 1 && acos_less(t1a, g.t0a) && acos_less(t2a, g.t0a)) { X = u3tmp; return; }   // |t0a| > 1: acos(t0a) is NaN in the reference
+    else fb = acos_less(t1a, t2a) ? 1 : 2;
     X = (fb == 1) ? (u1 + b) : (u2 + a);
   }
 

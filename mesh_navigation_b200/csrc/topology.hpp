@@ -75,10 +75,14 @@ struct HostTopology {
     std::vector<uint32_t> edge_first_face;
     if (edges_in) {
       E = E_in;
+      for (size_t i = 0; i < 2 * (size_t)E; ++i)
+        if (edges_in[i] >= V) throw std::runtime_error("edge endpoint out of range");
       edges.assign(edges_in, edges_in + 2 * (size_t)E);
       std::vector<uint64_t> ck(E); std::vector<uint32_t> cid(E);
       for (uint32_t e = 0; e < E; ++e) { ck[e] = ekey(edges[2 * (size_t)e], edges[2 * (size_t)e + 1]); cid[e] = e; }
       radix_sort_pairs(ck, cid);
+      for (uint32_t e = 1; e < E; ++e)
+        if (ck[e] == ck[e - 1]) throw std::runtime_error("duplicate edge in the caller's edge list");
       edge_face_cnt.assign(E, 0); edge_first_face.assign(E, 0xffffffffu);
       size_t c = 0;
       for (size_t i = 0; i < H; ++i) {

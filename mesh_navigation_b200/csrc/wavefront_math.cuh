@@ -34,10 +34,17 @@ struct CvpResult {
 //
 // ANGLES = true : literal restatement, three acos calls (cvp:456-458), fills r.direction.
 // ANGLES = false: the wavefront hot loop.  theta_i = acos(t_i) is strictly decreasing, so the
-//   reference's comparisons  theta1 < theta0, theta2 < theta0, theta1 < theta2  are evaluated as
-//   t1a > t0a, t2a > t0a, t1a > t2a  without calling acos (the decisions can differ only when two
-//   cosines are closer than one rounding of acos, ~1e-16 relative).  r.direction is NOT filled; the
-//   caller re-evaluates the winning face once with ANGLES = true when it stores the result.
+//   reference's comparisons  theta1 < theta0, theta2 < theta0, theta1 < theta2  are evaluated on the
+//   cosines (acos_less below) -- except where the two cosines are so close that their ROUNDED angles
+//   may coincide: |d acos| >= |dx|, and angles in (0, pi] are spaced up to 4.4e-16 apart, so cosines
+//   more than that apart have distinct, ordered angles; closer ones (a right angle at v3 puts t0a at
+//   ~0, where cosines are spaced 1e-300 apart but all map to pi/2) take the literal acos comparison.
+//   r.direction is NOT filled; the caller re-evaluates the winning face once with ANGLES = true when
+//   it stores the result.
+MNB_HD bool acos_less(double x, double y) {          // acos(x) < acos(y) as the reference's doubles decide it; |x|, |y| <= 1 or NaN
+  if (fabs(x - y) > 1e-15) return x > y;
+  return acos(x) < acos(y);
+}
 template <bool ANGLES>
 MNB_HD bool cvp_update_t(double u1, double u2, double u3, double a, double b, double c, CvpResult& r) {
   const double c_sq = c * c, b_sq = b * b, a_sq = a * a;
@@ -75,13 +82,13 @@ MNB_HD bool cvp_update_t(double u1, double u2, double u3, double a, double b, do
     // '>' on NaN is false as well, so the same branch (u2 + a) is taken.  The reference guards
     // |t1a|, |t2a| <= 1 but NOT t0a: with cost-weighted (non-geometric) edge weights |t0a| can exceed
     // 1, acos(t0a) is NaN and both comparisons against theta0 are false.
-    if (fabs(t0a) <= 1 && t1a > t0a && t2a > t0a) {
+    if (fabs(t0a) <= 1 && acos_less(t1a, t0a) && acos_less(t2a, t0a)) {
       r.value = (float)u3tmp;
-      r.pred_sel = (t1a > t2a) ? 1 : 2;
+      r.pred_sel = acos_less(t1a, t2a) ? 1 : 2;
       r.direction = 0.0f;
       return true;
     }
-    edge_fallback = (t1a > t2a) ? 1 : 2;
+    edge_fallback = acos_less(t1a, t2a) ? 1 : 2;
   }
   u3tmp = (edge_fallback == 1) ? (u1 + b) : (u2 + a);
   if (!(u3tmp < u3)) return false;

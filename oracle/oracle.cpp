@@ -681,6 +681,10 @@ void orc_inflation(void* h, const float* edge_distances, const uint8_t* invalid,
 //                    marked seen, and if |p_n - p_v| < radius it is visited and pushed; v itself is not visited
 // ---------------------------------------------------------------------------
 }  // extern "C"
+// acos of a float, evaluated in double and rounded once.  The reference (roughness via lvr2, steepness_layer.cpp:165) calls
+// its libm's float overload, whose last bit differs between libm versions; lethal sets are threshold tests on these
+// values, so the oracle and the CUDA kernels both use the correctly rounded value (see kernels_layers.cuh, acos_f).
+static inline float acosF(float x) { return (float)std::acos((double)x); }
 static inline void vsub(const float* a, const float* b, float* o) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; }
 
 extern "C" void orc_normals(void* h, float* face_normals /*3F*/, float* vertex_normals /*3V*/) {
@@ -762,11 +766,11 @@ extern "C" void orc_layers(void* h, const OrcLayerParams* P, const float* vertex
       const float* nn = &vertex_normals[3 * (size_t)n];
       float dot = nv[0] * nn[0] + nv[1] * nn[1] + nv[2] * nn[2];
       dot = std::min(1.0f, std::max(-1.0f, dot));
-      rsum = rsum + std::acos(dot); rcnt++;
+      rsum = rsum + acosF(dot); rcnt++;
     });
     const float ro = rcnt ? rsum / (float)rcnt : 0.0f;
     // steepness (steepness_layer.cpp:165)
-    const float st = std::acos(nv[2]);
+    const float st = acosF(nv[2]);
     // ridge (ridge_layer.cpp:155-184)
     float value = 0.0f; int num = 0;
     const float ref[3] = {pv[0] + nv[0], pv[1] + nv[1], pv[2] + nv[2]};

@@ -266,16 +266,13 @@ def test_geometric_layers_fused(api, oracle_mod):
     got = mm.computeLayers()
     for name in ("height_diff", "ridge", "clearance", "border"):      # no transcendental: bit-identical
         assert (got[name].view(np.uint32) == ref[name].view(np.uint32)).all(), name
-    for name in ("roughness", "steepness", "combined"):               # acosf: CUDA vs glibc differ by <= 2 ulp
-        assert np.allclose(got[name], ref[name], rtol=LAYER_RTOL, atol=1e-6), name
-    # lethal sets identical except where a cost sits within float noise of its threshold
-    thr = {2: 0.3, 4: 0.3}
-    diff = got["lethal_mask"] != ref["lethal_mask"]
-    for v in np.where(diff)[0]:
-        bits = int(got["lethal_mask"][v]) ^ int(ref["lethal_mask"][v])
-        assert bits in thr or bits == 6
-        name = {2: "roughness", 4: "steepness"}.get(bits, "steepness")
-        assert abs(float(ref[name][v]) - 0.3) < 1e-5
+    # acos is evaluated in double and rounded once on both sides (kernels_layers.cuh acos_f / oracle acosF): the values agree to
+    # the last bit except where the two double-precision acos implementations differ in their last bit AND that straddles a
+    # float rounding boundary (~1e-8 of the calls); the roughness sum may then differ by one ulp
+    for name in ("roughness", "steepness", "combined"):
+        assert np.allclose(got[name], ref[name], rtol=2e-7, atol=0), name
+        assert (got[name].view(np.uint32) != ref[name].view(np.uint32)).mean() < 1e-4, name
+    assert (got["lethal_mask"] == ref["lethal_mask"]).all()             # lethal sets identical
     assert (ref["lethal_mask"] != 0).sum() > 100
     # non-default radii (three separate walks) and a clearance input
     P = oracle_mod.LayerParams.defaults(); P.height_diff_radius = 0.25; P.ridge_radius = 0.4; P.roughness_radius = 0.2
@@ -298,7 +295,7 @@ def test_config3_layer_stack_chain(api, oracle_mod):
     ref_l = om.layers(); got_l = mm.computeLayers()
     lethal_ref = np.union1d(np.where(ref_l["lethal_mask"] != 0)[0], disc_lethals(pos, 15, 0.3)).astype(np.uint32)
     lethal_got = np.union1d(np.where(got_l["lethal_mask"] != 0)[0], disc_lethals(pos, 15, 0.3)).astype(np.uint32)
-    assert np.setxor1d(lethal_ref, lethal_got).size <= 2
+    assert np.array_equal(lethal_ref, lethal_got)                       # lethal sets identical
     ref_i = om.inflation(ed, lethal_ref); got_i = api.InflationLayer(mm).waveCostInflation(lethal_ref)
     check_inflation(got_i, ref_i, 0.4)
     vcost = np.where(np.isnan(ref_i["cost"]), 0.0, ref_i["cost"]).astype(np.float32)   # InflationLayer default value 0
@@ -383,8 +380,15 @@ def test_disconnected_and_tiny_meshes(api, oracle_mod):
     got = api.CVPMeshPlanner(mm).waveFrontPropagation(0, np.array([0.1, 0.1, 0.0], np.float32))
     ref = om.cvp(ed, np.zeros(3, np.float32), 0, np.array([0.1, 0.1, 0.0], np.float32))
     assert (got["dist"] == ref["dist"]).all()
+    # the reference's own triangle (inflation_layer_test.cpp:7-23): its known answer (d = 0, 0.5 -> 0.5) pins the ORACLE's
+    # waveFrontUpdate (tests/test_oracle_golden.py); a wave needs two fixed vertices, so here both corners are lethal and the
+    # kernel must reproduce the oracle's wave bit for bit
     got = api.InflationLayer(mm, 0.5, 1.5, 1.0, 0.9, 1.0).waveCostInflation(np.array([0, 1], np.uint32))
-    assert got["dist"][2] > 0 and np.isfinite(got["dist"][2])          # two lethal corners reach the third
+    ref = om.inflation(ed, np.array([0, 1], np.uint32), inscribed_radius=0.5, inflation_radius=1.5, lethal_value=1.0, inscribed_value=0.9,
+                       cost_scaling_factor=1.0)
+    assert got["dist"][:2].tolist() == [0.0, 0.0] and 0.5 <= got["dist"][2] < 0.7
+    assert (got["dist"].view(np.uint32) == ref["dist"].view(np.uint32)).all()
+    assert (got["cost"].view(np.uint32) == ref["cost"].view(np.uint32)).all()
     mm.close()
 
 
@@ -394,10 +398,15 @@ def test_cancel_returns_canceled(api, oracle_mod):
     pos, faces, om, mm, ed, vc, w = setup(api, oracle_mod, 700, True)
     mm.set_tuning(0.02, 1, 0)          # tiny band + one CTA: a deliberately slow plan (tens of ms)
     v, f, sp = centre_seed(pos, faces)
+    t0 = time.perf_counter(); full = api.CVPMeshPlanner(mm).waveFrontPropagation(f, sp); t_full = time.perf_counter() - t0
+    assert full["outcome"] == 0 and t_full > 0.02, "the uncancelled plan must take long enough for the cancel to land inside it"
     outcomes = []
-    t = threading.Thread(target=lambda: outcomes.append(api.CVPMeshPlanner(mm).waveFrontPropagation(f, sp)["outcome"]))
-    t.start(); time.sleep(0.004); mm.cancel(); t.join()
-    assert outcomes[0] in (51, 0)      # canceled unless the plan had already finished
+    def run():
+        t1 = time.perf_counter(); o = api.CVPMeshPlanner(mm).waveFrontPropagation(f, sp)["outcome"]; outcomes.append((o, time.perf_counter() - t1))
+    t = threading.Thread(target=run)
+    t.start(); time.sleep(0.25 * t_full); mm.cancel(); t.join()
+    assert outcomes[0][0] == 51, outcomes                    # CANCELED: the request took effect ...
+    assert outcomes[0][1] < 0.85 * t_full, (outcomes, t_full)  # ... and cut the plan short
     mm.set_tuning(0.3, -1, 0)
     assert api.CVPMeshPlanner(mm).waveFrontPropagation(f, sp)["outcome"] == 0     # the flag is reset per plan (cvp:679)
     mm.close()

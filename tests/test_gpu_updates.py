@@ -491,3 +491,31 @@ def test_batch_engine_on_the_hard_cases(api, oracle_mod, name):
         for i in range(len(sfs)):
             assert (got["dist"][i].view(np.uint32) == refs[i].view(np.uint32)).all(), (cluster, delta, i)
     mm.close()
+
+
+def test_abi_argument_validation_and_trivial_dijkstra(api, oracle_mod):
+    """advisor findings (round 1): caller-supplied edge lists are validated (range, duplicates) like faces; a failed
+    mnb_set_mesh leaves an empty context; mnb_dijkstra with start == goal (dijkstra_mesh_planner.cpp:252-255) returns the
+    cleared maps instead of uninitialised buffers"""
+    import ctypes as C
+    pos, faces = mesh_case(12, False)
+    om = oracle_mod.OracleMesh(pos, faces)
+    mm = api.MeshMap(pos, faces)
+    L, ctx = mm.L, mm._ctx
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    edges = np.ascontiguousarray(om.edges, np.uint32)
+    bad = edges.copy(); bad[3, 1] = om.V + 5
+    assert L.mnb_set_mesh(ctx, om.V, om.F, p(pos), p(faces), p(bad), bad.shape[0]) == -1       # MNB_E_ARG: endpoint out of range
+    assert L.mnb_num_vertices(ctx) == 0                                                          # nothing half-built
+    dup = edges.copy(); dup[5] = dup[4]
+    assert L.mnb_set_mesh(ctx, om.V, om.F, p(pos), p(faces), p(dup), dup.shape[0]) == -1
+    assert L.mnb_set_mesh(ctx, om.V, om.F, p(pos), p(faces), p(edges), edges.shape[0]) == 0
+    assert L.mnb_num_vertices(ctx) == om.V
+    mm.close()
+    mm = api.MeshMap(pos, faces)
+    mm.setCosts(np.zeros(om.V, np.float32), om.edge_distances())
+    got = api.DijkstraMeshPlanner(mm).dijkstra(17, 17)
+    assert got["outcome"] == 0
+    exp = np.full(om.V, np.inf, np.float32); exp[17] = 0.0
+    assert (got["dist"] == exp).all() and (got["pred"] == np.arange(om.V)).all()
+    mm.close()
