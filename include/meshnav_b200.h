@@ -244,6 +244,33 @@ int32_t mnb_get_stats(mnb_ctx* ctx, mnb_stats* out);
 /* tuning knobs: band width delta (metres) and CTAs per wavefront cluster (1,2,4,8,16) */
 int32_t mnb_set_tuning(mnb_ctx* ctx, float band_delta, int32_t cluster_size, int32_t threads_per_cta);
 
+/* ---- multi-GPU: one host process, N devices (north star: "batched multi-goal queries shard one goal per
+ * GPU ... with NCCL over NVLink only to gather the resulting potential arrays") ----------------------------------------
+ * A group owns one mnb_ctx per device (mnb_group_ctx: use it for everything that is per device -- layers, single plans,
+ * tuning) and the NCCL communicators of the gather.  NCCL is bound at run time (libnccl.so.2); a group of one device
+ * never touches it.  Reference counterpart: none -- the reference plans one query per MBF action on one CPU thread
+ * (mbf_mesh_nav/src/mesh_planner_execution.cpp:55-66); this is the batched form of CVPMeshPlanner::waveFrontPropagation
+ * (cvp_mesh_planner.cpp:651-886) behind mnb_cvp_batch, sharded. */
+typedef struct mnb_group mnb_group;
+int32_t mnb_group_create(int32_t n_devices, const int32_t* devices /* CUDA ordinals */, mnb_group** out_group);
+void mnb_group_destroy(mnb_group* group);
+int32_t mnb_group_size(mnb_group* group);
+mnb_ctx* mnb_group_ctx(mnb_group* group, int32_t rank);
+const char* mnb_group_last_error(mnb_group* group);
+/* replicate the map / the per-plan costs on every device (HOST pointers, as mnb_set_mesh / mnb_set_costs) */
+int32_t mnb_group_set_mesh(mnb_group* group, uint32_t V, uint32_t F, const float* pos, const uint32_t* faces,
+                           const uint32_t* edges, uint32_t E);
+int32_t mnb_group_set_costs(mnb_group* group, const float* vertex_costs, const float* edge_weights, const uint8_t* invalid);
+/* n full-field plans, goal k on rank k mod N, all devices concurrently; with gather != 0 one in-place ncclAllGather leaves
+ * every field on every device.  Result on each device: float[N][pad][V], pad = ceil(n / N), the field of goal k is row
+ * mnb_group_row(group, k); the buffers belong to the group and stay valid until its next sharded call.  seed arrays: HOST.
+ * Returns the MBF code / MNB_E_* of the first rank that failed. */
+int32_t mnb_cvp_batch_sharded(mnb_group* group, uint32_t n, const uint32_t* seed_faces, const float* seed_pos /* 3n */,
+                              double cost_limit, int32_t gather);
+uint32_t mnb_group_row(mnb_group* group, uint32_t goal);
+float* mnb_group_fields(mnb_group* group, int32_t rank /* device pointer on that rank's device */);
+int32_t mnb_group_read_fields(mnb_group* group, int32_t rank, uint32_t first_goal, uint32_t count, float* out_host /* count*V */);
+
 #ifdef __cplusplus
 }
 #endif

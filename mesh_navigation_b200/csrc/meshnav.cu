@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <functional>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -1180,3 +1181,5 @@ int32_t mnb_avg_combination_update(mnb_ctx* ctx, uint32_t n_layers, const float*
 }
 
 }  // extern "C"
+
+#include "group.cuh"
