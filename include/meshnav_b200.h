@@ -124,7 +124,7 @@ typedef struct mnb_inflation_params {
 int32_t mnb_inflate(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, const uint8_t* invalid /* V or NULL */,
                     const mnb_inflation_params* params, float* out_dist, float* out_cost);
 
-/* ---- geometric cost layers + MaxCombinationLayer (mesh_layers/src/*_layer.cpp) -------------------
+/* ---- geometric cost layers + MaxCombinationLayer (mesh_layers/src/<name>_layer.cpp) -------------------
  * HeightDiffLayer::computeLayer (height_diff_layer.cpp:103-110), RoughnessLayer (roughness_layer.cpp:91-147),
  * SteepnessLayer (steepness_layer.cpp:100-170), RidgeLayer (ridge_layer.cpp:101-187), ClearanceLayer cost
  * mapping (clearance_layer.cpp:67-99, on a caller-provided clearance array; NULL = +inf, no ray hits),
@@ -159,8 +159,9 @@ int32_t mnb_locate(mnb_ctx* ctx, uint32_t n, const float* points /* 3n */, uint3
  *   out[v] = normalize(p[pred[v]] - p[v]).
  * CVPMeshPlanner::computeVectorMap (cvp_mesh_planner.cpp:204-239): the vector is additionally rotated about the vertex
  *   normal by direction[v]; vertices without a cutting face are skipped.
- * out_vec: 3V floats, NaN = "no entry in the sparse vector map" (pred[v] == v or no cutting face). */
-int32_t mnb_vector_map(mnb_ctx* ctx, const uint32_t* pred /* V */, const float* direction /* V or NULL */,
+ * out_vec: 3V floats, NaN = "no entry in the sparse vector map" (pred[v] == v or no cutting face).
+ * pred == NULL: the field of the LAST successful mnb_cvp on this context, from its device-resident result (nothing is uploaded). */
+int32_t mnb_vector_map(mnb_ctx* ctx, const uint32_t* pred /* V or NULL */, const float* direction /* V or NULL */,
                        const int32_t* cutting_face /* V or NULL */, float* out_vec /* 3V */);
 
 /* ---- vector-field back-tracking -------------------------------------------------------------------

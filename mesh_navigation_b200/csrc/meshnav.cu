@@ -783,13 +783,17 @@ static int32_t impl_compute_layers(mnb_ctx* ctx, const mnb_layer_params* params,
 }
 
 static int32_t impl_vector_map(mnb_ctx* ctx, const uint32_t* pred, const float* direction, const int32_t* cutting_face, float* out_vec) {
-  if (!ctx || !ctx->V || !pred || !out_vec) return MNB_E_ARG;
+  if (!ctx || !ctx->V || !out_vec) return MNB_E_ARG;
+  if (!pred && !ctx->last_valid) { ctx->err = "mnb_vector_map(pred = NULL) needs a successful mnb_cvp on this context first"; return MNB_E_STATE; }
   CK(cudaSetDevice(ctx->device));
   const size_t V = ctx->V;
   const bool dev = ctx->ptr_mode == MNB_PTR_DEVICE;
   const uint32_t* d_pred = pred; const float* d_dir = direction; const int32_t* d_cut = cutting_face; float* d_out = out_vec;
   float* tmp_out = nullptr; uint32_t* tmp_pred = nullptr; float* tmp_dir = nullptr; int32_t* tmp_cut = nullptr;
-  if (!dev) {
+  if (!pred) {            // the device-resident result of the last CVP plan (nothing is uploaded)
+    d_pred = ctx->last_pred; d_dir = ctx->last_dir; d_cut = ctx->last_cut;
+    if (!dev) { CK(dalloc(&tmp_out, 3 * V)); d_out = tmp_out; }
+  } else if (!dev) {
     CK(dalloc(&tmp_out, 3 * V)); CK(dalloc(&tmp_pred, V));
     CK(cudaMemcpyAsync(tmp_pred, pred, sizeof(uint32_t) * V, cudaMemcpyHostToDevice, ctx->stream));
     d_pred = tmp_pred; d_out = tmp_out;
