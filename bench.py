@@ -481,36 +481,60 @@ def main():
             return out
 
         def leg_dynamic_update():
-            """one dynamic-obstacle cycle (SURVEY 3.4) on the 5M map: the 1000 discs move; InflationLayer::onInputChanged,
-            MaxCombinationLayer::onInputChanged on the update set, MeshMap::layerChanged (incremental: only the table
-            entries of the incident edges are patched) -- next to a full re-install of the same arrays"""
+            """one dynamic-obstacle cycle on the 5M map with every array resident on the device (MNB_PTR_DEVICE,
+            torch tensors): the 1000 discs move; InflationLayer::onInputChanged -> MaxCombinationLayer::onInputChanged on the
+            update set -> MeshMap::layerChanged (incremental: only the table entries of the incident edges are patched), wall
+            times around torch.cuda.synchronize(); the resulting tables are compared with a full re-install"""
+            import ctypes as C
             infl = InflationLayer(mm)
             static = shared["combined"]
             base = np.where(shared["lethal_mask"] != 0)[0]
-            le0 = np.union1d(base, synth.disc_lethals_grid(pos, n, n, 1000, 0.3, seed=7)).astype(np.uint32)
-            le1 = np.union1d(base, synth.disc_lethals_grid(pos, n, n, 1000, 0.3, seed=8)).astype(np.uint32)
+            n_discs = max(2, int(round(1000 * (n / 2240.0) ** 2)))
+            le0 = np.union1d(base, synth.disc_lethals_grid(pos, n, n, n_discs, 0.3, seed=7)).astype(np.uint32)
+            le1 = np.union1d(base, synth.disc_lethals_grid(pos, n, n, n_discs, 0.3, seed=8)).astype(np.uint32)
             r0 = infl.onInputChanged(le0)
-            final = np.maximum(static, np.nan_to_num(r0["cost"], nan=0.0)).astype(np.float32)
-            mm.computeEdgeWeights(final, 1.0, want_output=False)
-            t0 = time.perf_counter(); r1 = infl.onInputChanged(le1); t_infl = time.perf_counter() - t0
-            infl_ms = r1["kernel_ms"]
-            t0 = time.perf_counter(); field = infl.vectorMap(); t_vec = time.perf_counter() - t0
-            ch = r1["changed"]
-            t0 = time.perf_counter()
-            mm.maxCombinationUpdate([static, r1["cost"]], [0.0, 0.0], None, ch, final, None)
-            t_comb = time.perf_counter() - t0
-            vals = final[ch]
-            t0 = time.perf_counter(); mm.layerChanged(ch, vals, 1.0); t_inc = time.perf_counter() - t0
-            inc_ms = mm.stats()["kernel_ms"]
+            final0 = np.maximum(static, np.nan_to_num(r0["cost"], nan=0.0)).astype(np.float32)
+            mm.computeEdgeWeights(final0, 1.0, want_output=False)
+            d_static = torch.from_numpy(static).to(dev); d_final = torch.from_numpy(final0).to(dev)
+            d_le = [torch.from_numpy(x.astype(np.int64)).to(dev).to(torch.int32) for x in (le1, le0)]
+            d_dist = torch.empty(V, dtype=torch.float32, device=dev); d_cost = torch.empty(V, dtype=torch.float32, device=dev)
+            d_changed = torch.empty(V, dtype=torch.int32, device=dev); d_vec = torch.empty((V, 3), dtype=torch.float32, device=dev)
+            p = lambda t: C.c_void_p(t.data_ptr())
+            nch = C.c_uint32(0); defaults = np.zeros(2, np.float32); Lc = mm.L; cx = mm._ctx
+            mm.use_device_pointers(True)
+
+            def cycle(k, with_field):
+                t = {}
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                assert Lc.mnb_inflation_update(cx, p(d_le[k]), int(d_le[k].numel()), None, C.byref(infl.config), p(d_dist), p(d_cost), p(d_changed), C.byref(nch)) == 0
+                torch.cuda.synchronize(); t1 = time.perf_counter(); t["inflation_update_ms"] = 1e3 * (t1 - t0); t["inflation_kernel_ms"] = mm.stats()["kernel_ms"]
+                lc = (C.c_void_p * 2)(d_static.data_ptr(), d_cost.data_ptr())
+                assert Lc.mnb_max_combination_update(cx, 2, lc, defaults.ctypes.data_as(C.c_void_p), None, nch.value, p(d_changed), p(d_final), None) == 0
+                torch.cuda.synchronize(); t2 = time.perf_counter(); t["max_combination_ms"] = 1e3 * (t2 - t1)
+                assert Lc.mnb_update_vertex_costs(cx, nch.value, p(d_changed), p(d_final), 1, 0.0, 1.0) == 0
+                torch.cuda.synchronize(); t3 = time.perf_counter(); t["layer_changed_ms"] = 1e3 * (t3 - t2)
+                t["total_wall_ms"] = 1e3 * (t3 - t0)
+                if with_field:
+                    assert Lc.mnb_inflation_vector_map(cx, p(d_vec)) == 0
+                    torch.cuda.synchronize(); t["repulsive_vector_field_ms"] = 1e3 * (time.perf_counter() - t3)
+                return t
+
+            try:
+                for rep in range(2):
+                    cycle(0, False); cycle(1, False)
+                ta = cycle(0, True)
+            finally:
+                mm.use_device_pointers(False)
             gvc, gw = mm.costs()
-            t0 = time.perf_counter(); full_w = mm.computeEdgeWeights(final, 1.0); t_full = time.perf_counter() - t0
-            same = bool((gw.view(np.uint32) == full_w.view(np.uint32)).all() and (gvc.view(np.uint32) == final.view(np.uint32)).all())
+            final1 = d_final.cpu().numpy()
+            full_w = mm.computeEdgeWeights(final1, 1.0)
+            ref1 = np.maximum(static, np.nan_to_num(infl.onInputChanged(le1)["cost"], nan=0.0)).astype(np.float32)
+            same = bool((gw.view(np.uint32) == full_w.view(np.uint32)).all() and (gvc.view(np.uint32) == final1.view(np.uint32)).all()
+                        and (final1.view(np.uint32) == ref1.view(np.uint32)).all())
             mm.setCosts(vc, ed)
-            return {"changed_vertices": int(ch.size), "lethal_vertices": int(le1.size), "inflation_update_wall_ms": 1e3 * t_infl,
-                    "inflation_kernel_ms": infl_ms, "vector_field_wall_ms": 1e3 * t_vec, "vectors": int((np.abs(field).sum(1) > 0).sum()),
-                    "max_combination_wall_ms_host_maps": 1e3 * t_comb,
-                    "layer_changed_incremental_wall_ms": 1e3 * t_inc, "layer_changed_incremental_kernel_ms": inc_ms,
-                    "full_reinstall_wall_ms": 1e3 * t_full, "incremental_equals_full": same}
+            ta.update({"changed_vertices": int(nch.value), "lethal_vertices": int(le1.size), "incremental_equals_full": same,
+                       "arrays": "device-resident (MNB_PTR_DEVICE); the update set and its size are produced on the device, only the count is read back"})
+            return ta
 
         def leg_make_plan():
             # a whole makePlan through the host API: localisation of both poses, wavefront until the robot face is fixed,
@@ -532,7 +556,7 @@ def main():
             compared bit for bit.  Run last: nothing above depends on them."""
             import ctypes as C
             out = {}
-            for f in ("mnb_debug_set_skip_clean", "mnb_debug_set_layers_smem", "mnb_debug_set_infl_skip"):
+            for f in ("mnb_debug_set_layers_smem", "mnb_debug_set_infl_skip"):
                 getattr(mm.L, f).argtypes = [C.c_void_p, C.c_int32]
             # the inflation wave's clean-candidate skip is ON by default: time it against the all-candidates-every-round loop
             le = shared.get("lethals")
@@ -546,30 +570,17 @@ def main():
                 out["inflation_clean_candidate_skip"] = {
                     "kernel_ms": res[1][0], "without_skip_kernel_ms": res[0][0], "recomputes": int(res[1][1]), "without_skip_recomputes": int(res[0][1]),
                     "identical": bool((res[1][2].view(np.uint32) == res[0][2].view(np.uint32)).all())}
-            mm.setCosts(vc, ed)
-            base = planner.waveFrontPropagation(sf, sp)
-            mm.L.mnb_debug_set_skip_clean(mm._ctx, 1)
-            try:
-                best = None
-                for rep in range(3):
-                    g = planner.waveFrontPropagation(sf, sp)
-                    best = g["kernel_ms"] if best is None else min(best, g["kernel_ms"])
-                out["cvp_clean_candidate_skip"] = {
-                    "kernel_ms": best, "default_kernel_ms": base["kernel_ms"], "recomputes_per_vertex": g["recomputes"] / V,
-                    "default_recomputes_per_vertex": base["recomputes"] / V, "skipped_per_vertex": g["skipped"] / V,
-                    "identical_to_default": bool((g["dist"].view(np.uint32) == base["dist"].view(np.uint32)).all())}
-            finally:
-                mm.L.mnb_debug_set_skip_clean(mm._ctx, 0)
+            mm.L.mnb_debug_set_layers_smem(mm._ctx, 0)        # the thread-local walk of round 1 next to the default (prefetching walk)
             Lb = mm.computeLayers()
-            mm.L.mnb_debug_set_layers_smem(mm._ctx, 1)
+            mm.L.mnb_debug_set_layers_smem(mm._ctx, 2)
             try:
                 for rep in range(2):
                     Ls = mm.computeLayers()
                 same = all(bool((Ls[k].view(np.uint32) == Lb[k].view(np.uint32)).all()) for k in ("height_diff", "roughness", "steepness", "ridge", "combined"))
-                out["layers_shared_memory_packed"] = {"kernel_ms": Ls["kernel_ms"], "default_kernel_ms": Lb["kernel_ms"],
-                                                      "hbm_frac": 837 * V / (Ls["kernel_ms"] * 1e-3) / 1e9 / hbm0, "identical_to_default": same}
+                out["layers_prefetching_walk_vs_round1_walk"] = {"kernel_ms": Ls["kernel_ms"], "round1_walk_kernel_ms": Lb["kernel_ms"],
+                                                      "hbm_frac": 837 * V / (Ls["kernel_ms"] * 1e-3) / 1e9 / hbm0, "identical": same}
             finally:
-                mm.L.mnb_debug_set_layers_smem(mm._ctx, 0)
+                mm.L.mnb_debug_set_layers_smem(mm._ctx, 2)
             return out
 
         leg("dijkstra_full_field", leg_dijkstra)

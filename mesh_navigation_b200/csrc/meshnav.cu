@@ -75,7 +75,7 @@ struct mnb_ctx {
   float delta = 0.3f; int cluster = -1 /* -1: whole-grid cooperative kernel for single plans */; int batch_cluster = 0 /* 0: chosen per call from the goal count */; int threads = 512;
   int grid_blocks_per_sm = 0;
   int infl_skip_clean = 1;     // clean-candidate skip of the inflation wave (MNB_INFL_SKIP=0 turns it off)
-  int layers_smem = 0;         // k_layers with the seen-set / stack in shared memory (MNB_LAYERS_SMEM=1, mnb_debug_set_layers_smem)
+  int layers_smem = 2;         // neighbourhood walk of k_layers: 0 thread-local seen-set, 1 shared-memory seen-set, 2-4 prefetching walk (64 / 128 / 32 threads per CTA); 2 measured fastest on the B200 (6.1 vs 9.6 ms at 5M vertices)
   int skip_clean = 0;          // clean-candidate skip of the CVP kernels (band_engine.cuh): bit-identical on the kernel interpreter,
                                // not yet timed on a B200 -> opt-in (MNB_SKIP_CLEAN=1 / mnb_debug_set_skip_clean)
   int sweeps = -1;             // in-round sweeps of the whole-grid single-plan kernel; -1 = derived from the band width
@@ -466,7 +466,7 @@ static int32_t launch_cvp(mnb_ctx* ctx, const CvpKernelArgs& a, int cs, unsigned
   const unsigned blocks = groups * cs;
   const int threads = MNB_CVP_THREADS;
   switch (cs) {
-    case 1: e = a.skip_clean ? launch_cluster(k_cvp<1, true>, a, 1, blocks, threads, ctx->stream) : launch_cluster(k_cvp<1, false>, a, 1, blocks, threads, ctx->stream); break;
+    case 1: e = launch_cluster(k_cvp<1, false>, a, 1, blocks, threads, ctx->stream); break;
     case 2: e = launch_cluster(k_cvp<2, false>, a, 2, blocks, threads, ctx->stream); break;     // (the skip variant is built for the two
     case 4: e = launch_cluster(k_cvp<4, false>, a, 4, blocks, threads, ctx->stream); break;     //  default configurations only: per-CTA batches
     case 8: e = launch_cluster(k_cvp<8, false>, a, 8, blocks, threads, ctx->stream); break;     //  and the whole-grid single plan)
@@ -553,13 +553,11 @@ static int32_t impl_cvp(mnb_ctx* ctx, uint32_t seed_face, const float seed_pos[3
     a.delta = ctx->grid_delta;
     if (ctx->grid_blocks_per_sm == 0) {
       int nb = 0;
-      if (a.skip_clean) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_cvp_grid<true>, ctx->threads, 0));
-      else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_cvp_grid<false>, ctx->threads, 0));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_cvp_grid<false>, ctx->threads, 0));
       ctx->grid_blocks_per_sm = nb > MNB_GRID_MINBLOCKS ? MNB_GRID_MINBLOCKS : nb;
       if (nb <= 0) { ctx->err = "k_cvp_grid cannot be resident"; return MNB_E_CUDA; }
     }
-    if (a.skip_clean) CK(launch_cooperative(k_cvp_grid<true>, a, (unsigned)(ctx->sm_count * ctx->grid_blocks_per_sm), ctx->threads, ctx->stream));
-    else CK(launch_cooperative(k_cvp_grid<false>, a, (unsigned)(ctx->sm_count * ctx->grid_blocks_per_sm), ctx->threads, ctx->stream));
+    CK(launch_cooperative(k_cvp_grid<false>, a, (unsigned)(ctx->sm_count * ctx->grid_blocks_per_sm), ctx->threads, ctx->stream));
   } else {
     if ((rc = launch_cvp(ctx, a, ctx->cluster, 1)) != MNB_OK) return rc;
   }

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <stdexcept>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -38,20 +39,47 @@ struct HostTopology {
     return a < b ? (((uint64_t)a << 32) | b) : (((uint64_t)b << 32) | a);
   }
 
-  // LSD radix sort of (key, value) pairs by key, 16-bit digits; digits that are constant over the input are skipped
+  // host threads of the builder (the map is built once per MeshMap::readMap; 50M vertices = 300M half-edges)
+  static unsigned workers(size_t n) {
+    if (n < (1u << 20)) return 1;
+    const unsigned hc = std::thread::hardware_concurrency();
+    return hc < 2 ? 1 : (hc > 16 ? 16 : hc);
+  }
+  template <class Fn>
+  static void parallel_for(unsigned T, Fn fn) {            // fn(t) for t in [0, T)
+    if (T <= 1) { fn(0u); return; }
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; ++t) th.emplace_back(fn, t);
+    fn(0u);
+    for (auto& x : th) x.join();
+  }
+
+  // LSD radix sort of (key, value) pairs by key, 16-bit digits; digits that are constant over the input are skipped.
+  // Parallel over contiguous chunks (per-thread histograms, one prefix over (digit, thread)): stable, same result as the
+  // sequential sort whatever the thread count.
   static void radix_sort_pairs(std::vector<uint64_t>& keys, std::vector<uint32_t>& vals) {
     const size_t n = keys.size();
     if (n < 2) return;
     std::vector<uint64_t> k2(n); std::vector<uint32_t> v2(n);
-    std::vector<size_t> cnt(65536);
+    const unsigned T = workers(n);
+    std::vector<std::vector<size_t>> cnt(T, std::vector<size_t>(65536));
+    auto lo = [&](unsigned t) { return n * t / T; };
     for (int pass = 0; pass < 4; ++pass) {
       const int sh = 16 * pass;
-      std::fill(cnt.begin(), cnt.end(), (size_t)0);
-      for (size_t i = 0; i < n; ++i) cnt[(keys[i] >> sh) & 0xffffu]++;
-      if (cnt[(keys[0] >> sh) & 0xffffu] == n) continue;          // all keys share this digit
+      parallel_for(T, [&](unsigned t) {
+        auto& c = cnt[t]; std::fill(c.begin(), c.end(), (size_t)0);
+        for (size_t i = lo(t), e = lo(t + 1); i < e; ++i) c[(keys[i] >> sh) & 0xffffu]++;
+      });
+      size_t first = 0;
+      for (unsigned t = 0; t < T; ++t) first += cnt[t][(keys[0] >> sh) & 0xffffu];
+      if (first == n) continue;                                   // all keys share this digit
       size_t sum = 0;
-      for (size_t d = 0; d < 65536; ++d) { const size_t c = cnt[d]; cnt[d] = sum; sum += c; }
-      for (size_t i = 0; i < n; ++i) { const size_t d = cnt[(keys[i] >> sh) & 0xffffu]++; k2[d] = keys[i]; v2[d] = vals[i]; }
+      for (size_t d = 0; d < 65536; ++d)
+        for (unsigned t = 0; t < T; ++t) { const size_t c = cnt[t][d]; cnt[t][d] = sum; sum += c; }
+      parallel_for(T, [&](unsigned t) {
+        auto& c = cnt[t];
+        for (size_t i = lo(t), e = lo(t + 1); i < e; ++i) { const size_t d = c[(keys[i] >> sh) & 0xffffu]++; k2[d] = keys[i]; v2[d] = vals[i]; }
+      });
       keys.swap(k2); vals.swap(v2);
     }
   }
@@ -65,9 +93,14 @@ struct HostTopology {
     // caller keys).  5 M vertices: ~3x faster than sort + unique + lower_bound per half-edge.
     const size_t H = 3 * (size_t)F;
     std::vector<uint64_t> hk(H); std::vector<uint32_t> hs(H);
-    for (uint32_t f = 0; f < F; ++f) {
-      const uint32_t* v = faces + 3 * (size_t)f;
-      for (int k = 0; k < 3; ++k) { hk[3 * (size_t)f + k] = ekey(v[k], v[(k + 1) % 3]); hs[3 * (size_t)f + k] = 3 * f + (uint32_t)k; }
+    {
+      const unsigned T = workers(H);
+      parallel_for(T, [&](unsigned t) {
+        for (uint32_t f = (uint32_t)((size_t)F * t / T), fe = (uint32_t)((size_t)F * (t + 1) / T); f < fe; ++f) {
+          const uint32_t* v = faces + 3 * (size_t)f;
+          for (int k = 0; k < 3; ++k) { hk[3 * (size_t)f + k] = ekey(v[k], v[(k + 1) % 3]); hs[3 * (size_t)f + k] = 3 * f + (uint32_t)k; }
+        }
+      });
     }
     radix_sort_pairs(hk, hs);
     face_edges.resize(H);
@@ -119,11 +152,15 @@ struct HostTopology {
     vadj_nbr.resize(vadj_ptr[V]); vadj_eid.resize(vadj_ptr[V]);
     {
       std::vector<uint32_t> cur(vadj_ptr.begin(), vadj_ptr.end() - 1);
-      for (uint32_t e = 0; e < E; ++e) {
-        const uint32_t a = edges[2 * (size_t)e], b = edges[2 * (size_t)e + 1];
-        vadj_eid[cur[a]] = e; vadj_nbr[cur[a]++] = b;
-        vadj_eid[cur[b]] = e; vadj_nbr[cur[b]++] = a;
-      }
+      const unsigned T = workers(2 * (size_t)E);
+      parallel_for(T, [&](unsigned t) {                    // vertex ranges again: ascending edge id per vertex is kept
+        const uint32_t vlo = (uint32_t)((size_t)V * t / T), vhi = (uint32_t)((size_t)V * (t + 1) / T);
+        for (uint32_t e = 0; e < E; ++e) {
+          const uint32_t a = edges[2 * (size_t)e], b = edges[2 * (size_t)e + 1];
+          if (a >= vlo && a < vhi) { vadj_eid[cur[a]] = e; vadj_nbr[cur[a]++] = b; }
+          if (b >= vlo && b < vhi) { vadj_eid[cur[b]] = e; vadj_nbr[cur[b]++] = a; }
+        }
+      });
     }
     vcor_ptr.assign((size_t)V + 1, 0);
     for (size_t i = 0; i < 3 * (size_t)F; ++i) vcor_ptr[faces[i] + 1]++;
@@ -132,11 +169,16 @@ struct HostTopology {
     cor_v1.resize(NC); cor_v2.resize(NC); cor_face.resize(NC);
     cor_ec.resize(NC); cor_eb.resize(NC); cor_ea.resize(NC); cor_side.resize(NC);
     {
+      // every thread owns a range of vertices and scans all faces: the records of a vertex stay in ascending face order
       std::vector<uint32_t> cur(vcor_ptr.begin(), vcor_ptr.end() - 1);
+      const unsigned T = workers(3 * (size_t)F);
+      parallel_for(T, [&](unsigned t) {
+      const uint32_t vlo = (uint32_t)((size_t)V * t / T), vhi = (uint32_t)((size_t)V * (t + 1) / T);
       for (uint32_t f = 0; f < F; ++f) {
         const uint32_t* v = faces + 3 * (size_t)f;
         const uint32_t* fe = &face_edges[3 * (size_t)f];
         for (int k = 0; k < 3; ++k) {  // v3 = v[k], v1 = v[k+1], v2 = v[k+2]
+          if (v[k] < vlo || v[k] >= vhi) continue;
           const uint32_t slot = cur[v[k]]++;
           cor_v1[slot] = v[(k + 1) % 3];
           cor_v2[slot] = v[(k + 2) % 3];
@@ -148,6 +190,7 @@ struct HostTopology {
                                      (edge_first_face[cor_ea[slot]] != f ? 4 : 0));
         }
       }
+      });
     }
   }
 };

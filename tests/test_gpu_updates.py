@@ -227,10 +227,8 @@ def test_backtrack_with_repulsive_field(api, oracle_mod):
 
 @pytest.mark.parametrize("n,factor", [(160, 0.0), (200, 2.0)])
 def test_clean_candidate_skip_is_exact(api, oracle_mod, n, factor):
-    """opt-in engine variant (band_engine.cuh, clean-candidate skip): candidates whose sources were not re-labelled since
-    their last evaluation keep their label without a recompute -- same potentials bit for bit, fewer recomputes, for the
-    whole-grid single plan and for the per-CTA batch kernel"""
-    import ctypes as C
+    """the batch round loop (batch_engine.cuh) carries candidates whose inputs cannot have changed over without evaluating
+    them -- same potentials bit for bit as the oracle, about half the evaluations; single plans evaluate everything"""
     O = oracle_mod
     pos, faces = mesh_case(n, True)
     om = O.OracleMesh(pos, faces)
@@ -239,31 +237,19 @@ def test_clean_candidate_skip_is_exact(api, oracle_mod, n, factor):
     vc = (rng.random(om.V) * 0.7).astype(np.float32) if factor else np.zeros(om.V, np.float32)
     w = om.edge_weights(vc, ed, factor)
     v, f, sp = centre_seed(pos, faces, (0.3, 0.4))
-    ref = om.cvp(w, vc, f, sp)
     mm = api.MeshMap(pos, faces)
     mm.setCosts(vc, w)
-    mm.L.mnb_debug_set_skip_clean.argtypes = [C.c_void_p, C.c_int32]
     planner = api.CVPMeshPlanner(mm)
     base = planner.waveFrontPropagation(f, sp)
     assert base["skipped"] == 0
-    mm.L.mnb_debug_set_skip_clean(mm._ctx, 1)
-    got = planner.waveFrontPropagation(f, sp)
-    assert (got["dist"].view(np.uint32) == ref["dist"].view(np.uint32)).all()
-    assert (got["pred"] == ref["pred"]).all() and (got["cutting_face"] == ref["cutting_face"]).all()
-    assert got["skipped"] > 0          # (recompute counts depend on the timing of the in-round sweeps: not compared)
     sfs = np.array([f, f + 2, f + 40], np.uint32); sps = pos[faces[sfs]].mean(1).astype(np.float32)
-    mm.set_tuning(0.0, 1, 0)
-    b = planner.waveFrontPropagationBatch(sfs, sps)
-    assert b["skipped"] > 0
-    for k in range(3):
-        rk = om.cvp(w, vc, int(sfs[k]), sps[k])
-        assert (b["dist"][k].view(np.uint32) == rk["dist"].view(np.uint32)).all(), k
-    # a plan with a goal cutoff recomputes everything (the cutoff is an input of every label)
-    rv, rf, rp = centre_seed(pos, faces, (0.8, 0.75))
-    mm.set_tuning(0.0, -1, 0)
-    cut = planner.waveFrontPropagation(f, sp, rf)
-    refc = om.cvp(w, vc, f, sp, robot_face=rf)
-    assert cut["skipped"] == 0 and (cut["dist"].view(np.uint32) == refc["dist"].view(np.uint32)).all()
+    for cluster in (1, 2):
+        mm.set_tuning(0.0, cluster, 0)
+        b = planner.waveFrontPropagationBatch(sfs, sps)
+        assert b["skipped"] > 0 and b["recomputes"] < 0.75 * 3 * base["recomputes"]
+        for k in range(3):
+            rk = om.cvp(w, vc, int(sfs[k]), sps[k])
+            assert (b["dist"][k].view(np.uint32) == rk["dist"].view(np.uint32)).all(), (cluster, k)
     mm.close()
 
 
