@@ -376,11 +376,19 @@ __device__ __forceinline__ void run_band_rounds_batch(const Args& a, const Batch
             const bool v1_later = tb < ta || (tb == ta && v2 < v1);
             const float T1 = v1_later ? ta : tb;
             const float4 w = __ldg(&a.ell_w[(size_t)c * ELL_W + k]);
+            // the static part of the unfolding (apex of the triangle, cosine at v3) is recomputed from the three weights instead of
+            // being read from the precomputed table: 256 of the 512 bytes a vertex' ELL rows occupy, and the rows -- not the
+            // labels -- are what makes the hot set of a few hundred concurrent wavefronts overflow the L2 (MNB_BATCH_GEO_TABLE=1
+            // at compile time restores the table read)
+            double U, X;
+#ifdef MNB_BATCH_GEO_TABLE
             const double2* gp = reinterpret_cast<const double2*>(a.ell_geo) + 2 * ((size_t)c * ELL_W + k);
             const double2 g01 = __ldg(gp), g23 = __ldg(gp + 1);
             CvpEllProblemT<false>::FaceGeo fg; fg.p = g01.x; fg.hc = g01.y; fg.t0a = g23.x;
-            double U, X;
             CvpEllProblemT<false>::eval_face_geo((double)da, (double)db, (double)w.z, (double)w.y, (double)w.x, fg, U, X);
+#else
+            CvpEllProblemT<false>::eval_face((double)da, (double)db, (double)w.z, (double)w.y, (double)w.x, U, X);
+#endif
             const float Xf = (float)X;
             if (Xf > T1 && U <= X) m = fminf(m, Xf); else tmin_nc = fminf(tmin_nc, T1);
           }

@@ -36,6 +36,18 @@ __global__ void k_edge_weights(const float* __restrict__ cost, const uint32_t* _
   }
 }
 
+// sum and count of the finite edge weights (the scale the band widths follow): out = {sum, count}
+__global__ void k_weight_scale(const float* __restrict__ w, uint32_t E, double* __restrict__ out) {
+  double s = 0.0, n = 0.0;
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+    const float x = w[e];
+    if (x > 0.0f && __float_as_uint(x) < INF_BITS) { s += (double)x; n += 1.0; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); n += __shfl_xor_sync(0xffffffffu, n, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], s); atomicAdd(&out[1], n); }
+}
+
 // per-corner weight records {w(v1,v2), w(v1,c), w(v2,c), 0}
 __global__ void k_gather_corner_w(const uint4* __restrict__ cor_eid, const float* __restrict__ w, size_t NC,
                                   float4* __restrict__ out) {

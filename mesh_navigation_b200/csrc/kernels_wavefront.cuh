@@ -50,7 +50,8 @@ struct CvpKernelArgs {
   unsigned int* next_query;
   const int* cancel_flag;
   uint32_t max_rounds;
-  int sweeps;                   // in-round sweeps of a single plan (0 = off)
+  int sweeps;                   // in-round sweeps of a single plan (0 = off, -1 = from the band width)
+  float hop;                    // ~ one dependency hop in potential units (1.35 x mean edge weight)
   int skip_clean;               // clean-candidate skip (band_engine.cuh), 0 = off
 };
 
@@ -331,9 +332,9 @@ __global__ void __launch_bounds__(512, MNB_GRID_MINBLOCKS) k_cvp_grid(const CvpK
   }
   group_sync<0>(ctl->barrier);
   const float delta = a.delta;      // not clamped to goal_dist_offset: the engine caps settling instead (settle_cap)
-  // in-round sweeps pay off once the band is several dependency hops deep (one hop ~ 0.15 m of potential on these meshes)
+  // in-round sweeps pay off once the band is several dependency hops deep; 12 were measured best on the 5M terrain
   int sweeps = a.sweeps;
-  if (sweeps < 0) sweeps = delta < 0.45f ? 0 : min(15, (int)(delta / 0.16f));
+  if (sweeps < 0) sweeps = delta < 2.8f * a.hop ? 0 : min(12, (int)(delta / a.hop));
   run_band_rounds_sub8<0, true>(prob, ctl, list0, list1, mark, st, delta, gthreads, gtid, has_robot, r0, r1, r2,
                           a.goal_dist_offset, a.cancel_flag, nextafterf(seed_max, __uint_as_float(INF_BITS)), a.max_rounds, sweeps, &sws, V);
   group_sync<0>(ctl->barrier);
@@ -395,7 +396,7 @@ struct DijkstraKernelArgs {
   float* out_dist; uint32_t* out_pred;
   const int* cancel_flag;
   uint32_t max_rounds;
-  const uint4* ell_adj; int sweeps;   // whole-grid kernel only
+  const uint4* ell_adj; int sweeps; float hop;   // whole-grid kernel only
 };
 
 template <int CS>
@@ -469,7 +470,7 @@ __global__ void __launch_bounds__(512, 1) k_dijkstra_grid(const DijkstraKernelAr
   group_sync<0>(ctl->barrier);
   const float delta = a.delta;      // not clamped to goal_dist_offset: the engine caps settling instead (settle_cap)
   int sweeps = a.sweeps;
-  if (sweeps < 0) sweeps = delta < 0.45f ? 0 : min(15, (int)(delta / 0.16f));
+  if (sweeps < 0) sweeps = delta < 2.8f * a.hop ? 0 : min(15, (int)(delta / a.hop));
   run_band_rounds_sub8<0, true>(prob, ctl, list0, list1, mark, st, delta, gthreads, gtid, has_robot, rv, rv, rv,
                                 a.goal_dist_offset, a.cancel_flag, 1e-30f, a.max_rounds, sweeps, &sws, V);
   group_sync<0>(ctl->barrier);

@@ -81,6 +81,11 @@ struct mnb_ctx {
   int sweeps = -1;             // in-round sweeps of the whole-grid single-plan kernel; -1 = derived from the band width
   float grid_delta = 1.8f;     // band width of the whole-grid single-plan kernel (wide band + in-round sweeps)
   float dijkstra_grid_delta = 3.0f;
+  // The band widths above are potentials, i.e. multiples of the edge weights: unless the caller fixed them (mnb_set_tuning
+  // with band_delta > 0) they follow the mean finite edge weight w of the installed weights -- 2.5 w for batches, 20 w for a
+  // single CVP plan, 25 w for a single Dijkstra plan; one dependency hop is ~1.35 w (the in-round sweeps are counted in
+  // hops).  On the 0.1 m bench meshes (w = 0.118) that is 0.3 / 2.4 / 3.0 m, the values the kernels were tuned with.
+  bool delta_explicit = false; float w_mean = 0.0f; double* d_wsum = nullptr;
   mnb_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -102,7 +107,7 @@ static void dfree(T*& p) { if (p) cudaFree(p); p = nullptr; }
 static void free_mesh(mnb_ctx* c) {
   dfree(c->d_pos); dfree(c->d_faces); dfree(c->d_edges); dfree(c->d_cor_ptr); dfree(c->d_cor_idx); dfree(c->d_cor_eid);
   dfree(c->d_cor_w); dfree(c->d_cor_wd); dfree(c->d_ell_idx); dfree(c->d_ell_eid); dfree(c->d_ell_w); dfree(c->d_ell_wd); dfree(c->d_ell_geo); dfree(c->d_adj_ptr); dfree(c->d_adj_nbr); dfree(c->d_adj_eid); dfree(c->d_adj_nw); dfree(c->d_ell_adj);
-  dfree(c->d_edge_dist); dfree(c->d_edge_w); dfree(c->d_cost); dfree(c->d_invalid);
+  dfree(c->d_edge_dist); dfree(c->d_edge_w); dfree(c->d_cost); dfree(c->d_invalid); dfree(c->d_wsum);
   dfree(c->ws.state); dfree(c->ws.ext); dfree(c->ws.pool); dfree(c->ws.skipw); dfree(c->ws.root); dfree(c->ws.last_eval); dfree(c->ws.dirty); dfree(c->ws.excl); dfree(c->ws.chg); dfree(c->ws.ver); dfree(c->ws.mark); dfree(c->ws.list0); dfree(c->ws.list1); dfree(c->ws.ctl);
   c->ws_groups = 0;
   dfree(c->d_out_dist); c->out_dist_cap = 0; dfree(c->d_out_pred); dfree(c->d_out_dir); dfree(c->d_out_cut);
@@ -204,7 +209,7 @@ uint32_t mnb_num_edges(mnb_ctx* ctx) { return ctx ? ctx->E : 0; }
 
 int32_t mnb_set_tuning(mnb_ctx* ctx, float band_delta, int32_t cluster_size, int32_t threads_per_cta) {
   if (!ctx) return MNB_E_ARG;
-  if (band_delta > 0) { ctx->delta = band_delta; ctx->grid_delta = band_delta; ctx->dijkstra_grid_delta = band_delta; }
+  if (band_delta > 0) { ctx->delta = band_delta; ctx->grid_delta = band_delta; ctx->dijkstra_grid_delta = band_delta; ctx->delta_explicit = true; }
   if (cluster_size == 1 || cluster_size == 2 || cluster_size == 4 || cluster_size == 8 || cluster_size == 16) {
     ctx->cluster = cluster_size;
     ctx->batch_cluster = cluster_size > 8 ? 8 : cluster_size;
@@ -312,6 +317,16 @@ static int32_t install_weights(mnb_ctx* ctx) {
   MNB_LAUNCH(k_gather_adj_w, (unsigned)((ctx->NA + 255) / 256), 256, 0, ctx->stream, ctx->d_adj_nbr, ctx->d_adj_eid, ctx->d_edge_w, ctx->NA, ctx->d_adj_nw);
   MNB_LAUNCH(k_build_ell_adj, (unsigned)(((size_t)ctx->V * ELL_W + 255) / 256), 256, 0, ctx->stream, ctx->d_adj_ptr, ctx->d_adj_nw, ctx->V, ctx->d_ell_adj);
   CK(cudaGetLastError());
+  // scale of the potentials: mean finite edge weight (see mnb_ctx::delta_explicit)
+  if (!ctx->d_wsum) CK(dalloc(&ctx->d_wsum, 2));
+  CK(cudaMemsetAsync(ctx->d_wsum, 0, 2 * sizeof(double), ctx->stream));
+  MNB_LAUNCH(k_weight_scale, 296, 256, 0, ctx->stream, (const float*)ctx->d_edge_w, ctx->E, ctx->d_wsum);
+  CK(cudaGetLastError());
+  double hs[2] = {0.0, 0.0};
+  CK(cudaMemcpyAsync(hs, ctx->d_wsum, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->w_mean = hs[1] > 0 ? (float)(hs[0] / hs[1]) : 0.0f;
+  if (!ctx->delta_explicit && ctx->w_mean > 0) { ctx->delta = 2.5f * ctx->w_mean; ctx->grid_delta = 20.0f * ctx->w_mean; ctx->dijkstra_grid_delta = 25.0f * ctx->w_mean; }
   ctx->costs_set = true;
   return MNB_OK;
 }
@@ -516,6 +531,7 @@ static void fill_cvp_args(mnb_ctx* ctx, CvpKernelArgs& a) {
   a.cor_w = ctx->d_cor_w; a.ell_idx = ctx->d_ell_idx; a.ell_w = ctx->d_ell_w; a.ell_geo = ctx->d_ell_geo; a.cost = ctx->d_cost; a.invalid = ctx->has_invalid ? ctx->d_invalid : nullptr; a.ws = ctx->ws;
   a.seed_faces = ctx->d_seed_faces; a.seed_pos = ctx->d_seed_pos; a.delta = ctx->delta; a.next_query = ctx->d_next_query;
   a.cancel_flag = ctx->d_cancel; a.max_rounds = watchdog_rounds(ctx->V); a.sweeps = 0; a.skip_clean = ctx->skip_clean;
+  a.hop = ctx->w_mean > 0 ? 1.35f * ctx->w_mean : 0.16f;
 }
 
 extern "C" {
@@ -687,7 +703,7 @@ static int32_t impl_dijkstra(mnb_ctx* ctx, uint32_t seed_vertex, int64_t robot_v
   cudaError_t e;
   const int cs = ctx->cluster;
   if (cs == -1) {   // single plan on the whole GPU (cooperative launch, one CTA per SM)
-    a.delta = ctx->dijkstra_grid_delta; a.ell_adj = ctx->d_ell_adj; a.sweeps = ctx->sweeps;
+    a.delta = ctx->dijkstra_grid_delta; a.ell_adj = ctx->d_ell_adj; a.sweeps = ctx->sweeps; a.hop = ctx->w_mean > 0 ? 1.35f * ctx->w_mean : 0.16f;
     e = launch_cooperative(k_dijkstra_grid, a, (unsigned)ctx->sm_count, 512, ctx->stream);
   } else
   switch (cs) {

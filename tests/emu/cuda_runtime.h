@@ -154,6 +154,11 @@ static inline float atomicAdd(float* p, float v) {
   uint32_t* u = reinterpret_cast<uint32_t*>(p); uint32_t old = __atomic_load_n(u, __ATOMIC_RELAXED);
   for (;;) { const uint32_t nw = __float_as_uint(__uint_as_float(old) + v); if (__atomic_compare_exchange_n(u, &old, nw, false, __ATOMIC_SEQ_CST, __ATOMIC_RELAXED)) return __uint_as_float(old); }
 }
+static inline double atomicAdd(double* p, double v) {
+  uint64_t* u = reinterpret_cast<uint64_t*>(p); uint64_t old = __atomic_load_n(u, __ATOMIC_RELAXED);
+  for (;;) { double o; __builtin_memcpy(&o, &old, 8); const double nv = o + v; uint64_t nw; __builtin_memcpy(&nw, &nv, 8);
+             if (__atomic_compare_exchange_n(u, &old, nw, false, __ATOMIC_SEQ_CST, __ATOMIC_RELAXED)) return o; }
+}
 template <class T> static inline T atomicSub(T* p, T v) { return __atomic_fetch_sub(p, v, __ATOMIC_SEQ_CST); }
 template <class T> static inline T atomicOr(T* p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 template <class T> static inline T atomicAnd(T* p, T v) { return __atomic_fetch_and(p, v, __ATOMIC_SEQ_CST); }

@@ -108,7 +108,11 @@ def test_bench_orchestration_on_the_cpu_interpreter(emu_lib):
         assert "error" not in leg, (name, leg)
     assert line["other_kernels"]["dynamic_obstacle_update"]["incremental_equals_full"] is True
     v = line["other_kernels"]["optin_variants"]
-    assert v["cvp_clean_candidate_skip"]["identical_to_default"] and v["layers_shared_memory_packed"]["identical_to_default"]
+    assert v["layers_prefetching_walk_vs_round1_walk"]["identical"] and v["inflation_clean_candidate_skip"]["identical"]
+    # the parity blocks of the driver-run line: timed plan, config-3 plan, sampled batch fields
+    assert line["config"]["parity"]["ok"] and line["config"]["parity"]["n_mismatch"] == 0
+    assert line["config"]["config3"]["parity"]["ok"] and line["config"]["batched"]["parity_sampled"]["ok"]
+    assert "parity_failed" not in line
 
 
 def test_smoke_entry_on_the_cpu_interpreter(emu_lib):
