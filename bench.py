@@ -224,6 +224,7 @@ def main():
     ap.add_argument("--batch-cluster", type=int, default=0, help="CTAs per wavefront of the batched leg (0 = chosen per call)")
     ap.add_argument("--no-config3", action="store_true")
     ap.add_argument("--no-other-kernels", action="store_true")
+    ap.add_argument("--submesh-from", type=int, default=3000, help="grid side from which the 1M sub-mesh parity spot check runs (config 5)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -536,6 +537,36 @@ def main():
                        "arrays": "device-resident (MNB_PTR_DEVICE); the update set and its size are produced on the device, only the count is read back"})
             return ta
 
+        def leg_submesh_parity():
+            """parity spot check on a 1M-vertex sub-mesh of the large terrain -- the 1000x1000 window of the
+            same vertices around the goal is cut out, installed as its own map, and layers + a full-field CVP plan on it
+            are compared bit for bit with the oracle"""
+            from oracle import oracle as O
+            m = min(1000, n // 2)
+            v0 = int(faces[sf][0]); i0 = min(max(v0 % n - m // 2, 0), n - m); j0 = min(max(v0 // n - m // 2, 0), n - m)
+            spos = np.ascontiguousarray(pos.reshape(n, n, 3)[j0:j0 + m, i0:i0 + m].reshape(-1, 3))
+            sfaces = synth.grid_mesh(m, m)[1]
+            sm = MeshMap(spos, sfaces, device=local)
+            try:
+                sed = sm.edgeDistances(); svc = np.zeros(sm.V, np.float32); sm.setCosts(svc, sed)
+                fi, fj = v0 % n - i0, v0 // n - j0
+                f = 2 * (min(fj, m - 2) * (m - 1) + min(fi, m - 2)); spc = spos[sfaces[f]].mean(0).astype(np.float32)
+                g = CVPMeshPlanner(sm).waveFrontPropagation(f, spc)
+                Ly = sm.computeLayers()
+                som = O.OracleMesh(spos, sfaces)
+                ref = som.cvp(som.edge_distances(), svc, f, spc)
+                out = {"window": [int(i0), int(j0), m, m], "vertices": int(sm.V), "cvp": parity_block(g["dist"], g["pred"], ref, g["cutting_face"])}
+                rl = som.layers()
+                out["layers_bit_mismatch"] = {k: int((Ly[k].view(np.uint32) != rl[k].view(np.uint32)).sum()) for k in ("height_diff", "ridge", "border", "roughness", "steepness")}
+                rel = max(float(np.max(np.abs(Ly[k] - rl[k]) / np.maximum(np.abs(rl[k]), 1e-30))) for k in ("roughness", "steepness"))
+                out["layers_acos_max_rel"] = rel           # double acos, rounded once on both sides: last-bit differences only
+                out["lethal_masks_identical"] = bool((Ly["lethal_mask"] == rl["lethal_mask"]).all())
+                out["ok"] = bool(out["cvp"]["ok"] and out["lethal_masks_identical"] and rel <= 2e-7
+                                 and not any(out["layers_bit_mismatch"][k] for k in ("height_diff", "ridge", "border")))
+            finally:
+                sm.close()
+            return out
+
         def leg_make_plan():
             # a whole makePlan through the host API: localisation of both poses, wavefront until the robot face is fixed,
             # vector-field back-tracking on the device; only the path crosses PCIe
@@ -591,6 +622,8 @@ def main():
         leg("dynamic_obstacle_update", leg_dynamic_update)
         leg("make_plan_corner_to_corner", leg_make_plan)
         leg("optin_variants", leg_optin_variants)
+        if n >= args.submesh_from and not args.no_cpu_baseline:
+            leg("submesh_1m_parity", leg_submesh_parity)
         shared.clear()
 
     exit_code = 0

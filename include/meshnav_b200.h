@@ -214,6 +214,41 @@ int32_t mnb_inflation_update(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, 
                              const mnb_inflation_params* params, float* out_dist, float* out_cost,
                              uint32_t* out_changed /* V */, uint32_t* n_changed);
 
+/* ---- ray casting against the map -------------------------------------------------------------------------------------
+ * The shared raycaster of the map (MeshMap::raycaster(), mesh_map.h:318; lvr2::EmbreeRaycaster / BVHRaycaster built at
+ * mesh_map.cpp:317-321) as a linear BVH over the faces on the device, built at the first ray call after mnb_set_mesh.
+ * Results are those of a loop over all faces (the tree only prunes): two-sided Moeller-Trumbore in float, nearest hit,
+ * ties to the smallest face id -- the arithmetic is spelled out in oracle/oracle.cpp ("Ray casting against the map").
+ *
+ * mnb_cast_rays = RaycasterBase::castRays as called at obstacle_layer.cpp:239.  dirs: one unit vector per ray
+ * (dir_stride 3) or one for all rays (dir_stride 0, obstacle_layer.cpp:229).  Outputs (each may be NULL): hit flag,
+ * distance (+inf: no hit), face id (0xffffffff: no hit), hit point (NaN: no hit). */
+int32_t mnb_cast_rays(mnb_ctx* ctx, uint32_t n, const float* origins /* 3n */, const float* dirs, uint32_t dir_stride,
+                      uint8_t* out_hit /* n */, float* out_dist /* n */, uint32_t* out_face /* n */, float* out_point /* 3n */);
+
+/* ObstacleLayer::processPointCloud (obstacle_layer.cpp:215-296) without the ROS plumbing: points are the cloud in the
+ * message frame; tf the row-major 3x4 [R|t] of the message frame -> map frame transform (:176-180); down_axis the
+ * configured axis already rotated into the map frame (:183-205).  Points with |p| <= max_obstacle_dist are transformed
+ * and cast along down_axis; a hit within robot_height makes the three vertices of the hit face lethal (:245-256).
+ * out_lethals: the new lethal set, ascending (lethals_); out_changed: its symmetric difference with the set of the
+ * previous call on this context (:268-273, what notifyChange receives); both need room for V ids and may be NULL; the
+ * counts go to the host.  out_costs (V floats or NULL): +inf on lethal vertices, NaN = no entry (costs_, :250;
+ * defaultValue() 0).  mnb_obstacle_reset empties the remembered lethal set. */
+typedef struct mnb_obstacle_params {
+  double max_obstacle_dist, robot_height;
+  float tf[12];
+  float down_axis[3];
+} mnb_obstacle_params;
+int32_t mnb_obstacle_update(mnb_ctx* ctx, uint32_t n_points, const float* points /* 3n */, const mnb_obstacle_params* params,
+                            uint32_t* out_lethals /* V */, uint32_t* n_lethals, uint32_t* out_changed /* V */,
+                            uint32_t* n_changed, float* out_costs /* V or NULL */);
+int32_t mnb_obstacle_reset(mnb_ctx* ctx);
+
+/* lvr2::calcNormalClearance (clearance_layer.cpp:161): the free space above every vertex = distance along its normal
+ * to the first face not incident to it, +inf if there is none; the input of the clearance cost mapping of
+ * mnb_compute_layers.  vertex_normals: 3V floats or NULL = the normals mnb_set_mesh computed. */
+int32_t mnb_normal_clearance(mnb_ctx* ctx, const float* vertex_normals, float* out_clearance /* V */);
+
 /* ---- InflationLayer repulsive vector field -------------------------------------------------------------------------
  * vector_map_ as InflationLayer::waveFrontUpdate accumulates it (inflation_layer.cpp:277-308) for the LAST mnb_inflate /
  * mnb_inflation_update on this context; zero = no entry.  Derived from that wave's final labels, which live in the

@@ -161,6 +161,26 @@ class MeshMap:
         r.update(combined=comb, lethal_mask=mask, **self.stats())
         return r
 
+    def castRays(self, origins, dirs):
+        """the map's shared raycaster (MeshMap::raycaster()->castRays, mesh_map.h:318 / obstacle_layer.cpp:239): one unit
+        direction per ray ([n,3]) or one for all ([3]); returns hit flags, distances, face ids, hit points"""
+        o = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, dtype=np.float32)
+        stride = 0 if d.size == 3 and o.shape[0] != 1 else 3
+        if stride == 3 and d.size != o.size:
+            raise ValueError("dirs must be [3] or [n,3]")
+        n = o.shape[0]
+        hit = np.empty(n, np.uint8); dist = np.empty(n, np.float32); face = np.empty(n, np.uint32); point = np.empty((n, 3), np.float32)
+        self._check(self.L.mnb_cast_rays(self._ctx, n, _p(o), _p(d), stride, _p(hit), _p(dist), _p(face), _p(point)))
+        return dict(hit=hit, dist=dist, face=face, point=point, **self.stats())
+
+    def normalClearance(self, vertex_normals=None) -> np.ndarray:
+        """lvr2::calcNormalClearance (clearance_layer.cpp:161): free space above every vertex along its normal"""
+        vn = None if vertex_normals is None else np.ascontiguousarray(vertex_normals, dtype=np.float32)
+        out = np.empty(self.V, dtype=np.float32)
+        self._check(self.L.mnb_normal_clearance(self._ctx, _p(vn), _p(out)))
+        return out
+
     def locate(self, points):
         """getNearestVertexHandle + searchContainingFace (mesh_map.cpp:1110-1174) for a batch of points ->
         (nearest vertex u32[n], containing face i32[n] (-1 none), barycentric coords f32[n,3])"""
@@ -344,3 +364,36 @@ class InflationLayer:
         m._check(m.L.mnb_inflation_update(m._ctx, _p(le), le.size, _p(inv), C.byref(self.config), _p(dist), _p(cost),
                                           _p(changed), C.byref(n)))
         return dict(dist=dist, cost=cost, changed=changed[:n.value].copy(), **m.stats())
+
+
+class ObstacleLayer:
+    """mesh_layers::ObstacleLayer (obstacle_layer.cpp): the lethal set of the latest point cloud"""
+
+    def __init__(self, mesh_map: MeshMap, robot_height: float = 1.0, max_obstacle_dist: float = 10.0, down_axis=(0.0, 0.0, -1.0)):
+        self.map = mesh_map
+        self.config = _lib.ObstacleParams()
+        self.config.robot_height = robot_height; self.config.max_obstacle_dist = max_obstacle_dist
+        ax = np.asarray(down_axis, dtype=np.float32)
+        ax = ax / np.float32(np.linalg.norm(ax))                      # config_.down_axis is normalised (obstacle_layer.cpp:110)
+        self.down_axis = ax
+        self.map._check(self.map.L.mnb_obstacle_reset(self.map._ctx))
+
+    def processPointCloud(self, points, tf=None, down_axis_map=None, want_costs: bool = False):
+        """ObstacleLayer::processPointCloud (obstacle_layer.cpp:133-296): `points` in the message frame, `tf` the 3x4 [R|t]
+        into the map frame (identity if None), `down_axis_map` the down axis rotated into the map frame (the configured
+        axis if None).  Returns the new lethal set, the changed set (ascending) and optionally the cost map."""
+        m = self.map
+        pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+        T = np.hstack([np.eye(3, dtype=np.float32), np.zeros((3, 1), np.float32)]) if tf is None else np.asarray(tf, dtype=np.float32).reshape(3, 4)
+        ax = self.down_axis if down_axis_map is None else np.asarray(down_axis_map, dtype=np.float32)
+        self.config.tf[:] = [float(x) for x in T.reshape(-1)]
+        self.config.down_axis[:] = [float(x) for x in ax]
+        lethals = np.empty(m.V, np.uint32); changed = np.empty(m.V, np.uint32)
+        costs = np.empty(m.V, np.float32) if want_costs else None
+        nl, nc = C.c_uint32(0), C.c_uint32(0)
+        m._check(m.L.mnb_obstacle_update(m._ctx, pts.shape[0], _p(pts), C.byref(self.config), _p(lethals), C.byref(nl), _p(changed),
+                                         C.byref(nc), _p(costs)))
+        out = dict(lethals=lethals[:nl.value].copy(), changed=changed[:nc.value].copy(), **m.stats())
+        if want_costs:
+            out["costs"] = costs
+        return out

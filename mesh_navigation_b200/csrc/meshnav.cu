@@ -24,6 +24,7 @@ using namespace mnb;
 #include "kernels_layers.cuh"
 #include "kernels_field.cuh"
 #include "kernels_updates.cuh"
+#include "kernels_raycast.cuh"
 
 // ============================================================================
 // host side
@@ -86,6 +87,11 @@ struct mnb_ctx {
   // single CVP plan, 25 w for a single Dijkstra plan; one dependency hop is ~1.35 w (the in-round sweeps are counted in
   // hops).  On the 0.1 m bench meshes (w = 0.118) that is 0.3 / 2.4 / 3.0 m, the values the kernels were tuned with.
   bool delta_explicit = false; float w_mean = 0.0f; double* d_wsum = nullptr;
+  // ray caster over the faces (kernels_raycast.cuh; built on first use) + state of the obstacle layer
+  RayBvh bvh{}; bool bvh_valid = false; unsigned int* d_ray_overflow = nullptr;
+  float* d_ray_in = nullptr; size_t ray_in_cap = 0; float* d_ray_out = nullptr; size_t ray_out_cap = 0;
+  uint8_t* d_obst_now = nullptr; uint8_t* d_obst_mask = nullptr; float* d_obst_member = nullptr; float* d_obst_member_chg = nullptr;
+  uint32_t* d_obst_list = nullptr;
   mnb_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -104,7 +110,9 @@ static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * si
 template <class T>
 static void dfree(T*& p) { if (p) cudaFree(p); p = nullptr; }
 
+static void free_raycaster(mnb_ctx* c);
 static void free_mesh(mnb_ctx* c) {
+  free_raycaster(c);
   dfree(c->d_pos); dfree(c->d_faces); dfree(c->d_edges); dfree(c->d_cor_ptr); dfree(c->d_cor_idx); dfree(c->d_cor_eid);
   dfree(c->d_cor_w); dfree(c->d_cor_wd); dfree(c->d_ell_idx); dfree(c->d_ell_eid); dfree(c->d_ell_w); dfree(c->d_ell_wd); dfree(c->d_ell_geo); dfree(c->d_adj_ptr); dfree(c->d_adj_nbr); dfree(c->d_adj_eid); dfree(c->d_adj_nw); dfree(c->d_ell_adj);
   dfree(c->d_edge_dist); dfree(c->d_edge_w); dfree(c->d_cost); dfree(c->d_invalid); dfree(c->d_wsum);
@@ -1200,4 +1208,5 @@ int32_t mnb_avg_combination_update(mnb_ctx* ctx, uint32_t n_layers, const float*
 
 }  // extern "C"
 
+#include "raycast_host.cuh"
 #include "group.cuh"

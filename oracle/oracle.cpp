@@ -1149,3 +1149,134 @@ extern "C" uint32_t orc_inflation_update_set(uint32_t V, const float* new_costs,
     if (!std::isnan(new_costs[v]) || (old_costs && !std::isnan(old_costs[v]))) out[n++] = v;
   return n;
 }
+
+// ============================================================================
+// Ray casting against the map (MeshMap::raycaster(), mesh_map.h:318; built at mesh_map.cpp:317-321 as
+// lvr2::EmbreeRaycaster / lvr2::BVHRaycaster), ObstacleLayer::processPointCloud (obstacle_layer.cpp:215-296) and
+// lvr2::calcNormalClearance (called at clearance_layer.cpp:161).
+//
+// PARITY UNPINNED: the ray/triangle arithmetic lives in lvr2 / Embree (un-vendored, source_dependencies.yaml:4-7) and the
+// reference holds no test or golden vector for it.  Stated here and followed by the B200 kernels:
+//   * a ray (o, d) meets a triangle (a, b, c) by the two-sided Moeller-Trumbore test in float, evaluated in the order written
+//     in ray_triangle() below, and only inside the triangle's bounding box grown by eps = 1e-5f * max |coordinate| of the map
+//     (box_span(): per-axis slabs; entry tn clamped at 0, exit tf; the hit needs tn <= t <= tf);
+//   * of several hits the smallest t wins, ties go to the smallest face id;  dist = t (d is a unit vector at every call site),
+//     point = o + d * t.
+// This is a brute-force loop over all faces: the acceleration structure of the product must not change any result.
+// ============================================================================
+namespace {
+struct OrcBox { float lo[3], hi[3]; };
+inline bool box_span(const float o[3], const float d[3], const OrcBox& b, float& tn, float& tf) {
+  tn = 0.0f; tf = FINF;
+  for (int k = 0; k < 3; ++k) {
+    if (!(std::fabs(d[k]) >= 1e-20f)) {
+      if (o[k] < b.lo[k] || o[k] > b.hi[k]) return false;
+    } else {
+      const float inv = 1.0f / d[k];
+      const float t1 = (b.lo[k] - o[k]) * inv, t2 = (b.hi[k] - o[k]) * inv;
+      tn = std::fmax(tn, std::fmin(t1, t2));
+      tf = std::fmin(tf, std::fmax(t1, t2));
+    }
+  }
+  return tn <= tf;
+}
+inline float map_eps(const OrcMesh& m) {
+  float mx = 0.0f;
+  for (float x : m.pos) mx = std::fmax(mx, std::fabs(x));
+  const float e = 1e-5f * mx;
+  return e > 0.0f ? e : 1e-30f;
+}
+inline OrcBox tri_box(const OrcMesh& m, uint32_t f, float eps) {
+  OrcBox b;
+  const float* A = &m.pos[3 * (size_t)m.faces[3 * (size_t)f]];
+  const float* B = &m.pos[3 * (size_t)m.faces[3 * (size_t)f + 1]];
+  const float* Cc = &m.pos[3 * (size_t)m.faces[3 * (size_t)f + 2]];
+  for (int k = 0; k < 3; ++k) {
+    b.lo[k] = std::fmin(std::fmin(A[k], B[k]), Cc[k]) - eps;
+    b.hi[k] = std::fmax(std::fmax(A[k], B[k]), Cc[k]) + eps;
+  }
+  return b;
+}
+inline bool ray_triangle(const float o[3], const float d[3], const float* a, const float* b, const float* c, float& t) {
+  const float e1x = b[0] - a[0], e1y = b[1] - a[1], e1z = b[2] - a[2];
+  const float e2x = c[0] - a[0], e2y = c[1] - a[1], e2z = c[2] - a[2];
+  const float px = d[1] * e2z - d[2] * e2y, py = d[2] * e2x - d[0] * e2z, pz = d[0] * e2y - d[1] * e2x;
+  const float det = (e1x * px + e1y * py) + e1z * pz;
+  if (det == 0.0f) return false;
+  const float inv = 1.0f / det;
+  const float sx = o[0] - a[0], sy = o[1] - a[1], sz = o[2] - a[2];
+  const float u = ((sx * px + sy * py) + sz * pz) * inv;
+  if (!(u >= 0.0f && u <= 1.0f)) return false;
+  const float qx = sy * e1z - sz * e1y, qy = sz * e1x - sx * e1z, qz = sx * e1y - sy * e1x;
+  const float v = ((d[0] * qx + d[1] * qy) + d[2] * qz) * inv;
+  if (!(v >= 0.0f && u + v <= 1.0f)) return false;
+  t = ((e2x * qx + e2y * qy) + e2z * qz) * inv;
+  return t >= 0.0f;
+}
+// nearest hit of one ray; skip_vertex: faces with this corner are ignored (UINT32_MAX = none)
+inline bool cast_one(const OrcMesh& m, float eps, const float o[3], const float d[3], uint32_t skip_vertex, float& best_t, uint32_t& best_f) {
+  bool any = false;
+  for (uint32_t f = 0; f < m.F; ++f) {
+    const uint32_t* fv = &m.faces[3 * (size_t)f];
+    if (fv[0] == skip_vertex || fv[1] == skip_vertex || fv[2] == skip_vertex) continue;
+    float tn, tf, t;
+    if (!box_span(o, d, tri_box(m, f, eps), tn, tf)) continue;
+    if (!ray_triangle(o, d, &m.pos[3 * (size_t)fv[0]], &m.pos[3 * (size_t)fv[1]], &m.pos[3 * (size_t)fv[2]], t)) continue;
+    if (!(t >= tn && t <= tf)) continue;
+    if (!any || t < best_t) { any = true; best_t = t; best_f = f; }       // ascending f: ties keep the smallest face id
+  }
+  return any;
+}
+}  // namespace
+
+// lvr2::RaycasterBase::castRays as used at obstacle_layer.cpp:239: per ray hit flag, distance, face id, hit point.
+// dir_stride 0: one direction for all rays (obstacle_layer.cpp:229), 3: one per ray.
+extern "C" void orc_cast_rays(void* h, uint32_t n, const float* origins, const float* dirs, uint32_t dir_stride,
+                              uint8_t* hit, float* dist, uint32_t* face, float* point) {
+  const OrcMesh& m = *(const OrcMesh*)h;
+  const float eps = map_eps(m);
+  for (uint32_t i = 0; i < n; ++i) {
+    const float* o = origins + 3 * (size_t)i; const float* d = dirs + (size_t)dir_stride * i;
+    float t = 0; uint32_t f = 0;
+    const bool any = cast_one(m, eps, o, d, 0xffffffffu, t, f);
+    hit[i] = any ? 1 : 0;
+    dist[i] = any ? t : FINF; face[i] = any ? f : 0xffffffffu;
+    for (int k = 0; k < 3; ++k) point[3 * (size_t)i + k] = any ? o[k] + d[k] * t : std::numeric_limits<float>::quiet_NaN();
+  }
+}
+
+// ObstacleLayer::processPointCloud  obstacle_layer.cpp:215-296.  points: the cloud in the sensor frame; tf: the 3x4 row-major
+// [R|t] of the message frame -> map frame transform (:176-180; the caller expands its quaternion); axis: down_axis already
+// rotated into the map frame (:183-205).  Points with |p| <= max_obstacle_dist are transformed (:221-226), one ray each along
+// axis (:229-239); a hit no further than robot_height makes the three vertices of the hit face lethal (:245-256).
+// lethal_mask (in: the previous lethal set, out: the new one) and changed_mask (symmetric difference, :268-273) are V bytes.
+extern "C" void orc_obstacle_update(void* h, uint32_t n, const float* points, const float* tf, const float* axis,
+                                    double max_obstacle_dist, double robot_height, uint8_t* lethal_mask, uint8_t* changed_mask) {
+  const OrcMesh& m = *(const OrcMesh*)h;
+  const float eps = map_eps(m);
+  std::vector<uint8_t> now(m.V, 0);
+  for (uint32_t i = 0; i < n; ++i) {
+    const float x = points[3 * (size_t)i], y = points[3 * (size_t)i + 1], z = points[3 * (size_t)i + 2];
+    const float norm = std::sqrt((x * x + y * y) + z * z);
+    if (!((double)norm <= max_obstacle_dist)) continue;
+    float o[3];
+    for (int r = 0; r < 3; ++r) o[r] = ((tf[4 * r] * x + tf[4 * r + 1] * y) + tf[4 * r + 2] * z) + tf[4 * r + 3];
+    float t = 0; uint32_t f = 0;
+    if (cast_one(m, eps, o, axis, 0xffffffffu, t, f) && (double)t <= robot_height)
+      for (int k = 0; k < 3; ++k) now[m.faces[3 * (size_t)f + k]] = 1;
+  }
+  for (uint32_t v = 0; v < m.V; ++v) { changed_mask[v] = now[v] != lethal_mask[v]; lethal_mask[v] = now[v]; }
+}
+
+// lvr2::calcNormalClearance (clearance_layer.cpp:161): the free space above a vertex = distance from the vertex along its
+// normal to the first face that is not incident to it; +inf when nothing is hit or the normal is degenerate.
+extern "C" void orc_normal_clearance(void* h, const float* vertex_normals, float* clearance) {
+  const OrcMesh& m = *(const OrcMesh*)h;
+  const float eps = map_eps(m);
+  for (uint32_t v = 0; v < m.V; ++v) {
+    const float* d = vertex_normals + 3 * (size_t)v;
+    float t = 0; uint32_t f = 0;
+    const bool ok = ((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]) > 0.0f;
+    clearance[v] = (ok && cast_one(m, eps, &m.pos[3 * (size_t)v], d, v, t, f)) ? t : FINF;
+  }
+}

@@ -84,6 +84,9 @@ def lib():
         L.orc_layer_changed.argtypes = [vp, f32, vp, u32, vp]
         L.orc_update_edge_weights.argtypes = [vp, vp, vp, dbl, vp, u32, vp]
         L.orc_max_combination_update.argtypes = [u32, vp, vp, vp, vp, u32, vp, vp]
+        L.orc_cast_rays.argtypes = [vp, u32, vp, vp, u32, vp, vp, vp, vp]
+        L.orc_obstacle_update.argtypes = [vp, u32, vp, vp, vp, dbl, dbl, vp, vp]
+        L.orc_normal_clearance.argtypes = [vp, vp, vp]
         L.orc_inflation_update_set.restype = u32
         L.orc_inflation_update_set.argtypes = [u32, vp, vp, vp]
         _lib = L
@@ -347,3 +350,37 @@ def fading(distance, inscribed_radius=0.25, inflation_radius=0.4, lethal_value=1
            cost_scaling_factor=1.0) -> float:
     return float(lib().orc_fading(inscribed_radius, inflation_radius, lethal_value, inscribed_value,
                                   cost_scaling_factor, float(distance)))
+
+
+def _cast_rays(self, origins, dirs):
+    """orc_cast_rays: brute-force nearest hit of every ray (dirs [3] = one direction for all rays)"""
+    o = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
+    d = np.ascontiguousarray(dirs, dtype=np.float32)
+    stride = 0 if d.size == 3 and o.shape[0] != 1 else 3
+    n = o.shape[0]
+    hit = np.empty(n, np.uint8); dist = np.empty(n, np.float32); face = np.empty(n, np.uint32); point = np.empty((n, 3), np.float32)
+    lib().orc_cast_rays(self._h, n, _p(o), _p(d), stride, _p(hit), _p(dist), _p(face), _p(point))
+    return dict(hit=hit, dist=dist, face=face, point=point)
+
+
+def _obstacle_update(self, points, tf, axis, max_obstacle_dist, robot_height, lethal_mask):
+    """orc_obstacle_update: lethal_mask (V bytes) is rolled over in place; returns (new lethal ids, changed ids), ascending"""
+    pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+    T = np.ascontiguousarray(tf, dtype=np.float32).reshape(12)
+    ax = np.ascontiguousarray(axis, dtype=np.float32).reshape(3)
+    changed = np.zeros(self.V, np.uint8)
+    lib().orc_obstacle_update(self._h, pts.shape[0], _p(pts), _p(T), _p(ax), float(max_obstacle_dist), float(robot_height),
+                              _p(lethal_mask), _p(changed))
+    return np.nonzero(lethal_mask)[0].astype(np.uint32), np.nonzero(changed)[0].astype(np.uint32)
+
+
+def _normal_clearance(self, vertex_normals):
+    vn = np.ascontiguousarray(vertex_normals, dtype=np.float32).reshape(-1, 3)
+    out = np.empty(self.V, np.float32)
+    lib().orc_normal_clearance(self._h, _p(vn), _p(out))
+    return out
+
+
+OracleMesh.cast_rays = _cast_rays
+OracleMesh.obstacle_update = _obstacle_update
+OracleMesh.normal_clearance = _normal_clearance

@@ -98,6 +98,7 @@ static inline float __fmul_rn(float a, float b) { volatile float r = a * b; retu
 static inline int __popc(unsigned int x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
 static inline long long clock64() { return (long long)__rdtsc(); }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline unsigned int min(unsigned int a, unsigned int b) { return a < b ? a : b; }
