@@ -567,6 +567,43 @@ def main():
                 sm.close()
             return out
 
+        def leg_obstacle_raycast():
+            """the input side of the dynamic cycle (SURVEY 8 f3): a 262 144-point cloud through ObstacleLayer::processPointCloud
+            (obstacle_layer.cpp:215-296) on the bench map -- BVH build (once per map), range filter + transform + one ray per
+            point + lethal / changed sets; then calcNormalClearance (one ray per vertex).  Parity: a sample of the rays against
+            the oracle's loop over all faces"""
+            from mesh_navigation_b200.api import ObstacleLayer
+            rng = np.random.default_rng(5)
+            npts = 262144 if n >= 1000 else 2048
+            c = pos[(n // 2) * n + n // 2]
+            ij = rng.integers(0, n, size=(npts, 2))
+            base = pos[ij[:, 1] * n + ij[:, 0]]
+            near = np.linalg.norm(base[:, :2] - c[:2], axis=1) <= 12.0 if n >= 1000 else np.ones(npts, bool)
+            ij2 = np.clip(((c[:2] / 0.1)[None, :] + rng.normal(size=(npts, 2)) * 40.0).astype(np.int64), 0, n - 1)
+            base = np.where(near[:, None], base, pos[ij2[:, 1] * n + ij2[:, 0]])
+            pts_map = (base + np.stack([rng.normal(size=npts) * 0.02, rng.normal(size=npts) * 0.02, rng.random(npts) * 1.5 + 0.02], 1)).astype(np.float32)
+            pts = (pts_map - c).astype(np.float32)                                    # message frame: origin at the robot
+            T = np.hstack([np.eye(3, dtype=np.float32), c.reshape(3, 1)]).astype(np.float32)
+            t0 = time.perf_counter(); layer = ObstacleLayer(mm, robot_height=1.0, max_obstacle_dist=10.0)
+            mm.castRays(pts_map[:4], np.array([0, 0, -1], np.float32)); t_build = time.perf_counter() - t0
+            for rep in range(2):
+                t0 = time.perf_counter(); r = layer.processPointCloud(pts, T); t_wall = time.perf_counter() - t0
+            out = {"points": npts, "bvh_build_wall_ms": 1e3 * t_build, "faces": int(mm.F), "process_point_cloud_wall_ms": 1e3 * t_wall,
+                   "process_point_cloud_kernels_ms": r["kernel_ms"], "lethal_vertices": int(r["lethals"].size),
+                   "rays_per_s": npts / (r["kernel_ms"] * 1e-3)}
+            t0 = time.perf_counter(); cl = mm.normalClearance(); out["normal_clearance_wall_ms"] = 1e3 * (time.perf_counter() - t0)
+            out["normal_clearance_kernel_ms"] = mm.stats()["kernel_ms"]; out["finite_clearances"] = int(np.isfinite(cl).sum())
+            if not args.no_cpu_baseline:
+                from oracle import oracle as O
+                om = O.OracleMesh(pos, faces)
+                k = min(128 if mm.F < 1000000 else 32, npts)        # the oracle visits every face for every ray
+                down = np.array([0, 0, -1], np.float32)
+                got = mm.castRays(pts_map[:k], down); t0 = time.perf_counter(); ref = om.cast_rays(pts_map[:k], down); t_or = time.perf_counter() - t0
+                out["parity_sampled"] = {"rays": k, "ok": bool((got["face"] == ref["face"]).all() and (got["dist"].view(np.uint32) == ref["dist"].view(np.uint32)).all()
+                                                               and (got["hit"] == ref["hit"]).all()),
+                                         "oracle_rays_per_s": k / t_or}
+            return out
+
         def leg_make_plan():
             # a whole makePlan through the host API: localisation of both poses, wavefront until the robot face is fixed,
             # vector-field back-tracking on the device; only the path crosses PCIe
@@ -621,6 +658,7 @@ def main():
             leg("config3_plan", leg_config3)
         leg("dynamic_obstacle_update", leg_dynamic_update)
         leg("make_plan_corner_to_corner", leg_make_plan)
+        leg("obstacle_raycast", leg_obstacle_raycast)
         leg("optin_variants", leg_optin_variants)
         if n >= args.submesh_from and not args.no_cpu_baseline:
             leg("submesh_1m_parity", leg_submesh_parity)
