@@ -66,11 +66,14 @@ public:
     std::vector<float> clearance;
     if (!fused->valid && clearance_from_map_)
     {
-      // ClearanceLayer::computeLayer (clearance_layer.cpp:122-164) ray-casts with lvr2::calcNormalClearance: kept on the
-      // reference's side until the ray caster of this package replaces it; the COST mapping (:67-99) runs on the device
-      const auto cl = lvr2::calcNormalClearance(*map->mesh(), map->vertexNormals());
+      // ClearanceLayer::computeLayer (clearance_layer.cpp:122-164): lvr2::calcNormalClearance -> one ray per vertex along its
+      // normal on the device BVH (NULL = the vertex normals mnb_set_mesh computed); the cost mapping (:67-99) is fused below
       clearance.assign(b200_->V, std::numeric_limits<float>::infinity());
-      for (auto vH : cl) clearance[vH.idx()] = cl[vH];
+      if (mnb_normal_clearance(b200_->ctx, nullptr, clearance.data()) != MNB_OK)
+      {
+        RCLCPP_ERROR_STREAM(get_logger(), layer_name_ << ": " << mnb_last_error(b200_->ctx));
+        return false;
+      }
     }
     if (!fused->ensure(*b200_, clearance.empty() ? nullptr : &clearance)) return false;
     costs_.clear(); lethal_vertices_.clear();

@@ -29,6 +29,7 @@ template <class H, class V> struct AttributeMap {
 };
 template <class V> using VertexMap = AttributeMap<VertexHandle, V>;
 template <class V> using DenseVertexMap = AttributeMap<VertexHandle, V>;
+template <class V> using SparseVertexMap = AttributeMap<VertexHandle, V>;
 template <class V> using DenseEdgeMap = AttributeMap<EdgeHandle, V>;
 template <class V> using DenseFaceMap = AttributeMap<FaceHandle, V>;
 template <class Vec> struct PMPMesh {

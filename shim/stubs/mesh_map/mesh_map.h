@@ -7,6 +7,7 @@
 #include <lvr2/lvr2_stub.hpp>
 #include <rclcpp/rclcpp.hpp>
 namespace std_msgs { namespace msg { struct Header { rclcpp::Time stamp; std::string frame_id; }; } }
+#include <tf2_ros/buffer.h>
 namespace geometry_msgs { namespace msg {
 struct Point { double x = 0, y = 0, z = 0; }; struct Quaternion { double x = 0, y = 0, z = 0, w = 1; };
 struct Pose { Point position; Quaternion orientation; }; struct PoseStamped { std_msgs::msg::Header header; Pose pose; };
@@ -24,6 +25,7 @@ public:
   std::shared_ptr<lvr2::PMPMesh<Vector>> mesh();                                                  // :276
   const lvr2::DenseVertexMap<float>& vertexCosts();                                               // :292
   const std::string& mapFrame() const;                                                            // :300
+  const tf2_ros::Buffer& tf2Buffer() const;                                                       // :308
   const lvr2::DenseFaceMap<Normal>& faceNormals();                                                // :326
   const lvr2::DenseVertexMap<Normal>& vertexNormals();                                            // :334
   const lvr2::DenseEdgeMap<float>& edgeWeights();                                                 // :342

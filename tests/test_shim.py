@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_shim_sources_compile_against_the_interface_stubs():
     srcs = sorted(glob.glob(os.path.join(ROOT, "shim", "src", "*.cpp")))
-    assert len(srcs) == 4
+    assert len(srcs) == 5
     for src in srcs:
         r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-Werror=overloaded-virtual", "-Werror=suggest-override",
                             "-I" + os.path.join(ROOT, "shim", "stubs"), "-I" + os.path.join(ROOT, "shim", "include"),
@@ -27,7 +27,7 @@ def test_shim_has_no_placeholders_and_registers_every_class():
     exported = set(re.findall(r"PLUGINLIB_EXPORT_CLASS\(mesh_navigation_b200_plugins::(\w+),", text))
     xml = open(os.path.join(ROOT, "shim", "b200_planners.xml")).read() + open(os.path.join(ROOT, "shim", "b200_layers.xml")).read()
     declared = set(re.findall(r'type="mesh_navigation_b200_plugins::(\w+)"', xml))
-    assert exported == declared and len(exported) == 9
+    assert exported == declared and len(exported) == 10
     cm = open(os.path.join(ROOT, "shim", "CMakeLists.txt")).read()
     for f in glob.glob(os.path.join(ROOT, "shim", "src", "*.cpp")):
         assert "src/" + os.path.basename(f) in cm
