@@ -439,6 +439,79 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
     bool skip_ok = false;
     if constexpr (P::CAN_SKIP) skip_ok = prob.skip_clean && !has_robot && (P::SKIP_IN_STRICT || !prob.strict) && __float_as_uint(delta) == INF_BITS;
     float my_mtau = __uint_as_float(INF_BITS), my_lo = __uint_as_float(INF_BITS);
+    // the evaluation of one candidate: recompute, stamps of the clean-candidate skip, re-staging, activation of the neighbours
+    auto evaluate = [&](const uint32_t c, const Label& old, const bool nf) {
+      const float tau = old.t.a1;
+      float nd, ntau;
+      my_recomputes++;
+      if constexpr (P::CAN_SKIP) prob.deferred_flag = false;
+      const bool changed = prob.recompute(c, band_end, goal, r, old, nd, ntau);
+      if (changed) my_mtau = fminf(my_mtau, fminf(tau, ntau));
+      if constexpr (P::CAN_SKIP) if (skip_ok) {
+        __stcg(&prob.last_eval[c], prob.deferred_flag ? 0u : r + 1u);
+        if (changed) prob.activate(c, [&](uint32_t x) { __stcg(&prob.dirty_round[x], r + 1u); });
+      }
+      if (!nf) my_lo = fminf(my_lo, ntau);      // smallest pop time still in flight: the band follows it
+      stage_push(st, c, list_n, &ctl->count[next]);
+      // a vertex that holds a finite label pulls its neighbours into the candidate set (once)
+      if (__float_as_uint(nd) != INF_BITS && __ldcg(&mark[c]) == MARK_CAND) {
+        mark[c] = MARK_CAND_ACT;
+        prob.activate(c, [&](uint32_t x) {
+          if (__ldcg(&mark[x]) == MARK_NONE && prob.eligible(x) && atomicCAS(&mark[x], MARK_NONE, MARK_CAND) == MARK_NONE)
+            stage_push(st, x, list_n, &ctl->count[next]);
+        });
+      }
+    };
+    bool two_phase = false;
+    if constexpr (P::CAN_SKIP) two_phase = skip_ok;
+    if (two_phase) {
+      if constexpr (P::CAN_SKIP) {
+        // With the clean-candidate skip two thirds of the candidates of a round keep their label; one thread per list
+        // entry would leave the recomputing lanes scattered over all warps (a warp is as slow as its slowest lane).  So the
+        // CTA first CLASSIFIES its share of the list (settled / clean / needs an evaluation) and queues the last kind in
+        // shared memory, then evaluates the queue with full warps.  Same decisions, same stamps, same results.
+        constexpr unsigned int WQ_CAP = 2048;
+        __shared__ uint32_t wq[WQ_CAP];
+        __shared__ unsigned int wq_n;
+        if (threadIdx.x == 0) wq_n = 0;
+        __syncthreads();
+        auto drain = [&]() {                                 // called by all threads of the CTA, right after a barrier
+          const unsigned int m = wq_n;
+          for (unsigned int k = threadIdx.x; k < m; k += blockDim.x) {
+            const uint32_t c = wq[k];
+            evaluate(c, prob.load_label(c), prob.never_fixed(c));
+          }
+          __syncthreads();
+          if (threadIdx.x == 0) wq_n = 0;
+          __syncthreads();
+        };
+        unsigned int chunks = 0;
+        for (unsigned int b = gtid - threadIdx.x; b < n; b += gthreads) {
+          const unsigned int i = b + threadIdx.x;
+          if (i < n) {
+            const uint32_t c = __ldcg(&list_r[i]);
+            const Label old = prob.load_label(c);
+            const float tau = old.t.a1;
+            const bool nf = prob.never_fixed(c);
+            if (tau < m_prev && tau < band_end_prev && (!nf || __float_as_uint(m_prev) == INF_BITS)) {
+              mark[c] = MARK_FIXED; my_settled++;            // converged prefix (no robot bookkeeping: skip_ok excludes it)
+            } else {
+              const uint32_t le = __ldcg(&prob.last_eval[c]), dr = __ldcg(&prob.dirty_round[c]);
+              if (le != 0u && dr < le) {                     // clean: same inputs, same label
+                if (!nf) my_lo = fminf(my_lo, tau);
+                my_skipped++;
+                stage_push(st, c, list_n, &ctl->count[next]);
+              } else {
+                wq[atomicAdd(&wq_n, 1u)] = c;
+              }
+            }
+          }
+          if (++chunks == WQ_CAP / blockDim.x) { __syncthreads(); drain(); chunks = 0; }     // CTA-uniform: a chunk queues <= blockDim entries
+        }
+        __syncthreads();
+        drain();
+      }
+    } else
     for (unsigned int i = gtid; i < n; i += gthreads) {
       const uint32_t c = __ldcg(&list_r[i]);
       const Label old = prob.load_label(c);
@@ -467,36 +540,7 @@ __device__ void run_band_rounds(P& prob, GroupCtl* ctl, uint32_t* list0, uint32_
         }
         continue;
       }
-      float nd, ntau;
-      if constexpr (P::CAN_SKIP) if (skip_ok) {
-        // clean-candidate skip (see run_band_rounds_sub8): no source of c was re-labelled in or after the round of c's last
-        // evaluation -> same inputs, same label.  (delta = inf here: no source is ever excluded by the band end.)
-        const uint32_t le = __ldcg(&prob.last_eval[c]), dr = __ldcg(&prob.dirty_round[c]);
-        if (le != 0u && dr < le) {
-          if (!nf) my_lo = fminf(my_lo, tau);
-          my_skipped++;
-          stage_push(st, c, list_n, &ctl->count[next]);
-          continue;
-        }
-      }
-      my_recomputes++;
-      if constexpr (P::CAN_SKIP) prob.deferred_flag = false;
-      const bool changed = prob.recompute(c, band_end, goal, r, old, nd, ntau);
-      if (changed) my_mtau = fminf(my_mtau, fminf(tau, ntau));
-      if constexpr (P::CAN_SKIP) if (skip_ok) {
-        __stcg(&prob.last_eval[c], prob.deferred_flag ? 0u : r + 1u);
-        if (changed) prob.activate(c, [&](uint32_t x) { __stcg(&prob.dirty_round[x], r + 1u); });
-      }
-      if (!nf) my_lo = fminf(my_lo, ntau);      // smallest pop time still in flight: the band follows it
-      stage_push(st, c, list_n, &ctl->count[next]);
-      // a vertex that holds a finite label pulls its neighbours into the candidate set (once)
-      if (__float_as_uint(nd) != INF_BITS && __ldcg(&mark[c]) == MARK_CAND) {
-        mark[c] = MARK_CAND_ACT;
-        prob.activate(c, [&](uint32_t x) {
-          if (__ldcg(&mark[x]) == MARK_NONE && prob.eligible(x) && atomicCAS(&mark[x], MARK_NONE, MARK_CAND) == MARK_NONE)
-            stage_push(st, x, list_n, &ctl->count[next]);
-        });
-      }
+      evaluate(c, old, nf);
     }
     {
       my_mtau = fminf(my_mtau, prob.deferred_m);      // deferred back-steps are pending changes

@@ -13,11 +13,12 @@ using namespace mnb;
 // edges / faces and patch only the table entries that hold one of those edges' weights.
 // ============================================================================
 __global__ void k_update_costs(const uint32_t* __restrict__ changed, uint32_t n, const float* __restrict__ costs, int by_vertex,
-                               float default_value, uint32_t V, float* __restrict__ cost) {
+                               float default_value, uint32_t V, float* __restrict__ cost, uint32_t* __restrict__ stamp, uint32_t call) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t v = changed[i];
   if (v >= V) return;
+  stamp[v] = call;                                            // membership in this call's change set (k_refresh_weight_tables)
   float c = by_vertex ? costs[v] : costs[i];
   if (by_vertex && c != c) c = default_value;                 // cost_map.get(vH).value_or(default_value), mesh_map.cpp:486
   cost[v] = c;
@@ -51,16 +52,21 @@ struct RefreshArgs {
   const uint32_t* adj_ptr; const uint32_t* adj_nbr; const uint32_t* adj_eid;
   const float* w;
   float4* cor_w; float4* ell_w; double4* ell_geo; uint2* adj_nw; uint4* ell_adj;
+  const uint32_t* stamp; uint32_t call;      // stamp[x] == call: x is in the change set of this call
 };
 // every table entry that stores the weight of an edge incident to a changed vertex: the corner records (CSR + ELL +
-// precomputed unfolding geometry) of all three vertices of each incident face, and both directions of the adjacency
+// precomputed unfolding geometry) of all three vertices of each incident face, and both directions of the adjacency.
+// A face (an edge) whose vertices are all in the change set is patched once, by its smallest changed vertex: obstacle
+// discs change compact regions, where every face used to be rewritten three times.
 __global__ void k_refresh_weight_tables(const RefreshArgs a) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)a.n * ELL_W) return;
   const uint32_t v = a.changed[t / ELL_W], j = (uint32_t)(t % ELL_W);
   if (v >= a.V) return;
   for (uint32_t k = a.cor_ptr[v] + j; k < a.cor_ptr[v + 1]; k += ELL_W) {
-    const uint32_t f = (uint32_t)a.cor_idx[k].z;
+    const int4 ci = a.cor_idx[k];
+    const uint32_t f = (uint32_t)ci.z;
+    if (((uint32_t)ci.x < v && a.stamp[(uint32_t)ci.x] == a.call) || ((uint32_t)ci.y < v && a.stamp[(uint32_t)ci.y] == a.call)) continue;
     for (int c = 0; c < 3; ++c) {
       const uint32_t x = a.faces[3 * (size_t)f + c];
       const uint32_t kb = a.cor_ptr[x], ke = a.cor_ptr[x + 1];
@@ -81,7 +87,9 @@ __global__ void k_refresh_weight_tables(const RefreshArgs a) {
   }
   const uint32_t ab = a.adj_ptr[v];
   for (uint32_t k = ab + j; k < a.adj_ptr[v + 1]; k += ELL_W) {
-    const uint32_t u = a.adj_nbr[k], wb = __float_as_uint(a.w[a.adj_eid[k]]);
+    const uint32_t u = a.adj_nbr[k];
+    if (u < v && a.stamp[u] == a.call) continue;
+    const uint32_t wb = __float_as_uint(a.w[a.adj_eid[k]]);
     a.adj_nw[k] = make_uint2(u, wb);
     if (k - ab < ELL_W) reinterpret_cast<uint32_t*>(&a.ell_adj[(size_t)v * ELL_W + (k - ab)])[1] = wb;
     const uint32_t ub = a.adj_ptr[u], ue = a.adj_ptr[u + 1];

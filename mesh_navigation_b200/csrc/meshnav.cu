@@ -71,6 +71,7 @@ struct mnb_ctx {
   // incremental updates
   float* d_prev_risk = nullptr; bool prev_risk_valid = false;     // riskiness map of the previous inflation (NaN = no entry)
   uint32_t* d_upd_ids = nullptr; float* d_upd_costs = nullptr; size_t upd_cap = 0; size_t upd_cost_cap = 0;
+  uint32_t* d_upd_stamp = nullptr; uint32_t upd_call = 0;      // change-set membership stamps of mnb_update_vertex_costs
   uint32_t* d_changed = nullptr; unsigned int* d_tile_count = nullptr; unsigned int* d_total = nullptr;
   // tuning
   float delta = 0.3f; int cluster = -1 /* -1: whole-grid cooperative kernel for single plans */; int batch_cluster = 0 /* 0: chosen per call from the goal count */; int threads = 512;
@@ -87,6 +88,8 @@ struct mnb_ctx {
   // single CVP plan, 25 w for a single Dijkstra plan; one dependency hop is ~1.35 w (the in-round sweeps are counted in
   // hops).  On the 0.1 m bench meshes (w = 0.118) that is 0.3 / 2.4 / 3.0 m, the values the kernels were tuned with.
   bool delta_explicit = false; float w_mean = 0.0f; double* d_wsum = nullptr;
+  int grid_engine = 0;         // experiment: 1 = full-field single plans run the lean batch round loop on the whole grid (k_cvp_batch<0>)
+  float grid2_delta_w = 2.5f;  //             its band width in mean edge weights
   // ray caster over the faces (kernels_raycast.cuh; built on first use) + state of the obstacle layer
   RayBvh bvh{}; bool bvh_valid = false; unsigned int* d_ray_overflow = nullptr;
   float* d_ray_in = nullptr; size_t ray_in_cap = 0; float* d_ray_out = nullptr; size_t ray_out_cap = 0;
@@ -122,7 +125,7 @@ static void free_mesh(mnb_ctx* c) {
   dfree(c->d_infl_invalid); dfree(c->d_out_cost);
   dfree(c->d_infl_vec); dfree(c->d_infl_dist); dfree(c->d_infl_src); dfree(c->d_infl_flag);
   c->infl_labels_valid = false; c->infl_field_valid = false; c->repulsive_on = false;
-  dfree(c->d_prev_risk); c->prev_risk_valid = false; dfree(c->d_upd_ids); dfree(c->d_upd_costs); c->upd_cap = 0; c->upd_cost_cap = 0;
+  dfree(c->d_prev_risk); c->prev_risk_valid = false; dfree(c->d_upd_ids); dfree(c->d_upd_costs); c->upd_cap = 0; c->upd_cost_cap = 0; dfree(c->d_upd_stamp); c->upd_call = 0;
   dfree(c->d_changed); dfree(c->d_tile_count); dfree(c->d_total);
   dfree(c->d_path_pos); dfree(c->d_path_face); dfree(c->d_bt_result); c->path_cap = 0; c->last_valid = false;
   dfree(c->d_face_normals); dfree(c->d_vertex_normals); dfree(c->d_border); dfree(c->d_layer_costs); dfree(c->d_layer_combined);
@@ -180,6 +183,8 @@ int32_t mnb_create(int32_t device, mnb_ctx** out_ctx) {
   if (const char* e = getenv("MNB_INFL_SKIP")) c->infl_skip_clean = atoi(e) != 0;                                 // experiment knob
   if (const char* e = getenv("MNB_LAYERS_SMEM")) c->layers_smem = atoi(e);                                   // experiment knob
   if (const char* e = getenv("MNB_SKIP_CLEAN")) c->skip_clean = atoi(e) != 0;                                     // experiment knob
+  if (const char* e = getenv("MNB_GRID_ENGINE")) c->grid_engine = atoi(e);                                     // experiment knob
+  if (const char* e = getenv("MNB_GRID2_DELTA_W")) { const float k = (float)atof(e); if (k > 0) c->grid2_delta_w = k; }
   if (const char* e = getenv("MNB_SWEEPS")) { const int k = atoi(e); if (k >= -1 && k <= 64) c->sweeps = k; }   // experiment knob
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MNB_E_CUDA; }
   cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
@@ -581,6 +586,14 @@ static int32_t impl_cvp(mnb_ctx* ctx, uint32_t seed_face, const float seed_pos[3
       ctx->grid_blocks_per_sm = nb > MNB_GRID_MINBLOCKS ? MNB_GRID_MINBLOCKS : nb;
       if (nb <= 0) { ctx->err = "k_cvp_grid cannot be resident"; return MNB_E_CUDA; }
     }
+    if (ctx->grid_engine == 1 && robot_face < 0) {
+      int per_sm = 1;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cvp_batch<0>, MNB_BATCH_THREADS, 0));
+      if (per_sm > MNB_BATCH_MINBLOCKS) per_sm = MNB_BATCH_MINBLOCKS;
+      if (per_sm < 1) { ctx->err = "k_cvp_batch<0> cannot be resident"; return MNB_E_CUDA; }
+      a.delta = ctx->grid2_delta_w * (ctx->w_mean > 0.0f ? ctx->w_mean : 0.12f);
+      CK(launch_cooperative(k_cvp_batch<0>, a, (unsigned)(ctx->sm_count * per_sm), MNB_BATCH_THREADS, ctx->stream));
+    } else
     CK(launch_cooperative(k_cvp_grid<false>, a, (unsigned)(ctx->sm_count * ctx->grid_blocks_per_sm), ctx->threads, ctx->stream));
   } else {
     if ((rc = launch_cvp(ctx, a, ctx->cluster, 1)) != MNB_OK) return rc;
@@ -912,6 +925,7 @@ static int32_t impl_locate(mnb_ctx* ctx, uint32_t n, const float* points, uint32
 // experiment knob (not part of the public header): in-round sweeps of the whole-grid single-plan kernel
 int32_t mnb_debug_set_sweeps(mnb_ctx* ctx, int32_t k) { if (!ctx || k < -1 || k > 64) return MNB_E_ARG; ctx->sweeps = k; return MNB_OK; }
 
+int32_t mnb_debug_set_grid_engine(mnb_ctx* ctx, int32_t mode, float delta_w) { if (!ctx) return MNB_E_ARG; ctx->grid_engine = mode; if (delta_w > 0) ctx->grid2_delta_w = delta_w; return MNB_OK; }
 int32_t mnb_debug_set_infl_skip(mnb_ctx* ctx, int32_t on) { if (!ctx) return MNB_E_ARG; ctx->infl_skip_clean = on != 0; return MNB_OK; }
 int32_t mnb_debug_set_layers_smem(mnb_ctx* ctx, int32_t mode) { if (!ctx || mode < 0 || mode > 4) return MNB_E_ARG; ctx->layers_smem = mode; return MNB_OK; }
 int32_t mnb_debug_set_skip_clean(mnb_ctx* ctx, int32_t on) { if (!ctx) return MNB_E_ARG; ctx->skip_clean = on != 0; ctx->grid_blocks_per_sm = 0; return MNB_OK; }
@@ -1042,10 +1056,16 @@ static int32_t impl_update_vertex_costs(mnb_ctx* ctx, uint32_t n_changed, const 
     CK(cudaMemcpyAsync(ctx->d_upd_costs, costs, sizeof(float) * nc, cudaMemcpyHostToDevice, ctx->stream));
     d_ids = ctx->d_upd_ids; d_costs = ctx->d_upd_costs;
   }
+  if (!ctx->d_upd_stamp || ctx->upd_call == 0xffffffffu) {
+    if (!ctx->d_upd_stamp) CK(dalloc(&ctx->d_upd_stamp, (size_t)ctx->V));
+    CK(cudaMemsetAsync(ctx->d_upd_stamp, 0, sizeof(uint32_t) * (size_t)ctx->V, ctx->stream));
+    ctx->upd_call = 0;
+  }
+  ++ctx->upd_call;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   unsigned launches = 1;
   MNB_LAUNCH(k_update_costs, (n_changed + 255) / 256, 256, 0, ctx->stream, d_ids, n_changed, d_costs, (int)(costs_indexed_by_vertex != 0),
-             default_value, ctx->V, ctx->d_cost);
+             default_value, ctx->V, ctx->d_cost, ctx->d_upd_stamp, ctx->upd_call);
   if (edge_cost_factor != 0) {                       // mesh_map.cpp:568-572: no edge update at all for a zero factor
     const unsigned blocks = (unsigned)(((size_t)n_changed * ELL_W + 255) / 256);
     MNB_LAUNCH(k_update_edge_weights, blocks, 256, 0, ctx->stream, d_ids, n_changed, ctx->V, (const uint32_t*)ctx->d_adj_ptr,
@@ -1055,6 +1075,7 @@ static int32_t impl_update_vertex_costs(mnb_ctx* ctx, uint32_t n_changed, const 
     r.changed = d_ids; r.n = n_changed; r.V = ctx->V; r.faces = ctx->d_faces; r.cor_ptr = ctx->d_cor_ptr; r.cor_idx = ctx->d_cor_idx;
     r.cor_eid = ctx->d_cor_eid; r.adj_ptr = ctx->d_adj_ptr; r.adj_nbr = ctx->d_adj_nbr; r.adj_eid = ctx->d_adj_eid; r.w = ctx->d_edge_w;
     r.cor_w = ctx->d_cor_w; r.ell_w = ctx->d_ell_w; r.ell_geo = ctx->d_ell_geo; r.adj_nw = ctx->d_adj_nw; r.ell_adj = ctx->d_ell_adj;
+    r.stamp = ctx->d_upd_stamp; r.call = ctx->upd_call;
     MNB_LAUNCH(k_refresh_weight_tables, blocks, 256, 0, ctx->stream, r);
     launches = 3;
   }
