@@ -90,6 +90,11 @@ class MeshMap {
     const Vector p0 = vertexPosition(faces_[3 * (size_t)f]), p1 = vertexPosition(faces_[3 * (size_t)f + 1]), p2 = vertexPosition(faces_[3 * (size_t)f + 2]);
     return normalized(cross(p1 - p0, p2 - p0));
   }
+  // MeshMap::vertexNormals()[v] (mesh_map.h:334; computed by mnb_set_mesh, fetched once)
+  Vector vertexNormal(uint32_t v) const {
+    if (vertex_normals_.empty()) { vertex_normals_.resize(3 * (size_t)numVertices()); mnb_get_vertex_normals(ctx_, vertex_normals_.data()); }
+    return {vertex_normals_[3 * (size_t)v], vertex_normals_[3 * (size_t)v + 1], vertex_normals_[3 * (size_t)v + 2]};
+  }
   std::vector<float>& vertexCosts() { return vertex_costs_; }          // MeshMap::vertexCosts()
   std::vector<float>& edgeWeights() { return edge_weights_; }          // MeshMap::edgeWeights()
   const std::vector<float>& edgeDistances() const { return edge_distances_; }
@@ -136,6 +141,7 @@ class MeshMap {
   mnb_ctx* ctx_ = nullptr;
   std::vector<float> pos_; std::vector<uint32_t> faces_;
   std::vector<float> vertex_costs_, edge_weights_, edge_distances_;
+  mutable std::vector<float> vertex_normals_;
   std::vector<uint8_t> invalid_;
 };
 
@@ -167,15 +173,20 @@ class DijkstraMeshPlanner : public MeshPlanner {
     cost = 0;
     if (!path.empty()) {                                                         // :90-116
       Vector vec = start.position;
+      Vector normal = mesh_map_->vertexNormal(path.front());                     // :93-94
       while (!path.empty()) {
-        const Vector next = mesh_map_->vertexPosition(path.front());
+        const uint32_t vH = path.front();
+        const Vector next = mesh_map_->vertexPosition(vH);
         PoseStamped pose; pose.position = vec; pose.direction = normalized(next - vec);
+        pose.orientation = calculatePoseFromDirection(next - vec, normal);       // :106 calculatePoseFromPosition(vec, next, normal)
         cost += length(next - vec);
         vec = next;
+        normal = mesh_map_->vertexNormal(vH);                                    // :109
         plan.push_back(pose);
         path.pop_front();
       }
       PoseStamped pose; pose.position = vec; pose.direction = normalized(goal.position - vec);
+      pose.orientation = calculatePoseFromDirection(goal.position - vec, normal);   // :113
       cost += length(goal.position - vec);
       plan.push_back(pose);
     }

@@ -70,7 +70,10 @@ struct InflateKernelArgs {
   int skip_clean;
 };
 
-__global__ void __launch_bounds__(512, 1) k_inflate(const InflateKernelArgs a) {
+#ifndef MNB_INFL_MINBLOCKS
+#define MNB_INFL_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(512, MNB_INFL_MINBLOCKS) k_inflate(const InflateKernelArgs a) {
   __shared__ Stage st;
   uint32_t g, gthreads, gtid;
   group_coords<0>(g, gthreads, gtid);
@@ -79,6 +82,7 @@ __global__ void __launch_bounds__(512, 1) k_inflate(const InflateKernelArgs a) {
   GroupCtl* ctl = a.ws.ctl;
   if (threadIdx.x == 0) { st.n = 0; st.m_tau = INF_BITS; st.lo = INF_BITS; }
   __syncthreads();
+#pragma unroll 4
   for (uint32_t v = gtid; v < V; v += gthreads) { state[v] = state_inf(); mark[v] = MARK_NONE; a.ws.chg[v] = 0u; a.ws.last_eval[v] = 0u; a.ws.dirty[v] = 0u; }
   group_sync<0>(ctl->barrier);
   for (uint32_t i = gtid; i < a.n_lethals; i += gthreads) {      // :397-402
@@ -106,10 +110,18 @@ __global__ void __launch_bounds__(512, 1) k_inflate(const InflateKernelArgs a) {
   run_band_rounds<0>(prob, ctl, list0, list1, mark, st, __uint_as_float(INF_BITS), gthreads, gtid, 0, 0u, 0u, 0u, 0.0,
                      nullptr, 1e-30f, a.max_rounds);
   group_sync<0>(ctl->barrier);
-  for (uint32_t v = gtid; v < V; v += gthreads) {
-    const float d = __uint_as_float(state[v].x);
-    if (a.out_dist) a.out_dist[v] = d;
-    if (a.out_cost) a.out_cost[v] = (__float_as_uint(d) == INF_BITS) ? __int_as_float(0x7fc00000) : fading(a.params, d);
+  // dense outputs: four independent label loads in flight per thread (the loop is a stream over V, not part of the wave)
+  for (uint32_t v0 = gtid; v0 < V; v0 += 4 * gthreads) {
+    float d[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const uint32_t v = v0 + q * gthreads; d[q] = v < V ? __uint_as_float(__ldcg(reinterpret_cast<const uint32_t*>(state) + 4 * (size_t)v)) : 0.0f; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t v = v0 + q * gthreads;
+      if (v >= V) continue;
+      if (a.out_dist) a.out_dist[v] = d[q];
+      if (a.out_cost) a.out_cost[v] = (__float_as_uint(d[q]) == INF_BITS) ? __int_as_float(0x7fc00000) : fading(a.params, d[q]);
+    }
   }
 }
 

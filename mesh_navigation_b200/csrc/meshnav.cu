@@ -979,7 +979,12 @@ static int32_t inflate_impl(mnb_ctx* ctx, const uint32_t* lethals, uint32_t n, c
   a.out_cost = (dev && out_cost) ? out_cost : ctx->d_out_cost;
   a.max_rounds = watchdog_rounds(ctx->V); a.skip_clean = ctx->infl_skip_clean;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  CK(launch_cooperative(k_inflate, a, (unsigned)ctx->sm_count, ctx->threads, ctx->stream));
+  int infl_per_sm = 1;
+  if (MNB_INFL_MINBLOCKS > 1) {
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&infl_per_sm, k_inflate, ctx->threads, 0));
+    infl_per_sm = std::max(1, std::min(infl_per_sm, (int)MNB_INFL_MINBLOCKS));
+  }
+  CK(launch_cooperative(k_inflate, a, (unsigned)(ctx->sm_count * infl_per_sm), ctx->threads, ctx->stream));
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   if (!dev) {
     if (out_dist) CK(cudaMemcpyAsync(out_dist, a.out_dist, sizeof(float) * (size_t)ctx->V, cudaMemcpyDeviceToHost, ctx->stream));

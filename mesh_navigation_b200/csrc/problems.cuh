@@ -648,9 +648,7 @@ struct InflationProblem : LabelStore {
     const uint32_t kb = cor_ptr[c], ke = cor_ptr[c + 1];
     if (ke - kb > (uint32_t)MAXF || (invalid && invalid[c])) return false;
     const float INF = __uint_as_float(INF_BITS);
-    float Ta[MAXF];
-    int n = 0;
-    float m = INF;
+    float m = INF, tmin_nc = INF;                                       // smallest causal candidate / earliest non-causal face
     for (uint32_t k = kb; k < ke; ++k) {
       EvTime T; float u1, u2; uint32_t Tv;
       if (!corner_time(c, k, band_end, T, Tv, u1, u2)) continue;
@@ -659,14 +657,11 @@ struct InflationProblem : LabelStore {
       if (cand > T.a1) {                                               // causal
         if (!(u1 <= max_distance && u2 <= max_distance)) return false;   // accepted without (re)insertion: heap key != distance
         m = fminf(m, cand);
-        Ta[n] = -1.0f;
       } else {
-        Ta[n] = T.a1;
+        tmin_nc = fminf(tmin_nc, T.a1);
       }
-      ++n;
     }
-    for (int i = 0; i < n; ++i)
-      if (Ta[i] >= 0.0f && !(Ta[i] > m)) return false;                 // a non-causal face that could fire before c pops
+    if (__float_as_uint(tmin_nc) != INF_BITS && !(tmin_nc > m)) return false;   // a non-causal face that could fire before c pops
     nd = m; tc_out = ev_normal(m, c);
     return true;
   }

@@ -42,7 +42,11 @@ def unshard_order(n_goals: int, world: int) -> np.ndarray:
 def sharded_potentials(compute_chunk: Callable[[np.ndarray, "object"], None], n_goals: int, V: int, *, rank: int,
                        world: int, device, chunk: int = 0, dist=None, torch=None, timings: dict = None):
     """Run `compute_chunk(goal_indices, out_tensor)` for this rank's goals and all-gather every rank's
-    fields.  Returns a [n_goals, V] float32 tensor in goal order on `device` (every rank gets all fields).
+    fields (every rank gets all of them, float32 on `device`).  Return value, indexable by goal either way:
+      world == 1: the [n_goals, V] tensor itself;
+      world  > 1: a zero-copy [pad, world, V] view of the rank-major gather buffer -- row (i, r) is the field of goal
+                  i * world + r, rows of the ragged last shard are +inf.  `goal_order_rows(result, n_goals, V)` gives the
+                  contiguous [n_goals, V] tensor when a consumer needs one (it copies).
 
     compute_chunk fills out_tensor[:len(goal_indices)] (float32, [chunk, V], on `device`) with the
     potential fields of the given global goal indices.  chunk = 0: all goals of the rank in one call.

@@ -62,6 +62,16 @@ int main() {
   CHECK(std::memcmp(od.data(), dj.potential().data(), sizeof(float) * V) == 0);          // bit-identical distances
   CHECK(std::memcmp(op.data(), dj.predecessors().data(), sizeof(uint32_t) * V) == 0);    // bit-exact predecessors
   CHECK(std::fabs(cost - (double)od[robot_v]) < 0.05 * cost + 0.3);                      // path length ~ potential at the robot
+  // pose orientation (dijkstra_mesh_planner.cpp:93-113: calculatePoseFromPosition with the vertex normals): unit quaternions,
+  // x axis along the step, z axis within a few degrees of the up direction of the nearly flat test terrain
+  for (size_t i = 0; i + 1 < plan.size(); ++i) {
+    const Quaternion& q = plan[i].orientation;
+    CHECK(std::fabs(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w - 1.0) < 1e-9);
+    const double xx = 1 - 2 * (q.y * q.y + q.z * q.z), xy = 2 * (q.x * q.y + q.z * q.w), xz = 2 * (q.x * q.z - q.y * q.w);
+    const double zz = 1 - 2 * (q.x * q.x + q.y * q.y);
+    const Vector d = plan[i].direction;
+    CHECK(xx * d.x + xy * d.y + xz * d.z > 0.9 && zz > 0.5);
+  }
   // robot == goal vertex -> SUCCESS with an empty vertex path (dijkstra_mesh_planner.cpp:252-255)
   plan.clear(); CHECK(dj.makePlan(goal, goal, 0.1, plan, cost, msg) == SUCCESS);
   // lethal wall -> NO_PATH_FOUND (:358-362)

@@ -1,12 +1,15 @@
-import sys, time, numpy as np
-sys.path.insert(0,'.')
-from mesh_navigation_b200 import synth
-from mesh_navigation_b200.api import MeshMap, InflationLayer
-from tests.util import disc_lethals
-for n in [int(x) for x in sys.argv[1:]]:
-    pos,faces=synth.grid_mesh(n,n,terrain=True)
-    mm=MeshMap(pos,faces)
-    L=mm.computeLayers(); print(n,"layers ms",L['kernel_ms'],"lethal",int((L['lethal_mask']!=0).sum()), flush=True)
-    le=np.union1d(np.where(L['lethal_mask']!=0)[0], disc_lethals(pos, 1000, 0.3)).astype(np.uint32)
-    t=time.time(); I=InflationLayer(mm).waveCostInflation(le); print(n,"inflate ms",I['kernel_ms'],"wall",time.time()-t,"rounds",I['rounds'],"labelled",int(np.isfinite(I['dist']).sum()),"recomputes",I['recomputes'], flush=True)
-    mm.close()
+"""Dev script (GPU box): inflation wave + device-resident dynamic cycle timing for a given build of the library.
+  python tools/gpu_infl.py <path to .so>"""
+import sys, os, json, subprocess
+lib = os.path.abspath(sys.argv[1])
+code = ("import sys; sys.path.insert(0, '.'); from mesh_navigation_b200 import _lib; _lib.LIB_PATH = %r; sys.argv = ['bench.py', '--batch-goals', '0', '--no-config3', "
+        "'--no-cpu-baseline', '--steps', '3']; import runpy; runpy.run_path('bench.py', run_name='__main__')") % lib
+r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+try:
+    l = json.loads(r.stdout.strip().splitlines()[-1]); o = l["other_kernels"]
+    d = o["dynamic_obstacle_update"]
+    print(os.path.basename(lib), "inflation", round(o["inflation"]["kernel_ms"], 3), "rounds", o["inflation"]["rounds"], "| dynamic total", round(d["total_wall_ms"], 3),
+          "infl_update", round(d["inflation_update_ms"], 3), "kernel", round(d["inflation_kernel_ms"], 3), "layer_changed", round(d["layer_changed_ms"], 3), "equal", d["incremental_equals_full"],
+          "| headline ms", round(l["ms_per_step"], 2), "layers", round(o["fused_layers"]["kernel_ms"], 2), flush=True)
+except Exception as ex:
+    print("failed", ex, r.stdout[-500:], r.stderr[-1500:])
