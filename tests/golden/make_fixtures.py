@@ -62,10 +62,32 @@ def run_case(name):
         at = m.inflation_vector_at(fq, b, i1["dist"], i1["vectors"])
         return dict(vectors0=i0["vectors"], vectors1=i1["vectors"], update_set=upd, final=final, vertex_costs=vc2, edge_weights=w2,
                     vector_at=at)
+    if name.startswith("raycast"):
+        # f3 remainder: ray casting, the obstacle layer's point-cloud update (two clouds in a row) and calcNormalClearance on a
+        # terrain with a tilted roof patch above its middle
+        rpos, rfaces = mesh_case(12, False, seed=5)
+        rpos = rpos.copy(); rpos[:, 0] += 0.9; rpos[:, 1] += 0.9
+        rpos[:, 2] = float(pos[:, 2].max()) + 0.6 + 0.1 * (rpos[:, 0] - 0.9)
+        P = np.vstack([pos, rpos]).astype(np.float32); Fc = np.vstack([faces, rfaces + pos.shape[0]]).astype(np.uint32)
+        mr = O.OracleMesh(P, Fc)
+        o = (P.min(0) - 0.3 + rng.random((300, 3)) * (P.max(0) - P.min(0) + 0.6)).astype(np.float32)
+        d = rng.normal(size=(300, 3)); d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+        d[:60] = np.float32([0, 0, -1]); d[60:80] = np.float32([0, 0, 1]); o[:20] = P[::37][:20] + np.float32([0, 0, 0.5])
+        rc = mr.cast_rays(o, d)
+        mask = np.zeros(mr.V, np.uint8)
+        T = np.float32([[0.96, -0.28, 0, 1.5], [0.28, 0.96, 0, 1.4], [0, 0, 1, float(P[:, 2].mean()) + 1.0]])
+        ax = np.float32([0.06, -0.03, -1.0]); ax = (ax / np.linalg.norm(ax)).astype(np.float32)
+        out = {}
+        for step in range(2):
+            pts = (rng.normal(size=(500, 3)) * np.float32([0.8, 0.8, 0.5])).astype(np.float32)
+            le, ch = mr.obstacle_update(pts, T, ax, 2.0, 0.9, mask)
+            out[f"lethals{step}"] = le; out[f"changed{step}"] = ch
+        vn = mr.layers()["vertex_normals"]
+        return dict(hit=rc["hit"].astype(np.uint32), dist=rc["dist"], face=rc["face"], point=rc["point"], clearance=mr.normal_clearance(vn), **out)
     raise KeyError(name)
 
 
 if __name__ == "__main__":
-    for n in ["cvp_planar30", "cvp_terrain30", "dijkstra_terrain30", "inflation_terrain30", "path_terrain30", "dynamic_terrain30"]:
+    for n in ["cvp_planar30", "cvp_terrain30", "dijkstra_terrain30", "inflation_terrain30", "path_terrain30", "dynamic_terrain30", "raycast_terrain30"]:
         np.savez_compressed(os.path.join(HERE, n + ".npz"), **run_case(n))
         print("wrote", n)

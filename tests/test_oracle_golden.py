@@ -120,7 +120,7 @@ def test_goal_cutoff_and_no_path(oracle_mod):
 
 
 @pytest.mark.parametrize("name", ["cvp_planar30", "cvp_terrain30", "dijkstra_terrain30", "inflation_terrain30", "path_terrain30",
-                                  "dynamic_terrain30"])
+                                  "dynamic_terrain30", "raycast_terrain30"])
 def test_committed_fixtures(oracle_mod, name):
     """Fixtures under tests/golden were generated by tests/golden/make_fixtures.py from this oracle
     (the reference cannot run here); they guard the oracle against silent changes."""
@@ -282,3 +282,34 @@ def test_dijkstra_against_an_independent_implementation(oracle_mod):
         for x in idx:
             a, b = (int(p[x]), int(x)) if p[x] < x else (int(x), int(p[x]))
             assert r["dist"][x] == np.float32(r["dist"][p[x]] + w[ekey[(a, b)]])
+
+
+def test_ray_cast_known_answers(oracle_mod):
+    """hand-computed values for the ray-casting restatement (parity unpinned: lvr2 / Embree are not vendored): a unit right
+    triangle in the plane z = 0 and a parallel copy at z = 2"""
+    O = oracle_mod
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 2], [1, 0, 2], [0, 1, 2]], np.float32)
+    faces = np.array([[0, 1, 2], [3, 4, 5]], np.uint32)
+    m = O.OracleMesh(pos, faces)
+    o = np.array([[0.25, 0.25, 1.0], [0.25, 0.25, 1.0], [0.25, 0.25, 1.0], [0.5, 0.5, 3.0], [0.75, 0.75, 1.0], [0.25, 0.25, 0.0], [0.25, 0.25, -1.0]], np.float32)
+    d = np.array([[0, 0, -1], [0, 0, 1], [1, 0, 0], [0, 0, -1], [0, 0, -1], [0, 0, -1], [0, 0, 1]], np.float32)
+    r = m.cast_rays(o, d)
+    assert r["hit"].tolist() == [1, 1, 0, 1, 0, 1, 1]
+    assert r["face"].tolist()[:2] == [0, 1] and r["dist"][0] == 1.0 and r["dist"][1] == 1.0     # two-sided: hit from above and from below
+    assert np.isinf(r["dist"][2]) and r["face"][2] == 0xffffffff and np.isnan(r["point"][2]).all()   # parallel to both planes
+    assert r["face"][3] == 1 and r["dist"][3] == 1.0                                      # on the hypotenuse of the upper triangle (u + v == 1): the nearest face wins
+    assert r["dist"][5] == 0.0 and r["face"][5] == 0                                       # a point on the surface hits at t = 0
+    assert r["face"][6] == 0 and r["dist"][6] == 1.0 and np.allclose(r["point"][6], [0.25, 0.25, 0.0])
+    # calcNormalClearance: the lower triangle sees the upper one 2 m above along +z; the upper one sees nothing
+    vn = np.tile(np.float32([0, 0, 1]), (6, 1))
+    cl = m.normal_clearance(vn)
+    assert cl[:3].tolist() == [2.0, 2.0, 2.0] and np.isinf(cl[3:]).all()
+    # obstacle layer: points 0.4 m above the lower triangle, robot height 0.5 -> its three vertices; 0.3 -> too far
+    mask = np.zeros(6, np.uint8)
+    T = np.hstack([np.eye(3, dtype=np.float32), np.zeros((3, 1), np.float32)])
+    le, ch = m.obstacle_update(np.float32([[0.2, 0.2, 0.4], [5, 5, 0.4]]), T, np.float32([0, 0, -1]), 10.0, 0.5, mask)
+    assert le.tolist() == [0, 1, 2] and ch.tolist() == [0, 1, 2]
+    le, ch = m.obstacle_update(np.float32([[0.2, 0.2, 0.4]]), T, np.float32([0, 0, -1]), 10.0, 0.3, mask)
+    assert le.size == 0 and ch.tolist() == [0, 1, 2]
+    le, ch = m.obstacle_update(np.float32([[0.2, 0.2, 0.4]]), T, np.float32([0, 0, -1]), 0.3, 0.5, mask)    # beyond max_obstacle_dist
+    assert le.size == 0 and ch.size == 0
