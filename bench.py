@@ -638,17 +638,20 @@ def main():
                 out["inflation_clean_candidate_skip"] = {
                     "kernel_ms": res[1][0], "without_skip_kernel_ms": res[0][0], "recomputes": int(res[1][1]), "without_skip_recomputes": int(res[0][1]),
                     "identical": bool((res[1][2].view(np.uint32) == res[0][2].view(np.uint32)).all())}
-            mm.L.mnb_debug_set_layers_smem(mm._ctx, 0)        # the thread-local walk of round 1 next to the default (prefetching walk)
-            Lb = mm.computeLayers()
-            mm.L.mnb_debug_set_layers_smem(mm._ctx, 2)
+            # the layer walk: round 1's thread-local form (mode 0), the prefetching walk (2) and the default (5: compact seen-set)
+            res = {}
             try:
-                for rep in range(2):
-                    Ls = mm.computeLayers()
-                same = all(bool((Ls[k].view(np.uint32) == Lb[k].view(np.uint32)).all()) for k in ("height_diff", "roughness", "steepness", "ridge", "combined"))
-                out["layers_prefetching_walk_vs_round1_walk"] = {"kernel_ms": Ls["kernel_ms"], "round1_walk_kernel_ms": Lb["kernel_ms"],
-                                                      "hbm_frac": 837 * V / (Ls["kernel_ms"] * 1e-3) / 1e9 / hbm0, "identical": same}
+                for mode in (0, 2, 5):
+                    mm.L.mnb_debug_set_layers_smem(mm._ctx, mode)
+                    for rep in range(2):
+                        res[mode] = mm.computeLayers()
+                same = all(bool((res[m][k].view(np.uint32) == res[0][k].view(np.uint32)).all()) for m in (2, 5)
+                           for k in ("height_diff", "roughness", "steepness", "ridge", "combined"))
+                out["layers_prefetching_walk_vs_round1_walk"] = {
+                    "kernel_ms": res[5]["kernel_ms"], "prefetching_walk_32bit_seen_set_kernel_ms": res[2]["kernel_ms"], "round1_walk_kernel_ms": res[0]["kernel_ms"],
+                    "hbm_frac": 837 * V / (res[5]["kernel_ms"] * 1e-3) / 1e9 / hbm0, "identical": same}
             finally:
-                mm.L.mnb_debug_set_layers_smem(mm._ctx, 2)
+                mm.L.mnb_debug_set_layers_smem(mm._ctx, 5)
             return out
 
         leg("dijkstra_full_field", leg_dijkstra)

@@ -338,6 +338,89 @@ __device__ __forceinline__ void walk_pf(const LayerKernelArgs& a, uint32_t v, fl
   }
 }
 
+// Fourth form: walk_pf with a COMPACT seen-set.  The 704 bytes of shared memory a thread of walk_pf owns (128 x 4-byte hash
+// entries + 48 x 4-byte stack) cap the kernel at 10 resident warps per SM, and it is bound by instruction issue at that
+// occupancy (ncu: 34 % issue utilisation at 15 % active warps).  Vertex ids inside one neighbourhood are close to the centre's
+// id on any mesh whose numbering has spatial locality (scan order, Morton order, most reconstruction outputs), so the hash
+// stores 16-bit codes  n - v + 32768  (0 = empty) and the stack the 8-bit hash slot of the vertex: 304 bytes per thread, 18
+// resident warps.  A neighbour whose id is further than 32767 from the centre's raises `overflow` like a full table does:
+// the vertex is redone by walk_linear -- same traversal order, same sums, so every output stays bit-identical.
+template <int WHICH, int T>
+__device__ __forceinline__ void walk_pf16(const LayerKernelArgs& a, uint32_t v, float radius, float& zmin, float& zmax,
+                                          float& rsum, int& rcnt, float& value, int& num, uint16_t* __restrict__ ht,
+                                          uint8_t* __restrict__ stack) {
+#pragma unroll 8
+  for (int i = 0; i < NB_HASH; ++i) ht[i * T] = 0;
+  const float zmin0 = zmin, zmax0 = zmax, rsum0 = rsum, value0 = value; const int rcnt0 = rcnt, num0 = num;
+  int ns = 0, sp = 0;
+  { const uint32_t h0 = (v * 2654435761u) >> 25; ht[h0 * T] = (uint16_t)32768u; ns = 1; stack[(sp++) * T] = (uint8_t)h0; }
+  const float4 pv = __ldg(&a.pos4[v]), nv = __ldg(&a.vn4[v]);
+  const float px = pv.x, py = pv.y, pz = pv.z;
+  const float nvx = nv.x, nvy = nv.y, nvz = nv.z;
+  const float rx = px + nvx, ry = py + nvy, rz = pz + nvz;
+  bool overflow = false;
+  auto visit = [&](uint32_t n, const float4& q, const float4& nn) {
+    const uint32_t code32 = n - v + 32768u;                       // wraps for n < v; in range <=> 1 <= code32 <= 65535
+    if (code32 - 1u >= 65535u) { overflow = true; return; }
+    const uint16_t code = (uint16_t)code32;
+    uint32_t h = (n * 2654435761u) >> 25;
+    for (;;) {
+      const uint16_t e = ht[h * T];
+      if (e == code) return;
+      if (e == 0) break;
+      h = (h + 1u) & (uint32_t)(NB_HASH - 1);
+    }
+    if (ns >= NB_HSEEN) { overflow = true; return; }
+    ht[h * T] = code; ++ns;
+    const float qx = q.x, qy = q.y, qz = q.z;
+    const float dx = qx - px, dy = qy - py, dz = qz - pz;
+    if (sqrtf(dx * dx + dy * dy + dz * dz) < radius) {
+      if (WHICH & 1) { zmin = fminf(zmin, qz); zmax = fmaxf(zmax, qz); }
+      if (WHICH & 6) {
+        const float nnx = nn.x, nny = nn.y, nnz = nn.z;
+        if (WHICH & 2) {
+          float dot = nvx * nnx + nvy * nny + nvz * nnz;
+          dot = fminf(1.0f, fmaxf(-1.0f, dot));
+          rsum = rsum + acos_f(dot); rcnt++;
+        }
+        if (WHICH & 4) {
+          const float cx = (qx + nnx) - rx, cy = (qy + nny) - ry, cz = (qz + nnz) - rz;
+          value += sqrtf(cx * cx + cy * cy + cz * cz); num++;
+        }
+      }
+      if (sp >= LS_STACK) { overflow = true; return; }
+      stack[(sp++) * T] = (uint8_t)h;
+      mnb_prefetch_l2(a.nbr8 + 2 * (size_t)n);   // its row is needed when it is popped
+    }
+  };
+  while (sp > 0 && !overflow) {
+    const uint32_t u = v + (uint32_t)ht[(uint32_t)stack[(--sp) * T] * T] - 32768u;
+    const uint4 r0 = __ldg(&a.nbr8[2 * (size_t)u]);
+    if (r0.x == NBR8_BIG) {                       // more than 8 neighbours: CSR row, one at a time
+      for (uint32_t k = a.adj_ptr[u]; k < a.adj_ptr[u + 1] && !overflow; ++k) { const uint32_t n = a.adj_nbr[k]; visit(n, __ldg(&a.pos4[n]), __ldg(&a.vn4[n])); }
+      continue;
+    }
+    const uint4 r1 = __ldg(&a.nbr8[2 * (size_t)u + 1]);
+    const uint32_t ids[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    float4 q[8], nn[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {                 // all requests first ...
+      const uint32_t n = ids[j] == NBR8_EMPTY ? v : ids[j];
+      q[j] = __ldg(&a.pos4[n]);
+      if (WHICH & 6) nn[j] = __ldg(&a.vn4[n]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {                 // ... then the sequential part, in the reference's order
+      if (ids[j] == NBR8_EMPTY || overflow) break;
+      visit(ids[j], q[j], nn[j]);
+    }
+  }
+  if (overflow) {
+    zmin = zmin0; zmax = zmax0; rsum = rsum0; value = value0; rcnt = rcnt0; num = num0;
+    walk_linear<WHICH>(a, v, radius, zmin, zmax, rsum, rcnt, value, num);
+  }
+}
+
 // per-vertex layer values from the accumulators of the walks, lethal bits, MaxCombination
 __device__ __forceinline__ void layers_epilogue(const LayerKernelArgs& a, uint32_t v, float zmin, float zmax, float rsum, int rcnt, float value, int num) {
   const mnb_layer_params& P = a.P;
@@ -416,6 +499,28 @@ __global__ void __launch_bounds__(T) k_layers_pf(const LayerKernelArgs a) {
     walk_pf<1, T>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num, ht, stack);
     walk_pf<2, T>(a, v, r_ro, zmin, zmax, rsum, rcnt, value, num, ht, stack);
     walk_pf<4, T>(a, v, r_ri, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+  }
+  layers_epilogue(a, v, zmin, zmax, rsum, rcnt, value, num);
+}
+
+// walk_pf16 with T threads per CTA; dynamic shared memory = (2 * NB_HASH + LS_STACK) * T bytes
+template <int T, int MINB = 1>
+__global__ void __launch_bounds__(T, MINB) k_layers_pf16(const LayerKernelArgs a) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= a.V) return;
+  const mnb_layer_params& P = a.P;
+  const float pz = a.pos[3 * (size_t)v + 2];
+  float zmin = pz, zmax = pz, rsum = 0.0f, value = 0.0f; int rcnt = 0, num = 0;
+  const float r_hd = (float)P.height_diff_radius, r_ro = (float)P.roughness_radius, r_ri = (float)P.ridge_radius;
+  MNB_DYNAMIC_SMEM(ls_raw);
+  uint16_t* ht = reinterpret_cast<uint16_t*>(ls_raw) + threadIdx.x;
+  uint8_t* stack = reinterpret_cast<uint8_t*>(ls_raw) + 2 * NB_HASH * T + threadIdx.x;
+  if (r_hd == r_ro && r_ro == r_ri) {
+    walk_pf16<7, T>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+  } else {
+    walk_pf16<1, T>(a, v, r_hd, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+    walk_pf16<2, T>(a, v, r_ro, zmin, zmax, rsum, rcnt, value, num, ht, stack);
+    walk_pf16<4, T>(a, v, r_ri, zmin, zmax, rsum, rcnt, value, num, ht, stack);
   }
   layers_epilogue(a, v, zmin, zmax, rsum, rcnt, value, num);
 }

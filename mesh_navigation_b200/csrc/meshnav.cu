@@ -77,7 +77,10 @@ struct mnb_ctx {
   float delta = 0.3f; int cluster = -1 /* -1: whole-grid cooperative kernel for single plans */; int batch_cluster = 0 /* 0: chosen per call from the goal count */; int threads = 512;
   int grid_blocks_per_sm = 0;
   int infl_skip_clean = 1;     // clean-candidate skip of the inflation wave (MNB_INFL_SKIP=0 turns it off)
-  int layers_smem = 2;         // neighbourhood walk of k_layers: 0 thread-local seen-set, 1 shared-memory seen-set, 2-4 prefetching walk (64 / 128 / 32 threads per CTA); 2 measured fastest on the B200 (6.1 vs 9.6 ms at 5M vertices)
+  int layers_smem = 5;         // neighbourhood walk of k_layers: 0 thread-local seen-set, 1 shared-memory seen-set, 2-4 prefetching walk (64 / 128 / 32
+                               // threads per CTA), 5-7 the same with the 16-bit seen-set (64 / 128 / 256), 8-9 its low-register builds.  5 M vertices on
+                               // the B200: 8.4 / - / 6.9 / ... / 5.1 ms for modes 0 / 2 / 5.  Chosen per mesh by mnb_set_mesh unless fixed by the caller.
+  bool layers_explicit = false;
   int skip_clean = 0;          // clean-candidate skip of the CVP kernels (band_engine.cuh): bit-identical on the kernel interpreter,
                                // not yet timed on a B200 -> opt-in (MNB_SKIP_CLEAN=1 / mnb_debug_set_skip_clean)
   int sweeps = -1;             // in-round sweeps of the whole-grid single-plan kernel; -1 = derived from the band width
@@ -181,7 +184,7 @@ int32_t mnb_create(int32_t device, mnb_ctx** out_ctx) {
   mnb_ctx* c = new mnb_ctx();
   c->device = device; c->sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("MNB_INFL_SKIP")) c->infl_skip_clean = atoi(e) != 0;                                 // experiment knob
-  if (const char* e = getenv("MNB_LAYERS_SMEM")) c->layers_smem = atoi(e);                                   // experiment knob
+  if (const char* e = getenv("MNB_LAYERS_SMEM")) { c->layers_smem = atoi(e); c->layers_explicit = true; }                                   // experiment knob
   if (const char* e = getenv("MNB_SKIP_CLEAN")) c->skip_clean = atoi(e) != 0;                                     // experiment knob
   if (const char* e = getenv("MNB_GRID_ENGINE")) c->grid_engine = atoi(e);                                     // experiment knob
   if (const char* e = getenv("MNB_GRID2_DELTA_W")) { const float k = (float)atof(e); if (k > 0) c->grid2_delta_w = k; }
@@ -251,6 +254,13 @@ static int32_t impl_set_mesh(mnb_ctx* ctx, uint32_t V, uint32_t F, const float* 
     return MNB_E_ARG;
   }
   HostTopology& T = ctx->topo;
+  if (!ctx->layers_explicit) {
+    // the compact seen-set of the layer walk (walk_pf16) holds ids within +-32767 of the centre's: a neighbourhood reaches a
+    // few edges out, so it pays when edges connect nearby ids (scan / Morton numbering); otherwise the 32-bit form
+    uint32_t maxd = 0;
+    for (size_t e = 0; e < (size_t)T.E; ++e) { const uint32_t a = T.edges[2 * e], b = T.edges[2 * e + 1]; maxd = std::max(maxd, a > b ? a - b : b - a); }
+    ctx->layers_smem = (maxd <= 8000u) ? 5 : 2;
+  }
   ctx->V = V; ctx->F = F; ctx->E = T.E; ctx->NC = T.cor_v1.size(); ctx->NA = T.vadj_nbr.size();
   const size_t NC = ctx->NC, NA = ctx->NA;
   CK(dalloc(&ctx->d_pos, 3 * (size_t)V)); CK(dalloc(&ctx->d_faces, 3 * (size_t)F)); CK(dalloc(&ctx->d_edges, 2 * (size_t)T.E));
@@ -787,6 +797,19 @@ static int32_t impl_compute_layers(mnb_ctx* ctx, const mnb_layer_params* params,
       CK(cudaGetLastError());
     }
     a.pos4 = ctx->d_pos4; a.vn4 = ctx->d_vn4; a.nbr8 = reinterpret_cast<const uint4*>(ctx->d_nbr8);
+    if (ctx->layers_smem == 8 || ctx->layers_smem == 9) {      // walk_pf16 compiled for more resident CTAs (fewer registers): 8 -> 64 x 12, 9 -> 128 x 6
+      const int T = ctx->layers_smem == 8 ? 64 : 128;
+      const size_t smem = (size_t)(2 * NB_HASH + LS_STACK) * T;
+      if (T == 64) { CK(cudaFuncSetAttribute(k_layers_pf16<64, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); MNB_LAUNCH((k_layers_pf16<64, 12>), (ctx->V + 63) / 64, 64, smem, ctx->stream, a); }
+      else { CK(cudaFuncSetAttribute(k_layers_pf16<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); MNB_LAUNCH((k_layers_pf16<128, 6>), (ctx->V + 127) / 128, 128, smem, ctx->stream, a); }
+    } else
+    if (ctx->layers_smem >= 5) {            // walk_pf16 (16-bit seen-set): 5 -> 64 threads per CTA, 6 -> 128, 7 -> 256
+      const int T = ctx->layers_smem == 5 ? 64 : (ctx->layers_smem == 6 ? 128 : 256);
+      const size_t smem = (size_t)(2 * NB_HASH + LS_STACK) * T;
+      if (T == 64) { CK(cudaFuncSetAttribute(k_layers_pf16<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); MNB_LAUNCH(k_layers_pf16<64>, (ctx->V + 63) / 64, 64, smem, ctx->stream, a); }
+      else if (T == 128) { CK(cudaFuncSetAttribute(k_layers_pf16<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); MNB_LAUNCH(k_layers_pf16<128>, (ctx->V + 127) / 128, 128, smem, ctx->stream, a); }
+      else { CK(cudaFuncSetAttribute(k_layers_pf16<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); MNB_LAUNCH(k_layers_pf16<256>, (ctx->V + 255) / 256, 256, smem, ctx->stream, a); }
+    } else
     if (ctx->layers_smem >= 2) {            // walk_pf: 2 -> 64 threads per CTA, 3 -> 128, 4 -> 32
       const int T = ctx->layers_smem == 2 ? 64 : (ctx->layers_smem == 3 ? 128 : 32);
       const size_t smem = sizeof(uint32_t) * (size_t)(NB_HASH + LS_STACK) * T;
@@ -927,7 +950,7 @@ int32_t mnb_debug_set_sweeps(mnb_ctx* ctx, int32_t k) { if (!ctx || k < -1 || k 
 
 int32_t mnb_debug_set_grid_engine(mnb_ctx* ctx, int32_t mode, float delta_w) { if (!ctx) return MNB_E_ARG; ctx->grid_engine = mode; if (delta_w > 0) ctx->grid2_delta_w = delta_w; return MNB_OK; }
 int32_t mnb_debug_set_infl_skip(mnb_ctx* ctx, int32_t on) { if (!ctx) return MNB_E_ARG; ctx->infl_skip_clean = on != 0; return MNB_OK; }
-int32_t mnb_debug_set_layers_smem(mnb_ctx* ctx, int32_t mode) { if (!ctx || mode < 0 || mode > 4) return MNB_E_ARG; ctx->layers_smem = mode; return MNB_OK; }
+int32_t mnb_debug_set_layers_smem(mnb_ctx* ctx, int32_t mode) { if (!ctx || mode < 0 || mode > 9) return MNB_E_ARG; ctx->layers_smem = mode; ctx->layers_explicit = true; return MNB_OK; }
 int32_t mnb_debug_set_skip_clean(mnb_ctx* ctx, int32_t on) { if (!ctx) return MNB_E_ARG; ctx->skip_clean = on != 0; ctx->grid_blocks_per_sm = 0; return MNB_OK; }
 
 // debugging aid (not part of the public header): raw labels {d, a1, a2, a3|flag} of wavefront group 0

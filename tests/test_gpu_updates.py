@@ -258,7 +258,12 @@ def test_layers_shared_memory_variant_is_identical(api, oracle_mod):
     output is bit-identical to the default kernel, including on an irregular mesh whose hub overflows into the fallback"""
     import ctypes as C
     from tests.util import delaunay_mesh
-    for pos, faces in (mesh_case(70, True), delaunay_mesh(1500, seed=5)):
+    # third mesh: a 200 x 200 terrain with randomly permuted vertex ids -- neighbour ids differ by up to 40 000, beyond the
+    # 16-bit codes of modes 5-7, so their per-vertex fallback runs next to the compact path
+    p3, f3 = mesh_case(200, True)
+    perm = np.random.default_rng(9).permutation(p3.shape[0]).astype(np.uint32)
+    q3 = np.empty_like(p3); q3[perm] = p3
+    for pos, faces in (mesh_case(70, True), delaunay_mesh(1500, seed=5), (q3, perm[f3])):
         mm = api.MeshMap(pos, faces)
         mm.L.mnb_debug_set_layers_smem.argtypes = [C.c_void_p, C.c_int32]
         P = api._lib.LayerParams.defaults()
@@ -266,7 +271,7 @@ def test_layers_shared_memory_variant_is_identical(api, oracle_mod):
         base = mm.computeLayers(P)
         P2 = api._lib.LayerParams.defaults(); P2.roughness_radius = 0.2; P2.ridge_radius = 0.45      # three separate walks
         b2 = mm.computeLayers(P2)
-        for mode in (1, 2, 3, 4):        # 1: shared-memory seen-set; 2-4: the prefetching walk with 64 / 128 / 32 threads per CTA
+        for mode in (1, 2, 3, 4, 5, 6, 7, 8, 9):   # 1: shared-memory seen-set; 2-4: the prefetching walk with 64 / 128 / 32 threads per CTA; 5-7: 16-bit seen-set, 64 / 128 / 256
             mm.L.mnb_debug_set_layers_smem(mm._ctx, mode)
             got = mm.computeLayers(P)
             for k in list(api._lib.LAYER_NAMES) + ["combined"]:

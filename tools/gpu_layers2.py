@@ -10,7 +10,7 @@ pos, faces = synth.grid_mesh(n, n, terrain=True, seed=42)
 mm = MeshMap(pos, faces)
 mm.L.mnb_debug_set_layers_smem.argtypes = [C.c_void_p, C.c_int32]
 base = None
-for mode in (0, 1, 2, 3, 4, 2, 0):
+for mode in (0, 2, 5, 6, 7, 8, 9, 2, 5):
     mm.L.mnb_debug_set_layers_smem(mm._ctx, mode)
     best = 1e9
     for it in range(3):
