@@ -313,3 +313,36 @@ def test_ray_cast_known_answers(oracle_mod):
     assert le.size == 0 and ch.tolist() == [0, 1, 2]
     le, ch = m.obstacle_update(np.float32([[0.2, 0.2, 0.4]]), T, np.float32([0, 0, -1]), 0.3, 0.5, mask)    # beyond max_obstacle_dist
     assert le.size == 0 and ch.size == 0
+
+
+@pytest.mark.parametrize("case", ["geometric", "cost_weighted", "walls_and_cutoff"])
+def test_cvp_against_an_independent_restatement(oracle_mod, case):
+    """the C++ oracle against tests/cvp_reference_py.py -- a second restatement of CVPMeshPlanner::waveFrontPropagation written
+    in plain Python straight from the reference source: potentials, predecessors, directions and cutting faces must agree to
+    the last bit (both evaluate the update in double with libm's sqrt / acos and store floats)"""
+    from tests.cvp_reference_py import wave_front_propagation
+    O = oracle_mod
+    pos, faces = mesh_case(26, True)
+    m = O.OracleMesh(pos, faces)
+    ed = m.edge_distances()
+    rng = np.random.default_rng({"geometric": 1, "cost_weighted": 2, "walls_and_cutoff": 3}[case])
+    vc = np.zeros(m.V, np.float32); w = ed; inv = None; robot = -1; cl = 1.0
+    v, f, sp = centre_seed(pos, faces, (0.35, 0.6))
+    if case != "geometric":
+        vc = (rng.random(m.V) * 0.7).astype(np.float32)
+        w = m.edge_weights(vc, ed, 2.5)                          # non-causal updates: back-steps occur
+    if case == "walls_and_cutoff":
+        vc[rng.random(m.V) < 0.12] = 1.5                         # over the cost limit
+        inv = (rng.random(m.V) < 0.03).astype(np.uint8)
+        for x in faces[f]:
+            vc[x] = 0.1; inv[x] = 0
+        w = m.edge_weights(vc, ed, 1.0)
+        rv, robot, rp = centre_seed(pos, faces, (0.8, 0.25))
+    ref = m.cvp(w, vc, f, sp, robot_face=robot, cost_limit=cl, invalid=inv)
+    got = wave_front_propagation(pos, faces, m.edges, w, vc, f, sp, robot_face=robot, invalid=inv, cost_limit=cl)
+    assert (got["dist"].view(np.uint32) == ref["dist"].view(np.uint32)).all()
+    assert (got["pred"] == ref["pred"]).all()
+    assert (got["cutting_face"] == ref["cutting_face"].astype(np.int64)).all()
+    assert (got["direction"].view(np.uint32) == ref["direction"].view(np.uint32)).all()
+    if case != "geometric":
+        assert ref.get("backsteps", 1) > 0
