@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.util import centre_seed, mesh_case
+from tests.util import centre_seed, mesh_case, disc_lethals
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -346,3 +346,25 @@ def test_cvp_against_an_independent_restatement(oracle_mod, case):
     assert (got["direction"].view(np.uint32) == ref["direction"].view(np.uint32)).all()
     if case != "geometric":
         assert ref.get("backsteps", 1) > 0
+
+
+@pytest.mark.parametrize("case", ["discs", "discs_and_invalid", "wide_radius"])
+def test_inflation_against_an_independent_restatement(oracle_mod, case):
+    """the C++ oracle against tests/inflation_reference_py.py -- a second restatement of InflationLayer::waveCostInflation
+    (Sethian update, fallback, fading, the heap loop with never-fixed invalid vertices) in plain Python from the reference
+    source: distances and riskiness values must agree to the last bit"""
+    from tests.inflation_reference_py import wave_cost_inflation
+    O = oracle_mod
+    pos, faces = mesh_case(28, True)
+    m = O.OracleMesh(pos, faces)
+    ed = m.edge_distances()
+    rng = np.random.default_rng(4)
+    le = disc_lethals(pos, 3, 0.22, seed=9)
+    inv = (rng.random(m.V) < 0.05).astype(np.uint8) if case == "discs_and_invalid" else None
+    kw = dict(inscribed_radius=0.3, inflation_radius=0.9, cost_scaling_factor=2.0) if case == "wide_radius" else {}
+    ref = m.inflation(ed, le, invalid=inv, **kw)
+    got = wave_cost_inflation(pos, faces, m.edges, ed, le, invalid=inv, **kw)
+    assert (got["dist"].view(np.uint32) == ref["dist"].view(np.uint32)).all()
+    both_nan = np.isnan(got["cost"]) & np.isnan(ref["cost"])
+    assert ((got["cost"].view(np.uint32) == ref["cost"].view(np.uint32)) | both_nan).all()
+    assert np.isfinite(ref["dist"]).sum() > le.size + 50
