@@ -88,8 +88,9 @@ struct mnb_ctx {
   float dijkstra_grid_delta = 3.0f;
   // The band widths above are potentials, i.e. multiples of the edge weights: unless the caller fixed them (mnb_set_tuning
   // with band_delta > 0) they follow the mean finite edge weight w of the installed weights -- 2.5 w for batches, 20 w for a
-  // single CVP plan, 25 w for a single Dijkstra plan; one dependency hop is ~1.35 w (the in-round sweeps are counted in
-  // hops).  On the 0.1 m bench meshes (w = 0.118) that is 0.3 / 2.4 / 3.0 m, the values the kernels were tuned with.
+  // single CVP plan, 25 w for a single Dijkstra plan, less on maps above ~12 M vertices (install_weights); one dependency hop is
+  // ~1.35 w (the in-round sweeps are counted in hops).  On the 0.1 m bench meshes (w = 0.118) that is 0.3 / 2.4 / 3.0 m, the values
+  // the kernels were tuned with.
   bool delta_explicit = false; float w_mean = 0.0f; double* d_wsum = nullptr;
   int grid_engine = 0;         // experiment: 1 = full-field single plans run the lean batch round loop on the whole grid (k_cvp_batch<0>)
   float grid2_delta_w = 2.5f;  //             its band width in mean edge weights
@@ -349,7 +350,18 @@ static int32_t install_weights(mnb_ctx* ctx) {
   CK(cudaMemcpyAsync(hs, ctx->d_wsum, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->w_mean = hs[1] > 0 ? (float)(hs[0] / hs[1]) : 0.0f;
-  if (!ctx->delta_explicit && ctx->w_mean > 0) { ctx->delta = 2.5f * ctx->w_mean; ctx->grid_delta = 20.0f * ctx->w_mean; ctx->dijkstra_grid_delta = 25.0f * ctx->w_mean; }
+  if (!ctx->delta_explicit && ctx->w_mean > 0) {
+    // Single plans: the band should hold about as many candidates as the grid has sweep slots (SM count x Stage::SW_CAP);
+    // beyond that the in-round sweeps cannot follow and the band's rows fall out of the L2.  A front is ~3 sqrt(V) vertices
+    // long on a compact map and a hop is ~1.35 w deep.  5 M vertices: 20 w / 25 w (the values the kernels were tuned with);
+    // 50 M: 9.6 w -- measured there: CVP 342 -> 232 ms, Dijkstra 178 -> 98 ms against the fixed 20 w / 25 w.
+    const float slots = (float)ctx->sm_count * (float)Stage::SW_CAP;
+    const float hops = slots / (3.0f * sqrtf((float)ctx->V));
+    const float k = fmaxf(4.0f, 1.35f * hops);
+    ctx->delta = 2.5f * ctx->w_mean;
+    ctx->grid_delta = fminf(20.0f, k) * ctx->w_mean;
+    ctx->dijkstra_grid_delta = fminf(25.0f, k) * ctx->w_mean;
+  }
   ctx->costs_set = true;
   return MNB_OK;
 }
