@@ -89,6 +89,40 @@ for case in range(N):
         ri = om.inflation(ed, le); gi = infl.onInputChanged(le)
         upd = O.inflation_update_set(ri["cost"], old); old = ri["cost"]
         if not np.array_equal(gi["changed"], upd): msg.append(f"inflation update set {it} differs")
+    # ---- ray casting, obstacle layer, normal clearance (a tilted roof patch is added for a third of the cases)
+    rpos, rfaces = pos, faces
+    if r.integers(3) == 0:
+        m = int(r.integers(6, 14))
+        qp, qf = synth.grid_mesh(m, m, terrain=False, seed=int(r.integers(1 << 30)))
+        qp = qp.copy(); ctr = pos[:, :2].mean(0)
+        qp[:, 0] += ctr[0] - 0.05 * m; qp[:, 1] += ctr[1] - 0.05 * m
+        qp[:, 2] = float(pos[:, 2].max()) + float(r.random() * 1.0 + 0.2) + float(r.normal() * 0.2) * (qp[:, 0] - ctr[0])
+        rpos = np.vstack([pos, qp]).astype(np.float32); rfaces = np.vstack([faces, qf + pos.shape[0]]).astype(np.uint32)
+    omr = O.OracleMesh(rpos, rfaces) if rpos is not pos else om
+    mr = api.MeshMap(rpos, rfaces) if rpos is not pos else mm
+    nr = 150
+    lo, hi = rpos.min(0) - 0.3, rpos.max(0) + 0.3
+    ro = (lo + r.random((nr, 3)) * (hi - lo)).astype(np.float32)
+    rd = r.normal(size=(nr, 3)); rd = (rd / np.linalg.norm(rd, axis=1, keepdims=True)).astype(np.float32)
+    rd[:40] = np.float32([0, 0, -1]); ro[:15] = rpos[r.integers(rpos.shape[0], size=15)] + np.float32([0, 0, 0.6])
+    gr, rr = mr.castRays(ro, rd), omr.cast_rays(ro, rd)
+    if (gr["hit"] != rr["hit"]).any() or (gr["face"] != rr["face"]).any() or (gr["dist"].view(np.uint32) != rr["dist"].view(np.uint32)).any() \
+            or (gr["point"].view(np.uint32) != rr["point"].view(np.uint32)).any():
+        msg.append(f"ray cast differs ({int((gr['face'] != rr['face']).sum())} faces)")
+    ol = api.ObstacleLayer(mr, robot_height=float(r.choice([0.3, 0.8, 5.0])), max_obstacle_dist=float(r.choice([1.5, 4.0])))
+    mask = np.zeros(omr.V, np.uint8)
+    for it in range(2):
+        npts = int(r.integers(0, 400))
+        pts = (r.normal(size=(npts, 3)) * np.float32([1.0, 1.0, 0.5])).astype(np.float32)
+        ang = float(r.random() * 6.28)
+        T = np.float32([[np.cos(ang), -np.sin(ang), 0, rpos[:, 0].mean()], [np.sin(ang), np.cos(ang), 0, rpos[:, 1].mean()], [0, 0, 1, rpos[:, 2].max() + 0.5]])
+        ax = np.float32([r.normal() * 0.05, r.normal() * 0.05, -1.0]); ax = (ax / np.linalg.norm(ax)).astype(np.float32)
+        rle, rch = omr.obstacle_update(pts, T, ax, ol.config.max_obstacle_dist, ol.config.robot_height, mask)
+        go = ol.processPointCloud(pts, T, ax)
+        if not np.array_equal(go["lethals"], rle) or not np.array_equal(go["changed"], rch): msg.append(f"obstacle update {it} differs")
+    gvn = mr.vertexNormals()
+    if (mr.normalClearance(gvn).view(np.uint32) != omr.normal_clearance(gvn).view(np.uint32)).any(): msg.append("normal clearance differs")
+    if mr is not mm: mr.close()
     print(f"case {case}: {kind} V={V}: " + ("ok" if not msg else "MISMATCH " + "; ".join(msg)), flush=True)
     bad += bool(msg)
     mm.close(); fresh.close()
