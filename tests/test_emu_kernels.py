@@ -25,7 +25,7 @@ GROUPS = [
     (PARITY, "irregular or disconnected or vector_maps or backtrack or make_plan or locate"),
     (PARITY, "cancel"),
     ("test_gpu_group.py", "sharded_batch"),
-    ("test_gpu_raycast.py", "cast_rays or obstacle_layer or normal_clearance"),
+    ("test_gpu_raycast.py", "cast_rays or obstacle_layer or obstacle_update or normal_clearance"),
     ("test_gpu_updates.py", "layer_changed or max_combination or on_input_changed or vector_field or repulsive or clean_candidate or shared_memory_variant or high_degree or edge_cases or goal_cutoff_armed or deeply_nested or backstep_deep or seed_pops_after or never_fixed or batch_engine or abi_argument"),
 ]
 # the same tests under a randomised warp schedule (MNB_EMU_SHUFFLE, see tests/emu/cuda_runtime.h): warps are visited in a

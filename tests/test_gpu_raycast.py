@@ -158,3 +158,41 @@ def test_normal_clearance_and_clearance_layer(api, oracle_mod):
     assert (L["lethal_mask"] == R["lethal_mask"]).all()
     assert int((L["clearance"] == 1.0).sum()) > 20
     mm.close()
+
+
+def test_obstacle_update_with_device_resident_arrays(api, oracle_mod):
+    """MNB_PTR_DEVICE: the cloud, the lethal list and the changed list stay on the device (what a device-resident layer stack
+    feeds into mnb_inflation_update); only the two counts come back.  Same sets as the host-pointer call and as the oracle."""
+    import ctypes as C
+    pos, faces = two_storey()
+    om = oracle_mod.OracleMesh(pos, faces); mm = api.MeshMap(pos, faces)
+    rng = np.random.default_rng(4)
+    pts = (rng.normal(size=(3000, 3)) * np.array([1.0, 1.0, 0.5])).astype(np.float32)
+    centre = pos[:, :2].mean(0)
+    T = np.float32([[1, 0, 0, centre[0]], [0, 1, 0, centre[1]], [0, 0, 1, float(pos[:, 2].mean()) + 1.0]])
+    ax = np.float32([0, 0, -1])
+    mask = np.zeros(om.V, np.uint8)
+    ref_le, ref_ch = om.obstacle_update(pts, T, ax, 3.0, 0.9, mask)
+    try:
+        import torch
+        on_gpu = torch.cuda.is_available()
+    except Exception:
+        on_gpu = False
+    if on_gpu:      # a real device: torch owns the buffers
+        d_pts = torch.from_numpy(pts).cuda(); d_le = torch.empty(om.V, dtype=torch.int32, device="cuda"); d_ch = torch.empty(om.V, dtype=torch.int32, device="cuda")
+        ptr = lambda t: C.c_void_p(t.data_ptr()); back = lambda t, n: t[:n].cpu().numpy().view(np.uint32)
+    else:           # the CPU interpreter of the kernels: "device" memory is host memory
+        d_pts = pts.copy(); d_le = np.empty(om.V, np.uint32); d_ch = np.empty(om.V, np.uint32)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p); back = lambda a, n: a[:n].copy()
+    cfg = api._lib.ObstacleParams(); cfg.max_obstacle_dist = 3.0; cfg.robot_height = 0.9
+    cfg.tf[:] = [float(x) for x in T.reshape(-1)]; cfg.down_axis[:] = [0.0, 0.0, -1.0]
+    assert mm.L.mnb_obstacle_reset(mm._ctx) == 0
+    nl, nc = C.c_uint32(0), C.c_uint32(0)
+    mm.use_device_pointers(True)
+    try:
+        rc = mm.L.mnb_obstacle_update(mm._ctx, pts.shape[0], ptr(d_pts), C.byref(cfg), ptr(d_le), C.byref(nl), ptr(d_ch), C.byref(nc), None)
+    finally:
+        mm.use_device_pointers(False)
+    assert rc == 0
+    assert np.array_equal(back(d_le, nl.value), ref_le) and np.array_equal(back(d_ch, nc.value), ref_ch) and ref_le.size > 50
+    mm.close()
