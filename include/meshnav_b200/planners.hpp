@@ -373,4 +373,58 @@ class InflationLayer {
   std::vector<float> riskiness_, distances_;
 };
 
+// mesh_layers::ObstacleLayer (mesh_layers/src/obstacle_layer.cpp) without the ROS plumbing: the lethal set of the latest
+// point cloud; costs: +inf on lethal vertices, no entry (NaN) elsewhere, defaultValue() 0, threshold() +inf.
+class ObstacleLayer {
+ public:
+  struct {                                                           // obstacle_layer.h:142-151
+    double robot_height = std::numeric_limits<double>::infinity();
+    double max_obstacle_dist = std::numeric_limits<double>::infinity();
+    Vector down_axis{0.0f, 0.0f, -1.0f};                             // normalised at configuration time (obstacle_layer.cpp:110)
+  } config_;
+  explicit ObstacleLayer(const std::shared_ptr<MeshMap>& map) : map_(map) { mnb_obstacle_reset(map_->ctx()); }
+
+  // ObstacleLayer::processPointCloud (obstacle_layer.cpp:133-296): `points` in the message frame, `tf` the row-major 3x4
+  // [R|t] into the map frame (:176-180), `axis_in_map` the down axis rotated into the map frame (:183-205).  `changed`
+  // receives what notifyChange is called with (:268-296).
+  bool processPointCloud(const std::vector<float>& points, const std::array<float, 12>& tf, const Vector& axis_in_map,
+                         std::vector<uint32_t>& changed) {
+    mnb_obstacle_params p{};
+    p.max_obstacle_dist = config_.max_obstacle_dist; p.robot_height = config_.robot_height;
+    for (int k = 0; k < 12; ++k) p.tf[k] = tf[k];
+    p.down_axis[0] = axis_in_map.x; p.down_axis[1] = axis_in_map.y; p.down_axis[2] = axis_in_map.z;
+    const uint32_t V = map_->numVertices();
+    lethals_.assign(V, 0u); changed.assign(V, 0u); costs_.assign(V, 0.0f);
+    uint32_t nl = 0, nc = 0;
+    if (mnb_obstacle_update(map_->ctx(), (uint32_t)(points.size() / 3), points.data(), &p, lethals_.data(), &nl, changed.data(), &nc,
+                            costs_.data()) != MNB_OK) return false;
+    lethals_.resize(nl); changed.resize(nc);
+    return true;
+  }
+  const std::vector<uint32_t>& lethals() const { return lethals_; }   // ascending (std::set order)
+  const std::vector<float>& costs() const { return costs_; }          // NaN = no entry
+  float defaultValue() const { return 0.0f; }                         // obstacle_layer.h:80
+  float threshold() const { return std::numeric_limits<float>::infinity(); }   // :89
+
+ private:
+  std::shared_ptr<MeshMap> map_;
+  std::vector<uint32_t> lethals_;
+  std::vector<float> costs_;
+};
+
+// MeshMap::raycaster()->castRays (mesh_map.h:318, obstacle_layer.cpp:239) and lvr2::calcNormalClearance
+// (clearance_layer.cpp:161) on the device BVH
+struct RayCastResult { std::vector<uint8_t> hit; std::vector<float> dist; std::vector<uint32_t> face; std::vector<float> point; };
+inline bool castRays(MeshMap& map, const std::vector<float>& origins, const std::vector<float>& dirs, RayCastResult& out) {
+  const uint32_t n = (uint32_t)(origins.size() / 3);
+  if (dirs.size() != 3 && dirs.size() != origins.size()) return false;
+  out.hit.assign(n, 0); out.dist.assign(n, 0.0f); out.face.assign(n, 0u); out.point.assign(3 * (size_t)n, 0.0f);
+  return mnb_cast_rays(map.ctx(), n, origins.data(), dirs.data(), dirs.size() == 3 && n != 1 ? 0u : 3u, out.hit.data(), out.dist.data(),
+                       out.face.data(), out.point.data()) == MNB_OK;
+}
+inline bool calcNormalClearance(MeshMap& map, std::vector<float>& clearance) {
+  clearance.assign(map.numVertices(), 0.0f);
+  return mnb_normal_clearance(map.ctx(), nullptr, clearance.data()) == MNB_OK;
+}
+
 }  // namespace meshnav_b200

@@ -22,6 +22,8 @@ int32_t orc_cvp_backtrack(void* h, const float* vector_map, const float start[3]
 uint32_t orc_cvp(void* h, const float* edge_weights, const float* vertex_costs, const uint8_t* invalid, uint32_t seed_face,
                  const float* seed_pos, int64_t robot_face, double cost_limit, double goal_dist_offset, int canonical_ties,
                  float* distances, uint32_t* predecessors, float* direction, int32_t* cutting_faces, double* stats);
+void orc_obstacle_update(void* h, uint32_t n, const float* points, const float* tf, const float* axis, double max_obstacle_dist,
+                         double robot_height, uint8_t* lethal_mask, uint8_t* changed_mask);
 }
 
 using namespace meshnav_b200;
@@ -156,6 +158,36 @@ int main() {
     CHECK(mnb_dijkstra(map->ctx(), seed_v, -1, 2.0, 0.3, d1.data(), p1.data()) == 0);
     CHECK(mnb_dijkstra(fresh->ctx(), seed_v, -1, 2.0, 0.3, d2.data(), p2.data()) == 0);
     CHECK(std::memcmp(d1.data(), d2.data(), sizeof(float) * V) == 0 && p1 == p2);
+  }
+  // ---- ObstacleLayer::processPointCloud, the shared raycaster, calcNormalClearance (f3 remainder) ----
+  {
+    ObstacleLayer obst(map);
+    obst.config_.robot_height = 0.6; obst.config_.max_obstacle_dist = 4.0;
+    std::vector<float> cloud;                                     // returns 0.3 m above the surface around (3, 3), in the frame of a sensor at (3, 3, 2)
+    for (uint32_t v = 0; v < V; ++v)
+      if (std::hypot(pos[3 * v] - 3.0f, pos[3 * v + 1] - 3.0f) < 0.3f) { cloud.push_back(pos[3 * v] - 3.0f); cloud.push_back(pos[3 * v + 1] - 3.0f); cloud.push_back(pos[3 * v + 2] + 0.3f - 2.0f); }
+    CHECK(cloud.size() >= 3 * 20);
+    const std::array<float, 12> tf = {1, 0, 0, 3.0f, 0, 1, 0, 3.0f, 0, 0, 1, 2.0f};
+    std::vector<uint32_t> changed;
+    CHECK(obst.processPointCloud(cloud, tf, Vector{0.0f, 0.0f, -1.0f}, changed));
+    CHECK(obst.lethals().size() > 20 && obst.lethals().size() < 200 && changed == obst.lethals());
+    for (uint32_t v : obst.lethals()) { CHECK(std::hypot(pos[3 * v] - 3.0f, pos[3 * v + 1] - 3.0f) < 0.7f); CHECK(std::isinf(obst.costs()[v])); }
+    // the oracle's loop over all faces marks the same set
+    std::vector<uint8_t> mask(V, 0), chg(V, 0);
+    const float ax[3] = {0, 0, -1};
+    orc_obstacle_update(om, (uint32_t)(cloud.size() / 3), cloud.data(), tf.data(), ax, 4.0, 0.6, mask.data(), chg.data());
+    size_t nref = 0; for (uint32_t v = 0; v < V; ++v) nref += mask[v];
+    CHECK(nref == obst.lethals().size());
+    for (uint32_t v : obst.lethals()) CHECK(mask[v]);
+    std::vector<float> empty;                                     // an empty cloud clears the set: everything changes back
+    CHECK(obst.processPointCloud(empty, tf, Vector{0.0f, 0.0f, -1.0f}, changed) && obst.lethals().empty() && changed.size() == nref);
+    RayCastResult rc;
+    CHECK(castRays(*map, {3.0f, 3.0f, 5.0f, 100.0f, 100.0f, 5.0f}, {0.0f, 0.0f, -1.0f}, rc));
+    CHECK(rc.hit[0] == 1 && rc.hit[1] == 0 && rc.dist[0] > 3.0f && rc.dist[0] < 7.0f && std::fabs(rc.point[0] - 3.0f) < 1e-5f);
+    std::vector<float> clearance;
+    CHECK(calcNormalClearance(*map, clearance));
+    size_t open_sky = 0; for (uint32_t v = 0; v < V; ++v) open_sky += std::isinf(clearance[v]);
+    CHECK(open_sky > V * 9 / 10);                                 // a terrain without overhangs: (almost) nothing above a vertex
   }
   orc_mesh_destroy(om);
   std::printf("cpp host mirror ok: dijkstra bit-exact, cvp max rel %.2e, %zu inflated vertices\n", maxrel, inflated);
