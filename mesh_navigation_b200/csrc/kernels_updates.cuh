@@ -85,6 +85,7 @@ __global__ void k_refresh_weight_tables(const RefreshArgs a) {
       }
     }
   }
+  if (!a.adj_nw) return;                       // the adjacency tables are stale as a whole: the next Dijkstra call rebuilds them
   const uint32_t ab = a.adj_ptr[v];
   for (uint32_t k = ab + j; k < a.adj_ptr[v + 1]; k += ELL_W) {
     const uint32_t u = a.adj_nbr[k];

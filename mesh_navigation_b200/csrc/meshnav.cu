@@ -46,6 +46,7 @@ struct mnb_ctx {
   uint32_t* d_adj_ptr = nullptr; uint32_t* d_adj_nbr = nullptr; uint32_t* d_adj_eid = nullptr; uint2* d_adj_nw = nullptr; uint4* d_ell_adj = nullptr;
   float* d_edge_dist = nullptr; float* d_edge_w = nullptr; float* d_cost = nullptr; uint8_t* d_invalid = nullptr;
   bool has_invalid = false, costs_set = false;
+  bool adj_dirty = true;       // the Dijkstra planner's weight tables (adj_nw, ell_adj) are rebuilt on its first call after new weights
   // workspace
   uint32_t ws_groups = 0;
   WaveWorkspace ws{};
@@ -338,8 +339,7 @@ static int32_t install_weights(mnb_ctx* ctx) {
   MNB_LAUNCH(k_gather_corner_w, (unsigned)((ctx->NC + 255) / 256), 256, 0, ctx->stream, ctx->d_cor_eid, ctx->d_edge_w, ctx->NC, ctx->d_cor_w);
   MNB_LAUNCH(k_gather_corner_w, (unsigned)(((size_t)ctx->V * ELL_W + 255) / 256), 256, 0, ctx->stream, ctx->d_ell_eid, ctx->d_edge_w, (size_t)ctx->V * ELL_W, ctx->d_ell_w);
   MNB_LAUNCH(k_corner_geo, (unsigned)(((size_t)ctx->V * ELL_W + 255) / 256), 256, 0, ctx->stream, ctx->d_ell_w, (size_t)ctx->V * ELL_W, ctx->d_ell_geo);
-  MNB_LAUNCH(k_gather_adj_w, (unsigned)((ctx->NA + 255) / 256), 256, 0, ctx->stream, ctx->d_adj_nbr, ctx->d_adj_eid, ctx->d_edge_w, ctx->NA, ctx->d_adj_nw);
-  MNB_LAUNCH(k_build_ell_adj, (unsigned)(((size_t)ctx->V * ELL_W + 255) / 256), 256, 0, ctx->stream, ctx->d_adj_ptr, ctx->d_adj_nw, ctx->V, ctx->d_ell_adj);
+  ctx->adj_dirty = true;        // adjacency form of the weights: only the Dijkstra planner reads it (ensure_adj_tables)
   CK(cudaGetLastError());
   // scale of the potentials: mean finite edge weight (see mnb_ctx::delta_explicit)
   if (!ctx->d_wsum) CK(dalloc(&ctx->d_wsum, 2));
@@ -363,6 +363,16 @@ static int32_t install_weights(mnb_ctx* ctx) {
     ctx->dijkstra_grid_delta = fminf(25.0f, k) * ctx->w_mean;
   }
   ctx->costs_set = true;
+  return MNB_OK;
+}
+
+// the vertex->neighbour form of the installed weights (CSR {neighbour, weight} + the 8-slot ELL rows of k_dijkstra_grid)
+static int32_t ensure_adj_tables(mnb_ctx* ctx) {
+  if (!ctx->adj_dirty) return MNB_OK;
+  MNB_LAUNCH(k_gather_adj_w, (unsigned)((ctx->NA + 255) / 256), 256, 0, ctx->stream, ctx->d_adj_nbr, ctx->d_adj_eid, ctx->d_edge_w, ctx->NA, ctx->d_adj_nw);
+  MNB_LAUNCH(k_build_ell_adj, (unsigned)(((size_t)ctx->V * ELL_W + 255) / 256), 256, 0, ctx->stream, ctx->d_adj_ptr, ctx->d_adj_nw, ctx->V, ctx->d_ell_adj);
+  CK(cudaGetLastError());
+  ctx->adj_dirty = false;
   return MNB_OK;
 }
 
@@ -722,6 +732,7 @@ static int32_t impl_dijkstra(mnb_ctx* ctx, uint32_t seed_vertex, int64_t robot_v
   if ((rc = ensure_out(ctx, (size_t)ctx->V, true)) != MNB_OK) return rc;
   if (ctx->h_cancel) *ctx->h_cancel = 0;     // dijkstra:238
   ctx->infl_labels_valid = false;
+  if ((rc = ensure_adj_tables(ctx)) != MNB_OK) return rc;
   CK(cudaMemsetAsync(ctx->ws.ctl, 0, sizeof(GroupCtl), ctx->stream));
   DijkstraKernelArgs a{};
   a.V = ctx->V; a.adj_ptr = ctx->d_adj_ptr; a.adj_nw = ctx->d_adj_nw; a.cost = ctx->d_cost;
@@ -1114,7 +1125,8 @@ static int32_t impl_update_vertex_costs(mnb_ctx* ctx, uint32_t n_changed, const 
     RefreshArgs r{};
     r.changed = d_ids; r.n = n_changed; r.V = ctx->V; r.faces = ctx->d_faces; r.cor_ptr = ctx->d_cor_ptr; r.cor_idx = ctx->d_cor_idx;
     r.cor_eid = ctx->d_cor_eid; r.adj_ptr = ctx->d_adj_ptr; r.adj_nbr = ctx->d_adj_nbr; r.adj_eid = ctx->d_adj_eid; r.w = ctx->d_edge_w;
-    r.cor_w = ctx->d_cor_w; r.ell_w = ctx->d_ell_w; r.ell_geo = ctx->d_ell_geo; r.adj_nw = ctx->d_adj_nw; r.ell_adj = ctx->d_ell_adj;
+    r.cor_w = ctx->d_cor_w; r.ell_w = ctx->d_ell_w; r.ell_geo = ctx->d_ell_geo;
+    r.adj_nw = ctx->adj_dirty ? nullptr : ctx->d_adj_nw; r.ell_adj = ctx->adj_dirty ? nullptr : ctx->d_ell_adj;   // stale tables are rebuilt whole anyway
     r.stamp = ctx->d_upd_stamp; r.call = ctx->upd_call;
     MNB_LAUNCH(k_refresh_weight_tables, blocks, 256, 0, ctx->stream, r);
     launches = 3;
