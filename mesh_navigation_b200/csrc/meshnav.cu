@@ -82,8 +82,9 @@ struct mnb_ctx {
                                // threads per CTA), 5-7 the same with the 16-bit seen-set (64 / 128 / 256), 8-9 its low-register builds.  5 M vertices on
                                // the B200: 8.4 / - / 6.9 / ... / 5.1 ms for modes 0 / 2 / 5.  Chosen per mesh by mnb_set_mesh unless fixed by the caller.
   bool layers_explicit = false;
-  int skip_clean = 0;          // clean-candidate skip of the CVP kernels (band_engine.cuh): bit-identical on the kernel interpreter,
-                               // not yet timed on a B200 -> opt-in (MNB_SKIP_CLEAN=1 / mnb_debug_set_skip_clean)
+  int skip_clean = 0;          // clean-candidate stamps of the generic 8-lane CVP loop: measured slower on the B200 (35.8 vs 31.5 ms), its kernel
+                               // instantiations are no longer built; the flag only reaches the legacy per-cluster kernel args.  The batch engine
+                               // and the inflation wave carry their own (exact) rule.
   int sweeps = -1;             // in-round sweeps of the whole-grid single-plan kernel; -1 = derived from the band width
   float grid_delta = 1.8f;     // band width of the whole-grid single-plan kernel (wide band + in-round sweeps)
   float dijkstra_grid_delta = 3.0f;
