@@ -297,6 +297,9 @@ const char* mnb_group_last_error(mnb_group* group);
 int32_t mnb_group_set_mesh(mnb_group* group, uint32_t V, uint32_t F, const float* pos, const uint32_t* faces,
                            const uint32_t* edges, uint32_t E);
 int32_t mnb_group_set_costs(mnb_group* group, const float* vertex_costs, const float* edge_weights, const uint8_t* invalid);
+/* MeshMap::layerChanged (mnb_update_vertex_costs) on every replica of the group, all devices concurrently; HOST arrays */
+int32_t mnb_group_update_vertex_costs(mnb_group* group, uint32_t n_changed, const uint32_t* changed, const float* costs,
+                                      int32_t costs_indexed_by_vertex, float default_value, double edge_cost_factor);
 /* n full-field plans, goal k on rank k mod N, all devices concurrently; with gather != 0 one in-place ncclAllGather leaves
  * every field on every device.  Result on each device: float[N][pad][V], pad = ceil(n / N), the field of goal k is row
  * mnb_group_row(group, k); the buffers belong to the group and stay valid until its next sharded call.  seed arrays: HOST.

@@ -102,6 +102,17 @@ int32_t mnb_group_set_costs(mnb_group* g, const float* vertex_costs, const float
   return group_foreach(g, [&](mnb_ctx* c, size_t) { if (c->ptr_mode != MNB_PTR_HOST) return (int32_t)MNB_E_STATE; return mnb_set_costs(c, vertex_costs, edge_weights, invalid); });
 }
 
+// MeshMap::layerChanged on every replica (mnb_update_vertex_costs per device, concurrently): keeps the maps of a group in step
+// under dynamic obstacles without re-uploading V + E floats per device.  HOST arrays.
+int32_t mnb_group_update_vertex_costs(mnb_group* g, uint32_t n_changed, const uint32_t* changed, const float* costs,
+                                      int32_t costs_indexed_by_vertex, float default_value, double edge_cost_factor) {
+  if (!g) return MNB_E_ARG;
+  return group_foreach(g, [&](mnb_ctx* c, size_t) {
+    if (c->ptr_mode != MNB_PTR_HOST) return (int32_t)MNB_E_STATE;
+    return mnb_update_vertex_costs(c, n_changed, changed, costs, costs_indexed_by_vertex, default_value, edge_cost_factor);
+  });
+}
+
 // Batched full-field CVP plans, sharded: goal k -> rank k mod N.  Every rank plans its goals (mnb_cvp_batch on its device,
 // all devices concurrently) straight into its slot of the gather buffer; one in-place ncclAllGather then leaves ALL fields
 // on EVERY device.  Layout of the per-device result (library-owned device memory, valid until the next sharded call):

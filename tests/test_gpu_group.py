@@ -49,4 +49,19 @@ def test_sharded_batch_through_the_c_abi(oracle_mod):
         for k in range(n):
             ref = om.cvp(ed, vc, int(sfs[k]), sps[k])["dist"]
             assert (out[k].view(np.uint32) == ref.view(np.uint32)).all(), (rank, k)
+    # dynamic obstacles: the change set goes to every replica (mnb_group_update_vertex_costs), the next sharded batch plans on it
+    L.mnb_group_update_vertex_costs.restype = C.c_int32
+    L.mnb_group_update_vertex_costs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_double]
+    ch = rng.choice(om.V, om.V // 6, replace=False).astype(np.uint32)
+    nv = (rng.random(ch.size) * 0.9).astype(np.float32)
+    assert L.mnb_group_update_vertex_costs(grp, ch.size, p(ch), p(nv), 0, 0.0, 1.5) == 0
+    vc2 = vc.copy(); vc2[ch] = nv
+    w2 = ed.copy(); om.update_edge_weights(vc2, ed, 1.5, ch, w2)
+    assert L.mnb_cvp_batch_sharded(grp, n, p(sfs), p(sps), 1.0, 1) == 0, L.mnb_group_last_error(grp)
+    for rank in range(ndev):
+        out = np.empty((n, om.V), np.float32)
+        assert L.mnb_group_read_fields(grp, rank, 0, n, p(out)) == 0
+        for k in range(n):
+            ref = om.cvp(w2, vc2, int(sfs[k]), sps[k])["dist"]
+            assert (out[k].view(np.uint32) == ref.view(np.uint32)).all(), ("after update", rank, k)
     L.mnb_group_destroy(grp)
