@@ -3,7 +3,7 @@
 // Same algorithm, same label format and bit-identical results as run_band_rounds_sub8 (band_engine.cuh); what differs is
 // what the hot loop carries.  The generic loop serves single plans (goal cutoff + re-queueing, in-round sweeps, the
 // clean-candidate skip, robot bookkeeping) and holds the whole problem object live: at the 64 registers a 2-CTA/SM batch
-// kernel may use it spilled -- ncu on 296 x 1M-vertex plans (profiles/r02_ncu_batch.md): 11.7 % of all executed
+// kernel may use it spilled -- ncu on 296 x 1M-vertex plans (profiles/r02_ncu_batch.md, r02a_k_cvp_batch_legacy_*): 11.7 % of all executed
 // instructions were LDL/STL, the local-memory footprint (240 MB) did not fit the L2 and local traffic was 3x the global
 // traffic, 559 warp-instructions per 4-candidate iteration at 34 % issue utilisation, everything waiting on the long
 // scoreboard.  A batch needs none of the extras:
