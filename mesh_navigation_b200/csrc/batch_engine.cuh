@@ -412,6 +412,35 @@ __device__ __forceinline__ void run_band_rounds_batch(const Args& a, const Batch
           if (changed || act_now) {
             // tell the face neighbours about the re-label (clean-candidate rule) / pull them into the candidate set (once)
             const uint32_t kb = __float_as_uint(fminf(tau, m));
+#ifndef MNB_BATCH_SERIAL_ACTIVATION
+            // The activation used to test mark[x] neighbour by neighbour inside the loop that also issues the CAS and the stage
+            // write: twelve dependent L2 round trips for the one evaluation per vertex that activates (11 % of the kernel's
+            // stall samples, profiles/r02_ncu_batch.md).  Now the marks of the whole ring are requested first (no store in
+            // that loop, so the loads overlap) and only the unmarked, eligible neighbours take the CAS.
+            uint32_t todo = 0u;
+            if (act_now) {
+#pragma unroll
+              for (int k = 0; k < (int)ELL_W; ++k) {
+                const int4 ix = __ldg(&a.ell_idx[(size_t)c * ELL_W + k]);
+                if (ix.x == ELL_EMPTY) continue;
+                if (__ldcg(&G.mark[(uint32_t)ix.x]) == MARK_NONE) todo |= 1u << (2 * k);
+                if (__ldcg(&G.mark[(uint32_t)ix.y]) == MARK_NONE) todo |= 2u << (2 * k);
+              }
+            }
+            for (int k = 0; k < (int)ELL_W; ++k) {
+              const int4 ix = __ldg(&a.ell_idx[(size_t)c * ELL_W + k]);
+              if (ix.x == ELL_EMPTY) continue;
+              const uint32_t xs[2] = {(uint32_t)ix.x, (uint32_t)ix.y};
+#pragma unroll
+              for (int t = 0; t < 2; ++t) {
+                const uint32_t x = xs[t];
+                if (changed) atomicMin(&skw[4 * (size_t)x + buf_now], kb);
+                if (((todo >> (2 * k + t)) & 1u) && !(a.invalid && a.invalid[x]) && !((double)__ldg(&a.cost[x]) >= a.cost_limit) &&
+                    atomicCAS(&G.mark[x], MARK_NONE, MARK_CAND) == MARK_NONE)
+                  batch_stage_write(st, atomicAdd(&st.n, 1u), x, list_n, count_next);
+              }
+            }
+#else
             for (int k = 0; k < (int)ELL_W; ++k) {
               const int4 ix = __ldg(&a.ell_idx[(size_t)c * ELL_W + k]);
               if (ix.x == ELL_EMPTY) continue;
@@ -425,6 +454,7 @@ __device__ __forceinline__ void run_band_rounds_batch(const Args& a, const Batch
                   batch_stage_write(st, atomicAdd(&st.n, 1u), x, list_n, count_next);
               }
             }
+#endif
           }
         }
         const unsigned dm = __ballot_sync(FULL, done), fm = __ballot_sync(FULL, has && defer);
