@@ -48,7 +48,7 @@ __global__ void k_update_edge_weights(const uint32_t* __restrict__ changed, uint
 struct RefreshArgs {
   const uint32_t* changed; uint32_t n, V;
   const uint32_t* faces;
-  const uint32_t* cor_ptr; const int4* cor_idx; const uint4* cor_eid;
+  const uint32_t* cor_ptr; const int4* cor_idx; const uint4* cor_eid; const uint32_t* face_cor;
   const uint32_t* adj_ptr; const uint32_t* adj_nbr; const uint32_t* adj_eid;
   const float* w;
   float4* cor_w; float4* ell_w; double4* ell_geo; uint2* adj_nw; uint4* ell_adj;
@@ -67,21 +67,17 @@ __global__ void k_refresh_weight_tables(const RefreshArgs a) {
     const int4 ci = a.cor_idx[k];
     const uint32_t f = (uint32_t)ci.z;
     if (((uint32_t)ci.x < v && a.stamp[(uint32_t)ci.x] == a.call) || ((uint32_t)ci.y < v && a.stamp[(uint32_t)ci.y] == a.call)) continue;
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < 3; ++c) {                      // the three corner records of the face, through the face -> corner table
       const uint32_t x = a.faces[3 * (size_t)f + c];
-      const uint32_t kb = a.cor_ptr[x], ke = a.cor_ptr[x + 1];
-      for (uint32_t kk = kb; kk < ke; ++kk) {
-        if ((uint32_t)a.cor_idx[kk].z != f) continue;
-        const uint4 e = a.cor_eid[kk];
-        const float4 ww = make_float4(a.w[e.x], a.w[e.y], a.w[e.z], 0.0f);
-        a.cor_w[kk] = ww;
-        if (kk - kb < ELL_W) {
-          const size_t s = (size_t)x * ELL_W + (kk - kb);
-          a.ell_w[s] = ww;
-          const CvpEllProblem::FaceGeo g = CvpEllProblem::face_geo((double)ww.z, (double)ww.y, (double)ww.x);
-          a.ell_geo[s] = make_double4(g.p, g.hc, g.t0a, 0.0);
-        }
-        break;
+      const uint32_t kk = a.face_cor[3 * (size_t)f + c], kb = a.cor_ptr[x];
+      const uint4 e = a.cor_eid[kk];
+      const float4 ww = make_float4(a.w[e.x], a.w[e.y], a.w[e.z], 0.0f);
+      a.cor_w[kk] = ww;
+      if (kk - kb < ELL_W) {
+        const size_t s = (size_t)x * ELL_W + (kk - kb);
+        a.ell_w[s] = ww;
+        const CvpEllProblem::FaceGeo g = CvpEllProblem::face_geo((double)ww.z, (double)ww.y, (double)ww.x);
+        a.ell_geo[s] = make_double4(g.p, g.hc, g.t0a, 0.0);
       }
     }
   }

@@ -31,6 +31,7 @@ struct HostTopology {
   std::vector<uint32_t> face_edges;  // 3F: edge(v0,v1), edge(v1,v2), edge(v2,v0)
   std::vector<uint32_t> vadj_ptr, vadj_nbr, vadj_eid;
   std::vector<uint32_t> vcor_ptr, cor_v1, cor_v2, cor_face, cor_ec, cor_eb, cor_ea;
+  std::vector<uint32_t> face_cor;    // 3F: index of the corner record of face f at its k-th vertex (the way back from a face to its three records)
   std::vector<uint8_t> cor_side;     // per corner record, bit i = this face is NOT the lowest-id face of edge i (0: ec, 1: eb, 2: ea),
                                      // i.e. the second face pmp lists for the halfedge pair (inflation_layer.cpp:427)
   std::vector<uint8_t> border;       // 1 = vertex lies on an edge with a single face
@@ -168,6 +169,7 @@ struct HostTopology {
     const size_t NC = vcor_ptr[V];
     cor_v1.resize(NC); cor_v2.resize(NC); cor_face.resize(NC);
     cor_ec.resize(NC); cor_eb.resize(NC); cor_ea.resize(NC); cor_side.resize(NC);
+    face_cor.resize(3 * (size_t)F);
     {
       // every thread owns a range of vertices and scans all faces: the records of a vertex stay in ascending face order
       std::vector<uint32_t> cur(vcor_ptr.begin(), vcor_ptr.end() - 1);
@@ -183,6 +185,7 @@ struct HostTopology {
           cor_v1[slot] = v[(k + 1) % 3];
           cor_v2[slot] = v[(k + 2) % 3];
           cor_face[slot] = f;
+          face_cor[3 * (size_t)f + k] = slot;
           cor_ec[slot] = fe[(k + 1) % 3];  // edge(v1,v2)
           cor_eb[slot] = fe[k];            // edge(v3,v1)
           cor_ea[slot] = fe[(k + 2) % 3];  // edge(v2,v3)
